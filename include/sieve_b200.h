@@ -1,0 +1,196 @@
+/*
+ * sieve_b200.h -- C-ABI of the B200-native tree-likelihood core for SIEVE.
+ *
+ * This is the drop-in boundary: the entry points are what a JNI shim behind SIEVE's
+ * `LikelihoodCore` / `RawReadCountsModel` seam binds (see INTEGRATION.md for the Java side).  Every function
+ * cites the reference interface it replaces; paths are relative to /root/reference/src/beast/.
+ *
+ * Conventions
+ *   - every function returns an int status (SIEVE_OK == 0); no exception crosses the boundary;
+ *     sieve_last_error() gives the text of the last failure on the calling thread.
+ *   - the caller owns all host arrays; the callee has consumed them when the call returns.
+ *   - one handle <=> one GPU <=> one contiguous site shard (the analogue of one worker of
+ *     likelihood/ThreadedScsTreeLikelihood.java:176-219).  Calls on one handle are serialised by the caller;
+ *     different handles may be driven from different host threads.
+ *   - node numbering is the reference's: leaves 0..n-1, internal nodes n..2n-2, unary root 2n-1
+ *     (tree/ScsTree.java:220-260).  Matrices are row = parent state, column = child state
+ *     (likelihood/ScsBeerLikelihoodCore.java:107-108).  Genotype states: 0/0, 0/1, 1/1, 1/1'
+ *     (substitutionmodel/ScsFiniteMuExtendedModel.java:62-66).
+ *   - NaN / -inf results are returned faithfully in the outputs (e.g. eff_seq_err == 0 with alt reads);
+ *     CUDA failures are status codes.
+ *   - there is no CPU fallback: every compute entry point fails with SIEVE_ERR_CUDA when no device is usable.
+ */
+#ifndef SIEVE_B200_H
+#define SIEVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sieve_core sieve_core_t;
+
+enum {
+    SIEVE_OK = 0,
+    SIEVE_ERR_INVALID = 1, /* bad argument */
+    SIEVE_ERR_CUDA = 2,    /* CUDA runtime failure (incl. no device) */
+    SIEVE_ERR_OOM = 3,     /* the requested residency does not fit the device */
+    SIEVE_ERR_STATE = 4    /* call sequence error (e.g. compute before counts were set) */
+};
+
+/* sieve_config_t.flags */
+#define SIEVE_FLAG_LOG_PARTIALS 1u   /* useLogPartials == true semantics (likelihood/ScsTreeLikelihood.java:297-300):      \
+                                        transition probabilities are clamped to Double.MIN_VALUE as                        \
+                                        ScsBeerLikelihoodCore.java:1430 does, and sieve_get_node_partials returns logs */
+#define SIEVE_FLAG_CONST_PARTIALS 2u /* maintain the constant-site partials (acquisition-bias correction on) */
+#define SIEVE_FLAG_SINGLE_ADO 4u     /* singleADO == true (rawreadcountsmodel/RawReadCountsModelInterface.java:178-181) */
+#define SIEVE_FLAG_EPHEMERAL 8u      /* do not keep internal partials resident: every update is a streamed full-tree    \
+                                        evaluation (needed when 2 * n * S * 136 B exceeds HBM) */
+
+typedef struct {
+    int32_t n_leaves;     /* cells (taxa) */
+    int32_t n_sites;      /* patterns of this shard */
+    int32_t n_categories; /* K, site-rate categories == matrixCount (1..4) */
+    int32_t n_states;     /* must be 4 */
+    uint32_t flags;
+    int32_t device; /* CUDA ordinal; -1 = current device */
+} sieve_config_t;
+
+/* The six RealParameter inputs of the raw-read-counts model:
+ * rawreadcountsmodel/RawReadCountsModelInterface.java:44-48 (adoRate),
+ * seqcovmodel/SeqCovModelInterface.java:30-67 (allelicSeqCov, allelicSeqCovRawVar),
+ * nucreadcountsmodel/NucReadCountsModelInterface.java:18-34 (effSeqErrRate, shapeCtrl1, shapeCtrl2). */
+typedef struct {
+    double ado_rate;
+    double allelic_seq_cov;
+    double allelic_seq_cov_raw_var;
+    double eff_seq_err_rate;
+    double shape_ctrl1;
+    double shape_ctrl2;
+} sieve_leaf_params_t;
+
+/* acquisition-bias modes, alignment/ScsAlignment.java:93-113 (ascertained, meanAscBiasCorrection) */
+enum { SIEVE_ASC_NONE = 0, SIEVE_ASC_FELSENSTEIN_MEAN = 1, SIEVE_ASC_FELSENSTEIN_GEOMETRIC = 2, SIEVE_ASC_LEWIS = 3 };
+
+/* What one shard reports per evaluation (the two doubles a worker returns,
+ * likelihood/ThreadedScsTreeLikelihood.java:466-471, plus the sums the other bias modes need). */
+typedef struct {
+    double sum_log_l;     /* sum_s w_s * logL_s                      (likelihood/ScsTreeLikelihood.java:2625-2629) */
+    double const_lse;     /* log sum_s w_s * exp(logConst_s)         (alignment/ScsAlignment.java:768-769) */
+    double const_sum;     /* sum_s w_s * logConst_s                  (alignment/ScsAlignment.java:773-774) */
+    double lewis_sum;     /* -sum_s w_s * log(1 - exp(logConst_s))   (alignment/ScsAlignment.java:746-752) */
+    double weight_sum;    /* sum_s w_s (loci of this shard) */
+} sieve_shard_result_t;
+
+const char *sieve_last_error(void);
+int sieve_version(void);
+/* number of usable CUDA devices (0 when none); never fails */
+int sieve_device_count(void);
+
+/* ScsBeerLikelihoodCore.initialize (likelihood/ScsBeerLikelihoodCore.java:91-128) + createNodePartials (:134-143):
+ * allocates the device pools.  Fails with SIEVE_ERR_OOM when the residency does not fit. */
+int sieve_create(const sieve_config_t *cfg, sieve_core_t **out);
+/* ScsBeerLikelihoodCore.finalize (:399-409) */
+int sieve_destroy(sieve_core_t *h);
+/* bytes of device memory held by the handle */
+int sieve_device_bytes(sieve_core_t *h, uint64_t *out);
+
+/* The read-count tensor: ScsAlignment.sitePatterns / getPattern (alignment/ScsAlignment.java:188, 400-446).
+ * counts is int32 [site][cell][tuple_len], tuple_len 4 = (alt1, alt2, alt3, cov) or 5 = the reference's
+ * (alt1, alt2, alt3, ref, cov) of datatype/FullSupsCov.java:74-77. */
+int sieve_set_counts(sieve_core_t *h, const int32_t *counts, int32_t tuple_len);
+/* as above but the tensor already lives on the device in the core's own layout int32 [cell][site][4] */
+int sieve_set_counts_device(sieve_core_t *h, const void *d_counts_cell_site_4);
+/* ScsAlignment.getPatternWeight (likelihood/ScsTreeLikelihood.java:2626); NULL = all 1 */
+int sieve_set_pattern_weights(sieve_core_t *h, const int32_t *weights);
+
+/* SeqCovModelInterface.Base.computeSizeFactors (seqcovmodel/SeqCovModelInterface.java:291-351) over THIS handle's sites
+ * (use it on an unsharded handle, or compute once and hand the result to every shard, as
+ * likelihood/ThreadedScsTreeLikelihood.java:119-131 + ExploredSharedAllelicSeqCovModel.java:103-109 do).
+ * out_size_factors[n_leaves]; out_stats[2] = {mean(cov)/2, var(cov)/4} (the start values of :322-325), may be NULL. */
+int sieve_compute_size_factors(sieve_core_t *h, int32_t zero_cov_mode, double *out_size_factors, double *out_stats);
+int sieve_set_size_factors(sieve_core_t *h, const double *size_factors);
+
+/* new values of the six leaf-model parameters; takes effect at the next sieve_update_leaves */
+int sieve_set_leaf_params(sieve_core_t *h, const sieve_leaf_params_t *p);
+/* rawReadCountsModel.computeLeafLikelihood + core.setNodePartials for every leaf
+ * (likelihood/ScsTreeLikelihood.java:583-601, rawreadcountsmodel/RawReadCountsModelInterface.java:458-506).
+ * for_update != 0 first flips the leaves' write buffer (setNodePartialsForUpdate, :586);
+ * for_update == 0 is the initialisation path (initializeLeafLikelihood + storeLeafPartials, :430-468). */
+int sieve_update_leaves(sieve_core_t *h, int32_t for_update);
+
+/* BeerLikelihoodCore.setNodeMatrixForUpdate / setNodeMatrix (external; call sites likelihood/ScsTreeLikelihood.java:566-578) */
+int sieve_set_node_matrix_for_update(sieve_core_t *h, int32_t node);
+int sieve_set_node_matrix(sieve_core_t *h, int32_t node, int32_t category, const double *p16);
+/* batched form: for every listed node (flip if for_update) all K matrices, P is [count][K][16] */
+int sieve_set_matrices(sieve_core_t *h, int32_t count, const int32_t *nodes, const double *P, int32_t for_update);
+
+/* BeerLikelihoodCore.setNodePartialsForUpdate (external; call site ScsTreeLikelihood.java:2951-2956) */
+int sieve_set_node_partials_for_update(sieve_core_t *h, int32_t node);
+/* ScsBeerLikelihoodCore.calculateLogPartials / calculatePartials (:1283-1369 / :857-943).  child2 == -1 <=> unary root.
+ * The op is queued; queued ops are launched together (one kernel) by the next call that needs their result. */
+int sieve_calculate_partials(sieve_core_t *h, int32_t child1, int32_t is_leaf1, int32_t child2, int32_t is_leaf2,
+                             int32_t parent, int32_t const_genotype);
+/* batched form of the two calls above: ops is [n_ops][3] = (parent, child1, child2 | -1) in post-order
+ * (children before parents).  level_offsets (n_levels + 1 entries, may be NULL) marks groups of mutually
+ * independent ops; with it and SIEVE_UPDATE_PER_LEVEL the update is issued as one launch per tree level. */
+#define SIEVE_UPDATE_FLIP 1u      /* setNodePartialsForUpdate on every parent first */
+#define SIEVE_UPDATE_PER_LEVEL 2u /* one launch per level instead of one launch per update */
+int sieve_update_nodes(sieve_core_t *h, int32_t n_ops, const int32_t *ops, const int32_t *level_offsets,
+                       int32_t n_levels, uint32_t mode);
+
+/* which node is the root and how categories are integrated there:
+ * integratePartials(root, proportions, rootGenotype, ...) (:153-218) + calculateLogLikelihoods (:255-269).
+ * The integration itself runs as the epilogue of the root's op. */
+int sieve_set_root(sieve_core_t *h, int32_t root, const double *proportions, int32_t root_genotype);
+/* launches everything queued, then the per-site log + reduction; fills *out (ScsTreeLikelihood.calcLogP, :2621-2651) */
+int sieve_evaluate(sieve_core_t *h, sieve_shard_result_t *out);
+
+/* One MCMC-step call: matrices of the changed nodes, the dirty ops, and the result, with one host->device copy,
+ * one device->host copy.  Equivalent to sieve_set_matrices(for_update) + sieve_update_nodes(FLIP) + sieve_evaluate.
+ * update_leaves != 0 runs sieve_update_leaves(for_update) first (parameters set by sieve_set_leaf_params). */
+int sieve_step(sieve_core_t *h, int32_t update_leaves, int32_t n_matrices, const int32_t *matrix_nodes, const double *P,
+               int32_t n_ops, const int32_t *ops, sieve_shard_result_t *out);
+
+/* Re-launches, n_times, exactly the kernels of the last sieve_step / sieve_evaluate from what is already staged in HBM
+ * (matrices, ops): no host<->device copy and no synchronisation.  update_leaves != 0 also rebuilds the tables and the
+ * leaf partials each time.  Used to time the device path in isolation; results are read with sieve_evaluate-style
+ * getters after the caller synchronises the handle's stream. */
+int sieve_replay(sieve_core_t *h, int32_t update_leaves, int32_t n_times);
+
+/* getPatternLogLikelihoods (likelihood/ScsTreeLikelihood.java:2958-2970); out_const may be NULL */
+int sieve_get_site_log_likelihoods(sieve_core_t *h, double *out_site_log_l, double *out_site_log_const);
+/* device pointers to the same two arrays (valid until destroy), for callers that combine shards on the device */
+int sieve_get_result_device_ptr(sieve_core_t *h, void **d_result /* sieve_shard_result_t */);
+
+/* BeerLikelihoodCore.getNodePartials in the reference layout [K][S][G] (:1417-1499 index order), logs when
+ * SIEVE_FLAG_LOG_PARTIALS.  which: 0 = partials, 1 = constant-site partials (internal nodes only). */
+int sieve_get_node_partials(sieve_core_t *h, int32_t node, int32_t which, double *out);
+
+/* ScsBeerLikelihoodCore.store / unstore (:4053-4065), BeerLikelihoodCore.restore (external) -- index flips only */
+int sieve_store(sieve_core_t *h);
+int sieve_unstore(sieve_core_t *h);
+int sieve_restore(sieve_core_t *h);
+
+/* ThreadedScsTreeLikelihood.calculateLogPByBeagle (likelihood/ThreadedScsTreeLikelihood.java:366-389) with
+ * ScsAlignment.getAscBiasCorrection (alignment/ScsAlignment.java:764-782 for one shard, :811-820 for several):
+ * logP = sum_r a_r + bias(asc_mode, b_r, M).  Pure host arithmetic on n_shards small structs. */
+double sieve_combine_shards(const sieve_shard_result_t *shards, int32_t n_shards, int32_t asc_mode,
+                            double n_background_sites);
+/* calcPatternPoints (likelihood/ThreadedScsTreeLikelihood.java:227-238): points[n_shards + 1] */
+void sieve_pattern_points(int32_t n_sites, int32_t n_shards, int32_t *points);
+
+/* kernel-time breakdown of the last sieve_evaluate / sieve_step in milliseconds (CUDA events on the handle's stream):
+ * out[0] leaf tables+kernel, out[1] pruning launches, out[2] reduce, out[3] total; and how many kernels were launched. */
+int sieve_last_timing(sieve_core_t *h, float *out_ms4, int32_t *out_launches);
+int sieve_enable_timing(sieve_core_t *h, int32_t on);
+/* total number of kernels this handle has launched so far */
+int sieve_launch_count(sieve_core_t *h, uint64_t *out);
+/* the CUDA stream the handle launches on (cudaStream_t) */
+int sieve_get_stream(sieve_core_t *h, void **out_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIEVE_B200_H */

@@ -1,0 +1,206 @@
+"""`ScsCudaLikelihoodCore` -- the device-backed stand-in for SIEVE's likelihood core plus leaf model.
+
+Method names and argument meaning follow the reference's `ScsBeerLikelihoodCore` / `LikelihoodCore`
+(likelihood/ScsBeerLikelihoodCore.java; the calls `ScsTreeLikelihood.traverse` makes, likelihood/ScsTreeLikelihood.java:545-935)
+so that a test written against the reference reads the same here.  Everything is a thin call into the C-ABI of
+include/sieve_b200.h; no arithmetic of the hot path happens in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (ASC_MODES, FLAG_CONST_PARTIALS, FLAG_LOG_PARTIALS, FLAG_SINGLE_ADO, UPDATE_FLIP, UPDATE_PER_LEVEL,
+                   LeafParams, ShardResult, check)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class ScsCudaLikelihoodCore:
+    def __init__(self, n_leaves, n_sites, n_categories=4, n_states=4, use_log_partials=True, asc_bias=False,
+                 single_ado=True, device=-1):
+        """initialize(nodeCount = 2n, leafCount = n, internalCount = n, patternCount, matrixCount, stateCount, ...)
+        (likelihood/ScsBeerLikelihoodCore.java:91-128)."""
+        self.L = _lib.lib()
+        self.n, self.S, self.K, self.G = int(n_leaves), int(n_sites), int(n_categories), int(n_states)
+        self.n_nodes = 2 * self.n
+        self.use_log = bool(use_log_partials)
+        self.asc_bias = bool(asc_bias)
+        flags = (FLAG_LOG_PARTIALS if use_log_partials else 0) | (FLAG_CONST_PARTIALS if asc_bias else 0) | \
+                (FLAG_SINGLE_ADO if single_ado else 0)
+        cfg = _lib.Config(self.n, self.S, self.K, self.G, flags, device)
+        h = C.c_void_p()
+        check(self.L.sieve_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sieve_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data ----------------------------------------------------------------------------------------------
+    def set_counts(self, counts):
+        """int32 [site][cell][4 | 5] as the alignment holds it (alignment/ScsAlignment.java:188)."""
+        c = np.ascontiguousarray(counts, dtype=np.int32)
+        assert c.shape[:2] == (self.S, self.n) and c.shape[2] in (4, 5), c.shape
+        check(self.L.sieve_set_counts(self.h, _iptr(c), c.shape[2]))
+
+    def set_counts_device(self, device_ptr):
+        check(self.L.sieve_set_counts_device(self.h, C.c_void_p(int(device_ptr))))
+
+    def set_pattern_weights(self, weights):
+        if weights is None:
+            check(self.L.sieve_set_pattern_weights(self.h, None))
+            return
+        w = np.ascontiguousarray(weights, dtype=np.int32)
+        assert w.shape == (self.S,)
+        check(self.L.sieve_set_pattern_weights(self.h, _iptr(w)))
+
+    def compute_size_factors(self, zero_cov_mode=0):
+        sf = np.empty(self.n)
+        st = np.empty(2)
+        check(self.L.sieve_compute_size_factors(self.h, zero_cov_mode, _dptr(sf), _dptr(st)))
+        return sf, st
+
+    def set_size_factors(self, sf):
+        a = np.ascontiguousarray(sf, dtype=np.float64)
+        assert a.shape == (self.n,)
+        check(self.L.sieve_set_size_factors(self.h, _dptr(a)))
+
+    # ---- leaves --------------------------------------------------------------------------------------------
+    def set_leaf_params(self, theta, t, v, eps, w1, w2):
+        p = LeafParams(theta, t, v, eps, w1, w2)
+        check(self.L.sieve_set_leaf_params(self.h, C.byref(p)))
+
+    def update_leaves(self, for_update=True):
+        check(self.L.sieve_update_leaves(self.h, int(bool(for_update))))
+
+    # ---- matrices ------------------------------------------------------------------------------------------
+    def set_node_matrix_for_update(self, node):
+        check(self.L.sieve_set_node_matrix_for_update(self.h, int(node)))
+
+    def set_node_matrix(self, node, category, matrix):
+        m = np.ascontiguousarray(matrix, dtype=np.float64).reshape(-1)
+        assert m.size == 16
+        check(self.L.sieve_set_node_matrix(self.h, int(node), int(category), _dptr(m)))
+
+    def set_matrices(self, nodes, P, for_update=True):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        m = np.ascontiguousarray(P, dtype=np.float64)
+        assert m.size == nd.size * self.K * 16
+        check(self.L.sieve_set_matrices(self.h, nd.size, _iptr(nd), _dptr(m), int(bool(for_update))))
+
+    # ---- partials ------------------------------------------------------------------------------------------
+    def set_node_partials_for_update(self, node):
+        check(self.L.sieve_set_node_partials_for_update(self.h, int(node)))
+
+    def calculate_partials(self, child1, is_leaf1, child2, is_leaf2, parent, const_genotype=0):
+        """calculateLogPartials / calculatePartials (queued; launched with the next evaluate)."""
+        check(self.L.sieve_calculate_partials(self.h, int(child1), int(bool(is_leaf1)), int(child2), int(bool(is_leaf2)),
+                                              int(parent), int(const_genotype)))
+
+    calculate_log_partials = calculate_partials
+
+    def update_nodes(self, ops, level_offsets=None, flip=True, per_level=False):
+        o = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 3)
+        mode = (UPDATE_FLIP if flip else 0) | (UPDATE_PER_LEVEL if per_level else 0)
+        lo, nl = None, 0
+        if level_offsets is not None:
+            lo_a = np.ascontiguousarray(level_offsets, dtype=np.int32)
+            lo, nl = _iptr(lo_a), lo_a.size - 1
+        check(self.L.sieve_update_nodes(self.h, o.shape[0], _iptr(o), lo, nl, mode))
+
+    def set_root(self, root, proportions, root_genotype=0):
+        p = np.zeros(4)
+        p[:self.K] = np.asarray(proportions, dtype=np.float64)[:self.K]
+        check(self.L.sieve_set_root(self.h, int(root), _dptr(p), int(root_genotype)))
+
+    def evaluate(self):
+        r = ShardResult()
+        check(self.L.sieve_evaluate(self.h, C.byref(r)))
+        return r
+
+    def step(self, matrix_nodes, P, ops, update_leaves=False):
+        nd = np.ascontiguousarray(matrix_nodes, dtype=np.int32)
+        m = np.ascontiguousarray(P, dtype=np.float64)
+        o = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 3)
+        r = ShardResult()
+        check(self.L.sieve_step(self.h, int(bool(update_leaves)), nd.size, _iptr(nd), _dptr(m), o.shape[0], _iptr(o),
+                                C.byref(r)))
+        return r
+
+    def replay(self, update_leaves=False, n_times=1):
+        """Re-launch the last step's kernels from what is staged in HBM (asynchronous, no copies)."""
+        check(self.L.sieve_replay(self.h, int(bool(update_leaves)), int(n_times)))
+
+    def site_log_likelihoods(self):
+        """getPatternLogLikelihoods + logConstRoot (likelihood/ScsTreeLikelihood.java:2958-2970, 915-920)."""
+        a = np.empty(self.S)
+        b = np.empty(self.S)
+        check(self.L.sieve_get_site_log_likelihoods(self.h, _dptr(a), _dptr(b)))
+        return a, b
+
+    def get_node_partials(self, node, const=False):
+        out = np.empty((self.K, self.S, self.G))
+        check(self.L.sieve_get_node_partials(self.h, int(node), int(bool(const)), _dptr(out)))
+        return out
+
+    def store(self):
+        check(self.L.sieve_store(self.h))
+
+    def unstore(self):
+        check(self.L.sieve_unstore(self.h))
+
+    def restore(self):
+        check(self.L.sieve_restore(self.h))
+
+    # ---- instrumentation -------------------------------------------------------------------------------------
+    def enable_timing(self, on=True):
+        check(self.L.sieve_enable_timing(self.h, int(on)))
+
+    def last_timing(self):
+        ms = (C.c_float * 4)()
+        n = C.c_int32()
+        check(self.L.sieve_last_timing(self.h, ms, C.byref(n)))
+        return dict(leaf_ms=ms[0], prune_ms=ms[1], reduce_ms=ms[2], total_ms=ms[3], launches=n.value)
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(self.L.sieve_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def device_bytes(self):
+        n = C.c_uint64()
+        check(self.L.sieve_device_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def stream(self):
+        p = C.c_void_p()
+        check(self.L.sieve_get_stream(self.h, C.byref(p)))
+        return p.value
+
+
+def combine_shards(results, asc_mode="none", n_background_sites=0.0):
+    """ThreadedScsTreeLikelihood.calculateLogPByBeagle (likelihood/ThreadedScsTreeLikelihood.java:366-389)."""
+    arr = (ShardResult * len(results))(*results)
+    m = ASC_MODES[asc_mode] if isinstance(asc_mode, str) else int(asc_mode)
+    return _lib.lib().sieve_combine_shards(arr, len(results), m, float(n_background_sites))
+
+
+def pattern_points(n_sites, n_shards):
+    pts = np.zeros(n_shards + 1, dtype=np.int32)
+    _lib.lib().sieve_pattern_points(int(n_sites), int(n_shards), _iptr(pts))
+    return pts

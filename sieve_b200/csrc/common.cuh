@@ -1,0 +1,56 @@
+// common.cuh -- small device helpers shared by the kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SV_MIN_VALUE 4.9406564584124654e-324  // java.lang.Double.MIN_VALUE
+#define SV_LN2 0.6931471805599453094
+#define SV_G 4                                 // genotype states (ScsFiniteMuExtendedModel.java:31-34)
+#define SV_KMAX 4                              // site-rate categories handled per site by 4 adjacent lanes
+#define SV_MAT_STRIDE 18                       // doubles between the K matrices in shared memory (bank padding)
+
+// One post-order step of the pruning: parent <- (child1, child2).  Slots index the device pools.
+struct SvOp {
+    int dst;    // internal slot (buffer * n_internal + internal index) of the parent
+    int c1;     // child 1: leaf slot (buffer * n_leaves + leaf) or internal slot
+    int c2;     // child 2, unused for a unary op
+    int m1;     // matrix slot (buffer * n_nodes + node) of child 1
+    int m2;     // matrix slot of child 2
+    int flags;  // SV_OP_*
+    int pad0, pad1;
+};
+#define SV_OP_LEAF1 1
+#define SV_OP_LEAF2 2
+#define SV_OP_UNARY 4
+#define SV_OP_ROOT 8
+
+// 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one (site, category) state vector.
+__device__ __forceinline__ void sv_ld256(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+// read-only variant for data that no kernel in flight writes (leaf partials during pruning, counts)
+__device__ __forceinline__ void sv_ld256_nc(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void sv_st256(double* p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+__device__ __forceinline__ double sv_max4(const double (&v)[4]) { return fmax(fmax(v[0], v[1]), fmax(v[2], v[3])); }
+
+// Exact power-of-two renormalisation: returns factor = 2^-e and *shift_ln = e * ln 2 with e = floor(log2 mx),
+// so that mx * factor is in [1, 2).  Zero / non-finite maxima are left alone.
+__device__ __forceinline__ double sv_pow2_rescale(double mx, double* shift_ln) {
+    const int hi = __double2hiint(mx);
+    const int e = (hi >> 20) & 0x7ff;
+    if (hi > 0 && e >= 1 && e <= 2045) {
+        *shift_ln = (double)(e - 1023) * SV_LN2;
+        return __hiloint2double((2046 - e) << 20, 0);
+    }
+    if (mx > 0.0 && e == 0) {  // subnormal maximum (only reachable through the Double.MIN_VALUE clamps)
+        *shift_ln = -1022.0 * SV_LN2;
+        return __hiloint2double(2045 << 20, 0);  // 2^1022
+    }
+    *shift_ln = 0.0;
+    return 1.0;
+}

@@ -1,0 +1,285 @@
+// leaf.cuh -- leaf genotype likelihoods from the read-count tensor.
+//
+// Replaces RawReadCountsModelInterface.Base.computeLeafLikelihood (rawreadcountsmodel/RawReadCountsModelInterface.java:458-506)
+// with its callees NucReadCountsModelFiniteMuDM.computeNucReadCountsLikelihoods (nucreadcountsmodel/...DM.java:33-96),
+// ExploredSharedAllelicSeqCovModel.computeSeqCovLikelihoodPerAllele (seqcovmodel/...java:266-277) and
+// RawReadCountsModelFiniteMuDM.computeMixedLikelihoodCore (rawreadcountsmodel/RawReadCountsModelFiniteMuDM.java:121-260).
+//
+// Every logGamma argument of the reference is (alpha + c), c, (r + x) or (x + 1) with INTEGER c, x, only six distinct
+// alpha per parameter set and one (r, p) per (cell, allele count).  So per parameter proposal two small tables are built
+// on the device with the reference's own arithmetic (Lanczos logGamma, same operation order):
+//   dmA[c] = { LP(c, f*w1), LP(c, (1-eps)*w1), LP(c, (1/2-f)*w2), LP(c, f*w2) },  dmB[c] = { LP(c, w1), LP(c, w2) }
+//       with LP(c, a) = c <= 0 ? 0 : log c + logBeta(a, c)   (math/distributions/DirichletMultinomial.java:48-50)
+//   cell[j][x] = the allelic-dropout mixture weights of the two (three) negative-binomial coverage terms at coverage x
+// and the per-(cell, site) work becomes 4 table sums + 4 exp: HBM-bound instead of lgamma-bound.
+// Counts beyond the table are evaluated directly (same formulas), so any input is handled.
+//
+// Output per (cell, site): 4 linear genotype likelihoods, jointly scaled, plus the natural-log scale:
+//   true likelihood_g = x[g] * exp(lscale)
+#pragma once
+#include "common.cuh"
+
+// ---- commons-math 2.x Gamma.logGamma, restated (external to the reference; see oracle/sieve_oracle.c header) ----
+__device__ __forceinline__ double sv_log_gamma(double x) {
+    if (!(x > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+    const double L[15] = {0.99999999999999709182,     57.156235665862923517,      -59.597960355475491248,
+                          14.136097974741747174,      -0.49191381609762019978,    .33994649984811888699e-4,
+                          .46523628927048575665e-4,   -.98374475304879564677e-4,  .15808870322491248884e-3,
+                          -.21026444172410488319e-3,  .21743961811521264320e-3,   -.16431810653676389022e-3,
+                          .84418223983852743293e-4,   -.26190838401581408670e-4,  .36899182659531622704e-5};
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 14; i > 0; --i) sum = __dadd_rn(sum, __ddiv_rn(L[i], __dadd_rn(x, (double)i)));
+    sum = __dadd_rn(sum, L[0]);
+    const double tmp = __dadd_rn(__dadd_rn(x, 607.0 / 128.0), .5);
+    // ((x + .5) * log(tmp)) - tmp + HALF_LOG_2_PI + log(sum / x), left to right, no contraction
+    double r = __dmul_rn(__dadd_rn(x, .5), log(tmp));
+    r = __dadd_rn(r, -tmp);
+    r = __dadd_rn(r, 0.91893853320467274178);
+    r = __dadd_rn(r, log(__ddiv_rn(sum, x)));
+    return r;
+}
+
+// LP(c, a) of DirichletMultinomial.logPartial
+__device__ __forceinline__ double sv_dm_log_partial(int c, double a) {
+    if (c <= 0) return 0.0;
+    const double cd = (double)c;
+    if (!(a > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);  // logBeta is NaN for a <= 0
+    const double lb = __dadd_rn(__dadd_rn(sv_log_gamma(a), sv_log_gamma(cd)), -sv_log_gamma(__dadd_rn(a, cd)));
+    return __dadd_rn(log(cd), lb);
+}
+
+struct SvDmAlphas {
+    double fw1, omw1, hw2, fw2, w1, w2;
+};
+
+// NucReadCountsModelFiniteMuDM.java:40-51
+__host__ __device__ inline SvDmAlphas sv_dm_alphas(double eps, double w1, double w2) {
+    SvDmAlphas a;
+    const double oneThird = eps / 3;
+    const double oneMinus = 1 - eps;
+    const double halfMinus = 0.5 - eps / 3;
+    a.fw1 = oneThird * w1;
+    a.omw1 = oneMinus * w1;
+    a.fw2 = oneThird * w2;
+    a.hw2 = halfMinus * w2;
+    a.w1 = w1;
+    a.w2 = w2;
+    return a;
+}
+
+__global__ void k_build_dm_tables(double* __restrict__ dmA, double* __restrict__ dmB, int C, SvDmAlphas al) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    dmA[4 * c + 0] = sv_dm_log_partial(c, al.fw1);
+    dmA[4 * c + 1] = sv_dm_log_partial(c, al.omw1);
+    dmA[4 * c + 2] = sv_dm_log_partial(c, al.hw2);
+    dmA[4 * c + 3] = sv_dm_log_partial(c, al.fw2);
+    dmB[2 * c + 0] = sv_dm_log_partial(c, al.w1);
+    dmB[2 * c + 1] = sv_dm_log_partial(c, al.w2);
+}
+
+struct SvCovParams {
+    double t, v;        // allelicSeqCov, allelicSeqCovRawVar
+    double theta;       // adoRate
+    int single_ado;
+};
+
+// log NB(x; r, p) for `alleles` sequenced alleles of a cell with size factor s:
+// ExploredSharedAllelicSeqCovModel.java:266-277 + math/distributions/NegativeBinomial.java:76-79, same order.
+__device__ __forceinline__ double sv_seq_cov_log(int x, int alleles, double s, double t, double v) {
+    const double ka = __dadd_rn((double)alleles, 1e-6);
+    const double mean = __dmul_rn(__dmul_rn(ka, t), s);
+    const double var = __dadd_rn(mean, __dmul_rn(__dmul_rn(__dmul_rn(s, s), __dmul_rn(ka, ka)), v));
+    const double p = __ddiv_rn(mean, var);
+    const double r = __ddiv_rn(__dmul_rn(mean, mean), __dadd_rn(var, -mean));
+    const double beta = __dadd_rn(__ddiv_rn(1.0, p), -1.0);
+    const double rx = __dadd_rn(r, (double)x);
+    double l = __dadd_rn(sv_log_gamma(rx), __dmul_rn(rx, log(__dadd_rn(1.0, -p))));
+    l = __dadd_rn(l, -sv_log_gamma(__dadd_rn((double)x, 1.0)));
+    l = __dadd_rn(l, -sv_log_gamma(r));
+    l = __dadd_rn(l, -__dmul_rn(r, log(beta)));
+    return l;
+}
+
+// The coverage part of the dropout mixture at coverage x, scaled by its own maximum:
+//   single ADO: e[0] = (1-theta) * NB_2 / M, e[1] = theta * NB_1 / M, e[2] = log M, e[3] = -inf
+//   locus  ADO: e[0] = (1-theta)^2 * NB_2 / M, e[1] = theta (1-theta) * NB_1 / M, e[2] = log M, e[3] = log(theta^2 NB_0 / M)
+__device__ __forceinline__ void sv_cov_entry(int x, double s, const SvCovParams& cp, double (&e)[4]) {
+    const double c2 = sv_seq_cov_log(x, 2, s, cp.t, cp.v);
+    const double c1 = sv_seq_cov_log(x, 1, s, cp.t, cp.v);
+    const double lt = log(cp.theta), l1t = log(1 - cp.theta);
+    if (cp.single_ado) {
+        const double a = l1t + c2, b = lt + c1;
+        const double m = fmax(a, b);
+        e[0] = exp(a - m);
+        e[1] = exp(b - m);
+        e[2] = m;
+        e[3] = __longlong_as_double(0xfff0000000000000LL);
+    } else {
+        const double c0 = sv_seq_cov_log(x, 0, s, cp.t, cp.v);
+        const double a = 2 * l1t + c2, b = lt + l1t + c1, z = 2 * lt + c0;
+        const double m = fmax(fmax(a, b), z);
+        e[0] = exp(a - m);
+        e[1] = exp(b - m);
+        e[2] = m;
+        e[3] = z - m;
+    }
+}
+
+__global__ void k_build_cell_tables(double* __restrict__ cellT, const double* __restrict__ size_factors, int n_cells,
+                                    int C, SvCovParams cp) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (x >= C || j >= n_cells) return;
+    double e[4];
+    sv_cov_entry(x, size_factors[j], cp, e);
+    sv_st256(cellT + ((size_t)j * C + x) * 4, e);
+}
+
+// Slow paths for counts beyond the tables: out of line and returning by value, so that the hot loop keeps its
+// operands in registers and stays small.
+struct SvD4 {
+    double a, b, c, d;
+};
+struct SvD2 {
+    double a, b;
+};
+__device__ __noinline__ SvD4 sv_dm_partials_direct(int c, SvDmAlphas al) {
+    SvD4 o;
+    o.a = sv_dm_log_partial(c, al.fw1);
+    o.b = sv_dm_log_partial(c, al.omw1);
+    o.c = sv_dm_log_partial(c, al.hw2);
+    o.d = sv_dm_log_partial(c, al.fw2);
+    return o;
+}
+__device__ __noinline__ SvD2 sv_dm_totals_direct(int c, SvDmAlphas al) {
+    SvD2 o;
+    o.a = sv_dm_log_partial(c, al.w1);
+    o.b = sv_dm_log_partial(c, al.w2);
+    return o;
+}
+__device__ __noinline__ SvD4 sv_cov_entry_direct(int x, double s, SvCovParams cp) {
+    double e[4];
+    sv_cov_entry(x, s, cp, e);
+    SvD4 o;
+    o.a = e[0]; o.b = e[1]; o.c = e[2]; o.d = e[3];
+    return o;
+}
+
+// ---- the leaf kernel -------------------------------------------------------------------------------------------
+struct SvLeafArgs {
+    const int4* counts;     // [cell][site] (alt1, alt2, alt3, cov)
+    const double* dmA;      // [C][4]
+    const double* dmB;      // [C][2]
+    const double* cellT;    // [cell][C][4]
+    const double* size_factors;
+    double* leafX;          // [cell][site][4]   (already offset to the write buffer)
+    double* leafS;          // [cell][site]
+    int n_cells, S, C;
+    int sites_per_block;
+    SvDmAlphas al;
+    SvCovParams cp;
+};
+
+template <bool SMEM_TABLES>
+__global__ void __launch_bounds__(256) k_leaf(SvLeafArgs a) {
+    extern __shared__ double sm[];
+    const int j = blockIdx.y;
+    const int C = a.C;
+    const double* dmA = a.dmA;
+    const double* dmB = a.dmB;
+    const double* cT = a.cellT + (size_t)j * C * 4;
+    if (SMEM_TABLES) {
+        double* sA = sm;
+        double* sB = sm + 4 * (size_t)C;
+        double* sT = sm + 6 * (size_t)C;
+        for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sA[i] = dmA[i];
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sB[i] = dmB[i];
+        for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sT[i] = cT[i];
+        __syncthreads();
+        dmA = sA;
+        dmB = sB;
+        cT = sT;
+    }
+    const double sf = a.size_factors[j];
+    const int s0 = blockIdx.x * a.sites_per_block;
+    const int s1 = min(a.S, s0 + a.sites_per_block);
+    const int4* cnt = a.counts + (size_t)j * a.S;
+    double* outX = a.leafX + (size_t)j * a.S * 4;
+    double* outS = a.leafS + (size_t)j * a.S;
+
+    for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const int4 c = __ldg(cnt + s);
+        const int cov = c.w;
+        const int ref = cov - (c.x + c.y + c.z);
+        double N0, N1, N2, N3;
+        if (cov == 0) {
+            // DirichletMultinomial.logDensity returns 1.0 for an empty site, log mode included (:29-30)
+            N0 = N1 = N2 = N3 = 1.0;
+        } else {
+            double A1[4], A2[4], A3[4], AR[4], B[2];
+            // LP terms: table when the count is inside it, else the same formula evaluated directly
+            auto lpA = [&](int cval, double (&o)[4]) {
+                const int ci = cval < 0 ? 0 : cval;
+                if (ci < C) {
+                    const double2 u = *reinterpret_cast<const double2*>(dmA + 4 * ci);
+                    const double2 w = *reinterpret_cast<const double2*>(dmA + 4 * ci + 2);
+                    o[0] = u.x; o[1] = u.y; o[2] = w.x; o[3] = w.y;
+                } else {
+                    const SvD4 r = sv_dm_partials_direct(ci, a.al);
+                    o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
+                }
+            };
+            lpA(c.x, A1);
+            lpA(c.y, A2);
+            lpA(c.z, A3);
+            lpA(ref, AR);
+            if (cov > 0 && cov < C) {
+                const double2 u = *reinterpret_cast<const double2*>(dmB + 2 * cov);
+                B[0] = u.x; B[1] = u.y;
+            } else {
+                const SvD2 r = sv_dm_totals_direct(cov, a.al);
+                B[0] = r.a; B[1] = r.b;
+            }
+            // logDensity = LP(cov, a0) - (((LP(c1,a1) + LP(c2,a2)) + LP(c3,a3)) + LP(ref,a4)), summed left to right
+            N0 = B[0] - (((A1[0] + A2[0]) + A3[0]) + AR[1]);  // 0/0 : (f, f, f, 1-eps) w1
+            N1 = B[0] - (((A1[1] + A2[0]) + A3[0]) + AR[0]);  // 1/1 : (1-eps, f, f, f) w1
+            N2 = B[1] - (((A1[2] + A2[2]) + A3[3]) + AR[3]);  // 1/1': (h, h, f, f) w2
+            N3 = B[1] - (((A1[2] + A2[3]) + A3[3]) + AR[2]);  // 0/1 : (h, f, f, h) w2
+        }
+        double e[4];
+        if (cov >= 0 && cov < C) {
+            const double2 u = *reinterpret_cast<const double2*>(cT + 4 * cov);
+            const double2 w = *reinterpret_cast<const double2*>(cT + 4 * cov + 2);
+            e[0] = u.x; e[1] = u.y; e[2] = w.x; e[3] = w.y;
+        } else {
+            const SvD4 r = sv_cov_entry_direct(cov, sf, a.cp);
+            e[0] = r.a; e[1] = r.b; e[2] = r.c; e[3] = r.d;
+        }
+        double x[4], ls;
+        if (a.cp.single_ado) {
+            // RawReadCountsModelFiniteMuDM.java:133-225, single-ADO arms, in linear space with a common scale
+            const double m = fmax(fmax(N0, N1), fmax(N2, N3));
+            const double n0 = exp(N0 - m), n1 = exp(N1 - m), n2 = exp(N2 - m), n3 = exp(N3 - m);
+            const double both = e[0] + e[1];
+            x[0] = n0 * both;                              // 0/0
+            x[1] = n3 * e[0] + 0.5 * (n0 + n1) * e[1];     // 0/1
+            x[2] = n1 * both;                              // 1/1
+            x[3] = n2 * e[0] + n1 * e[1];                  // 1/1'
+            ls = m + e[2];
+        } else {
+            // locus-dropout arms (:147-160 etc.); the theta^2 * NB_0 term carries no nucleotide factor
+            const double m = fmax(fmax(fmax(N0, N1), fmax(N2, N3)), e[3]);
+            const double n0 = exp(N0 - m), n1 = exp(N1 - m), n2 = exp(N2 - m), n3 = exp(N3 - m);
+            const double z = exp(e[3] - m);
+            x[0] = n0 * e[0] + 2.0 * n0 * e[1] + z;
+            x[1] = n3 * e[0] + (n0 + n1) * e[1] + z;
+            x[2] = n1 * e[0] + 2.0 * n1 * e[1] + z;
+            x[3] = n2 * e[0] + 2.0 * n1 * e[1] + z;
+            ls = m + e[2];
+        }
+        sv_st256(outX + (size_t)s * 4, x);
+        outS[s] = ls;
+    }
+}

@@ -1,0 +1,104 @@
+// reduce.cuh -- per-shard totals: sum of weighted site log-likelihoods and the constant-site aggregates that the
+// acquisition-bias correction needs.
+//
+// Replaces ScsTreeLikelihood.calcLogP (likelihood/ScsTreeLikelihood.java:2621-2651) and the per-worker part of
+// ScsAlignment.getAscBiasCorrection* (alignment/ScsAlignment.java:746-782).  The reference sums sites left to right;
+// this is a fixed-shape tree (thread-strided -> warp shuffle -> block -> blocks in index order), deterministic run to
+// run, and differs from the sequential sum only in the last bits (budget: 1e-9 relative on the total).
+#pragma once
+#include "common.cuh"
+
+struct SvAcc {
+    double sum;    // sum w * logL
+    double m, se;  // running max and sum w * exp(c - m) of the constant-site logs
+    double csum;   // sum w * c
+    double lewis;  // sum w * log(1 - exp(c))
+    double wsum;   // sum w
+};
+
+__device__ __forceinline__ void sv_lse_merge(double& m, double& se, double m2, double se2) {
+    const double mm = fmax(m, m2);
+    const double a = (m == mm) ? se : se * exp(m - mm);
+    const double b = (m2 == mm) ? se2 : se2 * exp(m2 - mm);
+    m = mm;
+    se = a + b;
+}
+
+__device__ __forceinline__ void sv_acc_merge(SvAcc& a, const SvAcc& b) {
+    a.sum += b.sum;
+    sv_lse_merge(a.m, a.se, b.m, b.se);
+    a.csum += b.csum;
+    a.lewis += b.lewis;
+    a.wsum += b.wsum;
+}
+
+__device__ __forceinline__ SvAcc sv_acc_shfl_down(const SvAcc& a, int d) {
+    SvAcc b;
+    b.sum = __shfl_down_sync(0xffffffffu, a.sum, d);
+    b.m = __shfl_down_sync(0xffffffffu, a.m, d);
+    b.se = __shfl_down_sync(0xffffffffu, a.se, d);
+    b.csum = __shfl_down_sync(0xffffffffu, a.csum, d);
+    b.lewis = __shfl_down_sync(0xffffffffu, a.lewis, d);
+    b.wsum = __shfl_down_sync(0xffffffffu, a.wsum, d);
+    return b;
+}
+
+__device__ __forceinline__ SvAcc sv_acc_zero() {
+    SvAcc a;
+    a.sum = 0.0;
+    a.m = __longlong_as_double(0xfff0000000000000LL);
+    a.se = 0.0;
+    a.csum = 0.0;
+    a.lewis = 0.0;
+    a.wsum = 0.0;
+    return a;
+}
+
+// out layout == sieve_shard_result_t {sum_log_l, const_lse, const_sum, lewis_sum, weight_sum}
+__global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl, const double* __restrict__ cst,
+                                                const int* __restrict__ w, int S, int with_const,
+                                                SvAcc* __restrict__ partials, unsigned int* __restrict__ counter,
+                                                double* __restrict__ out) {
+    __shared__ SvAcc sm[8];
+    __shared__ bool last;
+    SvAcc acc = sv_acc_zero();
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+        const double wt = w ? (double)w[s] : 1.0;
+        acc.sum += wt * logl[s];
+        acc.wsum += wt;
+        if (with_const) {
+            const double c = cst[s];
+            sv_lse_merge(acc.m, acc.se, c, wt);
+            acc.csum += wt * c;
+            acc.lewis += wt * log(1.0 - exp(c));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const SvAcc b = sv_acc_shfl_down(acc, d);
+        sv_acc_merge(acc, b);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        SvAcc t = sm[0];
+        for (int i = 1; i < (int)(blockDim.x >> 5); i++) sv_acc_merge(t, sm[i]);
+        partials[blockIdx.x] = t;
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        SvAcc t = partials[0];
+        for (int i = 1; i < (int)gridDim.x; i++) sv_acc_merge(t, partials[i]);
+        out[0] = t.sum;
+        out[1] = with_const ? log(t.se) + t.m : 0.0;
+        out[2] = t.csum;
+        out[3] = -t.lewis;
+        out[4] = t.wsum;
+        *counter = 0u;
+    }
+}

@@ -1,0 +1,985 @@
+// sieve_core.cu -- the C-ABI of include/sieve_b200.h: device pools, buffer-index bookkeeping and kernel launches.
+//
+// Host-side state mirrors BeerLikelihoodCore's double buffering (external BEAST class; SIEVE's additions in
+// likelihood/ScsBeerLikelihoodCore.java:91-128, 4053-4065): per node a "current" and a "stored" buffer index for the
+// partials and for the transition matrices; reject == swap of the index arrays, nothing is copied on the device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sieve_b200.h"
+#include "common.cuh"
+#include "leaf.cuh"
+#include "prune.cuh"
+#include "reduce.cuh"
+#include "sizefactors.cuh"
+
+static thread_local std::string g_err;
+
+static int sv_fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define SV_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return sv_fail(SIEVE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+#define SV_REQUIRE(cond, msg) \
+    do {                      \
+        if (!(cond)) return sv_fail(SIEVE_ERR_INVALID, msg); \
+    } while (0)
+
+struct PendingMatrix {
+    int slot;
+    double v[SV_KMAX * 16];
+};
+
+struct sieve_core {
+    sieve_config_t cfg;
+    int n = 0, S = 0, K = 0, n_nodes = 0, n_internal = 0;
+    bool log_mode = false, with_const = false, single_ado = true, ephemeral = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t bytes = 0;
+    uint64_t launches = 0;
+    int step_launches = 0;  // since the last evaluate
+    bool leaf_attr_set = false;
+
+    // device pools
+    int4* d_counts = nullptr;  // [cell][site]
+    bool counts_owned = true;
+    int* d_weights = nullptr;
+    double* d_sf = nullptr;
+    double *d_dmA = nullptr, *d_dmB = nullptr, *d_cellT = nullptr;
+    int C = 0;  // table entries per table
+    int max_cov = -1;
+    double *d_leafX = nullptr, *d_leafS = nullptr;                                       // [2][n][S][4], [2][n][S]
+    double *d_part = nullptr, *d_scale = nullptr, *d_cpart = nullptr, *d_cscale = nullptr;  // [2][n_internal][S][K][4]
+    double* d_mats = nullptr;                                                            // [2][n_nodes][K][16]
+    double *d_site_logl = nullptr, *d_site_const = nullptr;
+    SvAcc* d_partials = nullptr;
+    unsigned int* d_counter = nullptr;
+    double* d_result = nullptr;
+    // staging
+    char* h_stage = nullptr;  // pinned
+    char* d_stage = nullptr;
+    size_t stage_cap = 0;
+    double* h_result = nullptr;  // pinned, 8 doubles
+
+    // host bookkeeping
+    std::vector<int> cur_part, stored_part, cur_mat, stored_mat;
+    int cur_leaf = 0, stored_leaf = 0;
+    std::vector<SvOp> pending_ops;
+    std::vector<int> pending_levels;  // offsets into pending_ops, empty == one group
+    bool pending_per_level = false;
+    std::vector<PendingMatrix> pending_mats;
+    int root = -1, root_genotype = 0, const_genotype = 0;
+    double prop[4] = {0.25, 0.25, 0.25, 0.25};
+    sieve_leaf_params_t lp{};
+    bool have_counts = false, have_sf = false, have_params = false, leaves_ready = false;
+    bool dm_dirty = true, cov_dirty = true;
+    sieve_leaf_params_t tab_lp{};  // parameters the current tables were built with
+
+    // what the last flush staged on the device (for sieve_replay)
+    size_t last_no = 0, last_nm = 0, last_off_mv = 0, last_off_ms = 0;
+    std::vector<int> last_levels;
+    bool last_per_level = false;
+
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    int last_launches = 0;
+    bool leaf_timed = false;
+};
+
+static inline void sv_count(sieve_core* h) {
+    h->launches++;
+    h->step_launches++;
+}
+
+static const int SV_TABLE_CAP_DEFAULT = 4096;
+static const int SV_REDUCE_BLOCKS = 296;
+
+extern "C" const char* sieve_last_error(void) { return g_err.c_str(); }
+extern "C" int sieve_version(void) { return 1; }
+extern "C" int sieve_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+template <typename T>
+static int sv_alloc(sieve_core* h, T** p, size_t count) {
+    const size_t b = count * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, b ? b : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return sv_fail(e == cudaErrorMemoryAllocation ? SIEVE_ERR_OOM : SIEVE_ERR_CUDA,
+                       std::string("cudaMalloc of ") + std::to_string(b) + " bytes: " + cudaGetErrorString(e));
+    }
+    h->bytes += b;
+    return SIEVE_OK;
+}
+#define SV_TRY(x)                    \
+    do {                             \
+        int r__ = (x);               \
+        if (r__ != SIEVE_OK) return r__; \
+    } while (0)
+
+static int sv_ensure_stage(sieve_core* h, size_t bytes) {
+    if (bytes <= h->stage_cap) return SIEVE_OK;
+    size_t cap = std::max<size_t>(bytes, std::max<size_t>(h->stage_cap * 2, (size_t)1 << 16));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->d_stage) {
+        cudaFree(h->d_stage);
+        h->bytes -= h->stage_cap;
+    }
+    h->h_stage = nullptr;
+    h->d_stage = nullptr;
+    h->stage_cap = 0;
+    SV_CUDA(cudaMallocHost((void**)&h->h_stage, cap));
+    SV_TRY(sv_alloc(h, &h->d_stage, cap));
+    h->stage_cap = cap;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
+    SV_REQUIRE(cfg && out, "sieve_create: null argument");
+    SV_REQUIRE(cfg->n_states == 4, "sieve_create: n_states must be 4 (ScsFiniteMuExtendedModel)");
+    SV_REQUIRE(cfg->n_categories >= 1 && cfg->n_categories <= SV_KMAX, "sieve_create: n_categories must be in 1..4");
+    SV_REQUIRE(cfg->n_leaves >= 1 && cfg->n_sites >= 1, "sieve_create: n_leaves and n_sites must be positive");
+    int ndev = 0;
+    SV_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return sv_fail(SIEVE_ERR_CUDA, "sieve_create: no CUDA device (there is no CPU fallback)");
+    int dev = cfg->device;
+    if (dev < 0) SV_CUDA(cudaGetDevice(&dev));
+    SV_REQUIRE(dev < ndev, "sieve_create: device ordinal out of range");
+    SV_CUDA(cudaSetDevice(dev));
+
+    sieve_core* h = new sieve_core();
+    h->cfg = *cfg;
+    h->device = dev;
+    h->n = cfg->n_leaves;
+    h->S = cfg->n_sites;
+    h->K = cfg->n_categories;
+    h->n_nodes = 2 * h->n;
+    h->n_internal = h->n;
+    h->log_mode = cfg->flags & SIEVE_FLAG_LOG_PARTIALS;
+    h->with_const = cfg->flags & SIEVE_FLAG_CONST_PARTIALS;
+    h->single_ado = cfg->flags & SIEVE_FLAG_SINGLE_ADO;
+    h->ephemeral = cfg->flags & SIEVE_FLAG_EPHEMERAL;
+    h->cur_part.assign(h->n_nodes, 0);
+    h->stored_part.assign(h->n_nodes, 0);
+    h->cur_mat.assign(h->n_nodes, 0);
+    h->stored_mat.assign(h->n_nodes, 0);
+    h->root = h->n_nodes - 1;
+
+    auto fail = [&](int code) {
+        sieve_destroy(h);
+        return code;
+    };
+    if (h->ephemeral) {
+        g_err = "sieve_create: SIEVE_FLAG_EPHEMERAL is not available in this build";
+        return fail(SIEVE_ERR_INVALID);
+    }
+    cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) {
+        g_err = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce);
+        return fail(SIEVE_ERR_CUDA);
+    }
+    const size_t n = h->n, S = h->S, K = h->K;
+    // does the residency fit?
+    size_t need = n * S * 16 + 2 * n * S * 40 + 2 * n * S * (K * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (need > free_b) {
+        g_err = "sieve_create: resident pools need " + std::to_string(need >> 20) + " MiB, device has " +
+                std::to_string(free_b >> 20) + " MiB free";
+        return fail(SIEVE_ERR_OOM);
+    }
+    int r;
+#define CR(x)                              \
+    do {                                   \
+        r = (x);                           \
+        if (r != SIEVE_OK) return fail(r); \
+    } while (0)
+    CR(sv_alloc(h, &h->d_counts, n * S));
+    CR(sv_alloc(h, &h->d_sf, n));
+    CR(sv_alloc(h, &h->d_leafX, 2 * n * S * 4));
+    CR(sv_alloc(h, &h->d_leafS, 2 * n * S));
+    CR(sv_alloc(h, &h->d_part, 2 * n * S * K * 4));
+    CR(sv_alloc(h, &h->d_scale, 2 * n * S));
+    if (h->with_const) {
+        CR(sv_alloc(h, &h->d_cpart, 2 * n * S * K * 4));
+        CR(sv_alloc(h, &h->d_cscale, 2 * n * S));
+    }
+    CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * K * 16));
+    CR(sv_alloc(h, &h->d_site_logl, S));
+    CR(sv_alloc(h, &h->d_site_const, S));
+    CR(sv_alloc(h, &h->d_partials, (size_t)SV_REDUCE_BLOCKS));
+    CR(sv_alloc(h, &h->d_counter, 1));
+    CR(sv_alloc(h, &h->d_result, 8));
+#undef CR
+    if (cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream) != cudaSuccess ||
+        cudaMemsetAsync(h->d_mats, 0, sizeof(double) * 2 * h->n_nodes * K * 16, h->stream) != cudaSuccess ||
+        cudaMemsetAsync(h->d_site_const, 0, sizeof(double) * S, h->stream) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_result, 8 * sizeof(double)) != cudaSuccess) {
+        g_err = "sieve_create: initialisation of device buffers failed";
+        return fail(SIEVE_ERR_CUDA);
+    }
+    for (int i = 0; i < 6; i++) cudaEventCreate(&h->ev[i]);
+    cudaStreamSynchronize(h->stream);
+    *out = h;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_destroy(sieve_core_t* h) {
+    if (!h) return SIEVE_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->counts_owned) cudaFree(h->d_counts);
+    cudaFree(h->d_weights);
+    cudaFree(h->d_sf);
+    cudaFree(h->d_dmA);
+    cudaFree(h->d_dmB);
+    cudaFree(h->d_cellT);
+    cudaFree(h->d_leafX);
+    cudaFree(h->d_leafS);
+    cudaFree(h->d_part);
+    cudaFree(h->d_scale);
+    cudaFree(h->d_cpart);
+    cudaFree(h->d_cscale);
+    cudaFree(h->d_mats);
+    cudaFree(h->d_site_logl);
+    cudaFree(h->d_site_const);
+    cudaFree(h->d_partials);
+    cudaFree(h->d_counter);
+    cudaFree(h->d_result);
+    cudaFree(h->d_stage);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_result) cudaFreeHost(h->h_result);
+    for (int i = 0; i < 6; i++)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_device_bytes(sieve_core_t* h, uint64_t* out) {
+    SV_REQUIRE(h && out, "null argument");
+    *out = h->bytes;
+    return SIEVE_OK;
+}
+
+// ---- counts ---------------------------------------------------------------------------------------------------
+// [site][cell][T] chunk -> [cell][site] int4, tracking the largest coverage
+__global__ void k_transpose_counts(const int* __restrict__ in, int tuple_len, int s0, int n_chunk_sites, int n_cells,
+                                   int S, int4* __restrict__ out, int* __restrict__ max_cov) {
+    // a 32 x 32 (site x cell) tile per block so that both the read and the write are coalesced
+    __shared__ int4 tile[32][33];
+    const int cs = blockIdx.x * 32, cc = blockIdx.y * 32;
+    int mx = 0;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int s = cs + r, c = cc + threadIdx.x;
+        if (s < n_chunk_sites && c < n_cells) {
+            const int* p = in + ((size_t)s * n_cells + c) * tuple_len;
+            int4 v;
+            v.x = p[0];
+            v.y = p[1];
+            v.z = p[2];
+            v.w = tuple_len == 5 ? p[4] : p[3];
+            tile[r][threadIdx.x] = v;
+            mx = max(mx, v.w);
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = cc + r, s = cs + threadIdx.x;
+        if (s < n_chunk_sites && c < n_cells) out[(size_t)c * S + s0 + s] = tile[threadIdx.x][r];
+    }
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    if (threadIdx.x == 0 && mx > 0) atomicMax(max_cov, mx);
+}
+
+__global__ void k_max_cov(const int4* __restrict__ c, size_t N, int* __restrict__ max_cov) {
+    int mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x)
+        mx = max(mx, c[i].w);
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(max_cov, mx);
+}
+
+static int sv_alloc_tables(sieve_core* h) {
+    int cap = SV_TABLE_CAP_DEFAULT;
+    if (const char* e = getenv("SIEVE_B200_TABLE_CAP")) cap = std::max(2, atoi(e));
+    const int C = std::min(h->max_cov + 1, cap);
+    if (C != h->C || !h->d_dmA) {
+        cudaFree(h->d_dmA);
+        cudaFree(h->d_dmB);
+        cudaFree(h->d_cellT);
+        h->d_dmA = h->d_dmB = h->d_cellT = nullptr;
+        h->C = std::max(C, 1);
+        SV_TRY(sv_alloc(h, &h->d_dmA, (size_t)h->C * 4));
+        SV_TRY(sv_alloc(h, &h->d_dmB, (size_t)h->C * 2));
+        SV_TRY(sv_alloc(h, &h->d_cellT, (size_t)h->n * h->C * 4));
+    }
+    h->dm_dirty = h->cov_dirty = true;
+    return SIEVE_OK;
+}
+
+static int sv_finish_counts(sieve_core* h, int* d_max) {
+    int mx = 0;
+    SV_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d_max);
+    h->max_cov = mx;
+    h->have_counts = true;
+    h->leaves_ready = false;
+    return sv_alloc_tables(h);
+}
+
+extern "C" int sieve_set_counts(sieve_core_t* h, const int32_t* counts, int32_t tuple_len) {
+    SV_REQUIRE(h && counts, "sieve_set_counts: null argument");
+    SV_REQUIRE(tuple_len == 4 || tuple_len == 5, "sieve_set_counts: tuple_len must be 4 or 5");
+    SV_CUDA(cudaSetDevice(h->device));
+    const size_t n = h->n, S = h->S;
+    // bounded staging: at most ~256 MiB of the host tensor on the device at a time
+    size_t chunk_sites = std::max<size_t>(32, std::min<size_t>(S, ((size_t)256 << 20) / (n * tuple_len * 4)));
+    chunk_sites = (chunk_sites + 31) / 32 * 32;
+    int* d_in = nullptr;
+    int* d_max = nullptr;
+    SV_CUDA(cudaMalloc(&d_in, chunk_sites * n * tuple_len * sizeof(int)));
+    SV_CUDA(cudaMalloc(&d_max, sizeof(int)));
+    SV_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
+    for (size_t s0 = 0; s0 < S; s0 += chunk_sites) {
+        const size_t ns = std::min(chunk_sites, S - s0);
+        SV_CUDA(cudaMemcpyAsync(d_in, counts + s0 * n * tuple_len, ns * n * tuple_len * sizeof(int),
+                                cudaMemcpyHostToDevice, h->stream));
+        dim3 g((unsigned)((ns + 31) / 32), (unsigned)((n + 31) / 32)), b(32, 8);
+        k_transpose_counts<<<g, b, 0, h->stream>>>(d_in, tuple_len, (int)s0, (int)ns, (int)n, (int)S, h->d_counts, d_max);
+        sv_count(h);
+        SV_CUDA(cudaGetLastError());
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(d_in);
+    return sv_finish_counts(h, d_max);
+}
+
+extern "C" int sieve_set_counts_device(sieve_core_t* h, const void* d_counts) {
+    SV_REQUIRE(h && d_counts, "sieve_set_counts_device: null argument");
+    SV_CUDA(cudaSetDevice(h->device));
+    const size_t N = (size_t)h->n * h->S;
+    SV_CUDA(cudaMemcpyAsync(h->d_counts, d_counts, N * sizeof(int4), cudaMemcpyDeviceToDevice, h->stream));
+    int* d_max = nullptr;
+    SV_CUDA(cudaMalloc(&d_max, sizeof(int)));
+    SV_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
+    k_max_cov<<<592, 256, 0, h->stream>>>(h->d_counts, N, d_max);
+    sv_count(h);
+    SV_CUDA(cudaGetLastError());
+    return sv_finish_counts(h, d_max);
+}
+
+extern "C" int sieve_set_pattern_weights(sieve_core_t* h, const int32_t* weights) {
+    SV_REQUIRE(h, "null handle");
+    SV_CUDA(cudaSetDevice(h->device));
+    if (!weights) {
+        cudaFree(h->d_weights);
+        h->d_weights = nullptr;
+        return SIEVE_OK;
+    }
+    if (!h->d_weights) SV_TRY(sv_alloc(h, &h->d_weights, (size_t)h->S));
+    SV_CUDA(cudaMemcpyAsync(h->d_weights, weights, sizeof(int) * h->S, cudaMemcpyHostToDevice, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_compute_size_factors(sieve_core_t* h, int32_t zero_cov_mode, double* out_sf, double* out_stats) {
+    SV_REQUIRE(h, "null handle");
+    SV_REQUIRE(zero_cov_mode == 0 || zero_cov_mode == 1, "zeroCovMode must be 0 or 1");
+    if (!h->have_counts) return sv_fail(SIEVE_ERR_STATE, "sieve_compute_size_factors: counts not set");
+    SV_CUDA(cudaSetDevice(h->device));
+    unsigned long long l = 0;
+    SV_CUDA(sv_compute_size_factors(h->d_counts, h->d_weights, h->n, h->S, zero_cov_mode, h->d_sf, out_stats, h->stream, &l));
+    h->launches += l;
+    h->step_launches += (int)l;
+    if (out_sf) {
+        SV_CUDA(cudaMemcpyAsync(out_sf, h->d_sf, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    h->have_sf = true;
+    h->cov_dirty = true;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_set_size_factors(sieve_core_t* h, const double* sf) {
+    SV_REQUIRE(h && sf, "null argument");
+    SV_CUDA(cudaSetDevice(h->device));
+    SV_CUDA(cudaMemcpyAsync(h->d_sf, sf, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_sf = true;
+    h->cov_dirty = true;
+    return SIEVE_OK;
+}
+
+// ---- leaves ---------------------------------------------------------------------------------------------------
+extern "C" int sieve_set_leaf_params(sieve_core_t* h, const sieve_leaf_params_t* p) {
+    SV_REQUIRE(h && p, "null argument");
+    h->lp = *p;
+    h->have_params = true;
+    return SIEVE_OK;
+}
+
+static int sv_launch_leaves(sieve_core* h) {
+    const SvDmAlphas al = sv_dm_alphas(h->lp.eff_seq_err_rate, h->lp.shape_ctrl1, h->lp.shape_ctrl2);
+    SvCovParams cp;
+    cp.t = h->lp.allelic_seq_cov;
+    cp.v = h->lp.allelic_seq_cov_raw_var;
+    cp.theta = h->lp.ado_rate;
+    cp.single_ado = h->single_ado ? 1 : 0;
+    const int C = h->C;
+    // tables are rebuilt only for the sub-model whose parameters moved (the reference's isDirtyCalculation checks,
+    // rawreadcountsmodel/RawReadCountsModelInterface.java:476-490)
+    if (h->lp.eff_seq_err_rate != h->tab_lp.eff_seq_err_rate || h->lp.shape_ctrl1 != h->tab_lp.shape_ctrl1 ||
+        h->lp.shape_ctrl2 != h->tab_lp.shape_ctrl2)
+        h->dm_dirty = true;
+    if (h->lp.allelic_seq_cov != h->tab_lp.allelic_seq_cov ||
+        h->lp.allelic_seq_cov_raw_var != h->tab_lp.allelic_seq_cov_raw_var || h->lp.ado_rate != h->tab_lp.ado_rate)
+        h->cov_dirty = true;
+    h->tab_lp = h->lp;
+    if (h->dm_dirty) {
+        k_build_dm_tables<<<(C + 127) / 128, 128, 0, h->stream>>>(h->d_dmA, h->d_dmB, C, al);
+        sv_count(h);
+        h->dm_dirty = false;
+    }
+    if (h->cov_dirty) {
+        dim3 g((C + 127) / 128, h->n);
+        k_build_cell_tables<<<g, 128, 0, h->stream>>>(h->d_cellT, h->d_sf, h->n, C, cp);
+        sv_count(h);
+        h->cov_dirty = false;
+    }
+    SV_CUDA(cudaGetLastError());
+    SvLeafArgs a;
+    a.counts = h->d_counts;
+    a.dmA = h->d_dmA;
+    a.dmB = h->d_dmB;
+    a.cellT = h->d_cellT;
+    a.size_factors = h->d_sf;
+    a.leafX = h->d_leafX + (size_t)h->cur_leaf * h->n * h->S * 4;
+    a.leafS = h->d_leafS + (size_t)h->cur_leaf * h->n * h->S;
+    a.n_cells = h->n;
+    a.S = h->S;
+    a.C = C;
+    a.al = al;
+    a.cp = cp;
+    // site ranges: enough blocks to fill the 148 SMs a few times over, but long enough to amortise the table staging
+    const size_t smem = (size_t)C * 10 * sizeof(double);
+    const bool use_smem = smem <= 100 * 1024;
+    int splits = std::max(1, (148 * 8 + h->n - 1) / h->n);
+    int spb = std::max(use_smem ? 2048 : 256, (h->S + splits - 1) / splits);
+    spb = (spb + 255) / 256 * 256;
+    a.sites_per_block = spb;
+    dim3 grid((h->S + spb - 1) / spb, h->n);
+    if (use_smem) {
+        if (!h->leaf_attr_set) {
+            SV_CUDA(cudaFuncSetAttribute(k_leaf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            h->leaf_attr_set = true;
+        }
+        k_leaf<true><<<grid, 256, smem, h->stream>>>(a);
+    } else {
+        k_leaf<false><<<grid, 256, 0, h->stream>>>(a);
+    }
+    sv_count(h);
+    SV_CUDA(cudaGetLastError());
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
+    SV_REQUIRE(h, "null handle");
+    if (!h->have_counts || !h->have_sf || !h->have_params)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_update_leaves: counts, size factors and leaf parameters must be set first");
+    SV_CUDA(cudaSetDevice(h->device));
+    if (for_update) h->cur_leaf = 1 - h->cur_leaf;
+    if (h->timing) {
+        SV_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    }
+    SV_TRY(sv_launch_leaves(h));
+    if (h->timing) {
+        SV_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        h->leaf_timed = true;
+    }
+    if (!for_update) {
+        // initialisation: both buffers hold the leaves (storeLeafPartials, ScsBeerLikelihoodCore.java:437-445)
+        const size_t nx = (size_t)h->n * h->S * 4, ns = (size_t)h->n * h->S;
+        SV_CUDA(cudaMemcpyAsync(h->d_leafX + (size_t)(1 - h->cur_leaf) * nx, h->d_leafX + (size_t)h->cur_leaf * nx,
+                                nx * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        SV_CUDA(cudaMemcpyAsync(h->d_leafS + (size_t)(1 - h->cur_leaf) * ns, h->d_leafS + (size_t)h->cur_leaf * ns,
+                                ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->leaves_ready = true;
+    return SIEVE_OK;
+}
+
+// ---- matrices -------------------------------------------------------------------------------------------------
+__global__ void k_scatter_matrices(const double* __restrict__ stage, const int* __restrict__ slots, int count, int K,
+                                   double* __restrict__ mats) {
+    const int i = blockIdx.x;
+    const int e = threadIdx.x;
+    if (i < count && e < K * 16) mats[(size_t)slots[i] * K * 16 + e] = stage[(size_t)i * K * 16 + e];
+}
+
+static bool sv_node_ok(const sieve_core* h, int node) { return node >= 0 && node < h->n_nodes; }
+
+extern "C" int sieve_set_node_matrix_for_update(sieve_core_t* h, int32_t node) {
+    SV_REQUIRE(h && sv_node_ok(h, node), "sieve_set_node_matrix_for_update: bad node");
+    h->cur_mat[node] = 1 - h->cur_mat[node];
+    return SIEVE_OK;
+}
+
+static PendingMatrix* sv_pending_matrix(sieve_core* h, int slot) {
+    for (auto it = h->pending_mats.rbegin(); it != h->pending_mats.rend(); ++it)
+        if (it->slot == slot) return &*it;
+    PendingMatrix pm;
+    pm.slot = slot;
+    memset(pm.v, 0, sizeof(pm.v));
+    h->pending_mats.push_back(pm);
+    return &h->pending_mats.back();
+}
+
+extern "C" int sieve_set_node_matrix(sieve_core_t* h, int32_t node, int32_t category, const double* p16) {
+    SV_REQUIRE(h && p16 && sv_node_ok(h, node), "sieve_set_node_matrix: bad argument");
+    SV_REQUIRE(category >= 0 && category < h->K, "sieve_set_node_matrix: bad category");
+    // the K categories of one node arrive one by one (ScsTreeLikelihood.java:567-578); they share a pending entry
+    PendingMatrix* pm = nullptr;
+    const int slot = h->cur_mat[node] * h->n_nodes + node;
+    if (!h->pending_mats.empty() && h->pending_mats.back().slot == slot)
+        pm = &h->pending_mats.back();
+    else
+        pm = sv_pending_matrix(h, slot);
+    memcpy(pm->v + category * 16, p16, 16 * sizeof(double));
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_set_matrices(sieve_core_t* h, int32_t count, const int32_t* nodes, const double* P, int32_t for_update) {
+    SV_REQUIRE(h && count >= 0 && (count == 0 || (nodes && P)), "sieve_set_matrices: bad argument");
+    const int K = h->K;
+    h->pending_mats.reserve(h->pending_mats.size() + count);
+    for (int i = 0; i < count; i++) {
+        SV_REQUIRE(sv_node_ok(h, nodes[i]), "sieve_set_matrices: bad node");
+        if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
+        PendingMatrix pm;
+        pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
+        memcpy(pm.v, P + (size_t)i * K * 16, sizeof(double) * K * 16);
+        h->pending_mats.push_back(pm);
+    }
+    return SIEVE_OK;
+}
+
+// ---- ops ------------------------------------------------------------------------------------------------------
+extern "C" int sieve_set_node_partials_for_update(sieve_core_t* h, int32_t node) {
+    SV_REQUIRE(h && sv_node_ok(h, node), "sieve_set_node_partials_for_update: bad node");
+    if (node < h->n) return sv_fail(SIEVE_ERR_INVALID, "leaves flip together: use sieve_update_leaves(for_update = 1)");
+    h->cur_part[node] = 1 - h->cur_part[node];
+    return SIEVE_OK;
+}
+
+static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
+    const int n = h->n;
+    SV_REQUIRE(parent >= n && parent < h->n_nodes, "op: parent must be an internal node");
+    SV_REQUIRE(c1 >= 0 && c1 < h->n_nodes && c1 != h->root, "op: bad child1");
+    SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
+    op->flags = 0;
+    op->dst = h->cur_part[parent] * h->n_internal + (parent - n);
+    if (c1 < n) {
+        op->flags |= SV_OP_LEAF1;
+        op->c1 = h->cur_leaf * n + c1;
+    } else
+        op->c1 = h->cur_part[c1] * h->n_internal + (c1 - n);
+    op->m1 = h->cur_mat[c1] * h->n_nodes + c1;
+    if (c2 < 0) {
+        op->flags |= SV_OP_UNARY;
+        op->c2 = 0;
+        op->m2 = 0;
+    } else {
+        if (c2 < n) {
+            op->flags |= SV_OP_LEAF2;
+            op->c2 = h->cur_leaf * n + c2;
+        } else
+            op->c2 = h->cur_part[c2] * h->n_internal + (c2 - n);
+        op->m2 = h->cur_mat[c2] * h->n_nodes + c2;
+    }
+    if (parent == h->root) op->flags |= SV_OP_ROOT;
+    op->pad0 = op->pad1 = 0;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_calculate_partials(sieve_core_t* h, int32_t child1, int32_t is_leaf1, int32_t child2, int32_t is_leaf2,
+                                        int32_t parent, int32_t const_genotype) {
+    SV_REQUIRE(h, "null handle");
+    SV_REQUIRE(const_genotype >= 0 && const_genotype < 4, "bad const genotype");
+    SV_REQUIRE((child1 < h->n) == (is_leaf1 != 0), "sieve_calculate_partials: is_leaf1 contradicts the node numbering");
+    SV_REQUIRE(child2 < 0 || ((child2 < h->n) == (is_leaf2 != 0)),
+               "sieve_calculate_partials: is_leaf2 contradicts the node numbering");
+    h->const_genotype = const_genotype;
+    SvOp op;
+    SV_TRY(sv_make_op(h, child1, child2, parent, &op));
+    if (!h->pending_levels.empty()) {  // mixing with a level-batched update: fall back to one group
+        h->pending_levels.clear();
+        h->pending_per_level = false;
+    }
+    h->pending_ops.push_back(op);
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t* ops, const int32_t* level_offsets,
+                                  int32_t n_levels, uint32_t mode) {
+    SV_REQUIRE(h && n_ops >= 0 && (n_ops == 0 || ops), "sieve_update_nodes: bad argument");
+    const bool per_level = (mode & SIEVE_UPDATE_PER_LEVEL) && level_offsets && n_levels > 0;
+    if (per_level) {
+        SV_REQUIRE(h->pending_ops.empty(), "sieve_update_nodes: per-level update with other ops pending");
+        SV_REQUIRE(level_offsets[0] == 0 && level_offsets[n_levels] == n_ops, "sieve_update_nodes: bad level offsets");
+    }
+    if (mode & SIEVE_UPDATE_FLIP)
+        for (int i = 0; i < n_ops; i++) {
+            const int p = ops[3 * i];
+            SV_REQUIRE(p >= h->n && p < h->n_nodes, "sieve_update_nodes: parent must be an internal node");
+            h->cur_part[p] = 1 - h->cur_part[p];
+        }
+    h->pending_ops.reserve(h->pending_ops.size() + n_ops);
+    for (int i = 0; i < n_ops; i++) {
+        SvOp op;
+        SV_TRY(sv_make_op(h, ops[3 * i + 1], ops[3 * i + 2], ops[3 * i], &op));
+        h->pending_ops.push_back(op);
+    }
+    if (per_level) {
+        h->pending_levels.assign(level_offsets, level_offsets + n_levels + 1);
+        h->pending_per_level = true;
+    }
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_set_root(sieve_core_t* h, int32_t root, const double* proportions, int32_t root_genotype) {
+    SV_REQUIRE(h && proportions, "null argument");
+    SV_REQUIRE(root >= h->n && root < h->n_nodes, "sieve_set_root: the root must be an internal node");
+    SV_REQUIRE(root_genotype >= 0 && root_genotype < 4, "sieve_set_root: bad root genotype");
+    h->root = root;
+    h->root_genotype = root_genotype;
+    for (int k = 0; k < 4; k++) h->prop[k] = k < h->K ? proportions[k] : 0.0;
+    return SIEVE_OK;
+}
+
+// launches scatter + pruning for what is staged on the device
+static int sv_launch_staged(sieve_core* h) {
+    const int K = h->K;
+    const size_t nm = h->last_nm, no = h->last_no, off_mv = h->last_off_mv, off_ms = h->last_off_ms, off_ops = 0;
+    if (nm) {
+        k_scatter_matrices<<<(unsigned)nm, 64, 0, h->stream>>>((const double*)(h->d_stage + off_mv),
+                                                              (const int*)(h->d_stage + off_ms), (int)nm, K, h->d_mats);
+        sv_count(h);
+    }
+    if (no) {
+        SvPruneArgs a;
+        a.part = h->d_part;
+        a.scale = h->d_scale;
+        a.cpart = h->d_cpart;
+        a.cscale = h->d_cscale;
+        a.leafX = h->d_leafX;
+        a.leafS = h->d_leafS;
+        a.mats = h->d_mats;
+        a.ops = (const SvOp*)(h->d_stage + off_ops);
+        a.S = h->S;
+        a.K = K;
+        a.clamp_matrices = h->log_mode ? 1 : 0;
+        a.const_genotype = h->const_genotype;
+        a.root_genotype = h->root_genotype;
+        for (int k = 0; k < 4; k++) a.prop[k] = h->prop[k];
+        a.site_logl = h->d_site_logl;
+        a.site_const = h->d_site_const;
+        const unsigned gx = (unsigned)((h->S + 63) / 64);
+        if (h->last_per_level) {
+            for (size_t l = 0; l + 1 < h->last_levels.size(); l++) {
+                const int b = h->last_levels[l], e = h->last_levels[l + 1];
+                if (e <= b) continue;
+                a.op_begin = b;
+                a.op_end = e;
+                a.per_level = 1;
+                // grid.y is limited to 65535
+                for (int b0 = b; b0 < e; b0 += 65535) {
+                    a.op_begin = b0;
+                    dim3 grid(gx, (unsigned)std::min(65535, e - b0));
+                    if (h->with_const)
+                        k_prune<true><<<grid, 256, 0, h->stream>>>(a);
+                    else
+                        k_prune<false><<<grid, 256, 0, h->stream>>>(a);
+                    sv_count(h);
+                }
+            }
+        } else {
+            a.op_begin = 0;
+            a.op_end = (int)no;
+            a.per_level = 0;
+            if (h->with_const)
+                k_prune<true><<<gx, 256, 0, h->stream>>>(a);
+            else
+                k_prune<false><<<gx, 256, 0, h->stream>>>(a);
+            sv_count(h);
+        }
+    }
+    SV_CUDA(cudaGetLastError());
+    return SIEVE_OK;
+}
+
+// uploads pending matrices + ops with ONE host->device copy and launches scatter + pruning
+static int sv_flush(sieve_core* h) {
+    const int K = h->K;
+    const size_t nm = h->pending_mats.size(), no = h->pending_ops.size();
+    if (nm == 0 && no == 0) return SIEVE_OK;
+    if (no > 0 && !h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "ops queued before the leaves were computed");
+    // staging layout: [ops][matrix values][matrix slots]
+    const size_t off_ops = 0;
+    const size_t off_mv = off_ops + no * sizeof(SvOp);
+    const size_t off_ms = off_mv + nm * K * 16 * sizeof(double);
+    const size_t total = off_ms + nm * sizeof(int);
+    SV_TRY(sv_ensure_stage(h, total));
+    SV_CUDA(cudaStreamSynchronize(h->stream));  // the previous step may still be reading the staging buffer
+    if (no) memcpy(h->h_stage + off_ops, h->pending_ops.data(), no * sizeof(SvOp));
+    for (size_t i = 0; i < nm; i++) {
+        memcpy(h->h_stage + off_mv + i * K * 16 * sizeof(double), h->pending_mats[i].v, K * 16 * sizeof(double));
+        ((int*)(h->h_stage + off_ms))[i] = h->pending_mats[i].slot;
+    }
+    SV_CUDA(cudaMemcpyAsync(h->d_stage, h->h_stage, total, cudaMemcpyHostToDevice, h->stream));
+    h->last_no = no;
+    h->last_nm = nm;
+    h->last_off_mv = off_mv;
+    h->last_off_ms = off_ms;
+    h->last_levels = h->pending_levels;
+    h->last_per_level = h->pending_per_level;
+    SV_TRY(sv_launch_staged(h));
+    SV_CUDA(cudaGetLastError());
+    h->pending_mats.clear();
+    h->pending_ops.clear();
+    h->pending_levels.clear();
+    h->pending_per_level = false;
+    return SIEVE_OK;
+}
+
+static int sv_evaluate(sieve_core* h, sieve_shard_result_t* out) {
+    if (h->timing) SV_CUDA(cudaEventRecord(h->ev[2], h->stream));
+    SV_TRY(sv_flush(h));
+    if (h->timing) SV_CUDA(cudaEventRecord(h->ev[3], h->stream));
+    const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
+    k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, h->d_site_const, h->d_weights, h->S, h->with_const ? 1 : 0,
+                                            h->d_partials, h->d_counter, h->d_result);
+    sv_count(h);
+    SV_CUDA(cudaGetLastError());
+    if (h->timing) SV_CUDA(cudaEventRecord(h->ev[4], h->stream));
+    SV_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    if (out) {
+        out->sum_log_l = h->h_result[0];
+        out->const_lse = h->h_result[1];
+        out->const_sum = h->h_result[2];
+        out->lewis_sum = h->h_result[3];
+        out->weight_sum = h->h_result[4];
+    }
+    if (h->timing) {
+        float leaf = 0, prune = 0, red = 0;
+        if (h->leaf_timed) cudaEventElapsedTime(&leaf, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&prune, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&red, h->ev[3], h->ev[4]);
+        h->last_ms[0] = leaf;
+        h->last_ms[1] = prune;
+        h->last_ms[2] = red;
+        h->last_ms[3] = leaf + prune + red;
+        h->leaf_timed = false;
+    }
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_evaluate(sieve_core_t* h, sieve_shard_result_t* out) {
+    SV_REQUIRE(h, "null handle");
+    SV_CUDA(cudaSetDevice(h->device));
+    int r = sv_evaluate(h, out);
+    h->last_launches = h->step_launches;
+    h->step_launches = 0;
+    return r;
+}
+
+extern "C" int sieve_step(sieve_core_t* h, int32_t update_leaves, int32_t n_matrices, const int32_t* matrix_nodes,
+                          const double* P, int32_t n_ops, const int32_t* ops, sieve_shard_result_t* out) {
+    SV_REQUIRE(h, "null handle");
+    SV_CUDA(cudaSetDevice(h->device));
+    if (update_leaves) SV_TRY(sieve_update_leaves(h, 1));
+    SV_TRY(sieve_set_matrices(h, n_matrices, matrix_nodes, P, 1));
+    SV_TRY(sieve_update_nodes(h, n_ops, ops, nullptr, 0, SIEVE_UPDATE_FLIP));
+    int r = sv_evaluate(h, out);
+    h->last_launches = h->step_launches;
+    h->step_launches = 0;
+    return r;
+}
+
+extern "C" int sieve_replay(sieve_core_t* h, int32_t update_leaves, int32_t n_times) {
+    SV_REQUIRE(h && n_times >= 0, "sieve_replay: bad argument");
+    SV_CUDA(cudaSetDevice(h->device));
+    if (!h->pending_ops.empty() || !h->pending_mats.empty())
+        return sv_fail(SIEVE_ERR_STATE, "sieve_replay: there is un-launched work queued");
+    if (h->last_no == 0) return sv_fail(SIEVE_ERR_STATE, "sieve_replay: nothing was staged yet");
+    const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
+    for (int i = 0; i < n_times; i++) {
+        if (update_leaves) {
+            h->dm_dirty = h->cov_dirty = true;  // a parameter proposal rebuilds the tables
+            SV_TRY(sv_launch_leaves(h));
+        }
+        SV_TRY(sv_launch_staged(h));
+        k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, h->d_site_const, h->d_weights, h->S,
+                                                h->with_const ? 1 : 0, h->d_partials, h->d_counter, h->d_result);
+        sv_count(h);
+    }
+    SV_CUDA(cudaGetLastError());
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_get_site_log_likelihoods(sieve_core_t* h, double* out_l, double* out_c) {
+    SV_REQUIRE(h && out_l, "null argument");
+    SV_CUDA(cudaSetDevice(h->device));
+    SV_TRY(sv_flush(h));
+    SV_CUDA(cudaMemcpyAsync(out_l, h->d_site_logl, sizeof(double) * h->S, cudaMemcpyDeviceToHost, h->stream));
+    if (out_c) SV_CUDA(cudaMemcpyAsync(out_c, h->d_site_const, sizeof(double) * h->S, cudaMemcpyDeviceToHost, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_get_result_device_ptr(sieve_core_t* h, void** d_result) {
+    SV_REQUIRE(h && d_result, "null argument");
+    *d_result = h->d_result;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t which, double* out) {
+    SV_REQUIRE(h && out && sv_node_ok(h, node), "sieve_get_node_partials: bad argument");
+    SV_REQUIRE(which == 0 || which == 1, "sieve_get_node_partials: which must be 0 or 1");
+    SV_CUDA(cudaSetDevice(h->device));
+    SV_TRY(sv_flush(h));
+    const size_t S = h->S, K = h->K, n = h->n;
+    const double *x, *sc;
+    int is_leaf = node < h->n;
+    if (is_leaf) {
+        SV_REQUIRE(which == 0, "leaves have no constant-site partials");
+        if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "leaves not computed yet");
+        x = h->d_leafX + ((size_t)h->cur_leaf * n + node) * S * 4;
+        sc = h->d_leafS + ((size_t)h->cur_leaf * n + node) * S;
+    } else {
+        const size_t slot = (size_t)h->cur_part[node] * h->n_internal + (node - n);
+        if (which == 1 && !h->with_const) return sv_fail(SIEVE_ERR_STATE, "constant-site partials are not maintained");
+        x = (which ? h->d_cpart : h->d_part) + slot * S * K * 4;
+        sc = (which ? h->d_cscale : h->d_scale) + slot * S;
+    }
+    double* d_out = nullptr;
+    const size_t N = K * S * 4;
+    SV_CUDA(cudaMalloc(&d_out, N * sizeof(double)));
+    k_export_partials<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(x, sc, (int)S, (int)K, is_leaf, h->log_mode ? 1 : 0, d_out);
+    sv_count(h);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    SV_CUDA(e);
+    return SIEVE_OK;
+}
+
+// ---- store / restore ------------------------------------------------------------------------------------------
+extern "C" int sieve_store(sieve_core_t* h) {
+    SV_REQUIRE(h, "null handle");
+    h->stored_part = h->cur_part;
+    h->stored_mat = h->cur_mat;
+    h->stored_leaf = h->cur_leaf;
+    return SIEVE_OK;
+}
+extern "C" int sieve_unstore(sieve_core_t* h) {
+    SV_REQUIRE(h, "null handle");
+    h->cur_part = h->stored_part;
+    h->cur_mat = h->stored_mat;
+    h->cur_leaf = h->stored_leaf;
+    return SIEVE_OK;
+}
+extern "C" int sieve_restore(sieve_core_t* h) {
+    SV_REQUIRE(h, "null handle");
+    h->cur_part.swap(h->stored_part);
+    h->cur_mat.swap(h->stored_mat);
+    std::swap(h->cur_leaf, h->stored_leaf);
+    // after a rejected parameter proposal the tables hold the rejected values; they are compared with the values of
+    // the next sieve_set_leaf_params at the next leaf update, so nothing has to be rebuilt here
+    return SIEVE_OK;
+}
+
+// ---- combining shards (host arithmetic on a handful of doubles) --------------------------------------------------
+extern "C" double sieve_combine_shards(const sieve_shard_result_t* sh, int32_t n_shards, int32_t asc_mode, double M) {
+    if (!sh || n_shards <= 0) return NAN;
+    double logP = 0.0;
+    for (int i = 0; i < n_shards; i++) logP += sh[i].sum_log_l;  // ThreadedScsTreeLikelihood.java:371-373
+    double loci = 0.0;
+    for (int i = 0; i < n_shards; i++) loci += sh[i].weight_sum;
+    switch (asc_mode) {
+        case SIEVE_ASC_FELSENSTEIN_MEAN: {
+            // one shard: ScsAlignment.java:768-772; several: :811-815 -- logSumExp over the per-shard log-sums
+            double mx = sh[0].const_lse;
+            for (int i = 1; i < n_shards; i++) mx = sh[i].const_lse > mx ? sh[i].const_lse : mx;
+            double s = 0.0;
+            for (int i = 0; i < n_shards; i++) s += exp(sh[i].const_lse - mx);
+            logP += (log(s) + mx - log(loci)) * M;
+            break;
+        }
+        case SIEVE_ASC_FELSENSTEIN_GEOMETRIC: {
+            double s = 0.0;
+            for (int i = 0; i < n_shards; i++) s += sh[i].const_sum;
+            // :773-776 divides by the number of loci for one worker, :816 by the number of workers for several
+            logP += n_shards == 1 ? s * M / loci : s * M / (double)n_shards;
+            break;
+        }
+        case SIEVE_ASC_LEWIS:
+            for (int i = 0; i < n_shards; i++) logP += sh[i].lewis_sum;  // :746-752, applied per worker
+            break;
+        default:
+            break;
+    }
+    return logP;
+}
+
+extern "C" void sieve_pattern_points(int32_t n_sites, int32_t n_shards, int32_t* points) {
+    points[0] = 0;
+    for (int i = 0; i < n_shards; i++) points[i + 1] = points[i] + n_sites / n_shards + (i < n_sites % n_shards ? 1 : 0);
+}
+
+// ---- instrumentation ------------------------------------------------------------------------------------------
+extern "C" int sieve_enable_timing(sieve_core_t* h, int32_t on) {
+    SV_REQUIRE(h, "null handle");
+    h->timing = on != 0;
+    return SIEVE_OK;
+}
+extern "C" int sieve_last_timing(sieve_core_t* h, float* out_ms4, int32_t* out_launches) {
+    SV_REQUIRE(h, "null handle");
+    if (out_ms4) memcpy(out_ms4, h->last_ms, sizeof(h->last_ms));
+    if (out_launches) *out_launches = h->last_launches;
+    return SIEVE_OK;
+}
+extern "C" int sieve_launch_count(sieve_core_t* h, uint64_t* out) {
+    SV_REQUIRE(h && out, "null argument");
+    *out = h->launches;
+    return SIEVE_OK;
+}
+extern "C" int sieve_get_stream(sieve_core_t* h, void** out) {
+    SV_REQUIRE(h && out, "null argument");
+    *out = (void*)h->stream;
+    return SIEVE_OK;
+}

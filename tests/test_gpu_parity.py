@@ -1,0 +1,400 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle on the same seeded inputs, and with the committed
+golden fixtures.  Tolerances (BASELINE.json north_star): per-site log-likelihood 1e-12 relative, total 1e-9 relative."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from sieve_b200 import substmodel  # noqa: E402
+from sieve_b200.data import synthetic  # noqa: E402
+from sieve_b200.tree import caterpillar, fixture_9_leaves, random_coalescent  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SITE_RTOL = 1e-12
+TOTAL_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def core_mod():
+    from sieve_b200 import _lib, core
+    _lib.lib()
+    assert _lib.lib().sieve_device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return core
+
+
+def _setup(core_mod, counts, tree, sf, params, mats, props, asc=False, use_log=True, single=True, weights=None, K=4):
+    S, n = counts.shape[:2]
+    c = core_mod.ScsCudaLikelihoodCore(n, S, K, 4, use_log, asc, single)
+    c.set_counts(counts)
+    c.set_pattern_weights(weights)
+    c.set_size_factors(sf)
+    c.set_leaf_params(*params)
+    c.update_leaves(for_update=False)
+    c.set_root(tree.root, props, 0)
+    nodes = [i for i in range(tree.node_count) if i != tree.root]
+    c.set_matrices(nodes, mats[nodes][:, :K], for_update=False)
+    return c
+
+
+def _oracle_eval(oracle, counts, tree, sf, params, mats, props, asc, M=0.0, weights=None, single=True, use_log=True,
+                 T=1):
+    P = oracle.leaf_params(*params, single_ado=single, use_log=use_log)
+    return oracle.full_eval(oracle.counts5(counts), sf, P, tree.ops(), mats, props, tree.root, asc, M, T, weights=weights)
+
+
+PARAMS = (0.3, 50.0, 50.0, 0.008, 150.0, 2.0)
+
+
+def _close(a, b, rtol):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.all(np.abs(a - b) <= rtol * np.abs(b)), (np.abs(a - b) / np.abs(b)).max()
+
+
+@pytest.mark.parametrize("tag", ["cells10", "cells40"])
+def test_golden_example_data(core_mod, tag):
+    z = np.load(os.path.join(GOLD, tag + ".npz"))
+    g = json.load(open(os.path.join(GOLD, "golden_" + tag + ".json")))
+    patterns, weights = z["patterns"], z["weights"]
+    n, S, M = g["n"], g["S"], g["M"]
+    tree = caterpillar(n, 0.0, 1.0)
+    tree.height *= g["tree_scale"]
+    mats = np.array(g["matrices"])
+    props = np.array(g["proportions"])
+    c = _setup(core_mod, patterns, tree, np.array(g["size_factors"]), PARAMS, mats, props, asc=True, weights=weights)
+    c.update_nodes(tree.ops(), flip=False)
+    r = c.evaluate()
+    sl, sc = c.site_log_likelihoods()
+    _close(sl, g["site_logl"], SITE_RTOL)
+    _close(sc, g["site_log_const"], SITE_RTOL)
+    for asc in ("none", "felsenstein_mean", "felsenstein_geometric", "lewis"):
+        got = core_mod.combine_shards([r], asc, M)
+        assert abs(got - g["logP_" + asc]) <= TOTAL_RTOL * abs(g["logP_" + asc]), (asc, got, g["logP_" + asc])
+    # leaf partials of cell 0, reference layout [K][S][G] with the K copies identical (ScsBeerLikelihoodCore.java:418-423)
+    lp = c.get_node_partials(0)
+    ref = np.array(g["leaf0_log_partials"])
+    for k in range(4):
+        np.testing.assert_allclose(lp[k], ref, rtol=1e-12, atol=1e-12)
+    # device size factors == oracle's (SeqCovModelInterface.java:291-351)
+    sf, st = c.compute_size_factors(0)
+    np.testing.assert_allclose(sf, g["size_factors"], rtol=1e-13)
+    np.testing.assert_allclose(st, g["cov_stats"], rtol=1e-10)
+    c.close()
+
+
+@pytest.mark.parametrize("asc,use_log,single,K", [("none", True, True, 4), ("felsenstein_mean", True, True, 4),
+                                                 ("lewis", True, False, 4), ("felsenstein_mean", False, True, 4),
+                                                 ("felsenstein_geometric", True, True, 2), ("none", True, True, 1)])
+def test_full_evaluation_matches_oracle(core_mod, oracle, asc, use_log, single, K):
+    d = synthetic(23, 700, seed=5)
+    counts, tree = d["counts"], d["tree"]
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    rates, props = substmodel.gamma_category_rates(0.8, K)
+    mats = substmodel.node_matrices(tree, rates)
+    M = 5000.0
+    c = _setup(core_mod, counts, tree, sf, PARAMS, mats, props, asc=(asc != "none"), use_log=use_log, single=single, K=K)
+    c.update_nodes(tree.ops(), flip=False)
+    r = c.evaluate()
+    sl, sc = c.site_log_likelihoods()
+    logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, asc, M, single=single, use_log=True)
+    _close(sl, osl, SITE_RTOL)
+    if asc != "none":
+        _close(sc, osc, SITE_RTOL)
+    got = core_mod.combine_shards([r], asc, M)
+    assert abs(got - logp) <= TOTAL_RTOL * abs(logp)
+    # every internal node's partials, reference layout, log space
+    if use_log:
+        P = oracle.leaf_params(*PARAMS, single_ado=single)
+        oc = oracle.Core(tree.node_count, tree.n, 700, K, 4, True)
+        c5 = oracle.counts5(counts)
+        for i in range(tree.n):
+            oc.set_node_partials(i, oracle.leaf_likelihood(c5, i, sf[i], P))
+        for node in range(tree.node_count):
+            if node != tree.root:
+                for k in range(K):
+                    oc.set_node_matrix(node, k, mats[node, k])
+        for p, c1, c2 in tree.ops():
+            oc.calculate_partials(c1, c1 < tree.n, c2, 0 <= c2 < tree.n, p, 0)
+        for node in (tree.n, tree.n + 7, tree.root - 1, tree.root):
+            np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=1e-11)
+            if asc != "none":
+                np.testing.assert_allclose(c.get_node_partials(node, const=True), oc.get_const_partials(node),
+                                           rtol=2e-12, atol=1e-11)
+    c.close()
+
+
+def test_leaf_kernel_all_cells_and_edge_counts(core_mod, oracle, monkeypatch):
+    rng = np.random.default_rng(8)
+    S, n = 300, 5
+    counts = np.zeros((S, n, 4), dtype=np.int32)
+    cov = rng.integers(0, 90, size=(S, n))
+    cov[:10] = 0                                   # empty sites: the 1.0 quirk of DirichletMultinomial.java:29-30
+    cov[10:20, 0] = rng.integers(3000, 9000, 10)   # beyond the lookup tables (direct evaluation path)
+    alt = (cov * rng.random((S, n)) * (rng.random((S, n)) < 0.4)).astype(np.int64)
+    counts[..., 0] = alt
+    counts[..., 1] = ((cov - alt) * 0.1 * rng.random((S, n))).astype(np.int64)
+    counts[..., 2] = ((cov - alt - counts[..., 1]) * 0.05 * rng.random((S, n))).astype(np.int64)
+    counts[..., 3] = cov
+    c5 = oracle.counts5(counts)
+    sf, _ = oracle.size_factors(c5)
+    tree = caterpillar(n)
+    for single in (True, False):
+        for params in (PARAMS, (0.05, 20.0, 80.0, 0.03, 60.0, 5.0)):
+            c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, False, single)
+            c.set_counts(counts)
+            c.set_size_factors(sf)
+            c.set_leaf_params(*params)
+            c.update_leaves(for_update=False)
+            P = oracle.leaf_params(*params, single_ado=single)
+            for j in range(n):
+                ref = oracle.leaf_likelihood(c5, j, sf[j], P)
+                got = c.get_node_partials(j)[0]
+                np.testing.assert_allclose(got, ref, rtol=2e-13, atol=2e-12)
+            c.close()
+
+
+def test_small_table_cap_uses_direct_path(core_mod, oracle, monkeypatch):
+    monkeypatch.setenv("SIEVE_B200_TABLE_CAP", "16")
+    d = synthetic(6, 200, seed=9)
+    counts = d["counts"]
+    c5 = oracle.counts5(counts)
+    sf, _ = oracle.size_factors(c5)
+    c = core_mod.ScsCudaLikelihoodCore(6, 200, 4, 4, True, False, True)
+    c.set_counts(counts)
+    c.set_size_factors(sf)
+    c.set_leaf_params(*PARAMS)
+    c.update_leaves(for_update=False)
+    P = oracle.leaf_params(*PARAMS)
+    for j in range(6):
+        np.testing.assert_allclose(c.get_node_partials(j)[0], oracle.leaf_likelihood(c5, j, sf[j], P), rtol=2e-13, atol=2e-12)
+    c.close()
+
+
+def test_nan_propagates_for_zero_error_rate(core_mod):
+    # logBeta(0, c) is NaN in the reference (SURVEY.md section 8a' item 2): effSeqErrRate == 0 with an alt read
+    counts = np.zeros((4, 2, 4), dtype=np.int32)
+    counts[..., 0] = 3
+    counts[..., 3] = 20
+    c = core_mod.ScsCudaLikelihoodCore(2, 4, 4, 4, True, False, True)
+    c.set_counts(counts)
+    c.set_size_factors(np.ones(2))
+    c.set_leaf_params(0.3, 50.0, 50.0, 0.0, 150.0, 2.0)
+    c.update_leaves(for_update=False)
+    assert np.isnan(c.get_node_partials(0)).all()
+    c.close()
+
+
+def test_per_level_launches_equal_single_walk(core_mod, oracle):
+    d = synthetic(40, 333, seed=12)
+    counts, tree = d["counts"], d["tree"]
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    out = []
+    for per_level in (False, True):
+        c = _setup(core_mod, counts, tree, sf, PARAMS, mats, props, asc=True)
+        if per_level:
+            ops, off = tree.ops_by_level()
+            c.update_nodes(ops, off, flip=False, per_level=True)
+        else:
+            c.update_nodes(tree.ops(), flip=False)
+        r = c.evaluate()
+        out.append((r.sum_log_l, r.const_lse) + c.site_log_likelihoods())
+        c.close()
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    np.testing.assert_array_equal(out[0][3], out[1][3])
+
+
+def test_reference_call_sequence_and_store_restore(core_mod, oracle):
+    """The traverse() call sequence, node by node, then a proposal that is rejected and one that is accepted."""
+    rng = np.random.default_rng(3)
+    tree = fixture_9_leaves()
+    d = synthetic(9, 257, seed=4, tree=tree)
+    counts = d["counts"]
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    n = tree.n
+    c = core_mod.ScsCudaLikelihoodCore(n, 257, 4, 4, True, True, True)
+    c.set_counts(counts)
+    c.set_size_factors(sf)
+    c.set_leaf_params(*PARAMS)
+    c.update_leaves(for_update=False)
+    c.set_root(tree.root, props, 0)
+    for node in range(tree.node_count):
+        if node != tree.root:
+            c.set_node_matrix_for_update(node)
+            for k in range(4):
+                c.set_node_matrix(node, k, mats[node, k])
+    for p, c1, c2 in tree.ops():
+        c.set_node_partials_for_update(p)
+        c.calculate_log_partials(c1, c1 < n, c2, 0 <= c2 < n, p, 0)
+    r0 = c.evaluate()
+    logp0, sl0, _ = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, "felsenstein_mean", 1000.0)
+    got0 = core_mod.combine_shards([r0], "felsenstein_mean", 1000.0)
+    assert abs(got0 - logp0) <= TOTAL_RTOL * abs(logp0)
+    site0 = c.site_log_likelihoods()[0]
+    # proposal: rescale the branch above leaf 4 (dirty chain 4 -> root)
+    c.store()
+    tree2 = tree.copy()
+    mats2 = mats.copy()
+    for k in range(4):
+        mats2[4, k] = substmodel.transition_probabilities(tree.branch_length(4) * 3.0 * rates[k]).reshape(16)
+    chain = tree.ops(tree.dirty_closure([tree.parent[4]]))
+    r1 = c.step([4], mats2[[4]], chain)
+    logp1, sl1, _ = _oracle_eval(oracle, counts, tree2, sf, PARAMS, mats2, props, "felsenstein_mean", 1000.0)
+    _close(c.site_log_likelihoods()[0], sl1, SITE_RTOL)
+    assert abs(core_mod.combine_shards([r1], "felsenstein_mean", 1000.0) - logp1) <= TOTAL_RTOL * abs(logp1)
+    # reject: index swap only; re-deriving the root from the restored buffers gives the old answer bit for bit
+    c.restore()
+    c.update_nodes(tree.ops([tree.root]), flip=False)
+    r2 = c.evaluate()
+    np.testing.assert_array_equal(c.site_log_likelihoods()[0], site0)
+    assert r2.sum_log_l == r0.sum_log_l
+    # accept path: same proposal again, then a leaf-parameter proposal on top
+    c.store()
+    c.step([4], mats2[[4]], chain)
+    c.store()
+    p2 = (0.25, 45.0, 60.0, 0.01, 120.0, 2.5)
+    c.set_leaf_params(*p2)
+    r3 = c.step([], np.zeros((0, 4, 16)), tree.ops(), update_leaves=True)
+    logp3, sl3, _ = _oracle_eval(oracle, counts, tree2, sf, p2, mats2, props, "felsenstein_mean", 1000.0)
+    _close(c.site_log_likelihoods()[0], sl3, SITE_RTOL)
+    # reject the parameter proposal: leaves flip back too
+    c.restore()
+    c.set_leaf_params(*PARAMS)
+    c.update_nodes(tree.ops([tree.root]), flip=False)
+    c.evaluate()
+    _close(c.site_log_likelihoods()[0], sl1, SITE_RTOL)
+    c.close()
+
+
+def test_incremental_updates_equal_full_recompute(core_mod, oracle):
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    rng = np.random.default_rng(21)
+    d = synthetic(60, 500, seed=22)
+    counts, tree = d["counts"], d["tree"]
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    tl = ScsTreeLikelihood(counts, tree.copy(), size_factors=sf, asc_mode="felsenstein_mean", n_background_sites=3000.0)
+    full = ScsTreeLikelihood(counts, tree.copy(), size_factors=sf, asc_mode="felsenstein_mean", n_background_sites=3000.0)
+    tl.calculate_logp()
+    for it in range(12):
+        t2 = tl.tree.copy()
+        node = int(rng.integers(tree.n, tree.node_count - 1))       # an internal non-root node: move its height
+        lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+        hi = t2.height[t2.parent[node]]
+        t2.height[node] = lo + (hi - lo) * rng.random()
+        tl.store()
+        tl.set_tree(t2, [node])
+        a = tl.calculate_logp()
+        full.has_dirt = 2
+        full.tree = t2.copy()
+        b = full.calculate_logp()
+        assert abs(a - b) <= 1e-12 * abs(b), (it, a, b)
+        np.testing.assert_allclose(tl.pattern_log_likelihoods()[0], full.pattern_log_likelihoods()[0], rtol=1e-13)
+        if it % 3 == 2:
+            tl.restore()
+            assert tl.calculate_logp() is not None
+    tl.close()
+    full.close()
+
+
+def test_site_shards_combine_like_threads(core_mod, oracle):
+    from sieve_b200.treelikelihood import ScsTreeLikelihood, ThreadedScsTreeLikelihood
+    d = synthetic(17, 403, seed=31)
+    counts, tree = d["counts"], d["tree"]
+    M = 7777.0
+    for asc in ("none", "felsenstein_mean", "lewis"):
+        one = ScsTreeLikelihood(counts, tree.copy(), asc_mode=asc, n_background_sites=M)
+        a = one.calculate_logp()
+        for T in (2, 3, 8):
+            many = ThreadedScsTreeLikelihood(counts, tree.copy(), T, asc_mode=asc, n_background_sites=M)
+            b = many.calculate_logp()
+            assert abs(a - b) <= 1e-11 * abs(a), (asc, T, a, b)
+            np.testing.assert_array_equal(many.pattern_log_likelihoods()[0], one.pattern_log_likelihoods()[0])
+            many.close()
+        sf = one.size_factors
+        logp, _, _ = _oracle_eval(oracle, counts, tree, sf, PARAMS, substmodel.node_matrices(tree, one.rates),
+                                  one.proportions, asc, M, T=3)
+        assert abs(a - logp) <= TOTAL_RTOL * abs(logp)
+        one.close()
+
+
+def test_weights_and_device_size_factors(core_mod, oracle):
+    rng = np.random.default_rng(41)
+    d = synthetic(12, 150, seed=42)
+    counts, tree = d["counts"], d["tree"]
+    w = rng.integers(1, 5, size=150).astype(np.int32)
+    c5 = oracle.counts5(counts)
+    sf_ref, st_ref = oracle.size_factors(c5, w)
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    c = core_mod.ScsCudaLikelihoodCore(12, 150, 4, 4, True, True, True)
+    c.set_counts(counts)
+    c.set_pattern_weights(w)
+    sf, st = c.compute_size_factors(0)
+    np.testing.assert_allclose(sf, sf_ref, rtol=1e-13)
+    np.testing.assert_allclose(st, st_ref, rtol=1e-10)
+    c.set_leaf_params(*PARAMS)
+    c.update_leaves(for_update=False)
+    c.set_root(tree.root, props, 0)
+    nodes = [i for i in range(tree.node_count) if i != tree.root]
+    c.set_matrices(nodes, mats[nodes], for_update=False)
+    c.update_nodes(tree.ops(), flip=False)
+    r = c.evaluate()
+    for asc in ("felsenstein_mean", "felsenstein_geometric", "lewis"):
+        logp, _, _ = _oracle_eval(oracle, counts, tree, sf_ref, PARAMS, mats, props, asc, 900.0, weights=w)
+        got = core_mod.combine_shards([r], asc, 900.0)
+        assert abs(got - logp) <= TOTAL_RTOL * abs(logp), asc
+    # zeroCovMode = 1 (SeqCovModelInterface.java:308-311)
+    sf1, _ = c.compute_size_factors(1)
+    np.testing.assert_allclose(sf1, oracle.size_factors(c5, w, 1)[0], rtol=1e-13)
+    c.close()
+
+
+def test_argument_errors_are_status_codes(core_mod):
+    from sieve_b200 import _lib
+    with pytest.raises(_lib.SieveError) as e:
+        core_mod.ScsCudaLikelihoodCore(4, 10, 4, 3)
+    assert e.value.code == _lib.ERR_INVALID
+    c = core_mod.ScsCudaLikelihoodCore(4, 10)
+    with pytest.raises(_lib.SieveError) as e:
+        c.update_leaves()
+    assert e.value.code == _lib.ERR_STATE
+    with pytest.raises(_lib.SieveError):
+        c.calculate_partials(0, False, 1, True, 5)    # is_leaf contradicts the numbering
+    with pytest.raises(_lib.SieveError):
+        c.set_node_matrix(99, 0, np.eye(4))
+    c.close()
+
+
+def test_mid_size_properties(core_mod):
+    """Size-independent checks at a size the oracle is not asked to follow: shard additivity, walk == per-level,
+    incremental == full, restore is exact."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood, ThreadedScsTreeLikelihood
+    d = synthetic(300, 6000, seed=77)
+    counts, tree = d["counts"], d["tree"]
+    one = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=1e5)
+    a = one.calculate_logp()
+    many = ThreadedScsTreeLikelihood(counts, tree.copy(), 4, asc_mode="felsenstein_mean", n_background_sites=1e5,
+                                     size_factors=one.size_factors)
+    b = many.calculate_logp()
+    assert np.isfinite(a) and abs(a - b) <= 1e-11 * abs(a)
+    site = one.pattern_log_likelihoods()[0]
+    one.store()
+    t2 = tree.copy()
+    node = tree.n + 5
+    lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+    t2.height[node] = 0.5 * (lo + t2.height[t2.parent[node]])
+    one.set_tree(t2, [node])
+    c = one.calculate_logp()
+    assert c != a
+    one.restore()
+    one.core.update_nodes(tree.ops([tree.root]), flip=False)
+    one.core.evaluate()
+    np.testing.assert_array_equal(one.pattern_log_likelihoods()[0], site)
+    one.close()
+    many.close()

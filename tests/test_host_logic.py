@@ -1,0 +1,106 @@
+"""Host-side pieces: the TSV grammar, pattern compression, tree bookkeeping, the rate matrix."""
+import os
+
+import numpy as np
+import pytest
+
+from sieve_b200 import data, substmodel
+from sieve_b200.tree import caterpillar, fixture_9_leaves, random_coalescent
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_rate_matrix_is_the_reference_q():
+    # Q = 0.3 * [[-1,1,0,0],[1/6,-2/3,1/6,1/3],[0,1/3,-1,2/3],[0,1/3,1/3,-2/3]]
+    Q = substmodel.rate_matrix()
+    ref = 0.3 * np.array([[-1, 1, 0, 0], [1 / 6, -2 / 3, 1 / 6, 1 / 3], [0, 1 / 3, -1, 2 / 3], [0, 1 / 3, 1 / 3, -2 / 3]])
+    np.testing.assert_allclose(Q, ref, atol=1e-15)
+    assert abs(-np.trace(Q) - 1.0) < 1e-15
+
+
+def test_transition_probabilities_against_expm():
+    from scipy.linalg import expm
+    Q = substmodel.rate_matrix()
+    for d in (0.0, 1e-6, 0.01, 0.3, 2.5, 40.0):
+        P = substmodel.transition_probabilities(d)
+        np.testing.assert_allclose(P, expm(Q * d), atol=2e-15)
+        np.testing.assert_allclose(P.sum(1), 1.0, atol=1e-14)
+
+
+def test_gamma_categories_have_mean_one():
+    for a in (0.1, 1.0, 7.3):
+        r, p = substmodel.gamma_category_rates(a, 4)
+        assert abs(r.mean() - 1.0) < 1e-14 and np.all(np.diff(r) > 0) and np.allclose(p, 0.25)
+
+
+def test_tsv_fixture_round_trip(tmp_path):
+    z = np.load(os.path.join(GOLD, "cells10.npz"))
+    counts = z["counts"]
+    S, n = counts.shape[:2]
+    p = tmp_path / "rc.tsv"
+    names = tmp_path / "names"
+    cells = ["cell%02d" % i for i in range(n)]
+    with open(p, "w") as f:
+        f.write("=numSamples=\n%d\n=numCandidateMutatedSites=\n%d\n=numBackgroundSites=\n9727\n=mutations=\n" % (n, S))
+        # written in reverse locus order and reverse cell order: the loader sorts both (DataCollector.java:477-502, 541-583)
+        for s in reversed(range(S)):
+            cols = ["T,C,G;" + ",".join(str(x) for x in counts[s, j]) for j in reversed(range(n))]
+            f.write("chr1\t%d\tA\tT\t%s\n" % (10 + s, "\t".join(cols)))
+        f.write("=background=\n0,5\t1,2\n")
+    with open(names, "w") as f:
+        for c in reversed(cells):
+            f.write(c + "\tCT\n")
+    d = data.load_read_counts_tsv(str(p), str(names))
+    np.testing.assert_array_equal(d["counts"], counts)
+    assert d["cell_names"] == cells and d["n_background_sites"] == 9727 and d["background"][0] == {0: 5, 1: 2}
+
+
+def test_tsv_errors(tmp_path):
+    p = tmp_path / "bad.tsv"
+    p.write_text("=numSamples=\n2\n=numCandidateMutatedSites=\n3\n=mutations=\nchr1\t5\tA\tT\tT,C,G;0,0,0,3\tT,C,G;1,0,0,3\n")
+    with pytest.raises(ValueError):
+        data.load_read_counts_tsv(str(p))
+
+
+def test_sort_patterns_merges_duplicates():
+    rng = np.random.default_rng(2)
+    base = rng.integers(0, 5, size=(6, 3, 4)).astype(np.int32)
+    base[..., 3] += base[..., :3].sum(-1)
+    sites = base[[0, 1, 2, 1, 0, 3, 4, 5, 0]]
+    pat, w, idx = data.sort_patterns(sites)
+    assert w.sum() == 9 and len(pat) == len(np.unique(sites.reshape(9, -1), axis=0))
+    for s in range(9):
+        np.testing.assert_array_equal(pat[idx[s]], sites[s])
+    # sorted lexicographically over (cell, [alt1, alt2, alt3, ref, cov])
+    key = np.concatenate([pat[..., :3], (pat[..., 3] - pat[..., :3].sum(-1))[..., None], pat[..., 3:]], -1).reshape(len(pat), -1)
+    assert all(tuple(key[i]) < tuple(key[i + 1]) for i in range(len(pat) - 1))
+
+
+def test_tree_shapes_and_ops():
+    t = caterpillar(5)
+    assert t.node_count == 10 and t.root == 9 and t.right[9] == -1 and t.left[9] == 8
+    np.testing.assert_allclose(t.height[5:], [1, 2, 3, 4, 5])
+    ops = t.ops()
+    assert len(ops) == 5 and tuple(ops[-1]) == (9, 8, -1)
+    seen = set(range(5))
+    for p, a, b in ops:
+        assert a in seen and (b < 0 or b in seen)
+        seen.add(p)
+    t9 = fixture_9_leaves()
+    lv_ops, off = t9.ops_by_level()
+    lv = t9.levels()
+    assert off[0] == 0 and off[-1] == len(lv_ops) == 9
+    for i in range(len(off) - 1):
+        assert len(set(lv[lv_ops[off[i]:off[i + 1], 0]])) == 1
+    assert t9.dirty_closure([t9.parent[4]]) == [12, 13, 15, 16, 17]
+    rt = random_coalescent(30, np.random.default_rng(0))
+    assert (rt.branch_lengths()[:-1] > 0).all() and len(rt.ops()) == 30
+
+
+def test_synthetic_generator_is_seeded_and_consistent():
+    a = data.synthetic(8, 64, seed=3)
+    b = data.synthetic(8, 64, seed=3)
+    np.testing.assert_array_equal(a["counts"], b["counts"])
+    c = a["counts"]
+    assert c.shape == (64, 8, 4) and (c[..., :3].sum(-1) <= c[..., 3]).all() and (c >= 0).all()
+    assert 0.0 < (c[..., 3] == 0).mean() < 0.2
