@@ -183,7 +183,7 @@ struct SvLeafArgs {
 };
 
 template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(256) k_leaf(SvLeafArgs a) {
+__global__ void __launch_bounds__(256, 4) k_leaf(SvLeafArgs a) {
     extern __shared__ double sm[];
     const int j = blockIdx.y;
     const int C = a.C;
@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(256) k_leaf(SvLeafArgs a) {
             // DirichletMultinomial.logDensity returns 1.0 for an empty site, log mode included (:29-30)
             N0 = N1 = N2 = N3 = 1.0;
         } else {
-            double A1[4], A2[4], A3[4], AR[4], B[2];
             // LP terms: table when the count is inside it, else the same formula evaluated directly
             auto lpA = [&](int cval, double (&o)[4]) {
                 const int ci = cval < 0 ? 0 : cval;
@@ -231,22 +230,29 @@ __global__ void __launch_bounds__(256) k_leaf(SvLeafArgs a) {
                     o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
                 }
             };
-            lpA(c.x, A1);
-            lpA(c.y, A2);
-            lpA(c.z, A3);
-            lpA(ref, AR);
+            // logDensity = LP(cov, a0) - (((LP(c1,a1) + LP(c2,a2)) + LP(c3,a3)) + LP(ref,a4)), summed left to right;
+            // table columns: [0] f*w1, [1] (1-eps)*w1, [2] (1/2-f)*w2, [3] f*w2
+            double T[4];
+            lpA(c.x, T);
+            double s0 = T[0], s1 = T[1], s2 = T[2], s3 = T[2];  // alt1: 0/0 f | 1/1 (1-eps) | 1/1' h | 0/1 h
+            lpA(c.y, T);
+            s0 += T[0]; s1 += T[0]; s2 += T[2]; s3 += T[3];      // alt2: f | f | h | f
+            lpA(c.z, T);
+            s0 += T[0]; s1 += T[0]; s2 += T[3]; s3 += T[3];      // alt3: f | f | f | f
+            lpA(ref, T);
+            s0 += T[1]; s1 += T[0]; s2 += T[3]; s3 += T[2];      // ref : (1-eps) | f | f | h
+            double B0, B1;
             if (cov > 0 && cov < C) {
                 const double2 u = *reinterpret_cast<const double2*>(dmB + 2 * cov);
-                B[0] = u.x; B[1] = u.y;
+                B0 = u.x; B1 = u.y;
             } else {
                 const SvD2 r = sv_dm_totals_direct(cov, a.al);
-                B[0] = r.a; B[1] = r.b;
+                B0 = r.a; B1 = r.b;
             }
-            // logDensity = LP(cov, a0) - (((LP(c1,a1) + LP(c2,a2)) + LP(c3,a3)) + LP(ref,a4)), summed left to right
-            N0 = B[0] - (((A1[0] + A2[0]) + A3[0]) + AR[1]);  // 0/0 : (f, f, f, 1-eps) w1
-            N1 = B[0] - (((A1[1] + A2[0]) + A3[0]) + AR[0]);  // 1/1 : (1-eps, f, f, f) w1
-            N2 = B[1] - (((A1[2] + A2[2]) + A3[3]) + AR[3]);  // 1/1': (h, h, f, f) w2
-            N3 = B[1] - (((A1[2] + A2[3]) + A3[3]) + AR[2]);  // 0/1 : (h, f, f, h) w2
+            N0 = B0 - s0;
+            N1 = B0 - s1;
+            N2 = B1 - s2;
+            N3 = B1 - s3;
         }
         double e[4];
         if (cov >= 0 && cov < C) {

@@ -54,120 +54,166 @@ __device__ __forceinline__ double sv_sel(const double (&x)[4], int g) {
     return g == 0 ? x[0] : (g == 1 ? x[1] : (g == 2 ? x[2] : x[3]));
 }
 
+// One child's contribution for one (site, category) lane: y = M x.  Either forwarded from registers (the child is the
+// op this warp finished last), or loaded: a leaf (category independent, read-only path) or an internal node.
+#define SV_PRUNE_THREADS 128
+#define SV_PRUNE_SITES (SV_PRUNE_THREADS / 4)
+
 template <bool WITH_CONST>
-__global__ void __launch_bounds__(256) k_prune(SvPruneArgs a) {
-    __shared__ __align__(16) double sm[2 * SV_KMAX * SV_MAT_STRIDE];
+__global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? 6 : 8) k_prune(SvPruneArgs a) {
+    // warp-private copies of the op's two K x 4 x 4 matrices: no block-wide barrier anywhere in the walk, so the
+    // warps of an SM drift apart and overlap each other's memory latency
+    __shared__ __align__(32) double sm[(SV_PRUNE_THREADS / 32) * 2 * SV_KMAX * SV_MAT_STRIDE];
     const int tid = threadIdx.x;
-    const int k = tid & 3;
-    const int site = blockIdx.x * 64 + (tid >> 2);
+    const int lane = tid & 31, warp = tid >> 5;
+    const int k = lane & 3;
+    const int site = blockIdx.x * SV_PRUNE_SITES + (tid >> 2);
     const int K = a.K;
     const size_t S = (size_t)a.S;
-    const bool active = (site < a.S) && (k < K);
     const bool site_ok = site < a.S;
+    const bool active = site_ok && (k < K);
+    double* wm = sm + warp * (2 * SV_KMAX * SV_MAT_STRIDE);
+    // staging role of this lane: matrix `which` (child 1 / 2), category kk, row q  ->  4 doubles = one 256-bit load
+    const int st_which = lane >> 4, st_kk = (lane >> 2) & 3, st_q = lane & 3;
+    double* st_dst = wm + st_which * (SV_KMAX * SV_MAT_STRIDE) + st_kk * SV_MAT_STRIDE + st_q * 4;
+    const double* M1 = wm + k * SV_MAT_STRIDE;
+    const double* M2 = wm + SV_KMAX * SV_MAT_STRIDE + k * SV_MAT_STRIDE;
+    const size_t tk = ((size_t)(site_ok ? site : 0) * K + (k < K ? k : 0)) * 4;  // offset of this lane inside a node's block
+    const size_t node_stride = S * K * 4;
 
     int i0 = a.op_begin, i1 = a.op_end;
     if (a.per_level) {
         i0 = a.op_begin + blockIdx.y;
         i1 = i0 + 1;
     }
+    // what this lane produced last: forwarded in registers when the next op consumes it (in a post-order walk at least
+    // one child of every op with an internal child is the op finished just before)
+    double fy[4] = {0, 0, 0, 0}, fcy[4] = {0, 0, 0, 0}, fls = 0.0, fcls = 0.0;
+    int fdst = -1;
+
     for (int i = i0; i < i1; i++) {
         const SvOp op = a.ops[i];
         const bool unary = op.flags & SV_OP_UNARY;
-        // ---- stage the (up to) two K x 4 x 4 transition matrices of this op in shared memory ----
-        __syncthreads();  // previous op's readers are done; its global writes are visible block-wide
-        if (tid < 128) {
-            const int which = tid >> 6, idx = tid & 63, kk = idx >> 4, e = idx & 15;
-            double v = 0.0;
-            if (kk < K && !(which == 1 && unary)) {
-                v = a.mats[(size_t)(which ? op.m2 : op.m1) * K * 16 + kk * 16 + e];
-                if (a.clamp_matrices) v = v > 0.0 ? v : SV_MIN_VALUE;
-            }
-            sm[which * (SV_KMAX * SV_MAT_STRIDE) + kk * SV_MAT_STRIDE + e] = v;
-        }
-        __syncthreads();
-        const double* M1 = sm + k * SV_MAT_STRIDE;
-        const double* M2 = sm + SV_KMAX * SV_MAT_STRIDE + k * SV_MAT_STRIDE;
-
-        double x1[4] = {0, 0, 0, 0}, x2[4] = {0, 0, 0, 0}, s1 = 0.0, s2 = 0.0;
-        double y[4], z[4];
-        double cy[4], cz[4], cs1 = 0.0, cs2 = 0.0;
-
-        // ---- child 1 ----
-        if (active) {
-            if (op.flags & SV_OP_LEAF1) {
-                sv_ld256_nc(a.leafX + ((size_t)op.c1 * S + site) * 4, x1);
-                s1 = __ldg(a.leafS + (size_t)op.c1 * S + site);
-            } else {
-                sv_ld256(a.part + (((size_t)op.c1 * S + site) * K + k) * 4, x1);
-                s1 = a.scale[(size_t)op.c1 * S + site];
-            }
-        }
-        sv_matvec(M1, x1, y);
-        if (WITH_CONST) {
-            if (op.flags & SV_OP_LEAF1) {
-                // leaf: only the constant genotype's term survives (:1432-1436)
-                const double xc = sv_sel(x1, a.const_genotype);
+        const bool leaf1 = op.flags & SV_OP_LEAF1, leaf2 = op.flags & SV_OP_LEAF2;
+        // ---- stage both matrices of the op: one 256-bit load per lane ----
+        {
+            double m[4] = {0, 0, 0, 0};
+            if (st_kk < K && !(st_which == 1 && unary))
+                sv_ld256_nc(a.mats + (size_t)(st_which ? op.m2 : op.m1) * K * 16 + st_kk * 16 + st_q * 4, m);
+            if (a.clamp_matrices) {
 #pragma unroll
-                for (int p = 0; p < 4; p++) cy[p] = M1[4 * p + a.const_genotype] * xc;
-                cs1 = s1;
-            } else {
-                double c1[4] = {0, 0, 0, 0};
-                if (active) {
-                    sv_ld256(a.cpart + (((size_t)op.c1 * S + site) * K + k) * 4, c1);
-                    cs1 = a.cscale[(size_t)op.c1 * S + site];
-                }
-                sv_matvec(M1, c1, cy);
+                for (int e = 0; e < 4; e++) m[e] = m[e] > 0.0 ? m[e] : SV_MIN_VALUE;
             }
+            __syncwarp();  // every lane is done with the previous op's matrices
+            *reinterpret_cast<double2*>(st_dst) = make_double2(m[0], m[1]);
+            *reinterpret_cast<double2*>(st_dst + 2) = make_double2(m[2], m[3]);
+            __syncwarp();
         }
-        // ---- child 2 ----
-        if (!unary) {
-            if (active) {
-                if (op.flags & SV_OP_LEAF2) {
-                    sv_ld256_nc(a.leafX + ((size_t)op.c2 * S + site) * 4, x2);
-                    s2 = __ldg(a.leafS + (size_t)op.c2 * S + site);
+        const bool fwd1 = !leaf1 && op.c1 == fdst;
+        const bool fwd2 = !unary && !leaf2 && op.c2 == fdst;
+
+        double y[4], ls;
+        double cy[4], cls = 0.0;
+        double xc1 = 0.0, xc2 = 0.0;  // the leaf children's constant-genotype entries
+        // ================= variant partials =================
+        {
+            double x[4] = {0, 0, 0, 0}, s1 = 0.0, s2 = 0.0;
+            if (fwd1) {
+#pragma unroll
+                for (int g = 0; g < 4; g++) x[g] = fy[g];
+                s1 = fls;
+            } else if (active) {
+                if (leaf1) {
+                    sv_ld256_nc(a.leafX + ((size_t)op.c1 * S + site) * 4, x);
+                    s1 = __ldg(a.leafS + (size_t)op.c1 * S + site);
                 } else {
-                    sv_ld256(a.part + (((size_t)op.c2 * S + site) * K + k) * 4, x2);
-                    s2 = a.scale[(size_t)op.c2 * S + site];
+                    sv_ld256(a.part + (size_t)op.c1 * node_stride + tk, x);
+                    s1 = a.scale[(size_t)op.c1 * S + site];
                 }
             }
-            sv_matvec(M2, x2, z);
+            if (WITH_CONST) xc1 = sv_sel(x, a.const_genotype);
+            sv_matvec(M1, x, y);
+            if (!unary) {
+                double w[4] = {0, 0, 0, 0}, z[4];
+                if (fwd2) {
 #pragma unroll
-            for (int p = 0; p < 4; p++) y[p] *= z[p];
-            if (WITH_CONST) {
-                if (op.flags & SV_OP_LEAF2) {
-                    const double xc = sv_sel(x2, a.const_genotype);
-#pragma unroll
-                    for (int p = 0; p < 4; p++) cz[p] = M2[4 * p + a.const_genotype] * xc;
-                    cs2 = s2;
-                } else {
-                    double c2[4] = {0, 0, 0, 0};
-                    if (active) {
-                        sv_ld256(a.cpart + (((size_t)op.c2 * S + site) * K + k) * 4, c2);
-                        cs2 = a.cscale[(size_t)op.c2 * S + site];
+                    for (int g = 0; g < 4; g++) w[g] = fy[g];
+                    s2 = fls;
+                } else if (active) {
+                    if (leaf2) {
+                        sv_ld256_nc(a.leafX + ((size_t)op.c2 * S + site) * 4, w);
+                        s2 = __ldg(a.leafS + (size_t)op.c2 * S + site);
+                    } else {
+                        sv_ld256(a.part + (size_t)op.c2 * node_stride + tk, w);
+                        s2 = a.scale[(size_t)op.c2 * S + site];
                     }
-                    sv_matvec(M2, c2, cz);
+                }
+                if (WITH_CONST) xc2 = sv_sel(w, a.const_genotype);
+                sv_matvec(M2, w, z);
+#pragma unroll
+                for (int p = 0; p < 4; p++) y[p] *= z[p];
+            }
+            // renormalise the site's K x 4 values by a power of two
+            double mx = sv_max4(y);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            double sh;
+            const double f = sv_pow2_rescale(mx, &sh);
+#pragma unroll
+            for (int p = 0; p < 4; p++) y[p] *= f;
+            ls = (s1 + s2) + sh;
+            if (WITH_CONST) {  // leaf children: scale of the constant twin == the leaf's scale
+                if (leaf1) cls = s1;
+                if (!unary && leaf2) cls += s2;
+            }
+        }
+        // ================= constant-site partials =================
+        if (WITH_CONST) {
+            double cs = 0.0;
+            if (leaf1) {
+                // leaf: only the constant genotype's term survives (:1432-1436)
+#pragma unroll
+                for (int p = 0; p < 4; p++) cy[p] = M1[4 * p + a.const_genotype] * xc1;
+            } else {
+                double c[4] = {0, 0, 0, 0};
+                if (fwd1) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) c[g] = fcy[g];
+                    cs = fcls;
+                } else if (active) {
+                    sv_ld256(a.cpart + (size_t)op.c1 * node_stride + tk, c);
+                    cs = a.cscale[(size_t)op.c1 * S + site];
+                }
+                sv_matvec(M1, c, cy);
+                cls += cs;
+            }
+            if (!unary) {
+                double cz[4];
+                if (leaf2) {
+#pragma unroll
+                    for (int p = 0; p < 4; p++) cz[p] = M2[4 * p + a.const_genotype] * xc2;
+                } else {
+                    double c[4] = {0, 0, 0, 0};
+                    cs = 0.0;
+                    if (fwd2) {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) c[g] = fcy[g];
+                        cs = fcls;
+                    } else if (active) {
+                        sv_ld256(a.cpart + (size_t)op.c2 * node_stride + tk, c);
+                        cs = a.cscale[(size_t)op.c2 * S + site];
+                    }
+                    sv_matvec(M2, c, cz);
+                    cls += cs;
                 }
 #pragma unroll
                 for (int p = 0; p < 4; p++) cy[p] *= cz[p];
             }
-        }
-        if (WITH_CONST && !a.clamp_matrices) {
-            // linear-mode clamp of the constant-site product (:1041-1047)
+            if (!a.clamp_matrices) {
+                // linear-mode clamp of the constant-site product (:1041-1047)
 #pragma unroll
-            for (int p = 0; p < 4; p++) cy[p] = cy[p] > 0.0 ? cy[p] : (active ? SV_MIN_VALUE : 0.0);
-        }
-
-        // ---- renormalise the site's K x 4 values by a power of two ----
-        double mx = sv_max4(y);
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        double sh;
-        const double f = sv_pow2_rescale(mx, &sh);
-#pragma unroll
-        for (int p = 0; p < 4; p++) y[p] *= f;
-        const double ls = (s1 + s2) + sh;
-        double cls = 0.0;
-        if (WITH_CONST) {
+                for (int p = 0; p < 4; p++) cy[p] = cy[p] > 0.0 ? cy[p] : (active ? SV_MIN_VALUE : 0.0);
+            }
             double cmx = sv_max4(cy);
             cmx = fmax(cmx, __shfl_xor_sync(0xffffffffu, cmx, 1));
             cmx = fmax(cmx, __shfl_xor_sync(0xffffffffu, cmx, 2));
@@ -175,17 +221,26 @@ __global__ void __launch_bounds__(256) k_prune(SvPruneArgs a) {
             const double cf = sv_pow2_rescale(cmx, &csh);
 #pragma unroll
             for (int p = 0; p < 4; p++) cy[p] *= cf;
-            cls = (cs1 + cs2) + csh;
+            cls += csh;
         }
 
         if (active) {
-            sv_st256(a.part + (((size_t)op.dst * S + site) * K + k) * 4, y);
-            if (WITH_CONST) sv_st256(a.cpart + (((size_t)op.dst * S + site) * K + k) * 4, cy);
-            if (k == 0) {
-                a.scale[(size_t)op.dst * S + site] = ls;
-                if (WITH_CONST) a.cscale[(size_t)op.dst * S + site] = cls;
+            sv_st256(a.part + (size_t)op.dst * node_stride + tk, y);
+            // every category lane writes the (identical) scale: a lane only ever re-reads what it wrote itself
+            a.scale[(size_t)op.dst * S + site] = ls;
+            if (WITH_CONST) {
+                sv_st256(a.cpart + (size_t)op.dst * node_stride + tk, cy);
+                a.cscale[(size_t)op.dst * S + site] = cls;
             }
         }
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            fy[g] = y[g];
+            if (WITH_CONST) fcy[g] = cy[g];
+        }
+        fls = ls;
+        fcls = cls;
+        fdst = op.dst;
 
         // ---- root: integrate over categories and take the log (:153-218, :255-269) ----
         if (op.flags & SV_OP_ROOT) {

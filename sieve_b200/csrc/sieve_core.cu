@@ -706,7 +706,7 @@ static int sv_launch_staged(sieve_core* h) {
         for (int k = 0; k < 4; k++) a.prop[k] = h->prop[k];
         a.site_logl = h->d_site_logl;
         a.site_const = h->d_site_const;
-        const unsigned gx = (unsigned)((h->S + 63) / 64);
+        const unsigned gx = (unsigned)((h->S + SV_PRUNE_SITES - 1) / SV_PRUNE_SITES);
         if (h->last_per_level) {
             for (size_t l = 0; l + 1 < h->last_levels.size(); l++) {
                 const int b = h->last_levels[l], e = h->last_levels[l + 1];
@@ -719,9 +719,9 @@ static int sv_launch_staged(sieve_core* h) {
                     a.op_begin = b0;
                     dim3 grid(gx, (unsigned)std::min(65535, e - b0));
                     if (h->with_const)
-                        k_prune<true><<<grid, 256, 0, h->stream>>>(a);
+                        k_prune<true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
                     else
-                        k_prune<false><<<grid, 256, 0, h->stream>>>(a);
+                        k_prune<false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
                     sv_count(h);
                 }
             }
@@ -730,9 +730,9 @@ static int sv_launch_staged(sieve_core* h) {
             a.op_end = (int)no;
             a.per_level = 0;
             if (h->with_const)
-                k_prune<true><<<gx, 256, 0, h->stream>>>(a);
+                k_prune<true><<<gx, SV_PRUNE_THREADS, 0, h->stream>>>(a);
             else
-                k_prune<false><<<gx, 256, 0, h->stream>>>(a);
+                k_prune<false><<<gx, SV_PRUNE_THREADS, 0, h->stream>>>(a);
             sv_count(h);
         }
     }
