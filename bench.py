@@ -62,6 +62,8 @@ def generate_counts_device(tree, rates, br, n, S, seed, device):
     from sieve_b200 import substmodel
     g = torch.Generator(device=device)
     g.manual_seed(seed)
+    torch.manual_seed(seed)          # _standard_gamma draws from the global generator
+    torch.cuda.manual_seed_all(seed)
     theta, t, v, eps, w1, w2 = PARAMS
     bl = tree.branch_lengths()
     cat = torch.randint(0, K_CAT, (S,), device=device, generator=g)

@@ -9,20 +9,23 @@
 #define SV_KMAX 4                              // site-rate categories handled per site by 4 adjacent lanes
 #define SV_MAT_STRIDE 18                       // doubles between the K matrices in shared memory (bank padding)
 
-// One post-order step of the pruning: parent <- (child1, child2).  Slots index the device pools.
-struct SvOp {
-    int dst;    // internal slot (buffer * n_internal + internal index) of the parent
-    int c1;     // child 1: leaf slot (buffer * n_leaves + leaf) or internal slot
-    int c2;     // child 2, unused for a unary op
-    int m1;     // matrix slot (buffer * n_nodes + node) of child 1
-    int m2;     // matrix slot of child 2
-    int flags;  // SV_OP_*
-    int pad0, pad1;
+// One post-order step of the pruning: parent <- (child1, child2).  Rows index the device pools: row = slot * S, so that
+// the address of (slot, site) is base + (row + site) * stride with no multiplication in the kernel.  The host puts a
+// child that is the destination of the immediately preceding op FIRST and flags it SV_OP_FWD1 (the product of the two
+// children's contributions commutes), so the walk can consume it from registers.
+struct __align__(16) SvOp {
+    long long dst_row;  // internal slot (buffer * n_internal + internal index) * S
+    long long c1_row;   // child 1: leaf slot (buffer * n_leaves + leaf) * S  or  internal slot * S
+    long long c2_row;   // child 2, unused for a unary op
+    int m1, m2;         // matrix slots (buffer * n_nodes + node) of the two children
+    int flags;          // SV_OP_*
+    int pad;
 };
 #define SV_OP_LEAF1 1
 #define SV_OP_LEAF2 2
 #define SV_OP_UNARY 4
 #define SV_OP_ROOT 8
+#define SV_OP_FWD1 16
 
 // 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one (site, category) state vector.
 __device__ __forceinline__ void sv_ld256(const double* p, double (&v)[4]) {
@@ -37,6 +40,27 @@ __device__ __forceinline__ void sv_st256(double* p, const double (&v)[4]) {
 }
 
 __device__ __forceinline__ double sv_max4(const double (&v)[4]) { return fmax(fmax(v[0], v[1]), fmax(v[2], v[3])); }
+
+// For NON-NEGATIVE doubles the order of the values is the order of their high words as signed integers, and the
+// renormalisation only needs the exponent of the maximum: 3 integer max instead of 3 double compares + selects.
+// (NaN has the largest high word, so it surfaces as "exponent 0x7ff" and the values are left alone.)
+__device__ __forceinline__ int sv_maxhi4(const double (&v)[4]) {
+    return max(max(__double2hiint(v[0]), __double2hiint(v[1])), max(__double2hiint(v[2]), __double2hiint(v[3])));
+}
+// factor = 2^-e and *shift_ln = e ln 2 from the high word of the maximum (see sv_pow2_rescale)
+__device__ __forceinline__ double sv_pow2_rescale_hi(int hi, double* shift_ln) {
+    const int e = (hi >> 20) & 0x7ff;
+    if (hi > 0 && e >= 1 && e <= 2045) {
+        *shift_ln = (double)(e - 1023) * SV_LN2;
+        return __hiloint2double((2046 - e) << 20, 0);
+    }
+    if (hi > 0 && e == 0) {  // subnormal maximum with a non-zero high word
+        *shift_ln = -1022.0 * SV_LN2;
+        return __hiloint2double(2045 << 20, 0);
+    }
+    *shift_ln = 0.0;  // zero (or a subnormal below 2^-1042, treated as zero), inf, NaN
+    return 1.0;
+}
 
 // Exact power-of-two renormalisation: returns factor = 2^-e and *shift_ln = e * ln 2 with e = floor(log2 mx),
 // so that mx * factor is in [1, 2).  Zero / non-finite maxima are left alone.

@@ -200,7 +200,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     }
     const size_t n = h->n, S = h->S, K = h->K;
     // does the residency fit?
-    size_t need = n * S * 16 + 2 * n * S * 40 + 2 * n * S * (K * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
+    size_t need = n * S * 16 + 2 * n * S * 40 + 2 * n * S * (SV_KMAX * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (need > free_b) {
@@ -218,13 +218,13 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     CR(sv_alloc(h, &h->d_sf, n));
     CR(sv_alloc(h, &h->d_leafX, 2 * n * S * 4));
     CR(sv_alloc(h, &h->d_leafS, 2 * n * S));
-    CR(sv_alloc(h, &h->d_part, 2 * n * S * K * 4));
+    CR(sv_alloc(h, &h->d_part, 2 * n * S * SV_KMAX * 4));
     CR(sv_alloc(h, &h->d_scale, 2 * n * S));
     if (h->with_const) {
-        CR(sv_alloc(h, &h->d_cpart, 2 * n * S * K * 4));
+        CR(sv_alloc(h, &h->d_cpart, 2 * n * S * SV_KMAX * 4));
         CR(sv_alloc(h, &h->d_cscale, 2 * n * S));
     }
-    CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * K * 16));
+    CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * SV_KMAX * 16));
     CR(sv_alloc(h, &h->d_site_logl, S));
     CR(sv_alloc(h, &h->d_site_const, S));
     CR(sv_alloc(h, &h->d_partials, (size_t)SV_REDUCE_BLOCKS));
@@ -232,7 +232,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     CR(sv_alloc(h, &h->d_result, 8));
 #undef CR
     if (cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream) != cudaSuccess ||
-        cudaMemsetAsync(h->d_mats, 0, sizeof(double) * 2 * h->n_nodes * K * 16, h->stream) != cudaSuccess ||
+        cudaMemsetAsync(h->d_mats, 0, sizeof(double) * 2 * h->n_nodes * SV_KMAX * 16, h->stream) != cudaSuccess ||
         cudaMemsetAsync(h->d_site_const, 0, sizeof(double) * S, h->stream) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_result, 8 * sizeof(double)) != cudaSuccess) {
         g_err = "sieve_create: initialisation of device buffers failed";
@@ -532,11 +532,17 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
 }
 
 // ---- matrices -------------------------------------------------------------------------------------------------
+// staging [count][K][16] -> pool [slot][4][16]; the Double.MIN_VALUE clamp of the log-space reference
+// (ScsBeerLikelihoodCore.java:1430: log(P > 0 ? P : MIN_VALUE)) is applied here, once per uploaded matrix
 __global__ void k_scatter_matrices(const double* __restrict__ stage, const int* __restrict__ slots, int count, int K,
-                                   double* __restrict__ mats) {
+                                   int clamp, double* __restrict__ mats) {
     const int i = blockIdx.x;
     const int e = threadIdx.x;
-    if (i < count && e < K * 16) mats[(size_t)slots[i] * K * 16 + e] = stage[(size_t)i * K * 16 + e];
+    if (i < count && e < K * 16) {
+        double v = stage[(size_t)i * K * 16 + e];
+        if (clamp) v = v > 0.0 ? v : SV_MIN_VALUE;
+        mats[(size_t)slots[i] * (SV_KMAX * 16) + e] = v;
+    }
 }
 
 static bool sv_node_ok(const sieve_core* h, int node) { return node >= 0 && node < h->n_nodes; }
@@ -596,32 +602,51 @@ extern "C" int sieve_set_node_partials_for_update(sieve_core_t* h, int32_t node)
 
 static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
     const int n = h->n;
+    const long long S = h->S;
     SV_REQUIRE(parent >= n && parent < h->n_nodes, "op: parent must be an internal node");
     SV_REQUIRE(c1 >= 0 && c1 < h->n_nodes && c1 != h->root, "op: bad child1");
     SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
     op->flags = 0;
-    op->dst = h->cur_part[parent] * h->n_internal + (parent - n);
-    if (c1 < n) {
-        op->flags |= SV_OP_LEAF1;
-        op->c1 = h->cur_leaf * n + c1;
-    } else
-        op->c1 = h->cur_part[c1] * h->n_internal + (c1 - n);
-    op->m1 = h->cur_mat[c1] * h->n_nodes + c1;
+    op->pad = 0;
+    op->dst_row = (long long)(h->cur_part[parent] * h->n_internal + (parent - n)) * S;
+    auto child = [&](int c, int leaf_flag, long long* row, int* m) {
+        if (c < n) {
+            op->flags |= leaf_flag;
+            *row = (long long)(h->cur_leaf * n + c) * S;
+        } else
+            *row = (long long)(h->cur_part[c] * h->n_internal + (c - n)) * S;
+        *m = h->cur_mat[c] * h->n_nodes + c;
+    };
+    child(c1, SV_OP_LEAF1, &op->c1_row, &op->m1);
     if (c2 < 0) {
         op->flags |= SV_OP_UNARY;
-        op->c2 = 0;
+        op->c2_row = 0;
         op->m2 = 0;
-    } else {
-        if (c2 < n) {
-            op->flags |= SV_OP_LEAF2;
-            op->c2 = h->cur_leaf * n + c2;
-        } else
-            op->c2 = h->cur_part[c2] * h->n_internal + (c2 - n);
-        op->m2 = h->cur_mat[c2] * h->n_nodes + c2;
-    }
+    } else
+        child(c2, SV_OP_LEAF2, &op->c2_row, &op->m2);
     if (parent == h->root) op->flags |= SV_OP_ROOT;
-    op->pad0 = op->pad1 = 0;
     return SIEVE_OK;
+}
+
+// Register forwarding for the single-launch walk: when an op consumes the destination of the op right before it, that
+// child is made child 1 (the two children's contributions commute) and flagged.
+static void sv_link_forwarding(std::vector<SvOp>& ops, bool per_level) {
+    for (size_t i = 0; i < ops.size(); i++) {
+        SvOp& op = ops[i];
+        op.flags &= ~SV_OP_FWD1;
+        if (per_level || i == 0) continue;
+        const long long prev = ops[i - 1].dst_row;
+        const bool c1_int = !(op.flags & SV_OP_LEAF1);
+        const bool c2_int = !(op.flags & SV_OP_UNARY) && !(op.flags & SV_OP_LEAF2);
+        if (c2_int && op.c2_row == prev && !(c1_int && op.c1_row == prev)) {
+            std::swap(op.c1_row, op.c2_row);
+            std::swap(op.m1, op.m2);
+            const int l1 = op.flags & SV_OP_LEAF1;
+            op.flags &= ~(SV_OP_LEAF1 | SV_OP_LEAF2);
+            if (l1) op.flags |= SV_OP_LEAF2;
+        }
+        if (!(op.flags & SV_OP_LEAF1) && op.c1_row == prev) op.flags |= SV_OP_FWD1;
+    }
 }
 
 extern "C" int sieve_calculate_partials(sieve_core_t* h, int32_t child1, int32_t is_leaf1, int32_t child2, int32_t is_leaf2,
@@ -679,13 +704,29 @@ extern "C" int sieve_set_root(sieve_core_t* h, int32_t root, const double* propo
     return SIEVE_OK;
 }
 
+static void sv_launch_prune(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
+    const bool g0 = a.const_genotype == 0 && a.root_genotype == 0;
+    if (h->with_const) {
+        if (g0)
+            k_prune<true, true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+        else
+            k_prune<true, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+    } else {
+        if (g0)
+            k_prune<false, true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+        else
+            k_prune<false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+    }
+}
+
 // launches scatter + pruning for what is staged on the device
 static int sv_launch_staged(sieve_core* h) {
     const int K = h->K;
     const size_t nm = h->last_nm, no = h->last_no, off_mv = h->last_off_mv, off_ms = h->last_off_ms, off_ops = 0;
     if (nm) {
         k_scatter_matrices<<<(unsigned)nm, 64, 0, h->stream>>>((const double*)(h->d_stage + off_mv),
-                                                              (const int*)(h->d_stage + off_ms), (int)nm, K, h->d_mats);
+                                                              (const int*)(h->d_stage + off_ms), (int)nm, K,
+                                                              h->log_mode ? 1 : 0, h->d_mats);
         sv_count(h);
     }
     if (no) {
@@ -700,7 +741,7 @@ static int sv_launch_staged(sieve_core* h) {
         a.ops = (const SvOp*)(h->d_stage + off_ops);
         a.S = h->S;
         a.K = K;
-        a.clamp_matrices = h->log_mode ? 1 : 0;
+        a.linear_const_clamp = h->log_mode ? 0 : 1;
         a.const_genotype = h->const_genotype;
         a.root_genotype = h->root_genotype;
         for (int k = 0; k < 4; k++) a.prop[k] = h->prop[k];
@@ -718,10 +759,7 @@ static int sv_launch_staged(sieve_core* h) {
                 for (int b0 = b; b0 < e; b0 += 65535) {
                     a.op_begin = b0;
                     dim3 grid(gx, (unsigned)std::min(65535, e - b0));
-                    if (h->with_const)
-                        k_prune<true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
-                    else
-                        k_prune<false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+                    sv_launch_prune(h, grid, a);
                     sv_count(h);
                 }
             }
@@ -729,10 +767,7 @@ static int sv_launch_staged(sieve_core* h) {
             a.op_begin = 0;
             a.op_end = (int)no;
             a.per_level = 0;
-            if (h->with_const)
-                k_prune<true><<<gx, SV_PRUNE_THREADS, 0, h->stream>>>(a);
-            else
-                k_prune<false><<<gx, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            sv_launch_prune(h, dim3(gx), a);
             sv_count(h);
         }
     }
@@ -753,6 +788,7 @@ static int sv_flush(sieve_core* h) {
     const size_t total = off_ms + nm * sizeof(int);
     SV_TRY(sv_ensure_stage(h, total));
     SV_CUDA(cudaStreamSynchronize(h->stream));  // the previous step may still be reading the staging buffer
+    sv_link_forwarding(h->pending_ops, h->pending_per_level);
     if (no) memcpy(h->h_stage + off_ops, h->pending_ops.data(), no * sizeof(SvOp));
     for (size_t i = 0; i < nm; i++) {
         memcpy(h->h_stage + off_mv + i * K * 16 * sizeof(double), h->pending_mats[i].v, K * 16 * sizeof(double));
@@ -882,7 +918,7 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     } else {
         const size_t slot = (size_t)h->cur_part[node] * h->n_internal + (node - n);
         if (which == 1 && !h->with_const) return sv_fail(SIEVE_ERR_STATE, "constant-site partials are not maintained");
-        x = (which ? h->d_cpart : h->d_part) + slot * S * K * 4;
+        x = (which ? h->d_cpart : h->d_part) + slot * S * SV_KMAX * 4;
         sc = (which ? h->d_cscale : h->d_scale) + slot * S;
     }
     double* d_out = nullptr;
