@@ -1,0 +1,44 @@
+package beast.evolution.likelihood;
+
+/**
+ * Native entry points of libsieve_b200.so (include/sieve_b200.h), one static method per C function.
+ * The JNI glue (java/jni/sieve_jni.c) pins the Java arrays and forwards; it contains no logic.
+ * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no JDK (SURVEY.md section 0).
+ */
+public final class SieveB200 {
+    static {
+        System.loadLibrary("sieve_b200_jni"); // links against libsieve_b200.so
+    }
+
+    private SieveB200() {}
+
+    public static final int FLAG_LOG_PARTIALS = 1, FLAG_CONST_PARTIALS = 2, FLAG_SINGLE_ADO = 4;
+    public static final int UPDATE_FLIP = 1, UPDATE_PER_LEVEL = 2;
+
+    /** sieve_create; returns the opaque handle; throws RuntimeException(sieve_last_error()) on failure */
+    public static native long create(int nLeaves, int nSites, int nCategories, int nStates, int flags, int device);
+    public static native void destroy(long h);
+    /** counts: [site][cell][5] flattened, exactly ScsAlignment.sitePatterns (tupleLen = 5) */
+    public static native void setCounts(long h, int[] counts, int tupleLen);
+    public static native void setPatternWeights(long h, int[] weights);
+    public static native void computeSizeFactors(long h, int zeroCovMode, double[] outSizeFactors, double[] outStats);
+    public static native void setSizeFactors(long h, double[] sizeFactors);
+    public static native void setLeafParams(long h, double adoRate, double allelicSeqCov, double allelicSeqCovRawVar,
+                                            double effSeqErrRate, double shapeCtrl1, double shapeCtrl2);
+    public static native void updateLeaves(long h, boolean forUpdate);
+    public static native void setNodeMatrixForUpdate(long h, int node);
+    public static native void setNodeMatrix(long h, int node, int category, double[] p16);
+    public static native void setNodePartialsForUpdate(long h, int node);
+    public static native void calculatePartials(long h, int child1, boolean isLeaf1, int child2, boolean isLeaf2,
+                                                int parent, int constGenotype);
+    public static native void setRoot(long h, int root, double[] proportions, int rootGenotype);
+    /** out[5] = {sumLogL, constLse, constSum, lewisSum, weightSum} */
+    public static native void evaluate(long h, double[] out5);
+    public static native void getSiteLogLikelihoods(long h, double[] outLogL, double[] outLogConst);
+    public static native void getNodePartials(long h, int node, int which, double[] out);
+    public static native void store(long h);
+    public static native void unstore(long h);
+    public static native void restore(long h);
+    /** shards: nShards x 5 doubles in worker order; ascMode 0 none, 1 felsenstein/mean, 2 felsenstein/geometric, 3 lewis */
+    public static native double combineShards(double[] shards, int nShards, int ascMode, double nBackgroundSites);
+}

@@ -1,0 +1,107 @@
+/* JNI glue for java/beast/evolution/likelihood/SieveB200.java: pins the arrays, forwards to include/sieve_b200.h,
+ * turns a non-zero status into a RuntimeException carrying sieve_last_error().  No logic lives here.
+ * Build (needs a JDK, absent from this repository's image):
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include sieve_jni.c \
+ *       -L../../sieve_b200 -lsieve_b200 -o libsieve_b200_jni.so
+ */
+#ifdef SIEVE_HAVE_JNI
+#include <jni.h>
+#include "sieve_b200.h"
+
+#define H(h) ((sieve_core_t *)(intptr_t)(h))
+static void chk(JNIEnv *e, int rc) {
+    if (rc != SIEVE_OK) (*e)->ThrowNew(e, (*e)->FindClass(e, "java/lang/RuntimeException"), sieve_last_error());
+}
+#define FN(name) Java_beast_evolution_likelihood_SieveB200_##name
+
+JNIEXPORT jlong JNICALL FN(create)(JNIEnv *e, jclass c, jint nl, jint ns, jint k, jint g, jint flags, jint dev) {
+    sieve_config_t cfg = {nl, ns, k, g, (uint32_t)flags, dev};
+    sieve_core_t *h = NULL;
+    chk(e, sieve_create(&cfg, &h));
+    return (jlong)(intptr_t)h;
+}
+JNIEXPORT void JNICALL FN(destroy)(JNIEnv *e, jclass c, jlong h) { chk(e, sieve_destroy(H(h))); }
+JNIEXPORT void JNICALL FN(setCounts)(JNIEnv *e, jclass c, jlong h, jintArray a, jint tl) {
+    jint *p = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    int rc = sieve_set_counts(H(h), (const int32_t *)p, tl);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(setPatternWeights)(JNIEnv *e, jclass c, jlong h, jintArray a) {
+    jint *p = a ? (*e)->GetPrimitiveArrayCritical(e, a, NULL) : NULL;
+    int rc = sieve_set_pattern_weights(H(h), (const int32_t *)p);
+    if (a) (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(computeSizeFactors)(JNIEnv *e, jclass c, jlong h, jint z, jdoubleArray sf, jdoubleArray st) {
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, sf, NULL);
+    jdouble *q = st ? (*e)->GetPrimitiveArrayCritical(e, st, NULL) : NULL;
+    int rc = sieve_compute_size_factors(H(h), z, p, q);
+    if (st) (*e)->ReleasePrimitiveArrayCritical(e, st, q, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, sf, p, 0);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(setSizeFactors)(JNIEnv *e, jclass c, jlong h, jdoubleArray a) {
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    int rc = sieve_set_size_factors(H(h), p);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(setLeafParams)(JNIEnv *e, jclass c, jlong h, jdouble th, jdouble t, jdouble v, jdouble eps,
+                                         jdouble w1, jdouble w2) {
+    sieve_leaf_params_t p = {th, t, v, eps, w1, w2};
+    chk(e, sieve_set_leaf_params(H(h), &p));
+}
+JNIEXPORT void JNICALL FN(updateLeaves)(JNIEnv *e, jclass c, jlong h, jboolean f) { chk(e, sieve_update_leaves(H(h), f)); }
+JNIEXPORT void JNICALL FN(setNodeMatrixForUpdate)(JNIEnv *e, jclass c, jlong h, jint n) {
+    chk(e, sieve_set_node_matrix_for_update(H(h), n));
+}
+JNIEXPORT void JNICALL FN(setNodeMatrix)(JNIEnv *e, jclass c, jlong h, jint n, jint k, jdoubleArray a) {
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    int rc = sieve_set_node_matrix(H(h), n, k, p);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(setNodePartialsForUpdate)(JNIEnv *e, jclass c, jlong h, jint n) {
+    chk(e, sieve_set_node_partials_for_update(H(h), n));
+}
+JNIEXPORT void JNICALL FN(calculatePartials)(JNIEnv *e, jclass c, jlong h, jint c1, jboolean l1, jint c2, jboolean l2,
+                                             jint p, jint cg) {
+    chk(e, sieve_calculate_partials(H(h), c1, l1, c2, l2, p, cg));
+}
+JNIEXPORT void JNICALL FN(setRoot)(JNIEnv *e, jclass c, jlong h, jint r, jdoubleArray a, jint rg) {
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    int rc = sieve_set_root(H(h), r, p, rg);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(evaluate)(JNIEnv *e, jclass c, jlong h, jdoubleArray a) {
+    sieve_shard_result_t r;
+    int rc = sieve_evaluate(H(h), &r);
+    if (rc == SIEVE_OK) (*e)->SetDoubleArrayRegion(e, a, 0, 5, (const jdouble *)&r);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(getSiteLogLikelihoods)(JNIEnv *e, jclass c, jlong h, jdoubleArray a, jdoubleArray b) {
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    jdouble *q = b ? (*e)->GetPrimitiveArrayCritical(e, b, NULL) : NULL;
+    int rc = sieve_get_site_log_likelihoods(H(h), p, q);
+    if (b) (*e)->ReleasePrimitiveArrayCritical(e, b, q, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, p, 0);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(getNodePartials)(JNIEnv *e, jclass c, jlong h, jint n, jint w, jdoubleArray a) {
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    int rc = sieve_get_node_partials(H(h), n, w, p);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, p, 0);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(store)(JNIEnv *e, jclass c, jlong h) { chk(e, sieve_store(H(h))); }
+JNIEXPORT void JNICALL FN(unstore)(JNIEnv *e, jclass c, jlong h) { chk(e, sieve_unstore(H(h))); }
+JNIEXPORT void JNICALL FN(restore)(JNIEnv *e, jclass c, jlong h) { chk(e, sieve_restore(H(h))); }
+JNIEXPORT jdouble JNICALL FN(combineShards)(JNIEnv *e, jclass c, jdoubleArray a, jint n, jint mode, jdouble M) {
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    double r = sieve_combine_shards((const sieve_shard_result_t *)p, n, mode, M);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
+    return r;
+}
+#endif /* SIEVE_HAVE_JNI */

@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libsieve_b200.so")
+SO_PATH = os.environ.get("SIEVE_B200_LIB") or os.path.join(_HERE, "libsieve_b200.so")   # override: kernel-variant experiments only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sieve_b200.h")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, 1, 2, 3, 4

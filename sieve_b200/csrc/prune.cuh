@@ -55,25 +55,56 @@ __device__ __forceinline__ double sv_sel(const double (&x)[4], int g) {
 }
 
 #define SV_PRUNE_THREADS 128
-#define SV_PRUNE_SITES (SV_PRUNE_THREADS / 4)
-#ifndef SV_PRUNE_MINB_CONST
-#define SV_PRUNE_MINB_CONST 5
+#ifndef SV_PRUNE_PREFETCH
+#define SV_PRUNE_PREFETCH 1  // ops ahead whose (non-forwarded) children are prefetched into L2; 0 = off
 #endif
+__device__ __forceinline__ void sv_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef SV_PRUNE_NS
+#define SV_PRUNE_NS 2  // sites per lane: the op's matrices are read from shared memory once and applied to NS sites
+#endif
+#define SV_PRUNE_SITES ((SV_PRUNE_THREADS / 4) * SV_PRUNE_NS)
+#ifndef SV_PRUNE_MINB_CONST
+#define SV_PRUNE_MINB_CONST 3
+#endif
+#ifndef SV_PRUNE_MINB
+#define SV_PRUNE_MINB 5
+#endif
+
+// y_j = M x_j for the NS sites of a lane; every matrix element is read from shared memory once
+template <int NS>
+__device__ __forceinline__ void sv_matvec_n(const double* __restrict__ M, const double (&x)[NS][4], double (&y)[NS][4]) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const double2 a = *reinterpret_cast<const double2*>(M + 4 * p);
+        const double2 b = *reinterpret_cast<const double2*>(M + 4 * p + 2);
+#pragma unroll
+        for (int j = 0; j < NS; j++) y[j][p] = fma(b.y, x[j][3], fma(b.x, x[j][2], fma(a.y, x[j][1], a.x * x[j][0])));
+    }
+}
 
 // GENO0: root genotype == constant genotype == 0 (always so for ScsFiniteMuExtendedModel.java:37-40); the general
 // case takes the same kernel with run-time selects.
 template <bool WITH_CONST, bool GENO0>
-__global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_CONST : 8) k_prune(SvPruneArgs a) {
+__global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB) k_prune(SvPruneArgs a) {
+    constexpr int NS = SV_PRUNE_NS;
     // warp-private copies of the op's two 4 x 4 x 4 matrices: no block-wide barrier anywhere in the walk, so the
     // warps of an SM drift apart and overlap each other's memory latency
     __shared__ __align__(32) double sm[(SV_PRUNE_THREADS / 32) * 2 * SV_KMAX * SV_MAT_STRIDE];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int k = lane & 3;
-    const int site = blockIdx.x * SV_PRUNE_SITES + (tid >> 2);
-    const bool site_ok = site < a.S;
-    const bool active = site_ok && (k < a.K);
-    const long long srow = site_ok ? site : 0;
+    // a warp owns 8 * NS consecutive sites; pass j of a lane is site base + 8 j, so that every pass of the warp is one
+    // contiguous 1 KB access
+    const int site0 = blockIdx.x * SV_PRUNE_SITES + warp * (8 * NS) + (lane >> 2);
+    bool site_ok[NS], active[NS];
+    long long srow[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        const int site = site0 + 8 * j;
+        site_ok[j] = site < a.S;
+        active[j] = site_ok[j] && (k < a.K);
+        srow[j] = site_ok[j] ? site : 0;
+    }
     double* wm = sm + warp * (2 * SV_KMAX * SV_MAT_STRIDE);
     // staging role of this lane: matrix `which` (child 1 / 2), category kk, row q  ->  4 doubles = one 256-bit load
     const int st_which = lane >> 4, st_kk = (lane >> 2) & 3, st_q = lane & 3;
@@ -91,48 +122,103 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
     }
     // The previous op's result stays in registers (x / cx with scales xs / cxs): the host orders the children so that
     // a consumer of it has it as child 1 (SV_OP_FWD1).
-    double x[4] = {0, 0, 0, 0}, cx[4] = {0, 0, 0, 0}, xs = 0.0, cxs = 0.0;
+    double x[NS][4], cx[NS][4], xs[NS], cxs[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        xs[j] = cxs[j] = 0.0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) x[j][g] = cx[j][g] = 0.0;
+    }
 
     for (int i = i0; i < i1; i++) {
         const int4* opp = reinterpret_cast<const int4*>(a.ops + i);
         const int4 o0 = __ldg(opp), o1 = __ldg(opp + 1), o2 = __ldg(opp + 2);
-        const long long dst_row = ((long long)(unsigned)o0.x | ((long long)o0.y << 32)) + srow;
-        const long long c1_row = ((long long)(unsigned)o0.z | ((long long)o0.w << 32)) + srow;
-        const long long c2_row = ((long long)(unsigned)o1.x | ((long long)o1.y << 32)) + srow;
+        const long long dst_base = (long long)(unsigned)o0.x | ((long long)o0.y << 32);
+        const long long c1_base = (long long)(unsigned)o0.z | ((long long)o0.w << 32);
+        const long long c2_base = (long long)(unsigned)o1.x | ((long long)o1.y << 32);
         const int m1 = o1.z, m2 = o1.w, flags = o2.x;
         const bool unary = flags & SV_OP_UNARY;
         const bool leaf1 = flags & SV_OP_LEAF1, leaf2 = flags & SV_OP_LEAF2;
 
+#if SV_PRUNE_PREFETCH > 0
+        // ---- pull the children of a later op from DRAM into L2 while this op computes (no register cost) ----
+        if (i + SV_PRUNE_PREFETCH < i1) {
+            const int4* npp = reinterpret_cast<const int4*>(a.ops + i + SV_PRUNE_PREFETCH);
+            const int4 n0 = __ldg(npp), n1 = __ldg(npp + 1), n2 = __ldg(npp + 2);
+            const long long nc1 = (long long)(unsigned)n0.z | ((long long)n0.w << 32);
+            const long long nc2 = (long long)(unsigned)n1.x | ((long long)n1.y << 32);
+            const int nfl = n2.x;
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                if (!active[j]) continue;
+                if (!(nfl & SV_OP_FWD1)) {
+                    if (nfl & SV_OP_LEAF1) {
+                        sv_prefetch_l2(a.leafX + (nc1 + srow[j]) * 4);
+                        sv_prefetch_l2(a.leafS + (nc1 + srow[j]));
+                    } else {
+                        sv_prefetch_l2(a.part + (nc1 + srow[j]) * 16 + k * 4);
+                        sv_prefetch_l2(a.scale + (nc1 + srow[j]));
+                        if (WITH_CONST) {
+                            sv_prefetch_l2(a.cpart + (nc1 + srow[j]) * 16 + k * 4);
+                            sv_prefetch_l2(a.cscale + (nc1 + srow[j]));
+                        }
+                    }
+                }
+                if (!(nfl & SV_OP_UNARY)) {
+                    if (nfl & SV_OP_LEAF2) {
+                        sv_prefetch_l2(a.leafX + (nc2 + srow[j]) * 4);
+                        sv_prefetch_l2(a.leafS + (nc2 + srow[j]));
+                    } else {
+                        sv_prefetch_l2(a.part + (nc2 + srow[j]) * 16 + k * 4);
+                        sv_prefetch_l2(a.scale + (nc2 + srow[j]));
+                        if (WITH_CONST) {
+                            sv_prefetch_l2(a.cpart + (nc2 + srow[j]) * 16 + k * 4);
+                            sv_prefetch_l2(a.cscale + (nc2 + srow[j]));
+                        }
+                    }
+                }
+            }
+        }
+#endif
         // ---- issue every global load of this op up front: matrices (one 256-bit load per lane) and children ----
         double m[4] = {0, 0, 0, 0};
         if (!(st_which == 1 && unary))
             sv_ld256_nc(a.mats + (size_t)(st_which ? m2 : m1) * (SV_KMAX * 16) + st_off, m);
-        double w[4] = {0, 0, 0, 0}, ws = 0.0;      // child 2
-        double cw[4] = {0, 0, 0, 0}, cws = 0.0;    // child 2, constant-site twin
-        if (active) {
+        double w[NS][4], ws[NS];      // child 2
+        double cw[NS][4], cws[NS];    // child 2, constant-site twin
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            ws[j] = cws[j] = 0.0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) w[j][g] = cw[j][g] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            if (!active[j]) continue;
+            const long long c1_row = c1_base + srow[j], c2_row = c2_base + srow[j];
             if (!(flags & SV_OP_FWD1)) {
                 if (leaf1) {
-                    sv_ld256_nc(a.leafX + c1_row * 4, x);
-                    xs = __ldg(a.leafS + c1_row);
+                    sv_ld256_nc(a.leafX + c1_row * 4, x[j]);
+                    xs[j] = __ldg(a.leafS + c1_row);
                 } else {
-                    sv_ld256(a.part + c1_row * 16 + k * 4, x);
-                    xs = a.scale[c1_row];
+                    sv_ld256(a.part + c1_row * 16 + k * 4, x[j]);
+                    xs[j] = a.scale[c1_row];
                     if (WITH_CONST) {
-                        sv_ld256(a.cpart + c1_row * 16 + k * 4, cx);
-                        cxs = a.cscale[c1_row];
+                        sv_ld256(a.cpart + c1_row * 16 + k * 4, cx[j]);
+                        cxs[j] = a.cscale[c1_row];
                     }
                 }
             }
             if (!unary) {
                 if (leaf2) {
-                    sv_ld256_nc(a.leafX + c2_row * 4, w);
-                    ws = __ldg(a.leafS + c2_row);
+                    sv_ld256_nc(a.leafX + c2_row * 4, w[j]);
+                    ws[j] = __ldg(a.leafS + c2_row);
                 } else {
-                    sv_ld256(a.part + c2_row * 16 + k * 4, w);
-                    ws = a.scale[c2_row];
+                    sv_ld256(a.part + c2_row * 16 + k * 4, w[j]);
+                    ws[j] = a.scale[c2_row];
                     if (WITH_CONST) {
-                        sv_ld256(a.cpart + c2_row * 16 + k * 4, cw);
-                        cws = a.cscale[c2_row];
+                        sv_ld256(a.cpart + c2_row * 16 + k * 4, cw[j]);
+                        cws[j] = a.cscale[c2_row];
                     }
                 }
             }
@@ -143,89 +229,114 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
         __syncwarp();
 
         // ================= variant partials =================
-        double y[4], z[4];
-        sv_matvec(M1, x, y);
+        double y[NS][4];
+        sv_matvec_n<NS>(M1, x, y);
         if (!unary) {
-            sv_matvec(M2, w, z);
+            double z[NS][4];
+            sv_matvec_n<NS>(M2, w, z);
 #pragma unroll
-            for (int p = 0; p < 4; p++) y[p] *= z[p];
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int p = 0; p < 4; p++) y[j][p] *= z[j][p];
         }
         // ================= constant-site partials =================
-        double cy[4];
-        double cls = 0.0;
+        double cy[NS][4];
+        double cls[NS];
+#pragma unroll
+        for (int j = 0; j < NS; j++) cls[j] = 0.0;
         if (WITH_CONST) {
             if (leaf1) {
                 // leaf: only the constant genotype's term survives (:1432-1436); its scale is the leaf's
-                const double xc = GENO0 ? x[0] : sv_sel(x, cg);
 #pragma unroll
-                for (int p = 0; p < 4; p++) cy[p] = M1[4 * p + cg] * xc;
-                cls = xs;
-            } else {
-                sv_matvec(M1, cx, cy);
-                cls = cxs;
-            }
-            if (!unary) {
-                double cz[4];
-                if (leaf2) {
-                    const double wc = GENO0 ? w[0] : sv_sel(w, cg);
+                for (int p = 0; p < 4; p++) {
+                    const double mm = M1[4 * p + cg];
 #pragma unroll
-                    for (int p = 0; p < 4; p++) cz[p] = M2[4 * p + cg] * wc;
-                    cls += ws;
-                } else {
-                    sv_matvec(M2, cw, cz);
-                    cls += cws;
+                    for (int j = 0; j < NS; j++) cy[j][p] = mm * (GENO0 ? x[j][0] : sv_sel(x[j], cg));
                 }
 #pragma unroll
-                for (int p = 0; p < 4; p++) cy[p] *= cz[p];
+                for (int j = 0; j < NS; j++) cls[j] = xs[j];
+            } else {
+                sv_matvec_n<NS>(M1, cx, cy);
+#pragma unroll
+                for (int j = 0; j < NS; j++) cls[j] = cxs[j];
+            }
+            if (!unary) {
+                double cz[NS][4];
+                if (leaf2) {
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const double mm = M2[4 * p + cg];
+#pragma unroll
+                        for (int j = 0; j < NS; j++) cz[j][p] = mm * (GENO0 ? w[j][0] : sv_sel(w[j], cg));
+                    }
+#pragma unroll
+                    for (int j = 0; j < NS; j++) cls[j] += ws[j];
+                } else {
+                    sv_matvec_n<NS>(M2, cw, cz);
+#pragma unroll
+                    for (int j = 0; j < NS; j++) cls[j] += cws[j];
+                }
+#pragma unroll
+                for (int j = 0; j < NS; j++)
+#pragma unroll
+                    for (int p = 0; p < 4; p++) cy[j][p] *= cz[j][p];
             }
             if (a.linear_const_clamp) {
 #pragma unroll
-                for (int p = 0; p < 4; p++) cy[p] = cy[p] > 0.0 ? cy[p] : (active ? SV_MIN_VALUE : 0.0);
+                for (int j = 0; j < NS; j++)
+#pragma unroll
+                    for (int p = 0; p < 4; p++) cy[j][p] = cy[j][p] > 0.0 ? cy[j][p] : (active[j] ? SV_MIN_VALUE : 0.0);
             }
         }
-        // ---- renormalise the site's 4 x 4 values by a power of two (integer max over the high words) ----
-        {
-            int hi = sv_maxhi4(y);
+        // ---- renormalise each site's 4 x 4 values by a power of two (integer max over the high words) ----
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            int hi = sv_maxhi4(y[j]);
             hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
             hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
             double sh;
             const double f = sv_pow2_rescale_hi(hi, &sh);
 #pragma unroll
-            for (int p = 0; p < 4; p++) x[p] = y[p] * f;
-            xs = (xs + ws) + sh;
-        }
-        if (WITH_CONST) {
-            int hi = sv_maxhi4(cy);
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
-            double sh;
-            const double f = sv_pow2_rescale_hi(hi, &sh);
-#pragma unroll
-            for (int p = 0; p < 4; p++) cx[p] = cy[p] * f;
-            cxs = cls + sh;
-        }
-
-        if (active) {
-            sv_st256(a.part + dst_row * 16 + k * 4, x);
-            // every category lane writes the (identical) scale: a lane only ever re-reads what it wrote itself
-            a.scale[dst_row] = xs;
+            for (int p = 0; p < 4; p++) x[j][p] = y[j][p] * f;
+            xs[j] = (xs[j] + ws[j]) + sh;
             if (WITH_CONST) {
-                sv_st256(a.cpart + dst_row * 16 + k * 4, cx);
-                a.cscale[dst_row] = cxs;
+                int chi = sv_maxhi4(cy[j]);
+                chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
+                chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
+                double csh;
+                const double cf = sv_pow2_rescale_hi(chi, &csh);
+#pragma unroll
+                for (int p = 0; p < 4; p++) cx[j][p] = cy[j][p] * cf;
+                cxs[j] = cls[j] + csh;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            if (!active[j]) continue;
+            const long long dst_row = dst_base + srow[j];
+            sv_st256(a.part + dst_row * 16 + k * 4, x[j]);
+            // every category lane writes the (identical) scale: a lane only ever re-reads what it wrote itself
+            a.scale[dst_row] = xs[j];
+            if (WITH_CONST) {
+                sv_st256(a.cpart + dst_row * 16 + k * 4, cx[j]);
+                a.cscale[dst_row] = cxs[j];
             }
         }
 
         // ---- root: integrate over categories and take the log (:153-218, :255-269) ----
         if (flags & SV_OP_ROOT) {
-            double v = active ? a.prop[k] * (GENO0 ? x[0] : sv_sel(x, rg)) : 0.0;
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (site_ok && k == 0) a.site_logl[site] = log(v) + xs;
-            if (WITH_CONST) {
-                double cv = active ? a.prop[k] * (GENO0 ? cx[0] : sv_sel(cx, rg)) : 0.0;
-                cv += __shfl_xor_sync(0xffffffffu, cv, 1);
-                cv += __shfl_xor_sync(0xffffffffu, cv, 2);
-                if (site_ok && k == 0) a.site_const[site] = log(cv) + cxs;
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                double v = active[j] ? a.prop[k] * (GENO0 ? x[j][0] : sv_sel(x[j], rg)) : 0.0;
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (site_ok[j] && k == 0) a.site_logl[site0 + 8 * j] = log(v) + xs[j];
+                if (WITH_CONST) {
+                    double cv = active[j] ? a.prop[k] * (GENO0 ? cx[j][0] : sv_sel(cx[j], rg)) : 0.0;
+                    cv += __shfl_xor_sync(0xffffffffu, cv, 1);
+                    cv += __shfl_xor_sync(0xffffffffu, cv, 2);
+                    if (site_ok[j] && k == 0) a.site_const[site0 + 8 * j] = log(cv) + cxs[j];
+                }
             }
         }
     }
