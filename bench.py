@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-level", action="store_true", help="issue the pruning as one launch per tree level")
+    ap.add_argument("--matrices", action="store_true", help="hand the core 16-double matrices (generic kernel) instead of branch distances")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -291,6 +292,8 @@ def main():
     core.set_root(tree.root, props, 0)
     nodes = np.array([i for i in range(tree.node_count) if i != tree.root], dtype=np.int32)
     P_host = np.ascontiguousarray(mats[nodes])
+    from sieve_b200 import substmodel
+    D_host = np.ascontiguousarray(substmodel.node_distances(tree, rates, branch_rates=br)[nodes])
     if args.per_level:
         ops, level_off = tree.ops_by_level()
     else:
@@ -301,10 +304,15 @@ def main():
         # what the plugin does per MCMC state: leaf parameters changed + every matrix changed -> full evaluation
         if args.per_level:
             core.update_leaves(for_update=True)
-            core.set_matrices(nodes, P_host, for_update=True)
+            if args.matrices:
+                core.set_matrices(nodes, P_host, for_update=True)
+            else:
+                core.set_distances(nodes, D_host, for_update=True)
             core.update_nodes(ops, level_off, flip=True, per_level=True)
             return core.evaluate()
-        return core.step(nodes, P_host, ops, update_leaves=True)
+        if args.matrices:
+            return core.step(nodes, P_host, ops, update_leaves=True)
+        return core.step_distances(nodes, D_host, ops, update_leaves=True)
 
     gather_buf = torch.zeros((world, 5), dtype=torch.float64, device=dev)
     res_ptr = _lib.C.c_void_p()
@@ -386,7 +394,12 @@ def main():
     prune_ms = float(np.median([x["prune_ms"] for x in tm]))
     reduce_ms = float(np.median([x["reduce_ms"] for x in tm]))
     # tree-only evaluation (stage-2 style proposal: matrices change, leaves do not)
-    core.step(nodes, P_host, ops, update_leaves=False)
+    if args.matrices or args.per_level:
+        core.set_matrices(nodes, P_host, for_update=True) if args.matrices else core.set_distances(nodes, D_host, for_update=True)
+        core.update_nodes(ops, level_off, flip=True, per_level=args.per_level)
+        core.evaluate()
+    else:
+        core.step_distances(nodes, D_host, ops, update_leaves=False)
     torch.cuda.synchronize()
     ev0.record(lib_stream)
     core.replay(update_leaves=False, n_times=args.steps)
@@ -423,7 +436,7 @@ def main():
         alg_leaf = 48 * n * S
         value = world * args.steps / (dev_ms_max / 1000.0)
         e2e_value = world * args.steps / e2e_s_max
-        stage_bytes = ops.shape[0] * 32 + nodes.size * K_CAT * 16 * 8 + nodes.size * 4 + 48
+        stage_bytes = core.last_stage_bytes() + 48
         achieved = alg_prune / (prune_ms / 1000.0) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -433,13 +446,14 @@ def main():
                                    "felsenstein acquisition-bias correction (BASELINE.json configs[2])" % (n, S),
                        "step": "leaf recompute + all %d internal nodes + root + reduce" % (tree.n),
                        "schedule": "per-level launches" if args.per_level else "single-launch walk",
+                       "transition_matrices": "16-double matrices from the host" if args.matrices else "branch distances, P formed on the device (fixed Q)",
                        "l2": "inputs larger than L2 (%.1f GB of partials per evaluation)" % (alg_prune / 1e9),
                        "parallelism": "site shards x%d, all-gather of 5 doubles per rank" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stage_bytes), "d2h_bytes_per_step": 40,
                     "ms_per_step": 1000.0 * e2e_s_max / args.steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_prune<true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_prune<const, geno0, %s>" % ("generic" if args.matrices else "qfast"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_prune), "launch_ms": prune_ms},
             "kernels": {"leaf_ms": leaf_ms, "leaf_GBps": alg_leaf / (leaf_ms / 1000.0) / 1e9 if leaf_ms > 0 else None,

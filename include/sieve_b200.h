@@ -126,6 +126,14 @@ int sieve_set_node_matrix(sieve_core_t *h, int32_t node, int32_t category, const
 /* batched form: for every listed node (flip if for_update) all K matrices, P is [count][K][16] */
 int sieve_set_matrices(sieve_core_t *h, int32_t count, const int32_t *nodes, const double *P, int32_t for_update);
 
+/* Fast path for SIEVE's fixed rate matrix (substitutionmodel/ScsFiniteMuExtendedModel.java:62-86): instead of K
+ * matrices per node the host passes K branch distances, distance[k] = branch length * branch rate * site rate_k, i.e.
+ * the arguments of getTransitionProbabilities at likelihood/ScsTreeLikelihood.java:567-571.  The device forms
+ * P = exp(Q d) in closed form (Q has eigenvalues 0, -0.2, -0.4, -0.4) and, when every matrix of an update came
+ * in this way, walks the tree with two scalars per (node, category) instead of a matrix in shared memory.
+ * distances is [count][K].  Mixing with sieve_set_matrices is allowed (the generic kernel is used then). */
+int sieve_set_distances(sieve_core_t *h, int32_t count, const int32_t *nodes, const double *distances, int32_t for_update);
+
 /* BeerLikelihoodCore.setNodePartialsForUpdate (external; call site ScsTreeLikelihood.java:2951-2956) */
 int sieve_set_node_partials_for_update(sieve_core_t *h, int32_t node);
 /* ScsBeerLikelihoodCore.calculateLogPartials / calculatePartials (:1283-1369 / :857-943).  child2 == -1 <=> unary root.
@@ -152,6 +160,12 @@ int sieve_evaluate(sieve_core_t *h, sieve_shard_result_t *out);
  * update_leaves != 0 runs sieve_update_leaves(for_update) first (parameters set by sieve_set_leaf_params). */
 int sieve_step(sieve_core_t *h, int32_t update_leaves, int32_t n_matrices, const int32_t *matrix_nodes, const double *P,
                int32_t n_ops, const int32_t *ops, sieve_shard_result_t *out);
+
+/* sieve_step with branch distances [n_nodes][K] in place of matrices (see sieve_set_distances) */
+int sieve_step_distances(sieve_core_t *h, int32_t update_leaves, int32_t n_nodes, const int32_t *nodes,
+                         const double *distances, int32_t n_ops, const int32_t *ops, sieve_shard_result_t *out);
+/* bytes the last step copied host -> device (ops + matrices / distances) */
+int sieve_last_stage_bytes(sieve_core_t *h, uint64_t *out);
 
 /* Re-launches, n_times, exactly the kernels of the last sieve_step / sieve_evaluate from what is already staged in HBM
  * (matrices, ops): no host<->device copy and no synchronisation.  update_leaves != 0 also rebuilds the tables and the

@@ -58,12 +58,15 @@ SIGNATURES = {
     "sieve_set_node_matrix_for_update": (C.c_int, [_vp, C.c_int32]),
     "sieve_set_node_matrix": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp]),
     "sieve_set_matrices": (C.c_int, [_vp, C.c_int32, _ip, _dp, C.c_int32]),
+    "sieve_set_distances": (C.c_int, [_vp, C.c_int32, _ip, _dp, C.c_int32]),
     "sieve_set_node_partials_for_update": (C.c_int, [_vp, C.c_int32]),
     "sieve_calculate_partials": (C.c_int, [_vp] + [C.c_int32] * 6),
     "sieve_update_nodes": (C.c_int, [_vp, C.c_int32, _ip, _ip, C.c_int32, C.c_uint32]),
     "sieve_set_root": (C.c_int, [_vp, C.c_int32, _dp, C.c_int32]),
     "sieve_evaluate": (C.c_int, [_vp, C.POINTER(ShardResult)]),
     "sieve_step": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip, _dp, C.c_int32, _ip, C.POINTER(ShardResult)]),
+    "sieve_step_distances": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip, _dp, C.c_int32, _ip, C.POINTER(ShardResult)]),
+    "sieve_last_stage_bytes": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "sieve_replay": (C.c_int, [_vp, C.c_int32, C.c_int32]),
     "sieve_get_site_log_likelihoods": (C.c_int, [_vp, _dp, _dp]),
     "sieve_get_result_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),

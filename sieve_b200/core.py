@@ -103,6 +103,13 @@ class ScsCudaLikelihoodCore:
         assert m.size == nd.size * self.K * 16
         check(self.L.sieve_set_matrices(self.h, nd.size, _iptr(nd), _dptr(m), int(bool(for_update))))
 
+    def set_distances(self, nodes, distances, for_update=True):
+        """Fast path for the fixed rate matrix: distances [len(nodes)][K] = branch length * branch rate * site rate."""
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        d = np.ascontiguousarray(distances, dtype=np.float64)
+        assert d.size == nd.size * self.K
+        check(self.L.sieve_set_distances(self.h, nd.size, _iptr(nd), _dptr(d), int(bool(for_update))))
+
     # ---- partials ------------------------------------------------------------------------------------------
     def set_node_partials_for_update(self, node):
         check(self.L.sieve_set_node_partials_for_update(self.h, int(node)))
@@ -141,6 +148,21 @@ class ScsCudaLikelihoodCore:
         check(self.L.sieve_step(self.h, int(bool(update_leaves)), nd.size, _iptr(nd), _dptr(m), o.shape[0], _iptr(o),
                                 C.byref(r)))
         return r
+
+    def step_distances(self, nodes, distances, ops, update_leaves=False):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        d = np.ascontiguousarray(distances, dtype=np.float64)
+        o = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 3)
+        assert d.size == nd.size * self.K
+        r = ShardResult()
+        check(self.L.sieve_step_distances(self.h, int(bool(update_leaves)), nd.size, _iptr(nd), _dptr(d), o.shape[0],
+                                          _iptr(o), C.byref(r)))
+        return r
+
+    def last_stage_bytes(self):
+        n = C.c_uint64()
+        check(self.L.sieve_last_stage_bytes(self.h, C.byref(n)))
+        return n.value
 
     def replay(self, update_leaves=False, n_times=1):
         """Re-launch the last step's kernels from what is staged in HBM (asynchronous, no copies)."""

@@ -29,6 +29,8 @@ struct SvPruneArgs {
     const double* leafX;   // [leaf slots][S][4]
     const double* leafS;   // [leaf slots][S]
     const double* mats;    // [matrix slots][4][16], already clamped when SIEVE_FLAG_LOG_PARTIALS
+    const double2* qfac;   // [matrix slots][4] = (expm1(-0.2 d) / 8, expm1(-0.4 d) / 16): the Q-specialised path
+    int clamp_zero_distance;  // SIEVE_FLAG_LOG_PARTIALS: a zero distance gets the Double.MIN_VALUE off-diagonals
     const SvOp* ops;
     int op_begin, op_end;  // walk: ops [op_begin, op_end); per-level: op = op_begin + blockIdx.y
     int per_level;
@@ -56,7 +58,7 @@ __device__ __forceinline__ double sv_sel(const double (&x)[4], int g) {
 
 #define SV_PRUNE_THREADS 128
 #ifndef SV_PRUNE_PREFETCH
-#define SV_PRUNE_PREFETCH 1  // ops ahead whose (non-forwarded) children are prefetched into L2; 0 = off
+#define SV_PRUNE_PREFETCH 0  // ops ahead whose (non-forwarded) children are prefetched into L2; 0 = off
 #endif
 __device__ __forceinline__ void sv_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef SV_PRUNE_NS
@@ -64,11 +66,21 @@ __device__ __forceinline__ void sv_prefetch_l2(const void* p) { asm volatile("pr
 #endif
 #define SV_PRUNE_SITES ((SV_PRUNE_THREADS / 4) * SV_PRUNE_NS)
 #ifndef SV_PRUNE_MINB_CONST
-#define SV_PRUNE_MINB_CONST 3
+#define SV_PRUNE_MINB_CONST 4
 #endif
 #ifndef SV_PRUNE_MINB
 #define SV_PRUNE_MINB 5
 #endif
+#ifndef SV_PRUNE_NS_Q
+#define SV_PRUNE_NS_Q 2
+#endif
+#ifndef SV_PRUNE_MINB_CONST_Q
+#define SV_PRUNE_MINB_CONST_Q 4
+#endif
+#ifndef SV_PRUNE_MINB_Q
+#define SV_PRUNE_MINB_Q 6
+#endif
+#define SV_PRUNE_SITES_Q ((SV_PRUNE_THREADS / 4) * SV_PRUNE_NS_Q)
 
 // y_j = M x_j for the NS sites of a lane; every matrix element is read from shared memory once
 template <int NS>
@@ -82,11 +94,64 @@ __device__ __forceinline__ void sv_matvec_n(const double* __restrict__ M, const 
     }
 }
 
+// ---- the Q-specialised contraction ---------------------------------------------------------------------------------
+// SIEVE's only usable substitution model has a FIXED rate matrix (substitutionmodel/ScsFiniteMuExtendedModel.java:62-86,
+// normalised by ScsSubstitutionModelBase.java:200-231):  Q = 0.3 [[-1,1,0,0],[1/6,-2/3,1/6,1/3],[0,1/3,-1,2/3],[0,1/3,1/3,-2/3]]
+// with eigenvalues 0, -0.2, -0.4, -0.4 and is diagonalisable, so with g1 = expm1(-0.2 d), g2 = expm1(-0.4 d)
+//     P(d) = I + g1 * Pi1 + g2 * Pi2,   Pi1 = u v^T / 8 (u = (3,1,-1,-1), v = (1,2,-1,-2)),   Pi2 of rank 2,
+// and  y = P x  needs two scalars per (node, category) instead of a 4 x 4 matrix from shared memory:
+//     t1 = g1/8  (x0 + 2 x1 - x2 - 2 x3),  ta = g2/16 (-3 x0 + 6 x1 - x2 - 2 x3),  tb = g2/16 (x0 - 2 x1 - 5 x2 + 6 x3)
+//     y0 = x0 + 3 (t1 - ta),  y1 = x1 + (t1 + ta),  y3 = x3 + (tb - t1),  y2 = x2 + (tb - t1) + g2 (x2 - x3)
+// (expm1 keeps the O(d) entries accurate for short branches).  q = (g1 / 8, g2 / 16).
+template <int NS>
+__device__ __forceinline__ void sv_matvec_q(const double2 q, const double (&x)[NS][4], double (&y)[NS][4], bool clamp0) {
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        const double A = fma(2.0, x[j][1], x[j][0]);   // x0 + 2 x1
+        const double B = fma(2.0, x[j][3], x[j][2]);   // x2 + 2 x3
+        const double D = fma(-2.0, x[j][1], x[j][0]);  // x0 - 2 x1
+        const double t1 = q.x * (A - B);
+        const double ta = q.y * fma(-3.0, D, -B);
+        const double tb = q.y * (D + fma(6.0, x[j][3], -5.0 * x[j][2]));
+        const double u = tb - t1;
+        y[j][0] = fma(3.0, t1 - ta, x[j][0]);
+        y[j][1] = x[j][1] + (t1 + ta);
+        y[j][3] = x[j][3] + u;
+        y[j][2] = fma(16.0 * q.y, x[j][2] - x[j][3], x[j][2] + u);
+        if (clamp0 && q.x == 0.0) {
+            // d == 0: P = I; the reference takes log(P > 0 ? P : Double.MIN_VALUE) (:1430) for the 12 zero entries
+            const double sum = (x[j][0] + x[j][1]) + (x[j][2] + x[j][3]);
+#pragma unroll
+            for (int p = 0; p < 4; p++) y[j][p] = fma(SV_MIN_VALUE, sum - x[j][p], x[j][p]);
+        }
+    }
+}
+// the constant-site contribution of a LEAF child: only the genotype-0 column of P survives (:1432-1436)
+template <int NS>
+__device__ __forceinline__ void sv_col0_q(const double2 q, const double (&x)[NS][4], double (&y)[NS][4], bool clamp0) {
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        const double x0 = x[j][0];
+        const double t1 = q.x * x0, ta = -3.0 * (q.y * x0), tb = q.y * x0;
+        y[j][0] = fma(3.0, t1 - ta, x0);
+        y[j][1] = t1 + ta;
+        y[j][2] = tb - t1;
+        y[j][3] = tb - t1;
+        if (clamp0 && q.x == 0.0) {
+            y[j][1] = y[j][2] = y[j][3] = SV_MIN_VALUE * x0;
+        }
+    }
+}
+
 // GENO0: root genotype == constant genotype == 0 (always so for ScsFiniteMuExtendedModel.java:37-40); the general
 // case takes the same kernel with run-time selects.
-template <bool WITH_CONST, bool GENO0>
-__global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB) k_prune(SvPruneArgs a) {
-    constexpr int NS = SV_PRUNE_NS;
+// QFAST: every matrix of the launch was given as a branch distance (sieve_set_distances): no shared memory at all.
+template <bool WITH_CONST, bool GENO0, bool QFAST>
+__global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRUNE_MINB_CONST_Q : SV_PRUNE_MINB_Q)
+                                                          : (WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB))
+    k_prune(SvPruneArgs a) {
+    constexpr int NS = QFAST ? SV_PRUNE_NS_Q : SV_PRUNE_NS;
+    constexpr int SITES_PER_BLOCK = (SV_PRUNE_THREADS / 4) * NS;
     // warp-private copies of the op's two 4 x 4 x 4 matrices: no block-wide barrier anywhere in the walk, so the
     // warps of an SM drift apart and overlap each other's memory latency
     __shared__ __align__(32) double sm[(SV_PRUNE_THREADS / 32) * 2 * SV_KMAX * SV_MAT_STRIDE];
@@ -95,7 +160,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
     const int k = lane & 3;
     // a warp owns 8 * NS consecutive sites; pass j of a lane is site base + 8 j, so that every pass of the warp is one
     // contiguous 1 KB access
-    const int site0 = blockIdx.x * SV_PRUNE_SITES + warp * (8 * NS) + (lane >> 2);
+    const int site0 = blockIdx.x * SITES_PER_BLOCK + warp * (8 * NS) + (lane >> 2);
     bool site_ok[NS], active[NS];
     long long srow[NS];
 #pragma unroll
@@ -182,7 +247,11 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
 #endif
         // ---- issue every global load of this op up front: matrices (one 256-bit load per lane) and children ----
         double m[4] = {0, 0, 0, 0};
-        if (!(st_which == 1 && unary))
+        double2 q1 = make_double2(0.0, 0.0), q2 = make_double2(0.0, 0.0);
+        if (QFAST) {
+            q1 = __ldg(a.qfac + (size_t)m1 * SV_KMAX + k);
+            if (!unary) q2 = __ldg(a.qfac + (size_t)m2 * SV_KMAX + k);
+        } else if (!(st_which == 1 && unary))
             sv_ld256_nc(a.mats + (size_t)(st_which ? m2 : m1) * (SV_KMAX * 16) + st_off, m);
         double w[NS][4], ws[NS];      // child 2
         double cw[NS][4], cws[NS];    // child 2, constant-site twin
@@ -223,17 +292,20 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
                 }
             }
         }
-        __syncwarp();  // every lane is done with the previous op's matrices
-        *reinterpret_cast<double2*>(st_dst) = make_double2(m[0], m[1]);
-        *reinterpret_cast<double2*>(st_dst + 2) = make_double2(m[2], m[3]);
-        __syncwarp();
+        if (!QFAST) {
+            __syncwarp();  // every lane is done with the previous op's matrices
+            *reinterpret_cast<double2*>(st_dst) = make_double2(m[0], m[1]);
+            *reinterpret_cast<double2*>(st_dst + 2) = make_double2(m[2], m[3]);
+            __syncwarp();
+        }
+        const bool cz0 = a.clamp_zero_distance;
 
         // ================= variant partials =================
         double y[NS][4];
-        sv_matvec_n<NS>(M1, x, y);
+        if (QFAST) sv_matvec_q<NS>(q1, x, y, cz0); else sv_matvec_n<NS>(M1, x, y);
         if (!unary) {
             double z[NS][4];
-            sv_matvec_n<NS>(M2, w, z);
+            if (QFAST) sv_matvec_q<NS>(q2, w, z, cz0); else sv_matvec_n<NS>(M2, w, z);
 #pragma unroll
             for (int j = 0; j < NS; j++)
 #pragma unroll
@@ -245,7 +317,11 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
 #pragma unroll
         for (int j = 0; j < NS; j++) cls[j] = 0.0;
         if (WITH_CONST) {
-            if (leaf1) {
+            if (leaf1 && QFAST) {
+                sv_col0_q<NS>(q1, x, cy, cz0);
+#pragma unroll
+                for (int j = 0; j < NS; j++) cls[j] = xs[j];
+            } else if (leaf1) {
                 // leaf: only the constant genotype's term survives (:1432-1436); its scale is the leaf's
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
@@ -256,13 +332,17 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
 #pragma unroll
                 for (int j = 0; j < NS; j++) cls[j] = xs[j];
             } else {
-                sv_matvec_n<NS>(M1, cx, cy);
+                if (QFAST) sv_matvec_q<NS>(q1, cx, cy, cz0); else sv_matvec_n<NS>(M1, cx, cy);
 #pragma unroll
                 for (int j = 0; j < NS; j++) cls[j] = cxs[j];
             }
             if (!unary) {
                 double cz[NS][4];
-                if (leaf2) {
+                if (leaf2 && QFAST) {
+                    sv_col0_q<NS>(q2, w, cz, cz0);
+#pragma unroll
+                    for (int j = 0; j < NS; j++) cls[j] += ws[j];
+                } else if (leaf2) {
 #pragma unroll
                     for (int p = 0; p < 4; p++) {
                         const double mm = M2[4 * p + cg];
@@ -272,7 +352,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, WITH_CONST ? SV_PRUNE_MINB_C
 #pragma unroll
                     for (int j = 0; j < NS; j++) cls[j] += ws[j];
                 } else {
-                    sv_matvec_n<NS>(M2, cw, cz);
+                    if (QFAST) sv_matvec_q<NS>(q2, cw, cz, cz0); else sv_matvec_n<NS>(M2, cw, cz);
 #pragma unroll
                     for (int j = 0; j < NS; j++) cls[j] += cws[j];
                 }

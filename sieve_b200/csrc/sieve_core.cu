@@ -37,6 +37,7 @@ static int sv_fail(int code, const std::string& msg) {
 
 struct PendingMatrix {
     int slot;
+    int is_distance;  // v[0..K) are branch distances (length * branch rate * category rate) instead of K matrices
     double v[SV_KMAX * 16];
 };
 
@@ -61,7 +62,9 @@ struct sieve_core {
     int max_cov = -1;
     double *d_leafX = nullptr, *d_leafS = nullptr;                                       // [2][n][S][4], [2][n][S]
     double *d_part = nullptr, *d_scale = nullptr, *d_cpart = nullptr, *d_cscale = nullptr;  // [2][n_internal][S][K][4]
-    double* d_mats = nullptr;                                                            // [2][n_nodes][K][16]
+    double* d_mats = nullptr;                                                            // [2][n_nodes][4][16]
+    double2* d_qfac = nullptr;                                                           // [2][n_nodes][4]
+    std::vector<char> slot_is_q;  // per matrix slot: was it given as a distance?
     double *d_site_logl = nullptr, *d_site_const = nullptr;
     SvAcc* d_partials = nullptr;
     unsigned int* d_counter = nullptr;
@@ -87,7 +90,10 @@ struct sieve_core {
     sieve_leaf_params_t tab_lp{};  // parameters the current tables were built with
 
     // what the last flush staged on the device (for sieve_replay)
-    size_t last_no = 0, last_nm = 0, last_off_mv = 0, last_off_ms = 0;
+    size_t last_no = 0, last_nm = 0, last_nd = 0, last_off_mv = 0, last_off_ms = 0, last_off_dv = 0, last_off_ds = 0;
+    size_t last_stage_bytes = 0;
+    bool last_qfast = false;
+    bool force_generic = false;  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
     std::vector<int> last_levels;
     bool last_per_level = false;
 
@@ -184,6 +190,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->cur_mat.assign(h->n_nodes, 0);
     h->stored_mat.assign(h->n_nodes, 0);
     h->root = h->n_nodes - 1;
+    if (const char* e = getenv("SIEVE_B200_GENERIC")) h->force_generic = atoi(e) != 0;
 
     auto fail = [&](int code) {
         sieve_destroy(h);
@@ -225,6 +232,8 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         CR(sv_alloc(h, &h->d_cscale, 2 * n * S));
     }
     CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * SV_KMAX * 16));
+    CR(sv_alloc(h, &h->d_qfac, (size_t)2 * h->n_nodes * SV_KMAX));
+    h->slot_is_q.assign((size_t)2 * h->n_nodes, 0);
     CR(sv_alloc(h, &h->d_site_logl, S));
     CR(sv_alloc(h, &h->d_site_const, S));
     CR(sv_alloc(h, &h->d_partials, (size_t)SV_REDUCE_BLOCKS));
@@ -261,6 +270,7 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_cpart);
     cudaFree(h->d_cscale);
     cudaFree(h->d_mats);
+    cudaFree(h->d_qfac);
     cudaFree(h->d_site_logl);
     cudaFree(h->d_site_const);
     cudaFree(h->d_partials);
@@ -545,6 +555,27 @@ __global__ void k_scatter_matrices(const double* __restrict__ stage, const int* 
     }
 }
 
+// Branch distances -> (g1/8, g2/16) for the Q-specialised walk, and the full matrices P = I + g1 Pi1 + g2 Pi2 for the
+// generic kernel and the getters.  One thread per (entry, category).
+__global__ void k_scatter_distances(const double* __restrict__ stage, const int* __restrict__ slots, int count, int K,
+                                    int clamp, double2* __restrict__ qfac, double* __restrict__ mats) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * K) return;
+    const int i = idx / K, k = idx % K;
+    const double d = stage[(size_t)i * K + k];
+    const double g1 = expm1(-0.2 * d), g2 = expm1(-0.4 * d);
+    qfac[(size_t)slots[i] * SV_KMAX + k] = make_double2(g1 / 8.0, g2 / 16.0);
+    const double P1[16] = {3, 6, -3, -6, 1, 2, -1, -2, -1, -2, 1, 2, -1, -2, 1, 2};          // 8 Pi1
+    const double P2[16] = {9, -18, 3, 6, -3, 6, -1, -2, 1, -2, 11, -10, 1, -2, -5, 6};       // 16 Pi2
+    double* out = mats + (size_t)slots[i] * (SV_KMAX * 16) + k * 16;
+    for (int e = 0; e < 16; e++) {
+        double v = ((e % 5 == 0) ? 1.0 : 0.0) + (g1 / 8.0) * P1[e] + (g2 / 16.0) * P2[e];
+        if (d == 0.0) v = (e % 5 == 0) ? 1.0 : 0.0;
+        if (clamp) v = v > 0.0 ? v : SV_MIN_VALUE;
+        out[e] = v;
+    }
+}
+
 static bool sv_node_ok(const sieve_core* h, int node) { return node >= 0 && node < h->n_nodes; }
 
 extern "C" int sieve_set_node_matrix_for_update(sieve_core_t* h, int32_t node) {
@@ -558,6 +589,7 @@ static PendingMatrix* sv_pending_matrix(sieve_core* h, int slot) {
         if (it->slot == slot) return &*it;
     PendingMatrix pm;
     pm.slot = slot;
+    pm.is_distance = 0;
     memset(pm.v, 0, sizeof(pm.v));
     h->pending_mats.push_back(pm);
     return &h->pending_mats.back();
@@ -573,6 +605,7 @@ extern "C" int sieve_set_node_matrix(sieve_core_t* h, int32_t node, int32_t cate
         pm = &h->pending_mats.back();
     else
         pm = sv_pending_matrix(h, slot);
+    pm->is_distance = 0;
     memcpy(pm->v + category * 16, p16, 16 * sizeof(double));
     return SIEVE_OK;
 }
@@ -586,7 +619,28 @@ extern "C" int sieve_set_matrices(sieve_core_t* h, int32_t count, const int32_t*
         if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
         PendingMatrix pm;
         pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
+        pm.is_distance = 0;
         memcpy(pm.v, P + (size_t)i * K * 16, sizeof(double) * K * 16);
+        h->pending_mats.push_back(pm);
+    }
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_set_distances(sieve_core_t* h, int32_t count, const int32_t* nodes, const double* distances,
+                                   int32_t for_update) {
+    SV_REQUIRE(h && count >= 0 && (count == 0 || (nodes && distances)), "sieve_set_distances: bad argument");
+    const int K = h->K;
+    h->pending_mats.reserve(h->pending_mats.size() + count);
+    for (int i = 0; i < count; i++) {
+        SV_REQUIRE(sv_node_ok(h, nodes[i]), "sieve_set_distances: bad node");
+        if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
+        PendingMatrix pm;
+        pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
+        pm.is_distance = 1;
+        for (int k = 0; k < K; k++) {
+            SV_REQUIRE(distances[(size_t)i * K + k] >= 0.0, "sieve_set_distances: negative distance");
+            pm.v[k] = distances[(size_t)i * K + k];
+        }
         h->pending_mats.push_back(pm);
     }
     return SIEVE_OK;
@@ -704,29 +758,36 @@ extern "C" int sieve_set_root(sieve_core_t* h, int32_t root, const double* propo
     return SIEVE_OK;
 }
 
-static void sv_launch_prune(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
+template <bool QFAST>
+static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
     const bool g0 = a.const_genotype == 0 && a.root_genotype == 0;
     if (h->with_const) {
         if (g0)
-            k_prune<true, true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            k_prune<true, true, QFAST><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
         else
-            k_prune<true, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            k_prune<true, false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
     } else {
         if (g0)
-            k_prune<false, true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            k_prune<false, true, QFAST><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
         else
-            k_prune<false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            k_prune<false, false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
     }
 }
 
-// launches scatter + pruning for what is staged on the device
+// launches the scatters + the pruning for what is staged on the device
 static int sv_launch_staged(sieve_core* h) {
     const int K = h->K;
-    const size_t nm = h->last_nm, no = h->last_no, off_mv = h->last_off_mv, off_ms = h->last_off_ms, off_ops = 0;
+    const size_t nm = h->last_nm, nd = h->last_nd, no = h->last_no;
     if (nm) {
-        k_scatter_matrices<<<(unsigned)nm, 64, 0, h->stream>>>((const double*)(h->d_stage + off_mv),
-                                                              (const int*)(h->d_stage + off_ms), (int)nm, K,
+        k_scatter_matrices<<<(unsigned)nm, 64, 0, h->stream>>>((const double*)(h->d_stage + h->last_off_mv),
+                                                              (const int*)(h->d_stage + h->last_off_ms), (int)nm, K,
                                                               h->log_mode ? 1 : 0, h->d_mats);
+        sv_count(h);
+    }
+    if (nd) {
+        k_scatter_distances<<<(unsigned)((nd * K + 127) / 128), 128, 0, h->stream>>>(
+            (const double*)(h->d_stage + h->last_off_dv), (const int*)(h->d_stage + h->last_off_ds), (int)nd, K,
+            h->log_mode ? 1 : 0, h->d_qfac, h->d_mats);
         sv_count(h);
     }
     if (no) {
@@ -738,7 +799,9 @@ static int sv_launch_staged(sieve_core* h) {
         a.leafX = h->d_leafX;
         a.leafS = h->d_leafS;
         a.mats = h->d_mats;
-        a.ops = (const SvOp*)(h->d_stage + off_ops);
+        a.qfac = h->d_qfac;
+        a.clamp_zero_distance = h->log_mode ? 1 : 0;
+        a.ops = (const SvOp*)(h->d_stage);
         a.S = h->S;
         a.K = K;
         a.linear_const_clamp = h->log_mode ? 0 : 1;
@@ -747,62 +810,88 @@ static int sv_launch_staged(sieve_core* h) {
         for (int k = 0; k < 4; k++) a.prop[k] = h->prop[k];
         a.site_logl = h->d_site_logl;
         a.site_const = h->d_site_const;
-        const unsigned gx = (unsigned)((h->S + SV_PRUNE_SITES - 1) / SV_PRUNE_SITES);
+        // the Q-specialised walk needs every matrix of the launch to have been given as a distance (and genotype 0)
+        const bool qfast = h->last_qfast && a.const_genotype == 0 && a.root_genotype == 0 && !h->force_generic;
+        const int spb = qfast ? SV_PRUNE_SITES_Q : SV_PRUNE_SITES;
+        const unsigned gx = (unsigned)((h->S + spb - 1) / spb);
+        auto launch = [&](dim3 grid) {
+            if (qfast)
+                sv_launch_prune_t<true>(h, grid, a);
+            else
+                sv_launch_prune_t<false>(h, grid, a);
+            sv_count(h);
+        };
         if (h->last_per_level) {
             for (size_t l = 0; l + 1 < h->last_levels.size(); l++) {
                 const int b = h->last_levels[l], e = h->last_levels[l + 1];
                 if (e <= b) continue;
-                a.op_begin = b;
                 a.op_end = e;
                 a.per_level = 1;
-                // grid.y is limited to 65535
-                for (int b0 = b; b0 < e; b0 += 65535) {
+                for (int b0 = b; b0 < e; b0 += 65535) {  // grid.y is limited to 65535
                     a.op_begin = b0;
-                    dim3 grid(gx, (unsigned)std::min(65535, e - b0));
-                    sv_launch_prune(h, grid, a);
-                    sv_count(h);
+                    launch(dim3(gx, (unsigned)std::min(65535, e - b0)));
                 }
             }
         } else {
             a.op_begin = 0;
             a.op_end = (int)no;
             a.per_level = 0;
-            sv_launch_prune(h, dim3(gx), a);
-            sv_count(h);
+            launch(dim3(gx));
         }
     }
     SV_CUDA(cudaGetLastError());
     return SIEVE_OK;
 }
 
-// uploads pending matrices + ops with ONE host->device copy and launches scatter + pruning
+// uploads pending matrices / distances + ops with ONE host->device copy and launches scatter + pruning
 static int sv_flush(sieve_core* h) {
     const int K = h->K;
-    const size_t nm = h->pending_mats.size(), no = h->pending_ops.size();
-    if (nm == 0 && no == 0) return SIEVE_OK;
+    const size_t no = h->pending_ops.size();
+    size_t nm = 0, nd = 0;
+    for (const PendingMatrix& pm : h->pending_mats) (pm.is_distance ? nd : nm)++;
+    if (nm == 0 && nd == 0 && no == 0) return SIEVE_OK;
     if (no > 0 && !h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "ops queued before the leaves were computed");
-    // staging layout: [ops][matrix values][matrix slots]
-    const size_t off_ops = 0;
-    const size_t off_mv = off_ops + no * sizeof(SvOp);
-    const size_t off_ms = off_mv + nm * K * 16 * sizeof(double);
-    const size_t total = off_ms + nm * sizeof(int);
+    // staging layout: [ops][matrix values][distance values][matrix slots][distance slots]
+    const size_t off_mv = no * sizeof(SvOp);
+    const size_t off_dv = off_mv + nm * K * 16 * sizeof(double);
+    const size_t off_ms = off_dv + nd * K * sizeof(double);
+    const size_t off_ds = off_ms + nm * sizeof(int);
+    const size_t total = off_ds + nd * sizeof(int);
     SV_TRY(sv_ensure_stage(h, total));
     SV_CUDA(cudaStreamSynchronize(h->stream));  // the previous step may still be reading the staging buffer
     sv_link_forwarding(h->pending_ops, h->pending_per_level);
-    if (no) memcpy(h->h_stage + off_ops, h->pending_ops.data(), no * sizeof(SvOp));
-    for (size_t i = 0; i < nm; i++) {
-        memcpy(h->h_stage + off_mv + i * K * 16 * sizeof(double), h->pending_mats[i].v, K * 16 * sizeof(double));
-        ((int*)(h->h_stage + off_ms))[i] = h->pending_mats[i].slot;
+    if (no) memcpy(h->h_stage, h->pending_ops.data(), no * sizeof(SvOp));
+    size_t im = 0, id = 0;
+    for (const PendingMatrix& pm : h->pending_mats) {
+        if (pm.is_distance) {
+            memcpy(h->h_stage + off_dv + id * K * sizeof(double), pm.v, K * sizeof(double));
+            ((int*)(h->h_stage + off_ds))[id++] = pm.slot;
+        } else {
+            memcpy(h->h_stage + off_mv + im * K * 16 * sizeof(double), pm.v, K * 16 * sizeof(double));
+            ((int*)(h->h_stage + off_ms))[im++] = pm.slot;
+        }
+        h->slot_is_q[pm.slot] = pm.is_distance ? 1 : 0;
+    }
+    bool qfast = true;
+    for (const SvOp& op : h->pending_ops) {
+        if (!h->slot_is_q[op.m1] || (!(op.flags & SV_OP_UNARY) && !h->slot_is_q[op.m2])) {
+            qfast = false;
+            break;
+        }
     }
     SV_CUDA(cudaMemcpyAsync(h->d_stage, h->h_stage, total, cudaMemcpyHostToDevice, h->stream));
     h->last_no = no;
     h->last_nm = nm;
+    h->last_nd = nd;
     h->last_off_mv = off_mv;
     h->last_off_ms = off_ms;
+    h->last_off_dv = off_dv;
+    h->last_off_ds = off_ds;
+    h->last_qfast = qfast;
+    h->last_stage_bytes = total;
     h->last_levels = h->pending_levels;
     h->last_per_level = h->pending_per_level;
     SV_TRY(sv_launch_staged(h));
-    SV_CUDA(cudaGetLastError());
     h->pending_mats.clear();
     h->pending_ops.clear();
     h->pending_levels.clear();
@@ -863,6 +952,26 @@ extern "C" int sieve_step(sieve_core_t* h, int32_t update_leaves, int32_t n_matr
     h->last_launches = h->step_launches;
     h->step_launches = 0;
     return r;
+}
+
+extern "C" int sieve_step_distances(sieve_core_t* h, int32_t update_leaves, int32_t n_nodes, const int32_t* nodes,
+                                    const double* distances, int32_t n_ops, const int32_t* ops,
+                                    sieve_shard_result_t* out) {
+    SV_REQUIRE(h, "null handle");
+    SV_CUDA(cudaSetDevice(h->device));
+    if (update_leaves) SV_TRY(sieve_update_leaves(h, 1));
+    SV_TRY(sieve_set_distances(h, n_nodes, nodes, distances, 1));
+    SV_TRY(sieve_update_nodes(h, n_ops, ops, nullptr, 0, SIEVE_UPDATE_FLIP));
+    int r = sv_evaluate(h, out);
+    h->last_launches = h->step_launches;
+    h->step_launches = 0;
+    return r;
+}
+
+extern "C" int sieve_last_stage_bytes(sieve_core_t* h, uint64_t* out) {
+    SV_REQUIRE(h && out, "null argument");
+    *out = h->last_stage_bytes;
+    return SIEVE_OK;
 }
 
 extern "C" int sieve_replay(sieve_core_t* h, int32_t update_leaves, int32_t n_times) {

@@ -28,22 +28,19 @@ def rate_matrix():
     return Q / subst
 
 
-_EIG = None
-
-
-def _eig():
-    global _EIG
-    if _EIG is None:
-        w, V = np.linalg.eig(rate_matrix())
-        _EIG = (w.real, V.real, np.linalg.inv(V).real)
-    return _EIG
+# Spectral form of exp(Q d): Q has eigenvalues 0, -0.2, -0.4 (twice) and is diagonalisable, so
+#   P(d) = I + expm1(-0.2 d) * PI1 + expm1(-0.4 d) * PI2
+# with the two projectors below (exact rationals).  expm1 keeps the O(d) entries accurate for short branches.
+PI1 = np.array([[3, 6, -3, -6], [1, 2, -1, -2], [-1, -2, 1, 2], [-1, -2, 1, 2]], dtype=np.float64) / 8.0
+PI2 = np.array([[9, -18, 3, 6], [-3, 6, -1, -2], [1, -2, 11, -10], [1, -2, -5, 6]], dtype=np.float64) / 16.0
 
 
 def transition_probabilities(distance):
     """P = exp(Q * distance), row = parent state, column = child state (the layout `setNodeMatrix` takes,
     likelihood/ScsBeerLikelihoodCore.java:107-108). `distance` = branch length * branch rate * site rate."""
-    w, V, Vi = _eig()
-    P = (V * np.exp(w * distance)) @ Vi
+    if distance == 0.0:
+        return np.eye(4)
+    P = np.eye(4) + np.expm1(-0.2 * distance) * PI1 + np.expm1(-0.4 * distance) * PI2
     return np.clip(P, 0.0, None)
 
 
@@ -55,6 +52,14 @@ def gamma_category_rates(shape, k=4, mu=1.0):
     r = gamma.ppf(q, a=shape, scale=1.0 / shape)
     r = r / r.mean()
     return r * mu, np.full(k, 1.0 / k)
+
+
+def node_distances(tree, cat_rates, branch_rates=None, clock_rate=1.0):
+    """[2n][K] distances = length * branchRate * siteRate_k (the arguments of getTransitionProbabilities at
+    likelihood/ScsTreeLikelihood.java:567-571); the root's row is unused."""
+    bl = tree.branch_lengths()
+    br = clock_rate * (np.ones(tree.node_count) if branch_rates is None else np.asarray(branch_rates))
+    return (bl * br)[:, None] * np.asarray(cat_rates)[None, :]
 
 
 def node_matrices(tree, cat_rates, branch_rates=None, clock_rate=1.0):

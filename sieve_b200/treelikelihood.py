@@ -33,7 +33,7 @@ class ScsTreeLikelihood:
 
     def __init__(self, counts, tree, size_factors=None, leaf_params=None, gamma_shape=1.0, n_categories=4,
                  clock_rate=1.0, branch_rates=None, use_log_partials=True, asc_mode="none", n_background_sites=0.0,
-                 weights=None, single_ado=True, device=-1, return_const_sum=False):
+                 weights=None, single_ado=True, device=-1, return_const_sum=False, use_distances=True):
         counts = np.asarray(counts)
         self.S, self.n = counts.shape[0], counts.shape[1]
         assert tree.n == self.n, "The number of nodes in the tree does not match the number of sequences"
@@ -46,6 +46,8 @@ class ScsTreeLikelihood:
         self.asc_mode = asc_mode
         self.M = float(n_background_sites)
         self.return_const_sum = return_const_sum
+        # True: hand the core branch distances (fast path for the fixed rate matrix); False: 16-double matrices
+        self.use_distances = use_distances
         self.core = ScsCudaLikelihoodCore(self.n, self.S, n_categories, 4, use_log_partials, asc_mode != "none",
                                           single_ado, device)
         self.core.set_counts(counts)
@@ -112,11 +114,15 @@ class ScsTreeLikelihood:
         # traverse, first block (:563-580): which matrices are refreshed
         mat_nodes = [i for i in range(tree.node_count) if i != tree.root and
                      (all_dirty or i in self.dirty_nodes or branch_time[i] != self.branch_lengths[i])]
-        P = np.empty((len(mat_nodes), self.K, 16))
-        for j, node in enumerate(mat_nodes):
+        for node in mat_nodes:
             self.branch_lengths[node] = branch_time[node]
-            for k in range(self.K):
-                P[j, k] = substmodel.transition_probabilities(branch_time[node] * self.rates[k]).reshape(16)
+        if self.use_distances:
+            D = branch_time[mat_nodes][:, None] * self.rates[None, :] if len(mat_nodes) else np.zeros((0, self.K))
+        else:
+            P = np.empty((len(mat_nodes), self.K, 16))
+            for j, node in enumerate(mat_nodes):
+                for k in range(self.K):
+                    P[j, k] = substmodel.transition_probabilities(branch_time[node] * self.rates[k]).reshape(16)
         # second block (:615-628): a node is recomputed when something below it changed
         if all_dirty or self.update_leaves:
             ops = tree.ops()
@@ -126,7 +132,10 @@ class ScsTreeLikelihood:
             ops = tree.ops(tree.dirty_closure([tree.parent[x] for x in touched if tree.parent[x] >= 0]))
         if len(ops) == 0 and not self.update_leaves:
             return self.result if self.return_const_sum else self.logP
-        self.result = self.core.step(mat_nodes, P, ops, update_leaves=self.update_leaves)
+        if self.use_distances:
+            self.result = self.core.step_distances(mat_nodes, D, ops, update_leaves=self.update_leaves)
+        else:
+            self.result = self.core.step(mat_nodes, P, ops, update_leaves=self.update_leaves)
         self.has_dirt = IS_CLEAN
         self.update_leaves = False
         self.dirty_nodes = set()

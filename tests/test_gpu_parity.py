@@ -405,3 +405,68 @@ def test_mid_size_properties(core_mod):
     np.testing.assert_array_equal(one.pattern_log_likelihoods()[0], site)
     one.close()
     many.close()
+
+
+@pytest.mark.parametrize("asc,K,per_level", [("felsenstein_mean", 4, False), ("none", 4, False), ("felsenstein_mean", 3, False),
+                                            ("felsenstein_mean", 4, True)])
+def test_distance_fast_path_matches_oracle(core_mod, oracle, asc, K, per_level):
+    """sieve_set_distances: P = exp(Q d) formed on the device for SIEVE's fixed rate matrix, Q-specialised walk."""
+    d = synthetic(31, 555, seed=15)
+    counts, tree = d["counts"], d["tree"]
+    tree.height[tree.n + 3] = max(tree.height[tree.left[tree.n + 3]], tree.height[tree.right[tree.n + 3]])  # a zero-length branch
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    rates, props = substmodel.gamma_category_rates(0.6, K)
+    br = np.random.default_rng(1).lognormal(0, 0.3, tree.node_count)
+    mats = substmodel.node_matrices(tree, rates, branch_rates=br)
+    dist = substmodel.node_distances(tree, rates, branch_rates=br)
+    assert (dist[:tree.root] == 0).any()
+    S, n = counts.shape[:2]
+    out = {}
+    for mode in ("distances", "matrices"):
+        c = core_mod.ScsCudaLikelihoodCore(n, S, K, 4, True, asc != "none", True)
+        c.set_counts(counts)
+        c.set_size_factors(sf)
+        c.set_leaf_params(*PARAMS)
+        c.update_leaves(for_update=False)
+        c.set_root(tree.root, props, 0)
+        nodes = [i for i in range(tree.node_count) if i != tree.root]
+        if mode == "distances":
+            c.set_distances(nodes, dist[nodes], for_update=False)
+        else:
+            c.set_matrices(nodes, mats[nodes], for_update=False)
+        if per_level:
+            ops, off = tree.ops_by_level()
+            c.update_nodes(ops, off, flip=False, per_level=True)
+        else:
+            c.update_nodes(tree.ops(), flip=False)
+        r = c.evaluate()
+        out[mode] = (r, c.site_log_likelihoods(), c.get_node_partials(tree.root - 1), c)
+    logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, asc, 3000.0)
+    for mode in out:
+        r, (sl, sc), _, _ = out[mode]
+        _close(sl, osl, SITE_RTOL)
+        if asc != "none":
+            _close(sc, osc, SITE_RTOL)
+        got = core_mod.combine_shards([r], asc, 3000.0)
+        assert abs(got - logp) <= TOTAL_RTOL * abs(logp)
+    np.testing.assert_allclose(out["distances"][2], out["matrices"][2], rtol=1e-12, atol=1e-11)
+    # an incremental step through the fast path: new distance on one branch, dirty chain only
+    c = out["distances"][3]
+    c.store()
+    node = 5
+    dist2 = dist.copy()
+    dist2[node] *= 2.5
+    mats2 = mats.copy()
+    for k in range(K):
+        mats2[node, k] = substmodel.transition_probabilities(dist2[node, k]).reshape(16)
+    chain = tree.ops(tree.dirty_closure([tree.parent[node]]))
+    r = c.step_distances([node], dist2[[node]], chain)
+    logp2, osl2, _ = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats2, props, asc, 3000.0)
+    _close(c.site_log_likelihoods()[0], osl2, SITE_RTOL)
+    assert abs(core_mod.combine_shards([r], asc, 3000.0) - logp2) <= TOTAL_RTOL * abs(logp2)
+    c.restore()
+    c.update_nodes(tree.ops([tree.root]), flip=False)
+    c.evaluate()
+    np.testing.assert_array_equal(c.site_log_likelihoods()[0], out["distances"][1][0])
+    for mode in out:
+        out[mode][3].close()
