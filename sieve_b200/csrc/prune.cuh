@@ -72,13 +72,13 @@ __device__ __forceinline__ void sv_prefetch_l2(const void* p) { asm volatile("pr
 #define SV_PRUNE_MINB 5
 #endif
 #ifndef SV_PRUNE_NS_Q
-#define SV_PRUNE_NS_Q 2
+#define SV_PRUNE_NS_Q 1
 #endif
 #ifndef SV_PRUNE_MINB_CONST_Q
-#define SV_PRUNE_MINB_CONST_Q 4
+#define SV_PRUNE_MINB_CONST_Q 8
 #endif
 #ifndef SV_PRUNE_MINB_Q
-#define SV_PRUNE_MINB_Q 6
+#define SV_PRUNE_MINB_Q 8
 #endif
 #define SV_PRUNE_SITES_Q ((SV_PRUNE_THREADS / 4) * SV_PRUNE_NS_Q)
 

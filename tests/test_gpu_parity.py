@@ -470,3 +470,33 @@ def test_distance_fast_path_matches_oracle(core_mod, oracle, asc, K, per_level):
     np.testing.assert_array_equal(c.site_log_likelihoods()[0], out["distances"][1][0])
     for mode in out:
         out[mode][3].close()
+
+
+@pytest.mark.parametrize("mix,asc", [("stage1", "none"), ("stage2", "felsenstein_mean"), ("relaxed2", "felsenstein_mean")])
+def test_mcmc_replay_keeps_the_incremental_state_exact(core_mod, oracle, mix, asc):
+    """Hundreds of proposals (all operator classes, accept and reject) through store / step / restore; afterwards the
+    incrementally maintained log-likelihood must equal a from-scratch evaluation of the final state on the device AND
+    the oracle's evaluation of that state (tree, branch rates, parameters read back from the driver)."""
+    from sieve_b200.mcmc import McmcReplay, gamma_category_rates
+    d = synthetic(26, 400, seed=51)
+    counts, tree = d["counts"], d["tree"]
+    M = 6000.0
+    S, n = counts.shape[:2]
+    c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, asc != "none", True)
+    c.set_counts(counts)
+    sf, _ = c.compute_size_factors(0)
+    mc = McmcReplay(c, tree, mix=mix, asc_mode=asc, n_background_sites=M, seed=7)
+    st = mc.run(400)
+    assert st["states"] == 400 and 0 < st["accepted"] < 400 and st["likelihood_evaluations"] > 100
+    assert len(st["by_op"]) >= 7
+    state = mc.state()
+    t2 = state["tree"]
+    assert (t2.branch_lengths()[:t2.root] >= 0).all() and sorted(t2.post_order()) == list(range(n, 2 * n))
+    again = mc.full_recompute()
+    assert abs(again - state["log_p"]) <= 1e-11 * abs(again)
+    rates = gamma_category_rates(state["gamma_shape"], 4)
+    mats = substmodel.node_matrices(t2, rates, branch_rates=state["branch_rates"])
+    ref, _, _ = _oracle_eval(oracle, counts, t2, sf, state["leaf"], mats, np.full(4, 0.25), asc, M)
+    assert abs(state["log_p"] - ref) <= TOTAL_RTOL * abs(ref), (state["log_p"], ref)
+    mc.close()
+    c.close()

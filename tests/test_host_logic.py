@@ -104,3 +104,10 @@ def test_synthetic_generator_is_seeded_and_consistent():
     c = a["counts"]
     assert c.shape == (64, 8, 4) and (c[..., :3].sum(-1) <= c[..., 3]).all() and (c >= 0).all()
     assert 0.0 < (c[..., 3] == 0).mean() < 0.2
+
+
+def test_native_gamma_rates_match_scipy():
+    from sieve_b200.mcmc import gamma_category_rates
+    for a in (0.05, 0.5, 1.0, 3.7, 50.0):
+        ref, _ = substmodel.gamma_category_rates(a, 4)
+        np.testing.assert_allclose(gamma_category_rates(a, 4), ref, rtol=1e-9)
