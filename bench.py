@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-level", action="store_true", help="issue the pruning as one launch per tree level")
+    ap.add_argument("--mcmc-states", type=int, default=400, help="proposals per operator mix in the MCMC replay (0 = skip)")
     ap.add_argument("--matrices", action="store_true", help="hand the core 16-double matrices (generic kernel) instead of branch distances")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -281,7 +282,7 @@ def main():
     core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local)
     core.set_counts_device(counts_dev.data_ptr())
     # a host sample of this rank's sites for the parity spot check and the CPU baseline
-    n_keep = 1024
+    n_keep = min(S, 24576)
     sample = counts_dev[:, :n_keep, :].permute(1, 0, 2).contiguous().cpu().numpy()
     del counts_dev
     torch.cuda.empty_cache()
@@ -407,6 +408,30 @@ def main():
     torch.cuda.synchronize()
     tree_only_ms = ev0.elapsed_time(ev1) / args.steps
 
+    # ---------------- MCMC states/s: replay of the templates' operator schedules (native driver) ----------------
+    mcmc = {}
+    if args.mcmc_states > 0:
+        from sieve_b200.distributed import all_gather_results, result_to_tensor
+        from sieve_b200.mcmc import McmcReplay
+        for mix in ("stage1", "stage2", "relaxed2"):
+            mc = McmcReplay(core, tree, mix=mix, asc_mode="felsenstein_mean", n_background_sites=N_BACKGROUND,
+                            gamma_shape=1.0, leaf=PARAMS, branch_rates=br, seed=SEED)
+            if world > 1:
+                mc.set_combine(lambda r: combine_shards(all_gather_results(result_to_tensor(r, dev)),
+                                                        "felsenstein_mean", N_BACKGROUND))
+            mc.run(20)                      # warm-up
+            barrier()
+            st = mc.run(args.mcmc_states, reset=True)
+            barrier()
+            check = mc.full_recompute() if world == 1 else None
+            mcmc[mix] = {"states_per_s": st["states"] / st["seconds"], "states": st["states"],
+                         "acceptance": st["accepted"] / st["states"],
+                         "mean_nodes_recomputed": st["ops_total"] / max(1, st["likelihood_evaluations"]),
+                         "leaf_updates": st["leaf_updates"],
+                         "incremental_vs_full_recompute_rel": (abs(check - st["log_p"]) / abs(check)) if check else None,
+                         "ms_by_op": {k: 1000.0 * v["seconds"] / v["proposed"] for k, v in st["by_op"].items()}}
+            mc.close()
+
     # ---------------- parity spot check of this very workload against the oracle (outside the timed regions) ----------
     parity = None
     cpu = None
@@ -460,6 +485,8 @@ def main():
                         "leaf_frac": alg_leaf / (leaf_ms / 1000.0) / 1e9 / peak if leaf_ms > 0 else None,
                         "prune_ms": prune_ms, "reduce_ms": reduce_ms, "tree_only_eval_ms": tree_only_ms,
                         "tree_only_evals_per_s": 1000.0 / tree_only_ms},
+            "mcmc": mcmc,
+            "mcmc_states_per_s": mcmc.get("stage1", {}).get("states_per_s"),
             "device_bytes": core.device_bytes(),
             "parity": parity,
             "cpu_baseline": cpu,

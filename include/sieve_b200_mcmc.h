@@ -78,6 +78,11 @@ typedef struct {
 int sieve_mcmc_create(const sieve_mcmc_config_t *cfg, sieve_core_t *core, const int32_t *left, const int32_t *right,
                       const double *height, const double *branch_rates, sieve_mcmc_t **out);
 int sieve_mcmc_destroy(sieve_mcmc_t *m);
+/* Multi-shard chains: `combine` turns this shard's result into the log-likelihood of the WHOLE data set (the all-gather
+ * + fixed-order combine of sieve_combine_shards over ranks).  Every rank runs the same chain with the same seed and takes
+ * identical decisions because the combined value is bit-identical everywhere.  NULL restores the single-shard combine. */
+typedef double (*sieve_combine_fn)(const sieve_shard_result_t *local, void *user);
+int sieve_mcmc_set_combine(sieve_mcmc_t *m, sieve_combine_fn combine, void *user);
 /* runs n_states proposals; statistics accumulate over calls unless reset != 0 */
 int sieve_mcmc_run(sieve_mcmc_t *m, int64_t n_states, int32_t reset, sieve_mcmc_stats_t *out);
 /* the current tree (arrays of 2 n entries) and log-likelihood, e.g. to re-evaluate it from scratch as a check */

@@ -135,6 +135,8 @@ struct sieve_mcmc {
     std::vector<int> op_list;
     std::vector<int> stack, order;
     std::string err;
+    sieve_combine_fn combine = nullptr;
+    void* combine_user = nullptr;
 
     double unif() { return std::uniform_real_distribution<double>(0.0, 1.0)(rng); }
     int randint(int n) { return (int)std::uniform_int_distribution<int>(0, n - 1)(rng); }
@@ -207,7 +209,8 @@ int evaluate(sieve_mcmc* m, bool full, bool update_leaves, double* out_logp, int
     int rc = sieve_step_distances(m->core, update_leaves ? 1 : 0, *n_mats, m->mat_nodes.data(), m->dist.data(), *n_ops,
                                   m->op_list.data(), &r);
     if (rc != SIEVE_OK) return rc;
-    *out_logp = sieve_combine_shards(&r, 1, m->cfg.asc_mode, m->cfg.n_background_sites);
+    *out_logp = m->combine ? m->combine(&r, m->combine_user)
+                           : sieve_combine_shards(&r, 1, m->cfg.asc_mode, m->cfg.n_background_sites);
     return SIEVE_OK;
 }
 
@@ -581,6 +584,16 @@ extern "C" int sieve_mcmc_create(const sieve_mcmc_config_t* cfg, sieve_core_t* c
     m->stored_gamma_shape = m->gamma_shape;
     *out = m;
     return SIEVE_OK;
+}
+
+extern "C" int sieve_mcmc_set_combine(sieve_mcmc_t* m, sieve_combine_fn combine, void* user) {
+    if (!m) return SIEVE_ERR_INVALID;
+    m->combine = combine;
+    m->combine_user = user;
+    // the cached log-likelihood must be the global one from now on
+    int no = 0, nm = 0;
+    sieve_store(m->core);
+    return evaluate(m, true, false, &m->logp, &no, &nm);
 }
 
 extern "C" int sieve_mcmc_destroy(sieve_mcmc_t* m) {

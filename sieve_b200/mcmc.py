@@ -24,6 +24,7 @@ class McmcStats(C.Structure):
                 ("accepted_by_op", C.c_int64 * 13), ("seconds_by_op", C.c_double * 13)]
 
 
+COMBINE_FN = C.CFUNCTYPE(C.c_double, C.POINTER(_lib.ShardResult), C.c_void_p)
 _bound = False
 
 
@@ -41,6 +42,8 @@ def _bind():
         L.sieve_mcmc_get_state.argtypes = [vp, ip, ip, dp, dp, C.POINTER(LeafParams), dp, dp]
         L.sieve_mcmc_full_recompute.restype = C.c_int
         L.sieve_mcmc_full_recompute.argtypes = [vp, dp]
+        L.sieve_mcmc_set_combine.restype = C.c_int
+        L.sieve_mcmc_set_combine.argtypes = [vp, COMBINE_FN, vp]
         L.sieve_gamma_category_rates.restype = C.c_int
         L.sieve_gamma_category_rates.argtypes = [C.c_double, C.c_int32, dp]
         _bound = True
@@ -74,6 +77,14 @@ class McmcReplay:
                                        height.ctypes.data_as(dp), None if br is None else br.ctypes.data_as(dp),
                                        C.byref(h)))
         self.h = h
+
+    def set_combine(self, fn):
+        """fn(ShardResult) -> global log-likelihood (e.g. sieve_b200.distributed.global_log_p); None = single shard."""
+        if fn is None:
+            self._cb = COMBINE_FN()
+        else:
+            self._cb = COMBINE_FN(lambda r, user: float(fn(r.contents)))
+        check(self.L.sieve_mcmc_set_combine(self.h, self._cb, None))
 
     def close(self):
         if getattr(self, "h", None):
