@@ -408,6 +408,28 @@ def main():
     torch.cuda.synchronize()
     tree_only_ms = ev0.elapsed_time(ev1) / args.steps
 
+    # ---------------- parity spot check of this very workload against the oracle (outside the timed regions) ----------
+    parity = None
+    cpu = None
+    if rank == 0:
+        from oracle import sieve_oracle as so
+        so.build()
+        site_gpu, const_gpu = core.site_log_likelihoods()
+        n_chk = 16
+        c5 = so.counts5(sample[:n_chk])
+        _, osl, osc = so.full_eval(c5, sf, so.leaf_params(*PARAMS), tree.ops(), mats, props, tree.root, "none", 0.0,
+                                   min(so.max_threads(), n_chk))
+        parity = {"sites_checked": n_chk,
+                  "max_rel_site_logl": float(np.max(np.abs(site_gpu[:n_chk] - osl) / np.abs(osl))),
+                  "max_rel_site_const": float(np.max(np.abs(const_gpu[:n_chk] - osc) / np.abs(osc))),
+                  "logP": logp_last, "logP_repeatable": bool(logp_first == logp_last)}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = so.max_threads()
+            ns, dt, _ = cpu_eval_sample(tree, mats, props, sample, sf, threads)
+            cpu = {"value": (1.0 / dt) * ns / S, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": "one evaluation of %d of the %d sites (all %d cells) in %.1f s, site ranges over %d threads "
+                             "like ThreadedScsTreeLikelihood; evals/s scaled by %d/%d" % (ns, S, n, dt, threads, ns, S)}
+
     # ---------------- MCMC states/s: replay of the templates' operator schedules (native driver) ----------------
     mcmc = {}
     if args.mcmc_states > 0:
@@ -431,28 +453,6 @@ def main():
                          "incremental_vs_full_recompute_rel": (abs(check - st["log_p"]) / abs(check)) if check else None,
                          "ms_by_op": {k: 1000.0 * v["seconds"] / v["proposed"] for k, v in st["by_op"].items()}}
             mc.close()
-
-    # ---------------- parity spot check of this very workload against the oracle (outside the timed regions) ----------
-    parity = None
-    cpu = None
-    if rank == 0:
-        from oracle import sieve_oracle as so
-        so.build()
-        site_gpu, const_gpu = core.site_log_likelihoods()
-        n_chk = 16
-        c5 = so.counts5(sample[:n_chk])
-        _, osl, osc = so.full_eval(c5, sf, so.leaf_params(*PARAMS), tree.ops(), mats, props, tree.root, "none", 0.0,
-                                   min(so.max_threads(), n_chk))
-        parity = {"sites_checked": n_chk,
-                  "max_rel_site_logl": float(np.max(np.abs(site_gpu[:n_chk] - osl) / np.abs(osl))),
-                  "max_rel_site_const": float(np.max(np.abs(const_gpu[:n_chk] - osc) / np.abs(osc))),
-                  "logP": logp_last, "logP_repeatable": bool(logp_first == logp_last)}
-        if world == 1 and not args.no_cpu_baseline:
-            threads = so.max_threads()
-            ns, dt, _ = cpu_eval_sample(tree, mats, props, sample, sf, threads)
-            cpu = {"value": (1.0 / dt) * ns / S, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "one evaluation of %d of the %d sites (all %d cells) in %.1f s, site ranges over %d threads "
-                             "like ThreadedScsTreeLikelihood; evals/s scaled by %d/%d" % (ns, S, n, dt, threads, ns, S)}
 
     if rank == 0:
         peak, peak_src = measured_peak()

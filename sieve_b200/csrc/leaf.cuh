@@ -209,8 +209,13 @@ __global__ void __launch_bounds__(256, 4) k_leaf(SvLeafArgs a) {
     double* outX = a.leafX + (size_t)j * a.S * 4;
     double* outS = a.leafS + (size_t)j * a.S;
 
-    for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
-        const int4 c = __ldg(cnt + s);
+    // software pipeline: the count tuple of the next iteration is in flight while this one is evaluated
+    int s = s0 + threadIdx.x;
+    int4 cnext = make_int4(0, 0, 0, 0);
+    if (s < s1) cnext = __ldg(cnt + s);
+    for (; s < s1; s += blockDim.x) {
+        const int4 c = cnext;
+        if (s + (int)blockDim.x < s1) cnext = __ldg(cnt + s + blockDim.x);
         const int cov = c.w;
         const int ref = cov - (c.x + c.y + c.z);
         double N0, N1, N2, N3;
