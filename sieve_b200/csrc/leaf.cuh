@@ -176,7 +176,10 @@ struct SvLeafArgs {
     const double* size_factors;
     double* leafX;          // [cell][site][4]   (already offset to the write buffer)
     double* leafS;          // [cell][site]
-    int n_cells, S, C;
+    int n_cells, S, C;     // S = sites evaluated by this launch
+    long long counts_stride;  // sites per cell in `counts` (the whole shard)
+    long long site_begin;     // first site of this launch inside the shard (streamed evaluation walks site chunks)
+    long long out_stride;     // sites per cell in leafX / leafS (== S when resident, chunk capacity when streamed)
     int sites_per_block;
     SvDmAlphas al;
     SvCovParams cp;
@@ -205,9 +208,9 @@ __global__ void __launch_bounds__(256, 4) k_leaf(SvLeafArgs a) {
     const double sf = a.size_factors[j];
     const int s0 = blockIdx.x * a.sites_per_block;
     const int s1 = min(a.S, s0 + a.sites_per_block);
-    const int4* cnt = a.counts + (size_t)j * a.S;
-    double* outX = a.leafX + (size_t)j * a.S * 4;
-    double* outS = a.leafS + (size_t)j * a.S;
+    const int4* cnt = a.counts + (size_t)j * a.counts_stride + a.site_begin;
+    double* outX = a.leafX + (size_t)j * a.out_stride * 4;
+    double* outS = a.leafS + (size_t)j * a.out_stride;
 
     // software pipeline: the count tuple of the next iteration is in flight while this one is evaluated
     int s = s0 + threadIdx.x;

@@ -34,7 +34,8 @@ struct SvPruneArgs {
     const SvOp* ops;
     int op_begin, op_end;  // walk: ops [op_begin, op_end); per-level: op = op_begin + blockIdx.y
     int per_level;
-    int S, K;
+    int S, K;              // S = sites of this launch; the ops' rows were formed with the pools' site capacity
+    long long out_offset;  // first site of this launch in site_logl / site_const (streamed evaluation)
     int linear_const_clamp;  // !SIEVE_FLAG_LOG_PARTIALS: clamp of the constant-site product (:1041-1047)
     int const_genotype;
     int root_genotype;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
     }
 
     for (int i = i0; i < i1; i++) {
+        __syncwarp();  // scratch slots are reused (streamed mode): keep the warp's reads of an op ahead of the next op's writes
         const int4* opp = reinterpret_cast<const int4*>(a.ops + i);
         const int4 o0 = __ldg(opp), o1 = __ldg(opp + 1), o2 = __ldg(opp + 2);
         const long long dst_base = (long long)(unsigned)o0.x | ((long long)o0.y << 32);
@@ -410,12 +412,12 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
                 double v = active[j] ? a.prop[k] * (GENO0 ? x[j][0] : sv_sel(x[j], rg)) : 0.0;
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (site_ok[j] && k == 0) a.site_logl[site0 + 8 * j] = log(v) + xs[j];
+                if (site_ok[j] && k == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + xs[j];
                 if (WITH_CONST) {
                     double cv = active[j] ? a.prop[k] * (GENO0 ? cx[j][0] : sv_sel(cx[j], rg)) : 0.0;
                     cv += __shfl_xor_sync(0xffffffffu, cv, 1);
                     cv += __shfl_xor_sync(0xffffffffu, cv, 2);
-                    if (site_ok[j] && k == 0) a.site_const[site0 + 8 * j] = log(cv) + cxs[j];
+                    if (site_ok[j] && k == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + cxs[j];
                 }
             }
         }

@@ -93,7 +93,12 @@ struct sieve_core {
     size_t last_no = 0, last_nm = 0, last_nd = 0, last_off_mv = 0, last_off_ms = 0, last_off_dv = 0, last_off_ds = 0;
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
-    bool force_generic = false;  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
+    bool force_generic = false;
+    // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
+    int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
+    int n_slots = 0;     // scratch slots for internal partials
+    std::vector<int> eph_c1, eph_c2, eph_c1_stored, eph_c2_stored;  // children of every internal node (-2 = unset)
+    bool eph_leaves_dirty = true;  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
     std::vector<int> last_levels;
     bool last_per_level = false;
 
@@ -196,23 +201,40 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         sieve_destroy(h);
         return code;
     };
-    if (h->ephemeral) {
-        g_err = "sieve_create: SIEVE_FLAG_EPHEMERAL is not available in this build";
-        return fail(SIEVE_ERR_INVALID);
-    }
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) {
         g_err = std::string("cudaStreamCreate: ") + cudaGetErrorString(ce);
         return fail(SIEVE_ERR_CUDA);
     }
-    const size_t n = h->n, S = h->S, K = h->K;
+    const size_t n = h->n, S = h->S;
+    size_t pool_sites = S, part_slots = 2 * n, leaf_bufs = 2;
+    if (h->ephemeral) {
+        // scratch sized so that the per-chunk leaf partials stay around 4 GB; slots: Sethi-Ullman bound of the walk
+        size_t cap = std::max<size_t>(4096, ((size_t)4 << 30) / (40 * n));
+        if (const char* e = getenv("SIEVE_B200_CHUNK_SITES")) cap = std::max(32, atoi(e));
+        cap = std::min(S, cap);
+        cap = (cap + 31) / 32 * 32;
+        h->chunk_cap = (int)cap;
+        int lg = 1;
+        while (((size_t)1 << lg) < n) lg++;
+        h->n_slots = lg + 4;
+        pool_sites = cap;
+        part_slots = h->n_slots;
+        leaf_bufs = 1;
+        h->eph_c1.assign(h->n_nodes, -2);
+        h->eph_c2.assign(h->n_nodes, -2);
+        h->eph_c1_stored = h->eph_c1;
+        h->eph_c2_stored = h->eph_c2;
+    }
     // does the residency fit?
-    size_t need = n * S * 16 + 2 * n * S * 40 + 2 * n * S * (SV_KMAX * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
+    size_t need = n * S * 16 + leaf_bufs * n * pool_sites * 40 +
+                  part_slots * pool_sites * (SV_KMAX * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (need > free_b) {
-        g_err = "sieve_create: resident pools need " + std::to_string(need >> 20) + " MiB, device has " +
-                std::to_string(free_b >> 20) + " MiB free";
+        g_err = "sieve_create: the pools need " + std::to_string(need >> 20) + " MiB, the device has " +
+                std::to_string(free_b >> 20) + " MiB free" +
+                (h->ephemeral ? "" : " (SIEVE_FLAG_EPHEMERAL streams the evaluation instead of keeping partials resident)");
         return fail(SIEVE_ERR_OOM);
     }
     int r;
@@ -223,13 +245,13 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     } while (0)
     CR(sv_alloc(h, &h->d_counts, n * S));
     CR(sv_alloc(h, &h->d_sf, n));
-    CR(sv_alloc(h, &h->d_leafX, 2 * n * S * 4));
-    CR(sv_alloc(h, &h->d_leafS, 2 * n * S));
-    CR(sv_alloc(h, &h->d_part, 2 * n * S * SV_KMAX * 4));
-    CR(sv_alloc(h, &h->d_scale, 2 * n * S));
+    CR(sv_alloc(h, &h->d_leafX, leaf_bufs * n * pool_sites * 4));
+    CR(sv_alloc(h, &h->d_leafS, leaf_bufs * n * pool_sites));
+    CR(sv_alloc(h, &h->d_part, part_slots * pool_sites * SV_KMAX * 4));
+    CR(sv_alloc(h, &h->d_scale, part_slots * pool_sites));
     if (h->with_const) {
-        CR(sv_alloc(h, &h->d_cpart, 2 * n * S * SV_KMAX * 4));
-        CR(sv_alloc(h, &h->d_cscale, 2 * n * S));
+        CR(sv_alloc(h, &h->d_cpart, part_slots * pool_sites * SV_KMAX * 4));
+        CR(sv_alloc(h, &h->d_cscale, part_slots * pool_sites));
     }
     CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * SV_KMAX * 16));
     CR(sv_alloc(h, &h->d_qfac, (size_t)2 * h->n_nodes * SV_KMAX));
@@ -451,7 +473,8 @@ extern "C" int sieve_set_leaf_params(sieve_core_t* h, const sieve_leaf_params_t*
     return SIEVE_OK;
 }
 
-static int sv_launch_leaves(sieve_core* h) {
+// site_begin / n_sites: the range of the shard to evaluate; out_stride: site capacity of the leaf pool it goes to
+static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, long long out_stride) {
     const SvDmAlphas al = sv_dm_alphas(h->lp.eff_seq_err_rate, h->lp.shape_ctrl1, h->lp.shape_ctrl2);
     SvCovParams cp;
     cp.t = h->lp.allelic_seq_cov;
@@ -486,10 +509,13 @@ static int sv_launch_leaves(sieve_core* h) {
     a.dmB = h->d_dmB;
     a.cellT = h->d_cellT;
     a.size_factors = h->d_sf;
-    a.leafX = h->d_leafX + (size_t)h->cur_leaf * h->n * h->S * 4;
-    a.leafS = h->d_leafS + (size_t)h->cur_leaf * h->n * h->S;
+    a.leafX = h->d_leafX + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S * 4);
+    a.leafS = h->d_leafS + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S);
     a.n_cells = h->n;
-    a.S = h->S;
+    a.S = n_sites;
+    a.counts_stride = h->S;
+    a.site_begin = site_begin;
+    a.out_stride = out_stride;
     a.C = C;
     a.al = al;
     a.cp = cp;
@@ -497,10 +523,10 @@ static int sv_launch_leaves(sieve_core* h) {
     const size_t smem = (size_t)C * 10 * sizeof(double);
     const bool use_smem = smem <= 100 * 1024;
     int splits = std::max(1, (148 * 8 + h->n - 1) / h->n);
-    int spb = std::max(use_smem ? 2048 : 256, (h->S + splits - 1) / splits);
+    int spb = std::max(use_smem ? 2048 : 256, (n_sites + splits - 1) / splits);
     spb = (spb + 255) / 256 * 256;
     a.sites_per_block = spb;
-    dim3 grid((h->S + spb - 1) / spb, h->n);
+    dim3 grid((n_sites + spb - 1) / spb, h->n);
     if (use_smem) {
         if (!h->leaf_attr_set) {
             SV_CUDA(cudaFuncSetAttribute(k_leaf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -520,11 +546,17 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
     if (!h->have_counts || !h->have_sf || !h->have_params)
         return sv_fail(SIEVE_ERR_STATE, "sieve_update_leaves: counts, size factors and leaf parameters must be set first");
     SV_CUDA(cudaSetDevice(h->device));
+    if (h->ephemeral) {
+        // streamed mode: the leaves are recomputed chunk by chunk inside every evaluation; nothing to do now
+        h->leaves_ready = true;
+        h->eph_leaves_dirty = true;
+        return SIEVE_OK;
+    }
     if (for_update) h->cur_leaf = 1 - h->cur_leaf;
     if (h->timing) {
         SV_CUDA(cudaEventRecord(h->ev[0], h->stream));
     }
-    SV_TRY(sv_launch_leaves(h));
+    SV_TRY(sv_launch_leaves(h, 0, h->S, h->S));
     if (h->timing) {
         SV_CUDA(cudaEventRecord(h->ev[1], h->stream));
         h->leaf_timed = true;
@@ -650,6 +682,7 @@ extern "C" int sieve_set_distances(sieve_core_t* h, int32_t count, const int32_t
 extern "C" int sieve_set_node_partials_for_update(sieve_core_t* h, int32_t node) {
     SV_REQUIRE(h && sv_node_ok(h, node), "sieve_set_node_partials_for_update: bad node");
     if (node < h->n) return sv_fail(SIEVE_ERR_INVALID, "leaves flip together: use sieve_update_leaves(for_update = 1)");
+    if (h->ephemeral) return SIEVE_OK;  // no resident partials to flip
     h->cur_part[node] = 1 - h->cur_part[node];
     return SIEVE_OK;
 }
@@ -703,6 +736,104 @@ static void sv_link_forwarding(std::vector<SvOp>& ops, bool per_level) {
     }
 }
 
+// ---- streamed (ephemeral) evaluation: the host keeps parent -> children and regenerates the walk every time --------
+static int sv_record_children(sieve_core* h, int c1, int c2, int parent) {
+    const int n = h->n;
+    SV_REQUIRE(parent >= n && parent < h->n_nodes, "op: parent must be an internal node");
+    SV_REQUIRE(c1 >= 0 && c1 < h->n_nodes && c1 != h->root, "op: bad child1");
+    SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
+    h->eph_c1[parent] = c1;
+    h->eph_c2[parent] = c2;
+    return SIEVE_OK;
+}
+
+// Post-order over the whole tree with the child that needs more scratch first (Sethi-Ullman), scratch slots assigned
+// from a free list: a binary tree of n leaves needs at most ~log2(n) + 2 live partials.
+static int sv_build_streamed_ops(sieve_core* h) {
+    const int n = h->n, N = h->n_nodes, root = h->root;
+    const long long cap = h->chunk_cap;
+    std::vector<int> order;  // children before parents
+    order.reserve(n);
+    std::vector<std::pair<int, int>> st;
+    st.push_back({root, 0});
+    while (!st.empty()) {
+        auto [v, state] = st.back();
+        st.pop_back();
+        if (v < n) continue;
+        if (h->eph_c1[v] == -2) return sv_fail(SIEVE_ERR_STATE, "streamed evaluation: node " + std::to_string(v) + " has no children set yet");
+        if (state == 0) {
+            st.push_back({v, 1});
+            if (h->eph_c2[v] >= 0) st.push_back({h->eph_c2[v], 0});
+            st.push_back({h->eph_c1[v], 0});
+        } else
+            order.push_back(v);
+    }
+    std::vector<int> need(N, 0);
+    for (int v : order) {
+        int a = h->eph_c1[v], b = h->eph_c2[v];
+        int na = a >= n ? need[a] : 0, nb = (b >= n) ? need[b] : 0;
+        if (na < nb) std::swap(na, nb);
+        const int internal = (a >= n) + (b >= n);
+        need[v] = internal == 0 ? 1 : (internal == 1 ? std::max(na, 2) : std::max(std::max(na, nb + 1), 3));
+    }
+    if (need[root] > h->n_slots)
+        return sv_fail(SIEVE_ERR_STATE, "streamed evaluation: the tree needs " + std::to_string(need[root]) + " scratch slots, " +
+                                            std::to_string(h->n_slots) + " allocated");
+    std::vector<int> free_slots;
+    for (int s = h->n_slots - 1; s >= 0; s--) free_slots.push_back(s);
+    std::vector<int> slot_of(N, -1);
+    h->pending_ops.clear();
+    h->pending_levels.clear();
+    h->pending_per_level = false;
+    st.push_back({root, 0});
+    while (!st.empty()) {
+        auto [v, state] = st.back();
+        st.pop_back();
+        if (v < n) continue;
+        int a = h->eph_c1[v], b = h->eph_c2[v];
+        if (state == 0) {
+            st.push_back({v, 1});
+            // heavier child first == pushed last
+            const int na = a >= n ? need[a] : 0, nb = b >= n ? need[b] : 0;
+            if (na >= nb) {
+                if (b >= n) st.push_back({b, 0});
+                if (a >= n) st.push_back({a, 0});
+            } else {
+                if (a >= n) st.push_back({a, 0});
+                if (b >= n) st.push_back({b, 0});
+            }
+        } else {
+            SvOp op;
+            op.flags = 0;
+            op.pad = 0;
+            const int dst = free_slots.back();
+            free_slots.pop_back();
+            slot_of[v] = dst;
+            op.dst_row = (long long)dst * cap;
+            auto child = [&](int c, int leaf_flag, long long* row, int* m) {
+                if (c < n) {
+                    op.flags |= leaf_flag;
+                    *row = (long long)c * cap;
+                } else
+                    *row = (long long)slot_of[c] * cap;
+                *m = h->cur_mat[c] * N + c;
+            };
+            child(a, SV_OP_LEAF1, &op.c1_row, &op.m1);
+            if (b < 0) {
+                op.flags |= SV_OP_UNARY;
+                op.c2_row = 0;
+                op.m2 = 0;
+            } else
+                child(b, SV_OP_LEAF2, &op.c2_row, &op.m2);
+            if (v == root) op.flags |= SV_OP_ROOT;
+            h->pending_ops.push_back(op);
+            if (a >= n) free_slots.push_back(slot_of[a]);
+            if (b >= n) free_slots.push_back(slot_of[b]);
+        }
+    }
+    return SIEVE_OK;
+}
+
 extern "C" int sieve_calculate_partials(sieve_core_t* h, int32_t child1, int32_t is_leaf1, int32_t child2, int32_t is_leaf2,
                                         int32_t parent, int32_t const_genotype) {
     SV_REQUIRE(h, "null handle");
@@ -711,6 +842,7 @@ extern "C" int sieve_calculate_partials(sieve_core_t* h, int32_t child1, int32_t
     SV_REQUIRE(child2 < 0 || ((child2 < h->n) == (is_leaf2 != 0)),
                "sieve_calculate_partials: is_leaf2 contradicts the node numbering");
     h->const_genotype = const_genotype;
+    if (h->ephemeral) return sv_record_children(h, child1, child2, parent);
     SvOp op;
     SV_TRY(sv_make_op(h, child1, child2, parent, &op));
     if (!h->pending_levels.empty()) {  // mixing with a level-batched update: fall back to one group
@@ -724,6 +856,11 @@ extern "C" int sieve_calculate_partials(sieve_core_t* h, int32_t child1, int32_t
 extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t* ops, const int32_t* level_offsets,
                                   int32_t n_levels, uint32_t mode) {
     SV_REQUIRE(h && n_ops >= 0 && (n_ops == 0 || ops), "sieve_update_nodes: bad argument");
+    if (h->ephemeral) {
+        // streamed mode: every evaluation walks the whole tree; an update only edits the parent -> children map
+        for (int i = 0; i < n_ops; i++) SV_TRY(sv_record_children(h, ops[3 * i + 1], ops[3 * i + 2], ops[3 * i]));
+        return SIEVE_OK;
+    }
     const bool per_level = (mode & SIEVE_UPDATE_PER_LEVEL) && level_offsets && n_levels > 0;
     if (per_level) {
         SV_REQUIRE(h->pending_ops.empty(), "sieve_update_nodes: per-level update with other ops pending");
@@ -803,6 +940,7 @@ static int sv_launch_staged(sieve_core* h) {
         a.clamp_zero_distance = h->log_mode ? 1 : 0;
         a.ops = (const SvOp*)(h->d_stage);
         a.S = h->S;
+        a.out_offset = 0;
         a.K = K;
         a.linear_const_clamp = h->log_mode ? 0 : 1;
         a.const_genotype = h->const_genotype;
@@ -821,7 +959,19 @@ static int sv_launch_staged(sieve_core* h) {
                 sv_launch_prune_t<false>(h, grid, a);
             sv_count(h);
         };
-        if (h->last_per_level) {
+        if (h->ephemeral) {
+            // streamed evaluation: per site chunk, leaves from the counts, then the whole walk on scratch slots
+            a.op_begin = 0;
+            a.op_end = (int)no;
+            a.per_level = 0;
+            for (long long s0 = 0; s0 < h->S; s0 += h->chunk_cap) {
+                const int ns = (int)std::min<long long>(h->chunk_cap, h->S - s0);
+                SV_TRY(sv_launch_leaves(h, s0, ns, h->chunk_cap));
+                a.S = ns;
+                a.out_offset = s0;
+                launch(dim3((unsigned)((ns + spb - 1) / spb)));
+            }
+        } else if (h->last_per_level) {
             for (size_t l = 0; l + 1 < h->last_levels.size(); l++) {
                 const int b = h->last_levels[l], e = h->last_levels[l + 1];
                 if (e <= b) continue;
@@ -846,6 +996,7 @@ static int sv_launch_staged(sieve_core* h) {
 // uploads pending matrices / distances + ops with ONE host->device copy and launches scatter + pruning
 static int sv_flush(sieve_core* h) {
     const int K = h->K;
+    if (h->ephemeral) SV_TRY(sv_build_streamed_ops(h));
     const size_t no = h->pending_ops.size();
     size_t nm = 0, nd = 0;
     for (const PendingMatrix& pm : h->pending_mats) (pm.is_distance ? nd : nm)++;
@@ -984,7 +1135,7 @@ extern "C" int sieve_replay(sieve_core_t* h, int32_t update_leaves, int32_t n_ti
     for (int i = 0; i < n_times; i++) {
         if (update_leaves) {
             h->dm_dirty = h->cov_dirty = true;  // a parameter proposal rebuilds the tables
-            SV_TRY(sv_launch_leaves(h));
+            if (!h->ephemeral) SV_TRY(sv_launch_leaves(h, 0, h->S, h->S));
         }
         SV_TRY(sv_launch_staged(h));
         k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, h->d_site_const, h->d_weights, h->S,
@@ -1014,6 +1165,7 @@ extern "C" int sieve_get_result_device_ptr(sieve_core_t* h, void** d_result) {
 extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t which, double* out) {
     SV_REQUIRE(h && out && sv_node_ok(h, node), "sieve_get_node_partials: bad argument");
     SV_REQUIRE(which == 0 || which == 1, "sieve_get_node_partials: which must be 0 or 1");
+    if (h->ephemeral) return sv_fail(SIEVE_ERR_STATE, "sieve_get_node_partials: a streamed (SIEVE_FLAG_EPHEMERAL) core keeps no partials");
     SV_CUDA(cudaSetDevice(h->device));
     SV_TRY(sv_flush(h));
     const size_t S = h->S, K = h->K, n = h->n;
@@ -1049,6 +1201,10 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->stored_part = h->cur_part;
     h->stored_mat = h->cur_mat;
     h->stored_leaf = h->cur_leaf;
+    if (h->ephemeral) {
+        h->eph_c1_stored = h->eph_c1;
+        h->eph_c2_stored = h->eph_c2;
+    }
     return SIEVE_OK;
 }
 extern "C" int sieve_unstore(sieve_core_t* h) {
@@ -1056,6 +1212,10 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
     h->cur_part = h->stored_part;
     h->cur_mat = h->stored_mat;
     h->cur_leaf = h->stored_leaf;
+    if (h->ephemeral) {
+        h->eph_c1 = h->eph_c1_stored;
+        h->eph_c2 = h->eph_c2_stored;
+    }
     return SIEVE_OK;
 }
 extern "C" int sieve_restore(sieve_core_t* h) {
@@ -1063,6 +1223,10 @@ extern "C" int sieve_restore(sieve_core_t* h) {
     h->cur_part.swap(h->stored_part);
     h->cur_mat.swap(h->stored_mat);
     std::swap(h->cur_leaf, h->stored_leaf);
+    if (h->ephemeral) {
+        h->eph_c1.swap(h->eph_c1_stored);
+        h->eph_c2.swap(h->eph_c2_stored);
+    }
     // after a rejected parameter proposal the tables hold the rejected values; they are compared with the values of
     // the next sieve_set_leaf_params at the next leaf update, so nothing has to be rebuilt here
     return SIEVE_OK;

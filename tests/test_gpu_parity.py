@@ -500,3 +500,71 @@ def test_mcmc_replay_keeps_the_incremental_state_exact(core_mod, oracle, mix, as
     assert abs(state["log_p"] - ref) <= TOTAL_RTOL * abs(ref), (state["log_p"], ref)
     mc.close()
     c.close()
+
+
+def test_streamed_evaluation_equals_resident(core_mod, oracle, monkeypatch):
+    """SIEVE_FLAG_EPHEMERAL: site chunks, leaves recomputed per chunk, internal partials on a few reused scratch slots.
+    Same arithmetic per site => bit-identical site log-likelihoods; also through store / propose / restore."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    monkeypatch.setenv("SIEVE_B200_CHUNK_SITES", "96")      # 5 chunks, the last one ragged
+    d = synthetic(45, 437, seed=61)
+    counts, tree = d["counts"], d["tree"]
+    M = 2500.0
+    res = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=M)
+    eph = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=M, ephemeral=True,
+                            size_factors=res.size_factors)
+    a, b = res.calculate_logp(), eph.calculate_logp()
+    np.testing.assert_array_equal(eph.pattern_log_likelihoods()[0], res.pattern_log_likelihoods()[0])
+    np.testing.assert_array_equal(eph.pattern_log_likelihoods()[1], res.pattern_log_likelihoods()[1])
+    assert a == b
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    ref, _, _ = _oracle_eval(oracle, counts, tree, res.size_factors, PARAMS, substmodel.node_matrices(tree, rates), props,
+                             "felsenstein_mean", M)
+    assert abs(b - ref) <= TOTAL_RTOL * abs(ref)
+    rng = np.random.default_rng(5)
+    for it in range(6):
+        t2 = eph.tree.copy()
+        node = int(rng.integers(tree.n, tree.node_count - 1))
+        lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+        t2.height[node] = lo + (t2.height[t2.parent[node]] - lo) * rng.random()
+        for tl in (res, eph):
+            tl.store()
+            tl.set_tree(t2.copy(), [node])
+        a, b = res.calculate_logp(), eph.calculate_logp()
+        assert a == b
+        if it % 2:
+            for tl in (res, eph):
+                tl.restore()
+    # a leaf-parameter proposal and its rejection
+    from sieve_b200.treelikelihood import LeafModelParams
+    for tl in (res, eph):
+        tl.store()
+        tl.set_leaf_params(LeafModelParams(0.2, 40.0, 70.0, 0.02, 100.0, 3.0))
+    assert res.calculate_logp() == eph.calculate_logp()
+    for tl in (res, eph):
+        tl.restore()
+        tl.has_dirt = 2
+    assert res.calculate_logp() == eph.calculate_logp()
+    with pytest.raises(Exception):
+        eph.core.get_node_partials(tree.n)
+    res.close()
+    eph.close()
+
+
+def test_streamed_mcmc_replay(core_mod, oracle, monkeypatch):
+    from sieve_b200.mcmc import McmcReplay, gamma_category_rates
+    monkeypatch.setenv("SIEVE_B200_CHUNK_SITES", "128")
+    d = synthetic(20, 300, seed=71)
+    counts, tree = d["counts"], d["tree"]
+    c = core_mod.ScsCudaLikelihoodCore(20, 300, 4, 4, True, True, True, ephemeral=True)
+    c.set_counts(counts)
+    sf, _ = c.compute_size_factors(0)
+    mc = McmcReplay(c, tree, mix="stage1", asc_mode="felsenstein_mean", n_background_sites=900.0, seed=3)
+    st = mc.run(150)
+    state = mc.state()
+    rates = gamma_category_rates(state["gamma_shape"], 4)
+    mats = substmodel.node_matrices(state["tree"], rates, branch_rates=state["branch_rates"])
+    ref, _, _ = _oracle_eval(oracle, counts, state["tree"], sf, state["leaf"], mats, np.full(4, 0.25), "felsenstein_mean", 900.0)
+    assert 0 < st["accepted"] < 150 and abs(state["log_p"] - ref) <= TOTAL_RTOL * abs(ref)
+    mc.close()
+    c.close()
