@@ -36,7 +36,8 @@ N_BACKGROUND = 1.0e7
 PARAMS = (0.3, 50.0, 50.0, 0.008, 150.0, 2.0)   # theta, t, v, eps, w1, w2 (examples/templates/smc_stage_1.xml:30-38)
 SEED = 20260101
 METRIC = "loglik_evals_per_sec"
-UNIT = "evals/s (one eval = leaf + full-tree pruning + root + reduce over 1,000 cells x 100,000 sites; at N GPUs each rank evaluates one such shard per step)"
+UNIT = ("evals/s (one eval = leaf + full-tree pruning + root + reduce over {:,} cells x {:,} sites; at N GPUs each rank "
+        "evaluates one such shard per step)").format(N_CELLS, N_SITES)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -55,8 +56,8 @@ def make_tree_and_matrices(seed, n):
     return tree, rates, props, br, mats
 
 
-def generate_counts_device(tree, rates, br, n, S, seed, device):
-    """int32 [cell][site][4] on `device`."""
+def generate_counts_device(tree, rates, br, n, S, seed, device, chunk=None):
+    """int32 [cell][site][4] on `device`, generated in site chunks so that the temporaries stay small."""
     import torch
 
     from sieve_b200 import substmodel
@@ -66,28 +67,14 @@ def generate_counts_device(tree, rates, br, n, S, seed, device):
     torch.cuda.manual_seed_all(seed)
     theta, t, v, eps, w1, w2 = PARAMS
     bl = tree.branch_lengths()
-    cat = torch.randint(0, K_CAT, (S,), device=device, generator=g)
-    geno = torch.zeros((tree.node_count, S), dtype=torch.int64, device=device)
-    for p in tree.post_order()[::-1]:
+    order = tree.post_order()[::-1]
+    cums = {}
+    for p in order:
         for c in (tree.left[p], tree.right[p]):
-            if c < 0:
-                continue
-            cum = torch.tensor(np.stack([np.cumsum(substmodel.transition_probabilities(bl[c] * br[c] * rates[k]), axis=1)
-                                         for k in range(K_CAT)]), device=device)          # [K][4][4]
-            rows = cum[cat, geno[p]]                                                      # [S][4]
-            u = torch.rand(S, device=device, generator=g, dtype=torch.float64)
-            geno[c] = (u[:, None] > rows[:, :3]).sum(1)
-    gl = geno[:n]                                                                         # [n][S]
-    del geno
+            if c >= 0:
+                cums[c] = torch.tensor(np.stack([np.cumsum(substmodel.transition_probabilities(bl[c] * br[c] * rates[k]),
+                                                           axis=1) for k in range(K_CAT)]), device=device)   # [K][4][4]
     sf = torch.exp(0.3 * torch.randn(n, device=device, generator=g, dtype=torch.float64))
-    ado = torch.rand((n, S), device=device, generator=g) < theta
-    alleles = torch.where(ado, 1.0, 2.0).to(torch.float64)
-    mean = alleles * t * sf[:, None]
-    r = t * t / v
-    lam = torch._standard_gamma(torch.full((n, S), r, device=device, dtype=torch.float64)) * (mean / r)
-    cov = torch.poisson(lam, generator=g)
-    cov[torch.rand((n, S), device=device, generator=g) < 0.05] = 0.0
-    del lam, mean
     f = eps / 3.0
     table = torch.tensor([[f * w1, f * w1, f * w1, (1 - eps) * w1],          # 0: 0/0
                           [(1 - eps) * w1, f * w1, f * w1, f * w1],          # 1: 1/1
@@ -95,31 +82,53 @@ def generate_counts_device(tree, rates, br, n, S, seed, device):
                           [(.5 - f) * w2, f * w2, f * w2, (.5 - f) * w2],    # 3: 0/1
                           [f * w1, (1 - eps) * w1, f * w1, f * w1]],         # 4: 1'/1' (one allele of 1/1' left)
                          device=device, dtype=torch.float32)
-    coin = torch.rand((n, S), device=device, generator=g) < 0.5
-    idx = torch.zeros((n, S), dtype=torch.int64, device=device)
-    idx[(gl == 1) & ~ado] = 3
-    idx[(gl == 1) & ado & coin] = 1
-    idx[gl == 2] = 1
-    idx[(gl == 3) & ~ado] = 2
-    idx[(gl == 3) & ado & coin] = 1
-    idx[(gl == 3) & ado & ~coin] = 4
-    del gl, ado, coin
     out = torch.zeros((n, S, 4), dtype=torch.int32, device=device)
-    remaining = cov.clone()
-    # Dirichlet-multinomial by sequential beta-binomials, one component at a time to bound memory
-    alpha = table[idx]                                                                    # [n][S][4] float32
-    del idx
-    gam = torch._standard_gamma(alpha.clamp_min(1e-3))
-    del alpha
-    rest = gam.sum(-1).to(torch.float64)
-    for i in range(3):
-        gi = gam[..., i].to(torch.float64)
-        q = (gi / rest.clamp_min(1e-300)).clamp(0.0, 1.0)
-        x = torch.binomial(remaining, q, generator=g)
-        out[..., i] = x.to(torch.int32)
-        remaining -= x
-        rest -= gi
-    out[..., 3] = cov.to(torch.int32)
+    if chunk is None:
+        chunk = max(256, min(S, int(2.0e8 // n)))
+    for s0 in range(0, S, chunk):
+        ns = min(chunk, S - s0)
+        cat = torch.randint(0, K_CAT, (ns,), device=device, generator=g)
+        geno = torch.zeros((tree.node_count, ns), dtype=torch.int64, device=device)
+        for p in order:
+            for c in (tree.left[p], tree.right[p]):
+                if c < 0:
+                    continue
+                rows = cums[c][cat, geno[p]]                                              # [ns][4]
+                u = torch.rand(ns, device=device, generator=g, dtype=torch.float64)
+                geno[c] = (u[:, None] > rows[:, :3]).sum(1)
+        gl = geno[:n]                                                                     # [n][ns]
+        del geno
+        ado = torch.rand((n, ns), device=device, generator=g) < theta
+        mean = torch.where(ado, 1.0, 2.0).to(torch.float64) * t * sf[:, None]
+        r = t * t / v
+        lam = torch._standard_gamma(torch.full((n, ns), r, device=device, dtype=torch.float64)) * (mean / r)
+        cov = torch.poisson(lam, generator=g)
+        cov[torch.rand((n, ns), device=device, generator=g) < 0.05] = 0.0
+        del lam, mean
+        coin = torch.rand((n, ns), device=device, generator=g) < 0.5
+        idx = torch.zeros((n, ns), dtype=torch.int64, device=device)
+        idx[(gl == 1) & ~ado] = 3
+        idx[(gl == 1) & ado & coin] = 1
+        idx[gl == 2] = 1
+        idx[(gl == 3) & ~ado] = 2
+        idx[(gl == 3) & ado & coin] = 1
+        idx[(gl == 3) & ado & ~coin] = 4
+        del gl, ado, coin
+        # Dirichlet-multinomial by sequential beta-binomials
+        gam = torch._standard_gamma(table[idx].clamp_min(1e-3))                           # [n][ns][4] float32
+        del idx
+        rest = gam.sum(-1).to(torch.float64)
+        remaining = cov.clone()
+        o = out[:, s0:s0 + ns, :]
+        for i in range(3):
+            gi = gam[..., i].to(torch.float64)
+            q = (gi / rest.clamp_min(1e-300)).clamp(0.0, 1.0)
+            x = torch.binomial(remaining, q, generator=g)
+            o[..., i] = x.to(torch.int32)
+            remaining -= x
+            rest -= gi
+        o[..., 3] = cov.to(torch.int32)
+        del gam, rest, remaining, cov
     return out
 
 
@@ -252,6 +261,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-level", action="store_true", help="issue the pruning as one launch per tree level")
     ap.add_argument("--mcmc-states", type=int, default=400, help="proposals per operator mix in the MCMC replay (0 = skip)")
+    ap.add_argument("--streamed", action="store_true", help="SIEVE_FLAG_EPHEMERAL: no resident partials (shapes that exceed HBM, e.g. SIEVE_BENCH_CELLS=10000 SIEVE_BENCH_SITES=125000)")
     ap.add_argument("--matrices", action="store_true", help="hand the core 16-double matrices (generic kernel) instead of branch distances")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -280,10 +290,10 @@ def main():
     counts_dev = generate_counts_device(tree, rates, br, n, S, SEED + 17 * rank, dev)
     torch.cuda.synchronize()
 
-    core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local)
+    core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local, ephemeral=args.streamed)
     core.set_counts_device(counts_dev.data_ptr())
     # a host sample of this rank's sites for the parity spot check and the CPU baseline
-    n_keep = min(S, 24576)
+    n_keep = min(S, 64 if (args.no_cpu_baseline or world > 1) else max(64, int(2.4e7 // n)))
     sample = counts_dev[:, :n_keep, :].permute(1, 0, 2).contiguous().cpu().numpy()
     del counts_dev
     torch.cuda.empty_cache()
@@ -471,7 +481,8 @@ def main():
             "config": {"workload": "synthetic %d cells x %d sites per GPU, K=4 gamma categories, relaxed-clock branch rates, "
                                    "felsenstein acquisition-bias correction (BASELINE.json configs[2])" % (n, S),
                        "step": "leaf recompute + all %d internal nodes + root + reduce" % (tree.n),
-                       "schedule": "per-level launches" if args.per_level else "single-launch walk",
+                       "schedule": ("streamed: site chunks, leaves + walk on scratch slots" if args.streamed else
+                                    "per-level launches" if args.per_level else "single-launch walk"),
                        "transition_matrices": "16-double matrices from the host" if args.matrices else "branch distances, P formed on the device (fixed Q)",
                        "l2": "inputs larger than L2 (%.1f GB of partials per evaluation)" % (alg_prune / 1e9),
                        "parallelism": "site shards x%d, all-gather of 5 doubles per rank" % world},
