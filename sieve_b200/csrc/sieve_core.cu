@@ -210,7 +210,15 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     size_t pool_sites = S, part_slots = 2 * n, leaf_bufs = 2;
     if (h->ephemeral) {
         // scratch sized so that the per-chunk leaf partials stay around 4 GB; slots: Sethi-Ullman bound of the walk
-        size_t cap = std::max<size_t>(4096, ((size_t)4 << 30) / (40 * n));
+        // chunk: large enough to fill the GPU a few times over (>= 3 full waves of 32-site blocks), bounded by a
+        // leaf-scratch budget of a quarter of the free memory (at most 48 GB)
+        size_t free0 = 0, total0 = 0;
+        cudaMemGetInfo(&free0, &total0);
+        const size_t counts_bytes = n * S * 16;
+        const size_t avail = free0 > counts_bytes ? free0 - counts_bytes : 0;
+        const size_t budget = std::min<size_t>((size_t)48 << 30, avail / 4);
+        size_t cap = std::max<size_t>(4096, budget / (40 * n));
+        cap = std::min<size_t>(cap, (size_t)148 * 8 * 32 * 4);
         if (const char* e = getenv("SIEVE_B200_CHUNK_SITES")) cap = std::max(32, atoi(e));
         cap = std::min(S, cap);
         cap = (cap + 31) / 32 * 32;
