@@ -229,7 +229,11 @@ __global__ void __launch_bounds__(256, 4) k_leaf(SvLeafArgs a) {
             // LP terms: table when the count is inside it, else the same formula evaluated directly
             auto lpA = [&](int cval, double (&o)[4]) {
                 const int ci = cval < 0 ? 0 : cval;
-                if (ci < C) {
+                if (ci == 0) {
+                    // LP(0, .) == 0 (DirichletMultinomial.java:49): most alt counts are 0, and skipping the look-up keeps
+                    // the shared-memory pipe (the bound of this kernel) for the entries that carry information
+                    o[0] = o[1] = o[2] = o[3] = 0.0;
+                } else if (ci < C) {
                     const double2 u = *reinterpret_cast<const double2*>(dmA + 4 * ci);
                     const double2 w = *reinterpret_cast<const double2*>(dmA + 4 * ci + 2);
                     o[0] = u.x; o[1] = u.y; o[2] = w.x; o[3] = w.y;
