@@ -185,8 +185,14 @@ struct SvLeafArgs {
     SvCovParams cp;
 };
 
+#ifndef SV_LEAF_MINB
+#define SV_LEAF_MINB 3
+#endif
+#ifndef SV_LEAF_PREFETCH
+#define SV_LEAF_PREFETCH 1
+#endif
 template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(256, 4) k_leaf(SvLeafArgs a) {
+__global__ void __launch_bounds__(256, SV_LEAF_MINB) k_leaf(SvLeafArgs a) {
     extern __shared__ double sm[];
     const int j = blockIdx.y;
     const int C = a.C;
@@ -217,8 +223,14 @@ __global__ void __launch_bounds__(256, 4) k_leaf(SvLeafArgs a) {
     int4 cnext = make_int4(0, 0, 0, 0);
     if (s < s1) cnext = __ldg(cnt + s);
     for (; s < s1; s += blockDim.x) {
+#if SV_LEAF_PREFETCH
         const int4 c = cnext;
+#else
+        const int4 c = __ldg(cnt + s);
+#endif
+#if SV_LEAF_PREFETCH
         if (s + (int)blockDim.x < s1) cnext = __ldg(cnt + s + blockDim.x);
+#endif
         const int cov = c.w;
         const int ref = cov - (c.x + c.y + c.z);
         double N0, N1, N2, N3;
