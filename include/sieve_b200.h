@@ -195,6 +195,14 @@ double sieve_combine_shards(const sieve_shard_result_t *shards, int32_t n_shards
 /* calcPatternPoints (likelihood/ThreadedScsTreeLikelihood.java:227-238): points[n_shards + 1] */
 void sieve_pattern_points(int32_t n_sites, int32_t n_shards, int32_t *points);
 
+/* Stage-1 background likelihood, ScsBackgroundLikelihood.calculateLogPDirichletMultinomial
+ * (likelihood/ScsBackgroundLikelihood.java:169-268): the five histograms (variant1, variant2, variant3, normal, coverage;
+ * alignment/ScsBackgroundInfo.java:184-186) are given flattened: entry i has read count values[i] with multiplicity
+ * counts[i]; histogram h owns entries offsets6[h] .. offsets6[h+1].  Needs no handle. */
+int sieve_background_log_likelihood(int32_t device, const int64_t *values, const int64_t *counts, const int32_t *offsets6,
+                                    int64_t n_background_sites, int32_t n_taxa, double eff_seq_err_rate,
+                                    double shape_ctrl1, double *out_log_p);
+
 /* kernel-time breakdown of the last sieve_evaluate / sieve_step in milliseconds (CUDA events on the handle's stream):
  * out[0] leaf tables+kernel, out[1] pruning launches, out[2] reduce, out[3] total; and how many kernels were launched. */
 int sieve_last_timing(sieve_core_t *h, float *out_ms4, int32_t *out_launches);

@@ -942,3 +942,25 @@ int so_max_threads(void)
     long n = sysconf(_SC_NPROCESSORS_ONLN);
     return n > 0 ? (int)n : 1;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stage-1 background likelihood: likelihood/ScsBackgroundLikelihood.java:169-268              */
+/* (calculateLogPDirichletMultinomial).  hist h = 0..4 is (variant1, variant2, variant3,        */
+/* normal, coverage) in the order of ScsBackgroundInfo.getOrderedNamesFullSupsCov (:184-186);   */
+/* its entries are values[off[h]..off[h+1]) with multiplicities counts[...].                    */
+/* ------------------------------------------------------------------------------------------ */
+double so_background_log_likelihood(const long long *values, const long long *counts, const int *off,
+                                    long long n_background_sites, int n_taxa, double eff_seq_err, double shape1)
+{
+    /* NucReadCountsModelFiniteMuDM.getWildTypeNucReadCountModelParams (:99-112) */
+    double a[5];
+    a[0] = a[1] = a[2] = (eff_seq_err / 3) * shape1;
+    a[3] = (1 - eff_seq_err) * shape1;
+    a[4] = shape1;
+    double logP = (double)n_background_sites * n_taxa *
+                  (so_log_gamma(a[4]) - so_log_gamma(a[0]) - so_log_gamma(a[1]) - so_log_gamma(a[2]) - so_log_gamma(a[3]));
+    for (int i = off[4]; i < off[5]; i++) logP -= counts[i] * so_log_gamma(a[4] + values[i]);
+    for (int h = 0; h < 4; h++)
+        for (int i = off[h]; i < off[h + 1]; i++) logP += counts[i] * so_log_gamma(a[h] + values[i]);
+    return logP;
+}

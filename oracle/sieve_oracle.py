@@ -95,6 +95,9 @@ def lib():
     L.so_full_eval.argtypes = [_ip, _ip, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(LeafParams), _ip, C.c_int, _dp,
                                _dp, C.c_int, C.c_int, C.c_double, C.c_int, _dp, _dp]
     L.so_max_threads.restype = C.c_int
+    L.so_background_log_likelihood.restype = C.c_double
+    L.so_background_log_likelihood.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _ip, C.c_longlong,
+                                               C.c_int, C.c_double, C.c_double]
     _lib = L
     return L
 
@@ -301,3 +304,22 @@ def full_eval(counts_s_n_5, size_factors_n, params, ops, matrices, proportions, 
                               int(n_threads), sl.ctypes.data_as(_dp) if want_sites else None,
                               sc.ctypes.data_as(_dp) if want_sites else None)
     return logp, sl, sc
+
+
+def background_hist_arrays(hists):
+    """list of 5 {value: count} dicts (variant1, variant2, variant3, normal, coverage) -> (values, counts, offsets)."""
+    vals, cnts, off = [], [], [0]
+    for h in hists:
+        for v in sorted(h):
+            vals.append(v)
+            cnts.append(h[v])
+        off.append(len(vals))
+    return (np.array(vals, dtype=np.int64), np.array(cnts, dtype=np.int64), np.array(off, dtype=np.int32))
+
+
+def background_log_likelihood(hists, n_background_sites, n_taxa, eps, w1):
+    """ScsBackgroundLikelihood.calculateLogPDirichletMultinomial (likelihood/ScsBackgroundLikelihood.java:169-268)."""
+    v, c, off = background_hist_arrays(hists)
+    ll = C.POINTER(C.c_longlong)
+    return lib().so_background_log_likelihood(v.ctypes.data_as(ll), c.ctypes.data_as(ll), off.ctypes.data_as(_ip),
+                                              int(n_background_sites), int(n_taxa), float(eps), float(w1))

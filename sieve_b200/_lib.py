@@ -76,6 +76,8 @@ SIGNATURES = {
     "sieve_restore": (C.c_int, [_vp]),
     "sieve_combine_shards": (C.c_double, [C.POINTER(ShardResult), C.c_int32, C.c_int32, C.c_double]),
     "sieve_pattern_points": (None, [C.c_int32, C.c_int32, _ip]),
+    "sieve_background_log_likelihood": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _ip, C.c_int64,
+                                                   C.c_int32, C.c_double, C.c_double, _dp]),
     "sieve_last_timing": (C.c_int, [_vp, C.POINTER(C.c_float), _ip]),
     "sieve_enable_timing": (C.c_int, [_vp, C.c_int32]),
     "sieve_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),

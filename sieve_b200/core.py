@@ -226,3 +226,24 @@ def pattern_points(n_sites, n_shards):
     pts = np.zeros(n_shards + 1, dtype=np.int32)
     _lib.lib().sieve_pattern_points(int(n_sites), int(n_shards), _iptr(pts))
     return pts
+
+
+def background_log_likelihood(hists, n_background_sites, n_taxa, eps, w1, device=-1):
+    """ScsBackgroundLikelihood.calculateLogP for the Dirichlet-multinomial model
+    (likelihood/ScsBackgroundLikelihood.java:169-268). `hists`: 5 {value: count} dicts in the order
+    (variant1, variant2, variant3, normal, coverage)."""
+    vals, cnts, off = [], [], [0]
+    for h in hists:
+        for v in sorted(h):
+            vals.append(v)
+            cnts.append(h[v])
+        off.append(len(vals))
+    v = np.array(vals, dtype=np.int64)
+    c = np.array(cnts, dtype=np.int64)
+    o = np.array(off, dtype=np.int32)
+    out = C.c_double()
+    lp = C.POINTER(C.c_int64)
+    check(_lib.lib().sieve_background_log_likelihood(device, v.ctypes.data_as(lp), c.ctypes.data_as(lp), _iptr(o),
+                                                     int(n_background_sites), int(n_taxa), float(eps), float(w1),
+                                                     C.byref(out)))
+    return out.value

@@ -17,6 +17,7 @@
 #include "prune.cuh"
 #include "reduce.cuh"
 #include "sizefactors.cuh"
+#include "background.cuh"
 
 static thread_local std::string g_err;
 
@@ -1276,6 +1277,41 @@ extern "C" double sieve_combine_shards(const sieve_shard_result_t* sh, int32_t n
 extern "C" void sieve_pattern_points(int32_t n_sites, int32_t n_shards, int32_t* points) {
     points[0] = 0;
     for (int i = 0; i < n_shards; i++) points[i + 1] = points[i] + n_sites / n_shards + (i < n_sites % n_shards ? 1 : 0);
+}
+
+// ---- stage-1 background likelihood (a "next" row of the scope table) ----------------------------------------------
+extern "C" int sieve_background_log_likelihood(int32_t device, const int64_t* values, const int64_t* counts,
+                                               const int32_t* offsets6, int64_t n_background_sites, int32_t n_taxa,
+                                               double eff_seq_err_rate, double shape_ctrl1, double* out_log_p) {
+    SV_REQUIRE(values && counts && offsets6 && out_log_p, "sieve_background_log_likelihood: null argument");
+    SV_REQUIRE(offsets6[0] == 0, "sieve_background_log_likelihood: offsets must start at 0");
+    for (int i = 0; i < 5; i++) SV_REQUIRE(offsets6[i + 1] >= offsets6[i], "sieve_background_log_likelihood: offsets must ascend");
+    int ndev = 0;
+    SV_CUDA(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return sv_fail(SIEVE_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device >= 0) SV_CUDA(cudaSetDevice(device));
+    const int total = offsets6[5];
+    long long *d_v = nullptr, *d_c = nullptr;
+    int* d_o = nullptr;
+    double* d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_v, sizeof(long long) * std::max(total, 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, sizeof(long long) * std::max(total, 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, sizeof(int) * 6);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_v, values, sizeof(long long) * total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_c, counts, sizeof(long long) * total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_o, offsets6, sizeof(int) * 6, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_background<<<1, 256>>>(d_v, d_c, d_o, n_background_sites, n_taxa, eff_seq_err_rate, shape_ctrl1, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_log_p, d_out, sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_v);
+    cudaFree(d_c);
+    cudaFree(d_o);
+    cudaFree(d_out);
+    SV_CUDA(e);
+    return SIEVE_OK;
 }
 
 // ---- instrumentation ------------------------------------------------------------------------------------------

@@ -56,6 +56,9 @@ def main():
         # threaded combine (2 workers) for the Felsenstein path
         out["logP_felsenstein_mean_T2"] = so.full_eval(c5, sf, P, tree.ops(), mats, props, tree.root,
                                                        "felsenstein_mean", M, 2, weights=weights)[0]
+        # stage-1 background term (likelihood/ScsBackgroundLikelihood.java:169-268) from the file's five histograms
+        out["background_hists"] = [{str(k): v for k, v in h.items()} for h in d["background"]]
+        out["background_logP"] = so.background_log_likelihood(d["background"], d["n_background_sites"], n, 0.008, 150.0)
         with open(os.path.join(HERE, "golden_" + tag + ".json"), "w") as f:
             json.dump(out, f)
         print(tag, "S=%d patterns (of %d sites), n=%d, logP=%.10f" % (S, counts.shape[0], n, out["logP_none"]))

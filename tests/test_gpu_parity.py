@@ -568,3 +568,15 @@ def test_streamed_mcmc_replay(core_mod, oracle, monkeypatch):
     assert 0 < st["accepted"] < 150 and abs(state["log_p"] - ref) <= TOTAL_RTOL * abs(ref)
     mc.close()
     c.close()
+
+
+@pytest.mark.parametrize("tag", ["cells10", "cells40"])
+def test_background_likelihood_matches_oracle(core_mod, oracle, tag):
+    g = json.load(open(os.path.join(GOLD, "golden_" + tag + ".json")))
+    hists = [{int(k): v for k, v in h.items()} for h in g["background_hists"]]
+    got = core_mod.background_log_likelihood(hists, int(g["M"]), g["n"], 0.008, 150.0)
+    assert abs(got - g["background_logP"]) <= 1e-12 * abs(got)
+    for eps, w1 in ((0.02, 80.0), (0.001, 400.0)):
+        ref = oracle.background_log_likelihood(hists, int(g["M"]), g["n"], eps, w1)
+        got = core_mod.background_log_likelihood(hists, int(g["M"]), g["n"], eps, w1)
+        assert abs(got - ref) <= 1e-12 * abs(ref)
