@@ -26,6 +26,7 @@ struct __align__(16) SvOp {
 #define SV_OP_UNARY 4
 #define SV_OP_ROOT 8
 #define SV_OP_FWD1 16
+#define SV_OP_NOSTORE 32  // the result is consumed from registers by the next op and never needed again: skip the writes
 
 // 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one (site, category) state vector.
 __device__ __forceinline__ void sv_ld256(const double* p, double (&v)[4]) {

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
         }
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            if (!active[j]) continue;
+            if (!active[j] || (flags & SV_OP_NOSTORE)) continue;
             const long long dst_row = dst_base + srow[j];
             sv_st256(a.part + dst_row * 16 + k * 4, x[j]);
             // every category lane writes the (identical) scale: a lane only ever re-reads what it wrote itself

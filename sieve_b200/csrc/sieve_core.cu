@@ -99,7 +99,14 @@ struct sieve_core {
     int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
     int n_slots = 0;     // scratch slots for internal partials
     std::vector<int> eph_c1, eph_c2, eph_c1_stored, eph_c2_stored;  // children of every internal node (-2 = unset)
-    bool eph_leaves_dirty = true;  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
+    bool eph_leaves_dirty = true;
+    // resident mode: the core owns the walk order.  Callers name the dirty nodes (and their children); the planner
+    // orders them so that results are consumed from registers, and leaves small subtrees' results unsaved
+    // ("transient": at most transient_T leaves, consumed by the very next op); they are recomputed when needed again.
+    int transient_T = 8;
+    std::vector<char> valid, valid_stored;  // does the node's current buffer hold its partial?
+    std::vector<int> dirty_list;            // internal nodes queued for recomputation
+    std::vector<int> demand_list;           // nodes whose partial must be materialised (getNodePartials)  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
     std::vector<int> last_levels;
     bool last_per_level = false;
 
@@ -230,11 +237,14 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         pool_sites = cap;
         part_slots = h->n_slots;
         leaf_bufs = 1;
-        h->eph_c1.assign(h->n_nodes, -2);
-        h->eph_c2.assign(h->n_nodes, -2);
-        h->eph_c1_stored = h->eph_c1;
-        h->eph_c2_stored = h->eph_c2;
     }
+    h->eph_c1.assign(h->n_nodes, -2);
+    h->eph_c2.assign(h->n_nodes, -2);
+    h->eph_c1_stored = h->eph_c1;
+    h->eph_c2_stored = h->eph_c2;
+    h->valid.assign(h->n_nodes, 0);
+    h->valid_stored.assign(h->n_nodes, 0);
+    if (const char* e = getenv("SIEVE_B200_TRANSIENT_LEAVES")) h->transient_T = std::max(0, atoi(e));
     // does the residency fit?
     size_t need = n * S * 16 + leaf_bufs * n * pool_sites * 40 +
                   part_slots * pool_sites * (SV_KMAX * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
@@ -724,6 +734,142 @@ static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
     return SIEVE_OK;
 }
 
+// Resident-mode planner.  Input: the dirty nodes (dirty_list), nodes to materialise (demand_list), the parent -> children
+// map.  Output: pending_ops, children before parents, ordered so that as many results as possible are consumed by the
+// very next op (register forwarding), with the results of small subtrees (<= transient_T leaves) that are consumed at
+// once left unsaved (SV_OP_NOSTORE).  A clean node whose partial is not in memory is recomputed from its subtree on the
+// way (at most transient_T - 1 extra ops reading leaves).  Clean recomputed nodes that do get stored go to their
+// current buffer and become valid in both the current and the stored state: a clean subtree is the same in both.
+static int sv_plan_resident_ops(sieve_core* h) {
+    const int n = h->n, N = h->n_nodes, root = h->root;
+    std::vector<char> dirty(N, 0), demanded(N, 0);
+    for (int v : h->dirty_list) dirty[v] = 1;
+    for (int v : h->demand_list) demanded[v] = 1;
+    // parents and subtree leaf counts where the children are known
+    std::vector<int> parent(N, -1), leaves(N, 0);
+    for (int v = n; v < N; v++) {
+        if (h->eph_c1[v] >= 0) parent[h->eph_c1[v]] = v;
+        if (h->eph_c2[v] >= 0) parent[h->eph_c2[v]] = v;
+    }
+    {
+        // bottom-up leaf counts via an explicit post-order from every known node without a known parent
+        std::vector<char> done(N, 0);
+        std::vector<std::pair<int, int>> st;
+        for (int r = n; r < N; r++) {
+            if (parent[r] >= 0 || h->eph_c1[r] == -2) continue;
+            st.push_back({r, 0});
+            while (!st.empty()) {
+                auto [v, state] = st.back();
+                st.pop_back();
+                if (v < n) continue;
+                const int a = h->eph_c1[v], b = h->eph_c2[v];
+                if (a == -2) {  // never described: treat as large
+                    leaves[v] = 1 << 28;
+                    continue;
+                }
+                if (state == 0) {
+                    st.push_back({v, 1});
+                    if (b >= n) st.push_back({b, 0});
+                    if (a >= n) st.push_back({a, 0});
+                } else {
+                    const long long la = a < n ? 1 : leaves[a], lb = b < 0 ? 0 : (b < n ? 1 : leaves[b]);
+                    leaves[v] = (int)std::min<long long>(la + lb, 1 << 28);
+                }
+            }
+        }
+    }
+    auto needs = [&](int c) { return c >= n && (dirty[c] || !h->valid[c]); };
+    std::vector<int> emitted;
+    struct Frame {
+        int v, stage, first, last;
+    };
+    std::vector<Frame> st;
+    std::vector<char> visited(N, 0);
+    auto run_from = [&](int top) -> int {
+        st.push_back({top, 0, -1, -1});
+        while (!st.empty()) {
+            Frame& f = st.back();
+            const int v = f.v;
+            if (f.stage == 0) {
+                if (visited[v]) {
+                    st.pop_back();
+                    continue;
+                }
+                const int a = h->eph_c1[v], b = h->eph_c2[v];
+                if (a == -2)
+                    return sv_fail(SIEVE_ERR_STATE, "node " + std::to_string(v) + " is needed but was never computed (no children given)");
+                const bool na = needs(a), nb = b >= 0 && needs(b);
+                f.first = f.last = -1;
+                if (na && nb) {
+                    const bool ta = leaves[a] <= h->transient_T, tb = leaves[b] <= h->transient_T;
+                    int last;
+                    if (ta != tb)
+                        last = ta ? a : b;  // the transient one is consumed from registers and never written
+                    else
+                        last = leaves[a] >= leaves[b] ? a : b;
+                    f.last = last;
+                    f.first = last == a ? b : a;
+                } else if (na)
+                    f.last = a;
+                else if (nb)
+                    f.last = b;
+                f.stage = 1;
+                if (f.first >= 0) {
+                    const int nxt = f.first;
+                    st.push_back({nxt, 0, -1, -1});
+                }
+            } else if (f.stage == 1) {
+                f.stage = 2;
+                if (f.last >= 0) {
+                    const int nxt = f.last;
+                    st.push_back({nxt, 0, -1, -1});
+                }
+            } else {
+                visited[v] = 1;
+                SvOp op;
+                // the child that was computed last goes first in the op (forwarding), the rest is symmetric
+                int c1 = h->eph_c1[v], c2 = h->eph_c2[v];
+                int rc = sv_make_op(h, c1, c2, v, &op);
+                if (rc != SIEVE_OK) return rc;
+                h->pending_ops.push_back(op);
+                emitted.push_back(v);
+                st.pop_back();
+            }
+        }
+        return SIEVE_OK;
+    };
+    // tops: dirty / demanded nodes without a dirty parent; ancestors of a dirty node are expected to be dirty too
+    for (int v = N - 1; v >= n; v--) {
+        if (!(dirty[v] || demanded[v]) || visited[v]) continue;
+        if (parent[v] >= 0 && dirty[parent[v]]) continue;  // reached through its parent
+        if (!dirty[v] && h->valid[v]) continue;             // demanded but already in memory
+        SV_TRY(run_from(v));
+    }
+    // a dirty node whose parent was dirty but never reached it (inconsistent input) would be skipped: check
+    for (int v : h->dirty_list)
+        if (!visited[v]) SV_TRY(run_from(v));
+    // store decisions
+    const size_t base = h->pending_ops.size() - emitted.size();
+    for (size_t i = 0; i < emitted.size(); i++) {
+        const int v = emitted[i];
+        bool consumed_next = false;
+        if (i + 1 < emitted.size()) {
+            const int p = emitted[i + 1];
+            consumed_next = h->eph_c1[p] == v || h->eph_c2[p] == v;
+        }
+        const bool transient = h->transient_T > 0 && v != root && leaves[v] <= h->transient_T;
+        const bool store = !(transient && consumed_next) || demanded[v];
+        SvOp& op = h->pending_ops[base + i];
+        if (!store) op.flags |= SV_OP_NOSTORE;
+        h->valid[v] = store ? 1 : 0;
+        // a clean subtree is identical in the stored state; its buffer is shared when the indices agree
+        if (store && !dirty[v] && h->cur_part[v] == h->stored_part[v]) h->valid_stored[v] = 1;
+    }
+    h->dirty_list.clear();
+    h->demand_list.clear();
+    return SIEVE_OK;
+}
+
 // Register forwarding for the single-launch walk: when an op consumes the destination of the op right before it, that
 // child is made child 1 (the two children's contributions commute) and flagged.
 static void sv_link_forwarding(std::vector<SvOp>& ops, bool per_level) {
@@ -851,14 +997,10 @@ extern "C" int sieve_calculate_partials(sieve_core_t* h, int32_t child1, int32_t
     SV_REQUIRE(child2 < 0 || ((child2 < h->n) == (is_leaf2 != 0)),
                "sieve_calculate_partials: is_leaf2 contradicts the node numbering");
     h->const_genotype = const_genotype;
-    if (h->ephemeral) return sv_record_children(h, child1, child2, parent);
-    SvOp op;
-    SV_TRY(sv_make_op(h, child1, child2, parent, &op));
-    if (!h->pending_levels.empty()) {  // mixing with a level-batched update: fall back to one group
-        h->pending_levels.clear();
-        h->pending_per_level = false;
-    }
-    h->pending_ops.push_back(op);
+    SV_TRY(sv_record_children(h, child1, child2, parent));
+    if (h->ephemeral) return SIEVE_OK;
+    if (h->pending_per_level) return sv_fail(SIEVE_ERR_STATE, "sieve_calculate_partials: a per-level update is pending");
+    h->dirty_list.push_back(parent);
     return SIEVE_OK;
 }
 
@@ -881,16 +1023,24 @@ extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t*
             SV_REQUIRE(p >= h->n && p < h->n_nodes, "sieve_update_nodes: parent must be an internal node");
             h->cur_part[p] = 1 - h->cur_part[p];
         }
+    for (int i = 0; i < n_ops; i++) SV_TRY(sv_record_children(h, ops[3 * i + 1], ops[3 * i + 2], ops[3 * i]));
+    if (!per_level) {
+        // the planner orders the walk (sv_plan_resident_ops); the list only names the dirty nodes
+        if (h->pending_per_level) return sv_fail(SIEVE_ERR_STATE, "sieve_update_nodes: a per-level update is pending");
+        for (int i = 0; i < n_ops; i++) h->dirty_list.push_back(ops[3 * i]);
+        return SIEVE_OK;
+    }
+    // level-batched schedule: the caller's order and grouping are kept, every result is stored
+    SV_REQUIRE(h->dirty_list.empty(), "sieve_update_nodes: per-level update with other ops pending");
     h->pending_ops.reserve(h->pending_ops.size() + n_ops);
     for (int i = 0; i < n_ops; i++) {
         SvOp op;
         SV_TRY(sv_make_op(h, ops[3 * i + 1], ops[3 * i + 2], ops[3 * i], &op));
         h->pending_ops.push_back(op);
+        h->valid[ops[3 * i]] = 1;
     }
-    if (per_level) {
-        h->pending_levels.assign(level_offsets, level_offsets + n_levels + 1);
-        h->pending_per_level = true;
-    }
+    h->pending_levels.assign(level_offsets, level_offsets + n_levels + 1);
+    h->pending_per_level = true;
     return SIEVE_OK;
 }
 
@@ -1005,7 +1155,10 @@ static int sv_launch_staged(sieve_core* h) {
 // uploads pending matrices / distances + ops with ONE host->device copy and launches scatter + pruning
 static int sv_flush(sieve_core* h) {
     const int K = h->K;
-    if (h->ephemeral) SV_TRY(sv_build_streamed_ops(h));
+    if (h->ephemeral)
+        SV_TRY(sv_build_streamed_ops(h));
+    else if (!h->dirty_list.empty() || !h->demand_list.empty())
+        SV_TRY(sv_plan_resident_ops(h));
     const size_t no = h->pending_ops.size();
     size_t nm = 0, nd = 0;
     for (const PendingMatrix& pm : h->pending_mats) (pm.is_distance ? nd : nm)++;
@@ -1177,6 +1330,11 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     if (h->ephemeral) return sv_fail(SIEVE_ERR_STATE, "sieve_get_node_partials: a streamed (SIEVE_FLAG_EPHEMERAL) core keeps no partials");
     SV_CUDA(cudaSetDevice(h->device));
     SV_TRY(sv_flush(h));
+    if (node >= h->n && !h->valid[node]) {
+        // a transient node: its partial was consumed from registers and never written; recompute it into its buffer
+        h->demand_list.push_back(node);
+        SV_TRY(sv_flush(h));
+    }
     const size_t S = h->S, K = h->K, n = h->n;
     const double *x, *sc;
     int is_leaf = node < h->n;
@@ -1210,10 +1368,9 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->stored_part = h->cur_part;
     h->stored_mat = h->cur_mat;
     h->stored_leaf = h->cur_leaf;
-    if (h->ephemeral) {
-        h->eph_c1_stored = h->eph_c1;
-        h->eph_c2_stored = h->eph_c2;
-    }
+    h->eph_c1_stored = h->eph_c1;
+    h->eph_c2_stored = h->eph_c2;
+    h->valid_stored = h->valid;
     return SIEVE_OK;
 }
 extern "C" int sieve_unstore(sieve_core_t* h) {
@@ -1221,10 +1378,9 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
     h->cur_part = h->stored_part;
     h->cur_mat = h->stored_mat;
     h->cur_leaf = h->stored_leaf;
-    if (h->ephemeral) {
-        h->eph_c1 = h->eph_c1_stored;
-        h->eph_c2 = h->eph_c2_stored;
-    }
+    h->eph_c1 = h->eph_c1_stored;
+    h->eph_c2 = h->eph_c2_stored;
+    h->valid = h->valid_stored;
     return SIEVE_OK;
 }
 extern "C" int sieve_restore(sieve_core_t* h) {
@@ -1232,10 +1388,9 @@ extern "C" int sieve_restore(sieve_core_t* h) {
     h->cur_part.swap(h->stored_part);
     h->cur_mat.swap(h->stored_mat);
     std::swap(h->cur_leaf, h->stored_leaf);
-    if (h->ephemeral) {
-        h->eph_c1.swap(h->eph_c1_stored);
-        h->eph_c2.swap(h->eph_c2_stored);
-    }
+    h->eph_c1.swap(h->eph_c1_stored);
+    h->eph_c2.swap(h->eph_c2_stored);
+    h->valid.swap(h->valid_stored);
     // after a rejected parameter proposal the tables hold the rejected values; they are compared with the values of
     // the next sieve_set_leaf_params at the next leaf update, so nothing has to be rebuilt here
     return SIEVE_OK;

@@ -580,3 +580,38 @@ def test_background_likelihood_matches_oracle(core_mod, oracle, tag):
         ref = oracle.background_log_likelihood(hists, int(g["M"]), g["n"], eps, w1)
         got = core_mod.background_log_likelihood(hists, int(g["M"]), g["n"], eps, w1)
         assert abs(got - ref) <= 1e-12 * abs(ref)
+
+
+def test_transient_nodes_do_not_change_results(core_mod, oracle, monkeypatch):
+    """The planner leaves small subtrees unsaved (SV_OP_NOSTORE) and recomputes them on demand: same numbers as with
+    every node saved, through proposals, rejections and partial read-backs."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    d = synthetic(50, 300, seed=81)
+    counts, tree = d["counts"], d["tree"]
+    runs = {}
+    for T in ("0", "3", "8", "64"):
+        monkeypatch.setenv("SIEVE_B200_TRANSIENT_LEAVES", T)
+        tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=4000.0)
+        out = [tl.calculate_logp()]
+        rng = np.random.default_rng(9)
+        for it in range(10):
+            t2 = tl.tree.copy()
+            node = int(rng.integers(tree.n, tree.node_count - 1))
+            lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+            t2.height[node] = lo + (t2.height[t2.parent[node]] - lo) * rng.random()
+            tl.store()
+            tl.set_tree(t2, [node])
+            out.append(tl.calculate_logp())
+            if it % 3 == 1:
+                tl.restore()
+                out.append(tl.calculate_logp())
+        parts = [tl.core.get_node_partials(v) for v in (tree.n, tree.n + 11, tree.n + 30, tree.root - 1)]
+        cparts = [tl.core.get_node_partials(v, const=True) for v in (tree.n + 3, tree.root)]
+        out.append(tl.calculate_logp())
+        runs[T] = (out, tl.pattern_log_likelihoods()[0], parts, cparts)
+        tl.close()
+    for T in ("3", "8", "64"):
+        assert runs[T][0] == runs["0"][0]
+        np.testing.assert_array_equal(runs[T][1], runs["0"][1])
+        for a, b in zip(runs[T][2] + runs[T][3], runs["0"][2] + runs["0"][3]):
+            np.testing.assert_array_equal(a, b)
