@@ -575,11 +575,12 @@ def test_background_likelihood_matches_oracle(core_mod, oracle, tag):
     g = json.load(open(os.path.join(GOLD, "golden_" + tag + ".json")))
     hists = [{int(k): v for k, v in h.items()} for h in g["background_hists"]]
     got = core_mod.background_log_likelihood(hists, int(g["M"]), g["n"], 0.008, 150.0)
-    assert abs(got - g["background_logP"]) <= 1e-12 * abs(got)
+    # the terms (up to ~1e9 each) cancel to ~1e5: the summation order alone moves the 12th digit; budget 1e-9
+    assert abs(got - g["background_logP"]) <= 1e-10 * abs(got)
     for eps, w1 in ((0.02, 80.0), (0.001, 400.0)):
         ref = oracle.background_log_likelihood(hists, int(g["M"]), g["n"], eps, w1)
         got = core_mod.background_log_likelihood(hists, int(g["M"]), g["n"], eps, w1)
-        assert abs(got - ref) <= 1e-12 * abs(ref)
+        assert abs(got - ref) <= 1e-10 * abs(ref)
 
 
 def test_transient_nodes_do_not_change_results(core_mod, oracle, monkeypatch):
