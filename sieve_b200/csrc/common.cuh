@@ -14,18 +14,19 @@
 // child that is the destination of the immediately preceding op FIRST and flags it SV_OP_FWD1 (the product of the two
 // children's contributions commutes), so the walk can consume it from registers.
 struct __align__(16) SvOp {
-    long long dst_row;  // internal slot (buffer * n_internal + internal index) * S
-    long long c1_row;   // child 1: leaf slot (buffer * n_leaves + leaf) * S  or  internal slot * S
-    long long c2_row;   // child 2, unused for a unary op
-    int m1, m2;         // matrix slots (buffer * n_nodes + node) of the two children
-    int flags;          // SV_OP_*
-    int pad;
-};
+    unsigned dst_row;  // internal slot (buffer * n_internal + internal index) * S
+    unsigned c1_row;   // child 1: leaf slot (buffer * n_leaves + leaf) * S  or  internal slot * S
+    unsigned c2_row;   // child 2, unused for a unary op
+    int m1, m2;        // matrix slots (buffer * n_nodes + node) of the two children
+    int flags;         // SV_OP_*
+    int pad0, pad1;
+};  // 32 bytes: two 128-bit loads.  Rows are 32-bit: every pool holds fewer than 2^32 (slot, site) rows (checked at create).
 #define SV_OP_LEAF1 1
 #define SV_OP_LEAF2 2
 #define SV_OP_UNARY 4
 #define SV_OP_ROOT 8
 #define SV_OP_FWD1 16
+#define SV_OP_ZEROD 64    // one of the two distances is exactly 0: take the Double.MIN_VALUE clamp path
 #define SV_OP_NOSTORE 32  // the result is consumed from registers by the next op and never needed again: skip the writes
 
 // 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one (site, category) state vector.
@@ -48,19 +49,15 @@ __device__ __forceinline__ double sv_max4(const double (&v)[4]) { return fmax(fm
 __device__ __forceinline__ int sv_maxhi4(const double (&v)[4]) {
     return max(max(__double2hiint(v[0]), __double2hiint(v[1])), max(__double2hiint(v[2]), __double2hiint(v[3])));
 }
-// factor = 2^-e and *shift_ln = e ln 2 from the high word of the maximum (see sv_pow2_rescale)
+// factor = 2^-e and *shift_ln = e ln 2 from the high word of the maximum (see sv_pow2_rescale); selects only, no branch
 __device__ __forceinline__ double sv_pow2_rescale_hi(int hi, double* shift_ln) {
     const int e = (hi >> 20) & 0x7ff;
-    if (hi > 0 && e >= 1 && e <= 2045) {
-        *shift_ln = (double)(e - 1023) * SV_LN2;
-        return __hiloint2double((2046 - e) << 20, 0);
-    }
-    if (hi > 0 && e == 0) {  // subnormal maximum with a non-zero high word
-        *shift_ln = -1022.0 * SV_LN2;
-        return __hiloint2double(2045 << 20, 0);
-    }
-    *shift_ln = 0.0;  // zero (or a subnormal below 2^-1042, treated as zero), inf, NaN
-    return 1.0;
+    const bool normal = hi > 0 && (unsigned)(e - 1) < 2045u;
+    const bool sub = hi > 0 && e == 0;  // subnormal maximum with a non-zero high word (Double.MIN_VALUE clamps only)
+    const int fe = normal ? 2046 - e : (sub ? 2045 : 1023);
+    const int se = normal ? e - 1023 : (sub ? -1022 : 0);
+    *shift_ln = (double)se * SV_LN2;  // zero / tiny subnormal / inf / NaN: left alone
+    return __hiloint2double(fe << 20, 0);
 }
 
 // Exact power-of-two renormalisation: returns factor = 2^-e and *shift_ln = e * ln 2 with e = floor(log2 mx),

@@ -58,10 +58,6 @@ __device__ __forceinline__ double sv_sel(const double (&x)[4], int g) {
 }
 
 #define SV_PRUNE_THREADS 128
-#ifndef SV_PRUNE_PREFETCH
-#define SV_PRUNE_PREFETCH 0  // ops ahead whose (non-forwarded) children are prefetched into L2; 0 = off
-#endif
-__device__ __forceinline__ void sv_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef SV_PRUNE_NS
 #define SV_PRUNE_NS 2  // sites per lane: the op's matrices are read from shared memory once and applied to NS sites
 #endif
@@ -158,18 +154,21 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
     __shared__ __align__(32) double sm[(SV_PRUNE_THREADS / 32) * 2 * SV_KMAX * SV_MAT_STRIDE];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int k = lane & 3;
+    const int k = min(lane & 3, a.K - 1);
+    const int klane = lane & 3;
     // a warp owns 8 * NS consecutive sites; pass j of a lane is site base + 8 j, so that every pass of the warp is one
     // contiguous 1 KB access
     const int site0 = blockIdx.x * SITES_PER_BLOCK + warp * (8 * NS) + (lane >> 2);
-    bool site_ok[NS], active[NS];
-    long long srow[NS];
+    // Lanes beyond the last site (or beyond the last category) are clamped onto the last valid site (category): they
+    // compute and store bit-identical duplicates of a real lane's values to the same (or an unused) address, so the loop
+    // needs no predicates at all.
+    bool site_ok[NS];
+    unsigned srow[NS];
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         const int site = site0 + 8 * j;
         site_ok[j] = site < a.S;
-        active[j] = site_ok[j] && (k < a.K);
-        srow[j] = site_ok[j] ? site : 0;
+        srow[j] = (unsigned)(site_ok[j] ? site : a.S - 1);
     }
     double* wm = sm + warp * (2 * SV_KMAX * SV_MAT_STRIDE);
     // staging role of this lane: matrix `which` (child 1 / 2), category kk, row q  ->  4 doubles = one 256-bit load
@@ -199,54 +198,12 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
     for (int i = i0; i < i1; i++) {
         __syncwarp();  // scratch slots are reused (streamed mode): keep the warp's reads of an op ahead of the next op's writes
         const int4* opp = reinterpret_cast<const int4*>(a.ops + i);
-        const int4 o0 = __ldg(opp), o1 = __ldg(opp + 1), o2 = __ldg(opp + 2);
-        const long long dst_base = (long long)(unsigned)o0.x | ((long long)o0.y << 32);
-        const long long c1_base = (long long)(unsigned)o0.z | ((long long)o0.w << 32);
-        const long long c2_base = (long long)(unsigned)o1.x | ((long long)o1.y << 32);
-        const int m1 = o1.z, m2 = o1.w, flags = o2.x;
+        const int4 o0 = __ldg(opp), o1 = __ldg(opp + 1);
+        const unsigned dst_base = (unsigned)o0.x, c1_base = (unsigned)o0.y, c2_base = (unsigned)o0.z;
+        const int m1 = o0.w, m2 = o1.x, flags = o1.y;
         const bool unary = flags & SV_OP_UNARY;
         const bool leaf1 = flags & SV_OP_LEAF1, leaf2 = flags & SV_OP_LEAF2;
 
-#if SV_PRUNE_PREFETCH > 0
-        // ---- pull the children of a later op from DRAM into L2 while this op computes (no register cost) ----
-        if (i + SV_PRUNE_PREFETCH < i1) {
-            const int4* npp = reinterpret_cast<const int4*>(a.ops + i + SV_PRUNE_PREFETCH);
-            const int4 n0 = __ldg(npp), n1 = __ldg(npp + 1), n2 = __ldg(npp + 2);
-            const long long nc1 = (long long)(unsigned)n0.z | ((long long)n0.w << 32);
-            const long long nc2 = (long long)(unsigned)n1.x | ((long long)n1.y << 32);
-            const int nfl = n2.x;
-#pragma unroll
-            for (int j = 0; j < NS; j++) {
-                if (!active[j]) continue;
-                if (!(nfl & SV_OP_FWD1)) {
-                    if (nfl & SV_OP_LEAF1) {
-                        sv_prefetch_l2(a.leafX + (nc1 + srow[j]) * 4);
-                        sv_prefetch_l2(a.leafS + (nc1 + srow[j]));
-                    } else {
-                        sv_prefetch_l2(a.part + (nc1 + srow[j]) * 16 + k * 4);
-                        sv_prefetch_l2(a.scale + (nc1 + srow[j]));
-                        if (WITH_CONST) {
-                            sv_prefetch_l2(a.cpart + (nc1 + srow[j]) * 16 + k * 4);
-                            sv_prefetch_l2(a.cscale + (nc1 + srow[j]));
-                        }
-                    }
-                }
-                if (!(nfl & SV_OP_UNARY)) {
-                    if (nfl & SV_OP_LEAF2) {
-                        sv_prefetch_l2(a.leafX + (nc2 + srow[j]) * 4);
-                        sv_prefetch_l2(a.leafS + (nc2 + srow[j]));
-                    } else {
-                        sv_prefetch_l2(a.part + (nc2 + srow[j]) * 16 + k * 4);
-                        sv_prefetch_l2(a.scale + (nc2 + srow[j]));
-                        if (WITH_CONST) {
-                            sv_prefetch_l2(a.cpart + (nc2 + srow[j]) * 16 + k * 4);
-                            sv_prefetch_l2(a.cscale + (nc2 + srow[j]));
-                        }
-                    }
-                }
-            }
-        }
-#endif
         // ---- issue every global load of this op up front: matrices (one 256-bit load per lane) and children ----
         double m[4] = {0, 0, 0, 0};
         double2 q1 = make_double2(0.0, 0.0), q2 = make_double2(0.0, 0.0);
@@ -265,8 +222,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
         }
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            if (!active[j]) continue;
-            const long long c1_row = c1_base + srow[j], c2_row = c2_base + srow[j];
+            const size_t c1_row = c1_base + srow[j], c2_row = c2_base + srow[j];  // 32-bit sums, widened once
             if (!(flags & SV_OP_FWD1)) {
                 if (leaf1) {
                     sv_ld256_nc(a.leafX + c1_row * 4, x[j]);
@@ -300,7 +256,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
             *reinterpret_cast<double2*>(st_dst + 2) = make_double2(m[2], m[3]);
             __syncwarp();
         }
-        const bool cz0 = a.clamp_zero_distance;
+        const bool cz0 = flags & SV_OP_ZEROD;  // set by the host only in log mode and only when a distance is exactly 0
 
         // ================= variant partials =================
         double y[NS][4];
@@ -367,7 +323,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
 #pragma unroll
                 for (int j = 0; j < NS; j++)
 #pragma unroll
-                    for (int p = 0; p < 4; p++) cy[j][p] = cy[j][p] > 0.0 ? cy[j][p] : (active[j] ? SV_MIN_VALUE : 0.0);
+                    for (int p = 0; p < 4; p++) cy[j][p] = cy[j][p] > 0.0 ? cy[j][p] : SV_MIN_VALUE;
             }
         }
         // ---- renormalise each site's 4 x 4 values by a power of two (integer max over the high words) ----
@@ -394,8 +350,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
         }
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            if (!active[j] || (flags & SV_OP_NOSTORE)) continue;
-            const long long dst_row = dst_base + srow[j];
+            if (flags & SV_OP_NOSTORE) continue;
+            const size_t dst_row = dst_base + srow[j];
             sv_st256(a.part + dst_row * 16 + k * 4, x[j]);
             // every category lane writes the (identical) scale: a lane only ever re-reads what it wrote itself
             a.scale[dst_row] = xs[j];
@@ -409,15 +365,15 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
         if (flags & SV_OP_ROOT) {
 #pragma unroll
             for (int j = 0; j < NS; j++) {
-                double v = active[j] ? a.prop[k] * (GENO0 ? x[j][0] : sv_sel(x[j], rg)) : 0.0;
+                double v = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? x[j][0] : sv_sel(x[j], rg));
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (site_ok[j] && k == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + xs[j];
+                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + xs[j];
                 if (WITH_CONST) {
-                    double cv = active[j] ? a.prop[k] * (GENO0 ? cx[j][0] : sv_sel(cx[j], rg)) : 0.0;
+                    double cv = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? cx[j][0] : sv_sel(cx[j], rg));
                     cv += __shfl_xor_sync(0xffffffffu, cv, 1);
                     cv += __shfl_xor_sync(0xffffffffu, cv, 2);
-                    if (site_ok[j] && k == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + cxs[j];
+                    if (site_ok[j] && klane == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + cxs[j];
                 }
             }
         }

@@ -66,6 +66,7 @@ struct sieve_core {
     double* d_mats = nullptr;                                                            // [2][n_nodes][4][16]
     double2* d_qfac = nullptr;                                                           // [2][n_nodes][4]
     std::vector<char> slot_is_q;  // per matrix slot: was it given as a distance?
+    std::vector<char> slot_zero;  // ... and is one of its K distances exactly 0?
     double *d_site_logl = nullptr, *d_site_const = nullptr;
     SvAcc* d_partials = nullptr;
     unsigned int* d_counter = nullptr;
@@ -245,6 +246,10 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->valid.assign(h->n_nodes, 0);
     h->valid_stored.assign(h->n_nodes, 0);
     if (const char* e = getenv("SIEVE_B200_TRANSIENT_LEAVES")) h->transient_T = std::max(0, atoi(e));
+    if ((2 * n + 2) * pool_sites >= ((size_t)1 << 32) || part_slots * pool_sites >= ((size_t)1 << 32)) {
+        g_err = "sieve_create: more than 2^32 (slot, site) rows per pool; use SIEVE_FLAG_EPHEMERAL (streamed evaluation)";
+        return fail(SIEVE_ERR_OOM);
+    }
     // does the residency fit?
     size_t need = n * S * 16 + leaf_bufs * n * pool_sites * 40 +
                   part_slots * pool_sites * (SV_KMAX * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
@@ -275,6 +280,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * SV_KMAX * 16));
     CR(sv_alloc(h, &h->d_qfac, (size_t)2 * h->n_nodes * SV_KMAX));
     h->slot_is_q.assign((size_t)2 * h->n_nodes, 0);
+    h->slot_zero.assign((size_t)2 * h->n_nodes, 0);
     CR(sv_alloc(h, &h->d_site_logl, S));
     CR(sv_alloc(h, &h->d_site_const, S));
     CR(sv_alloc(h, &h->d_partials, (size_t)SV_REDUCE_BLOCKS));
@@ -713,15 +719,16 @@ static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
     SV_REQUIRE(c1 >= 0 && c1 < h->n_nodes && c1 != h->root, "op: bad child1");
     SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
     op->flags = 0;
-    op->pad = 0;
-    op->dst_row = (long long)(h->cur_part[parent] * h->n_internal + (parent - n)) * S;
-    auto child = [&](int c, int leaf_flag, long long* row, int* m) {
+    op->pad0 = op->pad1 = 0;
+    op->dst_row = (unsigned)((long long)(h->cur_part[parent] * h->n_internal + (parent - n)) * S);
+    auto child = [&](int c, int leaf_flag, unsigned* row, int* m) {
         if (c < n) {
             op->flags |= leaf_flag;
-            *row = (long long)(h->cur_leaf * n + c) * S;
+            *row = (unsigned)((long long)(h->cur_leaf * n + c) * S);
         } else
-            *row = (long long)(h->cur_part[c] * h->n_internal + (c - n)) * S;
+            *row = (unsigned)((long long)(h->cur_part[c] * h->n_internal + (c - n)) * S);
         *m = h->cur_mat[c] * h->n_nodes + c;
+        if (h->log_mode && h->slot_zero[*m]) op->flags |= SV_OP_ZEROD;
     };
     child(c1, SV_OP_LEAF1, &op->c1_row, &op->m1);
     if (c2 < 0) {
@@ -877,7 +884,7 @@ static void sv_link_forwarding(std::vector<SvOp>& ops, bool per_level) {
         SvOp& op = ops[i];
         op.flags &= ~SV_OP_FWD1;
         if (per_level || i == 0) continue;
-        const long long prev = ops[i - 1].dst_row;
+        const unsigned prev = ops[i - 1].dst_row;
         const bool c1_int = !(op.flags & SV_OP_LEAF1);
         const bool c2_int = !(op.flags & SV_OP_UNARY) && !(op.flags & SV_OP_LEAF2);
         if (c2_int && op.c2_row == prev && !(c1_int && op.c1_row == prev)) {
@@ -960,18 +967,19 @@ static int sv_build_streamed_ops(sieve_core* h) {
         } else {
             SvOp op;
             op.flags = 0;
-            op.pad = 0;
+            op.pad0 = op.pad1 = 0;
             const int dst = free_slots.back();
             free_slots.pop_back();
             slot_of[v] = dst;
-            op.dst_row = (long long)dst * cap;
-            auto child = [&](int c, int leaf_flag, long long* row, int* m) {
+            op.dst_row = (unsigned)((long long)dst * cap);
+            auto child = [&](int c, int leaf_flag, unsigned* row, int* m) {
                 if (c < n) {
                     op.flags |= leaf_flag;
-                    *row = (long long)c * cap;
+                    *row = (unsigned)((long long)c * cap);
                 } else
-                    *row = (long long)slot_of[c] * cap;
+                    *row = (unsigned)((long long)slot_of[c] * cap);
                 *m = h->cur_mat[c] * N + c;
+                if (h->log_mode && h->slot_zero[*m]) op.flags |= SV_OP_ZEROD;
             };
             child(a, SV_OP_LEAF1, &op.c1_row, &op.m1);
             if (b < 0) {
@@ -1155,6 +1163,14 @@ static int sv_launch_staged(sieve_core* h) {
 // uploads pending matrices / distances + ops with ONE host->device copy and launches scatter + pruning
 static int sv_flush(sieve_core* h) {
     const int K = h->K;
+    // slot attributes first: the op builders look at them
+    for (const PendingMatrix& pm : h->pending_mats) {
+        h->slot_is_q[pm.slot] = pm.is_distance ? 1 : 0;
+        char z = 0;
+        if (pm.is_distance)
+            for (int k = 0; k < K; k++) z |= pm.v[k] == 0.0;
+        h->slot_zero[pm.slot] = z;
+    }
     if (h->ephemeral)
         SV_TRY(sv_build_streamed_ops(h));
     else if (!h->dirty_list.empty() || !h->demand_list.empty())
@@ -1183,7 +1199,6 @@ static int sv_flush(sieve_core* h) {
             memcpy(h->h_stage + off_mv + im * K * 16 * sizeof(double), pm.v, K * 16 * sizeof(double));
             ((int*)(h->h_stage + off_ms))[im++] = pm.slot;
         }
-        h->slot_is_q[pm.slot] = pm.is_distance ? 1 : 0;
     }
     bool qfast = true;
     for (const SvOp& op : h->pending_ops) {
