@@ -90,15 +90,26 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl,
         last = (done == gridDim.x - 1);
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last) {
+        // the last block to finish merges the per-block partials: fixed-shape tree over block indices (deterministic)
+        __shared__ SvAcc fin[256];
         __threadfence();
-        SvAcc t = partials[0];
-        for (int i = 1; i < (int)gridDim.x; i++) sv_acc_merge(t, partials[i]);
-        out[0] = t.sum;
-        out[1] = with_const ? log(t.se) + t.m : 0.0;
-        out[2] = t.csum;
-        out[3] = -t.lewis;
-        out[4] = t.wsum;
-        *counter = 0u;
+        SvAcc t = sv_acc_zero();
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) sv_acc_merge(t, partials[i]);
+        fin[threadIdx.x] = t;
+        __syncthreads();
+        for (int d = 128; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) sv_acc_merge(fin[threadIdx.x], fin[threadIdx.x + d]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            t = fin[0];
+            out[0] = t.sum;
+            out[1] = with_const ? log(t.se) + t.m : 0.0;
+            out[2] = t.csum;
+            out[3] = -t.lewis;
+            out[4] = t.wsum;
+            *counter = 0u;
+        }
     }
 }
