@@ -499,7 +499,9 @@ def main():
     sampler.join(timeout=2)
     if rank == 0:
         peak, peak_src = measured_peak()
-        with_const = True
+        # the default core eliminates the constant-site twin algebraically: the walk then moves the
+        # variant partials only, so its algorithmic bytes are the 384 B figure; SIEVE_B200_CONST_TWIN=1 restores 768 B
+        with_const = os.environ.get("SIEVE_B200_CONST_TWIN", "0") == "1"
         alg_prune = algorithmic_bytes_prune(tree, S, with_const)
         alg_leaf = 48 * n * S
         value = world * args.steps / (dev_ms_max / 1000.0)
@@ -522,7 +524,7 @@ def main():
                     "ms_per_step": 1000.0 * e2e_s_max / args.steps},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "k_prune<const, geno0, %s>" % ("generic" if args.matrices else "qfast"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_prune<%s, geno0, %s>" % ("const twin" if with_const else "variant only", "generic" if args.matrices else "qfast"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_prune), "launch_ms": prune_ms},
             "kernels": {"leaf_ms": leaf_ms, "leaf_GBps": alg_leaf / (leaf_ms / 1000.0) / 1e9 if leaf_ms > 0 else None,

@@ -176,6 +176,8 @@ struct SvLeafArgs {
     const double* size_factors;
     double* leafX;          // [cell][site][4]   (already offset to the write buffer)
     double* leafS;          // [cell][site]
+    double* leaf0;          // [cell][site] log-likelihood of the constant genotype (x[cg] and the scale folded), or NULL
+    int const_genotype;
     int n_cells, S, C;     // S = sites evaluated by this launch
     long long counts_stride;  // sites per cell in `counts` (the whole shard)
     long long site_begin;     // first site of this launch inside the shard (streamed evaluation walks site chunks)
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(256, SV_LEAF_MINB) k_leaf(SvLeafArgs a) {
     const int4* cnt = a.counts + (size_t)j * a.counts_stride + a.site_begin;
     double* outX = a.leafX + (size_t)j * a.out_stride * 4;
     double* outS = a.leafS + (size_t)j * a.out_stride;
+    double* out0 = a.leaf0 ? a.leaf0 + (size_t)j * a.out_stride : nullptr;
 
     // software pipeline: the count tuple of the next iteration is in flight while this one is evaluated
     int s = s0 + threadIdx.x;
@@ -311,5 +314,9 @@ __global__ void __launch_bounds__(256, SV_LEAF_MINB) k_leaf(SvLeafArgs a) {
         }
         sv_st256(outX + (size_t)s * 4, x);
         outS[s] = ls;
+        if (out0) {
+            const int cg = a.const_genotype;
+            out0[s] = log(cg == 0 ? x[0] : (cg == 1 ? x[1] : (cg == 2 ? x[2] : x[3]))) + ls;
+        }
     }
 }

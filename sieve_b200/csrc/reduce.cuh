@@ -55,8 +55,11 @@ __device__ __forceinline__ SvAcc sv_acc_zero() {
 }
 
 // out layout == sieve_shard_result_t {sum_log_l, const_lse, const_sum, lewis_sum, weight_sum}
+// The constant-site log-likelihood of site s is  cst[s] + cst_shift:  with the algebraic constant-site path cst is
+// Lambda (sum over cells of the leaves' constant-genotype log-likelihoods) and cst_shift = log C_tree (one number per
+// tree, computed on the host); with the per-site twin cst is logConstRoot itself and cst_shift = 0.
 __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl, const double* __restrict__ cst,
-                                                const int* __restrict__ w, int S, int with_const,
+                                                double cst_shift, const int* __restrict__ w, int S, int with_const,
                                                 SvAcc* __restrict__ partials, unsigned int* __restrict__ counter,
                                                 double* __restrict__ out) {
     __shared__ SvAcc sm[8];
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl,
         acc.sum += wt * logl[s];
         acc.wsum += wt;
         if (with_const) {
-            const double c = cst[s];
+            const double c = cst[s] + cst_shift;
             sv_lse_merge(acc.m, acc.se, c, wt);
             acc.csum += wt * c;
             acc.lewis += wt * log(1.0 - exp(c));
@@ -112,4 +115,41 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl,
             *counter = 0u;
         }
     }
+}
+
+
+// Lambda[s] = sum over cells of leaf0[cell][s], cells in index order (deterministic), one thread per site.
+// The constant-site likelihood factorises: every constant-site partial is (a site-independent 4-vector per node and
+// category) x (the product over the leaves below of their constant-genotype likelihood), so the per-site part of the
+// whole acquisition-bias computation is this one column sum, and it only changes when the leaves change.
+__global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ leaf0, int n_cells, int S, long long stride,
+                                                double* __restrict__ lambda) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four chains for memory-level parallelism, merged in a fixed order
+    int j = 0;
+    for (; j + 3 < n_cells; j += 4) {
+        a0 += __ldg(leaf0 + (size_t)j * stride + s);
+        a1 += __ldg(leaf0 + (size_t)(j + 1) * stride + s);
+        a2 += __ldg(leaf0 + (size_t)(j + 2) * stride + s);
+        a3 += __ldg(leaf0 + (size_t)(j + 3) * stride + s);
+    }
+    for (; j < n_cells; j++) a0 += __ldg(leaf0 + (size_t)j * stride + s);
+    lambda[s] = (a0 + a1) + (a2 + a3);
+}
+
+// Constant-site partials of one node in the reference layout [K][S][G], rebuilt from the factorisation for
+// BeerLikelihoodCore-style read-back: out = G[k][g] * exp(gscale) * prod over the node's leaves of their leaf0.
+__global__ void k_export_const(const double* __restrict__ leaf0, const int* __restrict__ leaf_list, int n_list,
+                               long long stride, const double* __restrict__ G /*[4][4]*/, double gscale, int S, int K,
+                               int as_log, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double lam = 0.0;
+    for (int i = 0; i < n_list; i++) lam += leaf0[(size_t)leaf_list[i] * stride + s];
+    for (int k = 0; k < K; k++)
+        for (int g = 0; g < 4; g++) {
+            const double v = log(G[k * 4 + g]) + gscale + lam;
+            out[((size_t)k * S + s) * 4 + g] = as_log ? v : exp(v);
+        }
 }

@@ -68,6 +68,14 @@ struct sieve_core {
     std::vector<char> slot_is_q;  // per matrix slot: was it given as a distance?
     std::vector<char> slot_zero;  // ... and is one of its K distances exactly 0?
     double *d_site_logl = nullptr, *d_site_const = nullptr;
+    // algebraic constant-site path (default when SIEVE_FLAG_CONST_PARTIALS): see k_colsum in reduce.cuh
+    bool const_twin = false;     // SIEVE_B200_CONST_TWIN=1: prune the constant-site partials per site like the reference
+    double* d_leaf0 = nullptr;   // [leaf buffers][cell][site] constant-genotype log-likelihood of every leaf
+    double* d_lambda = nullptr;  // [leaf buffers][site] its sum over cells
+    std::vector<double> hP;      // [2][node][K][16] host mirror of the (clamped) transition matrices
+    std::vector<double> G, Gs;   // [2][node][K][4] site-independent factor of the constant-site partials + log-scale
+    double log_c = 0.0, log_c_stored = 0.0;  // log sum_k prop_k G_root[k][root genotype]
+    std::vector<int> g_nodes;    // nodes whose G has to be refreshed, children first
     SvAcc* d_partials = nullptr;
     unsigned int* d_counter = nullptr;
     double* d_result = nullptr;
@@ -197,6 +205,9 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->n_internal = h->n;
     h->log_mode = cfg->flags & SIEVE_FLAG_LOG_PARTIALS;
     h->with_const = cfg->flags & SIEVE_FLAG_CONST_PARTIALS;
+    if (const char* e = getenv("SIEVE_B200_CONST_TWIN")) h->const_twin = atoi(e) != 0;
+    const bool twin = h->with_const && h->const_twin;
+    const bool algebraic = h->with_const && !h->const_twin;
     h->single_ado = cfg->flags & SIEVE_FLAG_SINGLE_ADO;
     h->ephemeral = cfg->flags & SIEVE_FLAG_EPHEMERAL;
     h->cur_part.assign(h->n_nodes, 0);
@@ -252,7 +263,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     }
     // does the residency fit?
     size_t need = n * S * 16 + leaf_bufs * n * pool_sites * 40 +
-                  part_slots * pool_sites * (SV_KMAX * 32 + 8) * (h->with_const ? 2 : 1) + ((size_t)64 << 20);
+                  part_slots * pool_sites * (SV_KMAX * 32 + 8) * (twin ? 2 : 1) + ((size_t)64 << 20);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (need > free_b) {
@@ -273,9 +284,16 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     CR(sv_alloc(h, &h->d_leafS, leaf_bufs * n * pool_sites));
     CR(sv_alloc(h, &h->d_part, part_slots * pool_sites * SV_KMAX * 4));
     CR(sv_alloc(h, &h->d_scale, part_slots * pool_sites));
-    if (h->with_const) {
+    if (twin) {
         CR(sv_alloc(h, &h->d_cpart, part_slots * pool_sites * SV_KMAX * 4));
         CR(sv_alloc(h, &h->d_cscale, part_slots * pool_sites));
+    }
+    if (algebraic) {
+        CR(sv_alloc(h, &h->d_leaf0, leaf_bufs * n * pool_sites));
+        CR(sv_alloc(h, &h->d_lambda, 2 * S));
+        h->hP.assign((size_t)2 * h->n_nodes * SV_KMAX * 16, 0.0);
+        h->G.assign((size_t)2 * h->n_nodes * SV_KMAX * 4, 0.0);
+        h->Gs.assign((size_t)2 * h->n_nodes, 0.0);
     }
     CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * SV_KMAX * 16));
     CR(sv_alloc(h, &h->d_qfac, (size_t)2 * h->n_nodes * SV_KMAX));
@@ -315,6 +333,8 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_part);
     cudaFree(h->d_scale);
     cudaFree(h->d_cpart);
+    cudaFree(h->d_leaf0);
+    cudaFree(h->d_lambda);
     cudaFree(h->d_cscale);
     cudaFree(h->d_mats);
     cudaFree(h->d_qfac);
@@ -536,6 +556,9 @@ static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, lo
     a.size_factors = h->d_sf;
     a.leafX = h->d_leafX + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S * 4);
     a.leafS = h->d_leafS + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S);
+    const bool algebraic = h->with_const && !h->const_twin;
+    a.leaf0 = algebraic ? h->d_leaf0 + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S) : nullptr;
+    a.const_genotype = h->const_genotype;
     a.n_cells = h->n;
     a.S = n_sites;
     a.counts_stride = h->S;
@@ -562,6 +585,12 @@ static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, lo
         k_leaf<false><<<grid, 256, 0, h->stream>>>(a);
     }
     sv_count(h);
+    if (algebraic) {
+        // Lambda of this site range: streamed mode indexes it by the shard's site, resident mode per leaf buffer
+        double* lam = h->d_lambda + (h->ephemeral ? site_begin : (long long)h->cur_leaf * h->S);
+        k_colsum<<<(n_sites + 255) / 256, 256, 0, h->stream>>>(a.leaf0, h->n, n_sites, out_stride, lam);
+        sv_count(h);
+    }
     SV_CUDA(cudaGetLastError());
     return SIEVE_OK;
 }
@@ -593,6 +622,12 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
                                 nx * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         SV_CUDA(cudaMemcpyAsync(h->d_leafS + (size_t)(1 - h->cur_leaf) * ns, h->d_leafS + (size_t)h->cur_leaf * ns,
                                 ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        if (h->d_leaf0) {
+            SV_CUDA(cudaMemcpyAsync(h->d_leaf0 + (size_t)(1 - h->cur_leaf) * ns, h->d_leaf0 + (size_t)h->cur_leaf * ns,
+                                    ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            SV_CUDA(cudaMemcpyAsync(h->d_lambda + (size_t)(1 - h->cur_leaf) * h->S, h->d_lambda + (size_t)h->cur_leaf * h->S,
+                                    (size_t)h->S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
     }
     h->leaves_ready = true;
     return SIEVE_OK;
@@ -741,6 +776,75 @@ static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
     return SIEVE_OK;
 }
 
+// ---- algebraic constant-site path: the site-independent factor ----------------------------------------------------
+// constPartial[v][k][s][p] = G_v[k][p] * prod_{leaves l below v} leaf_l[s][cg]   (induction over
+// ScsBeerLikelihoodCore.java:1432-1440 / :1467-1490: a leaf child contributes P[p][cg] * leaf[cg], an internal child
+// sum_c P[p][c] * const[c], and the leaf factor is common to the four parent states).  G is 16 doubles per node, kept on
+// the host in the same double buffers as the partials, refreshed for the nodes an update recomputes.
+static void sv_host_matrix(sieve_core* h, const PendingMatrix& pm) {
+    const int K = h->K;
+    double* dst = h->hP.data() + (size_t)pm.slot * SV_KMAX * 16;
+    static const double P1[16] = {3, 6, -3, -6, 1, 2, -1, -2, -1, -2, 1, 2, -1, -2, 1, 2};     // 8 Pi1
+    static const double P2[16] = {9, -18, 3, 6, -3, 6, -1, -2, 1, -2, 11, -10, 1, -2, -5, 6};  // 16 Pi2
+    for (int k = 0; k < K; k++) {
+        for (int e = 0; e < 16; e++) {
+            double v;
+            if (pm.is_distance) {
+                const double d = pm.v[k];
+                const double g1 = expm1(-0.2 * d), g2 = expm1(-0.4 * d);
+                v = ((e % 5 == 0) ? 1.0 : 0.0) + (g1 / 8.0) * P1[e] + (g2 / 16.0) * P2[e];
+                if (d == 0.0) v = (e % 5 == 0) ? 1.0 : 0.0;
+            } else
+                v = pm.v[k * 16 + e];
+            if (h->log_mode) v = v > 0.0 ? v : SV_MIN_VALUE;
+            dst[k * 16 + e] = v;
+        }
+    }
+}
+
+static void sv_update_G(sieve_core* h) {
+    const int n = h->n, N = h->n_nodes, K = h->K, cg = h->const_genotype;
+    for (int v : h->g_nodes) {
+        const int a = h->eph_c1[v], b = h->eph_c2[v];
+        double* g = h->G.data() + ((size_t)h->cur_part[v] * N + v) * SV_KMAX * 4;
+        double gs = 0.0, mx = 0.0;
+        auto side = [&](int c, int k, double* y) {
+            const double* P = h->hP.data() + ((size_t)h->cur_mat[c] * N + c) * SV_KMAX * 16 + k * 16;
+            if (c < n) {
+                for (int p = 0; p < 4; p++) y[p] = P[4 * p + cg];
+            } else {
+                const double* gc = h->G.data() + ((size_t)h->cur_part[c] * N + c) * SV_KMAX * 4 + k * 4;
+                for (int p = 0; p < 4; p++) y[p] = P[4 * p] * gc[0] + P[4 * p + 1] * gc[1] + P[4 * p + 2] * gc[2] + P[4 * p + 3] * gc[3];
+            }
+        };
+        for (int k = 0; k < K; k++) {
+            double y[4], z[4];
+            side(a, k, y);
+            if (b >= 0) {
+                side(b, k, z);
+                for (int p = 0; p < 4; p++) y[p] *= z[p];
+            }
+            for (int p = 0; p < 4; p++) {
+                g[k * 4 + p] = y[p];
+                mx = std::max(mx, y[p]);
+            }
+        }
+        if (a >= n) gs += h->Gs[(size_t)h->cur_part[a] * N + a];
+        if (b >= n) gs += h->Gs[(size_t)h->cur_part[b] * N + b];
+        if (mx > 0.0 && std::isfinite(mx)) {
+            for (int i = 0; i < K * 4; i++) g[i] /= mx;
+            gs += std::log(mx);
+        }
+        h->Gs[(size_t)h->cur_part[v] * N + v] = gs;
+    }
+    h->g_nodes.clear();
+    const int root = h->root;
+    const double* gr = h->G.data() + ((size_t)h->cur_part[root] * N + root) * SV_KMAX * 4;
+    double sum = 0.0;
+    for (int k = 0; k < K; k++) sum += h->prop[k] * gr[k * 4 + h->root_genotype];
+    h->log_c = std::log(sum) + h->Gs[(size_t)h->cur_part[root] * N + root];
+}
+
 // Resident-mode planner.  Input: the dirty nodes (dirty_list), nodes to materialise (demand_list), the parent -> children
 // map.  Output: pending_ops, children before parents, ordered so that as many results as possible are consumed by the
 // very next op (register forwarding), with the results of small subtrees (<= transient_T leaves) that are consumed at
@@ -872,6 +976,9 @@ static int sv_plan_resident_ops(sieve_core* h) {
         // a clean subtree is identical in the stored state; its buffer is shared when the indices agree
         if (store && !dirty[v] && h->cur_part[v] == h->stored_part[v]) h->valid_stored[v] = 1;
     }
+    // the constant-site factor follows the dirty nodes only (a clean subtree keeps its G)
+    for (int v : emitted)
+        if (dirty[v]) h->g_nodes.push_back(v);
     h->dirty_list.clear();
     h->demand_list.clear();
     return SIEVE_OK;
@@ -990,6 +1097,7 @@ static int sv_build_streamed_ops(sieve_core* h) {
                 child(b, SV_OP_LEAF2, &op.c2_row, &op.m2);
             if (v == root) op.flags |= SV_OP_ROOT;
             h->pending_ops.push_back(op);
+            h->g_nodes.push_back(v);
             if (a >= n) free_slots.push_back(slot_of[a]);
             if (b >= n) free_slots.push_back(slot_of[b]);
         }
@@ -1045,6 +1153,7 @@ extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t*
         SvOp op;
         SV_TRY(sv_make_op(h, ops[3 * i + 1], ops[3 * i + 2], ops[3 * i], &op));
         h->pending_ops.push_back(op);
+        h->g_nodes.push_back(ops[3 * i]);
         h->valid[ops[3 * i]] = 1;
     }
     h->pending_levels.assign(level_offsets, level_offsets + n_levels + 1);
@@ -1065,7 +1174,7 @@ extern "C" int sieve_set_root(sieve_core_t* h, int32_t root, const double* propo
 template <bool QFAST>
 static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
     const bool g0 = a.const_genotype == 0 && a.root_genotype == 0;
-    if (h->with_const) {
+    if (h->with_const && h->const_twin) {
         if (g0)
             k_prune<true, true, QFAST><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
         else
@@ -1170,11 +1279,13 @@ static int sv_flush(sieve_core* h) {
         if (pm.is_distance)
             for (int k = 0; k < K; k++) z |= pm.v[k] == 0.0;
         h->slot_zero[pm.slot] = z;
+        if (!h->hP.empty()) sv_host_matrix(h, pm);
     }
     if (h->ephemeral)
         SV_TRY(sv_build_streamed_ops(h));
     else if (!h->dirty_list.empty() || !h->demand_list.empty())
         SV_TRY(sv_plan_resident_ops(h));
+    if (!h->hP.empty() && !h->g_nodes.empty()) sv_update_G(h);
     const size_t no = h->pending_ops.size();
     size_t nm = 0, nd = 0;
     for (const PendingMatrix& pm : h->pending_mats) (pm.is_distance ? nd : nm)++;
@@ -1227,13 +1338,20 @@ static int sv_flush(sieve_core* h) {
     return SIEVE_OK;
 }
 
+static void sv_launch_reduce(sieve_core* h) {
+    const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
+    const bool algebraic = h->with_const && !h->const_twin;
+    const double* cst = algebraic ? h->d_lambda + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S) : h->d_site_const;
+    k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, cst, algebraic ? h->log_c : 0.0, h->d_weights, h->S,
+                                            h->with_const ? 1 : 0, h->d_partials, h->d_counter, h->d_result);
+}
+
 static int sv_evaluate(sieve_core* h, sieve_shard_result_t* out) {
     if (h->timing) SV_CUDA(cudaEventRecord(h->ev[2], h->stream));
     SV_TRY(sv_flush(h));
     if (h->timing) SV_CUDA(cudaEventRecord(h->ev[3], h->stream));
     const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
-    k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, h->d_site_const, h->d_weights, h->S, h->with_const ? 1 : 0,
-                                            h->d_partials, h->d_counter, h->d_result);
+    sv_launch_reduce(h);
     sv_count(h);
     SV_CUDA(cudaGetLastError());
     if (h->timing) SV_CUDA(cudaEventRecord(h->ev[4], h->stream));
@@ -1315,8 +1433,7 @@ extern "C" int sieve_replay(sieve_core_t* h, int32_t update_leaves, int32_t n_ti
             if (!h->ephemeral) SV_TRY(sv_launch_leaves(h, 0, h->S, h->S));
         }
         SV_TRY(sv_launch_staged(h));
-        k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, h->d_site_const, h->d_weights, h->S,
-                                                h->with_const ? 1 : 0, h->d_partials, h->d_counter, h->d_result);
+        sv_launch_reduce(h);
         sv_count(h);
     }
     SV_CUDA(cudaGetLastError());
@@ -1328,8 +1445,14 @@ extern "C" int sieve_get_site_log_likelihoods(sieve_core_t* h, double* out_l, do
     SV_CUDA(cudaSetDevice(h->device));
     SV_TRY(sv_flush(h));
     SV_CUDA(cudaMemcpyAsync(out_l, h->d_site_logl, sizeof(double) * h->S, cudaMemcpyDeviceToHost, h->stream));
-    if (out_c) SV_CUDA(cudaMemcpyAsync(out_c, h->d_site_const, sizeof(double) * h->S, cudaMemcpyDeviceToHost, h->stream));
+    const bool algebraic = h->with_const && !h->const_twin;
+    if (out_c) {
+        const double* src = algebraic ? h->d_lambda + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S) : h->d_site_const;
+        SV_CUDA(cudaMemcpyAsync(out_c, src, sizeof(double) * h->S, cudaMemcpyDeviceToHost, h->stream));
+    }
     SV_CUDA(cudaStreamSynchronize(h->stream));
+    if (out_c && algebraic)  // logConstRoot[s] = log C_tree + Lambda[s]
+        for (int s = 0; s < h->S; s++) out_c[s] += h->log_c;
     return SIEVE_OK;
 }
 
@@ -1361,6 +1484,45 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     } else {
         const size_t slot = (size_t)h->cur_part[node] * h->n_internal + (node - n);
         if (which == 1 && !h->with_const) return sv_fail(SIEVE_ERR_STATE, "constant-site partials are not maintained");
+        if (which == 1 && !h->const_twin) {
+            // rebuilt from the factorisation: G_node x product over the node's leaves of their constant-genotype likelihood
+            std::vector<int> leaves, st;
+            st.push_back(node);
+            while (!st.empty()) {
+                const int v = st.back();
+                st.pop_back();
+                if (v < (int)n) {
+                    leaves.push_back(v);
+                    continue;
+                }
+                if (h->eph_c1[v] == -2) return sv_fail(SIEVE_ERR_STATE, "node was never computed");
+                st.push_back(h->eph_c1[v]);
+                if (h->eph_c2[v] >= 0) st.push_back(h->eph_c2[v]);
+            }
+            int* d_list = nullptr;
+            double *d_G = nullptr, *d_o = nullptr;
+            const size_t NN = K * S * 4;
+            cudaError_t e = cudaMalloc(&d_list, sizeof(int) * leaves.size());
+            if (e == cudaSuccess) e = cudaMalloc(&d_G, sizeof(double) * 16);
+            if (e == cudaSuccess) e = cudaMalloc(&d_o, sizeof(double) * NN);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_list, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, h->stream);
+            const double* g = h->G.data() + ((size_t)h->cur_part[node] * h->n_nodes + node) * SV_KMAX * 4;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_G, g, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) {
+                k_export_const<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(
+                    h->d_leaf0 + (size_t)h->cur_leaf * n * S, d_list, (int)leaves.size(), (long long)S, d_G,
+                    h->Gs[(size_t)h->cur_part[node] * h->n_nodes + node], (int)S, (int)K, h->log_mode ? 1 : 0, d_o);
+                sv_count(h);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, NN * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            cudaFree(d_list);
+            cudaFree(d_G);
+            cudaFree(d_o);
+            SV_CUDA(e);
+            return SIEVE_OK;
+        }
         x = (which ? h->d_cpart : h->d_part) + slot * S * SV_KMAX * 4;
         sc = (which ? h->d_cscale : h->d_scale) + slot * S;
     }
@@ -1386,6 +1548,7 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->eph_c1_stored = h->eph_c1;
     h->eph_c2_stored = h->eph_c2;
     h->valid_stored = h->valid;
+    h->log_c_stored = h->log_c;
     return SIEVE_OK;
 }
 extern "C" int sieve_unstore(sieve_core_t* h) {
@@ -1396,6 +1559,7 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
     h->eph_c1 = h->eph_c1_stored;
     h->eph_c2 = h->eph_c2_stored;
     h->valid = h->valid_stored;
+    h->log_c = h->log_c_stored;
     return SIEVE_OK;
 }
 extern "C" int sieve_restore(sieve_core_t* h) {
@@ -1406,6 +1570,7 @@ extern "C" int sieve_restore(sieve_core_t* h) {
     h->eph_c1.swap(h->eph_c1_stored);
     h->eph_c2.swap(h->eph_c2_stored);
     h->valid.swap(h->valid_stored);
+    std::swap(h->log_c, h->log_c_stored);
     // after a rejected parameter proposal the tables hold the rejected values; they are compared with the values of
     // the next sieve_set_leaf_params at the next leaf update, so nothing has to be rebuilt here
     return SIEVE_OK;

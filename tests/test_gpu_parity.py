@@ -616,3 +616,48 @@ def test_transient_nodes_do_not_change_results(core_mod, oracle, monkeypatch):
         np.testing.assert_array_equal(runs[T][1], runs["0"][1])
         for a, b in zip(runs[T][2] + runs[T][3], runs["0"][2] + runs["0"][3]):
             np.testing.assert_array_equal(a, b)
+
+
+def test_algebraic_constant_site_path_equals_per_site_twin(core_mod, oracle, monkeypatch):
+    """The constant-site partials factorise into (a site-independent 4-vector per node and category) x (product over the
+    leaves below of their constant-genotype likelihood); the default path uses that.  SIEVE_B200_CONST_TWIN=1 prunes them
+    per site like the reference: both must agree with each other and with the oracle, through proposals and rejections."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood, LeafModelParams
+    d = synthetic(37, 260, seed=91)
+    counts, tree = d["counts"], d["tree"]
+    M = 5000.0
+    out = {}
+    for twin in ("0", "1"):
+        monkeypatch.setenv("SIEVE_B200_CONST_TWIN", twin)
+        for asc in ("felsenstein_mean", "lewis"):
+            tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode=asc, n_background_sites=M)
+            vals = [tl.calculate_logp()]
+            consts = [tl.pattern_log_likelihoods()[1].copy()]
+            rng = np.random.default_rng(4)
+            for it in range(6):
+                t2 = tl.tree.copy()
+                node = int(rng.integers(tree.n, tree.node_count - 1))
+                lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+                t2.height[node] = lo + (t2.height[t2.parent[node]] - lo) * rng.random()
+                tl.store()
+                tl.set_tree(t2, [node])
+                vals.append(tl.calculate_logp())
+                if it % 2:
+                    tl.restore()
+                    consts.append(tl.pattern_log_likelihoods()[1].copy())
+            tl.store()
+            tl.set_leaf_params(LeafModelParams(0.25, 45.0, 60.0, 0.012, 130.0, 2.4))
+            vals.append(tl.calculate_logp())
+            consts.append(tl.pattern_log_likelihoods()[1].copy())
+            tl.restore()
+            tl.has_dirt = 2
+            vals.append(tl.calculate_logp())
+            cp = tl.core.get_node_partials(tree.n + 9, const=True)
+            out[(twin, asc)] = (vals, consts, cp)
+            tl.close()
+    for asc in ("felsenstein_mean", "lewis"):
+        a, b = out[("0", asc)], out[("1", asc)]
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
+        for x, y in zip(a[1], b[1]):
+            np.testing.assert_allclose(x, y, rtol=1e-13)
+        np.testing.assert_allclose(a[2], b[2], rtol=1e-12, atol=1e-11)
