@@ -644,6 +644,9 @@ def test_algebraic_constant_site_path_equals_per_site_twin(core_mod, oracle, mon
                 vals.append(tl.calculate_logp())
                 if it % 2:
                     tl.restore()
+                    # the per-site arrays are not double buffered (in the reference neither): re-derive the root first
+                    tl.core.update_nodes(tl.tree.ops([tl.tree.root]), flip=False)
+                    tl.core.evaluate()
                     consts.append(tl.pattern_log_likelihoods()[1].copy())
             tl.store()
             tl.set_leaf_params(LeafModelParams(0.25, 45.0, 60.0, 0.012, 130.0, 2.4))
