@@ -787,12 +787,17 @@ static void sv_host_matrix(sieve_core* h, const PendingMatrix& pm) {
     static const double P1[16] = {3, 6, -3, -6, 1, 2, -1, -2, -1, -2, 1, 2, -1, -2, 1, 2};     // 8 Pi1
     static const double P2[16] = {9, -18, 3, 6, -3, 6, -1, -2, 1, -2, 11, -10, 1, -2, -5, 6};  // 16 Pi2
     for (int k = 0; k < K; k++) {
+        double d = 0.0, q1 = 0.0, q2 = 0.0;
+        if (pm.is_distance) {
+            d = pm.v[k];
+            const double g1 = expm1(-0.2 * d);  // expm1(-0.4 d) = g1 (g1 + 2)
+            q1 = g1 / 8.0;
+            q2 = g1 * (g1 + 2.0) / 16.0;
+        }
         for (int e = 0; e < 16; e++) {
             double v;
             if (pm.is_distance) {
-                const double d = pm.v[k];
-                const double g1 = expm1(-0.2 * d), g2 = expm1(-0.4 * d);
-                v = ((e % 5 == 0) ? 1.0 : 0.0) + (g1 / 8.0) * P1[e] + (g2 / 16.0) * P2[e];
+                v = ((e % 5 == 0) ? 1.0 : 0.0) + q1 * P1[e] + q2 * P2[e];
                 if (d == 0.0) v = (e % 5 == 0) ? 1.0 : 0.0;
             } else
                 v = pm.v[k * 16 + e];
@@ -1279,13 +1284,11 @@ static int sv_flush(sieve_core* h) {
         if (pm.is_distance)
             for (int k = 0; k < K; k++) z |= pm.v[k] == 0.0;
         h->slot_zero[pm.slot] = z;
-        if (!h->hP.empty()) sv_host_matrix(h, pm);
     }
     if (h->ephemeral)
         SV_TRY(sv_build_streamed_ops(h));
     else if (!h->dirty_list.empty() || !h->demand_list.empty())
         SV_TRY(sv_plan_resident_ops(h));
-    if (!h->hP.empty() && !h->g_nodes.empty()) sv_update_G(h);
     const size_t no = h->pending_ops.size();
     size_t nm = 0, nd = 0;
     for (const PendingMatrix& pm : h->pending_mats) (pm.is_distance ? nd : nm)++;
@@ -1331,6 +1334,12 @@ static int sv_flush(sieve_core* h) {
     h->last_levels = h->pending_levels;
     h->last_per_level = h->pending_per_level;
     SV_TRY(sv_launch_staged(h));
+    // the site-independent constant-site factor is host arithmetic; done here it overlaps the kernels just launched
+    // (only the reduce kernel, launched later, needs its result log C_tree)
+    if (!h->hP.empty()) {
+        for (const PendingMatrix& pm : h->pending_mats) sv_host_matrix(h, pm);
+        if (!h->g_nodes.empty()) sv_update_G(h);
+    }
     h->pending_mats.clear();
     h->pending_ops.clear();
     h->pending_levels.clear();

@@ -663,4 +663,5 @@ def test_algebraic_constant_site_path_equals_per_site_twin(core_mod, oracle, mon
         np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
         for x, y in zip(a[1], b[1]):
             np.testing.assert_allclose(x, y, rtol=1e-13)
-        np.testing.assert_allclose(a[2], b[2], rtol=1e-12, atol=1e-11)
+        # entries that are O(d^2) in a short branch carry a relative error of ~eps/d in either path
+        np.testing.assert_allclose(a[2], b[2], rtol=1e-11, atol=1e-10)
