@@ -69,14 +69,16 @@ __host__ __device__ inline SvDmAlphas sv_dm_alphas(double eps, double w1, double
 }
 
 __global__ void k_build_dm_tables(double* __restrict__ dmA, double* __restrict__ dmB, int C, SvDmAlphas al) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per (count, column): six short logGamma chains per count instead of one long one
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = idx / 6, col = idx % 6;
     if (c >= C) return;
-    dmA[4 * c + 0] = sv_dm_log_partial(c, al.fw1);
-    dmA[4 * c + 1] = sv_dm_log_partial(c, al.omw1);
-    dmA[4 * c + 2] = sv_dm_log_partial(c, al.hw2);
-    dmA[4 * c + 3] = sv_dm_log_partial(c, al.fw2);
-    dmB[2 * c + 0] = sv_dm_log_partial(c, al.w1);
-    dmB[2 * c + 1] = sv_dm_log_partial(c, al.w2);
+    const double alpha = col == 0 ? al.fw1 : col == 1 ? al.omw1 : col == 2 ? al.hw2 : col == 3 ? al.fw2 : col == 4 ? al.w1 : al.w2;
+    const double v = sv_dm_log_partial(c, alpha);
+    if (col < 4)
+        dmA[4 * c + col] = v;
+    else
+        dmB[2 * c + (col - 4)] = v;
 }
 
 struct SvCovParams {
@@ -103,7 +105,7 @@ __device__ __forceinline__ double sv_seq_cov_log(int x, int alleles, double s, d
 }
 
 // The coverage part of the dropout mixture at coverage x, scaled by its own maximum:
-//   single ADO: e[0] = (1-theta) * NB_2 / M, e[1] = theta * NB_1 / M, e[2] = log M, e[3] = -inf
+//   single ADO: e[0] = (1-theta) * NB_2 / M, e[1] = theta * NB_1 / M, e[2] = log M, e[3] = log(e[0] + e[1]) + log M
 //   locus  ADO: e[0] = (1-theta)^2 * NB_2 / M, e[1] = theta (1-theta) * NB_1 / M, e[2] = log M, e[3] = log(theta^2 NB_0 / M)
 __device__ __forceinline__ void sv_cov_entry(int x, double s, const SvCovParams& cp, double (&e)[4]) {
     const double c2 = sv_seq_cov_log(x, 2, s, cp.t, cp.v);
@@ -115,7 +117,7 @@ __device__ __forceinline__ void sv_cov_entry(int x, double s, const SvCovParams&
         e[0] = exp(a - m);
         e[1] = exp(b - m);
         e[2] = m;
-        e[3] = __longlong_as_double(0xfff0000000000000LL);
+        e[3] = log(e[0] + e[1]) + m;  // log of the coverage mixture: the constant genotype's leaf log-likelihood is N0 + this
     } else {
         const double c0 = sv_seq_cov_log(x, 0, s, cp.t, cp.v);
         const double a = 2 * l1t + c2, b = lt + l1t + c1, z = 2 * lt + c0;
@@ -316,7 +318,10 @@ __global__ void __launch_bounds__(256, SV_LEAF_MINB) k_leaf(SvLeafArgs a) {
         outS[s] = ls;
         if (out0) {
             const int cg = a.const_genotype;
-            out0[s] = log(cg == 0 ? x[0] : (cg == 1 ? x[1] : (cg == 2 ? x[2] : x[3]))) + ls;
+            if (a.cp.single_ado && cg == 0)
+                out0[s] = N0 + e[3];  // log(e^{N0} (e0 + e1) M): no transcendental on the common path
+            else
+                out0[s] = log(cg == 0 ? x[0] : (cg == 1 ? x[1] : (cg == 2 ? x[2] : x[3]))) + ls;
         }
     }
 }

@@ -537,7 +537,7 @@ static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, lo
         h->cov_dirty = true;
     h->tab_lp = h->lp;
     if (h->dm_dirty) {
-        k_build_dm_tables<<<(C + 127) / 128, 128, 0, h->stream>>>(h->d_dmA, h->d_dmB, C, al);
+        k_build_dm_tables<<<(6 * C + 127) / 128, 128, 0, h->stream>>>(h->d_dmA, h->d_dmB, C, al);
         sv_count(h);
         h->dm_dirty = false;
     }
