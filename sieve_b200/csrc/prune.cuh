@@ -69,15 +69,23 @@ __device__ __forceinline__ double sv_sel(const double (&x)[4], int g) {
 #define SV_PRUNE_MINB 5
 #endif
 #ifndef SV_PRUNE_NS_Q
-#define SV_PRUNE_NS_Q 1
+#define SV_PRUNE_NS_Q 2       // variant-only Q walk: 2 sites per lane at 6 blocks/SM (78 regs) measured best
+#endif
+#ifndef SV_PRUNE_NS_Q_TWIN
+#define SV_PRUNE_NS_Q_TWIN 1  // with the per-site constant twin the state doubles: 1 site per lane at 8 blocks/SM
 #endif
 #ifndef SV_PRUNE_MINB_CONST_Q
 #define SV_PRUNE_MINB_CONST_Q 8
 #endif
 #ifndef SV_PRUNE_MINB_Q
-#define SV_PRUNE_MINB_Q 8
+#define SV_PRUNE_MINB_Q 6
 #endif
-#define SV_PRUNE_SITES_Q ((SV_PRUNE_THREADS / 4) * SV_PRUNE_NS_Q)
+__host__ __device__ constexpr int sv_prune_ns(bool with_const, bool qfast) {
+    return qfast ? (with_const ? SV_PRUNE_NS_Q_TWIN : SV_PRUNE_NS_Q) : SV_PRUNE_NS;
+}
+__host__ __device__ constexpr int sv_prune_sites(bool with_const, bool qfast) {
+    return (SV_PRUNE_THREADS / 4) * sv_prune_ns(with_const, qfast);
+}
 
 // y_j = M x_j for the NS sites of a lane; every matrix element is read from shared memory once
 template <int NS>
@@ -147,7 +155,7 @@ template <bool WITH_CONST, bool GENO0, bool QFAST>
 __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRUNE_MINB_CONST_Q : SV_PRUNE_MINB_Q)
                                                           : (WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB))
     k_prune(SvPruneArgs a) {
-    constexpr int NS = QFAST ? SV_PRUNE_NS_Q : SV_PRUNE_NS;
+    constexpr int NS = sv_prune_ns(WITH_CONST, QFAST);
     constexpr int SITES_PER_BLOCK = (SV_PRUNE_THREADS / 4) * NS;
     // warp-private copies of the op's two 4 x 4 x 4 matrices: no block-wide barrier anywhere in the walk, so the
     // warps of an SM drift apart and overlap each other's memory latency

@@ -1231,7 +1231,7 @@ static int sv_launch_staged(sieve_core* h) {
         a.site_const = h->d_site_const;
         // the Q-specialised walk needs every matrix of the launch to have been given as a distance (and genotype 0)
         const bool qfast = h->last_qfast && a.const_genotype == 0 && a.root_genotype == 0 && !h->force_generic;
-        const int spb = qfast ? SV_PRUNE_SITES_Q : SV_PRUNE_SITES;
+        const int spb = sv_prune_sites(h->with_const && h->const_twin, qfast);
         const unsigned gx = (unsigned)((h->S + spb - 1) / spb);
         auto launch = [&](dim3 grid) {
             if (qfast)
