@@ -100,6 +100,10 @@ int sieve_device_bytes(sieve_core_t *h, uint64_t *out);
  * counts is int32 [site][cell][tuple_len], tuple_len 4 = (alt1, alt2, alt3, cov) or 5 = the reference's
  * (alt1, alt2, alt3, ref, cov) of datatype/FullSupsCov.java:74-77. */
 int sieve_set_counts(sieve_core_t *h, const int32_t *counts, int32_t tuple_len);
+/* the tensor of the ingest format (sieve_b200/ingest.py): HOST memory already in the core's own
+ * order [cell][site][4] (alt1, alt2, alt3, cov), int32 (dtype_code 0) or uint16 (dtype_code 1); streamed in chunks, so
+ * `counts` may be a memory-mapped file */
+int sieve_set_counts_cellmajor(sieve_core_t *h, const void *counts, int32_t dtype_code);
 /* as above but the tensor already lives on the device in the core's own layout int32 [cell][site][4] */
 int sieve_set_counts_device(sieve_core_t *h, const void *d_counts_cell_site_4);
 /* ScsAlignment.getPatternWeight (likelihood/ScsTreeLikelihood.java:2626); NULL = all 1 */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "sieve_destroy": (C.c_int, [_vp]),
     "sieve_device_bytes": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "sieve_set_counts": (C.c_int, [_vp, _ip, C.c_int32]),
+    "sieve_set_counts_cellmajor": (C.c_int, [_vp, _vp, C.c_int32]),
     "sieve_set_counts_device": (C.c_int, [_vp, _vp]),
     "sieve_set_pattern_weights": (C.c_int, [_vp, _ip]),
     "sieve_compute_size_factors": (C.c_int, [_vp, C.c_int32, _dp, _dp]),

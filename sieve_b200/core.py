@@ -58,6 +58,11 @@ class ScsCudaLikelihoodCore:
         assert c.shape[:2] == (self.S, self.n) and c.shape[2] in (4, 5), c.shape
         check(self.L.sieve_set_counts(self.h, _iptr(c), c.shape[2]))
 
+    def set_counts_cellmajor(self, counts):
+        """[cell][site][4] int32 or uint16 in host memory (e.g. the memory-mapped tensor of sieve_b200.ingest)."""
+        assert counts.shape == (self.n, self.S, 4) and counts.dtype in (np.int32, np.uint16) and counts.flags.c_contiguous
+        check(self.L.sieve_set_counts_cellmajor(self.h, C.c_void_p(counts.ctypes.data), 0 if counts.dtype == np.int32 else 1))
+
     def set_counts_device(self, device_ptr):
         check(self.L.sieve_set_counts_device(self.h, C.c_void_p(int(device_ptr))))
 

@@ -454,6 +454,53 @@ extern "C" int sieve_set_counts(sieve_core_t* h, const int32_t* counts, int32_t 
     return sv_finish_counts(h, d_max);
 }
 
+// [cell][site][4] uint16 -> int4, tracking the largest coverage
+__global__ void k_widen_counts_u16(const ushort4* __restrict__ in, size_t N, int4* __restrict__ out, int* __restrict__ max_cov) {
+    int mx = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+        const ushort4 v = in[i];
+        out[i] = make_int4(v.x, v.y, v.z, v.w);
+        mx = max(mx, (int)v.w);
+    }
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(max_cov, mx);
+}
+
+// The ingest format's tensor (sieve_b200/ingest.py): host memory, already in the core's own order [cell][site][4], as
+// int32 (dtype_code 0) or uint16 (dtype_code 1).  Copied in bounded chunks so that a memory-mapped file can be streamed.
+extern "C" int sieve_set_counts_cellmajor(sieve_core_t* h, const void* counts, int32_t dtype_code) {
+    SV_REQUIRE(h && counts, "sieve_set_counts_cellmajor: null argument");
+    SV_REQUIRE(dtype_code == 0 || dtype_code == 1, "sieve_set_counts_cellmajor: dtype_code must be 0 (int32) or 1 (uint16)");
+    SV_CUDA(cudaSetDevice(h->device));
+    const size_t N = (size_t)h->n * h->S;
+    int* d_max = nullptr;
+    SV_CUDA(cudaMalloc(&d_max, sizeof(int)));
+    SV_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
+    const size_t chunk = (size_t)16 << 20;  // tuples per chunk
+    if (dtype_code == 0) {
+        for (size_t i0 = 0; i0 < N; i0 += chunk) {
+            const size_t m = std::min(chunk, N - i0);
+            SV_CUDA(cudaMemcpyAsync(h->d_counts + i0, (const int4*)counts + i0, m * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+            SV_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        k_max_cov<<<592, 256, 0, h->stream>>>(h->d_counts, N, d_max);
+        sv_count(h);
+    } else {
+        ushort4* d_in = nullptr;
+        SV_CUDA(cudaMalloc(&d_in, chunk * sizeof(ushort4)));
+        for (size_t i0 = 0; i0 < N; i0 += chunk) {
+            const size_t m = std::min(chunk, N - i0);
+            SV_CUDA(cudaMemcpyAsync(d_in, (const ushort4*)counts + i0, m * sizeof(ushort4), cudaMemcpyHostToDevice, h->stream));
+            k_widen_counts_u16<<<592, 256, 0, h->stream>>>(d_in, m, h->d_counts + i0, d_max);
+            sv_count(h);
+            SV_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        cudaFree(d_in);
+    }
+    SV_CUDA(cudaGetLastError());
+    return sv_finish_counts(h, d_max);
+}
+
 extern "C" int sieve_set_counts_device(sieve_core_t* h, const void* d_counts) {
     SV_REQUIRE(h && d_counts, "sieve_set_counts_device: null argument");
     SV_CUDA(cudaSetDevice(h->device));

@@ -665,3 +665,27 @@ def test_algebraic_constant_site_path_equals_per_site_twin(core_mod, oracle, mon
             np.testing.assert_allclose(x, y, rtol=1e-13)
         # entries that are O(d^2) in a short branch carry a relative error of ~eps/d in either path
         np.testing.assert_allclose(a[2], b[2], rtol=1e-11, atol=1e-10)
+
+
+def test_ingest_shard_loads_like_set_counts(core_mod, tmp_path):
+    from sieve_b200 import ingest
+    d = synthetic(9, 130, seed=33)
+    counts = d["counts"]
+    outs = []
+    for mode in ("host_site_major", "shard_u16", "shard_i32"):
+        c = core_mod.ScsCudaLikelihoodCore(9, 130, 4, 4, True, False, True)
+        if mode == "host_site_major":
+            c.set_counts(counts)
+        else:
+            p = str(tmp_path / (mode + ".sieve"))
+            ingest.write_shard(p, counts, 0, 130, dtype="uint16" if mode == "shard_u16" else "int32")
+            meta, arr = ingest.open_shard(p)
+            c.set_counts_cellmajor(np.ascontiguousarray(arr))
+        sf, st = c.compute_size_factors(0)
+        c.set_leaf_params(*PARAMS)
+        c.update_leaves(for_update=False)
+        outs.append((sf, st, c.get_node_partials(3)))
+        c.close()
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o[0], outs[0][0])
+        np.testing.assert_array_equal(o[2], outs[0][2])

@@ -111,3 +111,32 @@ def test_native_gamma_rates_match_scipy():
     for a in (0.05, 0.5, 1.0, 3.7, 50.0):
         ref, _ = substmodel.gamma_category_rates(a, 4)
         np.testing.assert_allclose(gamma_category_rates(a, 4), ref, rtol=1e-9)
+
+
+def test_ingest_shards_round_trip(tmp_path):
+    from sieve_b200 import ingest
+    rng = np.random.default_rng(5)
+    counts = rng.integers(0, 200, size=(53, 7, 4)).astype(np.int32)
+    counts[..., 3] += counts[..., :3].sum(-1)
+    names = ["c%02d" % i for i in range(7)]
+    sf = rng.random(7) + 0.5
+    paths = ingest.write_shards(str(tmp_path / "d"), counts, 3, names, sf, 9727)
+    got, begin = [], 0
+    for r, p in enumerate(paths):
+        meta, arr = ingest.open_shard(p)
+        assert meta["site_begin"] == begin and meta["n_sites_total"] == 53 and meta["dtype"] == "uint16"
+        assert meta["cell_names"] == names and meta["n_background_sites"] == 9727
+        np.testing.assert_allclose(meta["size_factors"], sf)
+        assert arr.shape == (7, meta["n_sites"], 4)
+        got.append(np.asarray(arr).transpose(1, 0, 2))
+        begin += meta["n_sites"]
+    np.testing.assert_array_equal(np.concatenate(got), counts)
+    big = counts.copy()
+    big[0, 0, 3] = 70000
+    meta = ingest.write_shard(str(tmp_path / "big.sieve"), big, 0, 53)
+    assert meta["dtype"] == "int32"
+    with pytest.raises(ValueError):
+        ingest.write_shard(str(tmp_path / "bad.sieve"), -counts, 0, 53)
+    with pytest.raises(ValueError):
+        (tmp_path / "junk").write_bytes(b"hello")
+        ingest.open_shard(str(tmp_path / "junk"))
