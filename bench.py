@@ -398,9 +398,12 @@ def main():
     barrier()
     with torch.cuda.stream(lib_stream):
         ev0.record()
-    for _ in range(args.steps):
-        core.replay(update_leaves=True, n_times=1)
-        exchange()
+    if world == 1:
+        core.replay(update_leaves=True, n_times=args.steps)      # K steps enqueued by one native call: no host in the loop
+    else:
+        for _ in range(args.steps):
+            core.replay(update_leaves=True, n_times=1)
+            exchange()
     with torch.cuda.stream(lib_stream):
         ev1.record()
     barrier()
@@ -508,6 +511,15 @@ def main():
         e2e_value = world * args.steps / e2e_s_max
         stage_bytes = core.last_stage_bytes() + 48
         achieved = alg_prune / (prune_ms / 1000.0) / 1e9
+        traffic = None
+        try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this very workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            w = tr["workload"]
+            if (w["cells"], w["sites"]) == (n, S) and not (args.per_level or args.matrices or args.streamed or with_const):
+                k = tr["k_prune<0, 1, 1>"]
+                traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -525,7 +537,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": "k_prune<%s, geno0, %s>" % ("const twin" if with_const else "variant only", "generic" if args.matrices else "qfast"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_prune), "launch_ms": prune_ms},
             "kernels": {"leaf_ms": leaf_ms, "leaf_GBps": alg_leaf / (leaf_ms / 1000.0) / 1e9 if leaf_ms > 0 else None,
                         "leaf_frac": alg_leaf / (leaf_ms / 1000.0) / 1e9 / peak if leaf_ms > 0 else None,
