@@ -689,3 +689,40 @@ def test_ingest_shard_loads_like_set_counts(core_mod, tmp_path):
     for o in outs[1:]:
         np.testing.assert_array_equal(o[0], outs[0][0])
         np.testing.assert_array_equal(o[2], outs[0][2])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_smallest_trees(core_mod, oracle, n):
+    """n = 1: the unary root sits directly on the only leaf; n = 2: one cherry under the trunk."""
+    rng = np.random.default_rng(n)
+    tree = caterpillar(n, 0.0, 0.07)
+    S = 45
+    counts = np.zeros((S, n, 4), dtype=np.int32)
+    cov = rng.integers(0, 70, size=(S, n))
+    counts[..., 0] = (cov * rng.random((S, n)) * (rng.random((S, n)) < 0.5)).astype(int)
+    counts[..., 3] = cov
+    counts[3] = 0                                    # a site nobody covers
+    c5 = oracle.counts5(counts)
+    sf = np.ones(n) if n == 1 else oracle.size_factors(c5)[0]
+    rates, props = substmodel.gamma_category_rates(1.3, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    for mode in ("distances", "matrices"):
+        c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True)
+        c.set_counts(counts)
+        c.set_size_factors(sf)
+        c.set_leaf_params(*PARAMS)
+        c.update_leaves(for_update=False)
+        c.set_root(tree.root, props, 0)
+        nodes = [i for i in range(tree.node_count) if i != tree.root]
+        if mode == "distances":
+            c.set_distances(nodes, substmodel.node_distances(tree, rates)[nodes], for_update=False)
+        else:
+            c.set_matrices(nodes, mats[nodes], for_update=False)
+        c.update_nodes(tree.ops(), flip=False)
+        r = c.evaluate()
+        logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, "felsenstein_mean", 100.0)
+        sl, sc = c.site_log_likelihoods()
+        _close(sl, osl, SITE_RTOL)
+        _close(sc, osc, SITE_RTOL)
+        assert abs(core_mod.combine_shards([r], "felsenstein_mean", 100.0) - logp) <= TOTAL_RTOL * abs(logp)
+        c.close()
