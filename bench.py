@@ -477,14 +477,13 @@ def main():
     # ---------------- MCMC states/s: replay of the templates' operator schedules (native driver) ----------------
     mcmc = {}
     if args.mcmc_states > 0:
-        from sieve_b200.distributed import all_gather_results, result_to_tensor
+        from sieve_b200.distributed import bind_native_comm
         from sieve_b200.mcmc import McmcReplay
+        if world > 1:
+            bind_native_comm(core)      # the chain's per-state exchange is then a native NCCL all-gather inside sieve_step
         for mix in ("stage1", "stage2", "relaxed2"):
             mc = McmcReplay(core, tree, mix=mix, asc_mode="felsenstein_mean", n_background_sites=N_BACKGROUND,
                             gamma_shape=1.0, leaf=PARAMS, branch_rates=br, seed=SEED)
-            if world > 1:
-                mc.set_combine(lambda r: combine_shards(all_gather_results(result_to_tensor(r, dev)),
-                                                        "felsenstein_mean", N_BACKGROUND))
             mc.run(20)                      # warm-up
             barrier()
             st = mc.run(args.mcmc_states, reset=True)

@@ -196,6 +196,15 @@ int sieve_restore(sieve_core_t *h);
  * logP = sum_r a_r + bias(asc_mode, b_r, M).  Pure host arithmetic on n_shards small structs. */
 double sieve_combine_shards(const sieve_shard_result_t *shards, int32_t n_shards, int32_t asc_mode,
                             double n_background_sites);
+/* One process per GPU: the join of the reference's workers (likelihood/ThreadedScsTreeLikelihood.java:366-379) becomes an
+ * NCCL all-gather of the 5-double results on the handle's stream, issued by every sieve_evaluate / sieve_step once a
+ * communicator is bound.  Rank 0 draws an id (128 bytes), distributes it by any means, every rank calls sieve_comm_init.
+ * sieve_last_global_results returns the results of all ranks, rank order, of the last evaluation (out_world[comm size]). */
+int sieve_comm_unique_id(uint8_t *id_out128);
+int sieve_comm_init(sieve_core_t *h, int32_t rank, int32_t world, const uint8_t *id128);
+int sieve_comm_size(sieve_core_t *h);
+int sieve_last_global_results(sieve_core_t *h, sieve_shard_result_t *out_world);
+
 /* calcPatternPoints (likelihood/ThreadedScsTreeLikelihood.java:227-238): points[n_shards + 1] */
 void sieve_pattern_points(int32_t n_sites, int32_t n_shards, int32_t *points);
 

@@ -75,6 +75,10 @@ SIGNATURES = {
     "sieve_store": (C.c_int, [_vp]),
     "sieve_unstore": (C.c_int, [_vp]),
     "sieve_restore": (C.c_int, [_vp]),
+    "sieve_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "sieve_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
+    "sieve_comm_size": (C.c_int, [_vp]),
+    "sieve_last_global_results": (C.c_int, [_vp, C.POINTER(ShardResult)]),
     "sieve_combine_shards": (C.c_double, [C.POINTER(ShardResult), C.c_int32, C.c_int32, C.c_double]),
     "sieve_pattern_points": (None, [C.c_int32, C.c_int32, _ip]),
     "sieve_background_log_likelihood": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _ip, C.c_int64,

@@ -194,6 +194,20 @@ class ScsCudaLikelihoodCore:
     def restore(self):
         check(self.L.sieve_restore(self.h))
 
+    # ---- multi-process shards ---------------------------------------------------------------------------------
+    def comm_init(self, rank, world, unique_id_bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id_bytes))
+        check(self.L.sieve_comm_init(self.h, int(rank), int(world), buf))
+
+    def comm_size(self):
+        return self.L.sieve_comm_size(self.h)
+
+    def last_global_results(self):
+        n = self.comm_size()
+        arr = (ShardResult * n)()
+        check(self.L.sieve_last_global_results(self.h, arr))
+        return list(arr)
+
     # ---- instrumentation -------------------------------------------------------------------------------------
     def enable_timing(self, on=True):
         check(self.L.sieve_enable_timing(self.h, int(on)))
@@ -252,3 +266,9 @@ def background_log_likelihood(hists, n_background_sites, n_taxa, eps, w1, device
                                                      int(n_background_sites), int(n_taxa), float(eps), float(w1),
                                                      C.byref(out)))
     return out.value
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * 128)()
+    check(_lib.lib().sieve_comm_unique_id(buf))
+    return bytes(buf)

@@ -18,6 +18,7 @@
 #include "reduce.cuh"
 #include "sizefactors.cuh"
 #include "background.cuh"
+#include "comm.cuh"
 
 static thread_local std::string g_err;
 
@@ -118,6 +119,12 @@ struct sieve_core {
     std::vector<int> demand_list;           // nodes whose partial must be materialised (getNodePartials)  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
     std::vector<int> last_levels;
     bool last_per_level = false;
+
+    // multi-process shards: NCCL communicator bound to this handle's stream
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    double* d_gather = nullptr;   // [world][5]
+    double* h_gather = nullptr;   // pinned
 
     // timing
     bool timing = false;
@@ -343,6 +350,9 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_partials);
     cudaFree(h->d_counter);
     cudaFree(h->d_result);
+    if (h->comm && sv_nccl().ok) sv_nccl().CommDestroy(h->comm);
+    cudaFree(h->d_gather);
+    if (h->h_gather) cudaFreeHost(h->h_gather);
     cudaFree(h->d_stage);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->h_result) cudaFreeHost(h->h_result);
@@ -1412,6 +1422,13 @@ static int sv_evaluate(sieve_core* h, sieve_shard_result_t* out) {
     SV_CUDA(cudaGetLastError());
     if (h->timing) SV_CUDA(cudaEventRecord(h->ev[4], h->stream));
     SV_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->comm) {
+        // the one exchange of the multi-GPU path: every rank's 5 doubles to every rank, ordered after the reduce kernel
+        ncclResult_t nr = sv_nccl().AllGather(h->d_result, h->d_gather, 5, ncclDouble, h->comm, h->stream);
+        if (nr != ncclSuccess) return sv_fail(SIEVE_ERR_CUDA, std::string("ncclAllGather: ") + sv_nccl().GetErrorString(nr));
+        SV_CUDA(cudaMemcpyAsync(h->h_gather, h->d_gather, (size_t)h->comm_world * 5 * sizeof(double), cudaMemcpyDeviceToHost,
+                                h->stream));
+    }
     SV_CUDA(cudaStreamSynchronize(h->stream));
     if (out) {
         out->sum_log_l = h->h_result[0];
@@ -1668,6 +1685,51 @@ extern "C" double sieve_combine_shards(const sieve_shard_result_t* sh, int32_t n
 extern "C" void sieve_pattern_points(int32_t n_sites, int32_t n_shards, int32_t* points) {
     points[0] = 0;
     for (int i = 0; i < n_shards; i++) points[i + 1] = points[i] + n_sites / n_shards + (i < n_sites % n_shards ? 1 : 0);
+}
+
+// ---- multi-process shards -----------------------------------------------------------------------------------------------
+extern "C" int sieve_comm_unique_id(uint8_t* id_out128) {
+    SV_REQUIRE(id_out128, "null argument");
+    if (!sv_nccl().ok) return sv_fail(SIEVE_ERR_CUDA, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    ncclResult_t r = sv_nccl().GetUniqueId(&id);
+    if (r != ncclSuccess) return sv_fail(SIEVE_ERR_CUDA, std::string("ncclGetUniqueId: ") + sv_nccl().GetErrorString(r));
+    memcpy(id_out128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_comm_init(sieve_core_t* h, int32_t rank, int32_t world, const uint8_t* id128) {
+    SV_REQUIRE(h && id128 && world >= 1 && rank >= 0 && rank < world, "sieve_comm_init: bad argument");
+    if (!sv_nccl().ok) return sv_fail(SIEVE_ERR_CUDA, "libnccl.so.2 could not be loaded");
+    SV_CUDA(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    ncclResult_t r = sv_nccl().CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        h->comm = nullptr;
+        return sv_fail(SIEVE_ERR_CUDA, std::string("ncclCommInitRank: ") + sv_nccl().GetErrorString(r));
+    }
+    h->comm_rank = rank;
+    h->comm_world = world;
+    SV_TRY(sv_alloc(h, &h->d_gather, (size_t)world * 5));
+    SV_CUDA(cudaMallocHost((void**)&h->h_gather, (size_t)world * 5 * sizeof(double)));
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_comm_size(sieve_core_t* h) { return h && h->comm ? h->comm_world : 1; }
+
+extern "C" int sieve_last_global_results(sieve_core_t* h, sieve_shard_result_t* out_world) {
+    SV_REQUIRE(h && out_world, "null argument");
+    if (!h->comm) {
+        out_world[0].sum_log_l = h->h_result[0];
+        out_world[0].const_lse = h->h_result[1];
+        out_world[0].const_sum = h->h_result[2];
+        out_world[0].lewis_sum = h->h_result[3];
+        out_world[0].weight_sum = h->h_result[4];
+        return SIEVE_OK;
+    }
+    memcpy(out_world, h->h_gather, (size_t)h->comm_world * sizeof(sieve_shard_result_t));
+    return SIEVE_OK;
 }
 
 // ---- stage-1 background likelihood (a "next" row of the scope table) ----------------------------------------------

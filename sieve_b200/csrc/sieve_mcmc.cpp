@@ -135,6 +135,7 @@ struct sieve_mcmc {
     std::vector<int> op_list;
     std::vector<int> stack, order;
     std::string err;
+    std::vector<sieve_shard_result_t> world_results;
     sieve_combine_fn combine = nullptr;
     void* combine_user = nullptr;
 
@@ -209,8 +210,16 @@ int evaluate(sieve_mcmc* m, bool full, bool update_leaves, double* out_logp, int
     int rc = sieve_step_distances(m->core, update_leaves ? 1 : 0, *n_mats, m->mat_nodes.data(), m->dist.data(), *n_ops,
                                   m->op_list.data(), &r);
     if (rc != SIEVE_OK) return rc;
-    *out_logp = m->combine ? m->combine(&r, m->combine_user)
-                           : sieve_combine_shards(&r, 1, m->cfg.asc_mode, m->cfg.n_background_sites);
+    if (m->combine)
+        *out_logp = m->combine(&r, m->combine_user);
+    else {
+        // all ranks' results when a communicator is bound to the core (NCCL all-gather inside the step), else just ours
+        const int world = sieve_comm_size(m->core);
+        m->world_results.resize(world);
+        rc = sieve_last_global_results(m->core, m->world_results.data());
+        if (rc != SIEVE_OK) return rc;
+        *out_logp = sieve_combine_shards(m->world_results.data(), world, m->cfg.asc_mode, m->cfg.n_background_sites);
+    }
     return SIEVE_OK;
 }
 

@@ -45,3 +45,18 @@ def all_gather_results(local, group=None):
 def global_log_p(local, asc_mode="none", n_background_sites=0.0, group=None):
     """logP of the whole data set from this rank's shard result (identical on every rank)."""
     return combine_shards(all_gather_results(local, group), asc_mode, n_background_sites)
+
+
+def bind_native_comm(core, group=None):
+    """Binds an NCCL communicator to `core` (include/sieve_b200.h: sieve_comm_init) so that every evaluation all-gathers
+    the shard results natively on the core's stream.  The 128-byte id is drawn on rank 0 and broadcast with
+    torch.distributed (any backend)."""
+    from .core import comm_unique_id
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0, group=group)
+    core.comm_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+    return world

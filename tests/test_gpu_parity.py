@@ -726,3 +726,24 @@ def test_smallest_trees(core_mod, oracle, n):
         _close(sc, osc, SITE_RTOL)
         assert abs(core_mod.combine_shards([r], "felsenstein_mean", 100.0) - logp) <= TOTAL_RTOL * abs(logp)
         c.close()
+
+
+def test_native_comm_single_rank(core_mod):
+    """A one-rank NCCL communicator bound to the handle: every evaluation all-gathers the result struct on the handle's
+    stream (the N > 1 path is the same call with more ranks; covered at N = 2 by bench.py under torchrun)."""
+    from sieve_b200.mcmc import McmcReplay
+    d = synthetic(12, 200, seed=13)
+    counts, tree = d["counts"], d["tree"]
+    c = core_mod.ScsCudaLikelihoodCore(12, 200, 4, 4, True, True, True)
+    c.set_counts(counts)
+    c.compute_size_factors(0)
+    c.comm_init(0, 1, core_mod.comm_unique_id())
+    assert c.comm_size() == 1
+    mc = McmcReplay(c, tree, mix="stage2", asc_mode="felsenstein_mean", n_background_sites=500.0, seed=2)
+    st = mc.run(60)
+    g = c.last_global_results()
+    assert len(g) == 1 and np.isfinite(g[0].sum_log_l) and g[0].weight_sum == 200.0
+    again = mc.full_recompute()
+    assert abs(again - st["log_p"]) <= 1e-11 * abs(again)
+    mc.close()
+    c.close()
