@@ -466,7 +466,7 @@ def main():
         parity = {"sites_checked": n_chk,
                   "max_rel_site_logl": float(np.max(np.abs(site_gpu[:n_chk] - osl) / np.abs(osl))),
                   "max_rel_site_const": float(np.max(np.abs(const_gpu[:n_chk] - osc) / np.abs(osc))),
-                  "logP": logp_last, "logP_repeatable": bool(logp_first == logp_last)}
+                  "logP": logp_last, "logP_first": logp_first, "logP_repeatable": bool(logp_first == logp_last)}
         if world == 1 and not args.no_cpu_baseline:
             threads = so.max_threads()
             ns, dt, _ = cpu_eval_sample(tree, mats, props, sample, sf, threads)
