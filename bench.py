@@ -383,6 +383,9 @@ def main():
         return core.step_distances(nodes, D_host, ops, update_leaves=True)
 
     logp_first = combine_shards([exact_eval()], "felsenstein_mean", N_BACKGROUND)
+    if os.environ.get("SIEVE_BENCH_DEBUG"):
+        r_ = exact_eval()
+        print("debug first again", logp_first, combine_shards([r_], "felsenstein_mean", N_BACKGROUND), r_.sum_log_l, r_.const_lse, file=sys.stderr)
     # ---------------- warm-up (also stages matrices + ops in HBM for the device-only loop) ----------------
     for _ in range(max(args.warmup, 3)):
         r = one_step_e2e()
@@ -451,7 +454,11 @@ def main():
     torch.cuda.synchronize()
     tree_only_ms = ev0.elapsed_time(ev1) / args.steps
 
-    logp_last = combine_shards([exact_eval()], "felsenstein_mean", N_BACKGROUND)
+    r_last = exact_eval()
+    logp_last = combine_shards([r_last], "felsenstein_mean", N_BACKGROUND)
+    if os.environ.get("SIEVE_BENCH_DEBUG"):
+        r_ = exact_eval()
+        print("debug last again", logp_last, combine_shards([r_], "felsenstein_mean", N_BACKGROUND), r_last.sum_log_l, r_last.const_lse, r_.sum_log_l, r_.const_lse, file=sys.stderr)
     # ---------------- parity spot check of this very workload against the oracle (outside the timed regions) ----------
     parity = None
     cpu = None

@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
     // contiguous 1 KB access
     const int site0 = blockIdx.x * SITES_PER_BLOCK + warp * (8 * NS) + (lane >> 2);
     // Lanes beyond the last site (or beyond the last category) are clamped onto the last valid site (category): they
-    // compute and store bit-identical duplicates of a real lane's values to the same (or an unused) address, so the loop
-    // needs no predicates at all.
+    // load and compute duplicates of a real lane's values, so the loads and the arithmetic need no predicates; only the
+    // stores of out-of-range sites are suppressed.
     bool site_ok[NS];
     unsigned srow[NS];
 #pragma unroll
@@ -358,7 +358,9 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
         }
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            if (flags & SV_OP_NOSTORE) continue;
+            // clamped duplicate lanes never store: with reused scratch slots (streamed mode) a duplicate in another warp
+            // could otherwise overwrite a slot that the real lane of that site has not consumed yet
+            if ((flags & SV_OP_NOSTORE) || !site_ok[j]) continue;
             const size_t dst_row = dst_base + srow[j];
             sv_st256(a.part + dst_row * 16 + k * 4, x[j]);
             // every category lane writes the (identical) scale: a lane only ever re-reads what it wrote itself

@@ -747,3 +747,37 @@ def test_native_comm_single_rank(core_mod):
     assert abs(again - st["log_p"]) <= 1e-11 * abs(again)
     mc.close()
     c.close()
+
+
+def test_streamed_ragged_chunks_are_deterministic(core_mod, monkeypatch):
+    """Regression: with reused scratch slots, lanes beyond the last site of a chunk must not store (a duplicate lane in
+    another warp could overwrite a slot the real lane had not consumed yet).  Ragged chunk tails, deep tree, repeats."""
+    monkeypatch.setenv("SIEVE_B200_CHUNK_SITES", "1000")     # rounded to 1024: chunks 1024 + 1024 + 953 (tail 953 = 59 * 16 + 9)
+    rng = np.random.default_rng(3)
+    n, S = 700, 3001
+    tree = random_coalescent(n, rng)
+    tree.height *= 0.3 / tree.height[tree.root]
+    counts = np.zeros((S, n, 4), dtype=np.int32)
+    cov = rng.poisson(40, size=(S, n))
+    counts[..., 0] = (cov * rng.random((S, n)) * (rng.random((S, n)) < 0.2)).astype(np.int32)
+    counts[..., 3] = cov
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    nodes = np.array([i for i in range(tree.node_count) if i != tree.root], dtype=np.int32)
+    D = substmodel.node_distances(tree, rates)[nodes]
+    out = {}
+    for eph in (False, True):
+        c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True, ephemeral=eph)
+        c.set_counts(counts)
+        c.compute_size_factors(0)
+        c.set_leaf_params(*PARAMS)
+        c.update_leaves(False)
+        c.set_root(tree.root, props, 0)
+        vals = []
+        for _ in range(5):
+            r = c.step_distances(nodes, D, tree.ops(), update_leaves=True)
+            vals.append((r.sum_log_l, r.const_lse))
+        assert all(v == vals[0] for v in vals), vals
+        out[eph] = (vals[0], c.site_log_likelihoods()[0])
+        c.close()
+    assert out[True][0] == out[False][0]
+    np.testing.assert_array_equal(out[True][1], out[False][1])
