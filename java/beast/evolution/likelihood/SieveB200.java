@@ -28,6 +28,8 @@ public final class SieveB200 {
     public static native void updateLeaves(long h, boolean forUpdate);
     public static native void setNodeMatrixForUpdate(long h, int node);
     public static native void setNodeMatrix(long h, int node, int category, double[] p16);
+    /** fast path for the fixed rate matrix: distances[i * K + k] = branch length * branch rate * site rate_k of nodes[i] */
+    public static native void setDistances(long h, int[] nodes, double[] distances, boolean forUpdate);
     public static native void setNodePartialsForUpdate(long h, int node);
     public static native void calculatePartials(long h, int child1, boolean isLeaf1, int child2, boolean isLeaf2,
                                                 int parent, int constGenotype);

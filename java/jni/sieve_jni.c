@@ -62,6 +62,15 @@ JNIEXPORT void JNICALL FN(setNodeMatrix)(JNIEnv *e, jclass c, jlong h, jint n, j
     (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
     chk(e, rc);
 }
+JNIEXPORT void JNICALL FN(setDistances)(JNIEnv *e, jclass c, jlong h, jintArray nodes, jdoubleArray d, jboolean f) {
+    const jsize n = (*e)->GetArrayLength(e, nodes);
+    jint *pn = (*e)->GetPrimitiveArrayCritical(e, nodes, NULL);
+    jdouble *pd = (*e)->GetPrimitiveArrayCritical(e, d, NULL);
+    int rc = sieve_set_distances(H(h), n, (const int32_t *)pn, pd, f);
+    (*e)->ReleasePrimitiveArrayCritical(e, d, pd, JNI_ABORT);
+    (*e)->ReleasePrimitiveArrayCritical(e, nodes, pn, JNI_ABORT);
+    chk(e, rc);
+}
 JNIEXPORT void JNICALL FN(setNodePartialsForUpdate)(JNIEnv *e, jclass c, jlong h, jint n) {
     chk(e, sieve_set_node_partials_for_update(H(h), n));
 }
