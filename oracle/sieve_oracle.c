@@ -234,10 +234,11 @@ void so_nuc_likelihoods(const int *reads5, const so_leaf_params *P, double *out4
 /* rawreadcountsmodel/RawReadCountsModelFiniteMuDM.java:121-260.
  * N = nuc likelihoods (index 0..3 as above), C = coverage likelihoods indexed by position in
  * modeledAlleles ({1,2} for single ADO, {0,1,2} for locus ADO); genotype 0..3 = 0/0,0/1,1/1,1/1'. */
-double so_mixed_likelihood(int genotype, const double *N, const double *C, const so_leaf_params *P)
+static double so_mixed_core(int genotype, const double *N, const double *C, const so_leaf_params *P, double *comp)
 {
     const double theta = P->ado_rate;
-    double tmp[3], in2[2];
+    double tmp_local[3], in2[2];
+    double *tmp = comp ? comp : tmp_local; /* :130 "comp == null ? new double[...] : comp" */
     /* which nuc category carries the "no dropout" term, which the "one allele left" term */
     if (P->single_ado) {
         if (P->use_log) {
@@ -330,6 +331,46 @@ double so_mixed_likelihood(int genotype, const double *N, const double *C, const
                 tmp[2] = pow(theta, 2) * C[0];
                 return tmp[0] + tmp[1] + tmp[2];
             }
+        }
+    }
+}
+
+double so_mixed_likelihood(int genotype, const double *N, const double *C, const so_leaf_params *P)
+{
+    return so_mixed_core(genotype, N, C, P, NULL);
+}
+
+/* math/util/MathFunctions.java:168-180 maxIndices, as a bit mask (bit i set <=> index i is listed) */
+static unsigned so_max_indices_mask(const double *v, int n)
+{
+    double max = v[0];
+    unsigned mask = 1u;
+    for (int i = 1; i < n; i++) {
+        if (v[i] > max) {
+            max = v[i];
+            mask = 1u << i;
+        } else if (v[i] == max)
+            mask |= 1u << i;
+    }
+    return mask;
+}
+
+/* RawReadCountsModelFiniteMuDM.java:54-77 computeMixedLikelihood(..., MLCompIndex): the mixed likelihood plus the
+ * arg-max set of its dropout components (index = number of dropped alleles), used when traceMLGenotypes is on
+ * (RawReadCountsModelInterface.java:515-567).  out: [pattern][4]; ado: [pattern][4] tie masks. */
+void so_leaf_likelihood_ml(const int *counts, int n_taxa, int p0, int p1, int taxon, double size_factor,
+                           const so_leaf_params *P, double *out, unsigned char *ado)
+{
+    const int n_all = P->single_ado ? 2 : 3;
+    const int first = P->single_ado ? 1 : 0;
+    for (int p = p0; p < p1; p++) {
+        const int *reads = counts + ((size_t)p * n_taxa + taxon) * 5;
+        double C[3], N[4], comp[3];
+        for (int i = 0; i < n_all; i++) C[i] = so_seq_cov_likelihood(reads[4], first + i, size_factor, P);
+        so_nuc_likelihoods(reads, P, N);
+        for (int g = 0; g < 4; g++) {
+            out[(size_t)(p - p0) * 4 + g] = so_mixed_core(g, N, C, P, comp);
+            ado[(size_t)(p - p0) * 4 + g] = (unsigned char)so_max_indices_mask(comp, n_all);
         }
     }
 }
@@ -681,6 +722,78 @@ void so_core_calculate_partials(so_core *c, int child1, int is_leaf1, int child2
     else
         so_lin_pruning(c, ch1, ch1c, m1, ch2, ch2c, m2, so_part(c, parent), so_cpart(c, parent), const_genotype);
     if (c->use_scaling) so_scale_partials(c, parent);
+}
+
+/* Max-sum twin of the log-space pruning, ScsBeerLikelihoodCore.java:3054-3173 (leaf, leaf), :3175-3322 (leaf,
+ * internal), :3324-3486 (internal, internal / unary root).  The three reference functions differ only in which array
+ * a child contributes: a leaf its (sum-product) partials, an internal node its MLPartials -- the caller passes the
+ * right one as ch1 / ch2.  ch2 == NULL <=> unary root.  Layouts as the core: ch*, par_ml [K][S][G]; m* [K][G*G].
+ * back[K][S][G]: low nibble = arg-max set over the genotypes of child 1 (parentMLGenotypes[pIndex][0]), high nibble =
+ * child 2, bit c set <=> genotype c is listed; ties by exact equality, first index seeds the list (:3107-3131). */
+void so_ml_log_pruning(int K, int S, const double *ch1, const double *m1, const double *ch2, const double *m2,
+                       double *par_ml, unsigned char *back)
+{
+    const int G = 4;
+    size_t pIndex = 0, cIndex = 0;
+    for (int k = 0; k < K; k++) {
+        for (int s = 0; s < S; s++) {
+            size_t mIndex = (size_t)k * G * G;
+            for (int pg = 0; pg < G; pg++) {
+                double max1 = 0.0, max2 = 0.0;
+                unsigned l1 = 0, l2 = 0;
+                for (int cg = 0; cg < G; cg++) {
+                    const double tmp1 = log(m1[mIndex] > 0.0 ? m1[mIndex] : SO_MIN_VALUE) + ch1[cIndex + cg];
+                    double tmp2 = 0.0;
+                    if (ch2) tmp2 = log(m2[mIndex] > 0.0 ? m2[mIndex] : SO_MIN_VALUE) + ch2[cIndex + cg];
+                    if (cg == 0) {
+                        max1 = tmp1;
+                        l1 = 1u;
+                        if (ch2) {
+                            max2 = tmp2;
+                            l2 = 1u;
+                        }
+                    } else {
+                        if (max1 < tmp1) {
+                            max1 = tmp1;
+                            l1 = 1u << cg;
+                        } else if (max1 == tmp1)
+                            l1 |= 1u << cg;
+                        if (ch2) {
+                            if (max2 < tmp2) {
+                                max2 = tmp2;
+                                l2 = 1u << cg;
+                            } else if (max2 == tmp2)
+                                l2 |= 1u << cg;
+                        }
+                    }
+                    mIndex++;
+                }
+                par_ml[pIndex] = ch2 ? max1 + max2 : max1;
+                back[pIndex] = (unsigned char)(l1 | (l2 << 4));
+                pIndex++;
+            }
+            cIndex += G;
+        }
+    }
+}
+
+/* ScsBeerLikelihoodCore.java:278-296 getPatternCategories: arg-max set over the categories of the root's sum-product
+ * partial at the root genotype, as a bit mask per pattern. */
+void so_pattern_categories(int K, int S, const double *root_partials, int root_genotype, unsigned char *out)
+{
+    for (int i = 0; i < S; i++) {
+        double max = -1.7976931348623157e308;
+        unsigned mask = 0;
+        for (int j = 0; j < K; j++) {
+            const double tmp = root_partials[((size_t)j * S + i) * 4 + root_genotype];
+            if (max < tmp) {
+                max = tmp;
+                mask = 1u << j;
+            } else if (max == tmp)
+                mask |= 1u << j;
+        }
+        out[i] = (unsigned char)mask;
+    }
 }
 
 /* ScsBeerLikelihoodCore.java:153-218 */
