@@ -186,6 +186,31 @@ int sieve_get_result_device_ptr(sieve_core_t *h, void **d_result /* sieve_shard_
  * SIEVE_FLAG_LOG_PARTIALS.  which: 0 = partials, 1 = constant-site partials (internal nodes only). */
 int sieve_get_node_partials(sieve_core_t *h, int32_t node, int32_t which, double *out);
 
+/* ---- max-sum pass: maximum-likelihood genotypes and dropout states (variant calling) --------------------------------
+ * Replaces the traceMLGenotypes arm of the reference for ONE fixed state (tree, matrices, leaf parameters), i.e. what
+ * VariantCaller needs after the MCMC: the max-sum twin of the pruning with its arg-max lists
+ * (likelihood/ScsBeerLikelihoodCore.java:2918-3486), the leaves' arg-max dropout component
+ * (rawreadcountsmodel/RawReadCountsModelFiniteMuDM.java:54-77), the ML rate category per pattern
+ * (ScsBeerLikelihoodCore.java:278-296) and the top-down collection of the genotypes every node takes
+ * (likelihood/ScsTreeLikelihood.java:947-1460, MLGenotypesCollection).  A tie list of the reference is a bit mask here
+ * (bit g set <=> genotype / component g is listed).  Resident cores only.  The pass is recomputed by every call of
+ * sieve_ml_trace; any later change of the state invalidates the results (the getters then fail with SIEVE_ERR_STATE). */
+int sieve_ml_trace(sieve_core_t *h);
+/* The common case of ScsTreeLikelihood.collectMLGenotypesAndLogLikelihoods (:2033-2081), for the lowest ML category of
+ * every site: genotypes [node][S] and ado [leaf][S] hold the unique ML genotype / number of dropped alleles, or -1 where
+ * several are tied; category [S]; ambiguous [S]: bit 0 = several ML categories, bit 1 = several ML combinations. */
+int sieve_ml_call(sieve_core_t *h, int8_t *genotypes, int8_t *ado, uint8_t *category, uint8_t *ambiguous);
+/* getPatternCategories: bit mask over the categories per site */
+int sieve_ml_get_categories(sieve_core_t *h, uint8_t *out_S);
+/* Reference layouts, any of the outputs may be NULL: ml_partials [K][S][4] (MLPartials; a leaf: its log partials),
+ * back [K][S][4] one byte per (category, site, parent genotype): low nibble = arg-max list of child 0, high nibble = of
+ * child 1 (MLGenotypesNodes[..][node][..][0|1]); for a leaf the byte is the arg-max list of its dropout components;
+ * collection [K][S] = MLGenotypesCollection of the node. */
+int sieve_ml_get_node(sieve_core_t *h, int32_t node, double *ml_partials, uint8_t *back, uint8_t *collection);
+/* One site, all nodes: back [node][K][4] (bytes as above) and the nodes' sum-product log partials [node][K][4]
+ * (ScsBeerLikelihoodCore.getLogLikelihood :338-349): the inputs of the tie-break :2083-2160, done by the host. */
+int sieve_ml_get_site(sieve_core_t *h, int32_t site, uint8_t *back, double *log_partials);
+
 /* ScsBeerLikelihoodCore.store / unstore (:4053-4065), BeerLikelihoodCore.restore (external) -- index flips only */
 int sieve_store(sieve_core_t *h);
 int sieve_unstore(sieve_core_t *h);

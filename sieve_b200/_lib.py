@@ -72,6 +72,11 @@ SIGNATURES = {
     "sieve_get_site_log_likelihoods": (C.c_int, [_vp, _dp, _dp]),
     "sieve_get_result_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
     "sieve_get_node_partials": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp]),
+    "sieve_ml_trace": (C.c_int, [_vp]),
+    "sieve_ml_call": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "sieve_ml_get_categories": (C.c_int, [_vp, _vp]),
+    "sieve_ml_get_node": (C.c_int, [_vp, C.c_int32, _dp, _vp, _vp]),
+    "sieve_ml_get_site": (C.c_int, [_vp, C.c_int32, _vp, _dp]),
     "sieve_store": (C.c_int, [_vp]),
     "sieve_unstore": (C.c_int, [_vp]),
     "sieve_restore": (C.c_int, [_vp]),

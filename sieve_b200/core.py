@@ -185,6 +185,41 @@ class ScsCudaLikelihoodCore:
         check(self.L.sieve_get_node_partials(self.h, int(node), int(bool(const)), _dptr(out)))
         return out
 
+    # ---- max-sum pass (variant calling) --------------------------------------------------------------------
+    def ml_trace(self):
+        """The traceMLGenotypes evaluation of the current state (likelihood/ScsTreeLikelihood.java:700-722, 947-1460)."""
+        check(self.L.sieve_ml_trace(self.h))
+
+    def ml_call(self):
+        """-> (genotypes int8 [node][S], ado int8 [leaf][S], category uint8 [S], ambiguous uint8 [S]); -1 = tied."""
+        g = np.empty((self.n_nodes, self.S), dtype=np.int8)
+        a = np.empty((self.n, self.S), dtype=np.int8)
+        c = np.empty(self.S, dtype=np.uint8)
+        m = np.empty(self.S, dtype=np.uint8)
+        check(self.L.sieve_ml_call(self.h, g.ctypes.data, a.ctypes.data, c.ctypes.data, m.ctypes.data))
+        return g, a, c, m
+
+    def ml_categories(self):
+        """getPatternCategories (likelihood/ScsBeerLikelihoodCore.java:278-296) as a bit mask per site."""
+        out = np.empty(self.S, dtype=np.uint8)
+        check(self.L.sieve_ml_get_categories(self.h, out.ctypes.data))
+        return out
+
+    def ml_node(self, node):
+        """-> (ML partials [K][S][4], back-pointer bytes uint8 [K][S][4], genotype collection uint8 [K][S])."""
+        p = np.empty((self.K, self.S, 4))
+        b = np.empty((self.K, self.S, 4), dtype=np.uint8)
+        c = np.empty((self.K, self.S), dtype=np.uint8)
+        check(self.L.sieve_ml_get_node(self.h, int(node), _dptr(p), b.ctypes.data, c.ctypes.data))
+        return p, b, c
+
+    def ml_site(self, site):
+        """-> (back-pointer bytes uint8 [node][K][4], sum-product log partials [node][K][4]) of one site."""
+        b = np.empty((self.n_nodes, self.K, 4), dtype=np.uint8)
+        p = np.empty((self.n_nodes, self.K, 4))
+        check(self.L.sieve_ml_get_site(self.h, int(site), b.ctypes.data, _dptr(p)))
+        return b, p
+
     def store(self):
         check(self.L.sieve_store(self.h))
 

@@ -181,4 +181,4 @@ def synthetic(n_cells, n_sites, seed=20260101, theta=0.3, t=50.0, v=50.0, eps=0.
         rest -= probs[..., i]
     counts[..., 3] = cov
     params = dict(theta=theta, t=t, v=v, eps=eps, w1=w1, w2=w2, gamma_shape=gamma_shape, K=K)
-    return dict(counts=counts, tree=tree, size_factors_true=sf, params=params)
+    return dict(counts=counts, tree=tree, size_factors_true=sf, params=params, genotypes=geno, dropout=ado)

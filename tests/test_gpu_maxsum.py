@@ -1,0 +1,186 @@
+"""Parity of the device's max-sum pass (variant calling) with the oracle of oracle/ml_genotypes.py.
+
+Floating point: ML partials within 1e-12 relative.  Arg-max lists (bit masks) must be identical wherever the oracle's
+margin between the best and the runner-up is not a rounding-level near-tie: the reference decides ties by exact
+equality of doubles, so a last-bit difference in a leaf likelihood may legitimately flip a tie between two candidates
+that agree to 1e-13; such entries are counted and must stay a tiny fraction."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from sieve_b200 import substmodel, variants  # noqa: E402
+from sieve_b200.data import synthetic  # noqa: E402
+
+PARAMS = (0.3, 50.0, 50.0, 0.008, 150.0, 2.0)
+
+
+@pytest.fixture(scope="module")
+def core_mod():
+    from sieve_b200 import _lib, core
+    assert _lib.lib().sieve_device_count() > 0, "no CUDA device: the product path has no CPU fallback"
+    return core
+
+
+def _case(core_mod, oracle, n, S, seed, single=True, K=4, asc=True):
+    from oracle import ml_genotypes as mlo
+    d = synthetic(n, S, seed=seed)
+    counts, tree = d["counts"], d["tree"]
+    c5 = oracle.counts5(counts)
+    sf, _ = oracle.size_factors(c5)
+    rates, props = substmodel.gamma_category_rates(0.8, K)
+    mats = substmodel.node_matrices(tree, rates)
+    c = core_mod.ScsCudaLikelihoodCore(n, S, K, 4, True, asc, single)
+    c.set_counts(counts)
+    c.set_size_factors(sf)
+    c.set_leaf_params(*PARAMS)
+    c.update_leaves(for_update=False)
+    c.set_root(tree.root, props, 0)
+    nodes = [i for i in range(tree.node_count) if i != tree.root]
+    c.set_matrices(nodes, mats[nodes][:, :K], for_update=False)
+    c.update_nodes(tree.ops(), flip=False)
+    c.evaluate()
+    P = oracle.leaf_params(*PARAMS, single_ado=single)
+    tr = mlo.ml_trace(c5, sf, P, tree.ops(), mats[:, :K], 0)
+    return c, tree, tr
+
+
+def _margin_ok(values, mask_a, mask_b, rtol=1e-11):
+    """two arg-max sets over `values` differ only by candidates that are within rtol of the maximum"""
+    diff = int(mask_a) ^ int(mask_b)
+    mx = np.max(values)
+    return all(abs(values[i] - mx) <= rtol * max(1.0, abs(mx)) for i in range(len(values)) if (diff >> i) & 1)
+
+
+@pytest.mark.parametrize("single", [True, False])
+def test_leaf_log_partials_and_dropout_argmax(core_mod, oracle, single):
+    c, tree, tr = _case(core_mod, oracle, 12, 400, 21, single=single)
+    c.ml_trace()
+    flips = 0
+    for leaf in range(tree.n):
+        p, b, _ = c.ml_node(leaf)
+        for k in range(c.K):
+            np.testing.assert_allclose(p[k], tr["leaf"][leaf], rtol=1e-12, atol=1e-12)
+            flips += int((b[k] != tr["ado"][leaf]).sum())
+    assert flips == 0  # the dropout components of a leaf differ by whole units of log-likelihood, not by rounding
+    c.close()
+
+
+@pytest.mark.parametrize("single,K", [(True, 4), (False, 4), (True, 2)])
+def test_max_sum_partials_and_back_pointers(core_mod, oracle, single, K):
+    n, S = 17, 300
+    c, tree, tr = _case(core_mod, oracle, n, S, 33, single=single, K=K)
+    c.ml_trace()
+    total = near = 0
+    for node in range(n, 2 * n):
+        p, b, _ = c.ml_node(node)
+        ref, rb = tr["ml"][node], tr["back"][node]
+        assert np.all(np.abs(p - ref) <= 1e-12 * np.abs(ref)), node
+        total += b.size
+        bad = np.argwhere(b != rb)
+        for k, s, g in bad:
+            near += 1
+            # re-derive the candidates of this entry from the oracle's inputs and check that the flip is a near-tie
+            left, right = int(tree.left[node]), int(tree.right[node])
+            for side, child in ((0, left), (1, right)):
+                if child < 0:
+                    continue
+                vals = tr["leaf"][child][s] if child < n else tr["ml"][child][k, s]
+                m = np.asarray(substmodel.node_matrices(tree, substmodel.gamma_category_rates(0.8, K)[0])[child, k])
+                cand = np.log(np.where(m > 0, m, 4.9e-324)).reshape(4, 4)[g] + vals
+                assert _margin_ok(cand, (b[k, s, g] >> (4 * side)) & 15, (rb[k, s, g] >> (4 * side)) & 15)
+    assert near <= 1e-3 * total, (near, total)
+    # ML category per site (getPatternCategories)
+    cats = c.ml_categories()
+    mism = np.nonzero(cats != tr["categories"])[0]
+    for s in mism:
+        v = tr["partials"][tr["root"]][:, s, 0]
+        assert _margin_ok(v, cats[s], tr["categories"][s])
+    assert len(mism) <= 2
+    c.close()
+
+
+def test_collections_and_calls_match_enumeration(core_mod, oracle):
+    from oracle import ml_genotypes as mlo
+    n, S = 9, 250
+    c, tree, tr = _case(core_mod, oracle, n, S, 44)
+    calls = variants.call_variants(c, tree)
+    ops = tree.ops()
+    checked = 0
+    for s in range(S):
+        want = mlo.call_pattern(ops, n, tr, s, 0)
+        if s in calls.tied:
+            got = sorted(calls.tied[s])
+            assert got == sorted(want)
+        else:
+            assert len(want) == 1, (s, want)
+            k, comb = want[0]
+            assert calls.category[s] == k
+            assert list(calls.genotypes[:, s]) == list(comb[n:])
+            assert list(calls.ado[:, s]) == list(comb[:n])
+            checked += 1
+    assert checked > 0.9 * S
+    # the collection of a node = the set of genotypes it takes over all combinations of that (category, site)
+    node = n + 3
+    _, _, coll = c.ml_node(node)
+    for s in range(0, S, 17):
+        for k in range(4):
+            back_at = {v: tr["back"][v][k, s] for v in tr["back"]}
+            combos = mlo.enumerate_ml_genotypes(ops, n, back_at, tr["ado"][:, s, :], 0)
+            want = 0
+            for comb in combos:
+                want |= 1 << comb[n + node]
+            assert coll[k, s] == want
+    c.close()
+
+
+def test_trace_is_invalidated_by_changes_and_needs_resident_core(core_mod, oracle):
+    c, tree, tr = _case(core_mod, oracle, 6, 64, 5)
+    with pytest.raises(RuntimeError):
+        c.ml_categories()  # no trace yet
+    c.ml_trace()
+    c.ml_categories()
+    c.set_leaf_params(0.2, 50.0, 50.0, 0.008, 150.0, 2.0)
+    c.update_leaves(for_update=True)
+    with pytest.raises(RuntimeError):
+        c.ml_call()
+    c.update_nodes(tree.ops(), flip=True)
+    c.evaluate()
+    c.ml_trace()
+    g1, a1, k1, m1 = c.ml_call()
+    c.ml_trace()  # idempotent
+    g2, a2, k2, m2 = c.ml_call()
+    assert np.array_equal(g1, g2) and np.array_equal(a1, a2) and np.array_equal(k1, k2) and np.array_equal(m1, m2)
+    c.close()
+    e = core_mod.ScsCudaLikelihoodCore(6, 64, 4, 4, True, False, True, ephemeral=True)
+    with pytest.raises(RuntimeError):
+        e.ml_trace()
+    e.close()
+
+
+def test_called_genotypes_recover_simulated_truth(core_mod, oracle):
+    """Sanity on the model level: with 50x coverage the ML leaf genotypes are mostly the simulated ones."""
+    n, S = 20, 2000
+    d = synthetic(n, S, seed=77)
+    if "genotypes" not in d:
+        pytest.skip("generator does not expose the simulated genotypes")
+    counts, tree = d["counts"], d["tree"]
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, False, True)
+    c.set_counts(counts)
+    c.set_size_factors(sf)
+    c.set_leaf_params(*PARAMS)
+    c.update_leaves(for_update=False)
+    c.set_root(tree.root, props, 0)
+    nodes = [i for i in range(tree.node_count) if i != tree.root]
+    c.set_matrices(nodes, mats[nodes], for_update=False)
+    c.update_nodes(tree.ops(), flip=False)
+    c.evaluate()
+    calls = variants.call_variants(c, tree)
+    truth = np.asarray(d["genotypes"])[:n]  # [leaf][S]
+    covered = counts[:, :, 3].T > 10
+    agree = (calls.genotypes[:n] == truth)[covered].mean()
+    assert agree > 0.9, agree
+    c.close()
