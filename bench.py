@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--per-level", action="store_true", help="issue the pruning as one launch per tree level")
     ap.add_argument("--mcmc-states", type=int, default=400, help="proposals per operator mix in the MCMC replay (0 = skip)")
     ap.add_argument("--streamed", action="store_true", help="SIEVE_FLAG_EPHEMERAL: no resident partials (shapes that exceed HBM, e.g. SIEVE_BENCH_CELLS=10000 SIEVE_BENCH_SITES=125000)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the max-sum (variant calling) timing")
     ap.add_argument("--matrices", action="store_true", help="hand the core 16-double matrices (generic kernel) instead of branch distances")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -504,6 +505,22 @@ def main():
                          "ms_by_op": {k: 1000.0 * v["seconds"] / v["proposed"] for k, v in st["by_op"].items()}}
             mc.close()
 
+    # ---------------- variant calling: the max-sum pass on the final state (one-off per analysis) ----------------
+    variant_calling = None
+    if not args.streamed and not args.no_variants:
+        core.ml_trace()                     # first call allocates the pools
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        core.ml_trace()
+        t_trace = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        g_ml, a_ml, cat_ml, amb_ml = core.ml_call()
+        t_call = time.perf_counter() - t0
+        variant_calling = {"ml_trace_ms": 1000.0 * t_trace, "ml_call_ms_incl_d2h": 1000.0 * t_call,
+                           "sites": int(S), "tied_sites": int((amb_ml != 0).sum()),
+                           "non_reference_leaf_calls": int((g_ml[:n] > 0).sum()),
+                           "leaf_dropout_calls": int((a_ml > 0).sum())}
+
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if rank == 0:
@@ -551,6 +568,7 @@ def main():
                         "tree_only_evals_per_s": 1000.0 / tree_only_ms},
             "mcmc": mcmc,
             "mcmc_states_per_s": mcmc.get("stage1", {}).get("states_per_s"),
+            "variant_calling": variant_calling,
             "device_bytes": core.device_bytes(),
             "parity": parity,
             "cpu_baseline": cpu,

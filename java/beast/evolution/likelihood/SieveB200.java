@@ -30,6 +30,10 @@ public final class SieveB200 {
     public static native void setNodeMatrix(long h, int node, int category, double[] p16);
     /** fast path for the fixed rate matrix: distances[i * K + k] = branch length * branch rate * site rate_k of nodes[i] */
     public static native void setDistances(long h, int[] nodes, double[] distances, boolean forUpdate);
+    /** max-sum pass on the current state (variant calling); see include/sieve_b200.h "max-sum pass" */
+    public static native void mlTrace(long h);
+    public static native void mlCall(long h, byte[] genotypes, byte[] ado, byte[] category, byte[] ambiguous);
+    public static native void mlGetSite(long h, int site, byte[] back, double[] logPartials);
     public static native void setNodePartialsForUpdate(long h, int node);
     public static native void calculatePartials(long h, int child1, boolean isLeaf1, int child2, boolean isLeaf2,
                                                 int parent, int constGenotype);

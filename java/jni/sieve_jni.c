@@ -71,6 +71,25 @@ JNIEXPORT void JNICALL FN(setDistances)(JNIEnv *e, jclass c, jlong h, jintArray 
     (*e)->ReleasePrimitiveArrayCritical(e, nodes, pn, JNI_ABORT);
     chk(e, rc);
 }
+JNIEXPORT void JNICALL FN(mlTrace)(JNIEnv *e, jclass c, jlong h) { chk(e, sieve_ml_trace(H(h))); }
+JNIEXPORT void JNICALL FN(mlCall)(JNIEnv *e, jclass c, jlong h, jbyteArray g, jbyteArray a, jbyteArray k, jbyteArray m) {
+    jbyte *pg = (*e)->GetPrimitiveArrayCritical(e, g, NULL), *pa = (*e)->GetPrimitiveArrayCritical(e, a, NULL);
+    jbyte *pk = (*e)->GetPrimitiveArrayCritical(e, k, NULL), *pm = (*e)->GetPrimitiveArrayCritical(e, m, NULL);
+    int rc = sieve_ml_call(H(h), (int8_t *)pg, (int8_t *)pa, (uint8_t *)pk, (uint8_t *)pm);
+    (*e)->ReleasePrimitiveArrayCritical(e, m, pm, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, k, pk, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, a, pa, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, g, pg, 0);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(mlGetSite)(JNIEnv *e, jclass c, jlong h, jint site, jbyteArray b, jdoubleArray p) {
+    jbyte *pb = (*e)->GetPrimitiveArrayCritical(e, b, NULL);
+    jdouble *pp = (*e)->GetPrimitiveArrayCritical(e, p, NULL);
+    int rc = sieve_ml_get_site(H(h), site, (uint8_t *)pb, pp);
+    (*e)->ReleasePrimitiveArrayCritical(e, p, pp, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, b, pb, 0);
+    chk(e, rc);
+}
 JNIEXPORT void JNICALL FN(setNodePartialsForUpdate)(JNIEnv *e, jclass c, jlong h, jint n) {
     chk(e, sieve_set_node_partials_for_update(H(h), n));
 }

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "leaf.cuh"
 #include "prune.cuh"
+#include "prune_pipe.cuh"
 #include "reduce.cuh"
 #include "maxsum.cuh"
 #include "sizefactors.cuh"
@@ -106,6 +107,7 @@ struct sieve_core {
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
     bool force_generic = false;
+    bool use_pipe = false, pipe_attr_set = false;  // SIEVE_B200_PIPE=1: the cp.async-pipelined Q walk (measured slower, see prune_pipe.cuh)
     // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
     int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
     int n_slots = 0;     // scratch slots for internal partials
@@ -223,6 +225,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->log_mode = cfg->flags & SIEVE_FLAG_LOG_PARTIALS;
     h->with_const = cfg->flags & SIEVE_FLAG_CONST_PARTIALS;
     if (const char* e = getenv("SIEVE_B200_CONST_TWIN")) h->const_twin = atoi(e) != 0;
+    if (const char* e = getenv("SIEVE_B200_PIPE")) h->use_pipe = atoi(e) != 0;
     const bool twin = h->with_const && h->const_twin;
     const bool algebraic = h->with_const && !h->const_twin;
     h->single_ado = cfg->flags & SIEVE_FLAG_SINGLE_ADO;
@@ -1311,8 +1314,17 @@ static int sv_launch_staged(sieve_core* h) {
         const bool qfast = h->last_qfast && a.const_genotype == 0 && a.root_genotype == 0 && !h->force_generic;
         const int spb = sv_prune_sites(h->with_const && h->const_twin, qfast);
         const unsigned gx = (unsigned)((h->S + spb - 1) / spb);
+        // the software-pipelined walk (prune_pipe.cuh): Q-specialised, variant partials only, one launch for many ops
+        const bool pipe = qfast && !(h->with_const && h->const_twin) && h->use_pipe && !h->last_per_level;
+        if (pipe && !h->pipe_attr_set) {
+            SV_CUDA(cudaFuncSetAttribute(k_prune_pipe<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+            h->pipe_attr_set = true;
+        }
         auto launch = [&](dim3 grid) {
-            if (qfast)
+            if (pipe)
+                k_prune_pipe<true><<<grid, SV_PRUNE_THREADS, SV_PIPE_SMEM, h->stream>>>(a);
+            else if (qfast)
                 sv_launch_prune_t<true>(h, grid, a);
             else
                 sv_launch_prune_t<false>(h, grid, a);

@@ -618,6 +618,42 @@ def test_transient_nodes_do_not_change_results(core_mod, oracle, monkeypatch):
             np.testing.assert_array_equal(a, b)
 
 
+def test_pipelined_walk_is_bit_identical(core_mod, oracle, monkeypatch):
+    """SIEVE_B200_PIPE=1 takes the cp.async-pipelined walk (prune_pipe.cuh, opt-in: measured slower): same op list, same
+    arithmetic, so every number must be identical -- resident with proposals / rejections, and streamed with ragged chunks."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    d = synthetic(41, 333, seed=83)
+    counts, tree = d["counts"], d["tree"]
+    runs = {}
+    for P in ("0", "1"):
+        monkeypatch.setenv("SIEVE_B200_PIPE", P)
+        out = []
+        for eph in (False, True):
+            if eph:
+                monkeypatch.setenv("SIEVE_B200_CHUNK_SITES", "100")
+            tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=4000.0,
+                                   ephemeral=eph)
+            out.append(tl.calculate_logp())
+            rng = np.random.default_rng(9)
+            for it in range(6):
+                t2 = tl.tree.copy()
+                node = int(rng.integers(tree.n, tree.node_count - 1))
+                lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+                t2.height[node] = lo + (t2.height[t2.parent[node]] - lo) * rng.random()
+                tl.store()
+                tl.set_tree(t2, [node])
+                out.append(tl.calculate_logp())
+                if it % 2 == 1:
+                    tl.restore()
+                    out.append(tl.calculate_logp())
+            out.append(tl.pattern_log_likelihoods()[0].copy())
+            tl.close()
+            monkeypatch.delenv("SIEVE_B200_CHUNK_SITES", raising=False)
+        runs[P] = out
+    for a, b in zip(runs["0"], runs["1"]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_algebraic_constant_site_path_equals_per_site_twin(core_mod, oracle, monkeypatch):
     """The constant-site partials factorise into (a site-independent 4-vector per node and category) x (product over the
     leaves below of their constant-genotype likelihood); the default path uses that.  SIEVE_B200_CONST_TWIN=1 prunes them

@@ -144,3 +144,23 @@ def test_enumeration_is_consistent_with_update_function():
                 gs = sorted({c[n + node] for c in combos})
                 mlo.update_max_likelihood_genotypes(combos, children, node, gs, n, 2 * n)
         assert sorted(map(tuple, combos)) == before
+
+
+def test_host_enumerator_of_the_product_matches_the_oracle():
+    """sieve_b200/variants.py (product code, host half of the tie-break) against the oracle's enumeration, on
+    back-pointers with forced ties -- no device involved."""
+    from sieve_b200 import variants
+    n, S = 6, 10
+    tree, c5, sf, params, mats, ops = _small_case(n, S, 13)
+    tr = mlo.ml_trace(c5, sf, params, ops, mats, 0)
+    children = {int(p): (int(c1), int(c2)) for p, c1, c2 in ops}
+    for s in range(S):
+        back = np.zeros((2 * n, 4), dtype=np.uint8)
+        for node in range(n, 2 * n):
+            b = tr["back"][node][1, s]
+            back[node] = [x | (0x21 if x >> 4 else 0x01) for x in b]
+        back[:n] = tr["ado"][:, s, :] | 1
+        back_at = {node: back[node] for node in range(n, 2 * n)}
+        want = mlo.enumerate_ml_genotypes(ops, n, back_at, back[:n], 0)
+        got = variants.enumerate_combinations(children, tree.root, n, back, 0)
+        assert got == want and len(got) >= 1
