@@ -489,7 +489,11 @@ def main():
         from sieve_b200.mcmc import McmcReplay
         if world > 1:
             bind_native_comm(core)      # the chain's per-state exchange is then a native NCCL all-gather inside sieve_step
-        for mix in ("stage1", "stage2", "relaxed2"):
+        # relaxed2 twice: the product default (change tracking: a branch-rate proposal, for which the reference dirties
+        # the whole tree, recomputes only the path with new inputs -- same bits) and with every dirty node recomputed
+        for mix, elide in (("stage1", True), ("stage2", True), ("relaxed2", True), ("relaxed2", False)):
+            core.set_elision(elide)
+            key = mix if elide else mix + "_every_dirty_node_recomputed"
             mc = McmcReplay(core, tree, mix=mix, asc_mode="felsenstein_mean", n_background_sites=N_BACKGROUND,
                             gamma_shape=1.0, leaf=PARAMS, branch_rates=br, seed=SEED)
             mc.run(20)                      # warm-up
@@ -497,13 +501,14 @@ def main():
             st = mc.run(args.mcmc_states, reset=True)
             barrier()
             check = mc.full_recompute() if world == 1 else None
-            mcmc[mix] = {"states_per_s": st["states"] / st["seconds"], "states": st["states"],
+            mcmc[key] = {"states_per_s": st["states"] / st["seconds"], "states": st["states"],
                          "acceptance": st["accepted"] / st["states"],
                          "mean_nodes_recomputed": st["ops_total"] / max(1, st["likelihood_evaluations"]),
                          "leaf_updates": st["leaf_updates"],
                          "incremental_vs_full_recompute_rel": (abs(check - st["log_p"]) / abs(check)) if check else None,
                          "ms_by_op": {k: 1000.0 * v["seconds"] / v["proposed"] for k, v in st["by_op"].items()}}
             mc.close()
+        core.set_elision(True)
 
     # ---------------- variant calling: the max-sum pass on the final state (one-off per analysis) ----------------
     variant_calling = None

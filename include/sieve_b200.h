@@ -186,6 +186,15 @@ int sieve_get_result_device_ptr(sieve_core_t *h, void **d_result /* sieve_shard_
  * SIEVE_FLAG_LOG_PARTIALS.  which: 0 = partials, 1 = constant-site partials (internal nodes only). */
 int sieve_get_node_partials(sieve_core_t *h, int32_t node, int32_t which, double *out);
 
+/* Change tracking (resident cores).  The core versions every input (matrix slot contents, leaf buffers, node values); a
+ * node the caller marks dirty whose inputs are the very ones a value it still holds was computed from is not recomputed
+ * -- the kernels are deterministic, the bits would be the same.  This matters for callers that dirty more than changed:
+ * SIEVE recomputes the whole tree for every branch-rate proposal under a relaxed clock with Felsenstein's correction
+ * (likelihood/ScsTreeLikelihood.java:2814-2821, alignment/ScsAlignment.java:707-709); here the walk then covers only the
+ * path from the changed branch to the root.  On by default; `on = 0` makes every dirty node recompute (A/B, tests). */
+int sieve_set_elision(sieve_core_t *h, int32_t on);
+int sieve_elided_count(sieve_core_t *h, uint64_t *out); /* dirty nodes not recomputed so far */
+
 /* ---- max-sum pass: maximum-likelihood genotypes and dropout states (variant calling) --------------------------------
  * Replaces the traceMLGenotypes arm of the reference for ONE fixed state (tree, matrices, leaf parameters), i.e. what
  * VariantCaller needs after the MCMC: the max-sum twin of the pruning with its arg-max lists

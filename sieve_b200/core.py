@@ -185,6 +185,15 @@ class ScsCudaLikelihoodCore:
         check(self.L.sieve_get_node_partials(self.h, int(node), int(bool(const)), _dptr(out)))
         return out
 
+    def set_elision(self, on=True):
+        """Skip dirty nodes whose inputs did not change (see include/sieve_b200.h, "Change tracking")."""
+        check(self.L.sieve_set_elision(self.h, 1 if on else 0))
+
+    def elided_count(self):
+        v = C.c_uint64()
+        check(self.L.sieve_elided_count(self.h, C.byref(v)))
+        return int(v.value)
+
     # ---- max-sum pass (variant calling) --------------------------------------------------------------------
     def ml_trace(self):
         """The traceMLGenotypes evaluation of the current state (likelihood/ScsTreeLikelihood.java:700-722, 947-1460)."""

@@ -41,6 +41,7 @@ static int sv_fail(int code, const std::string& msg) {
 
 struct PendingMatrix {
     int slot;
+    int reuse = 0;    // host mirror of the matrix: 0 = compute, 1 = the slot already holds these values, 2 = copy the twin slot's
     int is_distance;  // v[0..K) are branch distances (length * branch rate * category rate) instead of K matrices
     double v[SV_KMAX * 16];
 };
@@ -128,6 +129,32 @@ struct sieve_core {
     int comm_rank = 0, comm_world = 1;
     double* d_gather = nullptr;   // [world][5]
     double* h_gather = nullptr;   // pinned
+
+    // Change tracking (resident planner): every matrix slot, leaf buffer and node value carries a version number, and a
+    // node remembers the versions of the inputs its value was computed from.  A node that the caller marks dirty but
+    // whose inputs are the ones its value in the stored state was computed from is NOT recomputed: the kernels are
+    // deterministic, so the result would be the same bits (SIEVE forces whole-tree recomputation for every branch-rate
+    // proposal under a relaxed clock with bias correction, ScsTreeLikelihood.java:2814-2821 -- here only the path from
+    // the changed branch to the root is walked).  sieve_set_elision(h, 0) switches the short-cut off.
+    struct SvFp {
+        int c1 = -9, c2 = -9;
+        uint64_t p1 = 0, p2 = 0, m1 = 0, m2 = 0;
+        bool operator==(const SvFp& o) const {
+            return c1 == o.c1 && c2 == o.c2 && p1 == o.p1 && p2 == o.p2 && m1 == o.m1 && m2 == o.m2;
+        }
+    };
+    bool elide = true;
+    uint64_t ver_counter = 0, elided_total = 0;
+    std::vector<uint64_t> mat_ver;      // [2 * n_nodes] per matrix slot
+    std::vector<double> mat_mirror;     // [2 * n_nodes][SV_KMAX * 16] what the slot was last given (matrix or K distances)
+    std::vector<char> mat_mirror_q;     // ... and in which form
+    uint64_t leaf_ver[2] = {0, 0};
+    std::vector<uint64_t> g_ver;        // [2 * n_nodes] version of the node value whose constant-site factor G sits in that slot
+    std::vector<char> buf_has;          // [2 * n_nodes] the partial buffer holds a value ...
+    std::vector<uint64_t> buf_ver;      // ... of this version ...
+    std::vector<SvFp> buf_fp;           // ... computed from these inputs
+    std::vector<uint64_t> ver_cur, ver_stored;  // [n_nodes] version of the node's value in the current / stored state
+    std::vector<SvFp> fp_cur, fp_stored;        // ... and what it was computed from
 
     // max-sum pass for variant calling (maxsum.cuh); its pools are allocated by the first sieve_ml_trace
     bool ml_alloc = false, ml_ready = false;
@@ -317,6 +344,18 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     if (algebraic) h->hP.assign((size_t)2 * h->n_nodes * SV_KMAX * 16, 0.0);
     CR(sv_alloc(h, &h->d_mats, (size_t)2 * h->n_nodes * SV_KMAX * 16));
     CR(sv_alloc(h, &h->d_qfac, (size_t)2 * h->n_nodes * SV_KMAX));
+    h->mat_ver.assign((size_t)2 * h->n_nodes, 0);
+    h->mat_mirror.assign((size_t)2 * h->n_nodes * SV_KMAX * 16, 0.0);
+    h->mat_mirror_q.assign((size_t)2 * h->n_nodes, 0);
+    h->g_ver.assign((size_t)2 * h->n_nodes, 0);
+    h->buf_has.assign((size_t)2 * h->n_nodes, 0);
+    h->buf_ver.assign((size_t)2 * h->n_nodes, 0);
+    h->buf_fp.assign((size_t)2 * h->n_nodes, sieve_core::SvFp());
+    h->ver_cur.assign(h->n_nodes, 0);
+    h->ver_stored.assign(h->n_nodes, 0);
+    h->fp_cur.assign(h->n_nodes, sieve_core::SvFp());
+    h->fp_stored.assign(h->n_nodes, sieve_core::SvFp());
+    if (const char* e = getenv("SIEVE_B200_ELIDE")) h->elide = atoi(e) != 0;
     h->slot_is_q.assign((size_t)2 * h->n_nodes, 0);
     h->slot_zero.assign((size_t)2 * h->n_nodes, 0);
     CR(sv_alloc(h, &h->d_site_logl, S));
@@ -688,6 +727,8 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
     }
     if (for_update) h->cur_leaf = 1 - h->cur_leaf;
     h->ml_ready = false;
+    h->leaf_ver[h->cur_leaf] = ++h->ver_counter;
+    if (!for_update) h->leaf_ver[1 - h->cur_leaf] = h->leaf_ver[h->cur_leaf];
     if (h->timing) {
         SV_CUDA(cudaEventRecord(h->ev[0], h->stream));
     }
@@ -922,6 +963,7 @@ static void sv_update_G(sieve_core* h) {
             gs += std::log(mx);
         }
         h->Gs[(size_t)h->cur_part[v] * N + v] = gs;
+        h->g_ver[(size_t)h->cur_part[v] * N + v] = h->ver_cur[v];
     }
     h->g_nodes.clear();
     const int root = h->root;
@@ -972,6 +1014,76 @@ static int sv_plan_resident_ops(sieve_core* h) {
                     const long long la = a < n ? 1 : leaves[a], lb = b < 0 ? 0 : (b < n ? 1 : leaves[b]);
                     leaves[v] = (int)std::min<long long>(la + lb, 1 << 28);
                 }
+            }
+        }
+    }
+    // ---- change tracking: which of the dirty nodes really get a new value? (children before parents) ----
+    {
+        std::vector<char> done(N, 0);
+        std::vector<std::pair<int, int>> st;
+        auto pver = [&](int c) -> uint64_t { return c < 0 ? 0 : (c < n ? h->leaf_ver[h->cur_leaf] : h->ver_cur[c]); };
+        auto mver = [&](int c) -> uint64_t { return c < 0 ? 0 : h->mat_ver[(size_t)h->cur_mat[c] * N + c]; };
+        for (int top : h->dirty_list) {
+            if (done[top]) continue;
+            st.push_back({top, 0});
+            while (!st.empty()) {
+                auto [v, state] = st.back();
+                st.pop_back();
+                if (v < n || !dirty[v] || done[v]) continue;
+                const int a = h->eph_c1[v], b = h->eph_c2[v];
+                if (a == -2) {
+                    done[v] = 1;
+                    continue;  // reported by the walk below
+                }
+                if (state == 0) {
+                    st.push_back({v, 1});
+                    if (b >= n) st.push_back({b, 0});
+                    if (a >= n) st.push_back({a, 0});
+                    continue;
+                }
+                done[v] = 1;
+                sieve_core::SvFp f;
+                f.c1 = a;
+                f.c2 = b;
+                f.p1 = pver(a);
+                f.p2 = pver(b);
+                f.m1 = mver(a);
+                f.m2 = mver(b);
+                const bool known = f.p1 != 0 && f.m1 != 0 && (b < 0 || (f.p2 != 0 && f.m2 != 0));
+                if (h->elide && known && v != root) {
+                    // 1. one of the node's two buffers holds the value of exactly these inputs
+                    int hit = -1;
+                    for (int t = 0; t < 2 && hit < 0; t++) {
+                        const int bsel = t == 0 ? h->cur_part[v] : 1 - h->cur_part[v];
+                        const size_t bi = (size_t)bsel * N + v;
+                        if (h->buf_has[bi] && h->buf_fp[bi] == f) hit = bsel;
+                    }
+                    if (hit >= 0) {
+                        h->cur_part[v] = hit;
+                        h->valid[v] = 1;
+                        h->ver_cur[v] = h->buf_ver[(size_t)hit * N + v];
+                        h->fp_cur[v] = f;
+                        dirty[v] = 0;
+                        h->elided_total++;
+                        if (!h->G.empty() && h->g_ver[(size_t)h->cur_part[v] * N + v] != h->ver_cur[v]) h->g_nodes.push_back(v);
+                        continue;
+                    }
+                    // 2. it is the stored state's value, which was consumed from registers and never written: the node
+                    //    is clean but not in memory (recomputed from its small subtree if a dirty parent needs it)
+                    if (h->ver_stored[v] != 0 && h->fp_stored[v] == f) {
+                        h->cur_part[v] = h->stored_part[v];
+                        h->valid[v] = 0;
+                        h->ver_cur[v] = h->ver_stored[v];
+                        h->fp_cur[v] = f;
+                        dirty[v] = 0;
+                        h->elided_total++;
+                        if (!h->G.empty() && h->g_ver[(size_t)h->cur_part[v] * N + v] != h->ver_cur[v]) h->g_nodes.push_back(v);
+                        continue;
+                    }
+                }
+                h->ver_cur[v] = ++h->ver_counter;
+                h->fp_cur[v] = known ? f : sieve_core::SvFp();
+                h->g_nodes.push_back(v);  // children first: this pass is a post-order over the dirty nodes
             }
         }
     }
@@ -1044,7 +1156,7 @@ static int sv_plan_resident_ops(sieve_core* h) {
     }
     // a dirty node whose parent was dirty but never reached it (inconsistent input) would be skipped: check
     for (int v : h->dirty_list)
-        if (!visited[v]) SV_TRY(run_from(v));
+        if (dirty[v] && !visited[v]) SV_TRY(run_from(v));
     // store decisions
     const size_t base = h->pending_ops.size() - emitted.size();
     for (size_t i = 0; i < emitted.size(); i++) {
@@ -1059,12 +1171,16 @@ static int sv_plan_resident_ops(sieve_core* h) {
         SvOp& op = h->pending_ops[base + i];
         if (!store) op.flags |= SV_OP_NOSTORE;
         h->valid[v] = store ? 1 : 0;
+        if (store) {
+            const size_t bi = (size_t)h->cur_part[v] * N + v;
+            h->buf_has[bi] = 1;
+            h->buf_ver[bi] = h->ver_cur[v];
+            h->buf_fp[bi] = h->fp_cur[v];
+        }
         // a clean subtree is identical in the stored state; its buffer is shared when the indices agree
         if (store && !dirty[v] && h->cur_part[v] == h->stored_part[v]) h->valid_stored[v] = 1;
     }
-    // the constant-site factor follows the dirty nodes only (a clean subtree keeps its G)
-    for (int v : emitted)
-        if (dirty[v]) h->g_nodes.push_back(v);
+    // (the constant-site factor follows the really dirty nodes only: queued by the change-tracking pass above)
     h->dirty_list.clear();
     h->demand_list.clear();
     return SIEVE_OK;
@@ -1241,6 +1357,14 @@ extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t*
         h->pending_ops.push_back(op);
         h->g_nodes.push_back(ops[3 * i]);
         h->valid[ops[3 * i]] = 1;
+        h->ver_cur[ops[3 * i]] = ++h->ver_counter;  // computed outside the planner: a new value of unknown provenance
+        h->fp_cur[ops[3 * i]] = sieve_core::SvFp();
+        {
+            const size_t bi = (size_t)h->cur_part[ops[3 * i]] * h->n_nodes + ops[3 * i];
+            h->buf_has[bi] = 1;
+            h->buf_ver[bi] = h->ver_cur[ops[3 * i]];
+            h->buf_fp[bi] = sieve_core::SvFp();
+        }
     }
     h->pending_levels.assign(level_offsets, level_offsets + n_levels + 1);
     h->pending_per_level = true;
@@ -1374,6 +1498,19 @@ static int sv_flush(sieve_core* h) {
         if (pm.is_distance)
             for (int k = 0; k < K; k++) z |= pm.v[k] == 0.0;
         h->slot_zero[pm.slot] = z;
+        // content version of the slot: the same values as the slot (or its twin in the other buffer) already holds
+        // keep that version, anything else is new
+        const size_t len = (pm.is_distance ? (size_t)K : (size_t)K * 16) * sizeof(double);
+        const int other = pm.slot < h->n_nodes ? pm.slot + h->n_nodes : pm.slot - h->n_nodes;
+        auto same = [&](int sl) {
+            return h->mat_ver[sl] != 0 && h->mat_mirror_q[sl] == (char)pm.is_distance &&
+                   memcmp(h->mat_mirror.data() + (size_t)sl * SV_KMAX * 16, pm.v, len) == 0;
+        };
+        const_cast<PendingMatrix&>(pm).reuse = same(pm.slot) ? 1 : (same(other) ? 2 : 0);
+        if (pm.reuse == 2) h->mat_ver[pm.slot] = h->mat_ver[other];
+        if (pm.reuse == 0) h->mat_ver[pm.slot] = ++h->ver_counter;
+        h->mat_mirror_q[pm.slot] = (char)pm.is_distance;
+        memcpy(h->mat_mirror.data() + (size_t)pm.slot * SV_KMAX * 16, pm.v, len);
     }
     if (h->ephemeral)
         SV_TRY(sv_build_streamed_ops(h));
@@ -1427,7 +1564,15 @@ static int sv_flush(sieve_core* h) {
     // the site-independent constant-site factor is host arithmetic; done here it overlaps the kernels just launched
     // (only the reduce kernel, launched later, needs its result log C_tree)
     if (!h->hP.empty())
-        for (const PendingMatrix& pm : h->pending_mats) sv_host_matrix(h, pm);
+        for (const PendingMatrix& pm : h->pending_mats) {
+            if (pm.reuse == 1) continue;
+            if (pm.reuse == 2) {
+                const int other = pm.slot < h->n_nodes ? pm.slot + h->n_nodes : pm.slot - h->n_nodes;
+                memcpy(h->hP.data() + (size_t)pm.slot * SV_KMAX * 16, h->hP.data() + (size_t)other * SV_KMAX * 16,
+                       sizeof(double) * SV_KMAX * 16);
+            } else
+                sv_host_matrix(h, pm);
+        }
     if (!h->G.empty() && !h->g_nodes.empty()) sv_update_G(h);
     h->g_nodes.clear();
     if (!h->pending_ops.empty() || !h->pending_mats.empty()) h->ml_ready = false;
@@ -1925,6 +2070,8 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->eph_c2_stored = h->eph_c2;
     h->valid_stored = h->valid;
     h->log_c_stored = h->log_c;
+    h->ver_stored = h->ver_cur;
+    h->fp_stored = h->fp_cur;
     return SIEVE_OK;
 }
 extern "C" int sieve_unstore(sieve_core_t* h) {
@@ -1936,6 +2083,8 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
     h->eph_c2 = h->eph_c2_stored;
     h->valid = h->valid_stored;
     h->log_c = h->log_c_stored;
+    h->ver_cur = h->ver_stored;
+    h->fp_cur = h->fp_stored;
     h->ml_ready = false;
     return SIEVE_OK;
 }
@@ -1948,6 +2097,8 @@ extern "C" int sieve_restore(sieve_core_t* h) {
     h->eph_c2.swap(h->eph_c2_stored);
     h->valid.swap(h->valid_stored);
     std::swap(h->log_c, h->log_c_stored);
+    h->ver_cur.swap(h->ver_stored);
+    h->fp_cur.swap(h->fp_stored);
     h->ml_ready = false;
     // after a rejected parameter proposal the tables hold the rejected values; they are compared with the values of
     // the next sieve_set_leaf_params at the next leaf update, so nothing has to be rebuilt here
@@ -2073,6 +2224,17 @@ extern "C" int sieve_background_log_likelihood(int32_t device, const int64_t* va
 }
 
 // ---- instrumentation ------------------------------------------------------------------------------------------
+extern "C" int sieve_set_elision(sieve_core_t* h, int32_t on) {
+    SV_REQUIRE(h, "null handle");
+    h->elide = on != 0;
+    return SIEVE_OK;
+}
+extern "C" int sieve_elided_count(sieve_core_t* h, uint64_t* out) {
+    SV_REQUIRE(h && out, "null argument");
+    *out = h->elided_total;
+    return SIEVE_OK;
+}
+
 extern "C" int sieve_enable_timing(sieve_core_t* h, int32_t on) {
     SV_REQUIRE(h, "null handle");
     h->timing = on != 0;

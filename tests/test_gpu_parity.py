@@ -618,6 +618,62 @@ def test_transient_nodes_do_not_change_results(core_mod, oracle, monkeypatch):
             np.testing.assert_array_equal(a, b)
 
 
+def test_change_tracking_skips_unchanged_nodes_bit_identically(core_mod, oracle, monkeypatch):
+    """A caller that dirties more than changed (SIEVE under a relaxed clock with Felsenstein's correction dirties the
+    whole tree for every branch-rate proposal, ScsTreeLikelihood.java:2814-2821): the core recomputes only what has new
+    inputs.  Every number must equal the run with the short-cut off, through accepts, rejects, tree moves, leaf
+    parameter moves and read-backs; and most of the dirty nodes must indeed have been skipped."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood, LeafModelParams
+    d = synthetic(60, 280, seed=101)
+    counts, tree = d["counts"], d["tree"]
+    runs, elided = {}, {}
+    for T in ("8", "0"):
+        monkeypatch.setenv("SIEVE_B200_TRANSIENT_LEAVES", T)
+        for on in (True, False):
+            rng = np.random.default_rng(17)
+            br0 = rng.lognormal(0.0, 0.2, size=tree.node_count)
+            tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=4000.0,
+                                   branch_rates=br0)
+            tl.core.set_elision(on)
+            out = [tl.calculate_logp()]
+            for it in range(24):
+                tl.store()
+                kind = it % 8
+                if kind == 5:      # tree move: one node height
+                    t2 = tl.tree.copy()
+                    node = int(rng.integers(tree.n, tree.node_count - 1))
+                    lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+                    t2.height[node] = lo + (t2.height[t2.parent[node]] - lo) * rng.random()
+                    tl.set_tree(t2, [node])
+                elif kind == 7:    # leaf parameter move
+                    p = tl.params.copy()
+                    p.eps *= float(np.exp(0.1 * rng.normal()))
+                    tl.set_leaf_params(p)
+                else:              # branch-rate move: ONE rate changes, the whole tree is flagged
+                    br = tl.branch_rates.copy()
+                    br[int(rng.integers(0, tree.node_count - 1))] *= float(np.exp(0.3 * rng.normal()))
+                    tl.set_branch_rates(br)
+                out.append(tl.calculate_logp())
+                if rng.random() < 0.6:
+                    tl.restore()
+                if it % 6 == 3:
+                    out.append(tl.core.get_node_partials(tree.n + 5))
+                    out.append(tl.core.get_node_partials(tree.root - 1, const=True))
+            out.append(tl.pattern_log_likelihoods()[0].copy())
+            out.append(tl.pattern_log_likelihoods()[1].copy())
+            runs[(T, on)] = out
+            elided[(T, on)] = tl.core.elided_count()
+            tl.close()
+    for T in ("8", "0"):
+        for a, b in zip(runs[(T, True)], runs[(T, False)]):
+            np.testing.assert_array_equal(a, b)
+        assert elided[(T, False)] == 0
+        # 18 branch-rate proposals x ~59 dirty internal nodes each; only the path to the root has new inputs
+        assert elided[(T, True)] > 18 * 40, elided
+    for a, b in zip(runs[("8", True)], runs[("0", True)]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_pipelined_walk_is_bit_identical(core_mod, oracle, monkeypatch):
     """SIEVE_B200_PIPE=1 takes the cp.async-pipelined walk (prune_pipe.cuh, opt-in: measured slower): same op list, same
     arithmetic, so every number must be identical -- resident with proposals / rejections, and streamed with ragged chunks."""
