@@ -42,6 +42,7 @@ static int sv_fail(int code, const std::string& msg) {
 struct PendingMatrix {
     int slot;
     int reuse = 0;    // host mirror of the matrix: 0 = compute, 1 = the slot already holds these values, 2 = copy the twin slot's
+    int skip = 0;     // not uploaded: superseded, or (change tracking) nothing new
     int is_distance;  // v[0..K) are branch distances (length * branch rate * category rate) instead of K matrices
     double v[SV_KMAX * 16];
 };
@@ -146,9 +147,13 @@ struct sieve_core {
     bool elide = true;
     uint64_t ver_counter = 0, elided_total = 0;
     std::vector<uint64_t> mat_ver;      // [2 * n_nodes] per matrix slot
-    std::vector<double> mat_mirror;     // [2 * n_nodes][SV_KMAX * 16] what the slot was last given (matrix or K distances)
+    std::vector<double> mat_mirror;     // [2 * n_nodes][SV_KMAX * 16] the matrices a slot was last given ...
+    std::vector<double> dist_mirror;    // [n_nodes][2][SV_KMAX] ... or its K distances
     std::vector<char> mat_mirror_q;     // ... and in which form
     uint64_t leaf_ver[2] = {0, 0};
+    std::vector<int> scratch_idx;       // per-flush scratch
+    std::vector<int> topo_parent, topo_leaves;  // planner: parents and subtree leaf counts of the current children map
+    bool topo_cache_ok = false;
     std::vector<uint64_t> g_ver;        // [2 * n_nodes] version of the node value whose constant-site factor G sits in that slot
     std::vector<char> buf_has;          // [2 * n_nodes] the partial buffer holds a value ...
     std::vector<uint64_t> buf_ver;      // ... of this version ...
@@ -346,6 +351,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     CR(sv_alloc(h, &h->d_qfac, (size_t)2 * h->n_nodes * SV_KMAX));
     h->mat_ver.assign((size_t)2 * h->n_nodes, 0);
     h->mat_mirror.assign((size_t)2 * h->n_nodes * SV_KMAX * 16, 0.0);
+    h->dist_mirror.assign((size_t)2 * h->n_nodes * SV_KMAX, 0.0);
     h->mat_mirror_q.assign((size_t)2 * h->n_nodes, 0);
     h->g_ver.assign((size_t)2 * h->n_nodes, 0);
     h->buf_has.assign((size_t)2 * h->n_nodes, 0);
@@ -848,14 +854,17 @@ extern "C" int sieve_set_distances(sieve_core_t* h, int32_t count, const int32_t
     for (int i = 0; i < count; i++) {
         SV_REQUIRE(sv_node_ok(h, nodes[i]), "sieve_set_distances: bad node");
         if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
-        PendingMatrix pm;
+        h->pending_mats.emplace_back();  // filled in place: only the first K of its 64 doubles are touched
+        PendingMatrix& pm = h->pending_mats.back();
         pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
         pm.is_distance = 1;
         for (int k = 0; k < K; k++) {
-            SV_REQUIRE(distances[(size_t)i * K + k] >= 0.0, "sieve_set_distances: negative distance");
+            if (!(distances[(size_t)i * K + k] >= 0.0)) {
+                h->pending_mats.pop_back();
+                return sv_fail(SIEVE_ERR_INVALID, "sieve_set_distances: negative distance");
+            }
             pm.v[k] = distances[(size_t)i * K + k];
         }
-        h->pending_mats.push_back(pm);
     }
     return SIEVE_OK;
 }
@@ -985,7 +994,11 @@ static int sv_plan_resident_ops(sieve_core* h) {
     for (int v : h->dirty_list) dirty[v] = 1;
     for (int v : h->demand_list) demanded[v] = 1;
     // parents and subtree leaf counts where the children are known
-    std::vector<int> parent(N, -1), leaves(N, 0);
+    // (cached between plans: they only change when an op names new children for a node)
+    std::vector<int>&parent = h->topo_parent, &leaves = h->topo_leaves;
+    if (!h->topo_cache_ok) {
+    parent.assign(N, -1);
+    leaves.assign(N, 0);
     for (int v = n; v < N; v++) {
         if (h->eph_c1[v] >= 0) parent[h->eph_c1[v]] = v;
         if (h->eph_c2[v] >= 0) parent[h->eph_c2[v]] = v;
@@ -1016,6 +1029,8 @@ static int sv_plan_resident_ops(sieve_core* h) {
                 }
             }
         }
+    }
+    h->topo_cache_ok = true;
     }
     // ---- change tracking: which of the dirty nodes really get a new value? (children before parents) ----
     {
@@ -1213,6 +1228,7 @@ static int sv_record_children(sieve_core* h, int c1, int c2, int parent) {
     SV_REQUIRE(parent >= n && parent < h->n_nodes, "op: parent must be an internal node");
     SV_REQUIRE(c1 >= 0 && c1 < h->n_nodes && c1 != h->root, "op: bad child1");
     SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
+    if (h->eph_c1[parent] != c1 || h->eph_c2[parent] != c2) h->topo_cache_ok = false;
     h->eph_c1[parent] = c1;
     h->eph_c2[parent] = c2;
     return SIEVE_OK;
@@ -1491,26 +1507,53 @@ static int sv_launch_staged(sieve_core* h) {
 // uploads pending matrices / distances + ops with ONE host->device copy and launches scatter + pruning
 static int sv_flush(sieve_core* h) {
     const int K = h->K;
-    // slot attributes first: the op builders look at them
-    for (const PendingMatrix& pm : h->pending_mats) {
-        h->slot_is_q[pm.slot] = pm.is_distance ? 1 : 0;
-        char z = 0;
-        if (pm.is_distance)
-            for (int k = 0; k < K; k++) z |= pm.v[k] == 0.0;
-        h->slot_zero[pm.slot] = z;
-        // content version of the slot: the same values as the slot (or its twin in the other buffer) already holds
-        // keep that version, anything else is new
-        const size_t len = (pm.is_distance ? (size_t)K : (size_t)K * 16) * sizeof(double);
-        const int other = pm.slot < h->n_nodes ? pm.slot + h->n_nodes : pm.slot - h->n_nodes;
-        auto same = [&](int sl) {
-            return h->mat_ver[sl] != 0 && h->mat_mirror_q[sl] == (char)pm.is_distance &&
-                   memcmp(h->mat_mirror.data() + (size_t)sl * SV_KMAX * 16, pm.v, len) == 0;
-        };
-        const_cast<PendingMatrix&>(pm).reuse = same(pm.slot) ? 1 : (same(other) ? 2 : 0);
-        if (pm.reuse == 2) h->mat_ver[pm.slot] = h->mat_ver[other];
-        if (pm.reuse == 0) h->mat_ver[pm.slot] = ++h->ver_counter;
-        h->mat_mirror_q[pm.slot] = (char)pm.is_distance;
-        memcpy(h->mat_mirror.data() + (size_t)pm.slot * SV_KMAX * 16, pm.v, len);
+    // slot attributes first: the op builders look at them.  Only the last entry of a slot counts.  With change tracking on,
+    // an entry that repeats what its slot already holds is dropped, and one that repeats what the node's OTHER matrix
+    // buffer holds (the usual case when a caller refreshes the matrices of unchanged branches after flipping them) is
+    // dropped too and the node is pointed at that buffer again: nothing is uploaded, scattered or mirrored for it.
+    if (!h->pending_mats.empty()) {
+        const int N = h->n_nodes;
+        std::vector<int>& last_idx = h->scratch_idx;
+        last_idx.assign((size_t)2 * N, -1);
+        for (size_t i = 0; i < h->pending_mats.size(); i++) last_idx[h->pending_mats[i].slot] = (int)i;
+        for (size_t i = 0; i < h->pending_mats.size(); i++) {
+            PendingMatrix& pm = h->pending_mats[i];
+            pm.skip = 0;
+            if (last_idx[pm.slot] != (int)i) {
+                pm.skip = 1;  // superseded by a later entry for the same slot
+                continue;
+            }
+            const size_t len = (pm.is_distance ? (size_t)K : (size_t)K * 16) * sizeof(double);
+            const int other = pm.slot < N ? pm.slot + N : pm.slot - N;
+            const int node = pm.slot < N ? pm.slot : pm.slot - N;
+            // distances are mirrored compactly with the node's two buffers side by side (one cache line per node)
+            auto mirror = [&](int sl) -> double* {
+                if (pm.is_distance) return h->dist_mirror.data() + ((size_t)(sl < N ? sl : sl - N) * 2 + (sl < N ? 0 : 1)) * SV_KMAX;
+                return h->mat_mirror.data() + (size_t)sl * SV_KMAX * 16;
+            };
+            auto same = [&](int sl) {
+                return h->mat_ver[sl] != 0 && h->mat_mirror_q[sl] == (char)pm.is_distance && memcmp(mirror(sl), pm.v, len) == 0;
+            };
+            pm.reuse = same(pm.slot) ? 1 : (same(other) ? 2 : 0);
+            if (h->elide && pm.reuse == 1) {
+                pm.skip = 1;
+                continue;
+            }
+            if (h->elide && pm.reuse == 2 && last_idx[other] < 0 && h->cur_mat[node] * N + node == pm.slot) {
+                h->cur_mat[node] = 1 - h->cur_mat[node];
+                pm.skip = 1;
+                continue;
+            }
+            h->slot_is_q[pm.slot] = pm.is_distance ? 1 : 0;
+            char z = 0;
+            if (pm.is_distance)
+                for (int k = 0; k < K; k++) z |= pm.v[k] == 0.0;
+            h->slot_zero[pm.slot] = z;
+            if (pm.reuse == 2) h->mat_ver[pm.slot] = h->mat_ver[other];
+            if (pm.reuse == 0) h->mat_ver[pm.slot] = ++h->ver_counter;
+            h->mat_mirror_q[pm.slot] = (char)pm.is_distance;
+            memcpy(mirror(pm.slot), pm.v, len);
+        }
     }
     if (h->ephemeral)
         SV_TRY(sv_build_streamed_ops(h));
@@ -1518,8 +1561,13 @@ static int sv_flush(sieve_core* h) {
         SV_TRY(sv_plan_resident_ops(h));
     const size_t no = h->pending_ops.size();
     size_t nm = 0, nd = 0;
-    for (const PendingMatrix& pm : h->pending_mats) (pm.is_distance ? nd : nm)++;
-    if (nm == 0 && nd == 0 && no == 0) return SIEVE_OK;
+    for (const PendingMatrix& pm : h->pending_mats)
+        if (!pm.skip) (pm.is_distance ? nd : nm)++;
+    if (nm == 0 && nd == 0 && no == 0) {
+        h->pending_mats.clear();
+        h->g_nodes.clear();
+        return SIEVE_OK;
+    }
     if (no > 0 && !h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "ops queued before the leaves were computed");
     // staging layout: [ops][matrix values][distance values][matrix slots][distance slots]
     const size_t off_mv = no * sizeof(SvOp);
@@ -1533,6 +1581,7 @@ static int sv_flush(sieve_core* h) {
     if (no) memcpy(h->h_stage, h->pending_ops.data(), no * sizeof(SvOp));
     size_t im = 0, id = 0;
     for (const PendingMatrix& pm : h->pending_mats) {
+        if (pm.skip) continue;
         if (pm.is_distance) {
             memcpy(h->h_stage + off_dv + id * K * sizeof(double), pm.v, K * sizeof(double));
             ((int*)(h->h_stage + off_ds))[id++] = pm.slot;
@@ -1565,7 +1614,7 @@ static int sv_flush(sieve_core* h) {
     // (only the reduce kernel, launched later, needs its result log C_tree)
     if (!h->hP.empty())
         for (const PendingMatrix& pm : h->pending_mats) {
-            if (pm.reuse == 1) continue;
+            if (pm.skip || pm.reuse == 1) continue;
             if (pm.reuse == 2) {
                 const int other = pm.slot < h->n_nodes ? pm.slot + h->n_nodes : pm.slot - h->n_nodes;
                 memcpy(h->hP.data() + (size_t)pm.slot * SV_KMAX * 16, h->hP.data() + (size_t)other * SV_KMAX * 16,
@@ -2085,6 +2134,7 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
     h->log_c = h->log_c_stored;
     h->ver_cur = h->ver_stored;
     h->fp_cur = h->fp_stored;
+    h->topo_cache_ok = false;
     h->ml_ready = false;
     return SIEVE_OK;
 }
@@ -2099,6 +2149,7 @@ extern "C" int sieve_restore(sieve_core_t* h) {
     std::swap(h->log_c, h->log_c_stored);
     h->ver_cur.swap(h->ver_stored);
     h->fp_cur.swap(h->fp_stored);
+    if (h->eph_c1 != h->eph_c1_stored || h->eph_c2 != h->eph_c2_stored) h->topo_cache_ok = false;
     h->ml_ready = false;
     // after a rejected parameter proposal the tables hold the rejected values; they are compared with the values of
     // the next sieve_set_leaf_params at the next leaf update, so nothing has to be rebuilt here
