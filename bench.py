@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--per-level", action="store_true", help="issue the pruning as one launch per tree level")
     ap.add_argument("--mcmc-states", type=int, default=400, help="proposals per operator mix in the MCMC replay (0 = skip)")
     ap.add_argument("--streamed", action="store_true", help="SIEVE_FLAG_EPHEMERAL: no resident partials (shapes that exceed HBM, e.g. SIEVE_BENCH_CELLS=10000 SIEVE_BENCH_SITES=125000)")
+    ap.add_argument("--sparse", action="store_true", help="SIEVE_FLAG_SPARSE: leaves resident, only the larger subtrees keep their partials (10 000-cell shapes)")
     ap.add_argument("--no-variants", action="store_true", help="skip the max-sum (variant calling) timing")
     ap.add_argument("--matrices", action="store_true", help="hand the core 16-double matrices (generic kernel) instead of branch distances")
     args = ap.parse_args()
@@ -301,7 +302,7 @@ def main():
     counts_dev = generate_counts_device(tree, rates, br, n, S, SEED + 17 * rank, dev)
     torch.cuda.synchronize()
 
-    core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local, ephemeral=args.streamed)
+    core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local, ephemeral=args.streamed, sparse=args.sparse)
     core.set_counts_device(counts_dev.data_ptr())
     # a host sample of this rank's sites for the parity spot check and the CPU baseline
     n_keep = min(S, 64 if (args.no_cpu_baseline or world > 1) else max(64, int(2.4e7 // n)))
@@ -512,7 +513,7 @@ def main():
 
     # ---------------- variant calling: the max-sum pass on the final state (one-off per analysis) ----------------
     variant_calling = None
-    if not args.streamed and not args.no_variants:
+    if not args.streamed and not args.sparse and not args.no_variants:
         core.ml_trace()                     # first call allocates the pools
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -543,7 +544,7 @@ def main():
         try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this very workload
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             w = tr["workload"]
-            if (w["cells"], w["sites"]) == (n, S) and not (args.per_level or args.matrices or args.streamed or with_const):
+            if (w["cells"], w["sites"]) == (n, S) and not (args.per_level or args.matrices or args.streamed or args.sparse or with_const):
                 k = tr["k_prune<0, 1, 1>"]
                 traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
         except Exception:
@@ -556,6 +557,7 @@ def main():
                                    "felsenstein acquisition-bias correction (BASELINE.json configs[2])" % (n, S),
                        "step": "leaf recompute + all %d internal nodes + root + reduce" % (tree.n),
                        "schedule": ("streamed: site chunks, leaves + walk on scratch slots" if args.streamed else
+                                    "sparse residency: leaves resident, partials of the larger subtrees only; single-launch walk" if args.sparse else
                                     "per-level launches" if args.per_level else "single-launch walk"),
                        "transition_matrices": "16-double matrices from the host" if args.matrices else "branch distances, P formed on the device (fixed Q)",
                        "l2": "inputs larger than L2 (%.1f GB of partials per evaluation)" % (alg_prune / 1e9),

@@ -47,6 +47,9 @@ enum {
 #define SIEVE_FLAG_SINGLE_ADO 4u     /* singleADO == true (rawreadcountsmodel/RawReadCountsModelInterface.java:178-181) */
 #define SIEVE_FLAG_EPHEMERAL 8u      /* do not keep internal partials resident: every update is a streamed full-tree    \
                                         evaluation (needed when 2 * n * S * 136 B exceeds HBM) */
+#define SIEVE_FLAG_SPARSE 16u        /* keep the leaves resident but only the partials of the larger subtrees (as many as  \
+                                        fit); small subtrees are recomputed on the way.  For shapes whose full residency       \
+                                        exceeds HBM but whose MCMC moves should still cost O(depth), e.g. 10^4 cells. */
 
 typedef struct {
     int32_t n_leaves;     /* cells (taxa) */

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (ASC_MODES, FLAG_CONST_PARTIALS, FLAG_EPHEMERAL, FLAG_LOG_PARTIALS, FLAG_SINGLE_ADO, UPDATE_FLIP, UPDATE_PER_LEVEL,
+from ._lib import (ASC_MODES, FLAG_CONST_PARTIALS, FLAG_EPHEMERAL, FLAG_SPARSE, FLAG_LOG_PARTIALS, FLAG_SINGLE_ADO, UPDATE_FLIP, UPDATE_PER_LEVEL,
                    LeafParams, ShardResult, check)
 
 
@@ -24,7 +24,7 @@ def _iptr(a):
 
 class ScsCudaLikelihoodCore:
     def __init__(self, n_leaves, n_sites, n_categories=4, n_states=4, use_log_partials=True, asc_bias=False,
-                 single_ado=True, device=-1, ephemeral=False):
+                 single_ado=True, device=-1, ephemeral=False, sparse=False):
         """initialize(nodeCount = 2n, leafCount = n, internalCount = n, patternCount, matrixCount, stateCount, ...)
         (likelihood/ScsBeerLikelihoodCore.java:91-128)."""
         self.L = _lib.lib()
@@ -33,7 +33,8 @@ class ScsCudaLikelihoodCore:
         self.use_log = bool(use_log_partials)
         self.asc_bias = bool(asc_bias)
         flags = (FLAG_LOG_PARTIALS if use_log_partials else 0) | (FLAG_CONST_PARTIALS if asc_bias else 0) | \
-                (FLAG_SINGLE_ADO if single_ado else 0) | (FLAG_EPHEMERAL if ephemeral else 0)
+                (FLAG_SINGLE_ADO if single_ado else 0) | (FLAG_EPHEMERAL if ephemeral else 0) | \
+                (FLAG_SPARSE if sparse else 0)
         cfg = _lib.Config(self.n, self.S, self.K, self.G, flags, device)
         h = C.c_void_p()
         check(self.L.sieve_create(C.byref(cfg), C.byref(h)))

@@ -151,6 +151,16 @@ struct sieve_core {
     std::vector<double> dist_mirror;    // [n_nodes][2][SV_KMAX] ... or its K distances
     std::vector<char> mat_mirror_q;     // ... and in which form
     uint64_t leaf_ver[2] = {0, 0};
+    // Sparse residency (SIEVE_FLAG_SPARSE): the partial pool has fewer slots than 2 * n_internal.  Nodes with more than
+    // keep_T leaves keep their partials (a slot per buffer that holds something the current or the stored state refers
+    // to); smaller subtrees are recomputed from the resident leaves when an update needs them, through temporary slots
+    // that are recycled inside the walk.  Dense cores use the same code with a fixed identity mapping.
+    bool sparse = false, sparse_recheck = true;
+    int pool_slots = 0;
+    int keep_T = 0;
+    std::vector<int> slot_of;      // [2 * n_nodes] physical slot of (buffer, node), -1 = none
+    std::vector<int> free_slots;
+    std::vector<int> held;         // (buffer * n_nodes + node) of small nodes materialised on demand: released by the next plan
     std::vector<int> scratch_idx;       // per-flush scratch
     std::vector<int> topo_parent, topo_leaves;  // planner: parents and subtree leaf counts of the current children map
     bool topo_cache_ok = false;
@@ -302,6 +312,30 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         part_slots = h->n_slots;
         leaf_bufs = 1;
     }
+    h->sparse = (cfg->flags & SIEVE_FLAG_SPARSE) && !h->ephemeral;
+    if (h->sparse) {
+        // everything but the internal partials is resident as usual; the pool takes what is left (minus head room)
+        size_t free0 = 0, total0 = 0;
+        cudaMemGetInfo(&free0, &total0);
+        const size_t fixed = n * S * 16 + 2 * n * S * (40 + (algebraic ? 8 : 0)) + ((size_t)3 << 30);
+        const size_t per_slot = S * (SV_KMAX * 32 + 8) * (twin ? 2 : 1);
+        size_t slots = free0 > fixed ? (free0 - fixed) / per_slot : 0;
+        if (const char* e = getenv("SIEVE_B200_POOL_SLOTS")) slots = (size_t)std::max(0, atoi(e));
+        slots = std::min<size_t>(slots, 2 * n);
+        if (slots < 96) {
+            g_err = "sieve_create: SIEVE_FLAG_SPARSE needs room for at least 96 partial slots";
+            return fail(SIEVE_ERR_OOM);
+        }
+        part_slots = slots;
+    }
+    h->pool_slots = (int)part_slots;
+    h->slot_of.assign((size_t)2 * h->n_nodes, -1);
+    if (h->sparse) {
+        for (int i = (int)part_slots - 1; i >= 0; i--) h->free_slots.push_back(i);
+    } else if (!h->ephemeral) {
+        for (int b = 0; b < 2; b++)
+            for (int v = h->n; v < h->n_nodes; v++) h->slot_of[(size_t)b * h->n_nodes + v] = b * h->n_internal + (v - h->n);
+    }
     h->eph_c1.assign(h->n_nodes, -2);
     h->eph_c2.assign(h->n_nodes, -2);
     h->eph_c1_stored = h->eph_c1;
@@ -309,7 +343,8 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->valid.assign(h->n_nodes, 0);
     h->valid_stored.assign(h->n_nodes, 0);
     if (const char* e = getenv("SIEVE_B200_TRANSIENT_LEAVES")) h->transient_T = std::max(0, atoi(e));
-    if ((2 * n + 2) * pool_sites >= ((size_t)1 << 32) || part_slots * pool_sites >= ((size_t)1 << 32)) {
+    h->keep_T = std::max(1, h->transient_T);
+    if ((2 * n + 2) * pool_sites >= ((size_t)1 << 32) || part_slots * pool_sites + 2 * n + 2 >= ((size_t)1 << 32)) {
         g_err = "sieve_create: more than 2^32 (slot, site) rows per pool; use SIEVE_FLAG_EPHEMERAL (streamed evaluation)";
         return fail(SIEVE_ERR_OOM);
     }
@@ -878,6 +913,41 @@ extern "C" int sieve_set_node_partials_for_update(sieve_core_t* h, int32_t node)
     return SIEVE_OK;
 }
 
+// row of (buffer, internal node) in the partial pools; a node without a slot (its value only ever lives in registers)
+// gets a unique row that is never dereferenced -- the forwarding link compares rows
+static inline unsigned sv_part_row(const sieve_core* h, int buf, int node) {
+    const int sl = h->slot_of[(size_t)buf * h->n_nodes + node];
+    if (sl < 0) return 0xFFFFFFFFu - (unsigned)node;
+    return (unsigned)((long long)sl * h->S);
+}
+
+static void sv_slot_release(sieve_core* h, int buf, int node) {
+    const size_t bi = (size_t)buf * h->n_nodes + node;
+    if (!h->sparse || h->slot_of[bi] < 0) return;
+    h->free_slots.push_back(h->slot_of[bi]);
+    h->slot_of[bi] = -1;
+    h->buf_has[bi] = 0;
+    if (h->cur_part[node] == buf) h->valid[node] = 0;
+    if (h->stored_part[node] == buf) h->valid_stored[node] = 0;
+}
+
+// a free slot; when none is left, buffers that neither the current nor the stored state refers to are reclaimed first
+static int sv_slot_alloc(sieve_core* h) {
+    if (h->free_slots.empty()) {
+        const int n = h->n, N = h->n_nodes;
+        for (int v = n; v < N; v++)
+            for (int b = 0; b < 2; b++) {
+                if (h->slot_of[(size_t)b * N + v] < 0) continue;
+                const bool used = (b == h->cur_part[v] && h->valid[v]) || (b == h->stored_part[v] && h->valid_stored[v]);
+                if (!used) sv_slot_release(h, b, v);
+            }
+    }
+    if (h->free_slots.empty()) return -1;
+    const int sl = h->free_slots.back();
+    h->free_slots.pop_back();
+    return sl;
+}
+
 static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
     const int n = h->n;
     const long long S = h->S;
@@ -886,13 +956,13 @@ static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
     SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
     op->flags = 0;
     op->pad0 = op->pad1 = 0;
-    op->dst_row = (unsigned)((long long)(h->cur_part[parent] * h->n_internal + (parent - n)) * S);
+    op->dst_row = sv_part_row(h, h->cur_part[parent], parent);
     auto child = [&](int c, int leaf_flag, unsigned* row, int* m) {
         if (c < n) {
             op->flags |= leaf_flag;
             *row = (unsigned)((long long)(h->cur_leaf * n + c) * S);
         } else
-            *row = (unsigned)((long long)(h->cur_part[c] * h->n_internal + (c - n)) * S);
+            *row = sv_part_row(h, h->cur_part[c], c);
         *m = h->cur_mat[c] * h->n_nodes + c;
         if (h->log_mode && h->slot_zero[*m]) op->flags |= SV_OP_ZEROD;
     };
@@ -1031,6 +1101,33 @@ static int sv_plan_resident_ops(sieve_core* h) {
         }
     }
     h->topo_cache_ok = true;
+    h->sparse_recheck = true;  // leaf counts moved: a node may have dropped below the keep threshold
+    }
+    if (h->sparse) {
+        // small nodes that were materialised for a read-back go back to "not in memory"
+        for (int bi : h->held) {
+            const int b = bi / N, v = bi % N;
+            if (v != root && leaves[v] <= h->keep_T) sv_slot_release(h, b, v);
+        }
+        h->held.clear();
+        // the nodes that keep their partials must fit twice (a whole-tree proposal flips every one of them) plus the
+        // temporaries of the walk; when they do not, the threshold goes up and the nodes below it give their slots back
+        auto kept_count = [&](int T) {
+            int c = 0;
+            for (int v = n; v < N; v++) c += (v == root || leaves[v] > T) ? 1 : 0;
+            return c;
+        };
+        int T = std::max(h->keep_T, 1);
+        while (2 * (long long)kept_count(T) + 64 > h->pool_slots && T < (1 << 28)) T *= 2;
+        if (T != h->keep_T || h->sparse_recheck) {
+            h->keep_T = T;
+            for (int v = n; v < N; v++)
+                if (v != root && leaves[v] <= T) {
+                    sv_slot_release(h, 0, v);
+                    sv_slot_release(h, 1, v);
+                }
+            h->sparse_recheck = false;
+        }
     }
     // ---- change tracking: which of the dirty nodes really get a new value? (children before parents) ----
     {
@@ -1125,7 +1222,8 @@ static int sv_plan_resident_ops(sieve_core* h) {
                 const bool na = needs(a), nb = b >= 0 && needs(b);
                 f.first = f.last = -1;
                 if (na && nb) {
-                    const bool ta = leaves[a] <= h->transient_T, tb = leaves[b] <= h->transient_T;
+                    const int small = h->sparse ? h->keep_T : h->transient_T;
+                    const bool ta = leaves[a] <= small, tb = leaves[b] <= small;
                     int last;
                     if (ta != tb)
                         last = ta ? a : b;  // the transient one is consumed from registers and never written
@@ -1150,13 +1248,7 @@ static int sv_plan_resident_ops(sieve_core* h) {
                 }
             } else {
                 visited[v] = 1;
-                SvOp op;
-                // the child that was computed last goes first in the op (forwarding), the rest is symmetric
-                int c1 = h->eph_c1[v], c2 = h->eph_c2[v];
-                int rc = sv_make_op(h, c1, c2, v, &op);
-                if (rc != SIEVE_OK) return rc;
-                h->pending_ops.push_back(op);
-                emitted.push_back(v);
+                emitted.push_back(v);  // the op itself is made below, when the destination slots are known
                 st.pop_back();
             }
         }
@@ -1172,8 +1264,8 @@ static int sv_plan_resident_ops(sieve_core* h) {
     // a dirty node whose parent was dirty but never reached it (inconsistent input) would be skipped: check
     for (int v : h->dirty_list)
         if (dirty[v] && !visited[v]) SV_TRY(run_from(v));
-    // store decisions
-    const size_t base = h->pending_ops.size() - emitted.size();
+    // store decisions and ops, in walk order
+    std::vector<char> is_temp(h->sparse ? N : 0, 0);
     for (size_t i = 0; i < emitted.size(); i++) {
         const int v = emitted[i];
         bool consumed_next = false;
@@ -1181,20 +1273,52 @@ static int sv_plan_resident_ops(sieve_core* h) {
             const int p = emitted[i + 1];
             consumed_next = h->eph_c1[p] == v || h->eph_c2[p] == v;
         }
-        const bool transient = h->transient_T > 0 && v != root && leaves[v] <= h->transient_T;
-        const bool store = !(transient && consumed_next) || demanded[v];
-        SvOp& op = h->pending_ops[base + i];
+        bool store;
+        const size_t bi = (size_t)h->cur_part[v] * N + v;
+        if (!h->sparse) {
+            const bool transient = h->transient_T > 0 && v != root && leaves[v] <= h->transient_T;
+            store = !(transient && consumed_next) || demanded[v];
+        } else {
+            const bool kept = v == root || leaves[v] > h->keep_T;
+            store = kept || demanded[v] || !consumed_next;
+            if (store && h->slot_of[bi] < 0) {
+                const int sl = sv_slot_alloc(h);
+                if (sl < 0)
+                    return sv_fail(SIEVE_ERR_OOM, "the sparse partial pool is exhausted (" + std::to_string(h->pool_slots) +
+                                                      " slots): raise SIEVE_B200_POOL_SLOTS or free device memory");
+                h->slot_of[bi] = sl;
+                if (!kept) {
+                    if (demanded[v])
+                        h->held.push_back((int)bi);  // read back after this flush, released by the next plan
+                    else
+                        is_temp[v] = 1;              // an intermediate of a small subtree: recycled once its parent has consumed it
+                }
+            }
+        }
+        SvOp op;
+        SV_TRY(sv_make_op(h, h->eph_c1[v], h->eph_c2[v], v, &op));
         if (!store) op.flags |= SV_OP_NOSTORE;
+        h->pending_ops.push_back(op);
         h->valid[v] = store ? 1 : 0;
         if (store) {
-            const size_t bi = (size_t)h->cur_part[v] * N + v;
             h->buf_has[bi] = 1;
             h->buf_ver[bi] = h->ver_cur[v];
             h->buf_fp[bi] = h->fp_cur[v];
         }
         // a clean subtree is identical in the stored state; its buffer is shared when the indices agree
         if (store && !dirty[v] && h->cur_part[v] == h->stored_part[v]) h->valid_stored[v] = 1;
+        if (h->sparse) {
+            // this op was the consumer of its children's temporary slots
+            for (int c : {h->eph_c1[v], h->eph_c2[v]})
+                if (c >= n && is_temp[c]) {
+                    is_temp[c] = 0;
+                    sv_slot_release(h, h->cur_part[c], c);
+                }
+        }
     }
+    if (h->sparse)
+        for (int v : emitted)
+            if (is_temp[v]) h->held.push_back(h->cur_part[v] * N + v);  // no consumer in this plan (inconsistent dirty set)
     // (the constant-site factor follows the really dirty nodes only: queued by the change-tracking pass above)
     h->dirty_list.clear();
     h->demand_list.clear();
@@ -1347,6 +1471,7 @@ extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t*
         return SIEVE_OK;
     }
     const bool per_level = (mode & SIEVE_UPDATE_PER_LEVEL) && level_offsets && n_levels > 0;
+    if (per_level && h->sparse) return sv_fail(SIEVE_ERR_STATE, "sieve_update_nodes: the per-level schedule needs a dense core");
     if (per_level) {
         SV_REQUIRE(h->pending_ops.empty(), "sieve_update_nodes: per-level update with other ops pending");
         SV_REQUIRE(level_offsets[0] == 0 && level_offsets[n_levels] == n_ops, "sieve_update_nodes: bad level offsets");
@@ -1783,7 +1908,9 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
         x = h->d_leafX + ((size_t)h->cur_leaf * n + node) * S * 4;
         sc = h->d_leafS + ((size_t)h->cur_leaf * n + node) * S;
     } else {
-        const size_t slot = (size_t)h->cur_part[node] * h->n_internal + (node - n);
+        const int sl = h->slot_of[(size_t)h->cur_part[node] * h->n_nodes + node];
+        if (sl < 0) return sv_fail(SIEVE_ERR_STATE, "sieve_get_node_partials: the node could not be materialised");
+        const size_t slot = (size_t)sl;
         if (which == 1 && !h->with_const) return sv_fail(SIEVE_ERR_STATE, "constant-site partials are not maintained");
         if (which == 1 && !h->const_twin) {
             // rebuilt from the factorisation: G_node x product over the node's leaves of their constant-genotype likelihood
@@ -1886,7 +2013,8 @@ static int sv_ml_require(sieve_core* h, const char* who) {
 
 extern "C" int sieve_ml_trace(sieve_core_t* h) {
     SV_REQUIRE(h, "null handle");
-    if (h->ephemeral) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: needs resident partials (not SIEVE_FLAG_EPHEMERAL)");
+    if (h->ephemeral || h->sparse)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: needs fully resident partials (not SIEVE_FLAG_EPHEMERAL / SIEVE_FLAG_SPARSE)");
     if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: leaves not computed yet");
     SV_CUDA(cudaSetDevice(h->device));
     SV_TRY(sv_flush(h));
@@ -2121,6 +2249,8 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->log_c_stored = h->log_c;
     h->ver_stored = h->ver_cur;
     h->fp_stored = h->fp_cur;
+    if (h->sparse)  // what only the previous stored state referred to gives its slot back
+        for (int v = h->n; v < h->n_nodes; v++) sv_slot_release(h, 1 - h->cur_part[v], v);
     return SIEVE_OK;
 }
 extern "C" int sieve_unstore(sieve_core_t* h) {

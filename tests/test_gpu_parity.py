@@ -674,6 +674,80 @@ def test_change_tracking_skips_unchanged_nodes_bit_identically(core_mod, oracle,
         np.testing.assert_array_equal(a, b)
 
 
+def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatch):
+    """SIEVE_FLAG_SPARSE with a pool far smaller than 2 * n_internal slots: only the larger subtrees keep their partials,
+    small ones are recomputed through recycled temporary slots.  Same ops per site => the same bits as the dense core,
+    through branch-rate, tree and leaf-parameter proposals, accepts, rejects and read-backs; the MCMC driver's
+    incrementally maintained state must still equal a from-scratch evaluation."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    from sieve_b200.mcmc import McmcReplay
+    d = synthetic(150, 200, seed=111)
+    counts, tree = d["counts"], d["tree"]
+    runs = {}
+    for tag, sparse, slots in (("dense", False, None), ("sparse", True, "110"), ("sparse_tight", True, "96")):
+        if slots:
+            monkeypatch.setenv("SIEVE_B200_POOL_SLOTS", slots)
+        rng = np.random.default_rng(23)
+        br0 = rng.lognormal(0.0, 0.2, size=tree.node_count)
+        tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=4000.0,
+                               branch_rates=br0, sparse=sparse)
+        out = [tl.calculate_logp()]
+        for it in range(30):
+            tl.store()
+            kind = it % 10
+            if kind in (2, 5, 8):      # tree move: one node height
+                t2 = tl.tree.copy()
+                node = int(rng.integers(tree.n, tree.node_count - 1))
+                lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+                t2.height[node] = lo + (t2.height[t2.parent[node]] - lo) * rng.random()
+                tl.set_tree(t2, [node])
+            elif kind == 7:            # leaf parameter move
+                p = tl.params.copy()
+                p.eps *= float(np.exp(0.1 * rng.normal()))
+                tl.set_leaf_params(p)
+            elif kind == 9:            # everything changes
+                tl.set_gamma_shape(tl.gamma_shape * float(np.exp(0.2 * rng.normal())))
+            else:                      # branch-rate move (whole tree flagged, one branch changed)
+                br = tl.branch_rates.copy()
+                br[int(rng.integers(0, tree.node_count - 1))] *= float(np.exp(0.3 * rng.normal()))
+                tl.set_branch_rates(br)
+            out.append(tl.calculate_logp())
+            if rng.random() < 0.6:
+                tl.restore()
+            if it % 7 == 3:
+                out.append(tl.core.get_node_partials(tree.n + 5))          # a small node: materialised on demand
+                out.append(tl.core.get_node_partials(tree.root - 1))
+                out.append(tl.core.get_node_partials(tree.root - 2, const=True))
+        out.append(tl.pattern_log_likelihoods()[0].copy())
+        out.append(tl.pattern_log_likelihoods()[1].copy())
+        runs[tag] = out
+        tl.close()
+    for tag in ("sparse", "sparse_tight"):
+        for a, b in zip(runs[tag], runs["dense"]):
+            np.testing.assert_array_equal(a, b)
+    # the native MCMC driver on a sparse core (topology moves included)
+    S, n = counts.shape[:2]
+    monkeypatch.setenv("SIEVE_B200_POOL_SLOTS", "120")
+    finals = {}
+    for sparse in (False, True):
+        c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True, sparse=sparse)
+        c.set_counts(counts)
+        c.compute_size_factors(0)
+        mc = McmcReplay(c, tree, mix="relaxed2", asc_mode="felsenstein_mean", n_background_sites=5000.0, seed=5)
+        st = mc.run(300)
+        again = mc.full_recompute()
+        assert abs(again - st["log_p"]) <= 1e-11 * abs(again)
+        finals[sparse] = (st["log_p"], st["accepted"])
+        mc.close()
+        c.close()
+    assert finals[True] == finals[False]
+    # misuse is loud
+    c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, False, True, sparse=True)
+    with pytest.raises(RuntimeError):
+        c.ml_trace()
+    c.close()
+
+
 def test_pipelined_walk_is_bit_identical(core_mod, oracle, monkeypatch):
     """SIEVE_B200_PIPE=1 takes the cp.async-pipelined walk (prune_pipe.cuh, opt-in: measured slower): same op list, same
     arithmetic, so every number must be identical -- resident with proposals / rejections, and streamed with ragged chunks."""
