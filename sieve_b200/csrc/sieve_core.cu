@@ -16,6 +16,7 @@
 #include "leaf.cuh"
 #include "prune.cuh"
 #include "prune_pipe.cuh"
+#include "prune_rp.cuh"
 #include "reduce.cuh"
 #include "maxsum.cuh"
 #include "sizefactors.cuh"
@@ -109,6 +110,7 @@ struct sieve_core {
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
     bool force_generic = false;
+    bool use_rp = false;  // SIEVE_B200_RP=1: next op's operands prefetched into registers (prune_rp.cuh)
     bool use_pipe = false, pipe_attr_set = false;  // SIEVE_B200_PIPE=1: the cp.async-pipelined Q walk (measured slower, see prune_pipe.cuh)
     // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
     int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
@@ -268,6 +270,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->with_const = cfg->flags & SIEVE_FLAG_CONST_PARTIALS;
     if (const char* e = getenv("SIEVE_B200_CONST_TWIN")) h->const_twin = atoi(e) != 0;
     if (const char* e = getenv("SIEVE_B200_PIPE")) h->use_pipe = atoi(e) != 0;
+    if (const char* e = getenv("SIEVE_B200_RP")) h->use_rp = atoi(e) != 0;
     const bool twin = h->with_const && h->const_twin;
     const bool algebraic = h->with_const && !h->const_twin;
     h->single_ado = cfg->flags & SIEVE_FLAG_SINGLE_ADO;
@@ -1581,6 +1584,7 @@ static int sv_launch_staged(sieve_core* h) {
         const unsigned gx = (unsigned)((h->S + spb - 1) / spb);
         // the software-pipelined walk (prune_pipe.cuh): Q-specialised, variant partials only, one launch for many ops
         const bool pipe = qfast && !(h->with_const && h->const_twin) && h->use_pipe && !h->last_per_level;
+        const bool rp = qfast && !(h->with_const && h->const_twin) && h->use_rp && !h->last_per_level && !pipe;
         if (pipe && !h->pipe_attr_set) {
             SV_CUDA(cudaFuncSetAttribute(k_prune_pipe<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
@@ -1589,6 +1593,8 @@ static int sv_launch_staged(sieve_core* h) {
         auto launch = [&](dim3 grid) {
             if (pipe)
                 k_prune_pipe<true><<<grid, SV_PRUNE_THREADS, SV_PIPE_SMEM, h->stream>>>(a);
+            else if (rp)
+                k_prune_rp<true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
             else if (qfast)
                 sv_launch_prune_t<true>(h, grid, a);
             else
