@@ -31,9 +31,25 @@ struct SvMlOp {
 };
 
 // ---- leaves: log-space mixture, component arg-max ---------------------------------------------------------------
+// log NB(x; r, p) of a cell at coverage x for 0, 1 and 2 sequenced alleles, tabulated like the linear-space tables of
+// leaf.cuh (same formula, same operation order): the max-sum leaf kernel then needs no logGamma per (cell, site)
+__global__ void k_build_cell_log_tables(double* __restrict__ cellL, const double* __restrict__ size_factors, int n_cells,
+                                        int C, SvCovParams cp) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (x >= C || j >= n_cells) return;
+    double e[4];
+    e[0] = cp.single_ado ? 0.0 : sv_seq_cov_log(x, 0, size_factors[j], cp.t, cp.v);
+    e[1] = sv_seq_cov_log(x, 1, size_factors[j], cp.t, cp.v);
+    e[2] = sv_seq_cov_log(x, 2, size_factors[j], cp.t, cp.v);
+    e[3] = 0.0;
+    sv_st256(cellL + ((size_t)j * C + x) * 4, e);
+}
+
 struct SvMlLeafArgs {
     const int4* counts;  // [cell][site]
     const double *dmA, *dmB;
+    const double* cellL;     // [cell][C][4] log NB for 0 / 1 / 2 sequenced alleles
     const double* size_factors;
     double* leafL;           // [cell][site][4] log genotype likelihoods (0/0, 0/1, 1/1, 1/1')
     unsigned short* ado;     // [cell][site] four nibbles: arg-max set of the dropout components of genotype g
@@ -114,8 +130,16 @@ __global__ void __launch_bounds__(128) k_leaf_ml(SvMlLeafArgs a) {
     }
     const double sf = a.size_factors[j];
     const double lt = log(a.cp.theta), l1t = log(1 - a.cp.theta);
-    const double nb2 = sv_seq_cov_log(cov, 2, sf, a.cp.t, a.cp.v);
-    const double nb1 = sv_seq_cov_log(cov, 1, sf, a.cp.t, a.cp.v);
+    double nb0, nb1, nb2;
+    if (cov >= 0 && cov < C) {
+        double e[4];
+        sv_ld256_nc(a.cellL + ((size_t)j * C + cov) * 4, e);
+        nb0 = e[0]; nb1 = e[1]; nb2 = e[2];
+    } else {
+        nb2 = sv_seq_cov_log(cov, 2, sf, a.cp.t, a.cp.v);
+        nb1 = sv_seq_cov_log(cov, 1, sf, a.cp.t, a.cp.v);
+        nb0 = a.cp.single_ado ? 0.0 : sv_seq_cov_log(cov, 0, sf, a.cp.t, a.cp.v);
+    }
     const double n01 = sv_lse2(N0, N1);  // logSumExp{nuc[+0], nuc[+1]} of the heterozygous one-allele term
     double out[4];
     unsigned masks = 0;
@@ -134,7 +158,6 @@ __global__ void __launch_bounds__(128) k_leaf_ml(SvMlLeafArgs a) {
         }
     } else {
         // locus dropout (:147-153 etc.): tmp[0] both alleles, tmp[1] one lost, tmp[2] both lost (no nucleotide factor)
-        const double nb0 = sv_seq_cov_log(cov, 0, sf, a.cp.t, a.cp.v);
         const double nn[4] = {N0, N3, N1, N2};
         const double na[4] = {N0, 0.0, N1, N1};
         const double two_l1t = __dmul_rn(2.0, l1t), two_lt = __dmul_rn(2.0, lt);
@@ -169,12 +192,13 @@ struct SvMlArgs {
 
 // one child's side of ScsBeerLikelihoodCore.java:3100-3131: max over child genotypes of log P[p][c] + value[c], with
 // the reference's sequential tie rule (first index seeds, '<' replaces, '==' appends)
-__device__ __forceinline__ void sv_ml_side(const double* __restrict__ lm, const double (&v)[4], double (&mx)[4],
+__device__ __forceinline__ void sv_ml_side(const double* lm /* shared */, const double (&v)[4], double (&mx)[4],
                                            unsigned (&mask)[4]) {
 #pragma unroll
     for (int p = 0; p < 4; p++) {
-        double m[4];
-        sv_ld256_nc(lm + 4 * p, m);
+        const double2 ma = *reinterpret_cast<const double2*>(lm + 4 * p);
+        const double2 mb = *reinterpret_cast<const double2*>(lm + 4 * p + 2);
+        const double m[4] = {ma.x, ma.y, mb.x, mb.y};
         double best = __dadd_rn(m[0], v[0]);
         unsigned bm = 1u;
 #pragma unroll
@@ -192,35 +216,58 @@ __device__ __forceinline__ void sv_ml_side(const double* __restrict__ lm, const 
 }
 
 __global__ void __launch_bounds__(128) k_ml_up(SvMlArgs a) {
-    const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long lane_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long lanes = (long long)a.S * a.K;
-    if (lane >= lanes) return;
+    // lanes past the end stay (every lane of a warp stages a matrix row) as duplicates of the last lane; they never store
+    const bool lane_ok = lane_raw < lanes;
+    const long long lane = lane_ok ? lane_raw : lanes - 1;
     const int K = a.K;
     const long long s = lane / K;
     const int k = (int)(lane - s * K);
+    // warp-private copies of the op's two log matrices (all K categories): one 256-bit load per lane stages them, the
+    // 32 reads per op then are shared-memory broadcasts instead of L1 transactions (ncu: the global-load queue was the
+    // limiter -- lg_throttle -- when every lane fetched its rows itself)
+    __shared__ __align__(32) double sm[(128 / 32) * 2 * SV_KMAX * SV_MAT_STRIDE];
+    const int wl = threadIdx.x & 31;
+    double* wm = sm + (threadIdx.x >> 5) * (2 * SV_KMAX * SV_MAT_STRIDE);
+    const int st_which = wl >> 4, st_kk = (wl >> 2) & 3, st_q = wl & 3;
+    double* st_dst = wm + st_which * (SV_KMAX * SV_MAT_STRIDE) + st_kk * SV_MAT_STRIDE + st_q * 4;
+    const double* M1 = wm + k * SV_MAT_STRIDE;
+    const double* M2 = wm + SV_KMAX * SV_MAT_STRIDE + k * SV_MAT_STRIDE;
     for (int i = 0; i < a.n_ops; i++) {
         const SvMlOp op = a.ops[i];
         double v1[4], v2[4], m1[4], m2[4];
         unsigned b1[4], b2[4] = {0u, 0u, 0u, 0u};
+        {
+            double m[4] = {0.0, 0.0, 0.0, 0.0};
+            if (st_kk < K && !(st_which == 1 && (op.flags & SV_OP_UNARY)))
+                sv_ld256_nc(a.logm + ((size_t)(st_which ? op.n2 : op.n1) * K + st_kk) * 16 + st_q * 4, m);
+            __syncwarp();  // every lane is done with the previous op's matrices
+            *reinterpret_cast<double2*>(st_dst) = make_double2(m[0], m[1]);
+            *reinterpret_cast<double2*>(st_dst + 2) = make_double2(m[2], m[3]);
+            __syncwarp();
+        }
         if (op.flags & SV_OP_LEAF1)
             sv_ld256_nc(a.leafL + ((size_t)op.c1 * a.S + s) * 4, v1);
         else
             sv_ld256(a.ml + ((size_t)op.c1 * lanes + lane) * 4, v1);
-        sv_ml_side(a.logm + ((size_t)op.n1 * K + k) * 16, v1, m1, b1);
+        sv_ml_side(M1, v1, m1, b1);
         if (!(op.flags & SV_OP_UNARY)) {
             if (op.flags & SV_OP_LEAF2)
                 sv_ld256_nc(a.leafL + ((size_t)op.c2 * a.S + s) * 4, v2);
             else
                 sv_ld256(a.ml + ((size_t)op.c2 * lanes + lane) * 4, v2);
-            sv_ml_side(a.logm + ((size_t)op.n2 * K + k) * 16, v2, m2, b2);
+            sv_ml_side(M2, v2, m2, b2);
 #pragma unroll
             for (int p = 0; p < 4; p++) m1[p] = __dadd_rn(m1[p], m2[p]);  // parentMLPartials = max1 + max2 (:3139)
         }
-        sv_st256(a.ml + ((size_t)op.dst * lanes + lane) * 4, m1);
         unsigned w = 0;
 #pragma unroll
         for (int p = 0; p < 4; p++) w |= (b1[p] | (b2[p] << 4)) << (8 * p);
-        a.back[(size_t)op.dst * lanes + lane] = w;
+        if (lane_ok) {
+            sv_st256(a.ml + ((size_t)op.dst * lanes + lane) * 4, m1);
+            a.back[(size_t)op.dst * lanes + lane] = w;
+        }
     }
 }
 

@@ -175,7 +175,7 @@ struct sieve_core {
 
     // max-sum pass for variant calling (maxsum.cuh); its pools are allocated by the first sieve_ml_trace
     bool ml_alloc = false, ml_ready = false;
-    double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr;
+    double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr, *d_mlcellL = nullptr;
     unsigned short* d_mlado = nullptr;
     unsigned* d_mlback = nullptr;
     unsigned char *d_mlcoll = nullptr, *d_mladosel = nullptr, *d_mlamb = nullptr, *d_mlcats = nullptr;
@@ -449,6 +449,7 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_mlL);
     cudaFree(h->d_ml);
     cudaFree(h->d_mllogm);
+    cudaFree(h->d_mlcellL);
     cudaFree(h->d_mlado);
     cudaFree(h->d_mlback);
     cudaFree(h->d_mlcoll);
@@ -2044,6 +2045,7 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
         SV_TRY(sv_alloc(h, &h->d_mlcats, S));
         SV_TRY(sv_alloc(h, &h->d_mllogm, N * K * 16));
         SV_TRY(sv_alloc(h, &h->d_mlops, n));
+        SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
         h->ml_alloc = true;
     }
     // log P on the host, in double precision with the reference's clamp (ScsBeerLikelihoodCore.java:3100-3101)
@@ -2064,6 +2066,7 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
     la.counts = h->d_counts;
     la.dmA = h->d_dmA;
     la.dmB = h->d_dmB;
+    la.cellL = h->d_mlcellL;
     la.size_factors = h->d_sf;
     la.leafL = h->d_mlL;
     la.ado = h->d_mlado;
@@ -2076,6 +2079,9 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
     la.cp.v = h->tab_lp.allelic_seq_cov_raw_var;
     la.cp.theta = h->tab_lp.ado_rate;
     la.cp.single_ado = h->single_ado ? 1 : 0;
+    k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
+                                                                                                  (int)n, h->C, la.cp);
+    sv_count(h);
     k_leaf_ml<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(la);
     sv_count(h);
 
