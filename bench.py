@@ -302,8 +302,20 @@ def main():
     counts_dev = generate_counts_device(tree, rates, br, n, S, SEED + 17 * rank, dev)
     torch.cuda.synchronize()
 
+    counts_host = None
+    if args.sparse:
+        # a sparse core sizes its partial pool from the memory that is free when it is created: give the generator's
+        # memory back first and load the counts from the host (as a production run would, from the ingest shard file)
+        counts_host = counts_dev.cpu().numpy()
+        del counts_dev
+        torch.cuda.empty_cache()
     core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local, ephemeral=args.streamed, sparse=args.sparse)
-    core.set_counts_device(counts_dev.data_ptr())
+    if args.sparse:
+        core.set_counts_cellmajor(counts_host)
+        counts_dev = torch.from_numpy(counts_host[:, :min(S, 4096), :].copy()).to(dev)   # only the sample below is read
+        del counts_host
+    else:
+        core.set_counts_device(counts_dev.data_ptr())
     # a host sample of this rank's sites for the parity spot check and the CPU baseline
     n_keep = min(S, 64 if (args.no_cpu_baseline or world > 1) else max(64, int(2.4e7 // n)))
     sample = counts_dev[:, :n_keep, :].permute(1, 0, 2).contiguous().cpu().numpy()
@@ -577,6 +589,7 @@ def main():
             "mcmc_states_per_s": mcmc.get("stage1", {}).get("states_per_s"),
             "variant_calling": variant_calling,
             "device_bytes": core.device_bytes(),
+            "residency": core.sparse_info(),
             "parity": parity,
             "cpu_baseline": cpu,
         }

@@ -196,6 +196,9 @@ int sieve_get_node_partials(sieve_core_t *h, int32_t node, int32_t which, double
  * (likelihood/ScsTreeLikelihood.java:2814-2821, alignment/ScsAlignment.java:707-709); here the walk then covers only the
  * path from the changed branch to the root.  On by default; `on = 0` makes every dirty node recompute (A/B, tests). */
 int sieve_set_elision(sieve_core_t *h, int32_t on);
+/* SIEVE_FLAG_SPARSE bookkeeping: slots in the partial pool, the current keep threshold (nodes with more leaves keep their
+ * partials resident; 0 for a dense core) and the slots that are free right now.  Outputs may be NULL. */
+int sieve_sparse_info(sieve_core_t *h, int32_t *pool_slots, int32_t *keep_leaves, int32_t *free_slots);
 int sieve_elided_count(sieve_core_t *h, uint64_t *out); /* dirty nodes not recomputed so far */
 
 /* ---- max-sum pass: maximum-likelihood genotypes and dropout states (variant calling) --------------------------------

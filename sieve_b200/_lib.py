@@ -73,6 +73,7 @@ SIGNATURES = {
     "sieve_get_result_device_ptr": (C.c_int, [_vp, C.POINTER(_vp)]),
     "sieve_get_node_partials": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp]),
     "sieve_set_elision": (C.c_int, [_vp, C.c_int32]),
+    "sieve_sparse_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sieve_elided_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "sieve_ml_trace": (C.c_int, [_vp]),
     "sieve_ml_call": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

@@ -190,6 +190,12 @@ class ScsCudaLikelihoodCore:
         """Skip dirty nodes whose inputs did not change (see include/sieve_b200.h, "Change tracking")."""
         check(self.L.sieve_set_elision(self.h, 1 if on else 0))
 
+    def sparse_info(self):
+        """-> dict(pool_slots, keep_leaves, free_slots) (keep_leaves == 0 for a dense core)."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.L.sieve_sparse_info(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"pool_slots": int(a.value), "keep_leaves": int(b.value), "free_slots": int(c.value)}
+
     def elided_count(self):
         v = C.c_uint64()
         check(self.L.sieve_elided_count(self.h, C.byref(v)))

@@ -44,8 +44,9 @@ struct PendingMatrix {
     int slot;
     int reuse = 0;    // host mirror of the matrix: 0 = compute, 1 = the slot already holds these values, 2 = copy the twin slot's
     int skip = 0;     // not uploaded: superseded, or (change tracking) nothing new
-    int is_distance;  // v[0..K) are branch distances (length * branch rate * category rate) instead of K matrices
-    double v[SV_KMAX * 16];
+    int is_distance;  // the values are K branch distances (length * branch rate * category rate) instead of K matrices
+    size_t off;       // its values in sieve_core::pending_vals (K doubles or K * 16): the entries stay small, a whole-tree
+                      // update of 10 000 cells queues 20 000 of them per proposal
 };
 
 struct sieve_core {
@@ -98,6 +99,7 @@ struct sieve_core {
     std::vector<int> pending_levels;  // offsets into pending_ops, empty == one group
     bool pending_per_level = false;
     std::vector<PendingMatrix> pending_mats;
+    std::vector<double> pending_vals;
     int root = -1, root_genotype = 0, const_genotype = 0;
     double prop[4] = {0.25, 0.25, 0.25, 0.25};
     sieve_leaf_params_t lp{};
@@ -844,12 +846,17 @@ extern "C" int sieve_set_node_matrix_for_update(sieve_core_t* h, int32_t node) {
 }
 
 static PendingMatrix* sv_pending_matrix(sieve_core* h, int slot) {
+    // (an earlier DISTANCE entry for the slot only has room for K doubles: it is superseded by a new matrix entry)
     for (auto it = h->pending_mats.rbegin(); it != h->pending_mats.rend(); ++it)
-        if (it->slot == slot) return &*it;
+        if (it->slot == slot) {
+            if (it->is_distance) break;
+            return &*it;
+        }
     PendingMatrix pm;
     pm.slot = slot;
     pm.is_distance = 0;
-    memset(pm.v, 0, sizeof(pm.v));
+    pm.off = h->pending_vals.size();
+    h->pending_vals.resize(pm.off + (size_t)SV_KMAX * 16, 0.0);
     h->pending_mats.push_back(pm);
     return &h->pending_mats.back();
 }
@@ -860,12 +867,12 @@ extern "C" int sieve_set_node_matrix(sieve_core_t* h, int32_t node, int32_t cate
     // the K categories of one node arrive one by one (ScsTreeLikelihood.java:567-578); they share a pending entry
     PendingMatrix* pm = nullptr;
     const int slot = h->cur_mat[node] * h->n_nodes + node;
-    if (!h->pending_mats.empty() && h->pending_mats.back().slot == slot)
+    if (!h->pending_mats.empty() && h->pending_mats.back().slot == slot && !h->pending_mats.back().is_distance)
         pm = &h->pending_mats.back();
     else
         pm = sv_pending_matrix(h, slot);
     pm->is_distance = 0;
-    memcpy(pm->v + category * 16, p16, 16 * sizeof(double));
+    memcpy(h->pending_vals.data() + pm->off + category * 16, p16, 16 * sizeof(double));
     return SIEVE_OK;
 }
 
@@ -879,7 +886,8 @@ extern "C" int sieve_set_matrices(sieve_core_t* h, int32_t count, const int32_t*
         PendingMatrix pm;
         pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
         pm.is_distance = 0;
-        memcpy(pm.v, P + (size_t)i * K * 16, sizeof(double) * K * 16);
+        pm.off = h->pending_vals.size();
+        h->pending_vals.insert(h->pending_vals.end(), P + (size_t)i * K * 16, P + (size_t)(i + 1) * K * 16);
         h->pending_mats.push_back(pm);
     }
     return SIEVE_OK;
@@ -893,17 +901,14 @@ extern "C" int sieve_set_distances(sieve_core_t* h, int32_t count, const int32_t
     for (int i = 0; i < count; i++) {
         SV_REQUIRE(sv_node_ok(h, nodes[i]), "sieve_set_distances: bad node");
         if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
-        h->pending_mats.emplace_back();  // filled in place: only the first K of its 64 doubles are touched
-        PendingMatrix& pm = h->pending_mats.back();
+        for (int k = 0; k < K; k++)
+            if (!(distances[(size_t)i * K + k] >= 0.0)) return sv_fail(SIEVE_ERR_INVALID, "sieve_set_distances: negative distance");
+        PendingMatrix pm;
         pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
         pm.is_distance = 1;
-        for (int k = 0; k < K; k++) {
-            if (!(distances[(size_t)i * K + k] >= 0.0)) {
-                h->pending_mats.pop_back();
-                return sv_fail(SIEVE_ERR_INVALID, "sieve_set_distances: negative distance");
-            }
-            pm.v[k] = distances[(size_t)i * K + k];
-        }
+        pm.off = h->pending_vals.size();
+        h->pending_vals.insert(h->pending_vals.end(), distances + (size_t)i * K, distances + (size_t)(i + 1) * K);
+        h->pending_mats.push_back(pm);
     }
     return SIEVE_OK;
 }
@@ -988,13 +993,14 @@ static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
 // the host in the same double buffers as the partials, refreshed for the nodes an update recomputes.
 static void sv_host_matrix(sieve_core* h, const PendingMatrix& pm) {
     const int K = h->K;
+    const double* pv = h->pending_vals.data() + pm.off;
     double* dst = h->hP.data() + (size_t)pm.slot * SV_KMAX * 16;
     static const double P1[16] = {3, 6, -3, -6, 1, 2, -1, -2, -1, -2, 1, 2, -1, -2, 1, 2};     // 8 Pi1
     static const double P2[16] = {9, -18, 3, 6, -3, 6, -1, -2, 1, -2, 11, -10, 1, -2, -5, 6};  // 16 Pi2
     for (int k = 0; k < K; k++) {
         double d = 0.0, q1 = 0.0, q2 = 0.0;
         if (pm.is_distance) {
-            d = pm.v[k];
+            d = pv[k];
             const double g1 = expm1(-0.2 * d);  // expm1(-0.4 d) = g1 (g1 + 2)
             q1 = g1 / 8.0;
             q2 = g1 * (g1 + 2.0) / 16.0;
@@ -1005,7 +1011,7 @@ static void sv_host_matrix(sieve_core* h, const PendingMatrix& pm) {
                 v = ((e % 5 == 0) ? 1.0 : 0.0) + q1 * P1[e] + q2 * P2[e];
                 if (d == 0.0) v = (e % 5 == 0) ? 1.0 : 0.0;
             } else
-                v = pm.v[k * 16 + e];
+                v = pv[k * 16 + e];
             if (h->log_mode) v = v > 0.0 ? v : SV_MIN_VALUE;
             dst[k * 16 + e] = v;
         }
@@ -1122,7 +1128,7 @@ static int sv_plan_resident_ops(sieve_core* h) {
             return c;
         };
         int T = std::max(h->keep_T, 1);
-        while (2 * (long long)kept_count(T) + 64 > h->pool_slots && T < (1 << 28)) T *= 2;
+        while (2 * (long long)kept_count(T) + 64 > h->pool_slots && T < (1 << 28)) T += std::max(1, T / 4);
         if (T != h->keep_T || h->sparse_recheck) {
             h->keep_T = T;
             for (int v = n; v < N; v++)
@@ -1650,6 +1656,7 @@ static int sv_flush(sieve_core* h) {
         for (size_t i = 0; i < h->pending_mats.size(); i++) last_idx[h->pending_mats[i].slot] = (int)i;
         for (size_t i = 0; i < h->pending_mats.size(); i++) {
             PendingMatrix& pm = h->pending_mats[i];
+            const double* pv = h->pending_vals.data() + pm.off;
             pm.skip = 0;
             if (last_idx[pm.slot] != (int)i) {
                 pm.skip = 1;  // superseded by a later entry for the same slot
@@ -1664,7 +1671,7 @@ static int sv_flush(sieve_core* h) {
                 return h->mat_mirror.data() + (size_t)sl * SV_KMAX * 16;
             };
             auto same = [&](int sl) {
-                return h->mat_ver[sl] != 0 && h->mat_mirror_q[sl] == (char)pm.is_distance && memcmp(mirror(sl), pm.v, len) == 0;
+                return h->mat_ver[sl] != 0 && h->mat_mirror_q[sl] == (char)pm.is_distance && memcmp(mirror(sl), pv, len) == 0;
             };
             pm.reuse = same(pm.slot) ? 1 : (same(other) ? 2 : 0);
             if (h->elide && pm.reuse == 1) {
@@ -1679,12 +1686,12 @@ static int sv_flush(sieve_core* h) {
             h->slot_is_q[pm.slot] = pm.is_distance ? 1 : 0;
             char z = 0;
             if (pm.is_distance)
-                for (int k = 0; k < K; k++) z |= pm.v[k] == 0.0;
+                for (int k = 0; k < K; k++) z |= pv[k] == 0.0;
             h->slot_zero[pm.slot] = z;
             if (pm.reuse == 2) h->mat_ver[pm.slot] = h->mat_ver[other];
             if (pm.reuse == 0) h->mat_ver[pm.slot] = ++h->ver_counter;
             h->mat_mirror_q[pm.slot] = (char)pm.is_distance;
-            memcpy(mirror(pm.slot), pm.v, len);
+            memcpy(mirror(pm.slot), pv, len);
         }
     }
     if (h->ephemeral)
@@ -1697,6 +1704,7 @@ static int sv_flush(sieve_core* h) {
         if (!pm.skip) (pm.is_distance ? nd : nm)++;
     if (nm == 0 && nd == 0 && no == 0) {
         h->pending_mats.clear();
+        h->pending_vals.clear();
         h->g_nodes.clear();
         return SIEVE_OK;
     }
@@ -1715,10 +1723,10 @@ static int sv_flush(sieve_core* h) {
     for (const PendingMatrix& pm : h->pending_mats) {
         if (pm.skip) continue;
         if (pm.is_distance) {
-            memcpy(h->h_stage + off_dv + id * K * sizeof(double), pm.v, K * sizeof(double));
+            memcpy(h->h_stage + off_dv + id * K * sizeof(double), h->pending_vals.data() + pm.off, K * sizeof(double));
             ((int*)(h->h_stage + off_ds))[id++] = pm.slot;
         } else {
-            memcpy(h->h_stage + off_mv + im * K * 16 * sizeof(double), pm.v, K * 16 * sizeof(double));
+            memcpy(h->h_stage + off_mv + im * K * 16 * sizeof(double), h->pending_vals.data() + pm.off, K * 16 * sizeof(double));
             ((int*)(h->h_stage + off_ms))[im++] = pm.slot;
         }
     }
@@ -1758,6 +1766,7 @@ static int sv_flush(sieve_core* h) {
     h->g_nodes.clear();
     if (!h->pending_ops.empty() || !h->pending_mats.empty()) h->ml_ready = false;
     h->pending_mats.clear();
+    h->pending_vals.clear();
     h->pending_ops.clear();
     h->pending_levels.clear();
     h->pending_per_level = false;
@@ -2417,6 +2426,14 @@ extern "C" int sieve_background_log_likelihood(int32_t device, const int64_t* va
 }
 
 // ---- instrumentation ------------------------------------------------------------------------------------------
+extern "C" int sieve_sparse_info(sieve_core_t* h, int32_t* pool_slots, int32_t* keep_leaves, int32_t* free_slots) {
+    SV_REQUIRE(h, "null handle");
+    if (pool_slots) *pool_slots = h->pool_slots;
+    if (keep_leaves) *keep_leaves = h->sparse ? h->keep_T : 0;
+    if (free_slots) *free_slots = h->sparse ? (int32_t)h->free_slots.size() : 0;
+    return SIEVE_OK;
+}
+
 extern "C" int sieve_set_elision(sieve_core_t* h, int32_t on) {
     SV_REQUIRE(h, "null handle");
     h->elide = on != 0;
