@@ -26,7 +26,9 @@ public class ScsCudaLikelihoodCore extends ScsBeerLikelihoodCore {
                            int stateCount, boolean integrateCategories, boolean useLogPartials) {
         this.patternCount = patternCount;
         int flags = (useLogPartials ? SieveB200.FLAG_LOG_PARTIALS : 0) | SieveB200.FLAG_CONST_PARTIALS
-                | SieveB200.FLAG_SINGLE_ADO;
+                | SieveB200.FLAG_SINGLE_ADO
+                | (Boolean.getBoolean("sieve.b200.sparse") ? SieveB200.FLAG_SPARSE : 0)        // 10 000-cell data sets
+                | (Boolean.getBoolean("sieve.b200.streamed") ? SieveB200.FLAG_EPHEMERAL : 0);  // beyond that
         h = SieveB200.create(leafNodeCount, patternCount, matrixCount, stateCount, flags,
                 Integer.getInteger("sieve.b200.device", 0));
     }

@@ -12,7 +12,7 @@ public final class SieveB200 {
 
     private SieveB200() {}
 
-    public static final int FLAG_LOG_PARTIALS = 1, FLAG_CONST_PARTIALS = 2, FLAG_SINGLE_ADO = 4;
+    public static final int FLAG_LOG_PARTIALS = 1, FLAG_CONST_PARTIALS = 2, FLAG_SINGLE_ADO = 4, FLAG_EPHEMERAL = 8, FLAG_SPARSE = 16;
     public static final int UPDATE_FLIP = 1, UPDATE_PER_LEVEL = 2;
 
     /** sieve_create; returns the opaque handle; throws RuntimeException(sieve_last_error()) on failure */

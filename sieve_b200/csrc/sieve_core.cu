@@ -2268,8 +2268,9 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->eph_c2_stored = h->eph_c2;
     h->valid_stored = h->valid;
     h->log_c_stored = h->log_c;
-    h->ver_stored = h->ver_cur;
-    h->fp_stored = h->fp_cur;
+    // (only internal nodes carry a value version / provenance: leaves are versioned per buffer)
+    std::copy(h->ver_cur.begin() + h->n, h->ver_cur.end(), h->ver_stored.begin() + h->n);
+    std::copy(h->fp_cur.begin() + h->n, h->fp_cur.end(), h->fp_stored.begin() + h->n);
     if (h->sparse)  // what only the previous stored state referred to gives its slot back
         for (int v = h->n; v < h->n_nodes; v++) sv_slot_release(h, 1 - h->cur_part[v], v);
     return SIEVE_OK;
