@@ -25,6 +25,20 @@ def test_every_declared_symbol_is_exported_and_bound(L):
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 
+def test_mcmc_header_symbols_are_exported(L):
+    import os
+    header = open(os.path.join(os.path.dirname(_lib.HEADER_PATH), "sieve_b200_mcmc.h")).read()
+    declared = set(re.findall(r"\b(sieve_[a-z_0-9]+)\s*\(", header))
+    assert {"sieve_mcmc_create", "sieve_mcmc_run", "sieve_gamma_category_rates"} <= declared
+    for name in sorted(declared):
+        assert hasattr(L, name), "missing export: " + name
+    # the discrete-gamma rates of the driver (no device needed) equal the host mirror's
+    from sieve_b200 import substmodel
+    from sieve_b200.mcmc import gamma_category_rates
+    for shape in (0.3, 1.0, 2.5):
+        np.testing.assert_allclose(gamma_category_rates(shape, 4), substmodel.gamma_category_rates(shape, 4)[0], rtol=1e-9)
+
+
 def test_no_device_is_a_loud_error_not_a_fallback(L):
     import torch
     if torch.cuda.is_available():
