@@ -303,14 +303,15 @@ def main():
     torch.cuda.synchronize()
 
     counts_host = None
-    if args.sparse:
+    via_host = args.sparse or n * S * 16 > 40e9   # (also when two copies of the counts would not fit next to the pools)
+    if via_host:
         # a sparse core sizes its partial pool from the memory that is free when it is created: give the generator's
         # memory back first and load the counts from the host (as a production run would, from the ingest shard file)
         counts_host = counts_dev.cpu().numpy()
         del counts_dev
         torch.cuda.empty_cache()
     core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local, ephemeral=args.streamed, sparse=args.sparse)
-    if args.sparse:
+    if via_host:
         core.set_counts_cellmajor(counts_host)
         counts_dev = torch.from_numpy(counts_host[:, :min(S, 4096), :].copy()).to(dev)   # only the sample below is read
         del counts_host

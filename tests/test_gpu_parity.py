@@ -627,13 +627,14 @@ def test_change_tracking_skips_unchanged_nodes_bit_identically(core_mod, oracle,
     d = synthetic(60, 280, seed=101)
     counts, tree = d["counts"], d["tree"]
     runs, elided = {}, {}
-    for T in ("8", "0"):
-        monkeypatch.setenv("SIEVE_B200_TRANSIENT_LEAVES", T)
+    for T in ("8", "0", "8m"):
+        monkeypatch.setenv("SIEVE_B200_TRANSIENT_LEAVES", T[0])
         for on in (True, False):
             rng = np.random.default_rng(17)
             br0 = rng.lognormal(0.0, 0.2, size=tree.node_count)
+            # "8m": the plugin hands over 16-double matrices instead of distances (content compare of whole matrices)
             tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=4000.0,
-                                   branch_rates=br0)
+                                   branch_rates=br0, use_distances=not T.endswith("m"))
             tl.core.set_elision(on)
             out = [tl.calculate_logp()]
             for it in range(24):
@@ -664,7 +665,7 @@ def test_change_tracking_skips_unchanged_nodes_bit_identically(core_mod, oracle,
             runs[(T, on)] = out
             elided[(T, on)] = tl.core.elided_count()
             tl.close()
-    for T in ("8", "0"):
+    for T in ("8", "0", "8m"):
         for a, b in zip(runs[(T, True)], runs[(T, False)]):
             np.testing.assert_array_equal(a, b)
         assert elided[(T, False)] == 0
