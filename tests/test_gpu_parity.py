@@ -729,19 +729,22 @@ def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatc
     # the native MCMC driver on a sparse core (topology moves included)
     S, n = counts.shape[:2]
     monkeypatch.setenv("SIEVE_B200_POOL_SLOTS", "120")
-    finals = {}
-    for sparse in (False, True):
-        c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True, sparse=sparse)
-        c.set_counts(counts)
-        c.compute_size_factors(0)
-        mc = McmcReplay(c, tree, mix="relaxed2", asc_mode="felsenstein_mean", n_background_sites=5000.0, seed=5)
-        st = mc.run(300)
-        again = mc.full_recompute()
-        assert abs(again - st["log_p"]) <= 1e-11 * abs(again)
-        finals[sparse] = (st["log_p"], st["accepted"])
-        mc.close()
-        c.close()
-    assert finals[True] == finals[False]
+    for mix, states in (("relaxed2", 300), ("stage1", 500)):
+        finals = {}
+        for sparse, elide in ((False, False), (False, True), (True, True)):
+            c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True, sparse=sparse)
+            c.set_elision(elide)
+            c.set_counts(counts)
+            c.compute_size_factors(0)
+            mc = McmcReplay(c, tree, mix=mix, asc_mode="felsenstein_mean", n_background_sites=5000.0, seed=5)
+            st = mc.run(states)
+            again = mc.full_recompute()
+            assert abs(again - st["log_p"]) <= 1e-11 * abs(again)
+            finals[(sparse, elide)] = (st["log_p"], st["accepted"])
+            mc.close()
+            c.close()
+        # the chain is a deterministic function of the likelihood values: any difference anywhere changes its course
+        assert finals[(True, True)] == finals[(False, True)] == finals[(False, False)], (mix, finals)
     # misuse is loud
     c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, False, True, sparse=True)
     with pytest.raises(RuntimeError):
