@@ -273,6 +273,7 @@ def main():
     ap.add_argument("--mcmc-states", type=int, default=400, help="proposals per operator mix in the MCMC replay (0 = skip)")
     ap.add_argument("--streamed", action="store_true", help="SIEVE_FLAG_EPHEMERAL: no resident partials (shapes that exceed HBM, e.g. SIEVE_BENCH_CELLS=10000 SIEVE_BENCH_SITES=125000)")
     ap.add_argument("--sparse", action="store_true", help="SIEVE_FLAG_SPARSE: leaves resident, only the larger subtrees keep their partials (10 000-cell shapes)")
+    ap.add_argument("--single-leaf-buffer", action="store_true", help="SIEVE_FLAG_SINGLE_LEAF_BUFFER: leaves are not double-buffered (rejected leaf-parameter proposals recompute them)")
     ap.add_argument("--no-variants", action="store_true", help="skip the max-sum (variant calling) timing")
     ap.add_argument("--matrices", action="store_true", help="hand the core 16-double matrices (generic kernel) instead of branch distances")
     args = ap.parse_args()
@@ -310,7 +311,8 @@ def main():
         counts_host = counts_dev.cpu().numpy()
         del counts_dev
         torch.cuda.empty_cache()
-    core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local, ephemeral=args.streamed, sparse=args.sparse)
+    core = ScsCudaLikelihoodCore(n, S, K_CAT, 4, True, True, True, local, ephemeral=args.streamed, sparse=args.sparse,
+                                 single_leaf_buffer=args.single_leaf_buffer)
     if via_host:
         core.set_counts_cellmajor(counts_host)
         counts_dev = torch.from_numpy(counts_host[:, :min(S, 4096), :].copy()).to(dev)   # only the sample below is read

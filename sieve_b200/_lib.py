@@ -9,7 +9,7 @@ SO_PATH = os.environ.get("SIEVE_B200_LIB") or os.path.join(_HERE, "libsieve_b200
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sieve_b200.h")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, 1, 2, 3, 4
-FLAG_LOG_PARTIALS, FLAG_CONST_PARTIALS, FLAG_SINGLE_ADO, FLAG_EPHEMERAL, FLAG_SPARSE = 1, 2, 4, 8, 16
+FLAG_LOG_PARTIALS, FLAG_CONST_PARTIALS, FLAG_SINGLE_ADO, FLAG_EPHEMERAL, FLAG_SPARSE, FLAG_SINGLE_LEAF_BUFFER = 1, 2, 4, 8, 16, 32
 UPDATE_FLIP, UPDATE_PER_LEVEL = 1, 2
 ASC_NONE, ASC_FELSENSTEIN_MEAN, ASC_FELSENSTEIN_GEOMETRIC, ASC_LEWIS = 0, 1, 2, 3
 ASC_MODES = {"none": 0, "felsenstein_mean": 1, "felsenstein_geometric": 2, "lewis": 3}

@@ -24,7 +24,7 @@ def _iptr(a):
 
 class ScsCudaLikelihoodCore:
     def __init__(self, n_leaves, n_sites, n_categories=4, n_states=4, use_log_partials=True, asc_bias=False,
-                 single_ado=True, device=-1, ephemeral=False, sparse=False):
+                 single_ado=True, device=-1, ephemeral=False, sparse=False, single_leaf_buffer=False):
         """initialize(nodeCount = 2n, leafCount = n, internalCount = n, patternCount, matrixCount, stateCount, ...)
         (likelihood/ScsBeerLikelihoodCore.java:91-128)."""
         self.L = _lib.lib()
@@ -34,7 +34,7 @@ class ScsCudaLikelihoodCore:
         self.asc_bias = bool(asc_bias)
         flags = (FLAG_LOG_PARTIALS if use_log_partials else 0) | (FLAG_CONST_PARTIALS if asc_bias else 0) | \
                 (FLAG_SINGLE_ADO if single_ado else 0) | (FLAG_EPHEMERAL if ephemeral else 0) | \
-                (FLAG_SPARSE if sparse else 0)
+                (FLAG_SPARSE if sparse else 0) | (_lib.FLAG_SINGLE_LEAF_BUFFER if single_leaf_buffer else 0)
         cfg = _lib.Config(self.n, self.S, self.K, self.G, flags, device)
         h = C.c_void_p()
         check(self.L.sieve_create(C.byref(cfg), C.byref(h)))

@@ -160,6 +160,11 @@ struct sieve_core {
     // to); smaller subtrees are recomputed from the resident leaves when an update needs them, through temporary slots
     // that are recycled inside the walk.  Dense cores use the same code with a fixed identity mapping.
     bool sparse = false, sparse_recheck = true;
+    // SIEVE_FLAG_SINGLE_LEAF_BUFFER: one leaf buffer instead of two.  A leaf-parameter proposal overwrites the leaves; if it is
+    // rejected, sieve_restore recomputes them from the stored parameters (same kernel, same bits) instead of flipping back.
+    bool single_leaf = false, leaf_changed_since_store = false;
+    sieve_leaf_params_t stored_lp{};
+    uint64_t leaf_ver_stored = 0;
     int pool_slots = 0;
     int keep_T = 0;
     std::vector<int> slot_of;      // [2 * n_nodes] physical slot of (buffer, node), -1 = none
@@ -318,11 +323,13 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         leaf_bufs = 1;
     }
     h->sparse = (cfg->flags & SIEVE_FLAG_SPARSE) && !h->ephemeral;
+    h->single_leaf = (cfg->flags & SIEVE_FLAG_SINGLE_LEAF_BUFFER) && !h->ephemeral;
+    if (h->single_leaf) leaf_bufs = 1;
     if (h->sparse) {
         // everything but the internal partials is resident as usual; the pool takes what is left (minus head room)
         size_t free0 = 0, total0 = 0;
         cudaMemGetInfo(&free0, &total0);
-        const size_t fixed = n * S * 16 + 2 * n * S * (40 + (algebraic ? 8 : 0)) + ((size_t)3 << 30);
+        const size_t fixed = n * S * 16 + leaf_bufs * n * S * (40 + (algebraic ? 8 : 0)) + ((size_t)3 << 30);
         const size_t per_slot = S * (SV_KMAX * 32 + 8) * (twin ? 2 : 1);
         size_t slots = free0 > fixed ? (free0 - fixed) / per_slot : 0;
         if (const char* e = getenv("SIEVE_B200_POOL_SLOTS")) slots = (size_t)std::max(0, atoi(e));
@@ -772,10 +779,11 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
         h->eph_leaves_dirty = true;
         return SIEVE_OK;
     }
-    if (for_update) h->cur_leaf = 1 - h->cur_leaf;
+    if (for_update && !h->single_leaf) h->cur_leaf = 1 - h->cur_leaf;
     h->ml_ready = false;
     h->leaf_ver[h->cur_leaf] = ++h->ver_counter;
     if (!for_update) h->leaf_ver[1 - h->cur_leaf] = h->leaf_ver[h->cur_leaf];
+    if (h->single_leaf) h->leaf_changed_since_store = true;
     if (h->timing) {
         SV_CUDA(cudaEventRecord(h->ev[0], h->stream));
     }
@@ -784,7 +792,7 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
         SV_CUDA(cudaEventRecord(h->ev[1], h->stream));
         h->leaf_timed = true;
     }
-    if (!for_update) {
+    if (!for_update && !h->single_leaf) {
         // initialisation: both buffers hold the leaves (storeLeafPartials, ScsBeerLikelihoodCore.java:437-445)
         const size_t nx = (size_t)h->n * h->S * 4, ns = (size_t)h->n * h->S;
         SV_CUDA(cudaMemcpyAsync(h->d_leafX + (size_t)(1 - h->cur_leaf) * nx, h->d_leafX + (size_t)h->cur_leaf * nx,
@@ -2264,6 +2272,9 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->stored_part = h->cur_part;
     h->stored_mat = h->cur_mat;
     h->stored_leaf = h->cur_leaf;
+    h->stored_lp = h->tab_lp;  // the parameters the current leaves were computed with
+    h->leaf_ver_stored = h->leaf_ver[h->cur_leaf];
+    h->leaf_changed_since_store = false;
     h->eph_c1_stored = h->eph_c1;
     h->eph_c2_stored = h->eph_c2;
     h->valid_stored = h->valid;
@@ -2275,8 +2286,20 @@ extern "C" int sieve_store(sieve_core_t* h) {
         for (int v = h->n; v < h->n_nodes; v++) sv_slot_release(h, 1 - h->cur_part[v], v);
     return SIEVE_OK;
 }
+// single leaf buffer: a rejected leaf-parameter proposal has overwritten the leaves -- put the stored state's back
+static int sv_leaves_back_to_stored(sieve_core* h) {
+    if (!h->single_leaf || !h->leaf_changed_since_store) return SIEVE_OK;
+    SV_CUDA(cudaSetDevice(h->device));
+    h->lp = h->stored_lp;  // the state's parameters are the stored ones again
+    SV_TRY(sv_launch_leaves(h, 0, h->S, h->S));
+    h->leaf_ver[h->cur_leaf] = h->leaf_ver_stored;  // same parameters, same kernel: the same bits as before the proposal
+    h->leaf_changed_since_store = false;
+    return SIEVE_OK;
+}
+
 extern "C" int sieve_unstore(sieve_core_t* h) {
     SV_REQUIRE(h, "null handle");
+    SV_TRY(sv_leaves_back_to_stored(h));
     h->cur_part = h->stored_part;
     h->cur_mat = h->stored_mat;
     h->cur_leaf = h->stored_leaf;
@@ -2292,6 +2315,7 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
 }
 extern "C" int sieve_restore(sieve_core_t* h) {
     SV_REQUIRE(h, "null handle");
+    SV_TRY(sv_leaves_back_to_stored(h));
     h->cur_part.swap(h->stored_part);
     h->cur_mat.swap(h->stored_mat);
     std::swap(h->cur_leaf, h->stored_leaf);

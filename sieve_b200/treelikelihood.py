@@ -34,7 +34,7 @@ class ScsTreeLikelihood:
     def __init__(self, counts, tree, size_factors=None, leaf_params=None, gamma_shape=1.0, n_categories=4,
                  clock_rate=1.0, branch_rates=None, use_log_partials=True, asc_mode="none", n_background_sites=0.0,
                  weights=None, single_ado=True, device=-1, return_const_sum=False, use_distances=True, ephemeral=False,
-                 sparse=False):
+                 sparse=False, single_leaf_buffer=False):
         counts = np.asarray(counts)
         self.S, self.n = counts.shape[0], counts.shape[1]
         assert tree.n == self.n, "The number of nodes in the tree does not match the number of sequences"
@@ -50,7 +50,7 @@ class ScsTreeLikelihood:
         # True: hand the core branch distances (fast path for the fixed rate matrix); False: 16-double matrices
         self.use_distances = use_distances
         self.core = ScsCudaLikelihoodCore(self.n, self.S, n_categories, 4, use_log_partials, asc_mode != "none",
-                                          single_ado, device, ephemeral, sparse)
+                                          single_ado, device, ephemeral, sparse, single_leaf_buffer)
         self.core.set_counts(counts)
         self.core.set_pattern_weights(weights)
         if size_factors is None:

@@ -685,13 +685,14 @@ def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatc
     d = synthetic(150, 200, seed=111)
     counts, tree = d["counts"], d["tree"]
     runs = {}
-    for tag, sparse, slots in (("dense", False, None), ("sparse", True, "110"), ("sparse_tight", True, "96")):
+    for tag, sparse, slots in (("dense", False, None), ("sparse", True, "110"), ("sparse_tight", True, "96"),
+                               ("sparse_single_leaf", True, "110"), ("dense_single_leaf", False, None)):
         if slots:
             monkeypatch.setenv("SIEVE_B200_POOL_SLOTS", slots)
         rng = np.random.default_rng(23)
         br0 = rng.lognormal(0.0, 0.2, size=tree.node_count)
         tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=4000.0,
-                               branch_rates=br0, sparse=sparse)
+                               branch_rates=br0, sparse=sparse, single_leaf_buffer=tag.endswith("single_leaf"))
         out = [tl.calculate_logp()]
         for it in range(30):
             tl.store()
@@ -723,7 +724,7 @@ def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatc
         out.append(tl.pattern_log_likelihoods()[1].copy())
         runs[tag] = out
         tl.close()
-    for tag in ("sparse", "sparse_tight"):
+    for tag in ("sparse", "sparse_tight", "sparse_single_leaf", "dense_single_leaf"):
         for a, b in zip(runs[tag], runs["dense"]):
             np.testing.assert_array_equal(a, b)
     # the native MCMC driver on a sparse core (topology moves included)
@@ -731,8 +732,8 @@ def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatc
     monkeypatch.setenv("SIEVE_B200_POOL_SLOTS", "120")
     for mix, states in (("relaxed2", 300), ("stage1", 500)):
         finals = {}
-        for sparse, elide in ((False, False), (False, True), (True, True)):
-            c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True, sparse=sparse)
+        for sparse, elide, single in ((False, False, False), (False, True, False), (True, True, False), (True, True, True)):
+            c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True, sparse=sparse, single_leaf_buffer=single)
             c.set_elision(elide)
             c.set_counts(counts)
             c.compute_size_factors(0)
@@ -740,11 +741,11 @@ def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatc
             st = mc.run(states)
             again = mc.full_recompute()
             assert abs(again - st["log_p"]) <= 1e-11 * abs(again)
-            finals[(sparse, elide)] = (st["log_p"], st["accepted"])
+            finals[(sparse, elide, single)] = (st["log_p"], st["accepted"])
             mc.close()
             c.close()
         # the chain is a deterministic function of the likelihood values: any difference anywhere changes its course
-        assert finals[(True, True)] == finals[(False, True)] == finals[(False, False)], (mix, finals)
+        assert len(set(finals.values())) == 1, (mix, finals)
     # misuse is loud
     c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, False, True, sparse=True)
     with pytest.raises(RuntimeError):
