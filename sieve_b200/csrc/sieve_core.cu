@@ -356,7 +356,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->valid_stored.assign(h->n_nodes, 0);
     if (const char* e = getenv("SIEVE_B200_TRANSIENT_LEAVES")) h->transient_T = std::max(0, atoi(e));
     h->keep_T = std::max(1, h->transient_T);
-    if ((2 * n + 2) * pool_sites >= ((size_t)1 << 32) || part_slots * pool_sites + 2 * n + 2 >= ((size_t)1 << 32)) {
+    if ((leaf_bufs * n + 2) * pool_sites >= ((size_t)1 << 32) || part_slots * pool_sites + 2 * n + 2 >= ((size_t)1 << 32)) {
         g_err = "sieve_create: more than 2^32 (slot, site) rows per pool; use SIEVE_FLAG_EPHEMERAL (streamed evaluation)";
         return fail(SIEVE_ERR_OOM);
     }
