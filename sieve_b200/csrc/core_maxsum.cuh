@@ -1,0 +1,277 @@
+// core_maxsum.cuh -- host side of the max-sum pass (kernels: maxsum.cuh): sieve_ml_trace and its getters.
+// Included by sieve_core.cu only.
+#pragma once
+// ---- max-sum pass: maximum-likelihood genotypes for variant calling (maxsum.cuh) --------------------------------
+// Post-order list of the whole current tree from the children the core has recorded (the planner's map).
+static int sv_ml_build_ops(sieve_core* h, std::vector<SvMlOp>& ops) {
+    const int n = h->n;
+    if (h->root < 0) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: sieve_set_root has not been called");
+    std::vector<std::pair<int, int>> st;
+    st.push_back({h->root, 0});
+    while (!st.empty()) {
+        auto [v, state] = st.back();
+        st.pop_back();
+        if (v < n) continue;
+        const int a = h->eph_c1[v], b = h->eph_c2[v];
+        if (a == -2) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: the tree has a node that was never computed");
+        if (state == 0) {
+            st.push_back({v, 1});
+            if (b >= 0) st.push_back({b, 0});
+            st.push_back({a, 0});
+        } else {
+            SvMlOp op{};
+            op.dst = v - n;
+            op.n1 = a;
+            op.c1 = a < n ? a : a - n;
+            if (a < n) op.flags |= SV_OP_LEAF1;
+            if (b < 0) {
+                op.flags |= SV_OP_UNARY;
+                op.c2 = -1;
+                op.n2 = 0;
+            } else {
+                op.n2 = b;
+                op.c2 = b < n ? b : b - n;
+                if (b < n) op.flags |= SV_OP_LEAF2;
+            }
+            ops.push_back(op);
+        }
+    }
+    return SIEVE_OK;
+}
+
+static int sv_ml_require(sieve_core* h, const char* who) {
+    if (!h) return sv_fail(SIEVE_ERR_INVALID, std::string(who) + ": null handle");
+    if (!h->ml_ready) return sv_fail(SIEVE_ERR_STATE, std::string(who) + ": call sieve_ml_trace first (and again after any change)");
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_ml_trace(sieve_core_t* h) {
+    SV_REQUIRE(h, "null handle");
+    if (h->ephemeral || h->sparse)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: needs fully resident partials (not SIEVE_FLAG_EPHEMERAL / SIEVE_FLAG_SPARSE)");
+    if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: leaves not computed yet");
+    SV_CUDA(cudaSetDevice(h->device));
+    SV_TRY(sv_flush(h));
+    const size_t n = h->n, S = h->S, K = h->K, N = h->n_nodes, lanes = S * K;
+    std::vector<SvMlOp> ops;
+    SV_TRY(sv_ml_build_ops(h, ops));
+    SV_REQUIRE(!ops.empty() && ops.back().dst == h->root - (int)n, "sieve_ml_trace: the root is not the last node of the tree");
+    // the root's sum-product partial decides the ML category; make sure it is materialised
+    if (!h->valid[h->root]) {
+        h->demand_list.push_back(h->root);
+        SV_TRY(sv_flush(h));
+    }
+    if (!h->ml_alloc) {
+        SV_TRY(sv_alloc(h, &h->d_mlL, n * S * 4));
+        SV_TRY(sv_alloc(h, &h->d_mlado, n * S));
+        SV_TRY(sv_alloc(h, &h->d_ml, n * lanes * 4));
+        SV_TRY(sv_alloc(h, &h->d_mlback, n * lanes));
+        SV_TRY(sv_alloc(h, &h->d_mlcoll, N * lanes));
+        SV_TRY(sv_alloc(h, &h->d_mladosel, n * lanes));
+        SV_TRY(sv_alloc(h, &h->d_mlamb, lanes));
+        SV_TRY(sv_alloc(h, &h->d_mlcats, S));
+        SV_TRY(sv_alloc(h, &h->d_mllogm, N * K * 16));
+        SV_TRY(sv_alloc(h, &h->d_mlops, n));
+        SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
+        h->ml_alloc = true;
+    }
+    // log P on the host, in double precision with the reference's clamp (ScsBeerLikelihoodCore.java:3100-3101)
+    std::vector<double> mats((size_t)2 * N * SV_KMAX * 16), logm(N * K * 16);
+    SV_CUDA(cudaMemcpyAsync(mats.data(), h->d_mats, mats.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t v = 0; v < N; v++)
+        for (size_t k = 0; k < K; k++)
+            for (int e = 0; e < 16; e++) {
+                const double P = mats[((size_t)h->cur_mat[v] * N + v) * SV_KMAX * 16 + k * 16 + e];
+                logm[(v * K + k) * 16 + e] = std::log(P > 0.0 ? P : SV_MIN_VALUE);
+            }
+    SV_CUDA(cudaMemcpyAsync(h->d_mllogm, logm.data(), logm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SV_CUDA(cudaMemcpyAsync(h->d_mlops, ops.data(), ops.size() * sizeof(SvMlOp), cudaMemcpyHostToDevice, h->stream));
+    h->ml_n_ops = (int)ops.size();
+
+    SvMlLeafArgs la;
+    la.counts = h->d_counts;
+    la.dmA = h->d_dmA;
+    la.dmB = h->d_dmB;
+    la.cellL = h->d_mlcellL;
+    la.size_factors = h->d_sf;
+    la.leafL = h->d_mlL;
+    la.ado = h->d_mlado;
+    la.n_cells = (int)n;
+    la.S = (int)S;
+    la.C = h->C;
+    // the tables on the device were built with tab_lp: the parameters of the leaves that are current
+    la.al = sv_dm_alphas(h->tab_lp.eff_seq_err_rate, h->tab_lp.shape_ctrl1, h->tab_lp.shape_ctrl2);
+    la.cp.t = h->tab_lp.allelic_seq_cov;
+    la.cp.v = h->tab_lp.allelic_seq_cov_raw_var;
+    la.cp.theta = h->tab_lp.ado_rate;
+    la.cp.single_ado = h->single_ado ? 1 : 0;
+    k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
+                                                                                                  (int)n, h->C, la.cp);
+    sv_count(h);
+    k_leaf_ml<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(la);
+    sv_count(h);
+
+    SvMlArgs a;
+    a.ops = h->d_mlops;
+    a.n_ops = h->ml_n_ops;
+    a.leafL = h->d_mlL;
+    a.ado = h->d_mlado;
+    a.logm = h->d_mllogm;
+    a.ml = h->d_ml;
+    a.back = h->d_mlback;
+    a.coll = h->d_mlcoll;
+    a.ado_sel = h->d_mladosel;
+    a.ambiguous = h->d_mlamb;
+    a.S = (int)S;
+    a.K = (int)K;
+    a.n_leaves = (int)n;
+    a.root_genotype = h->root_genotype;
+    const unsigned blocks = (unsigned)((lanes + 127) / 128);
+    k_ml_up<<<blocks, 128, 0, h->stream>>>(a);
+    sv_count(h);
+    k_ml_down<<<blocks, 128, 0, h->stream>>>(a);
+    sv_count(h);
+    const size_t rslot = (size_t)h->cur_part[h->root] * h->n_internal + (h->root - n);
+    k_ml_categories<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(h->d_part + rslot * S * SV_KMAX * 4, (int)S,
+                                                                       (int)K, h->root_genotype, h->d_mlcats);
+    sv_count(h);
+    SV_CUDA(cudaGetLastError());
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    h->ml_ready = true;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_ml_call(sieve_core_t* h, int8_t* genotypes, int8_t* ado, uint8_t* category, uint8_t* ambiguous) {
+    SV_TRY(sv_ml_require(h, "sieve_ml_call"));
+    SV_REQUIRE(genotypes && ado && category && ambiguous, "sieve_ml_call: null output");
+    SV_CUDA(cudaSetDevice(h->device));
+    const size_t n = h->n, S = h->S, N = h->n_nodes;
+    signed char *d_g = nullptr, *d_a = nullptr;
+    unsigned char *d_c = nullptr, *d_m = nullptr;
+    cudaError_t e = cudaMalloc(&d_g, N * S);
+    if (e == cudaSuccess) e = cudaMalloc(&d_a, n * S);
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, S);
+    if (e == cudaSuccess) e = cudaMalloc(&d_m, S);
+    if (e == cudaSuccess) {
+        k_ml_call<<<dim3((unsigned)((S + 255) / 256), (unsigned)N), 256, 0, h->stream>>>(
+            h->d_mlcoll, h->d_mladosel, h->d_mlcats, h->d_mlamb, (int)S, h->K, (int)N, (int)n, d_g, d_a, d_c, d_m);
+        sv_count(h);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(genotypes, d_g, N * S, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ado, d_a, n * S, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(category, d_c, S, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ambiguous, d_m, S, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_g);
+    cudaFree(d_a);
+    cudaFree(d_c);
+    cudaFree(d_m);
+    SV_CUDA(e);
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_ml_get_categories(sieve_core_t* h, uint8_t* out) {
+    SV_TRY(sv_ml_require(h, "sieve_ml_get_categories"));
+    SV_REQUIRE(out, "null output");
+    SV_CUDA(cudaSetDevice(h->device));
+    SV_CUDA(cudaMemcpyAsync(out, h->d_mlcats, (size_t)h->S, cudaMemcpyDeviceToHost, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    return SIEVE_OK;
+}
+
+// Reference layouts: ml_partials [K][S][4] (MLPartials[..][node - nrOfLeafNodes]), back [K][S][4] (one byte per
+// MLGenotypesNodes[..][node][(k, s, parent genotype)]: low nibble = list of child 0, high nibble = list of child 1; for a
+// leaf the byte is the list of arg-max dropout components), collection [K][S] (MLGenotypesCollection).
+extern "C" int sieve_ml_get_node(sieve_core_t* h, int32_t node, double* ml_partials, uint8_t* back, uint8_t* collection) {
+    SV_TRY(sv_ml_require(h, "sieve_ml_get_node"));
+    SV_REQUIRE(sv_node_ok(h, node), "sieve_ml_get_node: bad node");
+    SV_CUDA(cudaSetDevice(h->device));
+    const size_t n = h->n, S = h->S, K = h->K, lanes = S * K;
+    if (collection) {
+        std::vector<unsigned char> c(lanes);
+        SV_CUDA(cudaMemcpyAsync(c.data(), h->d_mlcoll + (size_t)node * lanes, lanes, cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+        for (size_t s = 0; s < S; s++)
+            for (size_t k = 0; k < K; k++) collection[k * S + s] = c[s * K + k];
+    }
+    if ((size_t)node < n) {
+        if (ml_partials) {
+            std::vector<double> v(S * 4);
+            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlL + (size_t)node * S * 4, S * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            SV_CUDA(cudaStreamSynchronize(h->stream));
+            for (size_t k = 0; k < K; k++) memcpy(ml_partials + k * S * 4, v.data(), S * 4 * sizeof(double));
+        }
+        if (back) {
+            std::vector<unsigned short> v(S);
+            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlado + (size_t)node * S, S * sizeof(unsigned short), cudaMemcpyDeviceToHost, h->stream));
+            SV_CUDA(cudaStreamSynchronize(h->stream));
+            for (size_t k = 0; k < K; k++)
+                for (size_t s = 0; s < S; s++)
+                    for (int g = 0; g < 4; g++) back[(k * S + s) * 4 + g] = (uint8_t)((v[s] >> (4 * g)) & 15u);
+        }
+        return SIEVE_OK;
+    }
+    const size_t idx = (size_t)node - n;
+    if (ml_partials) {
+        std::vector<double> v(lanes * 4);
+        SV_CUDA(cudaMemcpyAsync(v.data(), h->d_ml + idx * lanes * 4, lanes * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+        for (size_t s = 0; s < S; s++)
+            for (size_t k = 0; k < K; k++) memcpy(ml_partials + (k * S + s) * 4, v.data() + (s * K + k) * 4, 4 * sizeof(double));
+    }
+    if (back) {
+        std::vector<unsigned> v(lanes);
+        SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlback + idx * lanes, lanes * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+        for (size_t s = 0; s < S; s++)
+            for (size_t k = 0; k < K; k++) memcpy(back + (k * S + s) * 4, &v[s * K + k], 4);
+    }
+    return SIEVE_OK;
+}
+
+// One site, every node: back-pointer bytes [node][K][4] and sum-product log partials [node][K][4] -- what a host needs
+// to enumerate and rank the tied combinations of an ambiguous site (ScsTreeLikelihood.java:2083-2160).
+extern "C" int sieve_ml_get_site(sieve_core_t* h, int32_t site, uint8_t* back, double* log_partials) {
+    SV_TRY(sv_ml_require(h, "sieve_ml_get_site"));
+    SV_REQUIRE(site >= 0 && site < h->S && back && log_partials, "sieve_ml_get_site: bad argument");
+    SV_CUDA(cudaSetDevice(h->device));
+    const int n = h->n, N = h->n_nodes, K = h->K;
+    // every internal partial has to be in memory: recompute the transient ones (once; they stay valid)
+    bool missing = false;
+    for (int v = n; v < N; v++)
+        if (!h->valid[v]) {
+            h->demand_list.push_back(v);
+            missing = true;
+        }
+    if (missing) {
+        const bool keep = h->ml_ready;
+        SV_TRY(sv_flush(h));
+        h->ml_ready = keep;  // recomputing a partial into its buffer changes no value
+    }
+    std::vector<unsigned> rows(N, 0u);
+    for (int v = n; v < N; v++) rows[v] = (unsigned)(((size_t)h->cur_part[v] * h->n_internal + (v - n)) * h->S);
+    unsigned* d_rows = nullptr;
+    unsigned char* d_b = nullptr;
+    double* d_p = nullptr;
+    const size_t cnt = (size_t)N * K * 4;
+    cudaError_t e = cudaMalloc(&d_rows, N * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&d_b, cnt);
+    if (e == cudaSuccess) e = cudaMalloc(&d_p, cnt * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, rows.data(), N * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_ml_site_gather<<<(N * K + 127) / 128, 128, 0, h->stream>>>(h->d_mlback, h->d_mlado, h->d_mlL, h->d_part, h->d_scale,
+                                                                   d_rows, h->S, K, n, N, site, d_b, d_p);
+        sv_count(h);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(back, d_b, cnt, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(log_partials, d_p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_rows);
+    cudaFree(d_b);
+    cudaFree(d_p);
+    SV_CUDA(e);
+    return SIEVE_OK;
+}

@@ -1,0 +1,221 @@
+// core_state.cuh -- the handle behind sieve_core_t and the small host helpers every part of the core uses.
+// Included by sieve_core.cu only (one translation unit); split out for readability.
+#pragma once
+static thread_local std::string g_err;
+
+static int sv_fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define SV_CUDA(call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return sv_fail(SIEVE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+#define SV_REQUIRE(cond, msg) \
+    do {                      \
+        if (!(cond)) return sv_fail(SIEVE_ERR_INVALID, msg); \
+    } while (0)
+
+struct PendingMatrix {
+    int slot;
+    int reuse = 0;    // host mirror of the matrix: 0 = compute, 1 = the slot already holds these values, 2 = copy the twin slot's
+    int skip = 0;     // not uploaded: superseded, or (change tracking) nothing new
+    int is_distance;  // the values are K branch distances (length * branch rate * category rate) instead of K matrices
+    size_t off;       // its values in sieve_core::pending_vals (K doubles or K * 16): the entries stay small, a whole-tree
+                      // update of 10 000 cells queues 20 000 of them per proposal
+};
+
+struct sieve_core {
+    sieve_config_t cfg;
+    int n = 0, S = 0, K = 0, n_nodes = 0, n_internal = 0;
+    bool log_mode = false, with_const = false, single_ado = true, ephemeral = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t bytes = 0;
+    uint64_t launches = 0;
+    int step_launches = 0;  // since the last evaluate
+    bool leaf_attr_set = false;
+
+    // device pools
+    int4* d_counts = nullptr;  // [cell][site]
+    bool counts_owned = true;
+    int* d_weights = nullptr;
+    double* d_sf = nullptr;
+    double *d_dmA = nullptr, *d_dmB = nullptr, *d_cellT = nullptr;
+    int C = 0;  // table entries per table
+    int max_cov = -1;
+    double *d_leafX = nullptr, *d_leafS = nullptr;                                       // [2][n][S][4], [2][n][S]
+    double *d_part = nullptr, *d_scale = nullptr, *d_cpart = nullptr, *d_cscale = nullptr;  // [2][n_internal][S][K][4]
+    double* d_mats = nullptr;                                                            // [2][n_nodes][4][16]
+    double2* d_qfac = nullptr;                                                           // [2][n_nodes][4]
+    std::vector<char> slot_is_q;  // per matrix slot: was it given as a distance?
+    std::vector<char> slot_zero;  // ... and is one of its K distances exactly 0?
+    double *d_site_logl = nullptr, *d_site_const = nullptr;
+    // algebraic constant-site path (default when SIEVE_FLAG_CONST_PARTIALS): see k_colsum in reduce.cuh
+    bool const_twin = false;     // SIEVE_B200_CONST_TWIN=1: prune the constant-site partials per site like the reference
+    double* d_leaf0 = nullptr;   // [leaf buffers][cell][site] constant-genotype log-likelihood of every leaf
+    double* d_lambda = nullptr;  // [leaf buffers][site] its sum over cells
+    std::vector<double> hP;      // [2][node][K][16] host mirror of the (clamped) transition matrices
+    std::vector<double> G, Gs;   // [2][node][K][4] site-independent factor of the constant-site partials + log-scale
+    double log_c = 0.0, log_c_stored = 0.0;  // log sum_k prop_k G_root[k][root genotype]
+    std::vector<int> g_nodes;    // nodes whose G has to be refreshed, children first
+    SvAcc* d_partials = nullptr;
+    unsigned int* d_counter = nullptr;
+    double* d_result = nullptr;
+    // staging
+    char* h_stage = nullptr;  // pinned
+    char* d_stage = nullptr;
+    size_t stage_cap = 0;
+    double* h_result = nullptr;  // pinned, 8 doubles
+
+    // host bookkeeping
+    std::vector<int> cur_part, stored_part, cur_mat, stored_mat;
+    int cur_leaf = 0, stored_leaf = 0;
+    std::vector<SvOp> pending_ops;
+    std::vector<int> pending_levels;  // offsets into pending_ops, empty == one group
+    bool pending_per_level = false;
+    std::vector<PendingMatrix> pending_mats;
+    std::vector<double> pending_vals;
+    int root = -1, root_genotype = 0, const_genotype = 0;
+    double prop[4] = {0.25, 0.25, 0.25, 0.25};
+    sieve_leaf_params_t lp{};
+    bool have_counts = false, have_sf = false, have_params = false, leaves_ready = false;
+    bool dm_dirty = true, cov_dirty = true;
+    sieve_leaf_params_t tab_lp{};  // parameters the current tables were built with
+
+    // what the last flush staged on the device (for sieve_replay)
+    size_t last_no = 0, last_nm = 0, last_nd = 0, last_off_mv = 0, last_off_ms = 0, last_off_dv = 0, last_off_ds = 0;
+    size_t last_stage_bytes = 0;
+    bool last_qfast = false;
+    bool force_generic = false;
+    bool use_rp = false;  // SIEVE_B200_RP=1: next op's operands prefetched into registers (prune_rp.cuh)
+    bool use_pipe = false, pipe_attr_set = false;  // SIEVE_B200_PIPE=1: the cp.async-pipelined Q walk (measured slower, see prune_pipe.cuh)
+    // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
+    int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
+    int n_slots = 0;     // scratch slots for internal partials
+    std::vector<int> eph_c1, eph_c2, eph_c1_stored, eph_c2_stored;  // children of every internal node (-2 = unset)
+    bool eph_leaves_dirty = true;
+    // resident mode: the core owns the walk order.  Callers name the dirty nodes (and their children); the planner
+    // orders them so that results are consumed from registers, and leaves small subtrees' results unsaved
+    // ("transient": at most transient_T leaves, consumed by the very next op); they are recomputed when needed again.
+    int transient_T = 8;
+    std::vector<char> valid, valid_stored;  // does the node's current buffer hold its partial?
+    std::vector<int> dirty_list;            // internal nodes queued for recomputation
+    std::vector<int> demand_list;           // nodes whose partial must be materialised (getNodePartials)  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
+    std::vector<int> last_levels;
+    bool last_per_level = false;
+
+    // multi-process shards: NCCL communicator bound to this handle's stream
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    double* d_gather = nullptr;   // [world][5]
+    double* h_gather = nullptr;   // pinned
+
+    // Change tracking (resident planner): every matrix slot, leaf buffer and node value carries a version number, and a
+    // node remembers the versions of the inputs its value was computed from.  A node that the caller marks dirty but
+    // whose inputs are the ones its value in the stored state was computed from is NOT recomputed: the kernels are
+    // deterministic, so the result would be the same bits (SIEVE forces whole-tree recomputation for every branch-rate
+    // proposal under a relaxed clock with bias correction, ScsTreeLikelihood.java:2814-2821 -- here only the path from
+    // the changed branch to the root is walked).  sieve_set_elision(h, 0) switches the short-cut off.
+    struct SvFp {
+        int c1 = -9, c2 = -9;
+        uint64_t p1 = 0, p2 = 0, m1 = 0, m2 = 0;
+        bool operator==(const SvFp& o) const {
+            return c1 == o.c1 && c2 == o.c2 && p1 == o.p1 && p2 == o.p2 && m1 == o.m1 && m2 == o.m2;
+        }
+    };
+    bool elide = true;
+    uint64_t ver_counter = 0, elided_total = 0;
+    std::vector<uint64_t> mat_ver;      // [2 * n_nodes] per matrix slot
+    std::vector<double> mat_mirror;     // [2 * n_nodes][SV_KMAX * 16] the matrices a slot was last given ...
+    std::vector<double> dist_mirror;    // [n_nodes][2][SV_KMAX] ... or its K distances
+    std::vector<char> mat_mirror_q;     // ... and in which form
+    uint64_t leaf_ver[2] = {0, 0};
+    // Sparse residency (SIEVE_FLAG_SPARSE): the partial pool has fewer slots than 2 * n_internal.  Nodes with more than
+    // keep_T leaves keep their partials (a slot per buffer that holds something the current or the stored state refers
+    // to); smaller subtrees are recomputed from the resident leaves when an update needs them, through temporary slots
+    // that are recycled inside the walk.  Dense cores use the same code with a fixed identity mapping.
+    bool sparse = false, sparse_recheck = true;
+    // SIEVE_FLAG_SINGLE_LEAF_BUFFER: one leaf buffer instead of two.  A leaf-parameter proposal overwrites the leaves; if it is
+    // rejected, sieve_restore recomputes them from the stored parameters (same kernel, same bits) instead of flipping back.
+    bool single_leaf = false, leaf_changed_since_store = false;
+    sieve_leaf_params_t stored_lp{};
+    uint64_t leaf_ver_stored = 0;
+    int pool_slots = 0;
+    int keep_T = 0;
+    std::vector<int> slot_of;      // [2 * n_nodes] physical slot of (buffer, node), -1 = none
+    std::vector<int> free_slots;
+    std::vector<int> held;         // (buffer * n_nodes + node) of small nodes materialised on demand: released by the next plan
+    std::vector<int> scratch_idx;       // per-flush scratch
+    std::vector<int> topo_parent, topo_leaves;  // planner: parents and subtree leaf counts of the current children map
+    bool topo_cache_ok = false;
+    std::vector<uint64_t> g_ver;        // [2 * n_nodes] version of the node value whose constant-site factor G sits in that slot
+    std::vector<char> buf_has;          // [2 * n_nodes] the partial buffer holds a value ...
+    std::vector<uint64_t> buf_ver;      // ... of this version ...
+    std::vector<SvFp> buf_fp;           // ... computed from these inputs
+    std::vector<uint64_t> ver_cur, ver_stored;  // [n_nodes] version of the node's value in the current / stored state
+    std::vector<SvFp> fp_cur, fp_stored;        // ... and what it was computed from
+
+    // max-sum pass for variant calling (maxsum.cuh); its pools are allocated by the first sieve_ml_trace
+    bool ml_alloc = false, ml_ready = false;
+    double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr, *d_mlcellL = nullptr;
+    unsigned short* d_mlado = nullptr;
+    unsigned* d_mlback = nullptr;
+    unsigned char *d_mlcoll = nullptr, *d_mladosel = nullptr, *d_mlamb = nullptr, *d_mlcats = nullptr;
+    SvMlOp* d_mlops = nullptr;
+    int ml_n_ops = 0;
+
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    int last_launches = 0;
+    bool leaf_timed = false;
+};
+
+static inline void sv_count(sieve_core* h) {
+    h->launches++;
+    h->step_launches++;
+}
+
+static const int SV_TABLE_CAP_DEFAULT = 4096;
+static const int SV_REDUCE_BLOCKS = 296;
+
+
+template <typename T>
+static int sv_alloc(sieve_core* h, T** p, size_t count) {
+    const size_t b = count * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, b ? b : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return sv_fail(e == cudaErrorMemoryAllocation ? SIEVE_ERR_OOM : SIEVE_ERR_CUDA,
+                       std::string("cudaMalloc of ") + std::to_string(b) + " bytes: " + cudaGetErrorString(e));
+    }
+    h->bytes += b;
+    return SIEVE_OK;
+}
+#define SV_TRY(x)                    \
+    do {                             \
+        int r__ = (x);               \
+        if (r__ != SIEVE_OK) return r__; \
+    } while (0)
+
+static int sv_ensure_stage(sieve_core* h, size_t bytes) {
+    if (bytes <= h->stage_cap) return SIEVE_OK;
+    size_t cap = std::max<size_t>(bytes, std::max<size_t>(h->stage_cap * 2, (size_t)1 << 16));
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->d_stage) {
+        cudaFree(h->d_stage);
+        h->bytes -= h->stage_cap;
+    }
+    h->h_stage = nullptr;
+    h->d_stage = nullptr;
+    h->stage_cap = 0;
+    SV_CUDA(cudaMallocHost((void**)&h->h_stage, cap));
+    SV_TRY(sv_alloc(h, &h->d_stage, cap));
+    h->stage_cap = cap;
+    return SIEVE_OK;
+}

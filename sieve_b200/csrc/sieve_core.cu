@@ -23,187 +23,7 @@
 #include "background.cuh"
 #include "comm.cuh"
 
-static thread_local std::string g_err;
-
-static int sv_fail(int code, const std::string& msg) {
-    g_err = msg;
-    return code;
-}
-#define SV_CUDA(call)                                                                                      \
-    do {                                                                                                   \
-        cudaError_t e__ = (call);                                                                          \
-        if (e__ != cudaSuccess)                                                                            \
-            return sv_fail(SIEVE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
-    } while (0)
-#define SV_REQUIRE(cond, msg) \
-    do {                      \
-        if (!(cond)) return sv_fail(SIEVE_ERR_INVALID, msg); \
-    } while (0)
-
-struct PendingMatrix {
-    int slot;
-    int reuse = 0;    // host mirror of the matrix: 0 = compute, 1 = the slot already holds these values, 2 = copy the twin slot's
-    int skip = 0;     // not uploaded: superseded, or (change tracking) nothing new
-    int is_distance;  // the values are K branch distances (length * branch rate * category rate) instead of K matrices
-    size_t off;       // its values in sieve_core::pending_vals (K doubles or K * 16): the entries stay small, a whole-tree
-                      // update of 10 000 cells queues 20 000 of them per proposal
-};
-
-struct sieve_core {
-    sieve_config_t cfg;
-    int n = 0, S = 0, K = 0, n_nodes = 0, n_internal = 0;
-    bool log_mode = false, with_const = false, single_ado = true, ephemeral = false;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    uint64_t bytes = 0;
-    uint64_t launches = 0;
-    int step_launches = 0;  // since the last evaluate
-    bool leaf_attr_set = false;
-
-    // device pools
-    int4* d_counts = nullptr;  // [cell][site]
-    bool counts_owned = true;
-    int* d_weights = nullptr;
-    double* d_sf = nullptr;
-    double *d_dmA = nullptr, *d_dmB = nullptr, *d_cellT = nullptr;
-    int C = 0;  // table entries per table
-    int max_cov = -1;
-    double *d_leafX = nullptr, *d_leafS = nullptr;                                       // [2][n][S][4], [2][n][S]
-    double *d_part = nullptr, *d_scale = nullptr, *d_cpart = nullptr, *d_cscale = nullptr;  // [2][n_internal][S][K][4]
-    double* d_mats = nullptr;                                                            // [2][n_nodes][4][16]
-    double2* d_qfac = nullptr;                                                           // [2][n_nodes][4]
-    std::vector<char> slot_is_q;  // per matrix slot: was it given as a distance?
-    std::vector<char> slot_zero;  // ... and is one of its K distances exactly 0?
-    double *d_site_logl = nullptr, *d_site_const = nullptr;
-    // algebraic constant-site path (default when SIEVE_FLAG_CONST_PARTIALS): see k_colsum in reduce.cuh
-    bool const_twin = false;     // SIEVE_B200_CONST_TWIN=1: prune the constant-site partials per site like the reference
-    double* d_leaf0 = nullptr;   // [leaf buffers][cell][site] constant-genotype log-likelihood of every leaf
-    double* d_lambda = nullptr;  // [leaf buffers][site] its sum over cells
-    std::vector<double> hP;      // [2][node][K][16] host mirror of the (clamped) transition matrices
-    std::vector<double> G, Gs;   // [2][node][K][4] site-independent factor of the constant-site partials + log-scale
-    double log_c = 0.0, log_c_stored = 0.0;  // log sum_k prop_k G_root[k][root genotype]
-    std::vector<int> g_nodes;    // nodes whose G has to be refreshed, children first
-    SvAcc* d_partials = nullptr;
-    unsigned int* d_counter = nullptr;
-    double* d_result = nullptr;
-    // staging
-    char* h_stage = nullptr;  // pinned
-    char* d_stage = nullptr;
-    size_t stage_cap = 0;
-    double* h_result = nullptr;  // pinned, 8 doubles
-
-    // host bookkeeping
-    std::vector<int> cur_part, stored_part, cur_mat, stored_mat;
-    int cur_leaf = 0, stored_leaf = 0;
-    std::vector<SvOp> pending_ops;
-    std::vector<int> pending_levels;  // offsets into pending_ops, empty == one group
-    bool pending_per_level = false;
-    std::vector<PendingMatrix> pending_mats;
-    std::vector<double> pending_vals;
-    int root = -1, root_genotype = 0, const_genotype = 0;
-    double prop[4] = {0.25, 0.25, 0.25, 0.25};
-    sieve_leaf_params_t lp{};
-    bool have_counts = false, have_sf = false, have_params = false, leaves_ready = false;
-    bool dm_dirty = true, cov_dirty = true;
-    sieve_leaf_params_t tab_lp{};  // parameters the current tables were built with
-
-    // what the last flush staged on the device (for sieve_replay)
-    size_t last_no = 0, last_nm = 0, last_nd = 0, last_off_mv = 0, last_off_ms = 0, last_off_dv = 0, last_off_ds = 0;
-    size_t last_stage_bytes = 0;
-    bool last_qfast = false;
-    bool force_generic = false;
-    bool use_rp = false;  // SIEVE_B200_RP=1: next op's operands prefetched into registers (prune_rp.cuh)
-    bool use_pipe = false, pipe_attr_set = false;  // SIEVE_B200_PIPE=1: the cp.async-pipelined Q walk (measured slower, see prune_pipe.cuh)
-    // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
-    int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
-    int n_slots = 0;     // scratch slots for internal partials
-    std::vector<int> eph_c1, eph_c2, eph_c1_stored, eph_c2_stored;  // children of every internal node (-2 = unset)
-    bool eph_leaves_dirty = true;
-    // resident mode: the core owns the walk order.  Callers name the dirty nodes (and their children); the planner
-    // orders them so that results are consumed from registers, and leaves small subtrees' results unsaved
-    // ("transient": at most transient_T leaves, consumed by the very next op); they are recomputed when needed again.
-    int transient_T = 8;
-    std::vector<char> valid, valid_stored;  // does the node's current buffer hold its partial?
-    std::vector<int> dirty_list;            // internal nodes queued for recomputation
-    std::vector<int> demand_list;           // nodes whose partial must be materialised (getNodePartials)  // SIEVE_B200_GENERIC=1: never take the Q-specialised walk (A/B measurements)
-    std::vector<int> last_levels;
-    bool last_per_level = false;
-
-    // multi-process shards: NCCL communicator bound to this handle's stream
-    ncclComm_t comm = nullptr;
-    int comm_rank = 0, comm_world = 1;
-    double* d_gather = nullptr;   // [world][5]
-    double* h_gather = nullptr;   // pinned
-
-    // Change tracking (resident planner): every matrix slot, leaf buffer and node value carries a version number, and a
-    // node remembers the versions of the inputs its value was computed from.  A node that the caller marks dirty but
-    // whose inputs are the ones its value in the stored state was computed from is NOT recomputed: the kernels are
-    // deterministic, so the result would be the same bits (SIEVE forces whole-tree recomputation for every branch-rate
-    // proposal under a relaxed clock with bias correction, ScsTreeLikelihood.java:2814-2821 -- here only the path from
-    // the changed branch to the root is walked).  sieve_set_elision(h, 0) switches the short-cut off.
-    struct SvFp {
-        int c1 = -9, c2 = -9;
-        uint64_t p1 = 0, p2 = 0, m1 = 0, m2 = 0;
-        bool operator==(const SvFp& o) const {
-            return c1 == o.c1 && c2 == o.c2 && p1 == o.p1 && p2 == o.p2 && m1 == o.m1 && m2 == o.m2;
-        }
-    };
-    bool elide = true;
-    uint64_t ver_counter = 0, elided_total = 0;
-    std::vector<uint64_t> mat_ver;      // [2 * n_nodes] per matrix slot
-    std::vector<double> mat_mirror;     // [2 * n_nodes][SV_KMAX * 16] the matrices a slot was last given ...
-    std::vector<double> dist_mirror;    // [n_nodes][2][SV_KMAX] ... or its K distances
-    std::vector<char> mat_mirror_q;     // ... and in which form
-    uint64_t leaf_ver[2] = {0, 0};
-    // Sparse residency (SIEVE_FLAG_SPARSE): the partial pool has fewer slots than 2 * n_internal.  Nodes with more than
-    // keep_T leaves keep their partials (a slot per buffer that holds something the current or the stored state refers
-    // to); smaller subtrees are recomputed from the resident leaves when an update needs them, through temporary slots
-    // that are recycled inside the walk.  Dense cores use the same code with a fixed identity mapping.
-    bool sparse = false, sparse_recheck = true;
-    // SIEVE_FLAG_SINGLE_LEAF_BUFFER: one leaf buffer instead of two.  A leaf-parameter proposal overwrites the leaves; if it is
-    // rejected, sieve_restore recomputes them from the stored parameters (same kernel, same bits) instead of flipping back.
-    bool single_leaf = false, leaf_changed_since_store = false;
-    sieve_leaf_params_t stored_lp{};
-    uint64_t leaf_ver_stored = 0;
-    int pool_slots = 0;
-    int keep_T = 0;
-    std::vector<int> slot_of;      // [2 * n_nodes] physical slot of (buffer, node), -1 = none
-    std::vector<int> free_slots;
-    std::vector<int> held;         // (buffer * n_nodes + node) of small nodes materialised on demand: released by the next plan
-    std::vector<int> scratch_idx;       // per-flush scratch
-    std::vector<int> topo_parent, topo_leaves;  // planner: parents and subtree leaf counts of the current children map
-    bool topo_cache_ok = false;
-    std::vector<uint64_t> g_ver;        // [2 * n_nodes] version of the node value whose constant-site factor G sits in that slot
-    std::vector<char> buf_has;          // [2 * n_nodes] the partial buffer holds a value ...
-    std::vector<uint64_t> buf_ver;      // ... of this version ...
-    std::vector<SvFp> buf_fp;           // ... computed from these inputs
-    std::vector<uint64_t> ver_cur, ver_stored;  // [n_nodes] version of the node's value in the current / stored state
-    std::vector<SvFp> fp_cur, fp_stored;        // ... and what it was computed from
-
-    // max-sum pass for variant calling (maxsum.cuh); its pools are allocated by the first sieve_ml_trace
-    bool ml_alloc = false, ml_ready = false;
-    double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr, *d_mlcellL = nullptr;
-    unsigned short* d_mlado = nullptr;
-    unsigned* d_mlback = nullptr;
-    unsigned char *d_mlcoll = nullptr, *d_mladosel = nullptr, *d_mlamb = nullptr, *d_mlcats = nullptr;
-    SvMlOp* d_mlops = nullptr;
-    int ml_n_ops = 0;
-
-    // timing
-    bool timing = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    float last_ms[4] = {0, 0, 0, 0};
-    int last_launches = 0;
-    bool leaf_timed = false;
-};
-
-static inline void sv_count(sieve_core* h) {
-    h->launches++;
-    h->step_launches++;
-}
-
-static const int SV_TABLE_CAP_DEFAULT = 4096;
-static const int SV_REDUCE_BLOCKS = 296;
+#include "core_state.cuh"
 
 extern "C" const char* sieve_last_error(void) { return g_err.c_str(); }
 extern "C" int sieve_version(void) { return 1; }
@@ -214,42 +34,6 @@ extern "C" int sieve_device_count(void) {
         return 0;
     }
     return n;
-}
-
-template <typename T>
-static int sv_alloc(sieve_core* h, T** p, size_t count) {
-    const size_t b = count * sizeof(T);
-    cudaError_t e = cudaMalloc((void**)p, b ? b : 1);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return sv_fail(e == cudaErrorMemoryAllocation ? SIEVE_ERR_OOM : SIEVE_ERR_CUDA,
-                       std::string("cudaMalloc of ") + std::to_string(b) + " bytes: " + cudaGetErrorString(e));
-    }
-    h->bytes += b;
-    return SIEVE_OK;
-}
-#define SV_TRY(x)                    \
-    do {                             \
-        int r__ = (x);               \
-        if (r__ != SIEVE_OK) return r__; \
-    } while (0)
-
-static int sv_ensure_stage(sieve_core* h, size_t bytes) {
-    if (bytes <= h->stage_cap) return SIEVE_OK;
-    size_t cap = std::max<size_t>(bytes, std::max<size_t>(h->stage_cap * 2, (size_t)1 << 16));
-    SV_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->h_stage) cudaFreeHost(h->h_stage);
-    if (h->d_stage) {
-        cudaFree(h->d_stage);
-        h->bytes -= h->stage_cap;
-    }
-    h->h_stage = nullptr;
-    h->d_stage = nullptr;
-    h->stage_cap = 0;
-    SV_CUDA(cudaMallocHost((void**)&h->h_stage, cap));
-    SV_TRY(sv_alloc(h, &h->d_stage, cap));
-    h->stage_cap = cap;
-    return SIEVE_OK;
 }
 
 extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
@@ -930,540 +714,7 @@ extern "C" int sieve_set_node_partials_for_update(sieve_core_t* h, int32_t node)
     return SIEVE_OK;
 }
 
-// row of (buffer, internal node) in the partial pools; a node without a slot (its value only ever lives in registers)
-// gets a unique row that is never dereferenced -- the forwarding link compares rows
-static inline unsigned sv_part_row(const sieve_core* h, int buf, int node) {
-    const int sl = h->slot_of[(size_t)buf * h->n_nodes + node];
-    if (sl < 0) return 0xFFFFFFFFu - (unsigned)node;
-    return (unsigned)((long long)sl * h->S);
-}
-
-static void sv_slot_release(sieve_core* h, int buf, int node) {
-    const size_t bi = (size_t)buf * h->n_nodes + node;
-    if (!h->sparse || h->slot_of[bi] < 0) return;
-    h->free_slots.push_back(h->slot_of[bi]);
-    h->slot_of[bi] = -1;
-    h->buf_has[bi] = 0;
-    if (h->cur_part[node] == buf) h->valid[node] = 0;
-    if (h->stored_part[node] == buf) h->valid_stored[node] = 0;
-}
-
-// a free slot; when none is left, buffers that neither the current nor the stored state refers to are reclaimed first
-static int sv_slot_alloc(sieve_core* h) {
-    if (h->free_slots.empty()) {
-        const int n = h->n, N = h->n_nodes;
-        for (int v = n; v < N; v++)
-            for (int b = 0; b < 2; b++) {
-                if (h->slot_of[(size_t)b * N + v] < 0) continue;
-                const bool used = (b == h->cur_part[v] && h->valid[v]) || (b == h->stored_part[v] && h->valid_stored[v]);
-                if (!used) sv_slot_release(h, b, v);
-            }
-    }
-    if (h->free_slots.empty()) return -1;
-    const int sl = h->free_slots.back();
-    h->free_slots.pop_back();
-    return sl;
-}
-
-static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
-    const int n = h->n;
-    const long long S = h->S;
-    SV_REQUIRE(parent >= n && parent < h->n_nodes, "op: parent must be an internal node");
-    SV_REQUIRE(c1 >= 0 && c1 < h->n_nodes && c1 != h->root, "op: bad child1");
-    SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
-    op->flags = 0;
-    op->pad0 = op->pad1 = 0;
-    op->dst_row = sv_part_row(h, h->cur_part[parent], parent);
-    auto child = [&](int c, int leaf_flag, unsigned* row, int* m) {
-        if (c < n) {
-            op->flags |= leaf_flag;
-            *row = (unsigned)((long long)(h->cur_leaf * n + c) * S);
-        } else
-            *row = sv_part_row(h, h->cur_part[c], c);
-        *m = h->cur_mat[c] * h->n_nodes + c;
-        if (h->log_mode && h->slot_zero[*m]) op->flags |= SV_OP_ZEROD;
-    };
-    child(c1, SV_OP_LEAF1, &op->c1_row, &op->m1);
-    if (c2 < 0) {
-        op->flags |= SV_OP_UNARY;
-        op->c2_row = 0;
-        op->m2 = 0;
-    } else
-        child(c2, SV_OP_LEAF2, &op->c2_row, &op->m2);
-    if (parent == h->root) op->flags |= SV_OP_ROOT;
-    return SIEVE_OK;
-}
-
-// ---- algebraic constant-site path: the site-independent factor ----------------------------------------------------
-// constPartial[v][k][s][p] = G_v[k][p] * prod_{leaves l below v} leaf_l[s][cg]   (induction over
-// ScsBeerLikelihoodCore.java:1432-1440 / :1467-1490: a leaf child contributes P[p][cg] * leaf[cg], an internal child
-// sum_c P[p][c] * const[c], and the leaf factor is common to the four parent states).  G is 16 doubles per node, kept on
-// the host in the same double buffers as the partials, refreshed for the nodes an update recomputes.
-static void sv_host_matrix(sieve_core* h, const PendingMatrix& pm) {
-    const int K = h->K;
-    const double* pv = h->pending_vals.data() + pm.off;
-    double* dst = h->hP.data() + (size_t)pm.slot * SV_KMAX * 16;
-    static const double P1[16] = {3, 6, -3, -6, 1, 2, -1, -2, -1, -2, 1, 2, -1, -2, 1, 2};     // 8 Pi1
-    static const double P2[16] = {9, -18, 3, 6, -3, 6, -1, -2, 1, -2, 11, -10, 1, -2, -5, 6};  // 16 Pi2
-    for (int k = 0; k < K; k++) {
-        double d = 0.0, q1 = 0.0, q2 = 0.0;
-        if (pm.is_distance) {
-            d = pv[k];
-            const double g1 = expm1(-0.2 * d);  // expm1(-0.4 d) = g1 (g1 + 2)
-            q1 = g1 / 8.0;
-            q2 = g1 * (g1 + 2.0) / 16.0;
-        }
-        for (int e = 0; e < 16; e++) {
-            double v;
-            if (pm.is_distance) {
-                v = ((e % 5 == 0) ? 1.0 : 0.0) + q1 * P1[e] + q2 * P2[e];
-                if (d == 0.0) v = (e % 5 == 0) ? 1.0 : 0.0;
-            } else
-                v = pv[k * 16 + e];
-            if (h->log_mode) v = v > 0.0 ? v : SV_MIN_VALUE;
-            dst[k * 16 + e] = v;
-        }
-    }
-}
-
-static void sv_update_G(sieve_core* h) {
-    const int n = h->n, N = h->n_nodes, K = h->K, cg = h->const_genotype;
-    for (int v : h->g_nodes) {
-        const int a = h->eph_c1[v], b = h->eph_c2[v];
-        double* g = h->G.data() + ((size_t)h->cur_part[v] * N + v) * SV_KMAX * 4;
-        double gs = 0.0, mx = 0.0;
-        auto side = [&](int c, int k, double* y) {
-            const double* P = h->hP.data() + ((size_t)h->cur_mat[c] * N + c) * SV_KMAX * 16 + k * 16;
-            if (c < n) {
-                for (int p = 0; p < 4; p++) y[p] = P[4 * p + cg];
-            } else {
-                const double* gc = h->G.data() + ((size_t)h->cur_part[c] * N + c) * SV_KMAX * 4 + k * 4;
-                for (int p = 0; p < 4; p++) y[p] = P[4 * p] * gc[0] + P[4 * p + 1] * gc[1] + P[4 * p + 2] * gc[2] + P[4 * p + 3] * gc[3];
-            }
-        };
-        for (int k = 0; k < K; k++) {
-            double y[4], z[4];
-            side(a, k, y);
-            if (b >= 0) {
-                side(b, k, z);
-                for (int p = 0; p < 4; p++) y[p] *= z[p];
-            }
-            for (int p = 0; p < 4; p++) {
-                g[k * 4 + p] = y[p];
-                mx = std::max(mx, y[p]);
-            }
-        }
-        if (a >= n) gs += h->Gs[(size_t)h->cur_part[a] * N + a];
-        if (b >= n) gs += h->Gs[(size_t)h->cur_part[b] * N + b];
-        if (mx > 0.0 && std::isfinite(mx)) {
-            for (int i = 0; i < K * 4; i++) g[i] /= mx;
-            gs += std::log(mx);
-        }
-        h->Gs[(size_t)h->cur_part[v] * N + v] = gs;
-        h->g_ver[(size_t)h->cur_part[v] * N + v] = h->ver_cur[v];
-    }
-    h->g_nodes.clear();
-    const int root = h->root;
-    const double* gr = h->G.data() + ((size_t)h->cur_part[root] * N + root) * SV_KMAX * 4;
-    double sum = 0.0;
-    for (int k = 0; k < K; k++) sum += h->prop[k] * gr[k * 4 + h->root_genotype];
-    h->log_c = std::log(sum) + h->Gs[(size_t)h->cur_part[root] * N + root];
-}
-
-// Resident-mode planner.  Input: the dirty nodes (dirty_list), nodes to materialise (demand_list), the parent -> children
-// map.  Output: pending_ops, children before parents, ordered so that as many results as possible are consumed by the
-// very next op (register forwarding), with the results of small subtrees (<= transient_T leaves) that are consumed at
-// once left unsaved (SV_OP_NOSTORE).  A clean node whose partial is not in memory is recomputed from its subtree on the
-// way (at most transient_T - 1 extra ops reading leaves).  Clean recomputed nodes that do get stored go to their
-// current buffer and become valid in both the current and the stored state: a clean subtree is the same in both.
-static int sv_plan_resident_ops(sieve_core* h) {
-    const int n = h->n, N = h->n_nodes, root = h->root;
-    std::vector<char> dirty(N, 0), demanded(N, 0);
-    for (int v : h->dirty_list) dirty[v] = 1;
-    for (int v : h->demand_list) demanded[v] = 1;
-    // parents and subtree leaf counts where the children are known
-    // (cached between plans: they only change when an op names new children for a node)
-    std::vector<int>&parent = h->topo_parent, &leaves = h->topo_leaves;
-    if (!h->topo_cache_ok) {
-    parent.assign(N, -1);
-    leaves.assign(N, 0);
-    for (int v = n; v < N; v++) {
-        if (h->eph_c1[v] >= 0) parent[h->eph_c1[v]] = v;
-        if (h->eph_c2[v] >= 0) parent[h->eph_c2[v]] = v;
-    }
-    {
-        // bottom-up leaf counts via an explicit post-order from every known node without a known parent
-        std::vector<char> done(N, 0);
-        std::vector<std::pair<int, int>> st;
-        for (int r = n; r < N; r++) {
-            if (parent[r] >= 0 || h->eph_c1[r] == -2) continue;
-            st.push_back({r, 0});
-            while (!st.empty()) {
-                auto [v, state] = st.back();
-                st.pop_back();
-                if (v < n) continue;
-                const int a = h->eph_c1[v], b = h->eph_c2[v];
-                if (a == -2) {  // never described: treat as large
-                    leaves[v] = 1 << 28;
-                    continue;
-                }
-                if (state == 0) {
-                    st.push_back({v, 1});
-                    if (b >= n) st.push_back({b, 0});
-                    if (a >= n) st.push_back({a, 0});
-                } else {
-                    const long long la = a < n ? 1 : leaves[a], lb = b < 0 ? 0 : (b < n ? 1 : leaves[b]);
-                    leaves[v] = (int)std::min<long long>(la + lb, 1 << 28);
-                }
-            }
-        }
-    }
-    h->topo_cache_ok = true;
-    h->sparse_recheck = true;  // leaf counts moved: a node may have dropped below the keep threshold
-    }
-    if (h->sparse) {
-        // small nodes that were materialised for a read-back go back to "not in memory"
-        for (int bi : h->held) {
-            const int b = bi / N, v = bi % N;
-            if (v != root && leaves[v] <= h->keep_T) sv_slot_release(h, b, v);
-        }
-        h->held.clear();
-        // the nodes that keep their partials must fit twice (a whole-tree proposal flips every one of them) plus the
-        // temporaries of the walk; when they do not, the threshold goes up and the nodes below it give their slots back
-        auto kept_count = [&](int T) {
-            int c = 0;
-            for (int v = n; v < N; v++) c += (v == root || leaves[v] > T) ? 1 : 0;
-            return c;
-        };
-        int T = std::max(h->keep_T, 1);
-        while (2 * (long long)kept_count(T) + 64 > h->pool_slots && T < (1 << 28)) T += std::max(1, T / 4);
-        if (T != h->keep_T || h->sparse_recheck) {
-            h->keep_T = T;
-            for (int v = n; v < N; v++)
-                if (v != root && leaves[v] <= T) {
-                    sv_slot_release(h, 0, v);
-                    sv_slot_release(h, 1, v);
-                }
-            h->sparse_recheck = false;
-        }
-    }
-    // ---- change tracking: which of the dirty nodes really get a new value? (children before parents) ----
-    {
-        std::vector<char> done(N, 0);
-        std::vector<std::pair<int, int>> st;
-        auto pver = [&](int c) -> uint64_t { return c < 0 ? 0 : (c < n ? h->leaf_ver[h->cur_leaf] : h->ver_cur[c]); };
-        auto mver = [&](int c) -> uint64_t { return c < 0 ? 0 : h->mat_ver[(size_t)h->cur_mat[c] * N + c]; };
-        for (int top : h->dirty_list) {
-            if (done[top]) continue;
-            st.push_back({top, 0});
-            while (!st.empty()) {
-                auto [v, state] = st.back();
-                st.pop_back();
-                if (v < n || !dirty[v] || done[v]) continue;
-                const int a = h->eph_c1[v], b = h->eph_c2[v];
-                if (a == -2) {
-                    done[v] = 1;
-                    continue;  // reported by the walk below
-                }
-                if (state == 0) {
-                    st.push_back({v, 1});
-                    if (b >= n) st.push_back({b, 0});
-                    if (a >= n) st.push_back({a, 0});
-                    continue;
-                }
-                done[v] = 1;
-                sieve_core::SvFp f;
-                f.c1 = a;
-                f.c2 = b;
-                f.p1 = pver(a);
-                f.p2 = pver(b);
-                f.m1 = mver(a);
-                f.m2 = mver(b);
-                const bool known = f.p1 != 0 && f.m1 != 0 && (b < 0 || (f.p2 != 0 && f.m2 != 0));
-                if (h->elide && known && v != root) {
-                    // 1. one of the node's two buffers holds the value of exactly these inputs
-                    int hit = -1;
-                    for (int t = 0; t < 2 && hit < 0; t++) {
-                        const int bsel = t == 0 ? h->cur_part[v] : 1 - h->cur_part[v];
-                        const size_t bi = (size_t)bsel * N + v;
-                        if (h->buf_has[bi] && h->buf_fp[bi] == f) hit = bsel;
-                    }
-                    if (hit >= 0) {
-                        h->cur_part[v] = hit;
-                        h->valid[v] = 1;
-                        h->ver_cur[v] = h->buf_ver[(size_t)hit * N + v];
-                        h->fp_cur[v] = f;
-                        dirty[v] = 0;
-                        h->elided_total++;
-                        if (!h->G.empty() && h->g_ver[(size_t)h->cur_part[v] * N + v] != h->ver_cur[v]) h->g_nodes.push_back(v);
-                        continue;
-                    }
-                    // 2. it is the stored state's value, which was consumed from registers and never written: the node
-                    //    is clean but not in memory (recomputed from its small subtree if a dirty parent needs it)
-                    if (h->ver_stored[v] != 0 && h->fp_stored[v] == f) {
-                        h->cur_part[v] = h->stored_part[v];
-                        h->valid[v] = 0;
-                        h->ver_cur[v] = h->ver_stored[v];
-                        h->fp_cur[v] = f;
-                        dirty[v] = 0;
-                        h->elided_total++;
-                        if (!h->G.empty() && h->g_ver[(size_t)h->cur_part[v] * N + v] != h->ver_cur[v]) h->g_nodes.push_back(v);
-                        continue;
-                    }
-                }
-                h->ver_cur[v] = ++h->ver_counter;
-                h->fp_cur[v] = known ? f : sieve_core::SvFp();
-                h->g_nodes.push_back(v);  // children first: this pass is a post-order over the dirty nodes
-            }
-        }
-    }
-    auto needs = [&](int c) { return c >= n && (dirty[c] || !h->valid[c]); };
-    std::vector<int> emitted;
-    struct Frame {
-        int v, stage, first, last;
-    };
-    std::vector<Frame> st;
-    std::vector<char> visited(N, 0);
-    auto run_from = [&](int top) -> int {
-        st.push_back({top, 0, -1, -1});
-        while (!st.empty()) {
-            Frame& f = st.back();
-            const int v = f.v;
-            if (f.stage == 0) {
-                if (visited[v]) {
-                    st.pop_back();
-                    continue;
-                }
-                const int a = h->eph_c1[v], b = h->eph_c2[v];
-                if (a == -2)
-                    return sv_fail(SIEVE_ERR_STATE, "node " + std::to_string(v) + " is needed but was never computed (no children given)");
-                const bool na = needs(a), nb = b >= 0 && needs(b);
-                f.first = f.last = -1;
-                if (na && nb) {
-                    const int small = h->sparse ? h->keep_T : h->transient_T;
-                    const bool ta = leaves[a] <= small, tb = leaves[b] <= small;
-                    int last;
-                    if (ta != tb)
-                        last = ta ? a : b;  // the transient one is consumed from registers and never written
-                    else
-                        last = leaves[a] >= leaves[b] ? a : b;
-                    f.last = last;
-                    f.first = last == a ? b : a;
-                } else if (na)
-                    f.last = a;
-                else if (nb)
-                    f.last = b;
-                f.stage = 1;
-                if (f.first >= 0) {
-                    const int nxt = f.first;
-                    st.push_back({nxt, 0, -1, -1});
-                }
-            } else if (f.stage == 1) {
-                f.stage = 2;
-                if (f.last >= 0) {
-                    const int nxt = f.last;
-                    st.push_back({nxt, 0, -1, -1});
-                }
-            } else {
-                visited[v] = 1;
-                emitted.push_back(v);  // the op itself is made below, when the destination slots are known
-                st.pop_back();
-            }
-        }
-        return SIEVE_OK;
-    };
-    // tops: dirty / demanded nodes without a dirty parent; ancestors of a dirty node are expected to be dirty too
-    for (int v = N - 1; v >= n; v--) {
-        if (!(dirty[v] || demanded[v]) || visited[v]) continue;
-        if (parent[v] >= 0 && dirty[parent[v]]) continue;  // reached through its parent
-        if (!dirty[v] && h->valid[v]) continue;             // demanded but already in memory
-        SV_TRY(run_from(v));
-    }
-    // a dirty node whose parent was dirty but never reached it (inconsistent input) would be skipped: check
-    for (int v : h->dirty_list)
-        if (dirty[v] && !visited[v]) SV_TRY(run_from(v));
-    // store decisions and ops, in walk order
-    std::vector<char> is_temp(h->sparse ? N : 0, 0);
-    for (size_t i = 0; i < emitted.size(); i++) {
-        const int v = emitted[i];
-        bool consumed_next = false;
-        if (i + 1 < emitted.size()) {
-            const int p = emitted[i + 1];
-            consumed_next = h->eph_c1[p] == v || h->eph_c2[p] == v;
-        }
-        bool store;
-        const size_t bi = (size_t)h->cur_part[v] * N + v;
-        if (!h->sparse) {
-            const bool transient = h->transient_T > 0 && v != root && leaves[v] <= h->transient_T;
-            store = !(transient && consumed_next) || demanded[v];
-        } else {
-            const bool kept = v == root || leaves[v] > h->keep_T;
-            store = kept || demanded[v] || !consumed_next;
-            if (store && h->slot_of[bi] < 0) {
-                const int sl = sv_slot_alloc(h);
-                if (sl < 0)
-                    return sv_fail(SIEVE_ERR_OOM, "the sparse partial pool is exhausted (" + std::to_string(h->pool_slots) +
-                                                      " slots): raise SIEVE_B200_POOL_SLOTS or free device memory");
-                h->slot_of[bi] = sl;
-                if (!kept) {
-                    if (demanded[v])
-                        h->held.push_back((int)bi);  // read back after this flush, released by the next plan
-                    else
-                        is_temp[v] = 1;              // an intermediate of a small subtree: recycled once its parent has consumed it
-                }
-            }
-        }
-        SvOp op;
-        SV_TRY(sv_make_op(h, h->eph_c1[v], h->eph_c2[v], v, &op));
-        if (!store) op.flags |= SV_OP_NOSTORE;
-        h->pending_ops.push_back(op);
-        h->valid[v] = store ? 1 : 0;
-        if (store) {
-            h->buf_has[bi] = 1;
-            h->buf_ver[bi] = h->ver_cur[v];
-            h->buf_fp[bi] = h->fp_cur[v];
-        }
-        // a clean subtree is identical in the stored state; its buffer is shared when the indices agree
-        if (store && !dirty[v] && h->cur_part[v] == h->stored_part[v]) h->valid_stored[v] = 1;
-        if (h->sparse) {
-            // this op was the consumer of its children's temporary slots
-            for (int c : {h->eph_c1[v], h->eph_c2[v]})
-                if (c >= n && is_temp[c]) {
-                    is_temp[c] = 0;
-                    sv_slot_release(h, h->cur_part[c], c);
-                }
-        }
-    }
-    if (h->sparse)
-        for (int v : emitted)
-            if (is_temp[v]) h->held.push_back(h->cur_part[v] * N + v);  // no consumer in this plan (inconsistent dirty set)
-    // (the constant-site factor follows the really dirty nodes only: queued by the change-tracking pass above)
-    h->dirty_list.clear();
-    h->demand_list.clear();
-    return SIEVE_OK;
-}
-
-// Register forwarding for the single-launch walk: when an op consumes the destination of the op right before it, that
-// child is made child 1 (the two children's contributions commute) and flagged.
-static void sv_link_forwarding(std::vector<SvOp>& ops, bool per_level) {
-    for (size_t i = 0; i < ops.size(); i++) {
-        SvOp& op = ops[i];
-        op.flags &= ~SV_OP_FWD1;
-        if (per_level || i == 0) continue;
-        const unsigned prev = ops[i - 1].dst_row;
-        const bool c1_int = !(op.flags & SV_OP_LEAF1);
-        const bool c2_int = !(op.flags & SV_OP_UNARY) && !(op.flags & SV_OP_LEAF2);
-        if (c2_int && op.c2_row == prev && !(c1_int && op.c1_row == prev)) {
-            std::swap(op.c1_row, op.c2_row);
-            std::swap(op.m1, op.m2);
-            const int l1 = op.flags & SV_OP_LEAF1;
-            op.flags &= ~(SV_OP_LEAF1 | SV_OP_LEAF2);
-            if (l1) op.flags |= SV_OP_LEAF2;
-        }
-        if (!(op.flags & SV_OP_LEAF1) && op.c1_row == prev) op.flags |= SV_OP_FWD1;
-    }
-}
-
-// ---- streamed (ephemeral) evaluation: the host keeps parent -> children and regenerates the walk every time --------
-static int sv_record_children(sieve_core* h, int c1, int c2, int parent) {
-    const int n = h->n;
-    SV_REQUIRE(parent >= n && parent < h->n_nodes, "op: parent must be an internal node");
-    SV_REQUIRE(c1 >= 0 && c1 < h->n_nodes && c1 != h->root, "op: bad child1");
-    SV_REQUIRE(c2 >= -1 && c2 < h->n_nodes && c2 != h->root, "op: bad child2");
-    if (h->eph_c1[parent] != c1 || h->eph_c2[parent] != c2) h->topo_cache_ok = false;
-    h->eph_c1[parent] = c1;
-    h->eph_c2[parent] = c2;
-    return SIEVE_OK;
-}
-
-// Post-order over the whole tree with the child that needs more scratch first (Sethi-Ullman), scratch slots assigned
-// from a free list: a binary tree of n leaves needs at most ~log2(n) + 2 live partials.
-static int sv_build_streamed_ops(sieve_core* h) {
-    const int n = h->n, N = h->n_nodes, root = h->root;
-    const long long cap = h->chunk_cap;
-    std::vector<int> order;  // children before parents
-    order.reserve(n);
-    std::vector<std::pair<int, int>> st;
-    st.push_back({root, 0});
-    while (!st.empty()) {
-        auto [v, state] = st.back();
-        st.pop_back();
-        if (v < n) continue;
-        if (h->eph_c1[v] == -2) return sv_fail(SIEVE_ERR_STATE, "streamed evaluation: node " + std::to_string(v) + " has no children set yet");
-        if (state == 0) {
-            st.push_back({v, 1});
-            if (h->eph_c2[v] >= 0) st.push_back({h->eph_c2[v], 0});
-            st.push_back({h->eph_c1[v], 0});
-        } else
-            order.push_back(v);
-    }
-    std::vector<int> need(N, 0);
-    for (int v : order) {
-        int a = h->eph_c1[v], b = h->eph_c2[v];
-        int na = a >= n ? need[a] : 0, nb = (b >= n) ? need[b] : 0;
-        if (na < nb) std::swap(na, nb);
-        const int internal = (a >= n) + (b >= n);
-        need[v] = internal == 0 ? 1 : (internal == 1 ? std::max(na, 2) : std::max(std::max(na, nb + 1), 3));
-    }
-    if (need[root] > h->n_slots)
-        return sv_fail(SIEVE_ERR_STATE, "streamed evaluation: the tree needs " + std::to_string(need[root]) + " scratch slots, " +
-                                            std::to_string(h->n_slots) + " allocated");
-    std::vector<int> free_slots;
-    for (int s = h->n_slots - 1; s >= 0; s--) free_slots.push_back(s);
-    std::vector<int> slot_of(N, -1);
-    h->pending_ops.clear();
-    h->pending_levels.clear();
-    h->pending_per_level = false;
-    st.push_back({root, 0});
-    while (!st.empty()) {
-        auto [v, state] = st.back();
-        st.pop_back();
-        if (v < n) continue;
-        int a = h->eph_c1[v], b = h->eph_c2[v];
-        if (state == 0) {
-            st.push_back({v, 1});
-            // heavier child first == pushed last
-            const int na = a >= n ? need[a] : 0, nb = b >= n ? need[b] : 0;
-            if (na >= nb) {
-                if (b >= n) st.push_back({b, 0});
-                if (a >= n) st.push_back({a, 0});
-            } else {
-                if (a >= n) st.push_back({a, 0});
-                if (b >= n) st.push_back({b, 0});
-            }
-        } else {
-            SvOp op;
-            op.flags = 0;
-            op.pad0 = op.pad1 = 0;
-            const int dst = free_slots.back();
-            free_slots.pop_back();
-            slot_of[v] = dst;
-            op.dst_row = (unsigned)((long long)dst * cap);
-            auto child = [&](int c, int leaf_flag, unsigned* row, int* m) {
-                if (c < n) {
-                    op.flags |= leaf_flag;
-                    *row = (unsigned)((long long)c * cap);
-                } else
-                    *row = (unsigned)((long long)slot_of[c] * cap);
-                *m = h->cur_mat[c] * N + c;
-                if (h->log_mode && h->slot_zero[*m]) op.flags |= SV_OP_ZEROD;
-            };
-            child(a, SV_OP_LEAF1, &op.c1_row, &op.m1);
-            if (b < 0) {
-                op.flags |= SV_OP_UNARY;
-                op.c2_row = 0;
-                op.m2 = 0;
-            } else
-                child(b, SV_OP_LEAF2, &op.c2_row, &op.m2);
-            if (v == root) op.flags |= SV_OP_ROOT;
-            h->pending_ops.push_back(op);
-            h->g_nodes.push_back(v);
-            if (a >= n) free_slots.push_back(slot_of[a]);
-            if (b >= n) free_slots.push_back(slot_of[b]);
-        }
-    }
-    return SIEVE_OK;
-}
+#include "core_planner.cuh"
 
 extern "C" int sieve_calculate_partials(sieve_core_t* h, int32_t child1, int32_t is_leaf1, int32_t child2, int32_t is_leaf2,
                                         int32_t parent, int32_t const_genotype) {
@@ -1991,280 +1242,7 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     return SIEVE_OK;
 }
 
-// ---- max-sum pass: maximum-likelihood genotypes for variant calling (maxsum.cuh) --------------------------------
-// Post-order list of the whole current tree from the children the core has recorded (the planner's map).
-static int sv_ml_build_ops(sieve_core* h, std::vector<SvMlOp>& ops) {
-    const int n = h->n;
-    if (h->root < 0) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: sieve_set_root has not been called");
-    std::vector<std::pair<int, int>> st;
-    st.push_back({h->root, 0});
-    while (!st.empty()) {
-        auto [v, state] = st.back();
-        st.pop_back();
-        if (v < n) continue;
-        const int a = h->eph_c1[v], b = h->eph_c2[v];
-        if (a == -2) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: the tree has a node that was never computed");
-        if (state == 0) {
-            st.push_back({v, 1});
-            if (b >= 0) st.push_back({b, 0});
-            st.push_back({a, 0});
-        } else {
-            SvMlOp op{};
-            op.dst = v - n;
-            op.n1 = a;
-            op.c1 = a < n ? a : a - n;
-            if (a < n) op.flags |= SV_OP_LEAF1;
-            if (b < 0) {
-                op.flags |= SV_OP_UNARY;
-                op.c2 = -1;
-                op.n2 = 0;
-            } else {
-                op.n2 = b;
-                op.c2 = b < n ? b : b - n;
-                if (b < n) op.flags |= SV_OP_LEAF2;
-            }
-            ops.push_back(op);
-        }
-    }
-    return SIEVE_OK;
-}
-
-static int sv_ml_require(sieve_core* h, const char* who) {
-    if (!h) return sv_fail(SIEVE_ERR_INVALID, std::string(who) + ": null handle");
-    if (!h->ml_ready) return sv_fail(SIEVE_ERR_STATE, std::string(who) + ": call sieve_ml_trace first (and again after any change)");
-    return SIEVE_OK;
-}
-
-extern "C" int sieve_ml_trace(sieve_core_t* h) {
-    SV_REQUIRE(h, "null handle");
-    if (h->ephemeral || h->sparse)
-        return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: needs fully resident partials (not SIEVE_FLAG_EPHEMERAL / SIEVE_FLAG_SPARSE)");
-    if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: leaves not computed yet");
-    SV_CUDA(cudaSetDevice(h->device));
-    SV_TRY(sv_flush(h));
-    const size_t n = h->n, S = h->S, K = h->K, N = h->n_nodes, lanes = S * K;
-    std::vector<SvMlOp> ops;
-    SV_TRY(sv_ml_build_ops(h, ops));
-    SV_REQUIRE(!ops.empty() && ops.back().dst == h->root - (int)n, "sieve_ml_trace: the root is not the last node of the tree");
-    // the root's sum-product partial decides the ML category; make sure it is materialised
-    if (!h->valid[h->root]) {
-        h->demand_list.push_back(h->root);
-        SV_TRY(sv_flush(h));
-    }
-    if (!h->ml_alloc) {
-        SV_TRY(sv_alloc(h, &h->d_mlL, n * S * 4));
-        SV_TRY(sv_alloc(h, &h->d_mlado, n * S));
-        SV_TRY(sv_alloc(h, &h->d_ml, n * lanes * 4));
-        SV_TRY(sv_alloc(h, &h->d_mlback, n * lanes));
-        SV_TRY(sv_alloc(h, &h->d_mlcoll, N * lanes));
-        SV_TRY(sv_alloc(h, &h->d_mladosel, n * lanes));
-        SV_TRY(sv_alloc(h, &h->d_mlamb, lanes));
-        SV_TRY(sv_alloc(h, &h->d_mlcats, S));
-        SV_TRY(sv_alloc(h, &h->d_mllogm, N * K * 16));
-        SV_TRY(sv_alloc(h, &h->d_mlops, n));
-        SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
-        h->ml_alloc = true;
-    }
-    // log P on the host, in double precision with the reference's clamp (ScsBeerLikelihoodCore.java:3100-3101)
-    std::vector<double> mats((size_t)2 * N * SV_KMAX * 16), logm(N * K * 16);
-    SV_CUDA(cudaMemcpyAsync(mats.data(), h->d_mats, mats.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    SV_CUDA(cudaStreamSynchronize(h->stream));
-    for (size_t v = 0; v < N; v++)
-        for (size_t k = 0; k < K; k++)
-            for (int e = 0; e < 16; e++) {
-                const double P = mats[((size_t)h->cur_mat[v] * N + v) * SV_KMAX * 16 + k * 16 + e];
-                logm[(v * K + k) * 16 + e] = std::log(P > 0.0 ? P : SV_MIN_VALUE);
-            }
-    SV_CUDA(cudaMemcpyAsync(h->d_mllogm, logm.data(), logm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    SV_CUDA(cudaMemcpyAsync(h->d_mlops, ops.data(), ops.size() * sizeof(SvMlOp), cudaMemcpyHostToDevice, h->stream));
-    h->ml_n_ops = (int)ops.size();
-
-    SvMlLeafArgs la;
-    la.counts = h->d_counts;
-    la.dmA = h->d_dmA;
-    la.dmB = h->d_dmB;
-    la.cellL = h->d_mlcellL;
-    la.size_factors = h->d_sf;
-    la.leafL = h->d_mlL;
-    la.ado = h->d_mlado;
-    la.n_cells = (int)n;
-    la.S = (int)S;
-    la.C = h->C;
-    // the tables on the device were built with tab_lp: the parameters of the leaves that are current
-    la.al = sv_dm_alphas(h->tab_lp.eff_seq_err_rate, h->tab_lp.shape_ctrl1, h->tab_lp.shape_ctrl2);
-    la.cp.t = h->tab_lp.allelic_seq_cov;
-    la.cp.v = h->tab_lp.allelic_seq_cov_raw_var;
-    la.cp.theta = h->tab_lp.ado_rate;
-    la.cp.single_ado = h->single_ado ? 1 : 0;
-    k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
-                                                                                                  (int)n, h->C, la.cp);
-    sv_count(h);
-    k_leaf_ml<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(la);
-    sv_count(h);
-
-    SvMlArgs a;
-    a.ops = h->d_mlops;
-    a.n_ops = h->ml_n_ops;
-    a.leafL = h->d_mlL;
-    a.ado = h->d_mlado;
-    a.logm = h->d_mllogm;
-    a.ml = h->d_ml;
-    a.back = h->d_mlback;
-    a.coll = h->d_mlcoll;
-    a.ado_sel = h->d_mladosel;
-    a.ambiguous = h->d_mlamb;
-    a.S = (int)S;
-    a.K = (int)K;
-    a.n_leaves = (int)n;
-    a.root_genotype = h->root_genotype;
-    const unsigned blocks = (unsigned)((lanes + 127) / 128);
-    k_ml_up<<<blocks, 128, 0, h->stream>>>(a);
-    sv_count(h);
-    k_ml_down<<<blocks, 128, 0, h->stream>>>(a);
-    sv_count(h);
-    const size_t rslot = (size_t)h->cur_part[h->root] * h->n_internal + (h->root - n);
-    k_ml_categories<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(h->d_part + rslot * S * SV_KMAX * 4, (int)S,
-                                                                       (int)K, h->root_genotype, h->d_mlcats);
-    sv_count(h);
-    SV_CUDA(cudaGetLastError());
-    SV_CUDA(cudaStreamSynchronize(h->stream));
-    h->ml_ready = true;
-    return SIEVE_OK;
-}
-
-extern "C" int sieve_ml_call(sieve_core_t* h, int8_t* genotypes, int8_t* ado, uint8_t* category, uint8_t* ambiguous) {
-    SV_TRY(sv_ml_require(h, "sieve_ml_call"));
-    SV_REQUIRE(genotypes && ado && category && ambiguous, "sieve_ml_call: null output");
-    SV_CUDA(cudaSetDevice(h->device));
-    const size_t n = h->n, S = h->S, N = h->n_nodes;
-    signed char *d_g = nullptr, *d_a = nullptr;
-    unsigned char *d_c = nullptr, *d_m = nullptr;
-    cudaError_t e = cudaMalloc(&d_g, N * S);
-    if (e == cudaSuccess) e = cudaMalloc(&d_a, n * S);
-    if (e == cudaSuccess) e = cudaMalloc(&d_c, S);
-    if (e == cudaSuccess) e = cudaMalloc(&d_m, S);
-    if (e == cudaSuccess) {
-        k_ml_call<<<dim3((unsigned)((S + 255) / 256), (unsigned)N), 256, 0, h->stream>>>(
-            h->d_mlcoll, h->d_mladosel, h->d_mlcats, h->d_mlamb, (int)S, h->K, (int)N, (int)n, d_g, d_a, d_c, d_m);
-        sv_count(h);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(genotypes, d_g, N * S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ado, d_a, n * S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(category, d_c, S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ambiguous, d_m, S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_g);
-    cudaFree(d_a);
-    cudaFree(d_c);
-    cudaFree(d_m);
-    SV_CUDA(e);
-    return SIEVE_OK;
-}
-
-extern "C" int sieve_ml_get_categories(sieve_core_t* h, uint8_t* out) {
-    SV_TRY(sv_ml_require(h, "sieve_ml_get_categories"));
-    SV_REQUIRE(out, "null output");
-    SV_CUDA(cudaSetDevice(h->device));
-    SV_CUDA(cudaMemcpyAsync(out, h->d_mlcats, (size_t)h->S, cudaMemcpyDeviceToHost, h->stream));
-    SV_CUDA(cudaStreamSynchronize(h->stream));
-    return SIEVE_OK;
-}
-
-// Reference layouts: ml_partials [K][S][4] (MLPartials[..][node - nrOfLeafNodes]), back [K][S][4] (one byte per
-// MLGenotypesNodes[..][node][(k, s, parent genotype)]: low nibble = list of child 0, high nibble = list of child 1; for a
-// leaf the byte is the list of arg-max dropout components), collection [K][S] (MLGenotypesCollection).
-extern "C" int sieve_ml_get_node(sieve_core_t* h, int32_t node, double* ml_partials, uint8_t* back, uint8_t* collection) {
-    SV_TRY(sv_ml_require(h, "sieve_ml_get_node"));
-    SV_REQUIRE(sv_node_ok(h, node), "sieve_ml_get_node: bad node");
-    SV_CUDA(cudaSetDevice(h->device));
-    const size_t n = h->n, S = h->S, K = h->K, lanes = S * K;
-    if (collection) {
-        std::vector<unsigned char> c(lanes);
-        SV_CUDA(cudaMemcpyAsync(c.data(), h->d_mlcoll + (size_t)node * lanes, lanes, cudaMemcpyDeviceToHost, h->stream));
-        SV_CUDA(cudaStreamSynchronize(h->stream));
-        for (size_t s = 0; s < S; s++)
-            for (size_t k = 0; k < K; k++) collection[k * S + s] = c[s * K + k];
-    }
-    if ((size_t)node < n) {
-        if (ml_partials) {
-            std::vector<double> v(S * 4);
-            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlL + (size_t)node * S * 4, S * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            SV_CUDA(cudaStreamSynchronize(h->stream));
-            for (size_t k = 0; k < K; k++) memcpy(ml_partials + k * S * 4, v.data(), S * 4 * sizeof(double));
-        }
-        if (back) {
-            std::vector<unsigned short> v(S);
-            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlado + (size_t)node * S, S * sizeof(unsigned short), cudaMemcpyDeviceToHost, h->stream));
-            SV_CUDA(cudaStreamSynchronize(h->stream));
-            for (size_t k = 0; k < K; k++)
-                for (size_t s = 0; s < S; s++)
-                    for (int g = 0; g < 4; g++) back[(k * S + s) * 4 + g] = (uint8_t)((v[s] >> (4 * g)) & 15u);
-        }
-        return SIEVE_OK;
-    }
-    const size_t idx = (size_t)node - n;
-    if (ml_partials) {
-        std::vector<double> v(lanes * 4);
-        SV_CUDA(cudaMemcpyAsync(v.data(), h->d_ml + idx * lanes * 4, lanes * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        SV_CUDA(cudaStreamSynchronize(h->stream));
-        for (size_t s = 0; s < S; s++)
-            for (size_t k = 0; k < K; k++) memcpy(ml_partials + (k * S + s) * 4, v.data() + (s * K + k) * 4, 4 * sizeof(double));
-    }
-    if (back) {
-        std::vector<unsigned> v(lanes);
-        SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlback + idx * lanes, lanes * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-        SV_CUDA(cudaStreamSynchronize(h->stream));
-        for (size_t s = 0; s < S; s++)
-            for (size_t k = 0; k < K; k++) memcpy(back + (k * S + s) * 4, &v[s * K + k], 4);
-    }
-    return SIEVE_OK;
-}
-
-// One site, every node: back-pointer bytes [node][K][4] and sum-product log partials [node][K][4] -- what a host needs
-// to enumerate and rank the tied combinations of an ambiguous site (ScsTreeLikelihood.java:2083-2160).
-extern "C" int sieve_ml_get_site(sieve_core_t* h, int32_t site, uint8_t* back, double* log_partials) {
-    SV_TRY(sv_ml_require(h, "sieve_ml_get_site"));
-    SV_REQUIRE(site >= 0 && site < h->S && back && log_partials, "sieve_ml_get_site: bad argument");
-    SV_CUDA(cudaSetDevice(h->device));
-    const int n = h->n, N = h->n_nodes, K = h->K;
-    // every internal partial has to be in memory: recompute the transient ones (once; they stay valid)
-    bool missing = false;
-    for (int v = n; v < N; v++)
-        if (!h->valid[v]) {
-            h->demand_list.push_back(v);
-            missing = true;
-        }
-    if (missing) {
-        const bool keep = h->ml_ready;
-        SV_TRY(sv_flush(h));
-        h->ml_ready = keep;  // recomputing a partial into its buffer changes no value
-    }
-    std::vector<unsigned> rows(N, 0u);
-    for (int v = n; v < N; v++) rows[v] = (unsigned)(((size_t)h->cur_part[v] * h->n_internal + (v - n)) * h->S);
-    unsigned* d_rows = nullptr;
-    unsigned char* d_b = nullptr;
-    double* d_p = nullptr;
-    const size_t cnt = (size_t)N * K * 4;
-    cudaError_t e = cudaMalloc(&d_rows, N * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMalloc(&d_b, cnt);
-    if (e == cudaSuccess) e = cudaMalloc(&d_p, cnt * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, rows.data(), N * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-        k_ml_site_gather<<<(N * K + 127) / 128, 128, 0, h->stream>>>(h->d_mlback, h->d_mlado, h->d_mlL, h->d_part, h->d_scale,
-                                                                   d_rows, h->S, K, n, N, site, d_b, d_p);
-        sv_count(h);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(back, d_b, cnt, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(log_partials, d_p, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_rows);
-    cudaFree(d_b);
-    cudaFree(d_p);
-    SV_CUDA(e);
-    return SIEVE_OK;
-}
+#include "core_maxsum.cuh"
 
 // ---- store / restore ------------------------------------------------------------------------------------------
 extern "C" int sieve_store(sieve_core_t* h) {
