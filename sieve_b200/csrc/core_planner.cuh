@@ -220,6 +220,10 @@ static int sv_plan_resident_ops(sieve_core* h) {
         }
     }
     // ---- change tracking: which of the dirty nodes really get a new value? (children before parents) ----
+    if (h->prov_touched.size() > (size_t)8 * N) {  // a caller that never stores: keep the list a set
+        std::sort(h->prov_touched.begin(), h->prov_touched.end());
+        h->prov_touched.erase(std::unique(h->prov_touched.begin(), h->prov_touched.end()), h->prov_touched.end());
+    }
     {
         std::vector<char> done(N, 0);
         std::vector<std::pair<int, int>> st;
@@ -265,6 +269,7 @@ static int sv_plan_resident_ops(sieve_core* h) {
                         h->valid[v] = 1;
                         h->ver_cur[v] = h->buf_ver[(size_t)hit * N + v];
                         h->fp_cur[v] = f;
+                        h->prov_touched.push_back(v);
                         dirty[v] = 0;
                         h->elided_total++;
                         if (!h->G.empty() && h->g_ver[(size_t)h->cur_part[v] * N + v] != h->ver_cur[v]) h->g_nodes.push_back(v);
@@ -277,6 +282,7 @@ static int sv_plan_resident_ops(sieve_core* h) {
                         h->valid[v] = 0;
                         h->ver_cur[v] = h->ver_stored[v];
                         h->fp_cur[v] = f;
+                        h->prov_touched.push_back(v);
                         dirty[v] = 0;
                         h->elided_total++;
                         if (!h->G.empty() && h->g_ver[(size_t)h->cur_part[v] * N + v] != h->ver_cur[v]) h->g_nodes.push_back(v);
@@ -285,6 +291,7 @@ static int sv_plan_resident_ops(sieve_core* h) {
                 }
                 h->ver_cur[v] = ++h->ver_counter;
                 h->fp_cur[v] = known ? f : sieve_core::SvFp();
+                h->prov_touched.push_back(v);
                 h->g_nodes.push_back(v);  // children first: this pass is a post-order over the dirty nodes
             }
         }

@@ -155,6 +155,7 @@ struct sieve_core {
     std::vector<char> buf_has;          // [2 * n_nodes] the partial buffer holds a value ...
     std::vector<uint64_t> buf_ver;      // ... of this version ...
     std::vector<SvFp> buf_fp;           // ... computed from these inputs
+    std::vector<int> prov_touched;  // nodes whose ver_cur / fp_cur were written since the last store
     std::vector<uint64_t> ver_cur, ver_stored;  // [n_nodes] version of the node's value in the current / stored state
     std::vector<SvFp> fp_cur, fp_stored;        // ... and what it was computed from
 

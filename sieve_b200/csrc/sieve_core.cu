@@ -769,6 +769,7 @@ extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t*
         h->valid[ops[3 * i]] = 1;
         h->ver_cur[ops[3 * i]] = ++h->ver_counter;  // computed outside the planner: a new value of unknown provenance
         h->fp_cur[ops[3 * i]] = sieve_core::SvFp();
+        h->prov_touched.push_back(ops[3 * i]);
         {
             const size_t bi = (size_t)h->cur_part[ops[3 * i]] * h->n_nodes + ops[3 * i];
             h->buf_has[bi] = 1;
@@ -1257,9 +1258,13 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->eph_c2_stored = h->eph_c2;
     h->valid_stored = h->valid;
     h->log_c_stored = h->log_c;
-    // (only internal nodes carry a value version / provenance: leaves are versioned per buffer)
-    std::copy(h->ver_cur.begin() + h->n, h->ver_cur.end(), h->ver_stored.begin() + h->n);
-    std::copy(h->fp_cur.begin() + h->n, h->fp_cur.end(), h->fp_stored.begin() + h->n);
+    // value versions / provenance: the current and the stored arrays differ only where a plan has written since the last
+    // store (restore swaps the arrays, which keeps that true), so only those entries are copied
+    for (int v : h->prov_touched) {
+        h->ver_stored[v] = h->ver_cur[v];
+        h->fp_stored[v] = h->fp_cur[v];
+    }
+    h->prov_touched.clear();
     if (h->sparse)  // what only the previous stored state referred to gives its slot back
         for (int v = h->n; v < h->n_nodes; v++) sv_slot_release(h, 1 - h->cur_part[v], v);
     return SIEVE_OK;
@@ -1285,8 +1290,11 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
     h->eph_c2 = h->eph_c2_stored;
     h->valid = h->valid_stored;
     h->log_c = h->log_c_stored;
-    h->ver_cur = h->ver_stored;
-    h->fp_cur = h->fp_stored;
+    for (int v : h->prov_touched) {
+        h->ver_cur[v] = h->ver_stored[v];
+        h->fp_cur[v] = h->fp_stored[v];
+    }
+    h->prov_touched.clear();
     h->topo_cache_ok = false;
     h->ml_ready = false;
     return SIEVE_OK;

@@ -134,6 +134,8 @@ struct sieve_mcmc {
     std::vector<double> dist;
     std::vector<int> op_list;
     std::vector<int> stack, order;
+    std::vector<int> cand, rate_touched;  // evaluate(): nodes whose branch time may have moved
+    bool scan_all = true;                 // ... or all of them (whole-tree moves, first evaluation)
     std::string err;
     std::vector<sieve_shard_result_t> world_results;
     sieve_combine_fn combine = nullptr;
@@ -181,8 +183,8 @@ int evaluate(sieve_mcmc* m, bool full, bool update_leaves, double* out_logp, int
     std::fill(m->need.begin(), m->need.end(), 0);
     m->mat_nodes.clear();
     m->dist.clear();
-    for (int i = 0; i < N; i++) {
-        if (i == t.root()) continue;
+    auto visit = [&](int i) {
+        if (i == t.root()) return;
         const double bt = branch_len(t, i) * m->cfg.clock_rate * m->rate[i];
         // traverse, :563: refresh when the node is dirty or its branch time differs from the stored one
         if (full || m->dirty[i] || bt != m->branch_time[i]) {
@@ -192,6 +194,25 @@ int evaluate(sieve_mcmc* m, bool full, bool update_leaves, double* out_logp, int
             // its parent (and all ancestors) must be recomputed, :621-628
             for (int p = t.parent[i]; p >= 0 && !m->need[p]; p = t.parent[p]) m->need[p] = 1;
         }
+    };
+    if (full || m->scan_all) {
+        for (int i = 0; i < N; i++) visit(i);
+    } else {
+        // The reference's traverse visits every node; a branch time can only have moved where an operator touched the
+        // node (height or parent link: every move flags those) or its parent's height -- so the flagged nodes and their
+        // children are the only candidates.  Same outcome, O(flagged) instead of O(nodes) per state (node order kept).
+        m->cand = m->rate_touched;  // a rate proposal changes a branch time without flagging the node
+        for (int i = 0; i < N; i++)
+            if (m->dirty[i]) {
+                m->cand.push_back(i);
+                if (!t.is_leaf(i)) {
+                    m->cand.push_back(t.left[i]);
+                    if (t.right[i] >= 0) m->cand.push_back(t.right[i]);
+                }
+            }
+        std::sort(m->cand.begin(), m->cand.end());
+        m->cand.erase(std::unique(m->cand.begin(), m->cand.end()), m->cand.end());
+        for (int i : m->cand) visit(i);
     }
     if (full || update_leaves)
         for (int i = t.n; i < N; i++) m->need[i] = 1;
@@ -256,6 +277,7 @@ bool move_tree_scale(sieve_mcmc* m, double* lh) {
     Tree& t = m->tree;
     const double s = scale_draw(m, 0.95);
     for (int i = t.n; i < t.node_count(); i++) t.height[i] *= s;  // leaves stay at height 0
+    m->scan_all = true;  // every branch time moves and no node is flagged: evaluate() looks at all of them
     *lh = (t.n - 2) * std::log(s);
     return true;
 }
@@ -483,6 +505,7 @@ bool move_branch_rate(sieve_mcmc* m, double* lh) {
     } while (i == t.root());
     const double s = scale_draw(m, 0.75);
     m->rate[i] *= s;
+    m->rate_touched.push_back(i);
     *lh = -std::log(s);
     return true;
 }
@@ -633,6 +656,8 @@ extern "C" int sieve_mcmc_run(sieve_mcmc_t* m, int64_t n_states, int32_t reset, 
         } else {
             store(m);
             std::fill(m->dirty.begin(), m->dirty.end(), 0);
+            m->rate_touched.clear();
+            m->scan_all = false;
             double lh = 0.0;
             bool valid = false, full = false, leaves = false;
             switch (ow.cls) {
