@@ -208,7 +208,9 @@ static int sv_plan_resident_ops(sieve_core* h) {
             return c;
         };
         int T = std::max(h->keep_T, 1);
-        while (2 * (long long)kept_count(T) + 64 > h->pool_slots && T < (1 << 28)) T += std::max(1, T / 4);
+        // (a pool with a slot for every (buffer, node) keeps everything, like a dense core)
+        while (h->pool_slots < 2 * h->n_internal && 2 * (long long)kept_count(T) + 64 > h->pool_slots && T < (1 << 28))
+            T += std::max(1, T / 4);
         if (T != h->keep_T || h->sparse_recheck) {
             h->keep_T = T;
             for (int v = n; v < N; v++)

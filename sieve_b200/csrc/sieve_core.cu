@@ -118,7 +118,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         size_t slots = free0 > fixed ? (free0 - fixed) / per_slot : 0;
         if (const char* e = getenv("SIEVE_B200_POOL_SLOTS")) slots = (size_t)std::max(0, atoi(e));
         slots = std::min<size_t>(slots, 2 * n);
-        if (slots < 96) {
+        if (slots < std::min<size_t>(96, 2 * n)) {
             g_err = "sieve_create: SIEVE_FLAG_SPARSE needs room for at least 96 partial slots";
             return fail(SIEVE_ERR_OOM);
         }

@@ -880,15 +880,16 @@ def test_smallest_trees(core_mod, oracle, n):
     sf = np.ones(n) if n == 1 else oracle.size_factors(c5)[0]
     rates, props = substmodel.gamma_category_rates(1.3, 4)
     mats = substmodel.node_matrices(tree, rates)
-    for mode in ("distances", "matrices"):
-        c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True)
+    for mode in ("distances", "matrices", "sparse"):
+        c = core_mod.ScsCudaLikelihoodCore(n, S, 4, 4, True, True, True, sparse=mode == "sparse",
+                                           single_leaf_buffer=mode == "sparse")
         c.set_counts(counts)
         c.set_size_factors(sf)
         c.set_leaf_params(*PARAMS)
         c.update_leaves(for_update=False)
         c.set_root(tree.root, props, 0)
         nodes = [i for i in range(tree.node_count) if i != tree.root]
-        if mode == "distances":
+        if mode != "matrices":
             c.set_distances(nodes, substmodel.node_distances(tree, rates)[nodes], for_update=False)
         else:
             c.set_matrices(nodes, mats[nodes], for_update=False)
