@@ -1,0 +1,6 @@
+mkdir -p gpurun_out/exp5
+python -m pytest tests -m gpu -x -q > gpurun_out/exp5/pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/exp5/pytest.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --mcmc-states 0 --no-variants > gpurun_out/exp5/s100k.json 2> gpurun_out/exp5/s100k.err
+SIEVE_BENCH_SITES=125000 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --mcmc-states 0 --no-variants > gpurun_out/exp5/s125k.json 2> gpurun_out/exp5/s125k.err
+( time SIEVE_BENCH_CELLS=10000 SIEVE_BENCH_SITES=125000 python bench.py --sparse --steps 5 --warmup 3 --no-cpu-baseline --no-variants --mcmc-states 200 > gpurun_out/exp5/cfg4_sparse.json ) 2> gpurun_out/exp5/cfg4_sparse.err

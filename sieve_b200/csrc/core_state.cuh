@@ -37,6 +37,8 @@ struct sieve_core {
     uint64_t launches = 0;
     int step_launches = 0;  // since the last evaluate
     bool leaf_attr_set = false;
+    int leaf_tab = 1;    // SIEVE_B200_LEAF_TAB: where k_leaf reads its tables from (sv_launch_leaf_kernels)
+    int prune_minb = 0;  // SIEVE_B200_PRUNE_MINB: 6, 7 or 8 resident blocks per SM for the variant-only Q walk (0: chosen per launch)
 
     // device pools
     int4* d_counts = nullptr;  // [cell][site]
@@ -46,7 +48,11 @@ struct sieve_core {
     double *d_dmA = nullptr, *d_dmB = nullptr, *d_cellT = nullptr;
     int C = 0;  // table entries per table
     int max_cov = -1;
-    double *d_leafX = nullptr, *d_leafS = nullptr;                                       // [2][n][S][4], [2][n][S]
+    double* d_leafX = nullptr;                                                           // [2][n][S][4]
+    // the leaves' log scales are kept only as their sum over the cells (leaf.cuh): per-cell-group partial sums (scratch)
+    // and, per leaf buffer, the per-site total that the root adds
+    double *d_sumS = nullptr, *d_sum0 = nullptr;  // [cell groups][site]
+    double* d_lsum = nullptr;                     // [leaf buffers][site]
     double *d_part = nullptr, *d_scale = nullptr, *d_cpart = nullptr, *d_cscale = nullptr;  // [2][n_internal][S][K][4]
     double* d_mats = nullptr;                                                            // [2][n_nodes][4][16]
     double2* d_qfac = nullptr;                                                           // [2][n_nodes][4]
@@ -55,8 +61,7 @@ struct sieve_core {
     double *d_site_logl = nullptr, *d_site_const = nullptr;
     // algebraic constant-site path (default when SIEVE_FLAG_CONST_PARTIALS): see k_colsum in reduce.cuh
     bool const_twin = false;     // SIEVE_B200_CONST_TWIN=1: prune the constant-site partials per site like the reference
-    double* d_leaf0 = nullptr;   // [leaf buffers][cell][site] constant-genotype log-likelihood of every leaf
-    double* d_lambda = nullptr;  // [leaf buffers][site] its sum over cells
+    double* d_lambda = nullptr;  // [leaf buffers][site] sum over cells of the leaves' constant-genotype log-likelihood
     std::vector<double> hP;      // [2][node][K][16] host mirror of the (clamped) transition matrices
     std::vector<double> G, Gs;   // [2][node][K][4] site-independent factor of the constant-site partials + log-scale
     double log_c = 0.0, log_c_stored = 0.0;  // log sum_k prop_k G_root[k][root genotype]

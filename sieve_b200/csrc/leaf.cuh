@@ -170,158 +170,223 @@ __device__ __noinline__ SvD4 sv_cov_entry_direct(int x, double s, SvCovParams cp
 }
 
 // ---- the leaf kernel -------------------------------------------------------------------------------------------
+// One block = SV_LEAF_SITES sites x one GROUP of SV_LEAF_CELLS cells, cells taken one after the other.  Per (cell, site)
+// the kernel writes only the four scaled genotype likelihoods (32 B).  The natural-log scale of a leaf is NOT stored
+// per leaf: scales are additive along the pruning, so whatever the tree looks like, the scales of all leaves arrive at the
+// root as their plain sum over the cells.  The block therefore accumulates, per site and in registers, the sum of the
+// scales of its cells (and of the constant genotype's log-likelihoods, the column sum Lambda of the algebraic
+// constant-site path) and writes one partial sum per (cell group, site); k_colsum adds the groups in index order.  The
+// walk adds the sum once, at the root (prune.cuh).  Groups are a fixed number of consecutive cells, independent of the
+// site range, so resident, sparse and streamed evaluations produce the same bits.
 struct SvLeafArgs {
     const int4* counts;     // [cell][site] (alt1, alt2, alt3, cov)
     const double* dmA;      // [C][4]
     const double* dmB;      // [C][2]
     const double* cellT;    // [cell][C][4]
     const double* size_factors;
-    double* leafX;          // [cell][site][4]   (already offset to the write buffer)
-    double* leafS;          // [cell][site]
-    double* leaf0;          // [cell][site] log-likelihood of the constant genotype (x[cg] and the scale folded), or NULL
+    const int* cell_list;   // NULL: entry e is cell e; else the cells to evaluate (read-back of a subtree's sums)
+    double* leafX;          // [cell][site][4] (already offset to the write buffer), or NULL: sums only
+    double* sumS;           // [cell group][sum_stride] sum over the group's cells of the leaves' log scales
+    double* sum0;           // [cell group][sum_stride] ... of the constant genotype's log-likelihoods, or NULL
     int const_genotype;
-    int n_cells, S, C;     // S = sites evaluated by this launch
+    int n_cells, S, C;     // n_cells = entries evaluated; S = sites evaluated by this launch
     long long counts_stride;  // sites per cell in `counts` (the whole shard)
     long long site_begin;     // first site of this launch inside the shard (streamed evaluation walks site chunks)
-    long long out_stride;     // sites per cell in leafX / leafS (== S when resident, chunk capacity when streamed)
-    int sites_per_block;
+    long long out_stride;     // sites per cell in leafX (== S when resident, chunk capacity when streamed)
+    long long sum_stride;     // sites per cell group in sumS / sum0
     SvDmAlphas al;
     SvCovParams cp;
 };
 
-#ifndef SV_LEAF_MINB
-#define SV_LEAF_MINB 3
+#ifndef SV_LEAF_IT
+#define SV_LEAF_IT 4      // sites per thread and cell: four count tuples in flight per lane
 #endif
-#ifndef SV_LEAF_PREFETCH
-#define SV_LEAF_PREFETCH 1
-#endif
-template <bool SMEM_TABLES>
-__global__ void __launch_bounds__(256, SV_LEAF_MINB) k_leaf(SvLeafArgs a) {
-    extern __shared__ double sm[];
-    const int j = blockIdx.y;
+#define SV_LEAF_CELLS 32  // cells per group (fixed: the grouping of the sums must not depend on the launch)
+
+__device__ __forceinline__ void sv_leaf_cp16(double* dst_smem, const double* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sv_leaf_cp_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// one (cell, site): x[4] scaled linear genotype likelihoods, ls their natural-log scale, l0 the constant genotype's
+// log-likelihood (only when want0)
+__device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restrict__ dmA, const double* __restrict__ dmB,
+                                             const double* __restrict__ cT, const int C, const double sf,
+                                             const SvLeafArgs& a, const bool want0, double (&x)[4], double& ls,
+                                             double& l0) {
+    const int cov = c.w;
+    const int ref = cov - (c.x + c.y + c.z);
+    double N0, N1, N2, N3;
+    if (cov == 0) {
+        // DirichletMultinomial.logDensity returns 1.0 for an empty site, log mode included (:29-30)
+        N0 = N1 = N2 = N3 = 1.0;
+    } else {
+        // LP terms: table when the count is inside it, else the same formula evaluated directly
+        auto lpA = [&](int cval, double (&o)[4]) {
+            const int ci = cval < 0 ? 0 : cval;
+            if (ci == 0) {
+                // LP(0, .) == 0 (DirichletMultinomial.java:49): most alt counts are 0, and skipping the look-up keeps
+                // the shared-memory pipe for the entries that carry information
+                o[0] = o[1] = o[2] = o[3] = 0.0;
+            } else if (ci < C) {
+                const double2 u = *reinterpret_cast<const double2*>(dmA + 4 * ci);
+                const double2 w = *reinterpret_cast<const double2*>(dmA + 4 * ci + 2);
+                o[0] = u.x; o[1] = u.y; o[2] = w.x; o[3] = w.y;
+            } else {
+                const SvD4 r = sv_dm_partials_direct(ci, a.al);
+                o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
+            }
+        };
+        // logDensity = LP(cov, a0) - (((LP(c1,a1) + LP(c2,a2)) + LP(c3,a3)) + LP(ref,a4)), summed left to right;
+        // table columns: [0] f*w1, [1] (1-eps)*w1, [2] (1/2-f)*w2, [3] f*w2
+        double T[4];
+        lpA(c.x, T);
+        double s0 = T[0], s1 = T[1], s2 = T[2], s3 = T[2];  // alt1: 0/0 f | 1/1 (1-eps) | 1/1' h | 0/1 h
+        lpA(c.y, T);
+        s0 += T[0]; s1 += T[0]; s2 += T[2]; s3 += T[3];      // alt2: f | f | h | f
+        lpA(c.z, T);
+        s0 += T[0]; s1 += T[0]; s2 += T[3]; s3 += T[3];      // alt3: f | f | f | f
+        lpA(ref, T);
+        s0 += T[1]; s1 += T[0]; s2 += T[3]; s3 += T[2];      // ref : (1-eps) | f | f | h
+        double B0, B1;
+        if (cov > 0 && cov < C) {
+            const double2 u = *reinterpret_cast<const double2*>(dmB + 2 * cov);
+            B0 = u.x; B1 = u.y;
+        } else {
+            const SvD2 r = sv_dm_totals_direct(cov, a.al);
+            B0 = r.a; B1 = r.b;
+        }
+        N0 = B0 - s0;
+        N1 = B0 - s1;
+        N2 = B1 - s2;
+        N3 = B1 - s3;
+    }
+    double e[4];
+    if (cov >= 0 && cov < C) {
+        const double2 u = *reinterpret_cast<const double2*>(cT + 4 * cov);
+        const double2 w = *reinterpret_cast<const double2*>(cT + 4 * cov + 2);
+        e[0] = u.x; e[1] = u.y; e[2] = w.x; e[3] = w.y;
+    } else {
+        const SvD4 r = sv_cov_entry_direct(cov, sf, a.cp);
+        e[0] = r.a; e[1] = r.b; e[2] = r.c; e[3] = r.d;
+    }
+    if (a.cp.single_ado) {
+        // RawReadCountsModelFiniteMuDM.java:133-225, single-ADO arms, in linear space with a common scale
+        const double m = fmax(fmax(N0, N1), fmax(N2, N3));
+        const double n0 = exp(N0 - m), n1 = exp(N1 - m), n2 = exp(N2 - m), n3 = exp(N3 - m);
+        const double both = e[0] + e[1];
+        x[0] = n0 * both;                              // 0/0
+        x[1] = n3 * e[0] + 0.5 * (n0 + n1) * e[1];     // 0/1
+        x[2] = n1 * both;                              // 1/1
+        x[3] = n2 * e[0] + n1 * e[1];                  // 1/1'
+        ls = m + e[2];
+    } else {
+        // locus-dropout arms (:147-160 etc.); the theta^2 * NB_0 term carries no nucleotide factor
+        const double m = fmax(fmax(fmax(N0, N1), fmax(N2, N3)), e[3]);
+        const double n0 = exp(N0 - m), n1 = exp(N1 - m), n2 = exp(N2 - m), n3 = exp(N3 - m);
+        const double z = exp(e[3] - m);
+        x[0] = n0 * e[0] + 2.0 * n0 * e[1] + z;
+        x[1] = n3 * e[0] + (n0 + n1) * e[1] + z;
+        x[2] = n1 * e[0] + 2.0 * n1 * e[1] + z;
+        x[3] = n2 * e[0] + 2.0 * n1 * e[1] + z;
+        ls = m + e[2];
+    }
+    l0 = 0.0;
+    if (want0) {
+        const int cg = a.const_genotype;
+        if (a.cp.single_ado && cg == 0)
+            l0 = N0 + e[3];  // log(e^{N0} (e0 + e1) M): no transcendental on the common path
+        else
+            l0 = log(cg == 0 ? x[0] : (cg == 1 ? x[1] : (cg == 2 ? x[2] : x[3]))) + ls;
+    }
+}
+
+// TAB: where the look-up tables are read from.
+//   1: the two Dirichlet-multinomial tables staged once per block (6 C doubles of shared memory), the per-cell coverage
+//      table through L1: no barrier inside the cell loop, the warps of a block drift apart               [default]
+//   2: the cell table too in shared memory, double-buffered with cp.async (the next cell's table arrives while this
+//      cell's sites are evaluated; one barrier per cell): 14 C doubles.  Measured slower (profiles/README.md)
+//   0: everything through L1/L2 (tables too large for shared memory)
+// 256 threads x 2 blocks per SM: 128 registers hold the four unrolled site evaluations and the eight accumulators; at
+// 3 blocks per SM (85 registers) the accumulators spill and the kernel is 16 % slower (profiles/README.md).
+#define SV_LEAF_THREADS 256
+#define SV_LEAF_SITES (SV_LEAF_THREADS * SV_LEAF_IT)
+template <int TAB>
+__global__ void __launch_bounds__(SV_LEAF_THREADS, 2) k_leaf(SvLeafArgs a) {
+    extern __shared__ __align__(16) double sm[];
     const int C = a.C;
+    const int e0 = blockIdx.y * SV_LEAF_CELLS;
+    const int e1 = min(a.n_cells, e0 + SV_LEAF_CELLS);
     const double* dmA = a.dmA;
     const double* dmB = a.dmB;
-    const double* cT = a.cellT + (size_t)j * C * 4;
-    if (SMEM_TABLES) {
+    double* sT = sm + 6 * (size_t)C;
+    const int tid = threadIdx.x;
+    if (TAB >= 1) {
         double* sA = sm;
         double* sB = sm + 4 * (size_t)C;
-        double* sT = sm + 6 * (size_t)C;
-        for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sA[i] = dmA[i];
-        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sB[i] = dmB[i];
-        for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sT[i] = cT[i];
+        if (TAB == 2) {
+            const int j0 = a.cell_list ? a.cell_list[e0] : e0;
+            const double* src = a.cellT + (size_t)j0 * C * 4;
+            for (int i = tid; i < 2 * C; i += SV_LEAF_THREADS) sv_leaf_cp16(sT + 2 * i, src + 2 * i);
+        }
+        for (int i = tid; i < 4 * C; i += SV_LEAF_THREADS) sA[i] = dmA[i];
+        for (int i = tid; i < 2 * C; i += SV_LEAF_THREADS) sB[i] = dmB[i];
+        if (TAB == 2) sv_leaf_cp_wait_all();
         __syncthreads();
         dmA = sA;
         dmB = sB;
-        cT = sT;
     }
-    const double sf = a.size_factors[j];
-    const int s0 = blockIdx.x * a.sites_per_block;
-    const int s1 = min(a.S, s0 + a.sites_per_block);
-    const int4* cnt = a.counts + (size_t)j * a.counts_stride + a.site_begin;
-    double* outX = a.leafX + (size_t)j * a.out_stride * 4;
-    double* outS = a.leafS + (size_t)j * a.out_stride;
-    double* out0 = a.leaf0 ? a.leaf0 + (size_t)j * a.out_stride : nullptr;
+    const int sbase = blockIdx.x * SV_LEAF_SITES + tid;
+    const bool want0 = a.sum0 != nullptr;
+    double accS[SV_LEAF_IT], acc0[SV_LEAF_IT];
+#pragma unroll
+    for (int it = 0; it < SV_LEAF_IT; it++) accS[it] = acc0[it] = 0.0;
 
-    // software pipeline: the count tuple of the next iteration is in flight while this one is evaluated
-    int s = s0 + threadIdx.x;
-    int4 cnext = make_int4(0, 0, 0, 0);
-    if (s < s1) cnext = __ldg(cnt + s);
-    for (; s < s1; s += blockDim.x) {
-#if SV_LEAF_PREFETCH
-        const int4 c = cnext;
-#else
-        const int4 c = __ldg(cnt + s);
-#endif
-#if SV_LEAF_PREFETCH
-        if (s + (int)blockDim.x < s1) cnext = __ldg(cnt + s + blockDim.x);
-#endif
-        const int cov = c.w;
-        const int ref = cov - (c.x + c.y + c.z);
-        double N0, N1, N2, N3;
-        if (cov == 0) {
-            // DirichletMultinomial.logDensity returns 1.0 for an empty site, log mode included (:29-30)
-            N0 = N1 = N2 = N3 = 1.0;
-        } else {
-            // LP terms: table when the count is inside it, else the same formula evaluated directly
-            auto lpA = [&](int cval, double (&o)[4]) {
-                const int ci = cval < 0 ? 0 : cval;
-                if (ci == 0) {
-                    // LP(0, .) == 0 (DirichletMultinomial.java:49): most alt counts are 0, and skipping the look-up keeps
-                    // the shared-memory pipe (the bound of this kernel) for the entries that carry information
-                    o[0] = o[1] = o[2] = o[3] = 0.0;
-                } else if (ci < C) {
-                    const double2 u = *reinterpret_cast<const double2*>(dmA + 4 * ci);
-                    const double2 w = *reinterpret_cast<const double2*>(dmA + 4 * ci + 2);
-                    o[0] = u.x; o[1] = u.y; o[2] = w.x; o[3] = w.y;
-                } else {
-                    const SvD4 r = sv_dm_partials_direct(ci, a.al);
-                    o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
-                }
-            };
-            // logDensity = LP(cov, a0) - (((LP(c1,a1) + LP(c2,a2)) + LP(c3,a3)) + LP(ref,a4)), summed left to right;
-            // table columns: [0] f*w1, [1] (1-eps)*w1, [2] (1/2-f)*w2, [3] f*w2
-            double T[4];
-            lpA(c.x, T);
-            double s0 = T[0], s1 = T[1], s2 = T[2], s3 = T[2];  // alt1: 0/0 f | 1/1 (1-eps) | 1/1' h | 0/1 h
-            lpA(c.y, T);
-            s0 += T[0]; s1 += T[0]; s2 += T[2]; s3 += T[3];      // alt2: f | f | h | f
-            lpA(c.z, T);
-            s0 += T[0]; s1 += T[0]; s2 += T[3]; s3 += T[3];      // alt3: f | f | f | f
-            lpA(ref, T);
-            s0 += T[1]; s1 += T[0]; s2 += T[3]; s3 += T[2];      // ref : (1-eps) | f | f | h
-            double B0, B1;
-            if (cov > 0 && cov < C) {
-                const double2 u = *reinterpret_cast<const double2*>(dmB + 2 * cov);
-                B0 = u.x; B1 = u.y;
-            } else {
-                const SvD2 r = sv_dm_totals_direct(cov, a.al);
-                B0 = r.a; B1 = r.b;
+    for (int e = e0; e < e1; e++) {
+        const int j = a.cell_list ? a.cell_list[e] : e;
+        const double* cT = a.cellT + (size_t)j * C * 4;
+        if (TAB == 2) {
+            cT = sT + (size_t)((e - e0) & 1) * 4 * C;
+            if (e + 1 < e1) {
+                const int jn = a.cell_list ? a.cell_list[e + 1] : e + 1;
+                const double* src = a.cellT + (size_t)jn * C * 4;
+                double* dst = sT + (size_t)((e + 1 - e0) & 1) * 4 * C;
+                for (int i = tid; i < 2 * C; i += SV_LEAF_THREADS) sv_leaf_cp16(dst + 2 * i, src + 2 * i);
             }
-            N0 = B0 - s0;
-            N1 = B0 - s1;
-            N2 = B1 - s2;
-            N3 = B1 - s3;
         }
-        double e[4];
-        if (cov >= 0 && cov < C) {
-            const double2 u = *reinterpret_cast<const double2*>(cT + 4 * cov);
-            const double2 w = *reinterpret_cast<const double2*>(cT + 4 * cov + 2);
-            e[0] = u.x; e[1] = u.y; e[2] = w.x; e[3] = w.y;
-        } else {
-            const SvD4 r = sv_cov_entry_direct(cov, sf, a.cp);
-            e[0] = r.a; e[1] = r.b; e[2] = r.c; e[3] = r.d;
+        const double sf = __ldg(a.size_factors + j);
+        double* outX = a.leafX ? a.leafX + (size_t)j * a.out_stride * 4 : nullptr;
+        // the four count tuples of this cell: four independent 16-byte loads in flight per lane
+        const int4* cnt = a.counts + (size_t)j * a.counts_stride + a.site_begin;
+        int4 c[SV_LEAF_IT];
+#pragma unroll
+        for (int it = 0; it < SV_LEAF_IT; it++) {
+            const int s = sbase + it * SV_LEAF_THREADS;
+            c[it] = s < a.S ? __ldg(cnt + s) : make_int4(0, 0, 0, 0);
         }
-        double x[4], ls;
-        if (a.cp.single_ado) {
-            // RawReadCountsModelFiniteMuDM.java:133-225, single-ADO arms, in linear space with a common scale
-            const double m = fmax(fmax(N0, N1), fmax(N2, N3));
-            const double n0 = exp(N0 - m), n1 = exp(N1 - m), n2 = exp(N2 - m), n3 = exp(N3 - m);
-            const double both = e[0] + e[1];
-            x[0] = n0 * both;                              // 0/0
-            x[1] = n3 * e[0] + 0.5 * (n0 + n1) * e[1];     // 0/1
-            x[2] = n1 * both;                              // 1/1
-            x[3] = n2 * e[0] + n1 * e[1];                  // 1/1'
-            ls = m + e[2];
-        } else {
-            // locus-dropout arms (:147-160 etc.); the theta^2 * NB_0 term carries no nucleotide factor
-            const double m = fmax(fmax(fmax(N0, N1), fmax(N2, N3)), e[3]);
-            const double n0 = exp(N0 - m), n1 = exp(N1 - m), n2 = exp(N2 - m), n3 = exp(N3 - m);
-            const double z = exp(e[3] - m);
-            x[0] = n0 * e[0] + 2.0 * n0 * e[1] + z;
-            x[1] = n3 * e[0] + (n0 + n1) * e[1] + z;
-            x[2] = n1 * e[0] + 2.0 * n1 * e[1] + z;
-            x[3] = n2 * e[0] + 2.0 * n1 * e[1] + z;
-            ls = m + e[2];
+#pragma unroll
+        for (int it = 0; it < SV_LEAF_IT; it++) {
+            const int s = sbase + it * SV_LEAF_THREADS;
+            if (s >= a.S) continue;
+            double x[4], ls, l0;
+            sv_leaf_site(c[it], dmA, dmB, cT, C, sf, a, want0, x, ls, l0);
+            if (outX) sv_st256(outX + (size_t)s * 4, x);
+            accS[it] += ls;
+            acc0[it] += l0;
         }
-        sv_st256(outX + (size_t)s * 4, x);
-        outS[s] = ls;
-        if (out0) {
-            const int cg = a.const_genotype;
-            if (a.cp.single_ado && cg == 0)
-                out0[s] = N0 + e[3];  // log(e^{N0} (e0 + e1) M): no transcendental on the common path
-            else
-                out0[s] = log(cg == 0 ? x[0] : (cg == 1 ? x[1] : (cg == 2 ? x[2] : x[3]))) + ls;
+        if (TAB == 2) {
+            sv_leaf_cp_wait_all();
+            __syncthreads();  // the next cell's table is complete; every warp is done with the buffer it will replace
         }
+    }
+#pragma unroll
+    for (int it = 0; it < SV_LEAF_IT; it++) {
+        const int s = sbase + it * SV_LEAF_THREADS;
+        if (s >= a.S) continue;
+        a.sumS[(size_t)blockIdx.y * a.sum_stride + s] = accS[it];
+        if (want0) a.sum0[(size_t)blockIdx.y * a.sum_stride + s] = acc0[it];
     }
 }

@@ -12,7 +12,7 @@
 // staged (SIEVE_FLAG_LOG_PARTIALS), its linear-mode clamp of the constant-site product (:1041-1047) likewise.
 //
 // Layout in HBM: partials [slot][site][K][4] (one site = 128 contiguous bytes at K = 4), scales [slot][site];
-// leaves [slot][site][4] + [slot][site] (category independent).  Thread mapping: lane = 4 * site_in_warp + k, so a warp
+// leaves [slot][site][4] (category independent; no per-leaf scale, see leaf.cuh).  Thread mapping: lane = 4 * site_in_warp + k, so a warp
 // reads/writes 8 sites * 128 B = 1 KB contiguous with one 256-bit access per lane.
 //
 // Sites are independent, so one launch can walk ANY number of dependent ops: each thread only ever re-reads what it
@@ -26,8 +26,8 @@ struct SvPruneArgs {
     double* scale;         // [slots][S]
     double* cpart;         // constant-site twins (NULL when not maintained)
     double* cscale;
-    const double* leafX;   // [leaf slots][S][4]
-    const double* leafS;   // [leaf slots][S]
+    const double* leafX;   // [leaf slots][S][4]; the leaves' log scales are not stored per leaf (leaf.cuh) ...
+    const double* lsum;    // ... their sum over all cells, per site of the shard (+ out_offset): added at the root
     const double* mats;    // [matrix slots][4][16], already clamped when SIEVE_FLAG_LOG_PARTIALS
     const double2* qfac;   // [matrix slots][4] = (expm1(-0.2 d) / 8, expm1(-0.4 d) / 16): the Q-specialised path
     int clamp_zero_distance;  // SIEVE_FLAG_LOG_PARTIALS: a zero distance gets the Double.MIN_VALUE off-diagonals
@@ -151,9 +151,12 @@ __device__ __forceinline__ void sv_col0_q(const double2 q, const double (&x)[NS]
 // GENO0: root genotype == constant genotype == 0 (always so for ScsFiniteMuExtendedModel.java:37-40); the general
 // case takes the same kernel with run-time selects.
 // QFAST: every matrix of the launch was given as a branch distance (sieve_set_distances): no shared memory at all.
-template <bool WITH_CONST, bool GENO0, bool QFAST>
-__global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRUNE_MINB_CONST_Q : SV_PRUNE_MINB_Q)
-                                                          : (WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB))
+// MINB: resident blocks per SM asked of the compiler; 0 = the default of the variant (SIEVE_B200_PRUNE_MINB instantiates
+// the variant-only Q walk at 7 and 8 for comparison).
+template <bool WITH_CONST, bool GENO0, bool QFAST, int MINB = 0>
+__global__ void __launch_bounds__(SV_PRUNE_THREADS, MINB ? MINB
+                                                    : QFAST ? (WITH_CONST ? SV_PRUNE_MINB_CONST_Q : SV_PRUNE_MINB_Q)
+                                                            : (WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB))
     k_prune(SvPruneArgs a) {
     constexpr int NS = sv_prune_ns(WITH_CONST, QFAST);
     constexpr int SITES_PER_BLOCK = (SV_PRUNE_THREADS / 4) * NS;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
             if (!(flags & SV_OP_FWD1)) {
                 if (leaf1) {
                     sv_ld256_nc(a.leafX + c1_row * 4, x[j]);
-                    xs[j] = __ldg(a.leafS + c1_row);
+                    xs[j] = 0.0;
                 } else {
                     sv_ld256(a.part + c1_row * 16 + k * 4, x[j]);
                     xs[j] = a.scale[c1_row];
@@ -247,7 +250,6 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
             if (!unary) {
                 if (leaf2) {
                     sv_ld256_nc(a.leafX + c2_row * 4, w[j]);
-                    ws[j] = __ldg(a.leafS + c2_row);
                 } else {
                     sv_ld256(a.part + c2_row * 16 + k * 4, w[j]);
                     ws[j] = a.scale[c2_row];
@@ -378,12 +380,14 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
                 double v = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? x[j][0] : sv_sel(x[j], rg));
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + xs[j];
+                // the scales of ALL leaves, which the walk never carried, come in here
+                const double lsum = site_ok[j] ? __ldg(a.lsum + a.out_offset + site0 + 8 * j) : 0.0;
+                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + (xs[j] + lsum);
                 if (WITH_CONST) {
                     double cv = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? cx[j][0] : sv_sel(cx[j], rg));
                     cv += __shfl_xor_sync(0xffffffffu, cv, 1);
                     cv += __shfl_xor_sync(0xffffffffu, cv, 2);
-                    if (site_ok[j] && klane == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + cxs[j];
+                    if (site_ok[j] && klane == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + (cxs[j] + lsum);
                 }
             }
         }
@@ -391,14 +395,16 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, QFAST ? (WITH_CONST ? SV_PRU
 }
 
 // ---- BeerLikelihoodCore.getNodePartials in the reference layout [K][S][G] ------------------------------------------
-__global__ void k_export_partials(const double* __restrict__ x, const double* __restrict__ scale, int S, int K,
-                                  int is_leaf, int as_log, double* __restrict__ out) {
+// scale: the node's own (power-of-two) scale, NULL for a leaf; lsum: the sum of the scales of the leaves below the node
+__global__ void k_export_partials(const double* __restrict__ x, const double* __restrict__ scale,
+                                  const double* __restrict__ lsum, int S, int K, int is_leaf, int as_log,
+                                  double* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over K * S * 4
     if (idx >= K * S * 4) return;
     const int g = idx & 3;
     const int s = (idx >> 2) % S;
     const int k = (idx >> 2) / S;
     const double v = is_leaf ? x[(size_t)s * 4 + g] : x[((size_t)s * SV_KMAX + k) * 4 + g];
-    const double ls = scale[s];
+    const double ls = (scale ? scale[s] : 0.0) + lsum[s];
     out[idx] = as_log ? log(v) + ls : v * exp(ls);
 }

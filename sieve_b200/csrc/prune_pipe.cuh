@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_PIPE_MINB) k_prune_pipe(S
                 const unsigned d = base + vec_off + (unsigned)((0 * NS + j) * 2) * (SV_PRUNE_THREADS * 16);
                 sv_cp16(d, src);
                 sv_cp16(d + SV_PRUNE_THREADS * 16, src + 2);
-                sv_cp8(base + sc_off + (unsigned)(0 * NS + j) * (SV_PRUNE_THREADS * 8),
-                       ((flags & SV_OP_LEAF1) ? a.leafS : a.scale) + row);
+                if (!(flags & SV_OP_LEAF1))
+                    sv_cp8(base + sc_off + (unsigned)(0 * NS + j) * (SV_PRUNE_THREADS * 8), a.scale + row);
             }
             if (!(flags & SV_OP_UNARY)) {
                 const size_t row = c2_base + srow[j];
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_PIPE_MINB) k_prune_pipe(S
                 const unsigned d = base + vec_off + (unsigned)((1 * NS + j) * 2) * (SV_PRUNE_THREADS * 16);
                 sv_cp16(d, src);
                 sv_cp16(d + SV_PRUNE_THREADS * 16, src + 2);
-                sv_cp8(base + sc_off + (unsigned)(1 * NS + j) * (SV_PRUNE_THREADS * 8),
-                       ((flags & SV_OP_LEAF2) ? a.leafS : a.scale) + row);
+                if (!(flags & SV_OP_LEAF2))
+                    sv_cp8(base + sc_off + (unsigned)(1 * NS + j) * (SV_PRUNE_THREADS * 8), a.scale + row);
             }
         }
         sv_cp_commit();
@@ -170,11 +170,11 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_PIPE_MINB) k_prune_pipe(S
         for (int j = 0; j < NS; j++) {
             if (!(flags & SV_OP_FWD1)) {
                 sv_lds_vec(base + vec_off + (unsigned)((0 * NS + j) * 2) * (SV_PRUNE_THREADS * 16), x[j]);
-                xs[j] = sv_lds_f64(base + sc_off + (unsigned)(0 * NS + j) * (SV_PRUNE_THREADS * 8));
+                xs[j] = (flags & SV_OP_LEAF1) ? 0.0 : sv_lds_f64(base + sc_off + (unsigned)(0 * NS + j) * (SV_PRUNE_THREADS * 8));
             }
             if (!unary) {
                 sv_lds_vec(base + vec_off + (unsigned)((1 * NS + j) * 2) * (SV_PRUNE_THREADS * 16), w[j]);
-                ws[j] = sv_lds_f64(base + sc_off + (unsigned)(1 * NS + j) * (SV_PRUNE_THREADS * 8));
+                ws[j] = (flags & SV_OP_LEAF2) ? 0.0 : sv_lds_f64(base + sc_off + (unsigned)(1 * NS + j) * (SV_PRUNE_THREADS * 8));
             }
         }
         const bool cz0 = flags & SV_OP_ZEROD;
@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_PIPE_MINB) k_prune_pipe(S
                 double v = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? x[j][0] : sv_sel(x[j], rg));
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + xs[j];
+                const double lsum = site_ok[j] ? __ldg(a.lsum + a.out_offset + site0 + 8 * j) : 0.0;
+                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + (xs[j] + lsum);
             }
         }
         // the pipeline was cut for the next op (its operand is the value just stored): fetch it now

@@ -46,7 +46,7 @@ __device__ __forceinline__ void sv_rp_issue(const SvPruneArgs& a, int i, int k, 
         if (!(flags & SV_OP_FWD1)) {
             if (flags & SV_OP_LEAF1) {
                 sv_ld256_nc(a.leafX + c1_row * 4, o.x[j]);
-                o.xs[j] = __ldg(a.leafS + c1_row);
+                o.xs[j] = 0.0;
             } else {
                 sv_ld256(a.part + c1_row * 16 + k * 4, o.x[j]);
                 o.xs[j] = a.scale[c1_row];
@@ -56,7 +56,7 @@ __device__ __forceinline__ void sv_rp_issue(const SvPruneArgs& a, int i, int k, 
         if (!(flags & SV_OP_UNARY)) {
             if (flags & SV_OP_LEAF2) {
                 sv_ld256_nc(a.leafX + c2_row * 4, o.w[j]);
-                o.ws[j] = __ldg(a.leafS + c2_row);
+                o.ws[j] = 0.0;
             } else {
                 sv_ld256(a.part + c2_row * 16 + k * 4, o.w[j]);
                 o.ws[j] = a.scale[c2_row];
@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_RP_MINB) k_prune_rp(SvPru
                 double v = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? x[j][0] : sv_sel(x[j], rg));
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + xs[j];
+                const double lsum = site_ok[j] ? __ldg(a.lsum + a.out_offset + site0 + 8 * j) : 0.0;
+                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + (xs[j] + lsum);
             }
         }
     }

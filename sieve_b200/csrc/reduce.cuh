@@ -118,38 +118,38 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl,
 }
 
 
-// Lambda[s] = sum over cells of leaf0[cell][s], cells in index order (deterministic), one thread per site.
+// The leaf kernel leaves one partial sum per (cell group, site) of (a) the leaves' natural-log scales and (b) their
+// constant-genotype log-likelihoods; this adds the groups in index order (deterministic), one thread per site:
+//   lsum[s]   = sum over cells of the scale of leaf (cell, s): added to the site's log-likelihood once, at the root
+//   lambda[s] = sum over cells of log leaf[cell][s][constant genotype]
 // The constant-site likelihood factorises: every constant-site partial is (a site-independent 4-vector per node and
 // category) x (the product over the leaves below of their constant-genotype likelihood), so the per-site part of the
 // whole acquisition-bias computation is this one column sum, and it only changes when the leaves change.
-__global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ leaf0, int n_cells, int S, long long stride,
+__global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ sumS, const double* __restrict__ sum0,
+                                                int n_groups, int S, long long stride, double* __restrict__ lsum,
                                                 double* __restrict__ lambda) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four chains for memory-level parallelism, merged in a fixed order
-    int j = 0;
-    for (; j + 3 < n_cells; j += 4) {
-        a0 += __ldg(leaf0 + (size_t)j * stride + s);
-        a1 += __ldg(leaf0 + (size_t)(j + 1) * stride + s);
-        a2 += __ldg(leaf0 + (size_t)(j + 2) * stride + s);
-        a3 += __ldg(leaf0 + (size_t)(j + 3) * stride + s);
+    double a = 0.0, b = 0.0;
+    for (int g = 0; g < n_groups; g++) {
+        a += __ldg(sumS + (size_t)g * stride + s);
+        if (sum0) b += __ldg(sum0 + (size_t)g * stride + s);
     }
-    for (; j < n_cells; j++) a0 += __ldg(leaf0 + (size_t)j * stride + s);
-    lambda[s] = (a0 + a1) + (a2 + a3);
+    lsum[s] = a;
+    if (sum0) lambda[s] = b;
 }
 
 // Constant-site partials of one node in the reference layout [K][S][G], rebuilt from the factorisation for
-// BeerLikelihoodCore-style read-back: out = G[k][g] * exp(gscale) * prod over the node's leaves of their leaf0.
-__global__ void k_export_const(const double* __restrict__ leaf0, const int* __restrict__ leaf_list, int n_list,
-                               long long stride, const double* __restrict__ G /*[4][4]*/, double gscale, int S, int K,
-                               int as_log, double* __restrict__ out) {
+// BeerLikelihoodCore-style read-back: out = G[k][g] * exp(gscale) * prod over the node's leaves of their constant-
+// genotype likelihood (lam = the column sum over exactly those leaves).
+__global__ void k_export_const(const double* __restrict__ lam, const double* __restrict__ G /*[4][4]*/, double gscale,
+                               int S, int K, int as_log, double* __restrict__ out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    double lam = 0.0;
-    for (int i = 0; i < n_list; i++) lam += leaf0[(size_t)leaf_list[i] * stride + s];
+    const double l = lam[s];
     for (int k = 0; k < K; k++)
         for (int g = 0; g < 4; g++) {
-            const double v = log(G[k * 4 + g]) + gscale + lam;
+            const double v = log(G[k * 4 + g]) + gscale + l;
             out[((size_t)k * S + s) * 4 + g] = as_log ? v : exp(v);
         }
 }

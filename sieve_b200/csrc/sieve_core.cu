@@ -62,6 +62,8 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     if (const char* e = getenv("SIEVE_B200_CONST_TWIN")) h->const_twin = atoi(e) != 0;
     if (const char* e = getenv("SIEVE_B200_PIPE")) h->use_pipe = atoi(e) != 0;
     if (const char* e = getenv("SIEVE_B200_RP")) h->use_rp = atoi(e) != 0;
+    if (const char* e = getenv("SIEVE_B200_PRUNE_MINB")) h->prune_minb = atoi(e);
+    if (const char* e = getenv("SIEVE_B200_LEAF_TAB")) h->leaf_tab = std::min(2, std::max(0, atoi(e)));
     const bool twin = h->with_const && h->const_twin;
     const bool algebraic = h->with_const && !h->const_twin;
     h->single_ado = cfg->flags & SIEVE_FLAG_SINGLE_ADO;
@@ -113,7 +115,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         // everything but the internal partials is resident as usual; the pool takes what is left (minus head room)
         size_t free0 = 0, total0 = 0;
         cudaMemGetInfo(&free0, &total0);
-        const size_t fixed = n * S * 16 + leaf_bufs * n * S * (40 + (algebraic ? 8 : 0)) + ((size_t)3 << 30);
+        const size_t fixed = n * S * 16 + leaf_bufs * n * S * 32 + ((n + 31) / 32) * S * 16 + ((size_t)3 << 30);
         const size_t per_slot = S * (SV_KMAX * 32 + 8) * (twin ? 2 : 1);
         size_t slots = free0 > fixed ? (free0 - fixed) / per_slot : 0;
         if (const char* e = getenv("SIEVE_B200_POOL_SLOTS")) slots = (size_t)std::max(0, atoi(e));
@@ -145,7 +147,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         return fail(SIEVE_ERR_OOM);
     }
     // does the residency fit?
-    size_t need = n * S * 16 + leaf_bufs * n * pool_sites * 40 +
+    size_t need = n * S * 16 + leaf_bufs * n * pool_sites * 32 + ((n + 31) / 32) * pool_sites * 16 +
                   part_slots * pool_sites * (SV_KMAX * 32 + 8) * (twin ? 2 : 1) + ((size_t)64 << 20);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -164,7 +166,9 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     CR(sv_alloc(h, &h->d_counts, n * S));
     CR(sv_alloc(h, &h->d_sf, n));
     CR(sv_alloc(h, &h->d_leafX, leaf_bufs * n * pool_sites * 4));
-    CR(sv_alloc(h, &h->d_leafS, leaf_bufs * n * pool_sites));
+    const size_t leaf_groups = (n + SV_LEAF_CELLS - 1) / SV_LEAF_CELLS;
+    CR(sv_alloc(h, &h->d_sumS, leaf_groups * pool_sites));
+    CR(sv_alloc(h, &h->d_lsum, 2 * S));
     CR(sv_alloc(h, &h->d_part, part_slots * pool_sites * SV_KMAX * 4));
     CR(sv_alloc(h, &h->d_scale, part_slots * pool_sites));
     if (twin) {
@@ -172,7 +176,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         CR(sv_alloc(h, &h->d_cscale, part_slots * pool_sites));
     }
     if (algebraic) {
-        CR(sv_alloc(h, &h->d_leaf0, leaf_bufs * n * pool_sites));
+        CR(sv_alloc(h, &h->d_sum0, leaf_groups * pool_sites));
         CR(sv_alloc(h, &h->d_lambda, 2 * S));
         h->G.assign((size_t)2 * h->n_nodes * SV_KMAX * 4, 0.0);
         h->Gs.assign((size_t)2 * h->n_nodes, 0.0);
@@ -225,11 +229,12 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_dmB);
     cudaFree(h->d_cellT);
     cudaFree(h->d_leafX);
-    cudaFree(h->d_leafS);
+    cudaFree(h->d_sumS);
+    cudaFree(h->d_sum0);
+    cudaFree(h->d_lsum);
     cudaFree(h->d_part);
     cudaFree(h->d_scale);
     cudaFree(h->d_cpart);
-    cudaFree(h->d_leaf0);
     cudaFree(h->d_lambda);
     cudaFree(h->d_cscale);
     cudaFree(h->d_mats);
@@ -475,8 +480,8 @@ extern "C" int sieve_set_leaf_params(sieve_core_t* h, const sieve_leaf_params_t*
     return SIEVE_OK;
 }
 
-// site_begin / n_sites: the range of the shard to evaluate; out_stride: site capacity of the leaf pool it goes to
-static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, long long out_stride) {
+// brings the look-up tables of the leaf kernel up to date with h->lp
+static int sv_refresh_leaf_tables(sieve_core* h, SvDmAlphas* al_out, SvCovParams* cp_out) {
     const SvDmAlphas al = sv_dm_alphas(h->lp.eff_seq_err_rate, h->lp.shape_ctrl1, h->lp.shape_ctrl2);
     SvCovParams cp;
     cp.t = h->lp.allelic_seq_cov;
@@ -505,50 +510,109 @@ static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, lo
         h->cov_dirty = false;
     }
     SV_CUDA(cudaGetLastError());
+    *al_out = al;
+    *cp_out = cp;
+    return SIEVE_OK;
+}
+
+// One k_leaf + k_colsum pair over `n_entries` cells (d_cell_list NULL: all cells in index order) and the site range
+// [site_begin, site_begin + n_sites): leaf likelihoods into leafX (NULL: none), the sums of the leaves' log scales into
+// lsum_out[0 .. n_sites) and, when lambda_out is given, of their constant-genotype log-likelihoods into lambda_out.
+// sumS / sum0: scratch for the per-cell-group partial sums, ceil(n_entries / SV_LEAF_CELLS) x sum_stride doubles each.
+static int sv_launch_leaf_kernels(sieve_core* h, long long site_begin, int n_sites, long long out_stride, double* leafX,
+                                  const int* d_cell_list, int n_entries, double* sumS, double* sum0, long long sum_stride,
+                                  double* lsum_out, double* lambda_out) {
     SvLeafArgs a;
+    SV_TRY(sv_refresh_leaf_tables(h, &a.al, &a.cp));
+    const int C = h->C;
     a.counts = h->d_counts;
     a.dmA = h->d_dmA;
     a.dmB = h->d_dmB;
     a.cellT = h->d_cellT;
     a.size_factors = h->d_sf;
-    a.leafX = h->d_leafX + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S * 4);
-    a.leafS = h->d_leafS + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S);
-    const bool algebraic = h->with_const && !h->const_twin;
-    a.leaf0 = algebraic ? h->d_leaf0 + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S) : nullptr;
+    a.cell_list = d_cell_list;
+    a.leafX = leafX;
+    a.sumS = sumS;
+    a.sum0 = lambda_out ? sum0 : nullptr;
     a.const_genotype = h->const_genotype;
-    a.n_cells = h->n;
+    a.n_cells = n_entries;
     a.S = n_sites;
     a.counts_stride = h->S;
     a.site_begin = site_begin;
     a.out_stride = out_stride;
+    a.sum_stride = sum_stride;
     a.C = C;
-    a.al = al;
-    a.cp = cp;
-    // site ranges: enough blocks to fill the 148 SMs a few times over, but long enough to amortise the table staging
-    const size_t smem = (size_t)C * 10 * sizeof(double);
-    const bool use_smem = smem <= 100 * 1024;
-    int splits = std::max(1, (148 * 8 + h->n - 1) / h->n);
-    int spb = std::max(use_smem ? 2048 : 256, (n_sites + splits - 1) / splits);
-    spb = (spb + 255) / 256 * 256;
-    a.sites_per_block = spb;
-    dim3 grid((n_sites + spb - 1) / spb, h->n);
-    if (use_smem) {
-        if (!h->leaf_attr_set) {
-            SV_CUDA(cudaFuncSetAttribute(k_leaf<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            h->leaf_attr_set = true;
-        }
-        k_leaf<true><<<grid, 256, smem, h->stream>>>(a);
-    } else {
-        k_leaf<false><<<grid, 256, 0, h->stream>>>(a);
+    const int groups = (n_entries + SV_LEAF_CELLS - 1) / SV_LEAF_CELLS;
+    // SIEVE_B200_LEAF_TAB: 1 (default) Dirichlet-multinomial tables in shared memory, cell table through L1; 2 cell table
+    // double-buffered in shared memory; 0 (forced when the tables do not fit) everything through L1
+    int tab = h->leaf_tab;
+    if ((size_t)C * 14 * sizeof(double) > 100 * 1024 && tab == 2) tab = 1;
+    if ((size_t)C * 6 * sizeof(double) > 100 * 1024) tab = 0;
+    const size_t smem = (size_t)C * (tab == 2 ? 14 : tab == 1 ? 6 : 0) * sizeof(double);
+    dim3 grid((n_sites + SV_LEAF_SITES - 1) / SV_LEAF_SITES, groups);
+    if (!h->leaf_attr_set) {
+        SV_CUDA(cudaFuncSetAttribute(k_leaf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SV_CUDA(cudaFuncSetAttribute(k_leaf<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        h->leaf_attr_set = true;
     }
+    if (tab == 2)
+        k_leaf<2><<<grid, SV_LEAF_THREADS, smem, h->stream>>>(a);
+    else if (tab == 1)
+        k_leaf<1><<<grid, SV_LEAF_THREADS, smem, h->stream>>>(a);
+    else
+        k_leaf<0><<<grid, SV_LEAF_THREADS, 0, h->stream>>>(a);
     sv_count(h);
-    if (algebraic) {
-        // Lambda of this site range: streamed mode indexes it by the shard's site, resident mode per leaf buffer
-        double* lam = h->d_lambda + (h->ephemeral ? site_begin : (long long)h->cur_leaf * h->S);
-        k_colsum<<<(n_sites + 255) / 256, 256, 0, h->stream>>>(a.leaf0, h->n, n_sites, out_stride, lam);
-        sv_count(h);
-    }
+    k_colsum<<<(n_sites + 255) / 256, 256, 0, h->stream>>>(sumS, a.sum0, groups, n_sites, sum_stride, lsum_out, lambda_out);
+    sv_count(h);
     SV_CUDA(cudaGetLastError());
+    return SIEVE_OK;
+}
+
+// site_begin / n_sites: the range of the shard to evaluate; out_stride: site capacity of the leaf pool it goes to
+static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, long long out_stride) {
+    const bool algebraic = h->with_const && !h->const_twin;
+    // the per-site sums: streamed mode indexes them by the shard's site, resident mode per leaf buffer
+    const long long sum_at = h->ephemeral ? site_begin : (long long)h->cur_leaf * h->S;
+    return sv_launch_leaf_kernels(h, site_begin, n_sites, out_stride,
+                                  h->d_leafX + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->n * h->S * 4), nullptr, h->n,
+                                  h->d_sumS, h->d_sum0, out_stride, h->d_lsum + sum_at,
+                                  algebraic ? h->d_lambda + sum_at : nullptr);
+}
+
+// the sums over the leaves below `node` (the node itself when it is a leaf) of the leaves' log scales and, when lam is
+// given, of their constant-genotype log-likelihoods: what a read-back adds to the node's own scale.  d_ls / d_lam: [S].
+static int sv_subtree_leaf_sums(sieve_core* h, int node, double* d_ls, double* d_lam) {
+    std::vector<int> leaves, st;
+    st.push_back(node);
+    while (!st.empty()) {
+        const int v = st.back();
+        st.pop_back();
+        if (v < h->n) {
+            leaves.push_back(v);
+            continue;
+        }
+        if (h->eph_c1[v] == -2) return sv_fail(SIEVE_ERR_STATE, "node was never computed");
+        st.push_back(h->eph_c1[v]);
+        if (h->eph_c2[v] >= 0) st.push_back(h->eph_c2[v]);
+    }
+    std::sort(leaves.begin(), leaves.end());
+    const size_t S = h->S;
+    const size_t groups = (leaves.size() + SV_LEAF_CELLS - 1) / SV_LEAF_CELLS;
+    int* d_list = nullptr;
+    double* d_sums = nullptr;
+    cudaError_t e = cudaMalloc(&d_list, sizeof(int) * leaves.size());
+    if (e == cudaSuccess) e = cudaMalloc(&d_sums, sizeof(double) * 2 * groups * S);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_list, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, h->stream);
+    int r = SIEVE_OK;
+    if (e == cudaSuccess)
+        r = sv_launch_leaf_kernels(h, 0, (int)S, (long long)S, nullptr, d_list, (int)leaves.size(), d_sums,
+                                   d_sums + groups * S, (long long)S, d_ls, d_lam);
+    if (e == cudaSuccess && r == SIEVE_OK) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_list);
+    cudaFree(d_sums);
+    if (r != SIEVE_OK) return r;
+    SV_CUDA(e);
     return SIEVE_OK;
 }
 
@@ -578,17 +642,14 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
     }
     if (!for_update && !h->single_leaf) {
         // initialisation: both buffers hold the leaves (storeLeafPartials, ScsBeerLikelihoodCore.java:437-445)
-        const size_t nx = (size_t)h->n * h->S * 4, ns = (size_t)h->n * h->S;
+        const size_t nx = (size_t)h->n * h->S * 4;
         SV_CUDA(cudaMemcpyAsync(h->d_leafX + (size_t)(1 - h->cur_leaf) * nx, h->d_leafX + (size_t)h->cur_leaf * nx,
                                 nx * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        SV_CUDA(cudaMemcpyAsync(h->d_leafS + (size_t)(1 - h->cur_leaf) * ns, h->d_leafS + (size_t)h->cur_leaf * ns,
-                                ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        if (h->d_leaf0) {
-            SV_CUDA(cudaMemcpyAsync(h->d_leaf0 + (size_t)(1 - h->cur_leaf) * ns, h->d_leaf0 + (size_t)h->cur_leaf * ns,
-                                    ns * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        SV_CUDA(cudaMemcpyAsync(h->d_lsum + (size_t)(1 - h->cur_leaf) * h->S, h->d_lsum + (size_t)h->cur_leaf * h->S,
+                                (size_t)h->S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        if (h->d_lambda)
             SV_CUDA(cudaMemcpyAsync(h->d_lambda + (size_t)(1 - h->cur_leaf) * h->S, h->d_lambda + (size_t)h->cur_leaf * h->S,
                                     (size_t)h->S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        }
     }
     h->leaves_ready = true;
     return SIEVE_OK;
@@ -792,6 +853,31 @@ extern "C" int sieve_set_root(sieve_core_t* h, int32_t root, const double* propo
     return SIEVE_OK;
 }
 
+// Resident blocks per SM for the variant-only Q walk.  Every block walks the whole op list, so a launch takes as long as
+// its waves of blocks: full waves cost their share, the last partial wave (a fraction phi of the slots) costs about
+// 0.3 + 0.65 phi of a full one (its blocks run faster on a less crowded SM, measured at 6 blocks/SM over 1.0 .. 3.0
+// waves).  The kernel compiles to 74 registers (6 blocks/SM); capped at 72 / 64 registers it spills 16 / 36 bytes and
+// fits 7 / 8 blocks, which at whole waves is 3 % faster per site -- but what decides is how the launch's blocks divide
+// into waves: 100 000 sites are 1.76 / 1.51 / 1.32 waves (6 wins), 125 000 sites 2.20 / 1.89 / 1.65 (7 wins by 12 %).
+// Same PTX, same arithmetic: the choice cannot change a bit of the results.  profiles/README.md has the measurements.
+static int sv_pick_prune_blocks(unsigned blocks) {
+    static const int m[3] = {6, 7, 8};
+    static const double per_wave[3] = {6.0, 7.0 * 0.972, 8.0 * 0.975};
+    int best = 6;
+    double best_t = 0.0;
+    if (blocks <= 148u * 6u) return best;  // everything is resident at once anyway
+    for (int i = 0; i < 3; i++) {
+        const double w = (double)blocks / (148.0 * m[i]);
+        const double full = floor(w), phi = w - full;
+        const double t = per_wave[i] * (full + (phi > 0.0 ? 0.3 + 0.65 * phi : 0.0));
+        if (i == 0 || t < best_t * 0.99) {  // a higher block count has to win by more than 1 %
+            best = m[i];
+            best_t = t;
+        }
+    }
+    return best;
+}
+
 template <bool QFAST>
 static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
     const bool g0 = a.const_genotype == 0 && a.root_genotype == 0;
@@ -801,7 +887,12 @@ static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
         else
             k_prune<true, false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
     } else {
-        if (g0)
+        const int minb = QFAST && g0 && grid.y == 1 ? (h->prune_minb ? h->prune_minb : sv_pick_prune_blocks(grid.x)) : 0;
+        if (minb == 7)
+            k_prune<false, true, QFAST, 7><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+        else if (minb == 8)
+            k_prune<false, true, QFAST, 8><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+        else if (g0)
             k_prune<false, true, QFAST><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
         else
             k_prune<false, false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
@@ -831,7 +922,7 @@ static int sv_launch_staged(sieve_core* h) {
         a.cpart = h->d_cpart;
         a.cscale = h->d_cscale;
         a.leafX = h->d_leafX;
-        a.leafS = h->d_leafS;
+        a.lsum = h->d_lsum + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S);
         a.mats = h->d_mats;
         a.qfac = h->d_qfac;
         a.clamp_zero_distance = h->log_mode ? 1 : 0;
@@ -1178,50 +1269,43 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     const size_t S = h->S, K = h->K, n = h->n;
     const double *x, *sc;
     int is_leaf = node < h->n;
+    // the leaves' scales live only as sums (leaf.cuh): re-derive the sum over the leaves below this node
+    double* d_sub = nullptr;  // [2][S]: scales, constant-genotype log-likelihoods
+    SV_CUDA(cudaMalloc(&d_sub, sizeof(double) * 2 * S));
+    struct SubFree {
+        double* p;
+        ~SubFree() { cudaFree(p); }
+    } sub_free{d_sub};
     if (is_leaf) {
         SV_REQUIRE(which == 0, "leaves have no constant-site partials");
         if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "leaves not computed yet");
+        SV_TRY(sv_subtree_leaf_sums(h, node, d_sub, nullptr));
         x = h->d_leafX + ((size_t)h->cur_leaf * n + node) * S * 4;
-        sc = h->d_leafS + ((size_t)h->cur_leaf * n + node) * S;
+        sc = nullptr;
     } else {
         const int sl = h->slot_of[(size_t)h->cur_part[node] * h->n_nodes + node];
         if (sl < 0) return sv_fail(SIEVE_ERR_STATE, "sieve_get_node_partials: the node could not be materialised");
         const size_t slot = (size_t)sl;
         if (which == 1 && !h->with_const) return sv_fail(SIEVE_ERR_STATE, "constant-site partials are not maintained");
-        if (which == 1 && !h->const_twin) {
+        const bool from_factors = which == 1 && !h->const_twin;
+        SV_TRY(sv_subtree_leaf_sums(h, node, d_sub, from_factors ? d_sub + S : nullptr));
+        if (from_factors) {
             // rebuilt from the factorisation: G_node x product over the node's leaves of their constant-genotype likelihood
-            std::vector<int> leaves, st;
-            st.push_back(node);
-            while (!st.empty()) {
-                const int v = st.back();
-                st.pop_back();
-                if (v < (int)n) {
-                    leaves.push_back(v);
-                    continue;
-                }
-                if (h->eph_c1[v] == -2) return sv_fail(SIEVE_ERR_STATE, "node was never computed");
-                st.push_back(h->eph_c1[v]);
-                if (h->eph_c2[v] >= 0) st.push_back(h->eph_c2[v]);
-            }
-            int* d_list = nullptr;
             double *d_G = nullptr, *d_o = nullptr;
             const size_t NN = K * S * 4;
-            cudaError_t e = cudaMalloc(&d_list, sizeof(int) * leaves.size());
-            if (e == cudaSuccess) e = cudaMalloc(&d_G, sizeof(double) * 16);
+            cudaError_t e = cudaMalloc(&d_G, sizeof(double) * 16);
             if (e == cudaSuccess) e = cudaMalloc(&d_o, sizeof(double) * NN);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d_list, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, h->stream);
             const double* g = h->G.data() + ((size_t)h->cur_part[node] * h->n_nodes + node) * SV_KMAX * 4;
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_G, g, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream);
             if (e == cudaSuccess) {
                 k_export_const<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(
-                    h->d_leaf0 + (size_t)h->cur_leaf * n * S, d_list, (int)leaves.size(), (long long)S, d_G,
-                    h->Gs[(size_t)h->cur_part[node] * h->n_nodes + node], (int)S, (int)K, h->log_mode ? 1 : 0, d_o);
+                    d_sub + S, d_G, h->Gs[(size_t)h->cur_part[node] * h->n_nodes + node], (int)S, (int)K,
+                    h->log_mode ? 1 : 0, d_o);
                 sv_count(h);
                 e = cudaGetLastError();
             }
             if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, NN * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-            cudaFree(d_list);
             cudaFree(d_G);
             cudaFree(d_o);
             SV_CUDA(e);
@@ -1233,7 +1317,8 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     double* d_out = nullptr;
     const size_t N = K * S * 4;
     SV_CUDA(cudaMalloc(&d_out, N * sizeof(double)));
-    k_export_partials<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(x, sc, (int)S, (int)K, is_leaf, h->log_mode ? 1 : 0, d_out);
+    k_export_partials<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(x, sc, d_sub, (int)S, (int)K, is_leaf,
+                                                                          h->log_mode ? 1 : 0, d_out);
     sv_count(h);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
