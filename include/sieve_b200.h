@@ -50,7 +50,7 @@ enum {
 #define SIEVE_FLAG_SPARSE 16u        /* keep the leaves resident but only the partials of the larger subtrees (as many as  \
                                         fit); small subtrees are recomputed on the way.  For shapes whose full residency       \
                                         exceeds HBM but whose MCMC moves should still cost O(depth), e.g. 10^4 cells. */
-#define SIEVE_FLAG_SINGLE_LEAF_BUFFER 32u /* one leaf buffer instead of two (40 B per cell and site saved): a rejected         \
+#define SIEVE_FLAG_SINGLE_LEAF_BUFFER 32u /* one leaf buffer instead of two (32 B per cell and site saved): a rejected         \
                                         leaf-parameter proposal is undone by recomputing the leaves in sieve_restore */
 
 typedef struct {

@@ -14,8 +14,8 @@
 // and the per-(cell, site) work becomes 4 table sums + 4 exp: HBM-bound instead of lgamma-bound.
 // Counts beyond the table are evaluated directly (same formulas), so any input is handled.
 //
-// Output per (cell, site): 4 linear genotype likelihoods, jointly scaled, plus the natural-log scale:
-//   true likelihood_g = x[g] * exp(lscale)
+// Output per (cell, site): 4 linear genotype likelihoods, jointly scaled: true likelihood_g = x[g] * exp(lscale).
+// lscale itself is not stored per leaf, only its sum over the cells per site (see the kernel below).
 #pragma once
 #include "common.cuh"
 
@@ -311,7 +311,8 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
 //      cell's sites are evaluated; one barrier per cell): 14 C doubles.  Measured slower (profiles/README.md)
 //   0: everything through L1/L2 (tables too large for shared memory)
 // 256 threads x 2 blocks per SM: 128 registers hold the four unrolled site evaluations and the eight accumulators; at
-// 3 blocks per SM (85 registers) the accumulators spill and the kernel is 16 % slower (profiles/README.md).
+// 3 blocks per SM (85 registers) the accumulators spill and the kernel is 16 % slower; with the accumulators moved to
+// shared memory it fits 3 blocks with 28 bytes of spill and is 2 % slower (profiles/README.md).
 #define SV_LEAF_THREADS 256
 #define SV_LEAF_SITES (SV_LEAF_THREADS * SV_LEAF_IT)
 template <int TAB>

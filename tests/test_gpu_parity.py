@@ -125,6 +125,54 @@ def test_full_evaluation_matches_oracle(core_mod, oracle, asc, use_log, single, 
     c.close()
 
 
+def test_leaf_scale_sums_over_cell_groups_and_site_blocks(core_mod, oracle, monkeypatch):
+    """The leaves' log scales exist only as their per-site sum over the cells (leaf.cuh): 70 cells = three groups of 32
+    with a ragged last one, 2 300 sites = three blocks of 1 024 with a ragged last one.  Site log-likelihoods against the
+    oracle, read-backs of leaves / internal nodes (their scale sum is re-derived over the leaf list below the node), and
+    bit-identity of the streamed evaluation, whose site chunks cut the blocks differently."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    d = synthetic(70, 2300, seed=77)
+    counts, tree = d["counts"], d["tree"]
+    c5 = oracle.counts5(counts)
+    sf, _ = oracle.size_factors(c5)
+    rates, props = substmodel.gamma_category_rates(0.9, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    M = 8000.0
+    c = _setup(core_mod, counts, tree, sf, PARAMS, mats, props, asc=True)
+    c.update_nodes(tree.ops(), flip=False)
+    r = c.evaluate()
+    sl, sc = c.site_log_likelihoods()
+    logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, "felsenstein_mean", M)
+    _close(sl, osl, SITE_RTOL)
+    _close(sc, osc, SITE_RTOL)
+    got = core_mod.combine_shards([r], "felsenstein_mean", M)
+    assert abs(got - logp) <= TOTAL_RTOL * abs(logp)
+    P = oracle.leaf_params(*PARAMS)
+    for j in (0, 31, 32, 63, 64, 69):       # first / last cell of every group
+        np.testing.assert_allclose(c.get_node_partials(j)[0], oracle.leaf_likelihood(c5, j, sf[j], P), rtol=2e-13, atol=2e-12)
+    oc = oracle.Core(tree.node_count, tree.n, 2300, 4, 4, True)
+    for i in range(tree.n):
+        oc.set_node_partials(i, oracle.leaf_likelihood(c5, i, sf[i], P))
+    for node in range(tree.node_count):
+        if node != tree.root:
+            for k in range(4):
+                oc.set_node_matrix(node, k, mats[node, k])
+    for p, c1, c2 in tree.ops():
+        oc.calculate_partials(c1, c1 < tree.n, c2, 0 <= c2 < tree.n, p, 0)
+    for node in (tree.n, tree.n + 33, tree.root - 1, tree.root):
+        np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=1e-11)
+        np.testing.assert_allclose(c.get_node_partials(node, const=True), oc.get_const_partials(node), rtol=2e-12, atol=1e-11)
+    c.close()
+    monkeypatch.setenv("SIEVE_B200_CHUNK_SITES", "736")     # chunks of 736 sites: 4 chunks, none aligned to a leaf block
+    res = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=M, size_factors=sf)
+    eph = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=M, ephemeral=True, size_factors=sf)
+    assert res.calculate_logp() == eph.calculate_logp()
+    np.testing.assert_array_equal(eph.pattern_log_likelihoods()[0], res.pattern_log_likelihoods()[0])
+    np.testing.assert_array_equal(eph.pattern_log_likelihoods()[1], res.pattern_log_likelihoods()[1])
+    res.close()
+    eph.close()
+
+
 def test_leaf_kernel_all_cells_and_edge_counts(core_mod, oracle, monkeypatch):
     rng = np.random.default_rng(8)
     S, n = 300, 5
