@@ -37,6 +37,8 @@ struct sieve_core {
     uint64_t launches = 0;
     int step_launches = 0;  // since the last evaluate
     bool leaf_attr_set = false;
+    bool tables_cover_counts = false;  // every count of the shard is inside the look-up tables (checked at ingest)
+    bool leaf_force_checked = false;   // SIEVE_B200_LEAF_CHECKED=1: keep the out-of-table paths in k_leaf regardless
     int leaf_tab = 1;    // SIEVE_B200_LEAF_TAB: where k_leaf reads its tables from (sv_launch_leaf_kernels)
     int prune_minb = 0;  // SIEVE_B200_PRUNE_MINB: 6, 7 or 8 resident blocks per SM for the variant-only Q walk (0: chosen per launch)
 

@@ -213,6 +213,9 @@ __device__ __forceinline__ void sv_leaf_cp_wait_all() {
 
 // one (cell, site): x[4] scaled linear genotype likelihoods, ls their natural-log scale, l0 the constant genotype's
 // log-likelihood (only when want0)
+// COVERED: every count is known to index the tables (checked once at ingest, k_counts_outside_tables): no bounds
+// checks, no out-of-line calls -- the site evaluation is straight-line code that the compiler can interleave across sites.
+template <bool COVERED>
 __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restrict__ dmA, const double* __restrict__ dmB,
                                              const double* __restrict__ cT, const int C, const double sf,
                                              const SvLeafArgs& a, const bool want0, double (&x)[4], double& ls,
@@ -231,7 +234,7 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
                 // LP(0, .) == 0 (DirichletMultinomial.java:49): most alt counts are 0, and skipping the look-up keeps
                 // the shared-memory pipe for the entries that carry information
                 o[0] = o[1] = o[2] = o[3] = 0.0;
-            } else if (ci < C) {
+            } else if (COVERED || ci < C) {
                 const double2 u = *reinterpret_cast<const double2*>(dmA + 4 * ci);
                 const double2 w = *reinterpret_cast<const double2*>(dmA + 4 * ci + 2);
                 o[0] = u.x; o[1] = u.y; o[2] = w.x; o[3] = w.y;
@@ -252,7 +255,7 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
         lpA(ref, T);
         s0 += T[1]; s1 += T[0]; s2 += T[3]; s3 += T[2];      // ref : (1-eps) | f | f | h
         double B0, B1;
-        if (cov > 0 && cov < C) {
+        if (COVERED || (cov > 0 && cov < C)) {
             const double2 u = *reinterpret_cast<const double2*>(dmB + 2 * cov);
             B0 = u.x; B1 = u.y;
         } else {
@@ -265,7 +268,7 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
         N3 = B1 - s3;
     }
     double e[4];
-    if (cov >= 0 && cov < C) {
+    if (COVERED || (cov >= 0 && cov < C)) {
         const double2 u = *reinterpret_cast<const double2*>(cT + 4 * cov);
         const double2 w = *reinterpret_cast<const double2*>(cT + 4 * cov + 2);
         e[0] = u.x; e[1] = u.y; e[2] = w.x; e[3] = w.y;
@@ -315,7 +318,7 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
 // shared memory it fits 3 blocks with 28 bytes of spill and is 2 % slower (profiles/README.md).
 #define SV_LEAF_THREADS 256
 #define SV_LEAF_SITES (SV_LEAF_THREADS * SV_LEAF_IT)
-template <int TAB>
+template <int TAB, bool COVERED = false>
 __global__ void __launch_bounds__(SV_LEAF_THREADS, 2) k_leaf(SvLeafArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int C = a.C;
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(SV_LEAF_THREADS, 2) k_leaf(SvLeafArgs a) {
             const int s = sbase + it * SV_LEAF_THREADS;
             if (s >= a.S) continue;
             double x[4], ls, l0;
-            sv_leaf_site(c[it], dmA, dmB, cT, C, sf, a, want0, x, ls, l0);
+            sv_leaf_site<COVERED>(c[it], dmA, dmB, cT, C, sf, a, want0, x, ls, l0);
             if (outX) sv_st256(outX + (size_t)s * 4, x);
             accS[it] += ls;
             acc0[it] += l0;

@@ -64,6 +64,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     if (const char* e = getenv("SIEVE_B200_RP")) h->use_rp = atoi(e) != 0;
     if (const char* e = getenv("SIEVE_B200_PRUNE_MINB")) h->prune_minb = atoi(e);
     if (const char* e = getenv("SIEVE_B200_LEAF_TAB")) h->leaf_tab = std::min(2, std::max(0, atoi(e)));
+    if (const char* e = getenv("SIEVE_B200_LEAF_CHECKED")) h->leaf_force_checked = atoi(e) != 0;
     const bool twin = h->with_const && h->const_twin;
     const bool algebraic = h->with_const && !h->const_twin;
     h->single_ado = cfg->flags & SIEVE_FLAG_SINGLE_ADO;
@@ -313,6 +314,18 @@ __global__ void k_max_cov(const int4* __restrict__ c, size_t N, int* __restrict_
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(max_cov, mx);
 }
 
+// does every count of the shard index the look-up tables?  (0 <= alt1, alt2, alt3, cov < C; then the reference count
+// cov - sum(alt), clamped at 0, does too.)  If so the leaf kernel runs without its out-of-table paths.
+__global__ void k_counts_outside_tables(const int4* __restrict__ c, size_t N, int C, int* __restrict__ outside) {
+    int bad = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 v = c[i];
+        bad |= (unsigned)v.x >= (unsigned)C || (unsigned)v.y >= (unsigned)C || (unsigned)v.z >= (unsigned)C ||
+               (unsigned)v.w >= (unsigned)C;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(outside, 1);
+}
+
 static int sv_alloc_tables(sieve_core* h) {
     int cap = SV_TABLE_CAP_DEFAULT;
     if (const char* e = getenv("SIEVE_B200_TABLE_CAP")) cap = std::max(2, atoi(e));
@@ -328,6 +341,21 @@ static int sv_alloc_tables(sieve_core* h) {
         SV_TRY(sv_alloc(h, &h->d_cellT, (size_t)h->n * h->C * 4));
     }
     h->dm_dirty = h->cov_dirty = true;
+    // one pass over the counts (ingest time): are the tables complete for this shard?
+    int* d_flag = nullptr;
+    int flag = 1;
+    SV_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream);
+    if (e == cudaSuccess) {
+        k_counts_outside_tables<<<592, 256, 0, h->stream>>>(h->d_counts, (size_t)h->n * h->S, h->C, d_flag);
+        sv_count(h);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_flag);
+    SV_CUDA(e);
+    h->tables_cover_counts = flag == 0 && !h->leaf_force_checked;
     return SIEVE_OK;
 }
 
@@ -553,10 +581,13 @@ static int sv_launch_leaf_kernels(sieve_core* h, long long site_begin, int n_sit
     if (!h->leaf_attr_set) {
         SV_CUDA(cudaFuncSetAttribute(k_leaf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         SV_CUDA(cudaFuncSetAttribute(k_leaf<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SV_CUDA(cudaFuncSetAttribute(k_leaf<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         h->leaf_attr_set = true;
     }
     if (tab == 2)
         k_leaf<2><<<grid, SV_LEAF_THREADS, smem, h->stream>>>(a);
+    else if (tab == 1 && h->tables_cover_counts)
+        k_leaf<1, true><<<grid, SV_LEAF_THREADS, smem, h->stream>>>(a);
     else if (tab == 1)
         k_leaf<1><<<grid, SV_LEAF_THREADS, smem, h->stream>>>(a);
     else
