@@ -198,9 +198,6 @@ struct SvLeafArgs {
     SvCovParams cp;
 };
 
-#ifndef SV_LEAF_IT
-#define SV_LEAF_IT 4      // sites per thread and cell: four count tuples in flight per lane
-#endif
 #define SV_LEAF_CELLS 32  // cells per group (fixed: the grouping of the sums must not depend on the launch)
 
 __device__ __forceinline__ void sv_leaf_cp16(double* dst_smem, const double* src) {
@@ -215,7 +212,13 @@ __device__ __forceinline__ void sv_leaf_cp_wait_all() {
 // log-likelihood (only when want0)
 // COVERED: every count is known to index the tables (checked once at ingest, k_counts_outside_tables): no bounds
 // checks, no out-of-line calls -- the site evaluation is straight-line code that the compiler can interleave across sites.
-template <bool COVERED>
+// one 32-byte table row with one 256-bit load (global memory only; not volatile: the compiler may schedule it freely)
+__device__ __forceinline__ void sv_leaf_row256(const double* p, double (&v)[4]) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+// CT_GLOBAL: the cell table is in global memory (read through L1 with one 256-bit load per row: one sector per lane).
+template <bool COVERED, bool CT_GLOBAL>
 __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restrict__ dmA, const double* __restrict__ dmB,
                                              const double* __restrict__ cT, const int C, const double sf,
                                              const SvLeafArgs& a, const bool want0, double (&x)[4], double& ls,
@@ -269,9 +272,13 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
     }
     double e[4];
     if (COVERED || (cov >= 0 && cov < C)) {
-        const double2 u = *reinterpret_cast<const double2*>(cT + 4 * cov);
-        const double2 w = *reinterpret_cast<const double2*>(cT + 4 * cov + 2);
-        e[0] = u.x; e[1] = u.y; e[2] = w.x; e[3] = w.y;
+        if (CT_GLOBAL) {
+            sv_leaf_row256(cT + 4 * cov, e);
+        } else {
+            const double2 u = *reinterpret_cast<const double2*>(cT + 4 * cov);
+            const double2 w = *reinterpret_cast<const double2*>(cT + 4 * cov + 2);
+            e[0] = u.x; e[1] = u.y; e[2] = w.x; e[3] = w.y;
+        }
     } else {
         const SvD4 r = sv_cov_entry_direct(cov, sf, a.cp);
         e[0] = r.a; e[1] = r.b; e[2] = r.c; e[3] = r.d;
@@ -313,10 +320,13 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
 //   2: the cell table too in shared memory, double-buffered with cp.async (the next cell's table arrives while this
 //      cell's sites are evaluated; one barrier per cell): 14 C doubles.  Measured slower (profiles/README.md)
 //   0: everything through L1/L2 (tables too large for shared memory)
-// 256 threads x 2 blocks per SM: 128 registers hold the four unrolled site evaluations and the eight accumulators; at
-// 3 blocks per SM (85 registers) the accumulators spill and the kernel is 16 % slower; with the accumulators moved to
-// shared memory it fits 3 blocks with 28 bytes of spill and is 2 % slower (profiles/README.md).
+// 256 threads x 2 blocks per SM: 112-128 registers hold the four unrolled site evaluations and the eight accumulators.
+// Measured alternatives, all within +2..+16 % (profiles/README.md): 3 blocks per SM with spilled accumulators, with the
+// accumulators in shared memory, with 2 sites per thread (80 registers, no spill), and 6 sites per thread at 2 blocks:
+// the kernel is bound by the L1TEX data pipe (the random table look-ups: 2.5-way bank conflicts in shared memory, 32
+// sectors per look-up through L1), not by occupancy.
 #define SV_LEAF_THREADS 256
+#define SV_LEAF_IT 4  // sites per thread and cell: four count tuples in flight per lane
 #define SV_LEAF_SITES (SV_LEAF_THREADS * SV_LEAF_IT)
 template <int TAB, bool COVERED = false>
 __global__ void __launch_bounds__(SV_LEAF_THREADS, 2) k_leaf(SvLeafArgs a) {
@@ -376,7 +386,7 @@ __global__ void __launch_bounds__(SV_LEAF_THREADS, 2) k_leaf(SvLeafArgs a) {
             const int s = sbase + it * SV_LEAF_THREADS;
             if (s >= a.S) continue;
             double x[4], ls, l0;
-            sv_leaf_site<COVERED>(c[it], dmA, dmB, cT, C, sf, a, want0, x, ls, l0);
+            sv_leaf_site<COVERED, TAB != 2>(c[it], dmA, dmB, cT, C, sf, a, want0, x, ls, l0);
             if (outX) sv_st256(outX + (size_t)s * 4, x);
             accS[it] += ls;
             acc0[it] += l0;

@@ -173,6 +173,38 @@ def test_leaf_scale_sums_over_cell_groups_and_site_blocks(core_mod, oracle, monk
     eph.close()
 
 
+def test_leaf_kernel_without_bounds_checks_is_bit_identical(core_mod, monkeypatch):
+    """When the ingest scan finds every count inside the look-up tables the leaf kernel runs without its out-of-table
+    paths (k_leaf<1, true>); SIEVE_B200_LEAF_CHECKED=1 keeps them.  Same arithmetic, so the same bits -- also when the
+    tables are capped below the largest count, where the unchecked kernel must not be chosen at all."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    d = synthetic(37, 1300, seed=19)
+    counts, tree = d["counts"], d["tree"]
+    out = {}
+    for cap in (None, "24"):
+        for checked in ("0", "1"):
+            monkeypatch.setenv("SIEVE_B200_LEAF_CHECKED", checked)
+            if cap:
+                monkeypatch.setenv("SIEVE_B200_TABLE_CAP", cap)
+            else:
+                monkeypatch.delenv("SIEVE_B200_TABLE_CAP", raising=False)
+            tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=1000.0)
+            logp = tl.calculate_logp()
+            out[(cap, checked)] = (logp, tl.pattern_log_likelihoods()[0].copy(), tl.pattern_log_likelihoods()[1].copy())
+            tl.close()
+    ref = out[(None, "1")]
+    for key in ((None, "0"), ("24", "0"), ("24", "1")):
+        got = out[key]
+        if key[0] is None:
+            assert got[0] == ref[0]
+            np.testing.assert_array_equal(got[1], ref[1])
+            np.testing.assert_array_equal(got[2], ref[2])
+        else:   # direct evaluation beyond the capped tables: same formulas, equal to rounding
+            _close(got[1], ref[1], SITE_RTOL)
+            _close(got[2], ref[2], SITE_RTOL)
+    np.testing.assert_array_equal(out[("24", "0")][1], out[("24", "1")][1])
+
+
 def test_leaf_kernel_all_cells_and_edge_counts(core_mod, oracle, monkeypatch):
     rng = np.random.default_rng(8)
     S, n = 300, 5
