@@ -560,7 +560,7 @@ def main():
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             w = tr["workload"]
             if (w["cells"], w["sites"]) == (n, S) and not (args.per_level or args.matrices or args.streamed or args.sparse or with_const):
-                k = tr["k_prune<0, 1, 1>"]
+                k = next(v for name, v in tr.items() if name.startswith("k_prune<0, 1, 1"))
                 traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
         except Exception:
             traffic = None

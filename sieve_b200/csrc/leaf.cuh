@@ -129,13 +129,64 @@ __device__ __forceinline__ void sv_cov_entry(int x, double s, const SvCovParams&
     }
 }
 
+// The x-independent terms of sv_seq_cov_log for one (cell, allele count), computed once per block: the table kernel
+// then evaluates one logGamma per allele count and entry (plus logGamma(x + 1), shared by the allele counts) instead of
+// three.  Same functions of the same arguments in the same order as sv_seq_cov_log: the entries keep their bits.
+struct SvCovCellTerms {
+    double r, log1mp, lg_r, r_log_beta;
+};
+__device__ __forceinline__ SvCovCellTerms sv_seq_cov_cell_terms(int alleles, double s, double t, double v) {
+    const double ka = __dadd_rn((double)alleles, 1e-6);
+    const double mean = __dmul_rn(__dmul_rn(ka, t), s);
+    const double var = __dadd_rn(mean, __dmul_rn(__dmul_rn(__dmul_rn(s, s), __dmul_rn(ka, ka)), v));
+    const double p = __ddiv_rn(mean, var);
+    SvCovCellTerms o;
+    o.r = __ddiv_rn(__dmul_rn(mean, mean), __dadd_rn(var, -mean));
+    const double beta = __dadd_rn(__ddiv_rn(1.0, p), -1.0);
+    o.log1mp = log(__dadd_rn(1.0, -p));
+    o.lg_r = sv_log_gamma(o.r);
+    o.r_log_beta = __dmul_rn(o.r, log(beta));
+    return o;
+}
+__device__ __forceinline__ double sv_seq_cov_log_terms(int x, const SvCovCellTerms& c, double lg_x1) {
+    const double rx = __dadd_rn(c.r, (double)x);
+    double l = __dadd_rn(sv_log_gamma(rx), __dmul_rn(rx, c.log1mp));
+    l = __dadd_rn(l, -lg_x1);
+    l = __dadd_rn(l, -c.lg_r);
+    l = __dadd_rn(l, -c.r_log_beta);
+    return l;
+}
+
 __global__ void k_build_cell_tables(double* __restrict__ cellT, const double* __restrict__ size_factors, int n_cells,
                                     int C, SvCovParams cp) {
+    __shared__ SvCovCellTerms terms[3];  // 2, 1 and (locus dropout) 0 sequenced alleles
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
-    if (x >= C || j >= n_cells) return;
+    if (j >= n_cells) return;
+    if (threadIdx.x < 3) terms[threadIdx.x] = sv_seq_cov_cell_terms(2 - (int)threadIdx.x, size_factors[j], cp.t, cp.v);
+    __syncthreads();
+    if (x >= C) return;
+    const double lg_x1 = sv_log_gamma(__dadd_rn((double)x, 1.0));
+    const double c2 = sv_seq_cov_log_terms(x, terms[0], lg_x1);
+    const double c1 = sv_seq_cov_log_terms(x, terms[1], lg_x1);
+    const double lt = log(cp.theta), l1t = log(1 - cp.theta);
     double e[4];
-    sv_cov_entry(x, size_factors[j], cp, e);
+    if (cp.single_ado) {
+        const double a = l1t + c2, b = lt + c1;
+        const double m = fmax(a, b);
+        e[0] = exp(a - m);
+        e[1] = exp(b - m);
+        e[2] = m;
+        e[3] = log(e[0] + e[1]) + m;
+    } else {
+        const double c0 = sv_seq_cov_log_terms(x, terms[2], lg_x1);
+        const double a = 2 * l1t + c2, b = lt + l1t + c1, z = 2 * lt + c0;
+        const double m = fmax(fmax(a, b), z);
+        e[0] = exp(a - m);
+        e[1] = exp(b - m);
+        e[2] = m;
+        e[3] = z - m;
+    }
     sv_st256(cellT + ((size_t)j * C + x) * 4, e);
 }
 
