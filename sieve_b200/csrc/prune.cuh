@@ -206,10 +206,22 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, MINB ? MINB
         for (int g = 0; g < 4; g++) x[j][g] = cx[j][g] = 0.0;
     }
 
+    // the descriptor of the next op is fetched while this op's operands are in flight: it is off the critical path
+    // (descriptor -> addresses -> operand loads) of every op but the first
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
+    if (i0 < i1) {
+        const int4* opp = reinterpret_cast<const int4*>(a.ops + i0);
+        n0 = __ldg(opp);
+        n1 = __ldg(opp + 1);
+    }
     for (int i = i0; i < i1; i++) {
         __syncwarp();  // scratch slots are reused (streamed mode): keep the warp's reads of an op ahead of the next op's writes
-        const int4* opp = reinterpret_cast<const int4*>(a.ops + i);
-        const int4 o0 = __ldg(opp), o1 = __ldg(opp + 1);
+        const int4 o0 = n0, o1 = n1;
+        if (i + 1 < i1) {
+            const int4* opp = reinterpret_cast<const int4*>(a.ops + i + 1);
+            n0 = __ldg(opp);
+            n1 = __ldg(opp + 1);
+        }
         const unsigned dst_base = (unsigned)o0.x, c1_base = (unsigned)o0.y, c2_base = (unsigned)o0.z;
         const int m1 = o0.w, m2 = o1.x, flags = o1.y;
         const bool unary = flags & SV_OP_UNARY;
