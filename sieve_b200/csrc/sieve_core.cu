@@ -887,13 +887,14 @@ extern "C" int sieve_set_root(sieve_core_t* h, int32_t root, const double* propo
 // Resident blocks per SM for the variant-only Q walk.  Every block walks the whole op list, so a launch takes as long as
 // its waves of blocks: full waves cost their share, the last partial wave (a fraction phi of the slots) costs about
 // 0.3 + 0.65 phi of a full one (its blocks run faster on a less crowded SM, measured at 6 blocks/SM over 1.0 .. 3.0
-// waves).  The kernel compiles to 74 registers (6 blocks/SM); capped at 72 / 64 registers it spills 16 / 36 bytes and
-// fits 7 / 8 blocks, which at whole waves is 3 % faster per site -- but what decides is how the launch's blocks divide
-// into waves: 100 000 sites are 1.76 / 1.51 / 1.32 waves (6 wins), 125 000 sites 2.20 / 1.89 / 1.65 (7 wins by 12 %).
-// Same PTX, same arithmetic: the choice cannot change a bit of the results.  profiles/README.md has the measurements.
+// waves).  The kernel compiles to 78 registers (6 blocks/SM); capped at 72 / 64 registers it spills 8 / 48 bytes and
+// fits 7 / 8 blocks, which at whole waves is 3 / 6 % slower per site -- but what decides is how the launch's blocks
+// divide into waves: 100 000 sites are 1.76 / 1.51 / 1.32 waves (6 wins: 2.50 / 2.66 / 2.86 ms), 125 000 sites 2.20 /
+// 1.89 / 1.65 (7 wins: 3.29 / 3.19 / 3.50 ms).  Same PTX, same arithmetic: the choice cannot change a bit of the results.
+// profiles/README.md has the measurements.
 static int sv_pick_prune_blocks(unsigned blocks) {
     static const int m[3] = {6, 7, 8};
-    static const double per_wave[3] = {6.0, 7.0 * 0.972, 8.0 * 0.975};
+    static const double per_wave[3] = {6.0, 7.0 * 1.026, 8.0 * 1.058};
     int best = 6;
     double best_t = 0.0;
     if (blocks <= 148u * 6u) return best;  // everything is resident at once anyway
