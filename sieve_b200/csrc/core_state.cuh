@@ -97,6 +97,7 @@ struct sieve_core {
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
     bool force_generic = false;
+    int rp_blocks = 5;
     bool use_rp = false;  // SIEVE_B200_RP=1: next op's operands prefetched into registers (prune_rp.cuh)
     bool use_pipe = false, pipe_attr_set = false;  // SIEVE_B200_PIPE=1: the cp.async-pipelined Q walk (measured slower, see prune_pipe.cuh)
     // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk

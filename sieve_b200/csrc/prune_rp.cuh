@@ -1,72 +1,30 @@
-// prune_rp.cuh -- the Q-specialised, variant-only pruning walk with the NEXT op's operands prefetched into registers.
+// prune_rp.cuh -- the Q-specialised, variant-only pruning walk as a two-stage software pipeline in registers.
 //
-// Same arithmetic, op list and results (bit for bit) as k_prune<false, true, true>.  That kernel is latency bound
-// (profiles/r01g_*: issue slots 50 % busy, long-scoreboard stalls, DRAM 45 %): a warp issues the loads of an op, waits
-// ~1 us for DRAM, computes ~250 instructions, and only then learns the addresses of the next op.  Here the loads of op
-// i + 1 (both children's vectors and scales for the lane's two sites, the two branch factors) are issued BEFORE op i is
-// computed and land in a second set of registers; op i + 1 starts with its operands present.  More registers (4 blocks
-// of 128 threads per SM instead of 6), but every resident warp now always has a full op of loads in flight.
-// The staging through shared memory that prune_pipe.cuh tried for the same purpose doubled the L1TEX traffic; registers
-// do not.
+// Same arithmetic, op list and results (bit for bit) as k_prune<false, true, true>.  That kernel is latency bound: per
+// op a warp issues its operand loads, waits for DRAM, computes ~250 instructions and only then starts the next op.  In
+// a post-order walk the first operand of most ops is the previous result (SV_OP_FWD1, in registers), so what an op
+// waits for is its SECOND child.  Here the second child of op i + 1 is loaded into a second register set BEFORE op i is
+// computed -- and before op i waits for its own second child, which was requested one op earlier: two loads are in
+// flight per lane alternately and an op costs about (latency + compute) / 2 instead of their sum.  The two sets swap
+// roles by unrolling the walk by two (no register moves).  An op whose second child is the slot the previous op is
+// about to write (never the case for the planner's post-order lists, possible with reused scratch slots) loads it late,
+// like the plain walk; a first child that does not come from registers (both children leaves) is loaded at the top of
+// its op as before.  20 more registers than the plain walk: 5 blocks of 128 threads per SM instead of 6.
 //
-// MEASURED (B200, 1 000 cells x 100 000 sites, gpurun 2026-10-20): 3.37 ms against 2.85 ms for the plain walk -- SLOWER,
-// so this kernel too is opt-in (SIEVE_B200_RP=1) and kept as the record of the experiment: 124 registers leave 16 warps
-// per SM instead of 24, and the extra warps of the plain kernel hide more latency than one op of look-ahead per warp.
-// Results are bit-identical (tests/test_gpu_parity.py::test_pipelined_walk_is_bit_identical).
+// MEASURED (B200, 1 000 cells x 100 000 sites): 4.17 ms at 5 blocks/SM (96 registers, 52 bytes of spill) and 4.01 ms at
+// 4 blocks/SM (120 registers, no spill) against 2.50 ms for the plain walk -- SLOWER, bit-identical
+// (tests/test_gpu_parity.py::test_pipelined_walk_is_bit_identical), so the kernel stays opt-in (SIEVE_B200_RP=1 / 4) as
+// the record of the experiment.  Together with two other measurements -- storing a third as many partials
+// (SIEVE_B200_TRANSIENT_LEAVES=32: 5.5 -> 2 GB of writes) changes the walk by 1 %, and fetching the 32-byte descriptor
+// one op ahead gains 7 % -- this says that the walk is bound neither by DRAM bandwidth nor simply by the load latency
+// of one warp: a second load in flight per lane did not shorten an op.
+// A first version (earlier the same day) moved the prefetched operands into the working registers BEFORE issuing the
+// next prefetch -- the move waits for the data, so only one op's loads were ever in flight -- 3.37 vs 2.85 ms.
 #pragma once
 #include "prune.cuh"
 
-#ifndef SV_RP_MINB
-#define SV_RP_MINB 4
-#endif
-
-struct SvRpOperands {
-    double x[2][4], w[2][4];  // child 1 / child 2 vectors of the lane's two sites
-    double xs[2], ws[2];      // their scales
-    double2 q1, q2;           // branch factors
-    unsigned dst_base;
-    int flags;
-};
-
-// issue the loads of op `i`; nothing here waits
-template <int NS>
-__device__ __forceinline__ void sv_rp_issue(const SvPruneArgs& a, int i, int k, const unsigned (&srow)[NS], SvRpOperands& o) {
-    const int4* opp = reinterpret_cast<const int4*>(a.ops + i);
-    const int4 o0 = __ldg(opp), o1 = __ldg(opp + 1);
-    const unsigned c1_base = (unsigned)o0.y, c2_base = (unsigned)o0.z;
-    const int m1 = o0.w, m2 = o1.x, flags = o1.y;
-    o.dst_base = (unsigned)o0.x;
-    o.flags = flags;
-    o.q1 = __ldg(a.qfac + (size_t)m1 * SV_KMAX + k);
-    o.q2 = make_double2(0.0, 0.0);
-    if (!(flags & SV_OP_UNARY)) o.q2 = __ldg(a.qfac + (size_t)m2 * SV_KMAX + k);
-#pragma unroll
-    for (int j = 0; j < NS; j++) {
-        const size_t c1_row = c1_base + srow[j], c2_row = c2_base + srow[j];
-        if (!(flags & SV_OP_FWD1)) {
-            if (flags & SV_OP_LEAF1) {
-                sv_ld256_nc(a.leafX + c1_row * 4, o.x[j]);
-                o.xs[j] = 0.0;
-            } else {
-                sv_ld256(a.part + c1_row * 16 + k * 4, o.x[j]);
-                o.xs[j] = a.scale[c1_row];
-            }
-        }
-        o.ws[j] = 0.0;
-        if (!(flags & SV_OP_UNARY)) {
-            if (flags & SV_OP_LEAF2) {
-                sv_ld256_nc(a.leafX + c2_row * 4, o.w[j]);
-                o.ws[j] = 0.0;
-            } else {
-                sv_ld256(a.part + c2_row * 16 + k * 4, o.w[j]);
-                o.ws[j] = a.scale[c2_row];
-            }
-        }
-    }
-}
-
-template <bool GENO0>
-__global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_RP_MINB) k_prune_rp(SvPruneArgs a) {
+template <bool GENO0, int MINB>
+__global__ void __launch_bounds__(SV_PRUNE_THREADS, MINB) k_prune_rp(SvPruneArgs a) {
     constexpr int NS = 2;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -86,50 +44,73 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_RP_MINB) k_prune_rp(SvPru
     if (i0 >= i1) return;
 
     double x[NS][4], xs[NS];  // the running result (forwarded to the next op when it asks for it)
+    double wA[NS][4], wsA[NS], wB[NS][4], wsB[NS];  // the two register sets for second children
 #pragma unroll
     for (int j = 0; j < NS; j++) {
-        xs[j] = 0.0;
+        xs[j] = wsA[j] = wsB[j] = 0.0;
 #pragma unroll
-        for (int g = 0; g < 4; g++) x[j][g] = 0.0;
+        for (int g = 0; g < 4; g++) x[j][g] = wA[j][g] = wB[j][g] = 0.0;
     }
-    SvRpOperands nx;
-#pragma unroll
-    for (int j = 0; j < NS; j++)
-#pragma unroll
-        for (int g = 0; g < 4; g++) nx.x[j][g] = nx.w[j][g] = 0.0;
-    nx.xs[0] = nx.xs[1] = nx.ws[0] = nx.ws[1] = 0.0;
-    sv_rp_issue<NS>(a, i0, k, srow, nx);
-    bool refetch = false;
-    for (int i = i0; i < i1; i++) {
-        __syncwarp();  // scratch slots are reused (streamed / sparse walks): keep the warp's reads ahead of the next op's writes
-        if (refetch) sv_rp_issue<NS>(a, i, k, srow, nx);  // its operand was written by the previous op: could not be fetched early
-        // take over the prefetched operands
-        const int flags = nx.flags;
-        const unsigned dst_base = nx.dst_base;
-        const bool unary = flags & SV_OP_UNARY;
-        const double2 q1 = nx.q1, q2 = nx.q2;
-        double w[NS][4], ws[NS];
+    // requests the second child of the op described by (d0, flags); nothing here waits
+    auto issue_child2 = [&](const int4& d0, const int flags, double (&w)[NS][4], double (&ws)[NS]) {
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            if (!(flags & SV_OP_FWD1)) {
-#pragma unroll
-                for (int g = 0; g < 4; g++) x[j][g] = nx.x[j][g];
-                xs[j] = nx.xs[j];
+            const size_t row = (unsigned)d0.z + srow[j];
+            if (flags & SV_OP_LEAF2) {
+                sv_ld256_nc(a.leafX + row * 4, w[j]);
+                ws[j] = 0.0;
+            } else {
+                sv_ld256(a.part + row * 16 + k * 4, w[j]);
+                ws[j] = a.scale[row];
             }
-#pragma unroll
-            for (int g = 0; g < 4; g++) w[j][g] = nx.w[j][g];
-            ws[j] = nx.ws[j];
         }
-        // the next op's loads go out now and are in flight during this op's arithmetic -- unless one of its operands is
-        // what this op is about to store (the forwarding covers the common case; anything else is fetched afterwards)
-        refetch = false;
+    };
+    int4 n0 = __ldg(reinterpret_cast<const int4*>(a.ops + i0));
+    int4 n1 = __ldg(reinterpret_cast<const int4*>(a.ops + i0) + 1);
+    bool haveA = false, haveB = false;
+    if (!(n1.y & SV_OP_UNARY)) {
+        issue_child2(n0, n1.y, wA, wsA);
+        haveA = true;
+    }
+
+    // one op: operands of its second child in (w, ws) if `have`; the next op's second child goes to (wn, wsn)
+    auto step = [&](const int i, double (&w)[NS][4], double (&ws)[NS], const bool have, double (&wn)[NS][4],
+                    double (&wsn)[NS], bool& have_n) {
+        __syncwarp();  // scratch slots are reused (streamed / sparse walks): keep the warp's reads ahead of the next op's writes
+        const int4 o0 = n0, o1 = n1;
         if (i + 1 < i1) {
-            const int4 n0 = __ldg(reinterpret_cast<const int4*>(a.ops + i + 1));
-            const int4 n1 = __ldg(reinterpret_cast<const int4*>(a.ops + i + 1) + 1);
-            const bool dep1 = !(n1.y & (SV_OP_LEAF1 | SV_OP_FWD1)) && (unsigned)n0.y == dst_base;
-            const bool dep2 = !(n1.y & (SV_OP_LEAF2 | SV_OP_UNARY)) && (unsigned)n0.z == dst_base;
-            refetch = dep1 || dep2;
-            if (!refetch) sv_rp_issue<NS>(a, i + 1, k, srow, nx);
+            n0 = __ldg(reinterpret_cast<const int4*>(a.ops + i + 1));
+            n1 = __ldg(reinterpret_cast<const int4*>(a.ops + i + 1) + 1);
+        }
+        const unsigned dst_base = (unsigned)o0.x, c1_base = (unsigned)o0.y;
+        const int m1 = o0.w, m2 = o1.x, flags = o1.y;
+        const bool unary = flags & SV_OP_UNARY;
+        const double2 q1 = __ldg(a.qfac + (size_t)m1 * SV_KMAX + k);
+        double2 q2 = make_double2(0.0, 0.0);
+        if (!unary) q2 = __ldg(a.qfac + (size_t)m2 * SV_KMAX + k);
+        if (!(flags & SV_OP_FWD1)) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                const size_t c1_row = c1_base + srow[j];
+                if (flags & SV_OP_LEAF1) {
+                    sv_ld256_nc(a.leafX + c1_row * 4, x[j]);
+                    xs[j] = 0.0;
+                } else {
+                    sv_ld256(a.part + c1_row * 16 + k * 4, x[j]);
+                    xs[j] = a.scale[c1_row];
+                }
+            }
+        }
+        if (!unary && !have) issue_child2(o0, flags, w, ws);  // could not be requested early
+        // the next op's second child: requested now, in flight while this op waits for its own and computes
+        have_n = false;
+        if (i + 1 < i1) {
+            const int nf = n1.y;
+            const bool dep = !(nf & SV_OP_LEAF2) && (unsigned)n0.z == dst_base;  // it is what this op is about to write
+            if (!(nf & SV_OP_UNARY) && !dep) {
+                issue_child2(n0, nf, wn, wsn);
+                have_n = true;
+            }
         }
         const bool cz0 = flags & SV_OP_ZEROD;
         double y[NS][4];
@@ -151,7 +132,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_RP_MINB) k_prune_rp(SvPru
             const double f = sv_pow2_rescale_hi(hi, &sh);
 #pragma unroll
             for (int p = 0; p < 4; p++) x[j][p] = y[j][p] * f;
-            xs[j] = (xs[j] + ws[j]) + sh;
+            xs[j] = (xs[j] + (unary ? 0.0 : ws[j])) + sh;
         }
 #pragma unroll
         for (int j = 0; j < NS; j++) {
@@ -170,5 +151,9 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, SV_RP_MINB) k_prune_rp(SvPru
                 if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + (xs[j] + lsum);
             }
         }
+    };
+    for (int i = i0; i < i1; i += 2) {
+        step(i, wA, wsA, haveA, wB, wsB, haveB);
+        if (i + 1 < i1) step(i + 1, wB, wsB, haveB, wA, wsA, haveA);
     }
 }

@@ -61,7 +61,10 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->with_const = cfg->flags & SIEVE_FLAG_CONST_PARTIALS;
     if (const char* e = getenv("SIEVE_B200_CONST_TWIN")) h->const_twin = atoi(e) != 0;
     if (const char* e = getenv("SIEVE_B200_PIPE")) h->use_pipe = atoi(e) != 0;
-    if (const char* e = getenv("SIEVE_B200_RP")) h->use_rp = atoi(e) != 0;
+    if (const char* e = getenv("SIEVE_B200_RP")) {  // 1: the register-pipelined walk at 5 blocks/SM, 4: at 4 blocks/SM
+        h->use_rp = atoi(e) != 0;
+        h->rp_blocks = atoi(e) == 4 ? 4 : 5;
+    }
     if (const char* e = getenv("SIEVE_B200_PRUNE_MINB")) h->prune_minb = atoi(e);
     if (const char* e = getenv("SIEVE_B200_LEAF_TAB")) h->leaf_tab = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("SIEVE_B200_LEAF_CHECKED")) h->leaf_force_checked = atoi(e) != 0;
@@ -984,7 +987,12 @@ static int sv_launch_staged(sieve_core* h) {
             if (pipe)
                 k_prune_pipe<true><<<grid, SV_PRUNE_THREADS, SV_PIPE_SMEM, h->stream>>>(a);
             else if (rp)
-                k_prune_rp<true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            {
+                if (h->rp_blocks == 4)
+                    k_prune_rp<true, 4><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+                else
+                    k_prune_rp<true, 5><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            }
             else if (qfast)
                 sv_launch_prune_t<true>(h, grid, a);
             else
