@@ -1,6 +1,7 @@
 // core_state.cuh -- the handle behind sieve_core_t and the small host helpers every part of the core uses.
 // Included by sieve_core.cu only (one translation unit); split out for readability.
 #pragma once
+#include <unordered_map>
 static thread_local std::string g_err;
 
 static int sv_fail(int code, const std::string& msg) {
@@ -97,6 +98,9 @@ struct sieve_core {
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
     bool force_generic = false;
+    bool use_tma = false, tma_attr_set = false;  // SIEVE_B200_TMA: the TMA-staged walk (prune_tma.cuh)
+    int tma_stages = 3;
+    std::unordered_map<unsigned, int> scratch_writer;
     int rp_blocks = 5;
     bool use_rp = false;  // SIEVE_B200_RP=1: next op's operands prefetched into registers (prune_rp.cuh)
     bool use_pipe = false, pipe_attr_set = false;  // SIEVE_B200_PIPE=1: the cp.async-pipelined Q walk (measured slower, see prune_pipe.cuh)

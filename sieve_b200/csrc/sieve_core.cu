@@ -17,6 +17,7 @@
 #include "prune.cuh"
 #include "prune_pipe.cuh"
 #include "prune_rp.cuh"
+#include "prune_tma.cuh"
 #include "reduce.cuh"
 #include "maxsum.cuh"
 #include "sizefactors.cuh"
@@ -66,6 +67,10 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         h->rp_blocks = atoi(e) == 4 ? 4 : 5;
     }
     if (const char* e = getenv("SIEVE_B200_PRUNE_MINB")) h->prune_minb = atoi(e);
+    if (const char* e = getenv("SIEVE_B200_TMA")) {  // N > 0: the TMA-staged walk with N stages (2..4; 1 means 3)
+        h->use_tma = atoi(e) != 0;
+        h->tma_stages = atoi(e) == 2 ? 2 : atoi(e) == 4 ? 4 : 3;
+    }
     if (const char* e = getenv("SIEVE_B200_LEAF_TAB")) h->leaf_tab = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("SIEVE_B200_LEAF_CHECKED")) h->leaf_force_checked = atoi(e) != 0;
     const bool twin = h->with_const && h->const_twin;
@@ -978,13 +983,30 @@ static int sv_launch_staged(sieve_core* h) {
         // the software-pipelined walk (prune_pipe.cuh): Q-specialised, variant partials only, one launch for many ops
         const bool pipe = qfast && !(h->with_const && h->const_twin) && h->use_pipe && !h->last_per_level;
         const bool rp = qfast && !(h->with_const && h->const_twin) && h->use_rp && !h->last_per_level && !pipe;
+        // the TMA-staged walk (prune_tma.cuh): scale rows must be 16-byte aligned, i.e. the pools' site capacity even
+        const long long cap_sites = h->ephemeral ? (long long)h->chunk_cap : (long long)h->S;
+        const bool tma = qfast && !(h->with_const && h->const_twin) && h->use_tma && !h->last_per_level && !pipe && !rp &&
+                         cap_sites % 2 == 0;
+        if (tma && !h->tma_attr_set) {
+            SV_CUDA(cudaFuncSetAttribute(k_prune_tma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_tma_smem(2)));
+            SV_CUDA(cudaFuncSetAttribute(k_prune_tma<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_tma_smem(3)));
+            SV_CUDA(cudaFuncSetAttribute(k_prune_tma<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_tma_smem(4)));
+            h->tma_attr_set = true;
+        }
         if (pipe && !h->pipe_attr_set) {
             SV_CUDA(cudaFuncSetAttribute(k_prune_pipe<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
             h->pipe_attr_set = true;
         }
         auto launch = [&](dim3 grid) {
-            if (pipe)
+            if (tma && grid.y == 1) {
+                if (h->tma_stages == 2)
+                    k_prune_tma<true, 2><<<grid, SV_PRUNE_THREADS, sv_tma_smem(2), h->stream>>>(a);
+                else if (h->tma_stages == 4)
+                    k_prune_tma<true, 4><<<grid, SV_PRUNE_THREADS, sv_tma_smem(4), h->stream>>>(a);
+                else
+                    k_prune_tma<true, 3><<<grid, SV_PRUNE_THREADS, sv_tma_smem(3), h->stream>>>(a);
+            } else if (pipe)
                 k_prune_pipe<true><<<grid, SV_PRUNE_THREADS, SV_PIPE_SMEM, h->stream>>>(a);
             else if (rp)
             {
@@ -1109,7 +1131,29 @@ static int sv_flush(sieve_core* h) {
     SV_TRY(sv_ensure_stage(h, total));
     SV_CUDA(cudaStreamSynchronize(h->stream));  // the previous step may still be reading the staging buffer
     sv_link_forwarding(h->pending_ops, h->pending_per_level);
-    if (no) memcpy(h->h_stage, h->pending_ops.data(), no * sizeof(SvOp));
+    if (no) {
+        // dependencies through memory inside the list (prune_tma.cuh): for every op the last earlier op that writes one of
+        // its memory operands, and on that producer the flag that makes it publish its stores to the copy engine
+        std::vector<SvOp>& ops = h->pending_ops;
+        std::unordered_map<unsigned, int>& last_writer = h->scratch_writer;
+        last_writer.clear();
+        for (size_t i = 0; i < no; i++) {
+            SvOp& op = ops[i];
+            int r = -1;
+            if (!(op.flags & (SV_OP_LEAF1 | SV_OP_FWD1))) {
+                auto it = last_writer.find(op.c1_row);
+                if (it != last_writer.end()) r = std::max(r, it->second);
+            }
+            if (!(op.flags & (SV_OP_LEAF2 | SV_OP_UNARY))) {
+                auto it = last_writer.find(op.c2_row);
+                if (it != last_writer.end()) r = std::max(r, it->second);
+            }
+            op.pad0 = r;
+            if (r >= 0) ops[r].flags |= SV_OP_FENCE;
+            if (!(op.flags & SV_OP_NOSTORE)) last_writer[op.dst_row] = (int)i;
+        }
+        memcpy(h->h_stage, ops.data(), no * sizeof(SvOp));
+    }
     size_t im = 0, id = 0;
     for (const PendingMatrix& pm : h->pending_mats) {
         if (pm.skip) continue;

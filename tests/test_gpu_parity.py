@@ -834,16 +834,18 @@ def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatc
 
 
 def test_pipelined_walk_is_bit_identical(core_mod, oracle, monkeypatch):
-    """SIEVE_B200_PIPE=1 takes the cp.async-pipelined walk (prune_pipe.cuh), SIEVE_B200_RP=1 the register-prefetch walk
-    (prune_rp.cuh): same op list, same arithmetic, so every number must be identical -- resident with proposals /
-    rejections, and streamed with ragged chunks."""
+    """SIEVE_B200_PIPE=1 takes the cp.async-pipelined walk (prune_pipe.cuh), SIEVE_B200_RP=1 the register-pipelined walk
+    (prune_rp.cuh), SIEVE_B200_TMA=N the TMA-staged walk with N stages (prune_tma.cuh; needs an even site count): same op
+    list, same arithmetic, so every number must be identical -- resident with proposals / rejections, and streamed with
+    ragged chunks."""
     from sieve_b200.treelikelihood import ScsTreeLikelihood
-    d = synthetic(41, 333, seed=83)
+    d = synthetic(41, 334, seed=83)
     counts, tree = d["counts"], d["tree"]
     runs = {}
-    for P in ("0", "1", "rp"):
+    for P in ("0", "1", "rp", "tma2", "tma3", "tma4"):
         monkeypatch.setenv("SIEVE_B200_PIPE", "1" if P == "1" else "0")
         monkeypatch.setenv("SIEVE_B200_RP", "1" if P == "rp" else "0")
+        monkeypatch.setenv("SIEVE_B200_TMA", P[3] if P.startswith("tma") else "0")
         out = []
         for eph in (False, True):
             if eph:
@@ -867,9 +869,9 @@ def test_pipelined_walk_is_bit_identical(core_mod, oracle, monkeypatch):
             tl.close()
             monkeypatch.delenv("SIEVE_B200_CHUNK_SITES", raising=False)
         runs[P] = out
-    for a, b, c in zip(runs["0"], runs["1"], runs["rp"]):
-        np.testing.assert_array_equal(a, b)
-        np.testing.assert_array_equal(a, c)
+    for P in ("1", "rp", "tma2", "tma3", "tma4"):
+        for a, b in zip(runs["0"], runs[P]):
+            np.testing.assert_array_equal(a, b, err_msg=P)
 
 
 def test_algebraic_constant_site_path_equals_per_site_twin(core_mod, oracle, monkeypatch):
