@@ -19,8 +19,7 @@ struct __align__(16) SvOp {
     unsigned c2_row;   // child 2, unused for a unary op
     int m1, m2;        // matrix slots (buffer * n_nodes + node) of the two children
     int flags;         // SV_OP_*
-    int pad0;          // ready_after: index of the last earlier op of the list that writes one of this op's memory operands, -1: none
-    int pad1;
+    int pad0, pad1;
 };  // 32 bytes: two 128-bit loads.  Rows are 32-bit: every pool holds fewer than 2^32 (slot, site) rows (checked at create).
 #define SV_OP_LEAF1 1
 #define SV_OP_LEAF2 2
@@ -28,7 +27,8 @@ struct __align__(16) SvOp {
 #define SV_OP_ROOT 8
 #define SV_OP_FWD1 16
 #define SV_OP_ZEROD 64    // one of the two distances is exactly 0: take the Double.MIN_VALUE clamp path
-#define SV_OP_FENCE 128   // a later op of the same list reads this op's result from memory (set when the list is staged)
+#define SV_OP_DEP1 256    // child 1 / child 2 is read from memory AND written by an earlier op of the same list (set when
+#define SV_OP_DEP2 512    // the list is staged; prune_tma.cuh does not stage such an operand)
 #define SV_OP_NOSTORE 32  // the result is consumed from registers by the next op and never needed again: skip the writes
 
 // 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one (site, category) state vector.

@@ -8,24 +8,26 @@
 // stage, not per scoreboard: up to STAGES - 1 ops of loads are in flight per warp while it computes, the copies never
 // touch the LSU/L1 path of the lanes, and the lanes fetch their 32-byte slices with two conflict-free LDS.128.
 //
-// Hazards.  An operand that an op of the same launch writes must not be requested before that op has stored it: the
-// host annotates every op with `ready_after`, the index of the last earlier op that writes one of its memory operands
-// (-1: none), and flags that producer SV_OP_FENCE: after its stores the warp issues fence.proxy.async + __syncwarp so
-// that the copy engine (async proxy) sees them.  Ops are issued in order; an op that is not ready holds the ones behind
-// it back (the forwarded first child, the common dependency of a post-order walk, stays in registers as in k_prune).
+// Hazards.  An operand that an earlier op of the same launch writes is NOT staged: the host flags it (SV_OP_DEP1 /
+// SV_OP_DEP2) and the lanes load it themselves when the op is computed, exactly like k_prune (a lane only re-reads what
+// it wrote itself, so no fence is needed).  Everything else -- the leaves, and partials left by earlier launches -- is
+// read-only for the launch and can be requested any number of ops ahead.  (The first version staged the dependent
+// operands too, ordered by a host-computed `ready_after` and published with fence.proxy.async after the producing op:
+// that fence compiles to MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC and took 12 % of all stall samples.)  The forwarded first
+// child, the common dependency of a post-order walk, stays in registers as in k_prune.
 //
 // Needs an even site capacity (16-byte alignment of the scale rows); the host falls back to k_prune otherwise.
 //
-// MEASURED (B200, 1 000 cells x 100 000 sites, SIEVE_B200_TMA=2 / 3 / 4 stages): 5.7 / 5.6 / 7.3 ms against 2.50 ms for
-// the plain walk, bit-identical (tests/test_gpu_parity.py::test_pipelined_walk_is_bit_identical, resident and streamed).
-// SLOWER, so opt-in -- but for a different reason than the earlier pipelines (profiles/r01k_walk_tma_ncu.txt): the
-// pipeline works, long-scoreboard stalls per issue drop from 4.8 to 1.6 and DRAM is no longer waited for; what it costs
-// is instructions, 2.69e9 against 1.62e9 (every lane decodes the descriptors it requests, 64-bit address arithmetic,
-// the half-swapping selects of the slices), and the publishing fence: fence.proxy.async compiles to MEMBAR.ALL.CTA +
-// FENCE.VIEW.ASYNC and is executed by a third of the ops (12 % of all stall samples on that one instruction, 11 % more
-// on the first instruction after the mbarrier wait).  The version to try next: the request logic under a lane-0 branch
-// (or a dedicated producer warp per block), one fence per dependent REQUEST instead of per producing op, scales
-// packed next to the vectors so that an operand is one copy.
+// MEASURED (B200, 1 000 cells x 100 000 sites, SIEVE_B200_TMA=2 / 3 / 4 stages), bit-identical every time
+// (tests/test_gpu_parity.py::test_pipelined_walk_is_bit_identical, resident and streamed), against 2.50 ms for the plain walk:
+//   first version (dependent operands staged too, fence per producing op, half-swapped slices): 5.7 / 5.6 / 7.3 ms.
+//     ncu (profiles/r01k_walk_tma_ncu.txt): the pipeline works -- long-scoreboard stalls per issue drop from 4.8 to 1.6 --
+//     but 2.69e9 instructions against 1.62e9 (431 against 260 per op and warp: every lane decodes the descriptors it
+//     requests, 64-bit address arithmetic, the selects of the slices) and the fence on a third of the ops;
+//   this version: 4.2 / 4.9 / 6.2 ms.  Still SLOWER, so opt-in; and more stages are slower, i.e. the occupancy that the
+//     stages cost (52 KB per block at 3 stages: 4 blocks/SM, 94 registers) is worth more than the look-ahead they buy.
+// What is left to try: a producer warp per block instead of request logic in every warp, operands packed so that one is
+// one copy (scales next to the vectors), 8 sites per warp and stage to halve the shared memory.
 #pragma once
 #include "prune.cuh"
 
@@ -60,15 +62,11 @@ __device__ __forceinline__ bool sv_mbar_try_wait(unsigned bar, unsigned parity) 
 __device__ __forceinline__ void sv_lds128(unsigned addr, double& a, double& b) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
 }
-// a lane's 32-byte slice as two 16-byte halves, the half at `first` (0 or 16) fetched first
-__device__ __forceinline__ void sv_lds_slice(unsigned addr, unsigned first, double (&v)[4]) {
-    double a0, a1, b0, b1;
-    sv_lds128(addr + first, a0, a1);
-    sv_lds128(addr + (16 - first), b0, b1);
-    v[0] = first ? b0 : a0;
-    v[1] = first ? b1 : a1;
-    v[2] = first ? a0 : b0;
-    v[3] = first ? a1 : b1;
+// a lane's 32-byte slice as two 16-byte halves (2-way bank conflicts inside a quarter warp: the two sites of a quarter
+// warp are 128 bytes apart; swapping the halves by site parity avoids them but costs eight selects per slice)
+__device__ __forceinline__ void sv_lds_slice(unsigned addr, double (&v)[4]) {
+    sv_lds128(addr, v[0], v[1]);
+    sv_lds128(addr + 16, v[2], v[3]);
 }
 __device__ __forceinline__ double sv_lds64(unsigned addr) {
     double v;
@@ -111,9 +109,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS) k_prune_tma(SvPruneArgs a) {
     }
     __syncwarp();
 
-    // this lane's slices inside a stage: site j of the lane, category k -> 32 bytes, fetched as two 16-byte halves in an
-    // order that alternates with the site's parity (no bank conflicts inside a quarter warp)
-    const unsigned half0 = ((lane >> 2) & 1) * 16;
+    // this lane's slices inside a stage: site j of the lane, category k -> 32 bytes
     unsigned voff[NS], loff[NS], soff[NS];
 #pragma unroll
     for (int j = 0; j < NS; j++) {
@@ -131,7 +127,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS) k_prune_tma(SvPruneArgs a) {
         const unsigned st = (unsigned)((p - i0) % STAGES);
         const unsigned base = stage0 + st * SV_TMA_STAGE_BYTES;
         const unsigned bar = bar0 + 8 * st;
-        const bool need1 = !(flags & SV_OP_FWD1), need2 = !(flags & SV_OP_UNARY);
+        const bool need1 = !(flags & (SV_OP_FWD1 | SV_OP_DEP1)), need2 = !(flags & (SV_OP_UNARY | SV_OP_DEP2));
         const bool leaf1 = flags & SV_OP_LEAF1, leaf2 = flags & SV_OP_LEAF2;
         unsigned bytes = 0;
         if (need1) bytes += leaf1 ? (unsigned)n_valid * 32 : (unsigned)n_valid * 136;
@@ -158,7 +154,6 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS) k_prune_tma(SvPruneArgs a) {
             }
         }
     };
-    auto ready_after = [&](const int p) { return __ldg(&a.ops[p].pad0); };
 
     double x[NS][4], xs[NS];
 #pragma unroll
@@ -167,18 +162,15 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS) k_prune_tma(SvPruneArgs a) {
 #pragma unroll
         for (int g = 0; g < 4; g++) x[j][g] = 0.0;
     }
-    int issued = i0;  // next op whose operands have not been requested yet
+    for (int p = i0; p < i1 && p < i0 + STAGES - 1; p++) issue(p);  // the first STAGES - 1 ops are requested up front
     int4 n0 = __ldg(reinterpret_cast<const int4*>(a.ops + i0));
     int4 n1 = __ldg(reinterpret_cast<const int4*>(a.ops + i0) + 1);
     double2 qn1 = __ldg(a.qfac + (size_t)n0.w * SV_KMAX + k);
     double2 qn2 = (n1.y & SV_OP_UNARY) ? make_double2(0.0, 0.0) : __ldg(a.qfac + (size_t)n1.x * SV_KMAX + k);
 
     for (int i = i0; i < i1; i++) {
-        // ops before i are complete (stored, fenced where somebody reads them): request what has become possible
-        while (issued < i1 && issued < i + STAGES && ready_after(issued) < i) {
-            issue(issued);
-            issued++;
-        }
+        // the stage of op i - 1 was released by the __syncwarp of its op: it takes the request for op i + STAGES - 1
+        if (i + STAGES - 1 < i1) issue(i + STAGES - 1);
         const int4 o0 = n0, o1 = n1;
         const double2 q1 = qn1, q2 = qn2;
         if (i + 1 < i1) {
@@ -209,19 +201,27 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS) k_prune_tma(SvPruneArgs a) {
 #pragma unroll
         for (int j = 0; j < NS; j++) {
             if (!(flags & SV_OP_FWD1)) {
-                if (flags & SV_OP_LEAF1) {
-                    sv_lds_slice(base + loff[j], half0, x[j]);
+                if (flags & SV_OP_DEP1) {  // written by an earlier op of this launch: the lane's own load, as in k_prune
+                    const size_t row = (size_t)(unsigned)o0.y + srow[j];
+                    sv_ld256(a.part + row * 16 + k * 4, x[j]);
+                    xs[j] = a.scale[row];
+                } else if (flags & SV_OP_LEAF1) {
+                    sv_lds_slice(base + loff[j], x[j]);
                     xs[j] = 0.0;
                 } else {
-                    sv_lds_slice(base + voff[j], half0, x[j]);
+                    sv_lds_slice(base + voff[j], x[j]);
                     xs[j] = sv_lds64(base + 4096 + soff[j]);
                 }
             }
             if (!unary) {
-                if (flags & SV_OP_LEAF2) {
-                    sv_lds_slice(base + 2048 + loff[j], half0, w[j]);
+                if (flags & SV_OP_DEP2) {
+                    const size_t row = (size_t)(unsigned)o0.z + srow[j];
+                    sv_ld256(a.part + row * 16 + k * 4, w[j]);
+                    ws[j] = a.scale[row];
+                } else if (flags & SV_OP_LEAF2) {
+                    sv_lds_slice(base + 2048 + loff[j], w[j]);
                 } else {
-                    sv_lds_slice(base + 2048 + voff[j], half0, w[j]);
+                    sv_lds_slice(base + 2048 + voff[j], w[j]);
                     ws[j] = sv_lds64(base + 4096 + 128 + soff[j]);
                 }
             }
@@ -256,11 +256,6 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS) k_prune_tma(SvPruneArgs a) {
             const size_t dst_row = dst_base + srow[j];
             sv_st256(a.part + dst_row * 16 + k * 4, x[j]);
             a.scale[dst_row] = xs[j];
-        }
-        if (flags & SV_OP_FENCE) {
-            // a later op of this launch reads what was just stored through the copy engine
-            asm volatile("fence.proxy.async;" ::: "memory");
-            __syncwarp();
         }
         if (flags & SV_OP_ROOT) {
 #pragma unroll

@@ -1132,24 +1132,15 @@ static int sv_flush(sieve_core* h) {
     SV_CUDA(cudaStreamSynchronize(h->stream));  // the previous step may still be reading the staging buffer
     sv_link_forwarding(h->pending_ops, h->pending_per_level);
     if (no) {
-        // dependencies through memory inside the list (prune_tma.cuh): for every op the last earlier op that writes one of
-        // its memory operands, and on that producer the flag that makes it publish its stores to the copy engine
+        // dependencies through memory inside the list (prune_tma.cuh): an operand that an earlier op of the list writes
         std::vector<SvOp>& ops = h->pending_ops;
         std::unordered_map<unsigned, int>& last_writer = h->scratch_writer;
         last_writer.clear();
         for (size_t i = 0; i < no; i++) {
             SvOp& op = ops[i];
-            int r = -1;
-            if (!(op.flags & (SV_OP_LEAF1 | SV_OP_FWD1))) {
-                auto it = last_writer.find(op.c1_row);
-                if (it != last_writer.end()) r = std::max(r, it->second);
-            }
-            if (!(op.flags & (SV_OP_LEAF2 | SV_OP_UNARY))) {
-                auto it = last_writer.find(op.c2_row);
-                if (it != last_writer.end()) r = std::max(r, it->second);
-            }
-            op.pad0 = r;
-            if (r >= 0) ops[r].flags |= SV_OP_FENCE;
+            op.flags &= ~(SV_OP_DEP1 | SV_OP_DEP2);
+            if (!(op.flags & (SV_OP_LEAF1 | SV_OP_FWD1)) && last_writer.count(op.c1_row)) op.flags |= SV_OP_DEP1;
+            if (!(op.flags & (SV_OP_LEAF2 | SV_OP_UNARY)) && last_writer.count(op.c2_row)) op.flags |= SV_OP_DEP2;
             if (!(op.flags & SV_OP_NOSTORE)) last_writer[op.dst_row] = (int)i;
         }
         memcpy(h->h_stage, ops.data(), no * sizeof(SvOp));
