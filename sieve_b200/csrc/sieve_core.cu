@@ -1136,7 +1136,7 @@ static int sv_flush(sieve_core* h) {
         std::vector<SvOp>& ops = h->pending_ops;
         std::unordered_map<unsigned, int>& last_writer = h->scratch_writer;
         last_writer.clear();
-        for (size_t i = 0; i < no; i++) {
+        for (size_t i = 0; h->use_tma && i < no; i++) {  // only the TMA-staged walk looks at these flags
             SvOp& op = ops[i];
             op.flags &= ~(SV_OP_DEP1 | SV_OP_DEP2);
             if (!(op.flags & (SV_OP_LEAF1 | SV_OP_FWD1)) && last_writer.count(op.c1_row)) op.flags |= SV_OP_DEP1;
