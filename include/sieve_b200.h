@@ -202,6 +202,9 @@ int sieve_set_elision(sieve_core_t *h, int32_t on);
  * partials resident; 0 for a dense core) and the slots that are free right now.  Outputs may be NULL. */
 int sieve_sparse_info(sieve_core_t *h, int32_t *pool_slots, int32_t *keep_leaves, int32_t *free_slots);
 int sieve_elided_count(sieve_core_t *h, uint64_t *out); /* dirty nodes not recomputed so far */
+/* Diagnostic: resident blocks per SM (6, 7 or 8) that the single-launch walk over n_sites sites is compiled for -- chosen
+ * per launch from how its blocks of 64 sites divide into waves on the 148 SMs.  No device needed. */
+int sieve_walk_blocks_per_sm(int64_t n_sites);
 
 /* ---- max-sum pass: maximum-likelihood genotypes and dropout states (variant calling) --------------------------------
  * Replaces the traceMLGenotypes arm of the reference for ONE fixed state (tree, matrices, leaf parameters), i.e. what

@@ -75,6 +75,7 @@ SIGNATURES = {
     "sieve_set_elision": (C.c_int, [_vp, C.c_int32]),
     "sieve_sparse_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sieve_elided_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "sieve_walk_blocks_per_sm": (C.c_int, [C.c_int64]),
     "sieve_ml_trace": (C.c_int, [_vp]),
     "sieve_ml_call": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "sieve_ml_get_categories": (C.c_int, [_vp, _vp]),

@@ -918,6 +918,12 @@ static int sv_pick_prune_blocks(unsigned blocks) {
     return best;
 }
 
+extern "C" int sieve_walk_blocks_per_sm(int64_t n_sites) {
+    if (n_sites <= 0) return 6;
+    const int spb = sv_prune_sites(false, true);
+    return sv_pick_prune_blocks((unsigned)((n_sites + spb - 1) / spb));
+}
+
 template <bool QFAST>
 static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
     const bool g0 = a.const_genotype == 0 && a.root_genotype == 0;

@@ -83,3 +83,14 @@ def test_combine_shards_matches_oracle_formulas(L, oracle):
     for mode in ("felsenstein_mean", "felsenstein_geometric", "lewis", "none"):
         ref = ll[0].sum() + oracle.asc_bias(lc[0], None, mode, M)
         assert abs(combine_shards(one, mode, M) - ref) < 1e-9 * abs(ref)
+
+
+def test_walk_block_count_follows_the_wave_model(L):
+    """100 000 sites are 1.76 / 1.51 / 1.32 waves at 6 / 7 / 8 blocks per SM and stay at 6, 125 000 sites are
+    2.20 / 1.89 / 1.65 and go to 7; launches that fit into one wave are never squeezed."""
+    assert L.sieve_walk_blocks_per_sm(100000) == 6
+    assert L.sieve_walk_blocks_per_sm(125000) == 7
+    assert L.sieve_walk_blocks_per_sm(113664) == 6          # exactly two waves at 6
+    for s in (1, 273, 762, 56832):
+        assert L.sieve_walk_blocks_per_sm(s) == 6
+    assert all(L.sieve_walk_blocks_per_sm(s) in (6, 7, 8) for s in range(57000, 2000000, 7919))
