@@ -1,0 +1,156 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the per-pattern sequencing-coverage model of the reference,
+`PrivateAllelicSeqCovModel` (rawreadcountsmodel/seqcovmodel/PrivateAllelicSeqCovModel.java), SURVEY.md section 8 row f-4.
+
+Nothing of the product imports this file, and there is no CUDA counterpart yet: the model makes the leaf likelihoods
+depend on the rate category (one (t, v) pair per (matrix, pattern) instead of one shared pair) and re-estimates the
+pairs from the maximum-likelihood numbers of sequenced alleles after every accepted state.  This module is the first
+step the task prescribes for a new row -- the oracle -- so that the device side can be written against it.
+
+Parity: unpinned like the rest of the floating-point path (no JVM here, the reference holds no vector for this class);
+`tests/test_oracle_private_allelic.py` pins it by independent derivations (sample mean / variance identities, a
+vectorised re-implementation, scipy's negative binomial).
+
+Plain Python / numpy loops in the reference's own operation order; sizes are those of a unit test.
+"""
+import math
+
+import numpy as np
+
+NUMERICAL_STABILIZER = 1e-6   # SeqCovModelInterface.java:218
+
+
+def processed_seq_cov(cov, zero_cov_mode=0):
+    """SeqCovModelInterface.java:296-314: coverage as the model sees it (zeroCovMode 1 adds one to every entry)."""
+    cov = np.asarray(cov, dtype=np.int64)
+    if zero_cov_mode == 0:
+        return cov.copy()
+    if zero_cov_mode == 1:
+        return cov + 1
+    raise ValueError("ERROR! Illegal value for zeroCovMode. Only 0 or 1 is supported.")
+
+
+def seq_cov_mean_var(n_alleles, size_factor, t, v):
+    """PrivateAllelicSeqCovModel.java:505-506 (same as ExploredSharedAllelicSeqCovModel.java:266-277 with the pattern's
+    own t, v): mean and variance of the coverage of a cell with `n_alleles` sequenced alleles."""
+    ka = n_alleles + NUMERICAL_STABILIZER
+    mean = ka * t * size_factor
+    var = mean + math.pow(size_factor, 2) * math.pow(ka, 2) * v
+    return mean, var
+
+
+def seq_cov_log_likelihood_per_allele(cov, n_alleles, size_factor, t, v, nb_log_density):
+    """PrivateAllelicSeqCovModel.java:499-511, log mode.  `nb_log_density(x, r, p)` is the restated
+    math/distributions/NegativeBinomial.java:76-79 (oracle.sieve_oracle.nb_log_density)."""
+    mean, var = seq_cov_mean_var(n_alleles, size_factor, t, v)
+    p = mean / var
+    r = math.pow(mean, 2) / (var - mean)
+    return nb_log_density(cov, r, p)
+
+
+def deterministic_allelic_seq_cov_and_var(processed_cov, size_factors, n_alleles, prev_v=0.0):
+    """PrivateAllelicSeqCovModel.java:458-489 (`computeDeterministicAllelicSeqCovAndVar`), one pattern: every cell has
+    the same, known number of sequenced alleles.  Returns (t, v); v keeps `prev_v` when the moment estimate is not
+    positive (:485-486)."""
+    n = len(size_factors)
+    q = 0.0
+    for j in range(n):
+        q += processed_cov[j] / size_factors[j]
+    q /= n
+    w = z = 0.0
+    if n > 1:
+        for j in range(n):
+            w += math.pow(processed_cov[j] / size_factors[j] - q, 2)
+            z += 1 / size_factors[j]
+        w /= (n - 1)
+        z = w - q * z / n
+    t = q / (n_alleles + NUMERICAL_STABILIZER)
+    v = prev_v
+    if z > 0:
+        v = z / math.pow(n_alleles + NUMERICAL_STABILIZER, 2)
+    return t, v
+
+
+def update_allelic_seq_cov_and_raw_var(processed_cov, size_factors, modeled_alleles, combinations, weights, prev_v):
+    """PrivateAllelicSeqCovModel.java:312-432 (`updateAllelicSeqCovAndRawVar`) for ONE (matrix, pattern) pair.
+
+    processed_cov   [n] coverage of the pattern per cell (processed_seq_cov)
+    size_factors    [n]
+    modeled_alleles sorted numbers of sequenced alleles the evolutionary model allows, e.g. [1, 2]
+    combinations    list of [n] integer arrays: the maximum-likelihood number of sequenced alleles of every cell, one
+                    array per ML genotype combination (MLNrOfSequencedAllelesPatterns)
+    weights         list of ints, how often each combination occurred (MLNrOfSequencedAllelesWeights)
+    prev_v          the raw variance the pair held before: kept when no combination yields a positive estimate (:423-424)
+
+    Returns (t, v).  Quirks kept: a group of cells with a non-positive moment estimate z contributes 0 and does not count
+    (:389-402); the coverage estimate divides by the number of NON-EMPTY groups N[0] (:414), the variance estimate by
+    the number of groups with a positive z, N[1] (:416-419), and only combinations with N[1] > 0 enter its weighted mean.
+    """
+    n = len(size_factors)
+    A = len(modeled_alleles)
+    sum_seq_cov = 0.0
+    sum_seq_cov_var = 0.0
+    sum_weights = [0, 0]
+    for comb, weight in zip(combinations, weights):
+        h = [0] * A
+        indices = [[0] * n for _ in range(A)]
+        N = [0, 0]
+        q = [0.0] * A
+        w = [0.0] * A
+        z = [0.0] * A
+        for j in range(n):
+            idx = modeled_alleles.index(int(comb[j]))     # Arrays.binarySearch on the sorted modeledAlleles (:350)
+            indices[idx][h[idx]] = j
+            h[idx] += 1
+        for a in range(A):
+            if h[a] > 0:
+                N[0] += 1
+                sum_q = 0.0
+                for i in range(h[a]):
+                    j = indices[a][i]
+                    sum_q += processed_cov[j] / size_factors[j]
+                q[a] = sum_q / h[a]
+            if h[a] > 1:
+                N[1] += 1
+                sum_w = 0.0
+                sum_z = 0.0
+                for i in range(h[a]):
+                    j = indices[a][i]
+                    sum_w += math.pow(processed_cov[j] / size_factors[j] - q[a], 2)
+                    sum_z += 1 / size_factors[j]
+                w[a] = sum_w / (h[a] - 1)
+                z[a] = w[a] - q[a] * sum_z / h[a]
+                if z[a] <= 0:
+                    z[a] = 0.0
+                    N[1] -= 1
+        sum_t = 0.0
+        sum_v = 0.0
+        for a in range(A):
+            sum_t += q[a] / (modeled_alleles[a] + NUMERICAL_STABILIZER)
+            sum_v += z[a] / math.pow(modeled_alleles[a] + NUMERICAL_STABILIZER, 2)
+        sum_seq_cov += weight * sum_t / N[0]
+        sum_weights[0] += weight
+        if N[1] > 0:
+            sum_seq_cov_var += weight * sum_v / N[1]
+            sum_weights[1] += weight
+    t = sum_seq_cov / sum_weights[0]
+    v = prev_v
+    if sum_seq_cov_var > 0:
+        v = sum_seq_cov_var / sum_weights[1]
+    return t, v
+
+
+def leaf_seq_cov_log_likelihoods(cov, size_factors, modeled_alleles, t_kp, v_kp, nb_log_density):
+    """PrivateAllelicSeqCovModel.java:272-296 (`computeSeqCovLikelihood`) for all cells of all patterns:
+    out[k][p][cell][a] = log NB(cov[p][cell]; alleles a, t_kp[k][p], v_kp[k][p]) -- the category-dependent coverage term
+    that replaces the shared-model term in the leaf mixture (RawReadCountsModelFiniteMuDM.java:121-260)."""
+    cov = np.asarray(cov)
+    K, P = np.asarray(t_kp).shape
+    n = cov.shape[1]
+    out = np.empty((K, P, n, len(modeled_alleles)))
+    for k in range(K):
+        for p in range(P):
+            for j in range(n):
+                for a, al in enumerate(modeled_alleles):
+                    out[k, p, j, a] = seq_cov_log_likelihood_per_allele(int(cov[p, j]), al, size_factors[j], t_kp[k][p],
+                                                                        v_kp[k][p], nb_log_density)
+    return out
