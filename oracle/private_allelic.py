@@ -154,3 +154,20 @@ def leaf_seq_cov_log_likelihoods(cov, size_factors, modeled_alleles, t_kp, v_kp,
                     out[k, p, j, a] = seq_cov_log_likelihood_per_allele(int(cov[p, j]), al, size_factors[j], t_kp[k][p],
                                                                         v_kp[k][p], nb_log_density)
     return out
+
+
+def leaf_likelihood_private(oracle, counts_s_n_5, taxon, size_factor, params, t_kp, v_kp):
+    """The leaf log-partials of one cell under the private model, [K][S][4]: RawReadCountsModelInterface.java:458-506
+    with `nrOfMatrices = K` -- the nucleotide (Dirichlet-multinomial) terms are those of the shared model, the coverage
+    terms come from the (matrix, pattern) pair's own t, v (PrivateAllelicSeqCovModel.java:272-296), and the dropout
+    mixture (RawReadCountsModelFiniteMuDM.java:121-260) is taken per matrix.  Evaluated with the restated shared-model
+    leaf likelihood, one (matrix, pattern) at a time with that pair's t, v.  `oracle` is the oracle.sieve_oracle module."""
+    t_kp, v_kp = np.asarray(t_kp, dtype=np.float64), np.asarray(v_kp, dtype=np.float64)
+    K, S = t_kp.shape
+    out = np.empty((K, S, 4))
+    for k in range(K):
+        for p in range(S):
+            P = oracle.LeafParams(params.ado_rate, float(t_kp[k, p]), float(v_kp[k, p]), params.eff_seq_err, params.shape1,
+                                  params.shape2, params.single_ado, params.use_log)
+            out[k, p] = oracle.leaf_likelihood(counts_s_n_5, taxon, size_factor, P, p, p + 1)[0]
+    return out

@@ -125,3 +125,27 @@ def test_leaf_terms_depend_on_category_and_pattern():
     assert not np.allclose(out[0], out[1])
     assert pa.processed_seq_cov([0, 3], 1).tolist() == [1, 4] and pa.processed_seq_cov([0, 3], 0).tolist() == [0, 3]
     assert math.isclose(pa.NUMERICAL_STABILIZER, 1e-6)
+
+
+def test_private_leaf_partials_reduce_to_the_shared_model():
+    """With every (matrix, pattern) pair at the shared values the private model's leaf partials are K copies of the
+    shared model's; a pair that differs changes exactly its own (matrix, pattern) rows."""
+    from sieve_b200.data import synthetic
+    d = synthetic(6, 40, seed=4)
+    c5 = so.counts5(d["counts"])
+    sf, _ = so.size_factors(c5)
+    P = so.leaf_params()
+    K, S = 3, 40
+    t = np.full((K, S), P.allelic_cov)
+    v = np.full((K, S), P.allelic_raw_var)
+    shared = so.leaf_likelihood(c5, 2, sf[2], P)
+    got = pa.leaf_likelihood_private(so, c5, 2, sf[2], P, t, v)
+    for k in range(K):
+        np.testing.assert_array_equal(got[k], shared)
+    t[1, 7] *= 1.3
+    v[1, 7] *= 0.6
+    got2 = pa.leaf_likelihood_private(so, c5, 2, sf[2], P, t, v)
+    changed = np.argwhere((got2 != got).any(axis=2))
+    assert changed.tolist() in ([[1, 7]], [])      # (an empty site has no coverage term to change)
+    if d["counts"][7, 2, 3] > 0:
+        assert changed.tolist() == [[1, 7]]
