@@ -100,12 +100,15 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
     la.n_cells = (int)n;
     la.S = (int)S;
     la.C = h->C;
-    // the tables on the device were built with tab_lp: the parameters of the leaves that are current
-    la.al = sv_dm_alphas(h->tab_lp.eff_seq_err_rate, h->tab_lp.shape_ctrl1, h->tab_lp.shape_ctrl2);
-    la.cp.t = h->tab_lp.allelic_seq_cov;
-    la.cp.v = h->tab_lp.allelic_seq_cov_raw_var;
-    la.cp.theta = h->tab_lp.ado_rate;
-    la.cp.single_ado = h->single_ado ? 1 : 0;
+    // the trace belongs to the CURRENT leaf buffer: bring the tables to the parameters that buffer was computed with (after
+    // a rejected proposal they still hold the rejected values; parameters set since, without a leaf update, do not count)
+    {
+        const sieve_leaf_params_t pending = h->lp;
+        h->lp = h->leaf_lp[h->cur_leaf];
+        const int rr = sv_refresh_leaf_tables(h, &la.al, &la.cp);
+        h->lp = pending;
+        SV_TRY(rr);
+    }
     k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
                                                                                                   (int)n, h->C, la.cp);
     sv_count(h);

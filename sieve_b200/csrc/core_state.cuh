@@ -84,6 +84,7 @@ struct sieve_core {
     std::vector<SvOp> pending_ops;
     std::vector<int> pending_levels;  // offsets into pending_ops, empty == one group
     bool pending_per_level = false;
+    std::vector<int> pending_level_triples;  // (parent, child1, child2) of a queued per-level update; ops are made at flush
     std::vector<PendingMatrix> pending_mats;
     std::vector<double> pending_vals;
     int root = -1, root_genotype = 0, const_genotype = 0;
@@ -92,6 +93,7 @@ struct sieve_core {
     bool have_counts = false, have_sf = false, have_params = false, leaves_ready = false;
     bool dm_dirty = true, cov_dirty = true;
     sieve_leaf_params_t tab_lp{};  // parameters the current tables were built with
+    sieve_leaf_params_t leaf_lp[2]{};  // parameters each leaf buffer was computed with (read-backs, store)
 
     // what the last flush staged on the device (for sieve_replay)
     size_t last_no = 0, last_nm = 0, last_nd = 0, last_off_mv = 0, last_off_ms = 0, last_off_dv = 0, last_off_ds = 0;

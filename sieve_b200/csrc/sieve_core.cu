@@ -388,20 +388,25 @@ extern "C" int sieve_set_counts(sieve_core_t* h, const int32_t* counts, int32_t 
     chunk_sites = (chunk_sites + 31) / 32 * 32;
     int* d_in = nullptr;
     int* d_max = nullptr;
-    SV_CUDA(cudaMalloc(&d_in, chunk_sites * n * tuple_len * sizeof(int)));
-    SV_CUDA(cudaMalloc(&d_max, sizeof(int)));
-    SV_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
-    for (size_t s0 = 0; s0 < S; s0 += chunk_sites) {
+    cudaError_t e = cudaMalloc(&d_in, chunk_sites * n * tuple_len * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_max, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(int), h->stream);
+    for (size_t s0 = 0; e == cudaSuccess && s0 < S; s0 += chunk_sites) {
         const size_t ns = std::min(chunk_sites, S - s0);
-        SV_CUDA(cudaMemcpyAsync(d_in, counts + s0 * n * tuple_len, ns * n * tuple_len * sizeof(int),
-                                cudaMemcpyHostToDevice, h->stream));
+        e = cudaMemcpyAsync(d_in, counts + s0 * n * tuple_len, ns * n * tuple_len * sizeof(int), cudaMemcpyHostToDevice,
+                            h->stream);
+        if (e != cudaSuccess) break;
         dim3 g((unsigned)((ns + 31) / 32), (unsigned)((n + 31) / 32)), b(32, 8);
         k_transpose_counts<<<g, b, 0, h->stream>>>(d_in, tuple_len, (int)s0, (int)ns, (int)n, (int)S, h->d_counts, d_max);
         sv_count(h);
-        SV_CUDA(cudaGetLastError());
-        SV_CUDA(cudaStreamSynchronize(h->stream));
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     }
     cudaFree(d_in);
+    if (e != cudaSuccess) {
+        cudaFree(d_max);
+        SV_CUDA(e);
+    }
     return sv_finish_counts(h, d_max);
 }
 
@@ -425,30 +430,37 @@ extern "C" int sieve_set_counts_cellmajor(sieve_core_t* h, const void* counts, i
     SV_CUDA(cudaSetDevice(h->device));
     const size_t N = (size_t)h->n * h->S;
     int* d_max = nullptr;
-    SV_CUDA(cudaMalloc(&d_max, sizeof(int)));
-    SV_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
+    ushort4* d_in = nullptr;
+    cudaError_t e = cudaMalloc(&d_max, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(int), h->stream);
     const size_t chunk = (size_t)16 << 20;  // tuples per chunk
     if (dtype_code == 0) {
-        for (size_t i0 = 0; i0 < N; i0 += chunk) {
+        for (size_t i0 = 0; e == cudaSuccess && i0 < N; i0 += chunk) {
             const size_t m = std::min(chunk, N - i0);
-            SV_CUDA(cudaMemcpyAsync(h->d_counts + i0, (const int4*)counts + i0, m * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-            SV_CUDA(cudaStreamSynchronize(h->stream));
+            e = cudaMemcpyAsync(h->d_counts + i0, (const int4*)counts + i0, m * sizeof(int4), cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
         }
-        k_max_cov<<<592, 256, 0, h->stream>>>(h->d_counts, N, d_max);
-        sv_count(h);
+        if (e == cudaSuccess) {
+            k_max_cov<<<592, 256, 0, h->stream>>>(h->d_counts, N, d_max);
+            sv_count(h);
+        }
     } else {
-        ushort4* d_in = nullptr;
-        SV_CUDA(cudaMalloc(&d_in, chunk * sizeof(ushort4)));
-        for (size_t i0 = 0; i0 < N; i0 += chunk) {
+        if (e == cudaSuccess) e = cudaMalloc(&d_in, chunk * sizeof(ushort4));
+        for (size_t i0 = 0; e == cudaSuccess && i0 < N; i0 += chunk) {
             const size_t m = std::min(chunk, N - i0);
-            SV_CUDA(cudaMemcpyAsync(d_in, (const ushort4*)counts + i0, m * sizeof(ushort4), cudaMemcpyHostToDevice, h->stream));
+            e = cudaMemcpyAsync(d_in, (const ushort4*)counts + i0, m * sizeof(ushort4), cudaMemcpyHostToDevice, h->stream);
+            if (e != cudaSuccess) break;
             k_widen_counts_u16<<<592, 256, 0, h->stream>>>(d_in, m, h->d_counts + i0, d_max);
             sv_count(h);
-            SV_CUDA(cudaStreamSynchronize(h->stream));
+            e = cudaStreamSynchronize(h->stream);
         }
         cudaFree(d_in);
     }
-    SV_CUDA(cudaGetLastError());
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFree(d_max);
+        SV_CUDA(e);
+    }
     return sv_finish_counts(h, d_max);
 }
 
@@ -644,9 +656,15 @@ static int sv_subtree_leaf_sums(sieve_core* h, int node, double* d_ls, double* d
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_list, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, h->stream);
     int r = SIEVE_OK;
-    if (e == cudaSuccess)
+    if (e == cudaSuccess) {
+        // the sums must belong to the leaf buffer that is read back: evaluate them with the parameters THAT buffer was
+        // computed with, not with parameters set since (sieve_set_leaf_params without sieve_update_leaves)
+        const sieve_leaf_params_t pending = h->lp;
+        h->lp = h->leaf_lp[h->cur_leaf];
         r = sv_launch_leaf_kernels(h, 0, (int)S, (long long)S, nullptr, d_list, (int)leaves.size(), d_sums,
                                    d_sums + groups * S, (long long)S, d_ls, d_lam);
+        h->lp = pending;
+    }
     if (e == cudaSuccess && r == SIEVE_OK) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_list);
     cudaFree(d_sums);
@@ -664,6 +682,7 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
         // streamed mode: the leaves are recomputed chunk by chunk inside every evaluation; nothing to do now
         h->leaves_ready = true;
         h->eph_leaves_dirty = true;
+        h->leaf_lp[0] = h->leaf_lp[1] = h->lp;
         return SIEVE_OK;
     }
     if (for_update && !h->single_leaf) h->cur_leaf = 1 - h->cur_leaf;
@@ -675,6 +694,8 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
         SV_CUDA(cudaEventRecord(h->ev[0], h->stream));
     }
     SV_TRY(sv_launch_leaves(h, 0, h->S, h->S));
+    h->leaf_lp[h->cur_leaf] = h->lp;
+    if (!for_update) h->leaf_lp[1 - h->cur_leaf] = h->lp;
     if (h->timing) {
         SV_CUDA(cudaEventRecord(h->ev[1], h->stream));
         h->leaf_timed = true;
@@ -771,9 +792,9 @@ extern "C" int sieve_set_node_matrix(sieve_core_t* h, int32_t node, int32_t cate
 extern "C" int sieve_set_matrices(sieve_core_t* h, int32_t count, const int32_t* nodes, const double* P, int32_t for_update) {
     SV_REQUIRE(h && count >= 0 && (count == 0 || (nodes && P)), "sieve_set_matrices: bad argument");
     const int K = h->K;
+    for (int i = 0; i < count; i++) SV_REQUIRE(sv_node_ok(h, nodes[i]), "sieve_set_matrices: bad node");
     h->pending_mats.reserve(h->pending_mats.size() + count);
     for (int i = 0; i < count; i++) {
-        SV_REQUIRE(sv_node_ok(h, nodes[i]), "sieve_set_matrices: bad node");
         if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
         PendingMatrix pm;
         pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
@@ -789,12 +810,15 @@ extern "C" int sieve_set_distances(sieve_core_t* h, int32_t count, const int32_t
                                    int32_t for_update) {
     SV_REQUIRE(h && count >= 0 && (count == 0 || (nodes && distances)), "sieve_set_distances: bad argument");
     const int K = h->K;
-    h->pending_mats.reserve(h->pending_mats.size() + count);
+    // every input is checked before any buffer index or queue is touched: a rejected call leaves the handle as it was
     for (int i = 0; i < count; i++) {
         SV_REQUIRE(sv_node_ok(h, nodes[i]), "sieve_set_distances: bad node");
-        if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
         for (int k = 0; k < K; k++)
             if (!(distances[(size_t)i * K + k] >= 0.0)) return sv_fail(SIEVE_ERR_INVALID, "sieve_set_distances: negative distance");
+    }
+    h->pending_mats.reserve(h->pending_mats.size() + count);
+    for (int i = 0; i < count; i++) {
+        if (for_update) h->cur_mat[nodes[i]] = 1 - h->cur_mat[nodes[i]];
         PendingMatrix pm;
         pm.slot = h->cur_mat[nodes[i]] * h->n_nodes + nodes[i];
         pm.is_distance = 1;
@@ -842,7 +866,7 @@ extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t*
     const bool per_level = (mode & SIEVE_UPDATE_PER_LEVEL) && level_offsets && n_levels > 0;
     if (per_level && h->sparse) return sv_fail(SIEVE_ERR_STATE, "sieve_update_nodes: the per-level schedule needs a dense core");
     if (per_level) {
-        SV_REQUIRE(h->pending_ops.empty(), "sieve_update_nodes: per-level update with other ops pending");
+        SV_REQUIRE(h->pending_ops.empty() && !h->pending_per_level, "sieve_update_nodes: per-level update with other ops pending");
         SV_REQUIRE(level_offsets[0] == 0 && level_offsets[n_levels] == n_ops, "sieve_update_nodes: bad level offsets");
     }
     if (mode & SIEVE_UPDATE_FLIP)
@@ -858,22 +882,23 @@ extern "C" int sieve_update_nodes(sieve_core_t* h, int32_t n_ops, const int32_t*
         for (int i = 0; i < n_ops; i++) h->dirty_list.push_back(ops[3 * i]);
         return SIEVE_OK;
     }
-    // level-batched schedule: the caller's order and grouping are kept, every result is stored
+    // level-batched schedule: the caller's order and grouping are kept, every result is stored.  Only the (parent, child1,
+    // child2) triples are queued here: the ops themselves are made by sv_flush AFTER its matrix pass, because that pass
+    // may still retarget a node's matrix buffer (change tracking) and decides the zero-distance flags the ops carry.
     SV_REQUIRE(h->dirty_list.empty(), "sieve_update_nodes: per-level update with other ops pending");
-    h->pending_ops.reserve(h->pending_ops.size() + n_ops);
+    h->pending_level_triples.assign(ops, ops + (size_t)3 * n_ops);
     for (int i = 0; i < n_ops; i++) {
-        SvOp op;
-        SV_TRY(sv_make_op(h, ops[3 * i + 1], ops[3 * i + 2], ops[3 * i], &op));
-        h->pending_ops.push_back(op);
-        h->g_nodes.push_back(ops[3 * i]);
-        h->valid[ops[3 * i]] = 1;
-        h->ver_cur[ops[3 * i]] = ++h->ver_counter;  // computed outside the planner: a new value of unknown provenance
-        h->fp_cur[ops[3 * i]] = sieve_core::SvFp();
-        h->prov_touched.push_back(ops[3 * i]);
+        const int p = ops[3 * i];
+        SV_REQUIRE(p >= h->n && p < h->n_nodes, "sieve_update_nodes: parent must be an internal node");
+        h->g_nodes.push_back(p);
+        h->valid[p] = 1;
+        h->ver_cur[p] = ++h->ver_counter;  // computed outside the planner: a new value of unknown provenance
+        h->fp_cur[p] = sieve_core::SvFp();
+        h->prov_touched.push_back(p);
         {
-            const size_t bi = (size_t)h->cur_part[ops[3 * i]] * h->n_nodes + ops[3 * i];
+            const size_t bi = (size_t)h->cur_part[p] * h->n_nodes + p;
             h->buf_has[bi] = 1;
-            h->buf_ver[bi] = h->ver_cur[ops[3 * i]];
+            h->buf_ver[bi] = h->ver_cur[p];
             h->buf_fp[bi] = sieve_core::SvFp();
         }
     }
@@ -1115,7 +1140,17 @@ static int sv_flush(sieve_core* h) {
     }
     if (h->ephemeral)
         SV_TRY(sv_build_streamed_ops(h));
-    else if (!h->dirty_list.empty() || !h->demand_list.empty())
+    else if (h->pending_per_level) {
+        // the level-batched schedule's ops, made now that every node points at the matrix buffer it will be read from
+        const std::vector<int>& t = h->pending_level_triples;
+        h->pending_ops.reserve(t.size() / 3);
+        for (size_t i = 0; i + 2 < t.size(); i += 3) {
+            SvOp op;
+            SV_TRY(sv_make_op(h, t[i + 1], t[i + 2], t[i], &op));
+            h->pending_ops.push_back(op);
+        }
+        h->pending_level_triples.clear();
+    } else if (!h->dirty_list.empty() || !h->demand_list.empty())
         SV_TRY(sv_plan_resident_ops(h));
     const size_t no = h->pending_ops.size();
     size_t nm = 0, nd = 0;
@@ -1297,7 +1332,7 @@ extern "C" int sieve_last_stage_bytes(sieve_core_t* h, uint64_t* out) {
 extern "C" int sieve_replay(sieve_core_t* h, int32_t update_leaves, int32_t n_times) {
     SV_REQUIRE(h && n_times >= 0, "sieve_replay: bad argument");
     SV_CUDA(cudaSetDevice(h->device));
-    if (!h->pending_ops.empty() || !h->pending_mats.empty())
+    if (!h->pending_ops.empty() || !h->pending_mats.empty() || h->pending_per_level || !h->dirty_list.empty())
         return sv_fail(SIEVE_ERR_STATE, "sieve_replay: there is un-launched work queued");
     if (h->last_no == 0) return sv_fail(SIEVE_ERR_STATE, "sieve_replay: nothing was staged yet");
     const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
@@ -1417,7 +1452,7 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->stored_part = h->cur_part;
     h->stored_mat = h->cur_mat;
     h->stored_leaf = h->cur_leaf;
-    h->stored_lp = h->tab_lp;  // the parameters the current leaves were computed with
+    h->stored_lp = h->leaf_lp[h->cur_leaf];  // the parameters the current leaves were computed with
     h->leaf_ver_stored = h->leaf_ver[h->cur_leaf];
     h->leaf_changed_since_store = false;
     h->eph_c1_stored = h->eph_c1;
@@ -1441,6 +1476,7 @@ static int sv_leaves_back_to_stored(sieve_core* h) {
     SV_CUDA(cudaSetDevice(h->device));
     h->lp = h->stored_lp;  // the state's parameters are the stored ones again
     SV_TRY(sv_launch_leaves(h, 0, h->S, h->S));
+    h->leaf_lp[h->cur_leaf] = h->stored_lp;
     h->leaf_ver[h->cur_leaf] = h->leaf_ver_stored;  // same parameters, same kernel: the same bits as before the proposal
     h->leaf_changed_since_store = false;
     return SIEVE_OK;

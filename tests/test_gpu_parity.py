@@ -98,16 +98,17 @@ def test_full_evaluation_matches_oracle(core_mod, oracle, asc, use_log, single, 
     c.update_nodes(tree.ops(), flip=False)
     r = c.evaluate()
     sl, sc = c.site_log_likelihoods()
-    logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, asc, M, single=single, use_log=True)
+    # the oracle in the SAME mode: log-space pruning (ScsBeerLikelihoodCore.java:1384-1501) or its linear twin (:958-1055)
+    logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, asc, M, single=single, use_log=use_log)
     _close(sl, osl, SITE_RTOL)
     if asc != "none":
         _close(sc, osc, SITE_RTOL)
     got = core_mod.combine_shards([r], asc, M)
     assert abs(got - logp) <= TOTAL_RTOL * abs(logp)
-    # every internal node's partials, reference layout, log space
-    if use_log:
-        P = oracle.leaf_params(*PARAMS, single_ado=single)
-        oc = oracle.Core(tree.node_count, tree.n, 700, K, 4, True)
+    # every internal node's partials, reference layout: logs in log mode, plain likelihoods in linear mode
+    if True:
+        P = oracle.leaf_params(*PARAMS, single_ado=single, use_log=use_log)
+        oc = oracle.Core(tree.node_count, tree.n, 700, K, 4, use_log)
         c5 = oracle.counts5(counts)
         for i in range(tree.n):
             oc.set_node_partials(i, oracle.leaf_likelihood(c5, i, sf[i], P))
@@ -117,12 +118,77 @@ def test_full_evaluation_matches_oracle(core_mod, oracle, asc, use_log, single, 
                     oc.set_node_matrix(node, k, mats[node, k])
         for p, c1, c2 in tree.ops():
             oc.calculate_partials(c1, c1 < tree.n, c2, 0 <= c2 < tree.n, p, 0)
+        atol = 1e-11 if use_log else 0.0
         for node in (tree.n, tree.n + 7, tree.root - 1, tree.root):
-            np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=1e-11)
+            np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=atol)
             if asc != "none":
                 np.testing.assert_allclose(c.get_node_partials(node, const=True), oc.get_const_partials(node),
-                                           rtol=2e-12, atol=1e-11)
+                                           rtol=2e-12, atol=atol)
     c.close()
+
+
+def test_linear_partials_specific_behaviour(core_mod, oracle):
+    """useLogPartials = false (ScsBeerLikelihoodCore.java:857-1055), the cases where it differs from the log-space core:
+
+    * a zero-length branch: the linear twin multiplies by the plain matrix, there is no Double.MIN_VALUE clamp of P
+      (:1430 belongs to the log-space core only), so P = I passes the child's partial through unchanged;
+    * a constant-site product that is exactly 0: the leaf likelihood of the constant genotype underflows in the
+      reference's unscaled linear arithmetic, `cst1 * cst2 > 0 ? ... : Double.MIN_VALUE` (:1041-1047) fires and the site's
+      logConstRoot ends at log(Double.MIN_VALUE)-ish or -inf.  The device arithmetic is always scaled and keeps the true
+      value (documented deviation): the site contributes exp(.) = 0 to the Felsenstein sum either way,
+      so the totals agree; only the read-back of that site's logConstRoot differs.
+    """
+    d = synthetic(19, 300, seed=77, max_cov=200)
+    counts, tree = d["counts"].copy(), d["tree"]
+    tree.height[4] = tree.height[tree.parent[4]]             # zero-length branch above leaf 4
+    # site 11: the cell with the largest size factor has 1 500 reads, all of them the first alternative nucleotide: its
+    # genotype 0/0 log-likelihood is about -790 (exp underflows to 0), the other genotypes about -290 (representable)
+    sf0, _ = oracle.size_factors(oracle.counts5(counts))
+    counts[11, int(np.argmax(sf0))] = (1500, 0, 0, 1500)
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    assert np.array_equal(mats[4, 0].reshape(4, 4), np.eye(4))
+    M = 3000.0
+    c = _setup(core_mod, counts, tree, sf, PARAMS, mats, props, asc=True, use_log=False)
+    c.update_nodes(tree.ops(), flip=False)
+    r = c.evaluate()
+    sl, sc = c.site_log_likelihoods()
+    logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, "felsenstein_mean", M, use_log=False)
+    assert np.isfinite(osl).all()
+    _close(sl, osl, SITE_RTOL)
+    ok = np.ones(300, dtype=bool)
+    ok[11] = False
+    _close(sc[ok], osc[ok], SITE_RTOL)
+    # the reference's linear core lost site 11's constant-site likelihood to underflow; the device keeps it
+    assert osc[11] < -700.0 or np.isneginf(osc[11])
+    assert np.isfinite(sc[11]) and sc[11] < -745.0
+    got = core_mod.combine_shards([r], "felsenstein_mean", M)
+    assert abs(got - logp) <= TOTAL_RTOL * abs(logp)
+    # parent of the zero-length branch: linear partials against the oracle's linear core
+    P = oracle.leaf_params(*PARAMS, use_log=False)
+    oc = oracle.Core(tree.node_count, tree.n, 300, 4, 4, False)
+    c5 = oracle.counts5(counts)
+    for i in range(tree.n):
+        oc.set_node_partials(i, oracle.leaf_likelihood(c5, i, sf[i], P))
+    for node in range(tree.node_count):
+        if node != tree.root:
+            for k in range(4):
+                oc.set_node_matrix(node, k, mats[node, k])
+    for p, c1, c2 in tree.ops():
+        oc.calculate_partials(c1, c1 < tree.n, c2, 0 <= c2 < tree.n, p, 0)
+    for node in (int(tree.parent[4]), tree.root):
+        np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=0.0)
+    # and the same zero-length branch through the distance fast path (no clamp either in linear mode)
+    c2_ = _setup(core_mod, counts, tree, sf, PARAMS, mats, props, asc=True, use_log=False)
+    nodes = np.array([i for i in range(tree.node_count) if i != tree.root], dtype=np.int32)
+    c2_.set_distances(nodes, substmodel.node_distances(tree, rates)[nodes], for_update=False)
+    c2_.update_nodes(tree.ops(), flip=False)
+    c2_.evaluate()
+    sl2, _ = c2_.site_log_likelihoods()
+    _close(sl2, osl, SITE_RTOL)
+    c.close()
+    c2_.close()
 
 
 def test_leaf_scale_sums_over_cell_groups_and_site_blocks(core_mod, oracle, monkeypatch):
@@ -293,6 +359,59 @@ def test_per_level_launches_equal_single_walk(core_mod, oracle):
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
     np.testing.assert_array_equal(out[0][2], out[1][2])
     np.testing.assert_array_equal(out[0][3], out[1][3])
+
+
+@pytest.mark.parametrize("use_distances", [True, False])
+def test_per_level_steps_with_unchanged_matrices_and_change_tracking(core_mod, oracle, use_distances):
+    """Regression (round-1 advisor finding): consecutive per-level steps that flip the matrix buffers and hand in the SAME
+    values.  Change tracking points the node back at the buffer that already holds them -- the per-level ops must be made
+    after that decision, or they read the slot that never received the data.  Bit-for-bit against the single-launch walk,
+    with one branch of exactly zero length so that the zero-distance flag of the ops is exercised too."""
+    d = synthetic(37, 411, seed=21)
+    counts, tree = d["counts"], d["tree"]
+    leaf = 5
+    tree.height[leaf] = tree.height[tree.parent[leaf]]   # a zero-length branch (a cell sampled at its parent's height)
+    assert tree.branch_lengths()[leaf] == 0.0
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    rates, props = substmodel.gamma_category_rates(1.0, 4)
+    mats = substmodel.node_matrices(tree, rates)
+    nodes = np.array([i for i in range(tree.node_count) if i != tree.root], dtype=np.int32)
+    D = substmodel.node_distances(tree, rates)[nodes]
+    D2 = D.copy()
+    D2[3] *= 1.25                                          # third step: one branch really changes
+    mats2 = mats.copy()
+    for k in range(4):
+        mats2[nodes[3], k] = substmodel.transition_probabilities(D2[3, k]).reshape(16)
+    lvl_ops, lvl_off = tree.ops_by_level()
+    out = {}
+    for per_level in (False, True):
+        c = _setup(core_mod, counts, tree, sf, PARAMS, mats, props, asc=True)
+        c.set_elision(True)
+        res = []
+        for step in range(4):
+            Dn, Mn = (D2, mats2) if step == 2 else (D, mats)
+            if use_distances:
+                c.set_distances(nodes, Dn, for_update=True)
+            else:
+                c.set_matrices(nodes, Mn[nodes], for_update=True)
+            if per_level:
+                c.update_nodes(lvl_ops, lvl_off, flip=True, per_level=True)
+            else:
+                c.update_nodes(tree.ops(), flip=True)
+            r = c.evaluate()
+            res.append((r.sum_log_l, r.const_lse) + c.site_log_likelihoods())
+        out[per_level] = res
+        c.close()
+    for step in range(4):
+        a, b = out[False][step], out[True][step]
+        assert np.isfinite(a[0]) and a[0] == b[0] and a[1] == b[1], (step, a[0], b[0])
+        np.testing.assert_array_equal(a[2], b[2])
+        np.testing.assert_array_equal(a[3], b[3])
+    # steps 0, 1 and 3 evaluate the same state; the oracle agrees
+    assert out[True][0][0] == out[True][1][0] == out[True][3][0] != out[True][2][0]
+    _, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, "felsenstein_mean", 100.0)
+    _close(out[True][3][2], osl, SITE_RTOL)
+    _close(out[True][3][3], osc, SITE_RTOL)
 
 
 def test_reference_call_sequence_and_store_restore(core_mod, oracle):
