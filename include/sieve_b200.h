@@ -53,6 +53,11 @@ enum {
 #define SIEVE_FLAG_SINGLE_LEAF_BUFFER 32u /* one leaf buffer instead of two (32 B per cell and site saved): a rejected         \
                                         leaf-parameter proposal is undone by recomputing the leaves in sieve_restore */
 
+#define SIEVE_FLAG_EXTERNAL_COUNTS 64u /* the count tensor stays in caller-owned device memory: sieve_create allocates none, \
+                                        sieve_set_counts_device adopts the pointer instead of copying (it must stay valid   \
+                                        until sieve_destroy).  Saves 16 B per cell and site when the producer of the counts \
+                                        (an ingest kernel, a generator) already wrote the core's layout */
+
 typedef struct {
     int32_t n_leaves;     /* cells (taxa) */
     int32_t n_sites;      /* patterns of this shard */
@@ -120,6 +125,45 @@ int sieve_set_pattern_weights(sieve_core_t *h, const int32_t *weights);
  * out_size_factors[n_leaves]; out_stats[2] = {mean(cov)/2, var(cov)/4} (the start values of :322-325), may be NULL. */
 int sieve_compute_size_factors(sieve_core_t *h, int32_t zero_cov_mode, double *out_size_factors, double *out_stats);
 int sieve_set_size_factors(sieve_core_t *h, const double *size_factors);
+
+/* ---- size factors over a SITE-SHARDED alignment --------------------------------------------------------------------
+ * likelihood/ThreadedScsTreeLikelihood.java:119-131 initialises the coverage model on the FULL alignment before it splits
+ * the sites, so that every worker uses the same, global size factors (ExploredSharedAllelicSeqCovModel.java:103-109).
+ * With one GPU per site range no device holds the full alignment; the per-cell median of seqcovmodel/
+ * SeqCovModelInterface.java:291-351 is then found by exact distributed selection (csrc/sizefactors_global.cuh): per
+ * round every part counts, per cell, the weight of its coverage ratios below a pivot, the counts are summed over the
+ * parts (integers: the split cannot change the result), 63 rounds of bisection on the ratio's bit pattern.  The result is
+ * bit-identical to sieve_compute_size_factors on one handle that holds all sites.
+ *
+ * A part borrows a device-resident count tensor int32 [cell][site][4] (the core's own layout); it needs no core and no
+ * pools.  weights: host int32 [n_sites] or NULL (all 1).  */
+typedef struct sieve_sf sieve_sf_t;
+int sieve_sf_open(int32_t device, int32_t n_cells, int32_t n_sites, const void *d_counts_cell_site_4,
+                  const int32_t *weights, int32_t zero_cov_mode, sieve_sf_t **out);
+/* a part over the counts and pattern weights a handle already holds */
+int sieve_sf_open_core(sieve_core_t *h, int32_t zero_cov_mode, sieve_sf_t **out);
+int sieve_sf_close(sieve_sf_t *p);
+/* the two local primitives of the protocol: {sum cov, sum cov^2, number of entries} of this part; and, per cell and
+ * pivot (n_piv = 1 or 2 pivots per cell, bit patterns of doubles), the weight of the kept ratios <= the pivot */
+int sieve_sf_moments(sieve_sf_t *p, uint64_t *out3);
+int sieve_sf_weight_le(sieve_sf_t *p, int32_t n_piv, const uint64_t *pivots, int64_t *out);
+/* sum over all processes, in place; 0 = ok */
+typedef int (*sieve_sf_allreduce_fn)(void *user, int64_t *buf, int32_t count);
+/* The protocol itself is host logic over callbacks (no device needed: CPU tests drive it with stand-in primitives).
+ * moments / weight_le answer for everything THIS process holds; allreduce_sum_i64 sums over processes (NULL: one). */
+typedef struct {
+    void *user;
+    int32_t n_cells;
+    int (*moments)(void *user, uint64_t *out3);
+    int (*weight_le)(void *user, int32_t n_piv, const uint64_t *pivots, int64_t *out);
+    sieve_sf_allreduce_fn allreduce_sum_i64;
+} sieve_sf_ops_t;
+/* out_size_factors [n_cells]; out_stats[2] = {mean(cov) / 2, var(cov) / 4} (may be NULL) */
+int sieve_sf_solve(const sieve_sf_ops_t *ops, double *out_size_factors, double *out_stats);
+/* the usual wiring: the parts this process drives (one per GPU; the JVM drives all of them) + an optional all-reduce
+ * across processes (one process per GPU: torch.distributed / MPI / NCCL behind the callback; NULL for one process) */
+int sieve_sf_solve_parts(int32_t n_parts, sieve_sf_t *const *parts, sieve_sf_allreduce_fn allreduce, void *user,
+                         double *out_size_factors, double *out_stats);
 
 /* new values of the six leaf-model parameters; takes effect at the next sieve_update_leaves */
 int sieve_set_leaf_params(sieve_core_t *h, const sieve_leaf_params_t *p);

@@ -94,6 +94,15 @@ int sieve_mcmc_full_recompute(sieve_mcmc_t *m, double *log_p);
 /* discrete gamma category rates as ScsSiteModel yields them (BEAST1-style medians, mean 1); rates_out[k] */
 int sieve_gamma_category_rates(double shape, int32_t k, double *rates_out);
 
+/* The reference's own traverse sequence for a whole-tree update, issued call by call through the C-ABI the way the JNI
+ * shim forwards it when only the core behind the LikelihoodCore seam is swapped (likelihood/ScsTreeLikelihood.java:563-601,
+ * 621-628, 745-752, 854-861, 888-920, 2621-2651): per non-root node setNodeMatrixForUpdate + K x setNodeMatrix, (leaves),
+ * per internal node setNodePartialsForUpdate + calculateLogPartials, evaluation, getPatternLogLikelihoods.
+ * ops_post_order [n_ops][3] = (parent, child1, child2 | -1); P [n_nodes][K][16]; site_log_l [S] or NULL. */
+int sieve_traverse_full(sieve_core_t *h, int32_t n_nodes, int32_t n_categories, int32_t root, int32_t n_ops,
+                        const int32_t *ops_post_order, const double *P, int32_t update_leaves, double *site_log_l,
+                        sieve_shard_result_t *out);
+
 #ifdef __cplusplus
 }
 #endif

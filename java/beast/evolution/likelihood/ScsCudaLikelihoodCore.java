@@ -8,13 +8,26 @@ package beast.evolution.likelihood;
  * store / restore logic of the reference run unchanged.  Two differences a maintainer has to wire (INTEGRATION.md):
  *   - leaves are computed on the device: setNodePartials(leaf, ...) is replaced by updateLeaves();
  *   - calculateLogPartials only queues; integratePartials + calculateLogLikelihoods trigger the single launch.
- * NOT COMPILED IN THIS REPOSITORY'S CI (no JDK in the build image).
+ * Not compiled in this repository's CI (no JDK in the build image); the JNI glue below it is syntax- and symbol-checked.
  */
 public class ScsCudaLikelihoodCore extends ScsBeerLikelihoodCore {
     private long h;
     private int patternCount;
     private final double[] result = new double[5];
     private boolean evaluated;
+    private boolean singleADO = true, ascBias = true, singleLeafBuffer = false;
+
+    /**
+     * The model switches the device needs, read where ScsTreeLikelihood.initAndValidate has them (before initCore):
+     * singleADO from the raw-read-counts model (rawreadcountsmodel/RawReadCountsModelInterface.java:50-54, 178-181; an XML
+     * input, default true) and whether the alignment asks for acquisition-bias correction
+     * (alignment/ScsAlignment.java:697-699 isAscBiasCorrection): without it no constant-site work is done at all.
+     */
+    public void configure(boolean singleADO, boolean ascBiasCorrection) {
+        this.singleADO = singleADO;
+        this.ascBias = ascBiasCorrection;
+        this.singleLeafBuffer = Boolean.getBoolean("sieve.b200.singleLeafBuffer");
+    }
 
     public ScsCudaLikelihoodCore(int nrOfStates) {
         super(nrOfStates);
@@ -25,8 +38,9 @@ public class ScsCudaLikelihoodCore extends ScsBeerLikelihoodCore {
     public void initialize(int nodeCount, int leafNodeCount, int internalNodeCount, int patternCount, int matrixCount,
                            int stateCount, boolean integrateCategories, boolean useLogPartials) {
         this.patternCount = patternCount;
-        int flags = (useLogPartials ? SieveB200.FLAG_LOG_PARTIALS : 0) | SieveB200.FLAG_CONST_PARTIALS
-                | SieveB200.FLAG_SINGLE_ADO
+        int flags = (useLogPartials ? SieveB200.FLAG_LOG_PARTIALS : 0) | (ascBias ? SieveB200.FLAG_CONST_PARTIALS : 0)
+                | (singleADO ? SieveB200.FLAG_SINGLE_ADO : 0)
+                | (singleLeafBuffer ? SieveB200.FLAG_SINGLE_LEAF_BUFFER : 0)
                 | (Boolean.getBoolean("sieve.b200.sparse") ? SieveB200.FLAG_SPARSE : 0)        // 10 000-cell data sets
                 | (Boolean.getBoolean("sieve.b200.streamed") ? SieveB200.FLAG_EPHEMERAL : 0);  // beyond that
         h = SieveB200.create(leafNodeCount, patternCount, matrixCount, stateCount, flags,

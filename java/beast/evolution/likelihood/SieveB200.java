@@ -3,7 +3,8 @@ package beast.evolution.likelihood;
 /**
  * Native entry points of libsieve_b200.so (include/sieve_b200.h), one static method per C function.
  * The JNI glue (java/jni/sieve_jni.c) pins the Java arrays and forwards; it contains no logic.
- * NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no JDK (SURVEY.md section 0).
+ * The build image has no JDK (SURVEY.md section 0): tests/test_jni_shim_cpu.py compiles the glue against a minimal jni.h and
+ * checks that every native method below has its Java_..._SieveB200_* export (and vice versa).
  */
 public final class SieveB200 {
     static {
@@ -12,7 +13,8 @@ public final class SieveB200 {
 
     private SieveB200() {}
 
-    public static final int FLAG_LOG_PARTIALS = 1, FLAG_CONST_PARTIALS = 2, FLAG_SINGLE_ADO = 4, FLAG_EPHEMERAL = 8, FLAG_SPARSE = 16;
+    public static final int FLAG_LOG_PARTIALS = 1, FLAG_CONST_PARTIALS = 2, FLAG_SINGLE_ADO = 4, FLAG_EPHEMERAL = 8, FLAG_SPARSE = 16,
+            FLAG_SINGLE_LEAF_BUFFER = 32, FLAG_EXTERNAL_COUNTS = 64;
     public static final int UPDATE_FLIP = 1, UPDATE_PER_LEVEL = 2;
 
     /** sieve_create; returns the opaque handle; throws RuntimeException(sieve_last_error()) on failure */
@@ -45,6 +47,12 @@ public final class SieveB200 {
     public static native void store(long h);
     public static native void unstore(long h);
     public static native void restore(long h);
+    /** sieve_step_distances: one call per MCMC state (distances of the changed branches + dirty ops [n][3] flattened) */
+    public static native void stepDistances(long h, boolean updateLeaves, int[] nodes, double[] distances, int[] ops, double[] out5);
+    /** global size factors over the workers' site ranges without a device that holds the full alignment (sieve_sf_*) */
+    public static native long sfOpenCore(long h, int zeroCovMode);
+    public static native void sfClose(long part);
+    public static native void sfSolveParts(long[] parts, double[] outSizeFactors, double[] outStats);
     /** shards: nShards x 5 doubles in worker order; ascMode 0 none, 1 felsenstein/mean, 2 felsenstein/geometric, 3 lewis */
     public static native double combineShards(double[] shards, int nShards, int ascMode, double nBackgroundSites);
 }

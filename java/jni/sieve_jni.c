@@ -1,11 +1,15 @@
 /* JNI glue for java/beast/evolution/likelihood/SieveB200.java: pins the arrays, forwards to include/sieve_b200.h,
  * turns a non-zero status into a RuntimeException carrying sieve_last_error().  No logic lives here.
+ * tests/test_jni_shim_cpu.py compiles this file against a minimal jni.h (tests/jni_stub) with -Wall -Wextra -Werror and checks
+ * the exports against SieveB200.java's native methods.
  * Build (needs a JDK, absent from this repository's image):
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -I../../include sieve_jni.c \
  *       -L../../sieve_b200 -lsieve_b200 -o libsieve_b200_jni.so
  */
 #ifdef SIEVE_HAVE_JNI
 #include <jni.h>
+#include <stddef.h>
+#include <stdint.h>
 #include "sieve_b200.h"
 
 #define H(h) ((sieve_core_t *)(intptr_t)(h))
@@ -131,5 +135,44 @@ JNIEXPORT jdouble JNICALL FN(combineShards)(JNIEnv *e, jclass c, jdoubleArray a,
     double r = sieve_combine_shards((const sieve_shard_result_t *)p, n, mode, M);
     (*e)->ReleasePrimitiveArrayCritical(e, a, p, JNI_ABORT);
     return r;
+}
+JNIEXPORT void JNICALL FN(stepDistances)(JNIEnv *e, jclass c, jlong h, jboolean leaves, jintArray nodes, jdoubleArray d,
+                                         jintArray ops, jdoubleArray out5) {
+    const jsize nn = (*e)->GetArrayLength(e, nodes), no = (*e)->GetArrayLength(e, ops) / 3;
+    jint *pn = (*e)->GetPrimitiveArrayCritical(e, nodes, NULL);
+    jdouble *pd = (*e)->GetPrimitiveArrayCritical(e, d, NULL);
+    jint *po = (*e)->GetPrimitiveArrayCritical(e, ops, NULL);
+    sieve_shard_result_t r;
+    int rc = sieve_step_distances(H(h), leaves, nn, (const int32_t *)pn, pd, no, (const int32_t *)po, &r);
+    (*e)->ReleasePrimitiveArrayCritical(e, ops, po, JNI_ABORT);
+    (*e)->ReleasePrimitiveArrayCritical(e, d, pd, JNI_ABORT);
+    (*e)->ReleasePrimitiveArrayCritical(e, nodes, pn, JNI_ABORT);
+    if (rc == SIEVE_OK) (*e)->SetDoubleArrayRegion(e, out5, 0, 5, (const jdouble *)&r);
+    chk(e, rc);
+}
+/* size factors over the site shards of one JVM (one part per worker / GPU): sieve_sf_* */
+JNIEXPORT jlong JNICALL FN(sfOpenCore)(JNIEnv *e, jclass c, jlong h, jint zeroCovMode) {
+    sieve_sf_t *p = NULL;
+    chk(e, sieve_sf_open_core(H(h), zeroCovMode, &p));
+    return (jlong)(intptr_t)p;
+}
+JNIEXPORT void JNICALL FN(sfClose)(JNIEnv *e, jclass c, jlong p) { chk(e, sieve_sf_close((sieve_sf_t *)(intptr_t)p)); }
+JNIEXPORT void JNICALL FN(sfSolveParts)(JNIEnv *e, jclass c, jlongArray parts, jdoubleArray sf, jdoubleArray st) {
+    enum { MAX_PARTS = 64 };
+    sieve_sf_t *pp[MAX_PARTS];
+    const jsize n = (*e)->GetArrayLength(e, parts);
+    if (n < 1 || n > MAX_PARTS) {
+        (*e)->ThrowNew(e, (*e)->FindClass(e, "java/lang/IllegalArgumentException"), "sfSolveParts: 1..64 parts");
+        return;
+    }
+    jlong *pl = (*e)->GetPrimitiveArrayCritical(e, parts, NULL);
+    for (jsize i = 0; i < n; i++) pp[i] = (sieve_sf_t *)(intptr_t)pl[i];
+    (*e)->ReleasePrimitiveArrayCritical(e, parts, pl, JNI_ABORT);
+    jdouble *p = (*e)->GetPrimitiveArrayCritical(e, sf, NULL);
+    jdouble *q = st ? (*e)->GetPrimitiveArrayCritical(e, st, NULL) : NULL;
+    int rc = sieve_sf_solve_parts(n, pp, NULL, NULL, p, q);
+    if (st) (*e)->ReleasePrimitiveArrayCritical(e, st, q, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, sf, p, 0);
+    chk(e, rc);
 }
 #endif /* SIEVE_HAVE_JNI */

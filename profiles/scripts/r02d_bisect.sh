@@ -1,0 +1,26 @@
+mkdir -p gpurun_out
+Q="--steps 20 --warmup 3 --no-cpu-baseline --mcmc-states 0 --no-variants --no-dropin --no-north-star"
+for rep in 1 2; do
+for v in nopf def0 def4; do
+  lib=""; pf=0
+  [ $v = nopf ] && lib="$PWD/build/variants/libsieve_b200_nopf.so"
+  [ $v = def4 ] && pf=4
+  SIEVE_B200_LIB=$lib SIEVE_B200_PF_DIST=$pf python bench.py $Q > gpurun_out/r02d_${v}_$rep.json 2> gpurun_out/r02d_${v}_$rep.err
+done
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r02d_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, 'value %.2f ms/step %.3f e2e %.2f prune %.3f tree-only %.3f leaf %.3f'%(d['value'], d['ms_per_step'], d['e2e']['value'], d['kernels']['prune_ms'], d['kernels']['tree_only_eval_ms'], d['kernels']['leaf_ms']), d['clocks'])
+    except Exception as e:
+        print(f, 'ERR', e, open(f.replace('.json','.err')).read()[-600:])
+PY
+for v in nopf def4; do
+  lib=""; pf=0
+  [ $v = nopf ] && lib="$PWD/build/variants/libsieve_b200_nopf.so"
+  [ $v = def4 ] && pf=4
+  SIEVE_B200_LIB=$lib SIEVE_B200_PF_DIST=$pf ncu --set full --clock-control none --import-source on -k regex:k_prune -c 2 -o gpurun_out/r02d_prof_$v -f python profiles/ncu_target.py > gpurun_out/r02d_ncu_$v.log 2>&1
+done
+python -m pytest tests/test_gpu_parity.py -x -q -k "linear or full_evaluation" 2>&1 | tail -5

@@ -10,6 +10,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sieve_b200.h")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, 1, 2, 3, 4
 FLAG_LOG_PARTIALS, FLAG_CONST_PARTIALS, FLAG_SINGLE_ADO, FLAG_EPHEMERAL, FLAG_SPARSE, FLAG_SINGLE_LEAF_BUFFER = 1, 2, 4, 8, 16, 32
+FLAG_EXTERNAL_COUNTS = 64
 UPDATE_FLIP, UPDATE_PER_LEVEL = 1, 2
 ASC_NONE, ASC_FELSENSTEIN_MEAN, ASC_FELSENSTEIN_GEOMETRIC, ASC_LEWIS = 0, 1, 2, 3
 ASC_MODES = {"none": 0, "felsenstein_mean": 1, "felsenstein_geometric": 2, "lewis": 3}
@@ -39,6 +40,19 @@ class ShardResult(C.Structure):
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _vp = C.c_void_p
+_u64p = C.POINTER(C.c_uint64)
+_i64p = C.POINTER(C.c_int64)
+
+# callbacks of the distributed size-factor protocol (include/sieve_b200.h, sieve_sf_ops_t)
+SF_MOMENTS_FN = C.CFUNCTYPE(C.c_int, _vp, _u64p)
+SF_WEIGHT_LE_FN = C.CFUNCTYPE(C.c_int, _vp, C.c_int32, _u64p, _i64p)
+SF_ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _vp, _i64p, C.c_int32)
+
+
+class SfOps(C.Structure):
+    _fields_ = [("user", _vp), ("n_cells", C.c_int32), ("moments", SF_MOMENTS_FN), ("weight_le", SF_WEIGHT_LE_FN),
+                ("allreduce_sum_i64", SF_ALLREDUCE_FN)]
+
 
 # name -> (restype, argtypes); every symbol include/sieve_b200.h declares
 SIGNATURES = {
@@ -54,6 +68,13 @@ SIGNATURES = {
     "sieve_set_pattern_weights": (C.c_int, [_vp, _ip]),
     "sieve_compute_size_factors": (C.c_int, [_vp, C.c_int32, _dp, _dp]),
     "sieve_set_size_factors": (C.c_int, [_vp, _dp]),
+    "sieve_sf_open": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _vp, _ip, C.c_int32, C.POINTER(_vp)]),
+    "sieve_sf_open_core": (C.c_int, [_vp, C.c_int32, C.POINTER(_vp)]),
+    "sieve_sf_close": (C.c_int, [_vp]),
+    "sieve_sf_moments": (C.c_int, [_vp, _u64p]),
+    "sieve_sf_weight_le": (C.c_int, [_vp, C.c_int32, _u64p, _i64p]),
+    "sieve_sf_solve": (C.c_int, [C.POINTER(SfOps), _dp, _dp]),
+    "sieve_sf_solve_parts": (C.c_int, [C.c_int32, C.POINTER(_vp), SF_ALLREDUCE_FN, _vp, _dp, _dp]),
     "sieve_set_leaf_params": (C.c_int, [_vp, C.POINTER(LeafParams)]),
     "sieve_update_leaves": (C.c_int, [_vp, C.c_int32]),
     "sieve_set_node_matrix_for_update": (C.c_int, [_vp, C.c_int32]),

@@ -24,7 +24,8 @@ def _iptr(a):
 
 class ScsCudaLikelihoodCore:
     def __init__(self, n_leaves, n_sites, n_categories=4, n_states=4, use_log_partials=True, asc_bias=False,
-                 single_ado=True, device=-1, ephemeral=False, sparse=False, single_leaf_buffer=False):
+                 single_ado=True, device=-1, ephemeral=False, sparse=False, single_leaf_buffer=False,
+                 external_counts=False):
         """initialize(nodeCount = 2n, leafCount = n, internalCount = n, patternCount, matrixCount, stateCount, ...)
         (likelihood/ScsBeerLikelihoodCore.java:91-128)."""
         self.L = _lib.lib()
@@ -34,7 +35,8 @@ class ScsCudaLikelihoodCore:
         self.asc_bias = bool(asc_bias)
         flags = (FLAG_LOG_PARTIALS if use_log_partials else 0) | (FLAG_CONST_PARTIALS if asc_bias else 0) | \
                 (FLAG_SINGLE_ADO if single_ado else 0) | (FLAG_EPHEMERAL if ephemeral else 0) | \
-                (FLAG_SPARSE if sparse else 0) | (_lib.FLAG_SINGLE_LEAF_BUFFER if single_leaf_buffer else 0)
+                (FLAG_SPARSE if sparse else 0) | (_lib.FLAG_SINGLE_LEAF_BUFFER if single_leaf_buffer else 0) | \
+                (_lib.FLAG_EXTERNAL_COUNTS if external_counts else 0)
         cfg = _lib.Config(self.n, self.S, self.K, self.G, flags, device)
         h = C.c_void_p()
         check(self.L.sieve_create(C.byref(cfg), C.byref(h)))
@@ -164,6 +166,22 @@ class ScsCudaLikelihoodCore:
         check(self.L.sieve_step_distances(self.h, int(bool(update_leaves)), nd.size, _iptr(nd), _dptr(d), o.shape[0],
                                           _iptr(o), C.byref(r)))
         return r
+
+    def traverse_full(self, tree_root, ops, P_all_nodes, update_leaves=False, want_sites=True):
+        """The reference's own traverse call sequence, issued natively call by call (include/sieve_b200_mcmc.h,
+        sieve_traverse_full): the no-extra-edit integration.  P_all_nodes [2n][K][16]."""
+        o = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 3)
+        m = np.ascontiguousarray(P_all_nodes, dtype=np.float64)
+        assert m.size == self.n_nodes * self.K * 16
+        site = np.empty(self.S) if want_sites else None
+        r = ShardResult()
+        fn = self.L.sieve_traverse_full
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                       C.c_int32, C.POINTER(C.c_double), C.POINTER(ShardResult)]
+        check(fn(self.h, self.n_nodes, self.K, int(tree_root), o.shape[0], _iptr(o), _dptr(m), int(bool(update_leaves)),
+                 _dptr(site) if want_sites else None, C.byref(r)))
+        return r, site
 
     def last_stage_bytes(self):
         n = C.c_uint64()

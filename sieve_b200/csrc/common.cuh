@@ -19,7 +19,7 @@ struct __align__(16) SvOp {
     unsigned c2_row;   // child 2, unused for a unary op
     int m1, m2;        // matrix slots (buffer * n_nodes + node) of the two children
     int flags;         // SV_OP_*
-    int pad0, pad1;
+    unsigned pf_row1, pf_row2;  // see SV_OP_PF*
 };  // 32 bytes: two 128-bit loads.  Rows are 32-bit: every pool holds fewer than 2^32 (slot, site) rows (checked at create).
 #define SV_OP_LEAF1 1
 #define SV_OP_LEAF2 2
@@ -27,8 +27,13 @@ struct __align__(16) SvOp {
 #define SV_OP_ROOT 8
 #define SV_OP_FWD1 16
 #define SV_OP_ZEROD 64    // one of the two distances is exactly 0: take the Double.MIN_VALUE clamp path
-#define SV_OP_DEP1 256    // child 1 / child 2 is read from memory AND written by an earlier op of the same list (set when
-#define SV_OP_DEP2 512    // the list is staged; prune_tma.cuh does not stage such an operand)
+// L2 prefetch annotations (sv_link_prefetch): op i carries, in pf_row1 / pf_row2, the rows of the LEAF operands that op
+// i + D will read (leaf partials always come from DRAM: every one is read once per evaluation); the walk asks for
+// their lines a few ops ahead so that the op that consumes them pays an L2 hit instead of a DRAM round trip.
+#define SV_OP_PF1 256
+#define SV_OP_PF2 1024
+#define SV_OP_FAR1 4096   // this op's own child 1 / child 2 is such an operand (used for the first D ops of a list,
+#define SV_OP_FAR2 8192   // which no earlier op could announce)
 #define SV_OP_NOSTORE 32  // the result is consumed from registers by the next op and never needed again: skip the writes
 
 // 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one (site, category) state vector.
@@ -41,6 +46,11 @@ __device__ __forceinline__ void sv_ld256_nc(const double* p, double (&v)[4]) {
 }
 __device__ __forceinline__ void sv_st256(double* p, const double (&v)[4]) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+// one line into L2: no destination register, no scoreboard entry
+__device__ __forceinline__ void sv_prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 __device__ __forceinline__ double sv_max4(const double (&v)[4]) { return fmax(fmax(v[0], v[1]), fmax(v[2], v[3])); }

@@ -100,12 +100,7 @@ struct sieve_core {
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
     bool force_generic = false;
-    bool use_tma = false, tma_attr_set = false;  // SIEVE_B200_TMA: the TMA-staged walk (prune_tma.cuh)
-    int tma_stages = 3;
-    std::unordered_map<unsigned, int> scratch_writer;
-    int rp_blocks = 5;
-    bool use_rp = false;  // SIEVE_B200_RP=1: next op's operands prefetched into registers (prune_rp.cuh)
-    bool use_pipe = false, pipe_attr_set = false;  // SIEVE_B200_PIPE=1: the cp.async-pipelined Q walk (measured slower, see prune_pipe.cuh)
+    int pf_dist = 4;  // SIEVE_B200_PF_DIST: how many ops ahead the walk asks the TMA unit to bring operands into L2 (0: off)
     // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
     int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
     int n_slots = 0;     // scratch slots for internal partials

@@ -34,6 +34,7 @@ struct SvPruneArgs {
     const SvOp* ops;
     int op_begin, op_end;  // walk: ops [op_begin, op_end); per-level: op = op_begin + blockIdx.y
     int per_level;
+    int pf_dist;           // ops ahead that the L2 prefetch annotations look (0: none); the first pf_dist ops are announced by a prologue
     int S, K;              // S = sites of this launch; the ops' rows were formed with the pools' site capacity
     long long out_offset;  // first site of this launch in site_logl / site_const (streamed evaluation)
     int linear_const_clamp;  // !SIEVE_FLAG_LOG_PARTIALS: clamp of the constant-site product (:1041-1047)
@@ -57,7 +58,9 @@ __device__ __forceinline__ double sv_sel(const double (&x)[4], int g) {
     return g == 0 ? x[0] : (g == 1 ? x[1] : (g == 2 ? x[2] : x[3]));
 }
 
+#ifndef SV_PRUNE_THREADS
 #define SV_PRUNE_THREADS 128
+#endif
 #ifndef SV_PRUNE_NS
 #define SV_PRUNE_NS 2  // sites per lane: the op's matrices are read from shared memory once and applied to NS sites
 #endif
@@ -80,6 +83,9 @@ __device__ __forceinline__ double sv_sel(const double (&x)[4], int g) {
 #ifndef SV_PRUNE_MINB_Q
 #define SV_PRUNE_MINB_Q 6
 #endif
+// the MINB figures count resident groups of four warps per SM (the block size the kernels were tuned with); a build
+// with another block size keeps the same number of resident warps
+__host__ __device__ constexpr int sv_prune_min_blocks(int minb4) { return minb4 * 128 / SV_PRUNE_THREADS; }
 __host__ __device__ constexpr int sv_prune_ns(bool with_const, bool qfast) {
     return qfast ? (with_const ? SV_PRUNE_NS_Q_TWIN : SV_PRUNE_NS_Q) : SV_PRUNE_NS;
 }
@@ -154,9 +160,9 @@ __device__ __forceinline__ void sv_col0_q(const double2 q, const double (&x)[NS]
 // MINB: resident blocks per SM asked of the compiler; 0 = the default of the variant (SIEVE_B200_PRUNE_MINB instantiates
 // the variant-only Q walk at 7 and 8 for comparison).
 template <bool WITH_CONST, bool GENO0, bool QFAST, int MINB = 0>
-__global__ void __launch_bounds__(SV_PRUNE_THREADS, MINB ? MINB
-                                                    : QFAST ? (WITH_CONST ? SV_PRUNE_MINB_CONST_Q : SV_PRUNE_MINB_Q)
-                                                            : (WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB))
+__global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? MINB
+                                                                        : QFAST ? (WITH_CONST ? SV_PRUNE_MINB_CONST_Q : SV_PRUNE_MINB_Q)
+                                                                                : (WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB)))
     k_prune(SvPruneArgs a) {
     constexpr int NS = sv_prune_ns(WITH_CONST, QFAST);
     constexpr int SITES_PER_BLOCK = (SV_PRUNE_THREADS / 4) * NS;
@@ -206,6 +212,30 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, MINB ? MINB
         for (int g = 0; g < 4; g++) x[j][g] = cx[j][g] = 0.0;
     }
 
+    // L2 prefetch of leaf operands a few ops ahead (sv_link_prefetch).  The lanes with category index j < NS ask for the
+    // line of their site of pass j: the same address arithmetic as the real load, 8 addresses 32 bytes apart = two lines
+    // per pass; one predicated instruction per operand and lane, no register, no scoreboard, no branch.
+    const int pf_on = klane < NS ? 1 : 0;
+    auto announce = [&](unsigned row, int cond) {
+        unsigned sr = srow[0];
+#pragma unroll
+        for (int j = 1; j < NS; j++) sr = klane == j ? srow[j] : sr;
+        if (cond && pf_on) sv_prefetch_l2(a.leafX + (size_t)(row + sr) * 4);
+    };
+#ifndef SV_PRUNE_NO_PF
+    if (!a.per_level && a.pf_dist > 0) {
+        // the first pf_dist ops of the list: nobody could announce their operands earlier
+        const int jn = min(i1, i0 + a.pf_dist);
+#pragma unroll 1
+        for (int j = i0; j < jn; j++) {
+            const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.ops + j));
+            const int fl = __ldg(reinterpret_cast<const int*>(a.ops + j) + 5);
+            announce((unsigned)d0.y, fl & SV_OP_FAR1);
+            announce((unsigned)d0.z, fl & SV_OP_FAR2);
+        }
+    }
+#endif
+
     // the descriptor of the next op is fetched while this op's operands are in flight: it is off the critical path
     // (descriptor -> addresses -> operand loads) of every op but the first
     int4 n0 = make_int4(0, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
@@ -226,6 +256,11 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, MINB ? MINB
         const int m1 = o0.w, m2 = o1.x, flags = o1.y;
         const bool unary = flags & SV_OP_UNARY;
         const bool leaf1 = flags & SV_OP_LEAF1, leaf2 = flags & SV_OP_LEAF2;
+#ifndef SV_PRUNE_NO_PF
+        // leaf operands of the op pf_dist ahead: into L2 now
+        announce((unsigned)o1.z, flags & SV_OP_PF1);
+        announce((unsigned)o1.w, flags & SV_OP_PF2);
+#endif
 
         // ---- issue every global load of this op up front: matrices (one 256-bit load per lane) and children ----
         double m[4] = {0, 0, 0, 0};
@@ -410,7 +445,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, MINB ? MINB
 // scale: the node's own (power-of-two) scale, NULL for a leaf; lsum: the sum of the scales of the leaves below the node
 __global__ void k_export_partials(const double* __restrict__ x, const double* __restrict__ scale,
                                   const double* __restrict__ lsum, int S, int K, int is_leaf, int as_log,
-                                  double* __restrict__ out) {
+                                  int clamp_min, double* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over K * S * 4
     if (idx >= K * S * 4) return;
     const int g = idx & 3;
@@ -418,5 +453,7 @@ __global__ void k_export_partials(const double* __restrict__ x, const double* __
     const int k = (idx >> 2) / S;
     const double v = is_leaf ? x[(size_t)s * 4 + g] : x[((size_t)s * SV_KMAX + k) * 4 + g];
     const double ls = (scale ? scale[s] : 0.0) + lsum[s];
-    out[idx] = as_log ? log(v) + ls : v * exp(ls);
+    const double lin = v * exp(ls);
+    // clamp_min: linear-mode constant-site partials, clamped like ScsBeerLikelihoodCore.java:1041-1047
+    out[idx] = as_log ? log(v) + ls : (clamp_min && !(lin > 0.0) ? SV_MIN_VALUE : lin);
 }

@@ -150,6 +150,9 @@ __global__ void k_export_const(const double* __restrict__ lam, const double* __r
     for (int k = 0; k < K; k++)
         for (int g = 0; g < 4; g++) {
             const double v = log(G[k * 4 + g]) + gscale + l;
-            out[((size_t)k * S + s) * 4 + g] = as_log ? v : exp(v);
+            // linear mode: the reference clamps a constant-site product that underflowed to Double.MIN_VALUE
+            // (ScsBeerLikelihoodCore.java:1041-1047); the read-back shows the same
+            const double e = exp(v);
+            out[((size_t)k * S + s) * 4 + g] = as_log ? v : (e > 0.0 ? e : SV_MIN_VALUE);
         }
 }

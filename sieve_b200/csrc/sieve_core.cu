@@ -15,9 +15,6 @@
 #include "common.cuh"
 #include "leaf.cuh"
 #include "prune.cuh"
-#include "prune_pipe.cuh"
-#include "prune_rp.cuh"
-#include "prune_tma.cuh"
 #include "reduce.cuh"
 #include "maxsum.cuh"
 #include "sizefactors.cuh"
@@ -25,6 +22,7 @@
 #include "comm.cuh"
 
 #include "core_state.cuh"
+#include "sizefactors_global.cuh"
 
 extern "C" const char* sieve_last_error(void) { return g_err.c_str(); }
 extern "C" int sieve_version(void) { return 1; }
@@ -61,16 +59,8 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->log_mode = cfg->flags & SIEVE_FLAG_LOG_PARTIALS;
     h->with_const = cfg->flags & SIEVE_FLAG_CONST_PARTIALS;
     if (const char* e = getenv("SIEVE_B200_CONST_TWIN")) h->const_twin = atoi(e) != 0;
-    if (const char* e = getenv("SIEVE_B200_PIPE")) h->use_pipe = atoi(e) != 0;
-    if (const char* e = getenv("SIEVE_B200_RP")) {  // 1: the register-pipelined walk at 5 blocks/SM, 4: at 4 blocks/SM
-        h->use_rp = atoi(e) != 0;
-        h->rp_blocks = atoi(e) == 4 ? 4 : 5;
-    }
     if (const char* e = getenv("SIEVE_B200_PRUNE_MINB")) h->prune_minb = atoi(e);
-    if (const char* e = getenv("SIEVE_B200_TMA")) {  // N > 0: the TMA-staged walk with N stages (2..4; 1 means 3)
-        h->use_tma = atoi(e) != 0;
-        h->tma_stages = atoi(e) == 2 ? 2 : atoi(e) == 4 ? 4 : 3;
-    }
+    if (const char* e = getenv("SIEVE_B200_PF_DIST")) h->pf_dist = std::max(0, std::min(64, atoi(e)));
     if (const char* e = getenv("SIEVE_B200_LEAF_TAB")) h->leaf_tab = std::min(2, std::max(0, atoi(e)));
     if (const char* e = getenv("SIEVE_B200_LEAF_CHECKED")) h->leaf_force_checked = atoi(e) != 0;
     const bool twin = h->with_const && h->const_twin;
@@ -101,7 +91,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         // leaf-scratch budget of a quarter of the free memory (at most 48 GB)
         size_t free0 = 0, total0 = 0;
         cudaMemGetInfo(&free0, &total0);
-        const size_t counts_bytes = n * S * 16;
+        const size_t counts_bytes = (cfg->flags & SIEVE_FLAG_EXTERNAL_COUNTS) ? 0 : n * S * 16;
         const size_t avail = free0 > counts_bytes ? free0 - counts_bytes : 0;
         const size_t budget = std::min<size_t>((size_t)48 << 30, avail / 4);
         size_t cap = std::max<size_t>(4096, budget / (40 * n));
@@ -124,7 +114,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         // everything but the internal partials is resident as usual; the pool takes what is left (minus head room)
         size_t free0 = 0, total0 = 0;
         cudaMemGetInfo(&free0, &total0);
-        const size_t fixed = n * S * 16 + leaf_bufs * n * S * 32 + ((n + 31) / 32) * S * 16 + ((size_t)3 << 30);
+        const size_t fixed = ((cfg->flags & SIEVE_FLAG_EXTERNAL_COUNTS) ? 0 : n * S * 16) + leaf_bufs * n * S * 32 + ((n + 31) / 32) * S * 16 + ((size_t)3 << 30);
         const size_t per_slot = S * (SV_KMAX * 32 + 8) * (twin ? 2 : 1);
         size_t slots = free0 > fixed ? (free0 - fixed) / per_slot : 0;
         if (const char* e = getenv("SIEVE_B200_POOL_SLOTS")) slots = (size_t)std::max(0, atoi(e));
@@ -156,7 +146,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         return fail(SIEVE_ERR_OOM);
     }
     // does the residency fit?
-    size_t need = n * S * 16 + leaf_bufs * n * pool_sites * 32 + ((n + 31) / 32) * pool_sites * 16 +
+    size_t need = ((cfg->flags & SIEVE_FLAG_EXTERNAL_COUNTS) ? 0 : n * S * 16) + leaf_bufs * n * pool_sites * 32 + ((n + 31) / 32) * pool_sites * 16 +
                   part_slots * pool_sites * (SV_KMAX * 32 + 8) * (twin ? 2 : 1) + ((size_t)64 << 20);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -172,7 +162,10 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         r = (x);                           \
         if (r != SIEVE_OK) return fail(r); \
     } while (0)
-    CR(sv_alloc(h, &h->d_counts, n * S));
+    if (cfg->flags & SIEVE_FLAG_EXTERNAL_COUNTS)
+        h->counts_owned = false;  // adopted by sieve_set_counts_device
+    else
+        CR(sv_alloc(h, &h->d_counts, n * S));
     CR(sv_alloc(h, &h->d_sf, n));
     CR(sv_alloc(h, &h->d_leafX, leaf_bufs * n * pool_sites * 4));
     const size_t leaf_groups = (n + SV_LEAF_CELLS - 1) / SV_LEAF_CELLS;
@@ -381,6 +374,7 @@ static int sv_finish_counts(sieve_core* h, int* d_max) {
 extern "C" int sieve_set_counts(sieve_core_t* h, const int32_t* counts, int32_t tuple_len) {
     SV_REQUIRE(h && counts, "sieve_set_counts: null argument");
     SV_REQUIRE(tuple_len == 4 || tuple_len == 5, "sieve_set_counts: tuple_len must be 4 or 5");
+    if (!h->counts_owned) return sv_fail(SIEVE_ERR_STATE, "sieve_set_counts: SIEVE_FLAG_EXTERNAL_COUNTS handles take sieve_set_counts_device only");
     SV_CUDA(cudaSetDevice(h->device));
     const size_t n = h->n, S = h->S;
     // bounded staging: at most ~256 MiB of the host tensor on the device at a time
@@ -427,6 +421,7 @@ __global__ void k_widen_counts_u16(const ushort4* __restrict__ in, size_t N, int
 extern "C" int sieve_set_counts_cellmajor(sieve_core_t* h, const void* counts, int32_t dtype_code) {
     SV_REQUIRE(h && counts, "sieve_set_counts_cellmajor: null argument");
     SV_REQUIRE(dtype_code == 0 || dtype_code == 1, "sieve_set_counts_cellmajor: dtype_code must be 0 (int32) or 1 (uint16)");
+    if (!h->counts_owned) return sv_fail(SIEVE_ERR_STATE, "sieve_set_counts_cellmajor: SIEVE_FLAG_EXTERNAL_COUNTS handles take sieve_set_counts_device only");
     SV_CUDA(cudaSetDevice(h->device));
     const size_t N = (size_t)h->n * h->S;
     int* d_max = nullptr;
@@ -468,7 +463,10 @@ extern "C" int sieve_set_counts_device(sieve_core_t* h, const void* d_counts) {
     SV_REQUIRE(h && d_counts, "sieve_set_counts_device: null argument");
     SV_CUDA(cudaSetDevice(h->device));
     const size_t N = (size_t)h->n * h->S;
-    SV_CUDA(cudaMemcpyAsync(h->d_counts, d_counts, N * sizeof(int4), cudaMemcpyDeviceToDevice, h->stream));
+    if (!h->counts_owned)
+        h->d_counts = (int4*)const_cast<void*>(d_counts);  // SIEVE_FLAG_EXTERNAL_COUNTS: adopted, not copied
+    else
+        SV_CUDA(cudaMemcpyAsync(h->d_counts, d_counts, N * sizeof(int4), cudaMemcpyDeviceToDevice, h->stream));
     int* d_max = nullptr;
     SV_CUDA(cudaMalloc(&d_max, sizeof(int)));
     SV_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
@@ -518,6 +516,67 @@ extern "C" int sieve_set_size_factors(sieve_core_t* h, const double* sf) {
     h->have_sf = true;
     h->cov_dirty = true;
     return SIEVE_OK;
+}
+
+// ---- size factors over a site-sharded alignment (sizefactors_global.cuh) ------------------------------------------
+extern "C" int sieve_sf_open(int32_t device, int32_t n_cells, int32_t n_sites, const void* d_counts, const int32_t* weights,
+                             int32_t zero_cov_mode, sieve_sf_t** out) {
+    return sv_sf_open(device, n_cells, n_sites, d_counts, weights, zero_cov_mode, out);
+}
+extern "C" int sieve_sf_open_core(sieve_core_t* h, int32_t zero_cov_mode, sieve_sf_t** out) {
+    SV_REQUIRE(h && out, "sieve_sf_open_core: null argument");
+    if (!h->have_counts) return sv_fail(SIEVE_ERR_STATE, "sieve_sf_open_core: counts not set");
+    std::vector<int32_t> w;
+    if (h->d_weights) {
+        w.resize(h->S);
+        SV_CUDA(cudaSetDevice(h->device));
+        SV_CUDA(cudaMemcpy(w.data(), h->d_weights, sizeof(int) * (size_t)h->S, cudaMemcpyDeviceToHost));
+    }
+    return sv_sf_open(h->device, h->n, h->S, h->d_counts, h->d_weights ? w.data() : nullptr, zero_cov_mode, out);
+}
+extern "C" int sieve_sf_close(sieve_sf_t* p) {
+    if (!p) return SIEVE_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    cudaFree(p->d_geo);
+    cudaFree(p->d_mom);
+    cudaFree(p->d_piv);
+    cudaFree(p->d_cnt);
+    cudaFree(p->d_weights);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    cudaGetLastError();
+    delete p;
+    return SIEVE_OK;
+}
+extern "C" int sieve_sf_moments(sieve_sf_t* p, uint64_t* out3) {
+    SV_REQUIRE(p && out3, "sieve_sf_moments: null argument");
+    out3[0] = p->mom[0];
+    out3[1] = p->mom[1];
+    out3[2] = (uint64_t)p->n * (uint64_t)p->S;
+    return SIEVE_OK;
+}
+extern "C" int sieve_sf_weight_le(sieve_sf_t* p, int32_t n_piv, const uint64_t* pivots, int64_t* out) {
+    return sv_sf_weight_le(p, n_piv, pivots, out);
+}
+extern "C" int sieve_sf_solve(const sieve_sf_ops_t* ops, double* out_sf, double* out_stats) {
+    return sv_sf_solve(ops, out_sf, out_stats);
+}
+extern "C" int sieve_sf_solve_parts(int32_t n_parts, sieve_sf_t* const* parts, sieve_sf_allreduce_fn ar, void* user,
+                                    double* out_sf, double* out_stats) {
+    SV_REQUIRE(n_parts >= 1 && parts && out_sf, "sieve_sf_solve_parts: bad argument");
+    for (int i = 0; i < n_parts; i++) {
+        SV_REQUIRE(parts[i], "sieve_sf_solve_parts: null part");
+        SV_REQUIRE(parts[i]->n == parts[0]->n && parts[i]->zero_cov_mode == parts[0]->zero_cov_mode,
+                   "sieve_sf_solve_parts: the parts disagree on the number of cells or on zeroCovMode");
+    }
+    SvSfParts P{n_parts, parts, ar, user, {}};
+    sieve_sf_ops_t ops;
+    ops.user = &P;
+    ops.n_cells = parts[0]->n;
+    ops.moments = sv_sf_parts_moments;
+    ops.weight_le = sv_sf_parts_weight_le;
+    ops.allreduce_sum_i64 = sv_sf_parts_allreduce;
+    return sv_sf_solve(&ops, out_sf, out_stats);
 }
 
 // ---- leaves ---------------------------------------------------------------------------------------------------
@@ -925,7 +984,9 @@ extern "C" int sieve_set_root(sieve_core_t* h, int32_t root, const double* propo
 // divide into waves: 100 000 sites are 1.76 / 1.51 / 1.32 waves (6 wins: 2.50 / 2.66 / 2.86 ms), 125 000 sites 2.20 /
 // 1.89 / 1.65 (7 wins: 3.29 / 3.19 / 3.50 ms).  Same PTX, same arithmetic: the choice cannot change a bit of the results.
 // profiles/README.md has the measurements.
-static int sv_pick_prune_blocks(unsigned blocks) {
+static int sv_pick_prune_blocks(unsigned warps) {
+    // the model was fitted in units of four warps (64 sites): resident units per SM = 6, 7 or 8
+    const unsigned blocks = (warps + 3) / 4;
     static const int m[3] = {6, 7, 8};
     static const double per_wave[3] = {6.0, 7.0 * 1.026, 8.0 * 1.058};
     int best = 6;
@@ -946,7 +1007,7 @@ static int sv_pick_prune_blocks(unsigned blocks) {
 extern "C" int sieve_walk_blocks_per_sm(int64_t n_sites) {
     if (n_sites <= 0) return 6;
     const int spb = sv_prune_sites(false, true);
-    return sv_pick_prune_blocks((unsigned)((n_sites + spb - 1) / spb));
+    return sv_pick_prune_blocks((unsigned)((n_sites + spb - 1) / spb) * (SV_PRUNE_THREADS / 32));
 }
 
 template <bool QFAST>
@@ -958,7 +1019,7 @@ static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
         else
             k_prune<true, false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
     } else {
-        const int minb = QFAST && g0 && grid.y == 1 ? (h->prune_minb ? h->prune_minb : sv_pick_prune_blocks(grid.x)) : 0;
+        const int minb = QFAST && g0 && grid.y == 1 ? (h->prune_minb ? h->prune_minb : sv_pick_prune_blocks(grid.x * (SV_PRUNE_THREADS / 32))) : 0;
         if (minb == 7)
             k_prune<false, true, QFAST, 7><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
         else if (minb == 8)
@@ -998,6 +1059,7 @@ static int sv_launch_staged(sieve_core* h) {
         a.qfac = h->d_qfac;
         a.clamp_zero_distance = h->log_mode ? 1 : 0;
         a.ops = (const SvOp*)(h->d_stage);
+        a.pf_dist = h->last_per_level ? 0 : h->pf_dist;
         a.S = h->S;
         a.out_offset = 0;
         a.K = K;
@@ -1011,42 +1073,8 @@ static int sv_launch_staged(sieve_core* h) {
         const bool qfast = h->last_qfast && a.const_genotype == 0 && a.root_genotype == 0 && !h->force_generic;
         const int spb = sv_prune_sites(h->with_const && h->const_twin, qfast);
         const unsigned gx = (unsigned)((h->S + spb - 1) / spb);
-        // the software-pipelined walk (prune_pipe.cuh): Q-specialised, variant partials only, one launch for many ops
-        const bool pipe = qfast && !(h->with_const && h->const_twin) && h->use_pipe && !h->last_per_level;
-        const bool rp = qfast && !(h->with_const && h->const_twin) && h->use_rp && !h->last_per_level && !pipe;
-        // the TMA-staged walk (prune_tma.cuh): scale rows must be 16-byte aligned, i.e. the pools' site capacity even
-        const long long cap_sites = h->ephemeral ? (long long)h->chunk_cap : (long long)h->S;
-        const bool tma = qfast && !(h->with_const && h->const_twin) && h->use_tma && !h->last_per_level && !pipe && !rp &&
-                         cap_sites % 2 == 0;
-        if (tma && !h->tma_attr_set) {
-            SV_CUDA(cudaFuncSetAttribute(k_prune_tma<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_tma_smem(2)));
-            SV_CUDA(cudaFuncSetAttribute(k_prune_tma<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_tma_smem(3)));
-            SV_CUDA(cudaFuncSetAttribute(k_prune_tma<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sv_tma_smem(4)));
-            h->tma_attr_set = true;
-        }
-        if (pipe && !h->pipe_attr_set) {
-            SV_CUDA(cudaFuncSetAttribute(k_prune_pipe<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared));
-            h->pipe_attr_set = true;
-        }
         auto launch = [&](dim3 grid) {
-            if (tma && grid.y == 1) {
-                if (h->tma_stages == 2)
-                    k_prune_tma<true, 2><<<grid, SV_PRUNE_THREADS, sv_tma_smem(2), h->stream>>>(a);
-                else if (h->tma_stages == 4)
-                    k_prune_tma<true, 4><<<grid, SV_PRUNE_THREADS, sv_tma_smem(4), h->stream>>>(a);
-                else
-                    k_prune_tma<true, 3><<<grid, SV_PRUNE_THREADS, sv_tma_smem(3), h->stream>>>(a);
-            } else if (pipe)
-                k_prune_pipe<true><<<grid, SV_PRUNE_THREADS, SV_PIPE_SMEM, h->stream>>>(a);
-            else if (rp)
-            {
-                if (h->rp_blocks == 4)
-                    k_prune_rp<true, 4><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
-                else
-                    k_prune_rp<true, 5><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
-            }
-            else if (qfast)
+            if (qfast)
                 sv_launch_prune_t<true>(h, grid, a);
             else
                 sv_launch_prune_t<false>(h, grid, a);
@@ -1173,17 +1201,8 @@ static int sv_flush(sieve_core* h) {
     SV_CUDA(cudaStreamSynchronize(h->stream));  // the previous step may still be reading the staging buffer
     sv_link_forwarding(h->pending_ops, h->pending_per_level);
     if (no) {
-        // dependencies through memory inside the list (prune_tma.cuh): an operand that an earlier op of the list writes
         std::vector<SvOp>& ops = h->pending_ops;
-        std::unordered_map<unsigned, int>& last_writer = h->scratch_writer;
-        last_writer.clear();
-        for (size_t i = 0; h->use_tma && i < no; i++) {  // only the TMA-staged walk looks at these flags
-            SvOp& op = ops[i];
-            op.flags &= ~(SV_OP_DEP1 | SV_OP_DEP2);
-            if (!(op.flags & (SV_OP_LEAF1 | SV_OP_FWD1)) && last_writer.count(op.c1_row)) op.flags |= SV_OP_DEP1;
-            if (!(op.flags & (SV_OP_LEAF2 | SV_OP_UNARY)) && last_writer.count(op.c2_row)) op.flags |= SV_OP_DEP2;
-            if (!(op.flags & SV_OP_NOSTORE)) last_writer[op.dst_row] = (int)i;
-        }
+        sv_link_prefetch(ops, h->pending_per_level ? 0 : h->pf_dist);
         memcpy(h->h_stage, ops.data(), no * sizeof(SvOp));
     }
     size_t im = 0, id = 0;
@@ -1344,6 +1363,10 @@ extern "C" int sieve_replay(sieve_core_t* h, int32_t update_leaves, int32_t n_ti
         SV_TRY(sv_launch_staged(h));
         sv_launch_reduce(h);
         sv_count(h);
+        if (h->comm) {  // the per-evaluation exchange of a multi-process run, as in sv_evaluate
+            ncclResult_t nr = sv_nccl().AllGather(h->d_result, h->d_gather, 5, ncclDouble, h->comm, h->stream);
+            if (nr != ncclSuccess) return sv_fail(SIEVE_ERR_CUDA, std::string("ncclAllGather: ") + sv_nccl().GetErrorString(nr));
+        }
     }
     SV_CUDA(cudaGetLastError());
     return SIEVE_OK;
@@ -1434,7 +1457,7 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     const size_t N = K * S * 4;
     SV_CUDA(cudaMalloc(&d_out, N * sizeof(double)));
     k_export_partials<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(x, sc, d_sub, (int)S, (int)K, is_leaf,
-                                                                          h->log_mode ? 1 : 0, d_out);
+                                                                          h->log_mode ? 1 : 0, which == 1 ? 1 : 0, d_out);
     sv_count(h);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);

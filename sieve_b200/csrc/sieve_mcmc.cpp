@@ -734,3 +734,33 @@ extern "C" int sieve_mcmc_full_recompute(sieve_mcmc_t* m, double* log_p) {
     const int rc = evaluate(m, true, true, log_p, &no, &nm);
     return rc;
 }
+
+// ---- the reference's own traverse sequence, call by call ----------------------------------------------------------------
+// What ScsTreeLikelihood.traverse issues for a whole-tree update when the core behind the LikelihoodCore seam is swapped
+// and NOTHING else in the plugin changes (likelihood/ScsTreeLikelihood.java:563-580 matrices, :583-601 leaves, :621-628 +
+// :745-752 / :854-861 partials, :888-920 root; calcLogP :2621-2651): per non-root node setNodeMatrixForUpdate and K x
+// setNodeMatrix (16 doubles each), per internal node setNodePartialsForUpdate and calculateLogPartials, then the
+// evaluation and getPatternLogLikelihoods.  Every call goes through the public C-ABI, natively, as the JNI shim forwards
+// it -- this is the number for the no-extra-edit integration (the batched sieve_step_distances needs one more edit).
+extern "C" int sieve_traverse_full(sieve_core_t* h, int32_t n_nodes, int32_t n_categories, int32_t root, int32_t n_ops,
+                                   const int32_t* ops_post_order, const double* P, int32_t update_leaves,
+                                   double* site_log_l, sieve_shard_result_t* out) {
+    if (!h || !ops_post_order || !P || n_ops < 0) return SIEVE_ERR_INVALID;
+    int r;
+    const int n_leaves = n_nodes / 2;
+    for (int node = 0; node < n_nodes; node++) {
+        if (node == root) continue;
+        if ((r = sieve_set_node_matrix_for_update(h, node)) != SIEVE_OK) return r;
+        for (int k = 0; k < n_categories; k++)
+            if ((r = sieve_set_node_matrix(h, node, k, P + ((size_t)node * n_categories + k) * 16)) != SIEVE_OK) return r;
+    }
+    if (update_leaves && (r = sieve_update_leaves(h, 1)) != SIEVE_OK) return r;
+    for (int i = 0; i < n_ops; i++) {
+        const int parent = ops_post_order[3 * i], c1 = ops_post_order[3 * i + 1], c2 = ops_post_order[3 * i + 2];
+        if ((r = sieve_set_node_partials_for_update(h, parent)) != SIEVE_OK) return r;
+        if ((r = sieve_calculate_partials(h, c1, c1 < n_leaves, c2, c2 >= 0 && c2 < n_leaves, parent, 0)) != SIEVE_OK) return r;
+    }
+    if ((r = sieve_evaluate(h, out)) != SIEVE_OK) return r;
+    if (site_log_l && (r = sieve_get_site_log_likelihoods(h, site_log_l, nullptr)) != SIEVE_OK) return r;
+    return SIEVE_OK;
+}

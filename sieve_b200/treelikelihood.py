@@ -53,15 +53,15 @@ class ScsTreeLikelihood:
                                           single_ado, device, ephemeral, sparse, single_leaf_buffer)
         self.core.set_counts(counts)
         self.core.set_pattern_weights(weights)
-        if size_factors is None:
-            size_factors, self.cov_stats = self.core.compute_size_factors(0)
-        else:
-            self.core.set_size_factors(size_factors)
-        self.size_factors = np.asarray(size_factors)
-        # initCore (:430-468): leaves into both buffers, everything filthy
-        self.core.set_leaf_params(*self.params.as_tuple())
-        self.core.update_leaves(for_update=False)
         self.branch_lengths = np.full(tree.node_count, -1.0)   # m_branchLengths
+        self.size_factors = None
+        if isinstance(size_factors, str) and size_factors == "defer":
+            pass        # a shard of a larger alignment: the global size factors come later (finish_init)
+        elif size_factors is None:
+            size_factors, self.cov_stats = self.core.compute_size_factors(0)
+            self.finish_init(size_factors, already_set=True)
+        else:
+            self.finish_init(size_factors)
         self.stored_branch_lengths = self.branch_lengths.copy()
         self.has_dirt = IS_FILTHY
         self.update_leaves = False
@@ -69,6 +69,14 @@ class ScsTreeLikelihood:
         self.logP = None
         self.result = None
         self._refresh_site_model()
+
+    def finish_init(self, size_factors, already_set=False):
+        """initCore (:430-468) once the size factors are known: leaves into both buffers, everything filthy."""
+        if not already_set:
+            self.core.set_size_factors(size_factors)
+        self.size_factors = np.asarray(size_factors)
+        self.core.set_leaf_params(*self.params.as_tuple())
+        self.core.update_leaves(for_update=False)
 
     def close(self):
         self.core.close()
@@ -176,19 +184,25 @@ class ThreadedScsTreeLikelihood:
         self.points = pattern_points(S, n_shards)
         self.asc_mode, self.M = asc_mode, float(n_background_sites)
         sf = kw.pop("size_factors", None)
-        if sf is None:
-            # deeplyInitialize on the full alignment first, so that the size factors are global
-            tmp = ScsCudaLikelihoodCore(n, S, 1, 4, True, False, True, -1 if devices is None else devices[0])
-            tmp.set_counts(counts)
-            sf, _ = tmp.compute_size_factors(0)
-            tmp.close()
-        self.size_factors = sf
         self.shards = []
         for r in range(n_shards):
             dev = -1 if devices is None else devices[r % len(devices)]
-            self.shards.append(ScsTreeLikelihood(counts[self.points[r]:self.points[r + 1]], tree.copy(), size_factors=sf,
+            self.shards.append(ScsTreeLikelihood(counts[self.points[r]:self.points[r + 1]], tree.copy(),
+                                                 size_factors="defer" if sf is None else sf,
                                                  asc_mode=asc_mode, n_background_sites=n_background_sites, device=dev,
                                                  return_const_sum=True, **kw))
+        if sf is None:
+            # deeplyInitialize on the full alignment (:119-131): the size factors are global.  No device holds the full
+            # alignment here, so the per-cell medians are found by exact selection over the shards' own count tensors
+            # (sieve_sf_*): bit-identical to one handle over all sites, and nothing but the shards is ever allocated.
+            from .sizefactors import SizeFactorPart, solve_parts
+            parts = [SizeFactorPart(core=s.core) for s in self.shards]
+            sf, self.cov_stats = solve_parts(parts)
+            for p in parts:
+                p.close()
+            for s in self.shards:
+                s.finish_init(sf)
+        self.size_factors = sf
 
     def close(self):
         for s in self.shards:

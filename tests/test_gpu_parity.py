@@ -118,7 +118,7 @@ def test_full_evaluation_matches_oracle(core_mod, oracle, asc, use_log, single, 
                     oc.set_node_matrix(node, k, mats[node, k])
         for p, c1, c2 in tree.ops():
             oc.calculate_partials(c1, c1 < tree.n, c2, 0 <= c2 < tree.n, p, 0)
-        atol = 1e-11 if use_log else 0.0
+        atol = 1e-11 if use_log else 1e-318     # linear mode: subnormal values carry only a few bits
         for node in (tree.n, tree.n + 7, tree.root - 1, tree.root):
             np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=atol)
             if asc != "none":
@@ -157,12 +157,14 @@ def test_linear_partials_specific_behaviour(core_mod, oracle):
     logp, osl, osc = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, "felsenstein_mean", M, use_log=False)
     assert np.isfinite(osl).all()
     _close(sl, osl, SITE_RTOL)
-    ok = np.ones(300, dtype=bool)
-    ok[11] = False
+    # wherever the reference's unscaled constant-site product is representable the two agree ...
+    ok = np.isfinite(osc) & (osc > -700.0)
+    assert not ok[11] and ok.sum() >= 200
     _close(sc[ok], osc[ok], SITE_RTOL)
-    # the reference's linear core lost site 11's constant-site likelihood to underflow; the device keeps it
-    assert osc[11] < -700.0 or np.isneginf(osc[11])
-    assert np.isfinite(sc[11]) and sc[11] < -745.0
+    # ... and where the reference's linear core lost it to underflow (site 11 by construction, and any site with a real
+    # mutation carried by several well-covered cells) the device keeps the true, very negative value
+    assert np.isfinite(sc[~ok]).all() and (sc[~ok] < -700.0).all()
+    assert sc[11] < -745.0
     got = core_mod.combine_shards([r], "felsenstein_mean", M)
     assert abs(got - logp) <= TOTAL_RTOL * abs(logp)
     # parent of the zero-length branch: linear partials against the oracle's linear core
@@ -178,7 +180,7 @@ def test_linear_partials_specific_behaviour(core_mod, oracle):
     for p, c1, c2 in tree.ops():
         oc.calculate_partials(c1, c1 < tree.n, c2, 0 <= c2 < tree.n, p, 0)
     for node in (int(tree.parent[4]), tree.root):
-        np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=0.0)
+        np.testing.assert_allclose(c.get_node_partials(node), oc.get_node_partials(node), rtol=2e-12, atol=1e-318)
     # and the same zero-length branch through the distance fast path (no clamp either in linear mode)
     c2_ = _setup(core_mod, counts, tree, sf, PARAMS, mats, props, asc=True, use_log=False)
     nodes = np.array([i for i in range(tree.node_count) if i != tree.root], dtype=np.int32)
