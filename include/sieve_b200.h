@@ -58,6 +58,11 @@ enum {
                                         until sieve_destroy).  Saves 16 B per cell and site when the producer of the counts \
                                         (an ingest kernel, a generator) already wrote the core's layout */
 
+#define SIEVE_FLAG_PRIVATE_SEQ_COV 128u /* the coverage model is PrivateAllelicSeqCovModel (rawreadcountsmodel/seqcovmodel/        \
+                                        PrivateAllelicSeqCovModel.java): one (allelicSeqCov, allelicSeqCovRawVar) pair per (rate  \
+                                        category, pattern), set with sieve_set_private_seq_cov; the leaf partials then differ      \
+                                        between the categories (nrOfMatrices = K, 128 B per cell and site).  Dense resident cores. */
+
 typedef struct {
     int32_t n_leaves;     /* cells (taxa) */
     int32_t n_sites;      /* patterns of this shard */
@@ -164,6 +169,22 @@ int sieve_sf_solve(const sieve_sf_ops_t *ops, double *out_size_factors, double *
  * across processes (one process per GPU: torch.distributed / MPI / NCCL behind the callback; NULL for one process) */
 int sieve_sf_solve_parts(int32_t n_parts, sieve_sf_t *const *parts, sieve_sf_allreduce_fn allreduce, void *user,
                          double *out_size_factors, double *out_stats);
+
+/* ---- PrivateAllelicSeqCovModel (SIEVE_FLAG_PRIVATE_SEQ_COV) ------------------------------------------------------------
+ * allelicSeqCovPerPattern / allelicSeqCovRawVarPerPattern (PrivateAllelicSeqCovModel.java:16-17), both [K][n_sites] in the
+ * reference's index order matrixIndex * nrOfPatterns + patternIndex; they replace allelic_seq_cov / allelic_seq_cov_raw_var
+ * of sieve_leaf_params_t in the coverage term (computeSeqCovLikelihoodPerAllele, :499-511).  Takes effect at the next
+ * sieve_update_leaves.  The model initialises every pair with the shared start values (:159-161). */
+int sieve_set_private_seq_cov(sieve_core_t *h, const double *allelic_seq_cov_ks, const double *allelic_seq_cov_raw_var_ks);
+int sieve_get_private_seq_cov(sieve_core_t *h, double *allelic_seq_cov_ks, double *allelic_seq_cov_raw_var_ks);
+/* The accept-time re-estimation, PrivateAllelicSeqCovModel.updateAllelicSeqCovAndRawVar (:312-432) driven by
+ * ScsTreeLikelihood.postProcess (likelihood/ScsTreeLikelihood.java:2454-2520): for every (category, pattern) pair the
+ * maximum-likelihood numbers of sequenced alleles of the cells (from the max-sum trace of the current state, which this
+ * call runs) give new (t, v) by the grouped method of moments.  Pairs whose ML combination is not unique are left to the
+ * host (out_tied, [K][n_sites], may be NULL: 1 = tied, resolve with sieve_ml_get_site as for variant calling and write
+ * the pair back with sieve_set_private_seq_cov).  out_changed: number of pairs whose (t, v) moved.  The caller then
+ * recomputes the state (sieve_update_leaves + a whole-tree update), as postProcess does for the changed patterns. */
+int sieve_private_update_from_ml(sieve_core_t *h, int32_t zero_cov_mode, int32_t *out_changed, uint8_t *out_tied);
 
 /* new values of the six leaf-model parameters; takes effect at the next sieve_update_leaves */
 int sieve_set_leaf_params(sieve_core_t *h, const sieve_leaf_params_t *p);

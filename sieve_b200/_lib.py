@@ -11,6 +11,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sieve_b200.h")
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_STATE = 0, 1, 2, 3, 4
 FLAG_LOG_PARTIALS, FLAG_CONST_PARTIALS, FLAG_SINGLE_ADO, FLAG_EPHEMERAL, FLAG_SPARSE, FLAG_SINGLE_LEAF_BUFFER = 1, 2, 4, 8, 16, 32
 FLAG_EXTERNAL_COUNTS = 64
+FLAG_PRIVATE_SEQ_COV = 128
 UPDATE_FLIP, UPDATE_PER_LEVEL = 1, 2
 ASC_NONE, ASC_FELSENSTEIN_MEAN, ASC_FELSENSTEIN_GEOMETRIC, ASC_LEWIS = 0, 1, 2, 3
 ASC_MODES = {"none": 0, "felsenstein_mean": 1, "felsenstein_geometric": 2, "lewis": 3}
@@ -75,6 +76,9 @@ SIGNATURES = {
     "sieve_sf_weight_le": (C.c_int, [_vp, C.c_int32, _u64p, _i64p]),
     "sieve_sf_solve": (C.c_int, [C.POINTER(SfOps), _dp, _dp]),
     "sieve_sf_solve_parts": (C.c_int, [C.c_int32, C.POINTER(_vp), SF_ALLREDUCE_FN, _vp, _dp, _dp]),
+    "sieve_set_private_seq_cov": (C.c_int, [_vp, _dp, _dp]),
+    "sieve_get_private_seq_cov": (C.c_int, [_vp, _dp, _dp]),
+    "sieve_private_update_from_ml": (C.c_int, [_vp, C.c_int32, _ip, _vp]),
     "sieve_set_leaf_params": (C.c_int, [_vp, C.POINTER(LeafParams)]),
     "sieve_update_leaves": (C.c_int, [_vp, C.c_int32]),
     "sieve_set_node_matrix_for_update": (C.c_int, [_vp, C.c_int32]),

@@ -25,7 +25,7 @@ def _iptr(a):
 class ScsCudaLikelihoodCore:
     def __init__(self, n_leaves, n_sites, n_categories=4, n_states=4, use_log_partials=True, asc_bias=False,
                  single_ado=True, device=-1, ephemeral=False, sparse=False, single_leaf_buffer=False,
-                 external_counts=False):
+                 external_counts=False, private_seq_cov=False):
         """initialize(nodeCount = 2n, leafCount = n, internalCount = n, patternCount, matrixCount, stateCount, ...)
         (likelihood/ScsBeerLikelihoodCore.java:91-128)."""
         self.L = _lib.lib()
@@ -36,7 +36,8 @@ class ScsCudaLikelihoodCore:
         flags = (FLAG_LOG_PARTIALS if use_log_partials else 0) | (FLAG_CONST_PARTIALS if asc_bias else 0) | \
                 (FLAG_SINGLE_ADO if single_ado else 0) | (FLAG_EPHEMERAL if ephemeral else 0) | \
                 (FLAG_SPARSE if sparse else 0) | (_lib.FLAG_SINGLE_LEAF_BUFFER if single_leaf_buffer else 0) | \
-                (_lib.FLAG_EXTERNAL_COUNTS if external_counts else 0)
+                (_lib.FLAG_EXTERNAL_COUNTS if external_counts else 0) | \
+                (_lib.FLAG_PRIVATE_SEQ_COV if private_seq_cov else 0)
         cfg = _lib.Config(self.n, self.S, self.K, self.G, flags, device)
         h = C.c_void_p()
         check(self.L.sieve_create(C.byref(cfg), C.byref(h)))
@@ -92,6 +93,29 @@ class ScsCudaLikelihoodCore:
     def set_leaf_params(self, theta, t, v, eps, w1, w2):
         p = LeafParams(theta, t, v, eps, w1, w2)
         check(self.L.sieve_set_leaf_params(self.h, C.byref(p)))
+
+    # ---- PrivateAllelicSeqCovModel (rawreadcountsmodel/seqcovmodel/PrivateAllelicSeqCovModel.java) ----------------
+    def set_private_seq_cov(self, t_ks, v_ks):
+        """allelicSeqCovPerPattern / allelicSeqCovRawVarPerPattern, both [K][S] (index matrixIndex * nrOfPatterns + pattern)."""
+        t = np.ascontiguousarray(t_ks, dtype=np.float64)
+        v = np.ascontiguousarray(v_ks, dtype=np.float64)
+        assert t.shape == (self.K, self.S) and v.shape == (self.K, self.S)
+        check(self.L.sieve_set_private_seq_cov(self.h, _dptr(t), _dptr(v)))
+
+    def get_private_seq_cov(self):
+        t = np.empty((self.K, self.S))
+        v = np.empty((self.K, self.S))
+        check(self.L.sieve_get_private_seq_cov(self.h, _dptr(t), _dptr(v)))
+        return t, v
+
+    def private_update_from_ml(self, zero_cov_mode=0):
+        """updateAllelicSeqCovAndRawVar (:312-432) from the max-sum trace of the current state, as
+        ScsTreeLikelihood.postProcess does after an accepted move (likelihood/ScsTreeLikelihood.java:2454-2520).
+        -> (number of (category, pattern) pairs whose (t, v) moved, tied uint8 [K][S])"""
+        changed = C.c_int32()
+        tied = np.zeros((self.K, self.S), dtype=np.uint8)
+        check(self.L.sieve_private_update_from_ml(self.h, int(zero_cov_mode), C.byref(changed), tied.ctypes.data))
+        return int(changed.value), tied
 
     def update_leaves(self, for_update=True):
         check(self.L.sieve_update_leaves(self.h, int(bool(for_update))))

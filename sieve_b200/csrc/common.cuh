@@ -34,6 +34,7 @@ struct __align__(16) SvOp {
 #define SV_OP_PF2 1024
 #define SV_OP_FAR1 4096   // this op's own child 1 / child 2 is such an operand (used for the first D ops of a list,
 #define SV_OP_FAR2 8192   // which no earlier op could announce)
+#define SV_OP_RENORM 16384  // renormalise this op's result by a power of two (sv_bound_op decides; the root always does)
 #define SV_OP_NOSTORE 32  // the result is consumed from registers by the next op and never needed again: skip the writes
 
 // 256-bit global accesses (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): one (site, category) state vector.
@@ -69,6 +70,16 @@ __device__ __forceinline__ double sv_pow2_rescale_hi(int hi, double* shift_ln) {
     const int fe = normal ? 2046 - e : (sub ? 2045 : 1023);
     const int se = normal ? e - 1023 : (sub ? -1022 : 0);
     *shift_ln = (double)se * SV_LN2;  // zero / tiny subnormal / inf / NaN: left alone
+    return __hiloint2double(fe << 20, 0);
+}
+
+// the same with the exponent as an integer (the walk keeps a node's scale as an exact sum of binary exponents)
+__device__ __forceinline__ double sv_pow2_rescale_hi_int(int hi, int* e_out) {
+    const int e = (hi >> 20) & 0x7ff;
+    const bool normal = hi > 0 && (unsigned)(e - 1) < 2045u;
+    const bool sub = hi > 0 && e == 0;  // subnormal maximum with a non-zero high word (Double.MIN_VALUE clamps only)
+    const int fe = normal ? 2046 - e : (sub ? 2045 : 1023);
+    *e_out = normal ? e - 1023 : (sub ? -1022 : 0);  // zero / tiny subnormal / inf / NaN: left alone
     return __hiloint2double(fe << 20, 0);
 }
 

@@ -62,8 +62,8 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
         SV_TRY(sv_flush(h));
     }
     if (!h->ml_alloc) {
-        SV_TRY(sv_alloc(h, &h->d_mlL, n * S * 4));
-        SV_TRY(sv_alloc(h, &h->d_mlado, n * S));
+        SV_TRY(sv_alloc(h, &h->d_mlL, n * S * 4 * (h->private_cov ? K : 1)));
+        SV_TRY(sv_alloc(h, &h->d_mlado, n * S * (h->private_cov ? K : 1)));
         SV_TRY(sv_alloc(h, &h->d_ml, n * lanes * 4));
         SV_TRY(sv_alloc(h, &h->d_mlback, n * lanes));
         SV_TRY(sv_alloc(h, &h->d_mlcoll, N * lanes));
@@ -72,7 +72,7 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
         SV_TRY(sv_alloc(h, &h->d_mlcats, S));
         SV_TRY(sv_alloc(h, &h->d_mllogm, N * K * 16));
         SV_TRY(sv_alloc(h, &h->d_mlops, n));
-        SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
+        if (!h->private_cov) SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
         h->ml_alloc = true;
     }
     // log P on the host, in double precision with the reference's clamp (ScsBeerLikelihoodCore.java:3100-3101)
@@ -109,11 +109,32 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
         h->lp = pending;
         SV_TRY(rr);
     }
-    k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
-                                                                                                  (int)n, h->C, la.cp);
-    sv_count(h);
-    k_leaf_ml<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(la);
-    sv_count(h);
+    if (h->private_cov) {
+        if (!h->have_tv) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: sieve_set_private_seq_cov has not been called");
+        SvMlLeafPrivArgs pa;
+        pa.counts = h->d_counts;
+        pa.dmA = h->d_dmA;
+        pa.dmB = h->d_dmB;
+        pa.size_factors = h->d_sf;
+        pa.tv = h->d_tv;
+        pa.leafL = h->d_mlL;
+        pa.ado = h->d_mlado;
+        pa.n_cells = (int)n;
+        pa.S = (int)S;
+        pa.C = h->C;
+        pa.K = (int)K;
+        pa.al = la.al;
+        pa.theta = la.cp.theta;
+        pa.single_ado = la.cp.single_ado;
+        k_leaf_ml_private<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(pa);
+        sv_count(h);
+    } else {
+        k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
+                                                                                                      (int)n, h->C, la.cp);
+        sv_count(h);
+        k_leaf_ml<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(la);
+        sv_count(h);
+    }
 
     SvMlArgs a;
     a.ops = h->d_mlops;
@@ -130,6 +151,7 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
     a.K = (int)K;
     a.n_leaves = (int)n;
     a.root_genotype = h->root_genotype;
+    a.leaf_k = h->private_cov ? 1 : 0;
     const unsigned blocks = (unsigned)((lanes + 127) / 128);
     k_ml_up<<<blocks, 128, 0, h->stream>>>(a);
     sv_count(h);
@@ -200,19 +222,22 @@ extern "C" int sieve_ml_get_node(sieve_core_t* h, int32_t node, double* ml_parti
             for (size_t k = 0; k < K; k++) collection[k * S + s] = c[s * K + k];
     }
     if ((size_t)node < n) {
+        const size_t per = h->private_cov ? K : 1;  // per-category leaves under the private coverage model: [S][K]
         if (ml_partials) {
-            std::vector<double> v(S * 4);
-            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlL + (size_t)node * S * 4, S * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            SV_CUDA(cudaStreamSynchronize(h->stream));
-            for (size_t k = 0; k < K; k++) memcpy(ml_partials + k * S * 4, v.data(), S * 4 * sizeof(double));
-        }
-        if (back) {
-            std::vector<unsigned short> v(S);
-            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlado + (size_t)node * S, S * sizeof(unsigned short), cudaMemcpyDeviceToHost, h->stream));
+            std::vector<double> v(S * per * 4);
+            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlL + (size_t)node * S * per * 4, v.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             SV_CUDA(cudaStreamSynchronize(h->stream));
             for (size_t k = 0; k < K; k++)
                 for (size_t s = 0; s < S; s++)
-                    for (int g = 0; g < 4; g++) back[(k * S + s) * 4 + g] = (uint8_t)((v[s] >> (4 * g)) & 15u);
+                    memcpy(ml_partials + (k * S + s) * 4, v.data() + (per == 1 ? s : s * K + k) * 4, 4 * sizeof(double));
+        }
+        if (back) {
+            std::vector<unsigned short> v(S * per);
+            SV_CUDA(cudaMemcpyAsync(v.data(), h->d_mlado + (size_t)node * S * per, v.size() * sizeof(unsigned short), cudaMemcpyDeviceToHost, h->stream));
+            SV_CUDA(cudaStreamSynchronize(h->stream));
+            for (size_t k = 0; k < K; k++)
+                for (size_t s = 0; s < S; s++)
+                    for (int g = 0; g < 4; g++) back[(k * S + s) * 4 + g] = (uint8_t)((v[per == 1 ? s : s * K + k] >> (4 * g)) & 15u);
         }
         return SIEVE_OK;
     }
@@ -265,7 +290,7 @@ extern "C" int sieve_ml_get_site(sieve_core_t* h, int32_t site, uint8_t* back, d
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rows, rows.data(), N * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
         k_ml_site_gather<<<(N * K + 127) / 128, 128, 0, h->stream>>>(h->d_mlback, h->d_mlado, h->d_mlL, h->d_part, h->d_scale,
-                                                                   d_rows, h->S, K, n, N, site, d_b, d_p);
+                                                                   d_rows, h->S, K, n, N, site, h->private_cov ? 1 : 0, d_b, d_p);
         sv_count(h);
         e = cudaGetLastError();
     }
@@ -276,5 +301,48 @@ extern "C" int sieve_ml_get_site(sieve_core_t* h, int32_t site, uint8_t* back, d
     cudaFree(d_b);
     cudaFree(d_p);
     SV_CUDA(e);
+    return SIEVE_OK;
+}
+
+// ---- PrivateAllelicSeqCovModel: accept-time re-estimation (leaf_private.cuh, k_private_update) ----------------------
+extern "C" int sieve_private_update_from_ml(sieve_core_t* h, int32_t zero_cov_mode, int32_t* out_changed, uint8_t* out_tied) {
+    SV_REQUIRE(h && out_changed, "sieve_private_update_from_ml: null argument");
+    SV_REQUIRE(zero_cov_mode == 0 || zero_cov_mode == 1, "Illegal value for zeroCovMode. Only 0 or 1 is supported.");
+    if (!h->private_cov || !h->have_tv)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_private_update_from_ml: needs a SIEVE_FLAG_PRIVATE_SEQ_COV core with its (t, v) set");
+    SV_TRY(sieve_ml_trace(h));  // ScsTreeLikelihood.postProcess step 1 (:2454-2463)
+    const size_t S = h->S, K = h->K;
+    int* d_changed = nullptr;
+    unsigned char* d_tied = nullptr;
+    cudaError_t e = cudaMalloc(&d_changed, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tied, K * S);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_changed, 0, sizeof(int), h->stream);
+    int changed = 0;
+    if (e == cudaSuccess) {
+        SvPrivUpdArgs a;
+        a.counts = h->d_counts;
+        a.size_factors = h->d_sf;
+        a.ado_sel = h->d_mladosel;
+        a.ambiguous = h->d_mlamb;
+        a.tv = h->d_tv;
+        a.tied = d_tied;
+        a.changed = d_changed;
+        a.n_cells = h->n;
+        a.S = (int)S;
+        a.K = (int)K;
+        a.zero_cov_mode = zero_cov_mode;
+        a.single_ado = h->single_ado ? 1 : 0;
+        k_private_update<<<(unsigned)((S * K + 127) / 128), 128, 0, h->stream>>>(a);
+        sv_count(h);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && out_tied) e = cudaMemcpyAsync(out_tied, d_tied, K * S, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_changed);
+    cudaFree(d_tied);
+    SV_CUDA(e);
+    *out_changed = changed;
+    if (changed) h->ml_ready = false;  // the trace belongs to the old (t, v)
     return SIEVE_OK;
 }

@@ -66,6 +66,108 @@ static int sv_make_op(sieve_core* h, int c1, int c2, int parent, SvOp* op) {
     return SIEVE_OK;
 }
 
+// ---- where the walk renormalises -------------------------------------------------------------------------------------
+// Scaling by a power of two is exact and the exponents are summed as integers, so a partial may stay un-normalised for as
+// long as none of its 16 values per site can leave the normal range of a double.  The host bounds the magnitudes without
+// looking at the data:
+//   * a leaf partial has its largest value in [1, 2) (k_leaf normalises it), the others anywhere below;
+//   * y = P x with a stochastic matrix: every y[p] <= max x (rows sum to 1), every y[p] >= min P * max x, and
+//     max y >= min diag(P) * max x;
+//   * the product of the two children's contributions multiplies the bounds.
+// [2^lo, 2^hi) contains every entry of the node's value, 2^mlo is a lower bound of the largest one.  When the bounds
+// come near the limits of the exponent range the op renormalises (SV_OP_RENORM), and so do: the root (its log is taken:
+// the result must not depend on the schedule), a node below a zero-length branch in log mode (the Double.MIN_VALUE
+// entries of that matrix must meet normalised values, as the reference's arithmetic has it), every op of a core that
+// keeps the per-site constant-site twin (its values have no such bound).
+static inline int sv_badd(int a, int b) { return std::max(SV_BOUND_NONE, a + b); }
+static inline int sv_floor_log2(double x) {
+    if (!(x > 0.0) || !std::isfinite(x)) return SV_BOUND_NONE;
+    int e;
+    frexp(x, &e);
+    return e - 1;
+}
+
+// floor(log2) of the smallest entry / smallest diagonal entry of the K matrices just given to a slot (one less: slack for
+// the rounding of the device's sums)
+static void sv_slot_bounds(sieve_core* h, const PendingMatrix& pm) {
+    const int K = h->K;
+    const double* pv = h->pending_vals.data() + pm.off;
+    static const double P1[16] = {3, 6, -3, -6, 1, 2, -1, -2, -1, -2, 1, 2, -1, -2, 1, 2};     // 8 Pi1
+    static const double P2[16] = {9, -18, 3, 6, -3, 6, -1, -2, 1, -2, 11, -10, 1, -2, -5, 6};  // 16 Pi2
+    double mn = INFINITY, mnd = INFINITY;
+    for (int k = 0; k < K; k++)
+        for (int e = 0; e < 16; e++) {
+            double v;
+            if (pm.is_distance) {
+                const double d = pv[k];
+                const double g1 = expm1(-0.2 * d), g2 = expm1(-0.4 * d);
+                v = ((e % 5 == 0) ? 1.0 : 0.0) + (g1 / 8.0) * P1[e] + (g2 / 16.0) * P2[e];
+                if (d == 0.0) v = (e % 5 == 0) ? 1.0 : 0.0;
+            } else
+                v = pv[k * 16 + e];
+            if (h->log_mode) v = v > 0.0 ? v : SV_MIN_VALUE;
+            if (!(v > 0.0)) v = 0.0;
+            mn = std::min(mn, v);
+            if (e % 5 == 0) mnd = std::min(mnd, v);
+        }
+    // (the closed form above differs from the device's by rounding only; two binades of slack cover it)
+    const int b = sv_floor_log2(mn), bd = sv_floor_log2(mnd);
+    h->slot_b[pm.slot] = b == SV_BOUND_NONE ? b : b - 2;
+    h->slot_bd[pm.slot] = bd == SV_BOUND_NONE ? bd : bd - 2;
+}
+
+// bounds of the op's result from those of its operands; sets SV_OP_RENORM where needed and records the bounds of what
+// the node's current buffer will hold
+static void sv_bound_op(sieve_core* h, int parent, int c1, int c2, SvOp* op) {
+    const int n = h->n, N = h->n_nodes;
+    struct Bd {
+        int lo, hi, mlo;
+    };
+    auto side = [&](int c) {
+        Bd x;
+        if (c < n) {
+            x.lo = SV_BOUND_NONE;  // a genotype may be arbitrarily unlikely
+            x.hi = 1;
+            x.mlo = 0;
+        } else {
+            const size_t bi = (size_t)h->cur_part[c] * N + c;
+            x.lo = h->nb_lo[bi];
+            x.hi = h->nb_hi[bi];
+            x.mlo = h->nb_mlo[bi];
+        }
+        const size_t m = (size_t)h->cur_mat[c] * N + c;
+        const int b = h->slot_b[m], bd = h->slot_bd[m];
+        Bd y;
+        y.lo = std::max(x.lo, sv_badd(b, x.mlo));
+        y.hi = x.hi + 1;  // rows of P sum to 1 up to rounding
+        y.mlo = std::max(sv_badd(bd, x.mlo), y.lo);
+        return y;
+    };
+    Bd r = side(c1);
+    if (c2 >= 0) {
+        const Bd z = side(c2);
+        Bd t;
+        t.lo = sv_badd(r.lo, z.lo);
+        t.hi = r.hi + z.hi;
+        t.mlo = std::max(sv_badd(r.mlo, z.lo), sv_badd(z.mlo, r.lo));
+        r = t;
+    }
+    const size_t own_m = (size_t)h->cur_mat[parent] * N + parent;
+    const bool below_zero_branch = parent != h->root && h->log_mode && h->slot_zero[own_m];
+    const bool renorm = h->renorm_always || parent == h->root || (h->with_const && h->const_twin) || below_zero_branch ||
+                        r.lo < -900 || r.hi > 900;
+    if (renorm) {
+        op->flags |= SV_OP_RENORM;
+        r.lo = sv_badd(r.lo, -r.hi);  // the exponent taken out is at most hi
+        r.hi = 1;
+        r.mlo = 0;
+    }
+    const size_t bi = (size_t)h->cur_part[parent] * N + parent;
+    h->nb_lo[bi] = r.lo;
+    h->nb_hi[bi] = r.hi;
+    h->nb_mlo[bi] = r.mlo;
+}
+
 // ---- algebraic constant-site path: the site-independent factor ----------------------------------------------------
 // constPartial[v][k][s][p] = G_v[k][p] * prod_{leaves l below v} leaf_l[s][cg]   (induction over
 // ScsBeerLikelihoodCore.java:1432-1440 / :1467-1490: a leaf child contributes P[p][cg] * leaf[cg], an internal child
@@ -140,6 +242,9 @@ static void sv_update_G(sieve_core* h) {
     double sum = 0.0;
     for (int k = 0; k < K; k++) sum += h->prop[k] * gr[k * 4 + h->root_genotype];
     h->log_c = std::log(sum) + h->Gs[(size_t)h->cur_part[root] * N + root];
+    for (int k = 0; k < SV_KMAX; k++)  // per category, for the per-pattern coverage model (k_const_private)
+        h->logw[k] = k < K ? std::log(h->prop[k] * gr[k * 4 + h->root_genotype]) + h->Gs[(size_t)h->cur_part[root] * N + root]
+                           : -INFINITY;
 }
 
 // Resident-mode planner.  Input: the dirty nodes (dirty_list), nodes to materialise (demand_list), the parent -> children
@@ -396,6 +501,7 @@ static int sv_plan_resident_ops(sieve_core* h) {
         }
         SvOp op;
         SV_TRY(sv_make_op(h, h->eph_c1[v], h->eph_c2[v], v, &op));
+        sv_bound_op(h, v, h->eph_c1[v], h->eph_c2[v], &op);
         if (!store) op.flags |= SV_OP_NOSTORE;
         h->pending_ops.push_back(op);
         h->valid[v] = store ? 1 : 0;
@@ -566,6 +672,7 @@ static int sv_build_streamed_ops(sieve_core* h) {
             } else
                 child(b, SV_OP_LEAF2, &op.c2_row, &op.m2);
             if (v == root) op.flags |= SV_OP_ROOT;
+            sv_bound_op(h, v, a, b, &op);
             h->pending_ops.push_back(op);
             h->g_nodes.push_back(v);
             if (a >= n) free_slots.push_back(slot_of[a]);

@@ -56,7 +56,8 @@ struct sieve_core {
     // and, per leaf buffer, the per-site total that the root adds
     double *d_sumS = nullptr, *d_sum0 = nullptr;  // [cell groups][site]
     double* d_lsum = nullptr;                     // [leaf buffers][site]
-    double *d_part = nullptr, *d_scale = nullptr, *d_cpart = nullptr, *d_cscale = nullptr;  // [2][n_internal][S][K][4]
+    double *d_part = nullptr, *d_cpart = nullptr;  // [slot][S][K][4]
+    int *d_scale = nullptr, *d_cscale = nullptr;   // [slot][S] binary exponents
     double* d_mats = nullptr;                                                            // [2][n_nodes][4][16]
     double2* d_qfac = nullptr;                                                           // [2][n_nodes][4]
     std::vector<char> slot_is_q;  // per matrix slot: was it given as a distance?
@@ -100,7 +101,7 @@ struct sieve_core {
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
     bool force_generic = false;
-    int pf_dist = 4;  // SIEVE_B200_PF_DIST: how many ops ahead the walk asks the TMA unit to bring operands into L2 (0: off)
+    int pf_dist = 3;  // SIEVE_B200_PF_DIST: how many ops ahead the walk asks the TMA unit to bring operands into L2 (0: off)
     // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
     int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
     int n_slots = 0;     // scratch slots for internal partials
@@ -135,6 +136,13 @@ struct sieve_core {
             return c1 == o.c1 && c2 == o.c2 && p1 == o.p1 && p2 == o.p2 && m1 == o.m1 && m2 == o.m2;
         }
     };
+    // Magnitude bounds (sv_bound_op): for the value each (buffer, node) holds, every entry lies in [2^lo, 2^hi) and the
+    // largest is at least 2^mlo; per matrix slot floor(log2) of its smallest entry / smallest diagonal entry.  They decide
+    // where the walk renormalises (SV_OP_RENORM); SIEVE_B200_RENORM_ALWAYS=1 renormalises after every op (A/B, tests).
+    std::vector<int> nb_lo, nb_hi, nb_mlo;  // [2 * n_nodes]
+    std::vector<int> slot_b, slot_bd;       // [2 * n_nodes]
+    bool renorm_always = false;
+    bool use_k_prune = false;  // SIEVE_B200_WALK=0: never take the lean walk kernel (walk.cuh)
     bool elide = true;
     uint64_t ver_counter = 0, elided_total = 0;
     std::vector<uint64_t> mat_ver;      // [2 * n_nodes] per matrix slot
@@ -168,6 +176,14 @@ struct sieve_core {
     std::vector<uint64_t> ver_cur, ver_stored;  // [n_nodes] version of the node's value in the current / stored state
     std::vector<SvFp> fp_cur, fp_stored;        // ... and what it was computed from
 
+    // PrivateAllelicSeqCovModel (SIEVE_FLAG_PRIVATE_SEQ_COV, leaf_private.cuh): (t, v) per (category, site); the leaf pool
+    // then holds K x 4 values per (cell, site) and the constant-site column sums are kept per category
+    bool private_cov = false, have_tv = false;
+    double2* d_tv = nullptr;       // [KMAX][S]
+    double* d_lambdaK = nullptr;   // [leaf buffers][KMAX][S]
+    double* d_sum0K = nullptr;     // scratch [cell groups][KMAX][S]
+    double logw[SV_KMAX] = {0, 0, 0, 0}, logw_stored[SV_KMAX] = {0, 0, 0, 0};  // log(prop_k G_root[k][rg]) + scale of G_root
+
     // max-sum pass for variant calling (maxsum.cuh); its pools are allocated by the first sieve_ml_trace
     bool ml_alloc = false, ml_ready = false;
     double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr, *d_mlcellL = nullptr;
@@ -190,6 +206,7 @@ static inline void sv_count(sieve_core* h) {
     h->step_launches++;
 }
 
+#define SV_BOUND_NONE (-1000000)  // "no lower bound" of the magnitude bounds (core_planner.cuh, sv_bound_op)
 static const int SV_TABLE_CAP_DEFAULT = 4096;
 static const int SV_REDUCE_BLOCKS = 296;
 

@@ -269,14 +269,14 @@ __device__ __forceinline__ void sv_leaf_row256(const double* p, double (&v)[4]) 
 }
 
 // CT_GLOBAL: the cell table is in global memory (read through L1 with one 256-bit load per row: one sector per lane).
-template <bool COVERED, bool CT_GLOBAL>
-__device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restrict__ dmA, const double* __restrict__ dmB,
-                                             const double* __restrict__ cT, const int C, const double sf,
-                                             const SvLeafArgs& a, const bool want0, double (&x)[4], double& ls,
-                                             double& l0) {
+// The four Dirichlet-multinomial log-densities N0..N3 of one (cell, site) (genotypes 0/0, 1/1, 1/1', 0/1;
+// NucReadCountsModelFiniteMuDM.java:33-96) from the two LP tables; counts beyond the tables take the direct path.
+template <bool COVERED>
+__device__ __forceinline__ void sv_leaf_nuc_terms(const int4 c, const double* __restrict__ dmA, const double* __restrict__ dmB,
+                                                  const int C, const SvDmAlphas& al, double& N0, double& N1, double& N2,
+                                                  double& N3) {
     const int cov = c.w;
     const int ref = cov - (c.x + c.y + c.z);
-    double N0, N1, N2, N3;
     if (cov == 0) {
         // DirichletMultinomial.logDensity returns 1.0 for an empty site, log mode included (:29-30)
         N0 = N1 = N2 = N3 = 1.0;
@@ -293,7 +293,7 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
                 const double2 w = *reinterpret_cast<const double2*>(dmA + 4 * ci + 2);
                 o[0] = u.x; o[1] = u.y; o[2] = w.x; o[3] = w.y;
             } else {
-                const SvD4 r = sv_dm_partials_direct(ci, a.al);
+                const SvD4 r = sv_dm_partials_direct(ci, al);
                 o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
             }
         };
@@ -313,7 +313,7 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
             const double2 u = *reinterpret_cast<const double2*>(dmB + 2 * cov);
             B0 = u.x; B1 = u.y;
         } else {
-            const SvD2 r = sv_dm_totals_direct(cov, a.al);
+            const SvD2 r = sv_dm_totals_direct(cov, al);
             B0 = r.a; B1 = r.b;
         }
         N0 = B0 - s0;
@@ -321,6 +321,16 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
         N2 = B1 - s2;
         N3 = B1 - s3;
     }
+}
+
+template <bool COVERED, bool CT_GLOBAL>
+__device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restrict__ dmA, const double* __restrict__ dmB,
+                                             const double* __restrict__ cT, const int C, const double sf,
+                                             const SvLeafArgs& a, const bool want0, double (&x)[4], double& ls,
+                                             double& l0) {
+    const int cov = c.w;
+    double N0, N1, N2, N3;
+    sv_leaf_nuc_terms<COVERED>(c, dmA, dmB, C, a.al, N0, N1, N2, N3);
     double e[4];
     if (COVERED || (cov >= 0 && cov < C)) {
         if (CT_GLOBAL) {
@@ -354,6 +364,14 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
         x[2] = n1 * e[0] + 2.0 * n1 * e[1] + z;
         x[3] = n2 * e[0] + 2.0 * n1 * e[1] + z;
         ls = m + e[2];
+    }
+    {
+        // the largest of the four values into [1, 2) (exact power of two): the walk's magnitude bounds (core_planner.cuh,
+        // sv_bound_op) start from a normalised leaf
+        int e2;
+        const double f = sv_pow2_rescale_hi_int(sv_maxhi4(x), &e2);
+        x[0] *= f; x[1] *= f; x[2] *= f; x[3] *= f;
+        ls = fma((double)e2, SV_LN2, ls);
     }
     l0 = 0.0;
     if (want0) {

@@ -83,69 +83,16 @@ __device__ __forceinline__ unsigned sv_max_indices(const double* v, int n) {
     return mask;
 }
 
-__global__ void __launch_bounds__(128) k_leaf_ml(SvMlLeafArgs a) {
-    const int j = blockIdx.y;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.S) return;
-    const int C = a.C;
-    const int4 c = __ldg(a.counts + (size_t)j * a.S + s);
-    const int cov = c.w;
-    const int ref = cov - (c.x + c.y + c.z);
-    double N0, N1, N2, N3;  // nucleotide log-densities of 0/0, 1/1, 1/1', 0/1 (NucReadCountsModelFiniteMuDM.java:33-96)
-    if (cov == 0) {
-        N0 = N1 = N2 = N3 = 1.0;  // DirichletMultinomial.java:29-30
-    } else {
-        auto lpA = [&](int cval, double (&o)[4]) {
-            const int ci = cval < 0 ? 0 : cval;
-            if (ci == 0) {
-                o[0] = o[1] = o[2] = o[3] = 0.0;
-            } else if (ci < C) {
-                o[0] = __ldg(a.dmA + 4 * ci);
-                o[1] = __ldg(a.dmA + 4 * ci + 1);
-                o[2] = __ldg(a.dmA + 4 * ci + 2);
-                o[3] = __ldg(a.dmA + 4 * ci + 3);
-            } else {
-                const SvD4 r = sv_dm_partials_direct(ci, a.al);
-                o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
-            }
-        };
-        double T[4];
-        lpA(c.x, T);
-        double s0 = T[0], s1 = T[1], s2 = T[2], s3 = T[2];
-        lpA(c.y, T);
-        s0 += T[0]; s1 += T[0]; s2 += T[2]; s3 += T[3];
-        lpA(c.z, T);
-        s0 += T[0]; s1 += T[0]; s2 += T[3]; s3 += T[3];
-        lpA(ref, T);
-        s0 += T[1]; s1 += T[0]; s2 += T[3]; s3 += T[2];
-        double B0, B1;
-        if (cov > 0 && cov < C) {
-            B0 = __ldg(a.dmB + 2 * cov);
-            B1 = __ldg(a.dmB + 2 * cov + 1);
-        } else {
-            const SvD2 r = sv_dm_totals_direct(cov, a.al);
-            B0 = r.a; B1 = r.b;
-        }
-        N0 = B0 - s0; N1 = B0 - s1; N2 = B1 - s2; N3 = B1 - s3;
-    }
-    const double sf = a.size_factors[j];
-    const double lt = log(a.cp.theta), l1t = log(1 - a.cp.theta);
-    double nb0, nb1, nb2;
-    if (cov >= 0 && cov < C) {
-        double e[4];
-        sv_ld256_nc(a.cellL + ((size_t)j * C + cov) * 4, e);
-        nb0 = e[0]; nb1 = e[1]; nb2 = e[2];
-    } else {
-        nb2 = sv_seq_cov_log(cov, 2, sf, a.cp.t, a.cp.v);
-        nb1 = sv_seq_cov_log(cov, 1, sf, a.cp.t, a.cp.v);
-        nb0 = a.cp.single_ado ? 0.0 : sv_seq_cov_log(cov, 0, sf, a.cp.t, a.cp.v);
-    }
+// The dropout mixture of one (cell, site[, category]) in log space with the arg-max set of its components per genotype
+// (RawReadCountsModelFiniteMuDM.java:54-77, 121-260).  N0..N3: nucleotide log-densities of 0/0, 1/1, 1/1', 0/1;
+// nb0..nb2: log NB of the coverage for 0 / 1 / 2 sequenced alleles.  -> out[g], four nibbles of component masks.
+__device__ __forceinline__ unsigned sv_ml_leaf_mixture(double N0, double N1, double N2, double N3, double nb0, double nb1,
+                                                       double nb2, double lt, double l1t, int single_ado, double (&out)[4]) {
     const double n01 = sv_lse2(N0, N1);  // logSumExp{nuc[+0], nuc[+1]} of the heterozygous one-allele term
-    double out[4];
     unsigned masks = 0;
     double comp[3];
-    if (a.cp.single_ado) {
-        // RawReadCountsModelFiniteMuDM.java:137-141, 166-170, 195-199, 224-228: tmp[0] no dropout, tmp[1] one allele lost
+    if (single_ado) {
+        // :137-141, 166-170, 195-199, 224-228: tmp[0] no dropout, tmp[1] one allele lost
         const double nn[4] = {N0, N3, N1, N2};      // "no dropout" nucleotide term of genotype g
         const double na[4] = {N0, 0.0, N1, N1};     // "one allele left" term (g == 1 handled apart)
 #pragma unroll
@@ -171,8 +118,72 @@ __global__ void __launch_bounds__(128) k_leaf_ml(SvMlLeafArgs a) {
             masks |= sv_max_indices(comp, 3) << (4 * g);
         }
     }
+    return masks;
+}
+
+__global__ void __launch_bounds__(128) k_leaf_ml(SvMlLeafArgs a) {
+    const int j = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.S) return;
+    const int C = a.C;
+    const int4 c = __ldg(a.counts + (size_t)j * a.S + s);
+    const int cov = c.w;
+    double N0, N1, N2, N3;  // nucleotide log-densities of 0/0, 1/1, 1/1', 0/1 (NucReadCountsModelFiniteMuDM.java:33-96)
+    sv_leaf_nuc_terms<false>(c, a.dmA, a.dmB, C, a.al, N0, N1, N2, N3);
+    const double sf = a.size_factors[j];
+    const double lt = log(a.cp.theta), l1t = log(1 - a.cp.theta);
+    double nb0, nb1, nb2;
+    if (cov >= 0 && cov < C) {
+        double e[4];
+        sv_ld256_nc(a.cellL + ((size_t)j * C + cov) * 4, e);
+        nb0 = e[0]; nb1 = e[1]; nb2 = e[2];
+    } else {
+        nb2 = sv_seq_cov_log(cov, 2, sf, a.cp.t, a.cp.v);
+        nb1 = sv_seq_cov_log(cov, 1, sf, a.cp.t, a.cp.v);
+        nb0 = a.cp.single_ado ? 0.0 : sv_seq_cov_log(cov, 0, sf, a.cp.t, a.cp.v);
+    }
+    double out[4];
+    const unsigned masks = sv_ml_leaf_mixture(N0, N1, N2, N3, nb0, nb1, nb2, lt, l1t, a.cp.single_ado, out);
     sv_st256(a.leafL + ((size_t)j * a.S + s) * 4, out);
     a.ado[(size_t)j * a.S + s] = (unsigned short)masks;
+}
+
+// The same under the per-pattern coverage model (SIEVE_FLAG_PRIVATE_SEQ_COV, leaf_private.cuh): the coverage terms of
+// category k come from the (category, site) pair's own (t, v), evaluated directly; the leaves then differ between the
+// categories: leafL [cell][site][K][4], ado [cell][site][K].
+struct SvMlLeafPrivArgs {
+    const int4* counts;
+    const double *dmA, *dmB;
+    const double* size_factors;
+    const double2* tv;       // [K][S]
+    double* leafL;           // [cell][S][K][4]
+    unsigned short* ado;     // [cell][S][K]
+    int n_cells, S, C, K;
+    SvDmAlphas al;
+    double theta;
+    int single_ado;
+};
+__global__ void __launch_bounds__(128) k_leaf_ml_private(SvMlLeafPrivArgs a) {
+    const int j = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.S) return;
+    const int4 c = __ldg(a.counts + (size_t)j * a.S + s);
+    const int cov = c.w;
+    double N0, N1, N2, N3;
+    sv_leaf_nuc_terms<false>(c, a.dmA, a.dmB, a.C, a.al, N0, N1, N2, N3);
+    const double sf = a.size_factors[j];
+    const double lt = log(a.theta), l1t = log(1 - a.theta);
+    for (int k = 0; k < a.K; k++) {
+        const double2 p = a.tv[(size_t)k * a.S + s];
+        const double nb2 = sv_seq_cov_log(cov, 2, sf, p.x, p.y);
+        const double nb1 = sv_seq_cov_log(cov, 1, sf, p.x, p.y);
+        const double nb0 = a.single_ado ? 0.0 : sv_seq_cov_log(cov, 0, sf, p.x, p.y);
+        double out[4];
+        const unsigned masks = sv_ml_leaf_mixture(N0, N1, N2, N3, nb0, nb1, nb2, lt, l1t, a.single_ado, out);
+        const size_t at = ((size_t)j * a.S + s) * a.K + k;
+        sv_st256(a.leafL + at * 4, out);
+        a.ado[at] = (unsigned short)masks;
+    }
 }
 
 // ---- bottom-up: max-sum partials and back-pointers -------------------------------------------------------------
@@ -188,6 +199,7 @@ struct SvMlArgs {
     unsigned char* ado_sel; // [cell][S][K] union of the arg-max dropout components over the leaf's genotype set
     unsigned char* ambiguous;  // [S][K] 1 <=> more than one ML combination
     int S, K, n_leaves, root_genotype;
+    int leaf_k;             // 1: the leaves are per category (k_leaf_ml_private): leafL [cell][S][K][4], ado [cell][S][K]
 };
 
 // one child's side of ScsBeerLikelihoodCore.java:3100-3131: max over child genotypes of log P[p][c] + value[c], with
@@ -248,13 +260,13 @@ __global__ void __launch_bounds__(128) k_ml_up(SvMlArgs a) {
             __syncwarp();
         }
         if (op.flags & SV_OP_LEAF1)
-            sv_ld256_nc(a.leafL + ((size_t)op.c1 * a.S + s) * 4, v1);
+            sv_ld256_nc(a.leaf_k ? a.leafL + ((size_t)op.c1 * lanes + lane) * 4 : a.leafL + ((size_t)op.c1 * a.S + s) * 4, v1);
         else
             sv_ld256(a.ml + ((size_t)op.c1 * lanes + lane) * 4, v1);
         sv_ml_side(M1, v1, m1, b1);
         if (!(op.flags & SV_OP_UNARY)) {
             if (op.flags & SV_OP_LEAF2)
-                sv_ld256_nc(a.leafL + ((size_t)op.c2 * a.S + s) * 4, v2);
+                sv_ld256_nc(a.leaf_k ? a.leafL + ((size_t)op.c2 * lanes + lane) * 4 : a.leafL + ((size_t)op.c2 * a.S + s) * 4, v2);
             else
                 sv_ld256(a.ml + ((size_t)op.c2 * lanes + lane) * 4, v2);
             sv_ml_side(M2, v2, m2, b2);
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(128) k_ml_down(SvMlArgs a) {
             const unsigned g = side == 0 ? g1 : g2;
             if (is_leaf) {
                 a.coll[(size_t)c * lanes + lane] = (unsigned char)g;
-                const unsigned ad = a.ado[(size_t)c * a.S + s];
+                const unsigned ad = a.leaf_k ? a.ado[(size_t)c * lanes + lane] : a.ado[(size_t)c * a.S + s];
                 unsigned u = 0;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -369,8 +381,8 @@ __global__ void k_ml_call(const unsigned char* __restrict__ coll, const unsigned
 // back-pointer bytes (leaves: the dropout arg-max nibbles spread to bytes) and the node's sum-product log partial.
 __global__ void k_ml_site_gather(const unsigned* __restrict__ back, const unsigned short* __restrict__ ado,
                                  const double* __restrict__ leafL, const double* __restrict__ part,
-                                 const double* __restrict__ scale, const unsigned* __restrict__ part_row /*[node]*/,
-                                 int S, int K, int n_leaves, int n_nodes, int site,
+                                 const int* __restrict__ scale, const unsigned* __restrict__ part_row /*[node]*/,
+                                 int S, int K, int n_leaves, int n_nodes, int site, int leaf_k,
                                  unsigned char* __restrict__ out_back /*[node][K][4]*/,
                                  double* __restrict__ out_logp /*[node][K][4]*/) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,12 +391,13 @@ __global__ void k_ml_site_gather(const unsigned* __restrict__ back, const unsign
     const size_t lanes = (size_t)S * K, lane = (size_t)site * K + k;
     for (int g = 0; g < 4; g++) {
         if (node < n_leaves) {
-            out_back[(size_t)t * 4 + g] = (unsigned char)((ado[(size_t)node * S + site] >> (4 * g)) & 15u);
-            out_logp[(size_t)t * 4 + g] = leafL[((size_t)node * S + site) * 4 + g];
+            const size_t at = leaf_k ? (size_t)node * lanes + lane : (size_t)node * S + site;
+            out_back[(size_t)t * 4 + g] = (unsigned char)((ado[at] >> (4 * g)) & 15u);
+            out_logp[(size_t)t * 4 + g] = leafL[at * 4 + g];
         } else {
             out_back[(size_t)t * 4 + g] = (unsigned char)((back[(size_t)(node - n_leaves) * lanes + lane] >> (8 * g)) & 0xffu);
             const size_t row = (size_t)part_row[node] + site;
-            out_logp[(size_t)t * 4 + g] = log(part[(row * SV_KMAX + k) * 4 + g]) + scale[row];
+            out_logp[(size_t)t * 4 + g] = log(part[(row * SV_KMAX + k) * 4 + g]) + (double)scale[row] * SV_LN2;
         }
     }
 }

@@ -4,10 +4,12 @@
 // (likelihood/ScsBeerLikelihoodCore.java:1283-1501 / :857-1055), integratePartials (:153-218) and
 // calculateLogLikelihoods (:255-269).
 //
-// Arithmetic: scaled linear space.  A node's partial for (site, category k) is 4 doubles x[g] and ONE natural-log
-// scale per (node, site) shared by all categories and states: true value = x[g] * exp(lscale).  After every product the
-// 16 values of a site are renormalised by an exact power of two (sv_pow2_rescale), so no transcendental is evaluated
-// until the root's log.  The reference's log-space result is reproduced to rounding (~1e-16 relative on the
+// Arithmetic: scaled linear space.  A node's partial for (site, category k) is 4 doubles x[g] and ONE binary exponent
+// per (node, site) shared by all categories and states: true value = x[g] * 2^e * exp(sum of the leaves' scales below).
+// The 16 values of a site are renormalised by an exact power of two (sv_pow2_rescale_hi_int) only where the host's bound
+// on their magnitude asks for it (SV_OP_RENORM, core_planner.cuh sv_bound_op): scaling by 2^k is exact and the exponents
+// are summed as integers, so WHEN the renormalisation happens cannot change a bit of the result; the root always
+// renormalises.  No transcendental is evaluated until the root's log.  The reference's log-space result is reproduced to rounding (~1e-16 relative on the
 // likelihood); its clamp log(P > 0 ? P : Double.MIN_VALUE) (:1430) is mirrored by clamping the matrices when they are
 // staged (SIEVE_FLAG_LOG_PARTIALS), its linear-mode clamp of the constant-site product (:1041-1047) likewise.
 //
@@ -23,9 +25,9 @@
 
 struct SvPruneArgs {
     double* part;          // [slots][S][4][4]   (category stride is always 4; lanes k >= K idle)
-    double* scale;         // [slots][S]
+    int* scale;            // [slots][S] binary exponent of the slot's values
     double* cpart;         // constant-site twins (NULL when not maintained)
-    double* cscale;
+    int* cscale;
     const double* leafX;   // [leaf slots][S][4]; the leaves' log scales are not stored per leaf (leaf.cuh) ...
     const double* lsum;    // ... their sum over all cells, per site of the shard (+ out_offset): added at the root
     const double* mats;    // [matrix slots][4][16], already clamped when SIEVE_FLAG_LOG_PARTIALS
@@ -159,7 +161,9 @@ __device__ __forceinline__ void sv_col0_q(const double2 q, const double (&x)[NS]
 // QFAST: every matrix of the launch was given as a branch distance (sieve_set_distances): no shared memory at all.
 // MINB: resident blocks per SM asked of the compiler; 0 = the default of the variant (SIEVE_B200_PRUNE_MINB instantiates
 // the variant-only Q walk at 7 and 8 for comparison).
-template <bool WITH_CONST, bool GENO0, bool QFAST, int MINB = 0>
+// LEAFK: the leaf pool holds K x 4 values per (cell, site) (SIEVE_FLAG_PRIVATE_SEQ_COV, leaf_private.cuh) in the layout
+// of an internal partial; a leaf child is then read like one, without a scale.
+template <bool WITH_CONST, bool GENO0, bool QFAST, int MINB = 0, bool LEAFK = false>
 __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? MINB
                                                                         : QFAST ? (WITH_CONST ? SV_PRUNE_MINB_CONST_Q : SV_PRUNE_MINB_Q)
                                                                                 : (WITH_CONST ? SV_PRUNE_MINB_CONST : SV_PRUNE_MINB)))
@@ -204,10 +208,11 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
     }
     // The previous op's result stays in registers (x / cx with scales xs / cxs): the host orders the children so that
     // a consumer of it has it as child 1 (SV_OP_FWD1).
-    double x[NS][4], cx[NS][4], xs[NS], cxs[NS];
+    double x[NS][4], cx[NS][4];
+    int xs[NS], cxs[NS];  // binary exponents of x / cx
 #pragma unroll
     for (int j = 0; j < NS; j++) {
-        xs[j] = cxs[j] = 0.0;
+        xs[j] = cxs[j] = 0;
 #pragma unroll
         for (int g = 0; g < 4; g++) x[j][g] = cx[j][g] = 0.0;
     }
@@ -270,11 +275,11 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
             if (!unary) q2 = __ldg(a.qfac + (size_t)m2 * SV_KMAX + k);
         } else if (!(st_which == 1 && unary))
             sv_ld256_nc(a.mats + (size_t)(st_which ? m2 : m1) * (SV_KMAX * 16) + st_off, m);
-        double w[NS][4], ws[NS];      // child 2
-        double cw[NS][4], cws[NS];    // child 2, constant-site twin
+        double w[NS][4], cw[NS][4];   // child 2 and its constant-site twin
+        int ws[NS], cws[NS];
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-            ws[j] = cws[j] = 0.0;
+            ws[j] = cws[j] = 0;
 #pragma unroll
             for (int g = 0; g < 4; g++) w[j][g] = cw[j][g] = 0.0;
         }
@@ -283,8 +288,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
             const size_t c1_row = c1_base + srow[j], c2_row = c2_base + srow[j];  // 32-bit sums, widened once
             if (!(flags & SV_OP_FWD1)) {
                 if (leaf1) {
-                    sv_ld256_nc(a.leafX + c1_row * 4, x[j]);
-                    xs[j] = 0.0;
+                    sv_ld256_nc(LEAFK ? a.leafX + c1_row * 16 + k * 4 : a.leafX + c1_row * 4, x[j]);
+                    xs[j] = 0;
                 } else {
                     sv_ld256(a.part + c1_row * 16 + k * 4, x[j]);
                     xs[j] = a.scale[c1_row];
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
             }
             if (!unary) {
                 if (leaf2) {
-                    sv_ld256_nc(a.leafX + c2_row * 4, w[j]);
+                    sv_ld256_nc(LEAFK ? a.leafX + c2_row * 16 + k * 4 : a.leafX + c2_row * 4, w[j]);
                 } else {
                     sv_ld256(a.part + c2_row * 16 + k * 4, w[j]);
                     ws[j] = a.scale[c2_row];
@@ -328,9 +333,9 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         }
         // ================= constant-site partials =================
         double cy[NS][4];
-        double cls[NS];
+        int cls[NS];
 #pragma unroll
-        for (int j = 0; j < NS; j++) cls[j] = 0.0;
+        for (int j = 0; j < NS; j++) cls[j] = 0;
         if (WITH_CONST) {
             if (leaf1 && QFAST) {
                 sv_col0_q<NS>(q1, x, cy, cz0);
@@ -383,26 +388,41 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
                     for (int p = 0; p < 4; p++) cy[j][p] = cy[j][p] > 0.0 ? cy[j][p] : SV_MIN_VALUE;
             }
         }
-        // ---- renormalise each site's 4 x 4 values by a power of two (integer max over the high words) ----
+        // ---- the result's exponent; where the host asks for it, renormalise each site's 4 x 4 values by a power of two
+        //      (integer max over the high words) ----
+        if (flags & SV_OP_RENORM) {
 #pragma unroll
-        for (int j = 0; j < NS; j++) {
-            int hi = sv_maxhi4(y[j]);
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
-            double sh;
-            const double f = sv_pow2_rescale_hi(hi, &sh);
+            for (int j = 0; j < NS; j++) {
+                int hi = sv_maxhi4(y[j]);
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
+                int sh;
+                const double f = sv_pow2_rescale_hi_int(hi, &sh);
 #pragma unroll
-            for (int p = 0; p < 4; p++) x[j][p] = y[j][p] * f;
-            xs[j] = (xs[j] + ws[j]) + sh;
-            if (WITH_CONST) {
-                int chi = sv_maxhi4(cy[j]);
-                chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
-                chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
-                double csh;
-                const double cf = sv_pow2_rescale_hi(chi, &csh);
+                for (int p = 0; p < 4; p++) x[j][p] = y[j][p] * f;
+                xs[j] = (xs[j] + ws[j]) + sh;
+                if (WITH_CONST) {
+                    int chi = sv_maxhi4(cy[j]);
+                    chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
+                    chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
+                    int csh;
+                    const double cf = sv_pow2_rescale_hi_int(chi, &csh);
 #pragma unroll
-                for (int p = 0; p < 4; p++) cx[j][p] = cy[j][p] * cf;
-                cxs[j] = cls[j] + csh;
+                    for (int p = 0; p < 4; p++) cx[j][p] = cy[j][p] * cf;
+                    cxs[j] = cls[j] + csh;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+#pragma unroll
+                for (int p = 0; p < 4; p++) x[j][p] = y[j][p];
+                xs[j] = xs[j] + ws[j];
+                if (WITH_CONST) {
+#pragma unroll
+                    for (int p = 0; p < 4; p++) cx[j][p] = cy[j][p];
+                    cxs[j] = cls[j];
+                }
             }
         }
 #pragma unroll
@@ -429,12 +449,12 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 // the scales of ALL leaves, which the walk never carried, come in here
                 const double lsum = site_ok[j] ? __ldg(a.lsum + a.out_offset + site0 + 8 * j) : 0.0;
-                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + (xs[j] + lsum);
+                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + fma((double)xs[j], SV_LN2, lsum);
                 if (WITH_CONST) {
                     double cv = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? cx[j][0] : sv_sel(cx[j], rg));
                     cv += __shfl_xor_sync(0xffffffffu, cv, 1);
                     cv += __shfl_xor_sync(0xffffffffu, cv, 2);
-                    if (site_ok[j] && klane == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + (cxs[j] + lsum);
+                    if (site_ok[j] && klane == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + fma((double)cxs[j], SV_LN2, lsum);
                 }
             }
         }
@@ -442,18 +462,29 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
 }
 
 // ---- BeerLikelihoodCore.getNodePartials in the reference layout [K][S][G] ------------------------------------------
-// scale: the node's own (power-of-two) scale, NULL for a leaf; lsum: the sum of the scales of the leaves below the node
-__global__ void k_export_partials(const double* __restrict__ x, const double* __restrict__ scale,
+// scale: the node's own binary exponents, NULL for a leaf; lsum: the sum of the scales of the leaves below the node.
+// One thread per site: the site's K x 4 values are renormalised here, so that the exported bits do not depend on where
+// the walk happened to renormalise (which differs between the dense, sparse and streamed schedules).
+__global__ void k_export_partials(const double* __restrict__ x, const int* __restrict__ scale,
                                   const double* __restrict__ lsum, int S, int K, int is_leaf, int as_log,
                                   int clamp_min, double* __restrict__ out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over K * S * 4
-    if (idx >= K * S * 4) return;
-    const int g = idx & 3;
-    const int s = (idx >> 2) % S;
-    const int k = (idx >> 2) / S;
-    const double v = is_leaf ? x[(size_t)s * 4 + g] : x[((size_t)s * SV_KMAX + k) * 4 + g];
-    const double ls = (scale ? scale[s] : 0.0) + lsum[s];
-    const double lin = v * exp(ls);
-    // clamp_min: linear-mode constant-site partials, clamped like ScsBeerLikelihoodCore.java:1041-1047
-    out[idx] = as_log ? log(v) + ls : (clamp_min && !(lin > 0.0) ? SV_MIN_VALUE : lin);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double v[SV_KMAX][4];
+    int hi = 0;
+    for (int k = 0; k < K; k++)
+        for (int g = 0; g < 4; g++) {
+            v[k][g] = is_leaf ? x[(size_t)s * 4 + g] : x[((size_t)s * SV_KMAX + k) * 4 + g];
+            hi = max(hi, __double2hiint(v[k][g]));
+        }
+    int e;
+    const double f = sv_pow2_rescale_hi_int(hi, &e);
+    const double ls = fma((double)((scale ? scale[s] : 0) + e), SV_LN2, lsum[s]);
+    for (int k = 0; k < K; k++)
+        for (int g = 0; g < 4; g++) {
+            const double vn = v[k][g] * f;
+            const double lin = vn * exp(ls);
+            // clamp_min: linear-mode constant-site partials, clamped like ScsBeerLikelihoodCore.java:1041-1047
+            out[((size_t)k * S + s) * 4 + g] = as_log ? log(vn) + ls : (clamp_min && !(lin > 0.0) ? SV_MIN_VALUE : lin);
+        }
 }

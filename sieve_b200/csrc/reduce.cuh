@@ -142,13 +142,15 @@ __global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ sumS,
 // Constant-site partials of one node in the reference layout [K][S][G], rebuilt from the factorisation for
 // BeerLikelihoodCore-style read-back: out = G[k][g] * exp(gscale) * prod over the node's leaves of their constant-
 // genotype likelihood (lam = the column sum over exactly those leaves).
-__global__ void k_export_const(const double* __restrict__ lam, const double* __restrict__ G /*[4][4]*/, double gscale,
-                               int S, int K, int as_log, double* __restrict__ out) {
+// lam_stride_k: 0 when the column sum is the same for every category, else the distance between the categories' sums
+// (per-pattern coverage model, leaf_private.cuh).
+__global__ void k_export_const(const double* __restrict__ lam, long long lam_stride_k, const double* __restrict__ G /*[4][4]*/,
+                               double gscale, int S, int K, int as_log, double* __restrict__ out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const double l = lam[s];
     for (int k = 0; k < K; k++)
         for (int g = 0; g < 4; g++) {
+            const double l = lam[(size_t)k * lam_stride_k + s];
             const double v = log(G[k * 4 + g]) + gscale + l;
             // linear mode: the reference clamps a constant-site product that underflowed to Double.MIN_VALUE
             // (ScsBeerLikelihoodCore.java:1041-1047); the read-back shows the same

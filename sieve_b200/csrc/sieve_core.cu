@@ -14,7 +14,9 @@
 #include "../../include/sieve_b200.h"
 #include "common.cuh"
 #include "leaf.cuh"
+#include "leaf_private.cuh"
 #include "prune.cuh"
+#include "walk.cuh"
 #include "reduce.cuh"
 #include "maxsum.cuh"
 #include "sizefactors.cuh"
@@ -107,6 +109,12 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         part_slots = h->n_slots;
         leaf_bufs = 1;
     }
+    h->private_cov = cfg->flags & SIEVE_FLAG_PRIVATE_SEQ_COV;
+    if (h->private_cov && ((cfg->flags & (SIEVE_FLAG_EPHEMERAL | SIEVE_FLAG_SPARSE | SIEVE_FLAG_SINGLE_LEAF_BUFFER)) || twin)) {
+        g_err = "sieve_create: SIEVE_FLAG_PRIVATE_SEQ_COV needs a dense resident core (no streamed / sparse / single-leaf-buffer mode, no per-site constant twin)";
+        return fail(SIEVE_ERR_INVALID);
+    }
+    const size_t leaf_vals = h->private_cov ? SV_KMAX * 4 : 4;  // doubles per (cell, site) in the leaf pool
     h->sparse = (cfg->flags & SIEVE_FLAG_SPARSE) && !h->ephemeral;
     h->single_leaf = (cfg->flags & SIEVE_FLAG_SINGLE_LEAF_BUFFER) && !h->ephemeral;
     if (h->single_leaf) leaf_bufs = 1;
@@ -115,7 +123,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         size_t free0 = 0, total0 = 0;
         cudaMemGetInfo(&free0, &total0);
         const size_t fixed = ((cfg->flags & SIEVE_FLAG_EXTERNAL_COUNTS) ? 0 : n * S * 16) + leaf_bufs * n * S * 32 + ((n + 31) / 32) * S * 16 + ((size_t)3 << 30);
-        const size_t per_slot = S * (SV_KMAX * 32 + 8) * (twin ? 2 : 1);
+        const size_t per_slot = S * (SV_KMAX * 32 + 4) * (twin ? 2 : 1);
         size_t slots = free0 > fixed ? (free0 - fixed) / per_slot : 0;
         if (const char* e = getenv("SIEVE_B200_POOL_SLOTS")) slots = (size_t)std::max(0, atoi(e));
         slots = std::min<size_t>(slots, 2 * n);
@@ -146,8 +154,8 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         return fail(SIEVE_ERR_OOM);
     }
     // does the residency fit?
-    size_t need = ((cfg->flags & SIEVE_FLAG_EXTERNAL_COUNTS) ? 0 : n * S * 16) + leaf_bufs * n * pool_sites * 32 + ((n + 31) / 32) * pool_sites * 16 +
-                  part_slots * pool_sites * (SV_KMAX * 32 + 8) * (twin ? 2 : 1) + ((size_t)64 << 20);
+    size_t need = ((cfg->flags & SIEVE_FLAG_EXTERNAL_COUNTS) ? 0 : n * S * 16) + leaf_bufs * n * pool_sites * 8 * leaf_vals + ((n + 31) / 32) * pool_sites * 16 +
+                  part_slots * pool_sites * (SV_KMAX * 32 + 4) * (twin ? 2 : 1) + ((size_t)64 << 20);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (need > free_b) {
@@ -167,7 +175,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     else
         CR(sv_alloc(h, &h->d_counts, n * S));
     CR(sv_alloc(h, &h->d_sf, n));
-    CR(sv_alloc(h, &h->d_leafX, leaf_bufs * n * pool_sites * 4));
+    CR(sv_alloc(h, &h->d_leafX, leaf_bufs * n * pool_sites * leaf_vals));
     const size_t leaf_groups = (n + SV_LEAF_CELLS - 1) / SV_LEAF_CELLS;
     CR(sv_alloc(h, &h->d_sumS, leaf_groups * pool_sites));
     CR(sv_alloc(h, &h->d_lsum, 2 * S));
@@ -176,6 +184,14 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     if (twin) {
         CR(sv_alloc(h, &h->d_cpart, part_slots * pool_sites * SV_KMAX * 4));
         CR(sv_alloc(h, &h->d_cscale, part_slots * pool_sites));
+    }
+    if (h->private_cov) {
+        CR(sv_alloc(h, &h->d_tv, (size_t)SV_KMAX * S));
+        if (algebraic) {
+            CR(sv_alloc(h, &h->d_sum0K, leaf_groups * SV_KMAX * pool_sites));
+            CR(sv_alloc(h, &h->d_lambdaK, (size_t)2 * SV_KMAX * S));
+        }
+        h->pf_dist = 0;  // the prefetch annotations assume 32-byte leaf rows
     }
     if (algebraic) {
         CR(sv_alloc(h, &h->d_sum0, leaf_groups * pool_sites));
@@ -199,6 +215,13 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     h->fp_cur.assign(h->n_nodes, sieve_core::SvFp());
     h->fp_stored.assign(h->n_nodes, sieve_core::SvFp());
     if (const char* e = getenv("SIEVE_B200_ELIDE")) h->elide = atoi(e) != 0;
+    h->nb_lo.assign((size_t)2 * h->n_nodes, 0);
+    h->nb_hi.assign((size_t)2 * h->n_nodes, 1);
+    h->nb_mlo.assign((size_t)2 * h->n_nodes, 0);
+    h->slot_b.assign((size_t)2 * h->n_nodes, SV_BOUND_NONE);
+    h->slot_bd.assign((size_t)2 * h->n_nodes, SV_BOUND_NONE);
+    if (const char* e = getenv("SIEVE_B200_RENORM_ALWAYS")) h->renorm_always = atoi(e) != 0;
+    if (const char* e = getenv("SIEVE_B200_WALK")) h->use_k_prune = atoi(e) == 0;  // 0: the general kernel for everything (A/B, tests)
     h->slot_is_q.assign((size_t)2 * h->n_nodes, 0);
     h->slot_zero.assign((size_t)2 * h->n_nodes, 0);
     CR(sv_alloc(h, &h->d_site_logl, S));
@@ -238,6 +261,9 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_scale);
     cudaFree(h->d_cpart);
     cudaFree(h->d_lambda);
+    cudaFree(h->d_tv);
+    cudaFree(h->d_lambdaK);
+    cudaFree(h->d_sum0K);
     cudaFree(h->d_cscale);
     cudaFree(h->d_mats);
     cudaFree(h->d_qfac);
@@ -579,6 +605,41 @@ extern "C" int sieve_sf_solve_parts(int32_t n_parts, sieve_sf_t* const* parts, s
     return sv_sf_solve(&ops, out_sf, out_stats);
 }
 
+// ---- PrivateAllelicSeqCovModel: (t, v) per (category, site) -----------------------------------------------------------
+extern "C" int sieve_set_private_seq_cov(sieve_core_t* h, const double* t_ks, const double* v_ks) {
+    SV_REQUIRE(h && t_ks && v_ks, "sieve_set_private_seq_cov: null argument");
+    if (!h->private_cov) return sv_fail(SIEVE_ERR_STATE, "sieve_set_private_seq_cov: the core was not created with SIEVE_FLAG_PRIVATE_SEQ_COV");
+    SV_CUDA(cudaSetDevice(h->device));
+    const size_t S = h->S;
+    std::vector<double2> tv((size_t)SV_KMAX * S, make_double2(1.0, 1.0));
+    for (int k = 0; k < h->K; k++)
+        for (size_t s = 0; s < S; s++) {
+            const double t = t_ks[(size_t)k * S + s], v = v_ks[(size_t)k * S + s];
+            if (!(t >= 0.0) || !(v >= 0.0))
+                return sv_fail(SIEVE_ERR_INVALID, "sieve_set_private_seq_cov: allelicSeqCov and allelicSeqCovRawVar must not be negative");
+            tv[(size_t)k * S + s] = make_double2(t, v);
+        }
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    SV_CUDA(cudaMemcpy(h->d_tv, tv.data(), tv.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    h->have_tv = true;
+    return SIEVE_OK;
+}
+extern "C" int sieve_get_private_seq_cov(sieve_core_t* h, double* t_ks, double* v_ks) {
+    SV_REQUIRE(h && t_ks && v_ks, "sieve_get_private_seq_cov: null argument");
+    if (!h->private_cov || !h->have_tv) return sv_fail(SIEVE_ERR_STATE, "sieve_get_private_seq_cov: no per-pattern coverage parameters set");
+    SV_CUDA(cudaSetDevice(h->device));
+    const size_t S = h->S;
+    std::vector<double2> tv((size_t)SV_KMAX * S);
+    SV_CUDA(cudaStreamSynchronize(h->stream));
+    SV_CUDA(cudaMemcpy(tv.data(), h->d_tv, tv.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < h->K; k++)
+        for (size_t s = 0; s < S; s++) {
+            t_ks[(size_t)k * S + s] = tv[(size_t)k * S + s].x;
+            v_ks[(size_t)k * S + s] = tv[(size_t)k * S + s].y;
+        }
+    return SIEVE_OK;
+}
+
 // ---- leaves ---------------------------------------------------------------------------------------------------
 extern "C" int sieve_set_leaf_params(sieve_core_t* h, const sieve_leaf_params_t* p) {
     SV_REQUIRE(h && p, "null argument");
@@ -610,6 +671,7 @@ static int sv_refresh_leaf_tables(sieve_core* h, SvDmAlphas* al_out, SvCovParams
         sv_count(h);
         h->dm_dirty = false;
     }
+    if (h->cov_dirty && h->private_cov) h->cov_dirty = false;  // the coverage terms are evaluated directly (leaf_private.cuh)
     if (h->cov_dirty) {
         dim3 g((C + 127) / 128, h->n);
         k_build_cell_tables<<<g, 128, 0, h->stream>>>(h->d_cellT, h->d_sf, h->n, C, cp);
@@ -678,9 +740,58 @@ static int sv_launch_leaf_kernels(sieve_core* h, long long site_begin, int n_sit
     return SIEVE_OK;
 }
 
+// the same for a core with the per-pattern coverage model: k_leaf_private + k_colsum_private; lambdaK_out is [KMAX][lambda_stride]
+static int sv_launch_leaf_private(sieve_core* h, double* leafXK, const int* d_cell_list, int n_entries, double* sumS,
+                                  double* sum0K, double* lsum_out, double* lambdaK_out, long long lambda_stride) {
+    if (!h->have_tv) return sv_fail(SIEVE_ERR_STATE, "sieve_set_private_seq_cov must be called before the leaves are computed");
+    SvLeafPrivArgs a;
+    SvCovParams cp_unused;
+    SV_TRY(sv_refresh_leaf_tables(h, &a.al, &cp_unused));
+    a.counts = h->d_counts;
+    a.dmA = h->d_dmA;
+    a.dmB = h->d_dmB;
+    a.size_factors = h->d_sf;
+    a.cell_list = d_cell_list;
+    a.tv = h->d_tv;
+    a.leafXK = leafXK;
+    a.sumS = sumS;
+    a.sum0 = lambdaK_out ? sum0K : nullptr;
+    a.const_genotype = h->const_genotype;
+    a.n_cells = n_entries;
+    a.S = h->S;
+    a.C = h->C;
+    a.K = h->K;
+    a.counts_stride = h->S;
+    a.site_begin = 0;
+    a.out_stride = h->S;
+    a.sum_stride = h->S;
+    a.tv_stride = h->S;
+    a.theta = h->lp.ado_rate;
+    a.single_ado = h->single_ado ? 1 : 0;
+    const int groups = (n_entries + SV_LEAF_CELLS - 1) / SV_LEAF_CELLS;
+    const size_t smem = (size_t)h->C * 6 * sizeof(double) <= 96 * 1024 ? (size_t)h->C * 6 * sizeof(double) : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SV_CUDA(cudaFuncSetAttribute(k_leaf_private, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((h->S + SV_LEAFP_THREADS - 1) / SV_LEAFP_THREADS, groups);
+    k_leaf_private<<<grid, SV_LEAFP_THREADS, smem, h->stream>>>(a);
+    sv_count(h);
+    k_colsum_private<<<(h->S + 255) / 256, 256, 0, h->stream>>>(sumS, a.sum0, groups, h->S, h->K, h->S, lsum_out, lambdaK_out,
+                                                               lambda_stride);
+    sv_count(h);
+    SV_CUDA(cudaGetLastError());
+    return SIEVE_OK;
+}
+
 // site_begin / n_sites: the range of the shard to evaluate; out_stride: site capacity of the leaf pool it goes to
 static int sv_launch_leaves(sieve_core* h, long long site_begin, int n_sites, long long out_stride) {
     const bool algebraic = h->with_const && !h->const_twin;
+    if (h->private_cov)
+        return sv_launch_leaf_private(h, h->d_leafX + (size_t)h->cur_leaf * h->n * h->S * SV_KMAX * 4, nullptr, h->n, h->d_sumS,
+                                      h->d_sum0K, h->d_lsum + (size_t)h->cur_leaf * h->S,
+                                      algebraic ? h->d_lambdaK + (size_t)h->cur_leaf * SV_KMAX * h->S : nullptr, h->S);
     // the per-site sums: streamed mode indexes them by the shard's site, resident mode per leaf buffer
     const long long sum_at = h->ephemeral ? site_begin : (long long)h->cur_leaf * h->S;
     return sv_launch_leaf_kernels(h, site_begin, n_sites, out_stride,
@@ -711,7 +822,7 @@ static int sv_subtree_leaf_sums(sieve_core* h, int node, double* d_ls, double* d
     int* d_list = nullptr;
     double* d_sums = nullptr;
     cudaError_t e = cudaMalloc(&d_list, sizeof(int) * leaves.size());
-    if (e == cudaSuccess) e = cudaMalloc(&d_sums, sizeof(double) * 2 * groups * S);
+    if (e == cudaSuccess) e = cudaMalloc(&d_sums, sizeof(double) * (1 + (h->private_cov ? SV_KMAX : 1)) * groups * S);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_list, leaves.data(), sizeof(int) * leaves.size(), cudaMemcpyHostToDevice, h->stream);
     int r = SIEVE_OK;
@@ -720,8 +831,11 @@ static int sv_subtree_leaf_sums(sieve_core* h, int node, double* d_ls, double* d
         // computed with, not with parameters set since (sieve_set_leaf_params without sieve_update_leaves)
         const sieve_leaf_params_t pending = h->lp;
         h->lp = h->leaf_lp[h->cur_leaf];
-        r = sv_launch_leaf_kernels(h, 0, (int)S, (long long)S, nullptr, d_list, (int)leaves.size(), d_sums,
-                                   d_sums + groups * S, (long long)S, d_ls, d_lam);
+        if (h->private_cov)  // d_lam is [KMAX][S] here
+            r = sv_launch_leaf_private(h, nullptr, d_list, (int)leaves.size(), d_sums, d_sums + groups * S, d_ls, d_lam, (long long)S);
+        else
+            r = sv_launch_leaf_kernels(h, 0, (int)S, (long long)S, nullptr, d_list, (int)leaves.size(), d_sums,
+                                       d_sums + groups * S, (long long)S, d_ls, d_lam);
         h->lp = pending;
     }
     if (e == cudaSuccess && r == SIEVE_OK) e = cudaStreamSynchronize(h->stream);
@@ -761,7 +875,11 @@ extern "C" int sieve_update_leaves(sieve_core_t* h, int32_t for_update) {
     }
     if (!for_update && !h->single_leaf) {
         // initialisation: both buffers hold the leaves (storeLeafPartials, ScsBeerLikelihoodCore.java:437-445)
-        const size_t nx = (size_t)h->n * h->S * 4;
+        const size_t nx = (size_t)h->n * h->S * (h->private_cov ? SV_KMAX * 4 : 4);
+        if (h->d_lambdaK)
+            SV_CUDA(cudaMemcpyAsync(h->d_lambdaK + (size_t)(1 - h->cur_leaf) * SV_KMAX * h->S,
+                                    h->d_lambdaK + (size_t)h->cur_leaf * SV_KMAX * h->S,
+                                    (size_t)SV_KMAX * h->S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         SV_CUDA(cudaMemcpyAsync(h->d_leafX + (size_t)(1 - h->cur_leaf) * nx, h->d_leafX + (size_t)h->cur_leaf * nx,
                                 nx * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         SV_CUDA(cudaMemcpyAsync(h->d_lsum + (size_t)(1 - h->cur_leaf) * h->S, h->d_lsum + (size_t)h->cur_leaf * h->S,
@@ -1013,6 +1131,10 @@ extern "C" int sieve_walk_blocks_per_sm(int64_t n_sites) {
 template <bool QFAST>
 static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
     const bool g0 = a.const_genotype == 0 && a.root_genotype == 0;
+    if (h->private_cov) {  // per-category leaves (sieve_create rejects the twin; sv_launch_staged checks the genotypes)
+        k_prune<false, true, QFAST, 0, true><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+        return;
+    }
     if (h->with_const && h->const_twin) {
         if (g0)
             k_prune<true, true, QFAST><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
@@ -1020,7 +1142,15 @@ static void sv_launch_prune_t(sieve_core* h, dim3 grid, const SvPruneArgs& a) {
             k_prune<true, false, false><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
     } else {
         const int minb = QFAST && g0 && grid.y == 1 ? (h->prune_minb ? h->prune_minb : sv_pick_prune_blocks(grid.x * (SV_PRUNE_THREADS / 32))) : 0;
-        if (minb == 7)
+        if (QFAST && g0 && grid.y == 1 && !a.per_level && !h->use_k_prune) {
+            // the default: the lean single-launch walk (walk.cuh); same bits as k_prune<false, true, true>
+            if (minb == 7)
+                k_walk<7><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            else if (minb == 8)
+                k_walk<8><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+            else
+                k_walk<0><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
+        } else if (minb == 7)
             k_prune<false, true, QFAST, 7><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
         else if (minb == 8)
             k_prune<false, true, QFAST, 8><<<grid, SV_PRUNE_THREADS, 0, h->stream>>>(a);
@@ -1069,6 +1199,8 @@ static int sv_launch_staged(sieve_core* h) {
         for (int k = 0; k < 4; k++) a.prop[k] = h->prop[k];
         a.site_logl = h->d_site_logl;
         a.site_const = h->d_site_const;
+        if (h->private_cov && (a.const_genotype != 0 || a.root_genotype != 0))
+            return sv_fail(SIEVE_ERR_STATE, "SIEVE_FLAG_PRIVATE_SEQ_COV cores support root / constant genotype 0 only (ScsFiniteMuExtendedModel)");
         // the Q-specialised walk needs every matrix of the launch to have been given as a distance (and genotype 0)
         const bool qfast = h->last_qfast && a.const_genotype == 0 && a.root_genotype == 0 && !h->force_generic;
         const int spb = sv_prune_sites(h->with_const && h->const_twin, qfast);
@@ -1164,6 +1296,11 @@ static int sv_flush(sieve_core* h) {
             if (pm.reuse == 0) h->mat_ver[pm.slot] = ++h->ver_counter;
             h->mat_mirror_q[pm.slot] = (char)pm.is_distance;
             memcpy(mirror(pm.slot), pv, len);
+            if (pm.reuse == 2) {
+                h->slot_b[pm.slot] = h->slot_b[other];
+                h->slot_bd[pm.slot] = h->slot_bd[other];
+            } else
+                sv_slot_bounds(h, pm);
         }
     }
     if (h->ephemeral)
@@ -1175,6 +1312,7 @@ static int sv_flush(sieve_core* h) {
         for (size_t i = 0; i + 2 < t.size(); i += 3) {
             SvOp op;
             SV_TRY(sv_make_op(h, t[i + 1], t[i + 2], t[i], &op));
+            sv_bound_op(h, t[i], t[i + 1], t[i + 2], &op);
             h->pending_ops.push_back(op);
         }
         h->pending_level_triples.clear();
@@ -1259,8 +1397,23 @@ static int sv_flush(sieve_core* h) {
     return SIEVE_OK;
 }
 
+// logConstRoot per site of a private-model core into d_site_const (leaf_private.cuh, k_const_private)
+static void sv_launch_const_private(sieve_core* h) {
+    SvConstPrivW w;
+    for (int k = 0; k < SV_KMAX; k++) w.logw[k] = h->logw[k];
+    k_const_private<<<(h->S + 255) / 256, 256, 0, h->stream>>>(h->d_lambdaK + (size_t)h->cur_leaf * SV_KMAX * h->S, h->S, h->S, h->K,
+                                                              w, h->d_site_const);
+    sv_count(h);
+}
+
 static void sv_launch_reduce(sieve_core* h) {
     const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
+    if (h->private_cov && h->with_const) {
+        sv_launch_const_private(h);
+        k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, h->d_site_const, 0.0, h->d_weights, h->S, 1, h->d_partials,
+                                                h->d_counter, h->d_result);
+        return;
+    }
     const bool algebraic = h->with_const && !h->const_twin;
     const double* cst = algebraic ? h->d_lambda + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S) : h->d_site_const;
     k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, cst, algebraic ? h->log_c : 0.0, h->d_weights, h->S,
@@ -1377,7 +1530,8 @@ extern "C" int sieve_get_site_log_likelihoods(sieve_core_t* h, double* out_l, do
     SV_CUDA(cudaSetDevice(h->device));
     SV_TRY(sv_flush(h));
     SV_CUDA(cudaMemcpyAsync(out_l, h->d_site_logl, sizeof(double) * h->S, cudaMemcpyDeviceToHost, h->stream));
-    const bool algebraic = h->with_const && !h->const_twin;
+    const bool algebraic = h->with_const && !h->const_twin && !h->private_cov;
+    if (out_c && h->private_cov && h->with_const) sv_launch_const_private(h);
     if (out_c) {
         const double* src = algebraic ? h->d_lambda + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S) : h->d_site_const;
         SV_CUDA(cudaMemcpyAsync(out_c, src, sizeof(double) * h->S, cudaMemcpyDeviceToHost, h->stream));
@@ -1406,11 +1560,12 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
         SV_TRY(sv_flush(h));
     }
     const size_t S = h->S, K = h->K, n = h->n;
-    const double *x, *sc;
+    const double* x;
+    const int* sc;
     int is_leaf = node < h->n;
     // the leaves' scales live only as sums (leaf.cuh): re-derive the sum over the leaves below this node
-    double* d_sub = nullptr;  // [2][S]: scales, constant-genotype log-likelihoods
-    SV_CUDA(cudaMalloc(&d_sub, sizeof(double) * 2 * S));
+    double* d_sub = nullptr;  // [1 + (private model: K, else 1)][S]: scales, constant-genotype log-likelihoods (per category)
+    SV_CUDA(cudaMalloc(&d_sub, sizeof(double) * (1 + (h->private_cov ? SV_KMAX : 1)) * S));
     struct SubFree {
         double* p;
         ~SubFree() { cudaFree(p); }
@@ -1419,8 +1574,9 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
         SV_REQUIRE(which == 0, "leaves have no constant-site partials");
         if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "leaves not computed yet");
         SV_TRY(sv_subtree_leaf_sums(h, node, d_sub, nullptr));
-        x = h->d_leafX + ((size_t)h->cur_leaf * n + node) * S * 4;
+        x = h->d_leafX + ((size_t)h->cur_leaf * n + node) * S * (h->private_cov ? SV_KMAX * 4 : 4);
         sc = nullptr;
+        if (h->private_cov) is_leaf = 0;  // K x 4 values per site, the layout of an internal partial (no exponent: sc == NULL)
     } else {
         const int sl = h->slot_of[(size_t)h->cur_part[node] * h->n_nodes + node];
         if (sl < 0) return sv_fail(SIEVE_ERR_STATE, "sieve_get_node_partials: the node could not be materialised");
@@ -1438,8 +1594,8 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_G, g, sizeof(double) * 16, cudaMemcpyHostToDevice, h->stream);
             if (e == cudaSuccess) {
                 k_export_const<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(
-                    d_sub + S, d_G, h->Gs[(size_t)h->cur_part[node] * h->n_nodes + node], (int)S, (int)K,
-                    h->log_mode ? 1 : 0, d_o);
+                    d_sub + S, h->private_cov ? (long long)S : 0LL, d_G, h->Gs[(size_t)h->cur_part[node] * h->n_nodes + node],
+                    (int)S, (int)K, h->log_mode ? 1 : 0, d_o);
                 sv_count(h);
                 e = cudaGetLastError();
             }
@@ -1456,7 +1612,7 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     double* d_out = nullptr;
     const size_t N = K * S * 4;
     SV_CUDA(cudaMalloc(&d_out, N * sizeof(double)));
-    k_export_partials<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(x, sc, d_sub, (int)S, (int)K, is_leaf,
+    k_export_partials<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(x, sc, d_sub, (int)S, (int)K, is_leaf,
                                                                           h->log_mode ? 1 : 0, which == 1 ? 1 : 0, d_out);
     sv_count(h);
     cudaError_t e = cudaGetLastError();
@@ -1482,6 +1638,7 @@ extern "C" int sieve_store(sieve_core_t* h) {
     h->eph_c2_stored = h->eph_c2;
     h->valid_stored = h->valid;
     h->log_c_stored = h->log_c;
+    memcpy(h->logw_stored, h->logw, sizeof(h->logw));
     // value versions / provenance: the current and the stored arrays differ only where a plan has written since the last
     // store (restore swaps the arrays, which keeps that true), so only those entries are copied
     for (int v : h->prov_touched) {
@@ -1515,6 +1672,7 @@ extern "C" int sieve_unstore(sieve_core_t* h) {
     h->eph_c2 = h->eph_c2_stored;
     h->valid = h->valid_stored;
     h->log_c = h->log_c_stored;
+    memcpy(h->logw, h->logw_stored, sizeof(h->logw));
     for (int v : h->prov_touched) {
         h->ver_cur[v] = h->ver_stored[v];
         h->fp_cur[v] = h->fp_stored[v];
@@ -1534,6 +1692,7 @@ extern "C" int sieve_restore(sieve_core_t* h) {
     h->eph_c2.swap(h->eph_c2_stored);
     h->valid.swap(h->valid_stored);
     std::swap(h->log_c, h->log_c_stored);
+    for (int k = 0; k < SV_KMAX; k++) std::swap(h->logw[k], h->logw_stored[k]);
     h->ver_cur.swap(h->ver_stored);
     h->fp_cur.swap(h->fp_stored);
     if (h->eph_c1 != h->eph_c1_stored || h->eph_c2 != h->eph_c2_stored) h->topo_cache_ok = false;

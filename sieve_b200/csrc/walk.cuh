@@ -1,0 +1,173 @@
+// walk.cuh -- the default pruning kernel: single-launch walk over any number of dependent ops, Q-specialised contraction,
+// variant partials only (constant-site partials are handled algebraically, core_planner.cuh), root/constant genotype 0.
+//
+// Same arithmetic, same layouts, same op descriptors and the same bits as k_prune<false, true, true> (prune.cuh), which
+// stays for the level-batched schedule, the generic matrices and the per-site constant-site twin.  This kernel exists
+// because the walk is bound by instruction issue and exposed latency, not by DRAM (profiles/README.md): it does the same
+// work in ~40 % fewer instructions per op --
+//   * one address computation and ONE 256-bit load per child whatever it is: base pointer, shift and category offset are
+//     selected from the op's (uniform) flags, so the leaf / stored-partial distinction costs no branch;
+//   * the product of the two children's contributions is formed in place in the registers that carry the result to the
+//     next op (no copies), the second child's block is skipped by one uniform branch for the unary root;
+//   * binary exponents are integers and the power-of-two renormalisation only runs where the host's magnitude bounds ask
+//     for it (SV_OP_RENORM);
+//   * leaf operands of the op a few steps ahead are asked into L2 with one predicated prefetch per operand.
+#pragma once
+#include "prune.cuh"
+
+template <int MINB>
+__global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? MINB : SV_PRUNE_MINB_Q)) k_walk(SvPruneArgs a) {
+    constexpr int NS = SV_PRUNE_NS_Q;
+    constexpr int SITES_PER_BLOCK = (SV_PRUNE_THREADS / 4) * NS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int klane = lane & 3;
+    const int k = min(klane, a.K - 1);
+    const int site0 = blockIdx.x * SITES_PER_BLOCK + warp * (8 * NS) + (lane >> 2);
+    // lanes beyond the last site (category) are clamped onto the last valid one: they compute duplicates, only their
+    // stores are suppressed (see k_prune)
+    bool site_ok[NS];
+    unsigned srow[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        const int site = site0 + 8 * j;
+        site_ok[j] = site < a.S;
+        srow[j] = (unsigned)(site_ok[j] ? site : a.S - 1);
+    }
+    const char* const leaf_base = reinterpret_cast<const char*>(a.leafX);
+    const char* const part_base = reinterpret_cast<const char*>(a.part) + k * 32;
+    // prefetch role of this lane: the lanes with category index j < NS ask for the line of their site of pass j
+    unsigned pf_srow = srow[0];
+#pragma unroll
+    for (int j = 1; j < NS; j++) pf_srow = klane == j ? srow[j] : pf_srow;
+    const bool pf_lane = klane < NS;
+
+    const int i0 = a.op_begin, i1 = a.op_end;
+    if (a.pf_dist > 0 && pf_lane) {
+        // the first pf_dist ops of the list: nobody could announce their leaf operands earlier
+        const int jn = min(i1, i0 + a.pf_dist);
+#pragma unroll 1
+        for (int j = i0; j < jn; j++) {
+            const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.ops + j));
+            const int fl = __ldg(reinterpret_cast<const int*>(a.ops + j) + 5);
+            if (fl & SV_OP_FAR1) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)d0.y + pf_srow) << 5));
+            if (fl & SV_OP_FAR2) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)d0.z + pf_srow) << 5));
+        }
+    }
+
+    double x[NS][4];  // the previous op's result, consumed from registers by an op that has it as child 1 (SV_OP_FWD1)
+    int xe[NS];       // its binary exponent
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        xe[j] = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) x[j][g] = 0.0;
+    }
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
+    if (i0 < i1) {
+        const int4* opp = reinterpret_cast<const int4*>(a.ops + i0);
+        n0 = __ldg(opp);
+        n1 = __ldg(opp + 1);
+    }
+#pragma unroll 1
+    for (int i = i0; i < i1; i++) {
+        __syncwarp();  // scratch slots are reused (streamed mode): keep the warp's reads of an op ahead of the next op's writes
+        const int4 o0 = n0, o1 = n1;
+        if (i + 1 < i1) {  // the next op's descriptor, one op ahead: off the chain descriptor -> addresses -> loads
+            const int4* opp = reinterpret_cast<const int4*>(a.ops + i + 1);
+            n0 = __ldg(opp);
+            n1 = __ldg(opp + 1);
+        }
+        const int flags = o1.y;
+        // leaf operands of the op pf_dist ahead: into L2 now
+        if ((flags & SV_OP_PF1) && pf_lane) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)o1.z + pf_srow) << 5));
+        if ((flags & SV_OP_PF2) && pf_lane) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)o1.w + pf_srow) << 5));
+
+        const bool has2 = !(flags & SV_OP_UNARY);
+        const bool cz0 = flags & SV_OP_ZEROD;
+        const double2 q1 = __ldg(a.qfac + (size_t)o0.w * SV_KMAX + k);
+        double2 q2;
+        double w[NS][4];
+        int we[NS];
+        // ---- every global load of the op up front ----
+        if (has2) {
+            q2 = __ldg(a.qfac + (size_t)o1.x * SV_KMAX + k);
+            const bool leaf2 = flags & SV_OP_LEAF2;
+            const char* const base = leaf2 ? leaf_base : part_base;
+            const unsigned sh = leaf2 ? 5u : 7u;
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                const unsigned row = (unsigned)o0.z + srow[j];
+                sv_ld256(reinterpret_cast<const double*>(base + ((size_t)row << sh)), w[j]);
+                we[j] = 0;
+                if (!leaf2) we[j] = a.scale[row];
+            }
+        }
+        if (!(flags & SV_OP_FWD1)) {
+            const bool leaf1 = flags & SV_OP_LEAF1;
+            const char* const base = leaf1 ? leaf_base : part_base;
+            const unsigned sh = leaf1 ? 5u : 7u;
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                const unsigned row = (unsigned)o0.y + srow[j];
+                sv_ld256(reinterpret_cast<const double*>(base + ((size_t)row << sh)), x[j]);
+                xe[j] = 0;
+                if (!leaf1) xe[j] = a.scale[row];
+            }
+        }
+        // ---- contraction(s) and product; both arms of the (rare) renormalisation write the registers that carry the
+        //      result to the next op, so no copies are needed where they meet ----
+        double y[NS][4];
+        sv_matvec_q<NS>(q1, x, y, cz0);
+        if (has2) {
+            double z[NS][4];
+            sv_matvec_q<NS>(q2, w, z, cz0);
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+#pragma unroll
+                for (int p = 0; p < 4; p++) y[j][p] *= z[j][p];
+                xe[j] += we[j];
+            }
+        }
+        if (flags & SV_OP_RENORM) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                int hi = sv_maxhi4(y[j]);
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
+                int sh;
+                const double f = sv_pow2_rescale_hi_int(hi, &sh);
+#pragma unroll
+                for (int p = 0; p < 4; p++) x[j][p] = y[j][p] * f;
+                xe[j] += sh;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+#pragma unroll
+                for (int p = 0; p < 4; p++) x[j][p] = y[j][p];
+        }
+        if (!(flags & SV_OP_NOSTORE)) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                if (!site_ok[j]) continue;  // clamped duplicate lanes never store
+                const unsigned row = (unsigned)o0.x + srow[j];
+                sv_st256(a.part + (size_t)row * 16 + k * 4, x[j]);
+                a.scale[row] = xe[j];  // every category lane writes the (identical) exponent
+            }
+        }
+        if (flags & SV_OP_ROOT) {
+            // integrate over categories and take the log (ScsBeerLikelihoodCore.java:153-218, 255-269); the scales of ALL
+            // leaves, which the walk never carried, come in here
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                double v = (klane < a.K ? a.prop[klane] : 0.0) * x[j][0];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if (site_ok[j] && klane == 0) {
+                    const long long s = a.out_offset + site0 + 8 * j;
+                    a.site_logl[s] = log(v) + fma((double)xe[j], SV_LN2, __ldg(a.lsum + s));
+                }
+            }
+        }
+    }
+}

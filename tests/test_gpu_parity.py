@@ -1159,3 +1159,62 @@ def test_streamed_ragged_chunks_are_deterministic(core_mod, monkeypatch):
         c.close()
     assert out[True][0] == out[False][0]
     np.testing.assert_array_equal(out[True][1], out[False][1])
+
+
+def test_lazy_renormalisation_is_bit_identical_to_renormalising_every_op(core_mod, oracle, monkeypatch):
+    """The walk renormalises a partial only where the host's magnitude bounds ask for it (core_planner.cuh, sv_bound_op).
+    Scaling by 2^k is exact and exponents are summed as integers, so the schedule cannot change a bit: site
+    log-likelihoods, totals and exported node partials equal those of a core that renormalises after every op
+    (SIEVE_B200_RENORM_ALWAYS=1) -- on a deep caterpillar (the bounds run out every dozen ops), on a coalescent tree,
+    through a leaf-parameter proposal, a local move and a restore, resident and streamed."""
+    from sieve_b200.treelikelihood import LeafModelParams, ScsTreeLikelihood
+    for shape in ("caterpillar", "coalescent"):
+        if shape == "caterpillar":
+            n, S = 260, 700
+            tree = caterpillar(n, 0.0, 1.0)
+            tree.height *= 0.6 / tree.height[tree.root]
+            d = synthetic(n, S, seed=61, tree=tree)
+        else:
+            n, S = 180, 900
+            d = synthetic(n, S, seed=62)
+            tree = d["tree"]
+        counts = d["counts"]
+        sf, _ = oracle.size_factors(oracle.counts5(counts))
+        v = tree.n + tree.n // 2
+        moved = tree.copy()
+        lo = max(moved.height[moved.left[v]], moved.height[moved.right[v]])
+        moved.height[v] = lo + 0.41 * (moved.height[moved.parent[v]] - lo)
+        out = {}
+        for mode in ("lazy", "always", "lazy_streamed"):
+            if mode == "always":
+                monkeypatch.setenv("SIEVE_B200_RENORM_ALWAYS", "1")
+            else:
+                monkeypatch.delenv("SIEVE_B200_RENORM_ALWAYS", raising=False)
+            tl = ScsTreeLikelihood(counts, tree.copy(), size_factors=sf, asc_mode="felsenstein_mean", n_background_sites=1e4,
+                                   ephemeral=(mode == "lazy_streamed"))
+            seq = [tl.calculate_logp()]
+            seq.append(tl.pattern_log_likelihoods()[0].copy())
+            tl.store()
+            tl.set_leaf_params(LeafModelParams(0.25, 44.0, 61.0, 0.011, 120.0, 2.5))
+            seq.append(tl.calculate_logp())
+            tl.restore()
+            tl.store()
+            tl.set_tree(moved.copy(), [v])
+            seq.append(tl.calculate_logp())
+            seq.append(tl.pattern_log_likelihoods()[0].copy())
+            if mode != "lazy_streamed":
+                seq.append(tl.core.get_node_partials(v))
+                seq.append(tl.core.get_node_partials(tree.root - 1))
+            out[mode] = seq
+            tl.close()
+        for a, b in zip(out["lazy"], out["always"]):
+            np.testing.assert_array_equal(a, b)
+        for a, b in zip(out["lazy_streamed"], out["lazy"][:5]):
+            np.testing.assert_array_equal(a, b)
+        assert np.isfinite(out["lazy"][1]).all()
+        # and the numbers are right: against the oracle on the start state
+        rates, props = substmodel.gamma_category_rates(1.0, 4)
+        mats = substmodel.node_matrices(tree, rates)
+        logp, osl, _ = _oracle_eval(oracle, counts, tree, sf, PARAMS, mats, props, "felsenstein_mean", 1e4, T=8)
+        _close(out["lazy"][1], osl, SITE_RTOL)
+        assert abs(out["lazy"][0] - logp) <= TOTAL_RTOL * abs(logp)
