@@ -171,3 +171,101 @@ def leaf_likelihood_private(oracle, counts_s_n_5, taxon, size_factor, params, t_
                                   params.shape2, params.single_ado, params.use_log)
             out[k, p] = oracle.leaf_likelihood(counts_s_n_5, taxon, size_factor, P, p, p + 1)[0]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Whole evaluations under the private model (test infrastructure for the device side, sieve_b200/csrc/leaf_private.cuh)
+
+def full_eval_private(oracle, counts_s_n_5, size_factors, params, t_kp, v_kp, ops, matrices, proportions, root):
+    """Site log-likelihoods and logConstRoot with category-dependent leaves: the restated likelihood core
+    (oracle.Core = ScsBeerLikelihoodCore) fed the [K][S][4] leaf partials of `leaf_likelihood_private`
+    (ScsTreeLikelihood.java:583-601 with nrOfMatrices = K), then traverse / integratePartials / calculateLogLikelihoods.
+    -> (site_logl [S], site_log_const [S], {node: partials [K][S][4]})."""
+    c = np.ascontiguousarray(counts_s_n_5, dtype=np.int32)
+    S, n = c.shape[0], c.shape[1]
+    matrices = np.asarray(matrices, dtype=np.float64)
+    K = matrices.shape[1]
+    core = oracle.Core(2 * n, n, S, K, 4, use_log=params.use_log)
+    leaves = {}
+    for j in range(n):
+        leaves[j] = leaf_likelihood_private(oracle, c, j, size_factors[j], params, t_kp, v_kp)
+        core.set_node_partials(j, leaves[j])
+    for node in range(2 * n):
+        if node == root:
+            continue
+        for k in range(K):
+            core.set_node_matrix(node, k, matrices[node, k])
+    for parent, c1, c2 in ops:
+        parent, c1, c2 = int(parent), int(c1), int(c2)
+        core.calculate_partials(c1, c1 < n, c2, 0 <= c2 < n, parent, 0)
+    rp, cr = core.integrate_partials(root, proportions, 0)
+    sl, lc = core.calculate_log_likelihoods(rp, cr)
+    partials = dict(leaves)
+    for parent, _, _ in ops:
+        partials[int(parent)] = core.get_node_partials(int(parent)).reshape(K, S, 4)
+    return sl, lc, partials
+
+
+def ml_trace_private(oracle, mlo, counts_s_n_5, size_factors, params, t_kp, v_kp, ops, matrices):
+    """oracle.ml_genotypes.ml_trace with category-dependent leaves: leaf [n][K][S][4], ado [n][K][S][4]."""
+    import ctypes as C
+    c = np.ascontiguousarray(counts_s_n_5, dtype=np.int32)
+    S, n = c.shape[0], c.shape[1]
+    matrices = np.asarray(matrices, dtype=np.float64)
+    K = matrices.shape[1]
+    L = mlo._lib()
+    leaf = np.empty((n, K, S, 4))
+    ado = np.empty((n, K, S, 4), dtype=np.uint8)
+    _dp, _ip, _bp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_ubyte)
+    o = np.empty(4)
+    a = np.empty(4, dtype=np.uint8)
+    for j in range(n):
+        for k in range(K):
+            for p in range(S):
+                P = oracle.LeafParams(params.ado_rate, float(t_kp[k][p]), float(v_kp[k][p]), params.eff_seq_err,
+                                      params.shape1, params.shape2, params.single_ado, params.use_log)
+                L.so_leaf_likelihood_ml(c.ctypes.data_as(_ip), n, p, p + 1, j, float(size_factors[j]), C.byref(P),
+                                        o.ctypes.data_as(_dp), a.ctypes.data_as(_bp))
+                leaf[j, k, p] = o
+                ado[j, k, p] = a
+    ml, back = {}, {}
+    for parent, c1, c2 in ops:
+        parent, c1, c2 = int(parent), int(c1), int(c2)
+        a1 = leaf[c1] if c1 < n else ml[c1]
+        a2 = None
+        if c2 >= 0:
+            a2 = leaf[c2] if c2 < n else ml[c2]
+        ml[parent], back[parent] = mlo.ml_log_pruning(a1, matrices[c1], a2, matrices[c2] if c2 >= 0 else None)
+    return dict(leaf=leaf, ado=ado, ml=ml, back=back)
+
+
+def post_process(oracle, mlo, counts_s_n_5, size_factors, params, t_kp, v_kp, ops, matrices, zero_cov_mode=0):
+    """ScsTreeLikelihood.postProcess steps 1-2 (likelihood/ScsTreeLikelihood.java:2454-2475) from scratch: the ML genotype
+    combinations of every (matrix, pattern) pair (getMLGenotypes, first run), their numbers of sequenced alleles sorted and
+    de-duplicated into weighted patterns (:1066-1101), then updateAllelicSeqCovAndRawVar for every pair.
+    -> (t [K][S], v [K][S], n_combinations [K][S])."""
+    c = np.ascontiguousarray(counts_s_n_5, dtype=np.int32)
+    S, n = c.shape[0], c.shape[1]
+    K = np.asarray(matrices).shape[1]
+    tr = ml_trace_private(oracle, mlo, c, size_factors, params, t_kp, v_kp, ops, matrices)
+    modeled = [1, 2] if params.single_ado else [0, 1, 2]
+    cov = processed_seq_cov(c[:, :, 4] if c.shape[2] == 5 else c[:, :, 3], zero_cov_mode)   # [S][n]
+    t_new = np.array(t_kp, dtype=np.float64).copy()
+    v_new = np.array(v_kp, dtype=np.float64).copy()
+    ncomb = np.zeros((K, S), dtype=np.int64)
+    for k in range(K):
+        for p in range(S):
+            back_at = {node: tr["back"][node][k, p] for node in tr["back"]}
+            combos = mlo.enumerate_ml_genotypes(ops, n, back_at, tr["ado"][:, k, p, :], 0)
+            ncomb[k, p] = len(combos)
+            pats = sorted(tuple(2 - comb[j] for j in range(n)) for comb in combos)   # getNrOfAlleles() == 2 (:1080)
+            uniq, weights = [], []
+            for q in pats:
+                if uniq and uniq[-1] == q:
+                    weights[-1] += 1
+                else:
+                    uniq.append(q)
+                    weights.append(1)
+            t_new[k, p], v_new[k, p] = update_allelic_seq_cov_and_raw_var(cov[p], size_factors, modeled,
+                                                                          [np.array(q) for q in uniq], weights, v_new[k, p])
+    return t_new, v_new, ncomb

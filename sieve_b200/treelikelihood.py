@@ -34,7 +34,7 @@ class ScsTreeLikelihood:
     def __init__(self, counts, tree, size_factors=None, leaf_params=None, gamma_shape=1.0, n_categories=4,
                  clock_rate=1.0, branch_rates=None, use_log_partials=True, asc_mode="none", n_background_sites=0.0,
                  weights=None, single_ado=True, device=-1, return_const_sum=False, use_distances=True, ephemeral=False,
-                 sparse=False, single_leaf_buffer=False):
+                 sparse=False, single_leaf_buffer=False, private_seq_cov=False, zero_cov_mode=0):
         counts = np.asarray(counts)
         self.S, self.n = counts.shape[0], counts.shape[1]
         assert tree.n == self.n, "The number of nodes in the tree does not match the number of sequences"
@@ -49,8 +49,12 @@ class ScsTreeLikelihood:
         self.return_const_sum = return_const_sum
         # True: hand the core branch distances (fast path for the fixed rate matrix); False: 16-double matrices
         self.use_distances = use_distances
+        # PrivateAllelicSeqCovModel instead of ExploredSharedAllelicSeqCovModel: (t, v) per (category, pattern)
+        self.private_seq_cov, self.zero_cov_mode, self.single_ado = bool(private_seq_cov), int(zero_cov_mode), bool(single_ado)
+        self._counts = counts if private_seq_cov else None
         self.core = ScsCudaLikelihoodCore(self.n, self.S, n_categories, 4, use_log_partials, asc_mode != "none",
-                                          single_ado, device, ephemeral, sparse, single_leaf_buffer)
+                                          single_ado, device, ephemeral, sparse, single_leaf_buffer,
+                                          private_seq_cov=private_seq_cov)
         self.core.set_counts(counts)
         self.core.set_pattern_weights(weights)
         self.branch_lengths = np.full(tree.node_count, -1.0)   # m_branchLengths
@@ -76,7 +80,29 @@ class ScsTreeLikelihood:
             self.core.set_size_factors(size_factors)
         self.size_factors = np.asarray(size_factors)
         self.core.set_leaf_params(*self.params.as_tuple())
+        if self.private_seq_cov:
+            # every pair starts at the shared values (PrivateAllelicSeqCovModel.java:159-161)
+            self.core.set_private_seq_cov(np.full((self.K, self.S), self.params.t), np.full((self.K, self.S), self.params.v))
         self.core.update_leaves(for_update=False)
+
+    def accept(self):
+        """ScsTreeLikelihood.accept -> postProcess (:2454-2520, 2893-2916) for the per-pattern coverage model: max-sum trace
+        of the accepted state, re-estimation of every (category, pattern) pair's (t, v) from the ML numbers of sequenced
+        alleles, then the state is recomputed with the new pairs.  -> number of pairs that moved."""
+        if not self.private_seq_cov:
+            return 0
+        from .private_cov import resolve_tied_pairs
+        changed, tied = self.core.private_update_from_ml(self.zero_cov_mode)
+        if tied.any():
+            changed += resolve_tied_pairs(self.core, self.tree, self._counts, self.size_factors, tied, self.zero_cov_mode,
+                                          self.single_ado)
+        if changed:
+            # the reference re-traverses the changed patterns only (:2493-2498); every pattern here -- unchanged pairs
+            # reproduce their values bit for bit
+            self.update_leaves = True
+            self.has_dirt = max(self.has_dirt, IS_DIRTY)
+            self.calculate_logp()
+        return changed
 
     def close(self):
         self.core.close()

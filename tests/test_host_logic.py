@@ -140,3 +140,38 @@ def test_ingest_shards_round_trip(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "junk").write_bytes(b"hello")
         ingest.open_shard(str(tmp_path / "junk"))
+
+
+def test_private_cov_tied_pair_update_matches_the_oracle():
+    """sieve_b200.private_cov.update_pair (host half of PrivateAllelicSeqCovModel.updateAllelicSeqCovAndRawVar for tied
+    pairs) against the loop restatement of oracle/private_allelic.py, incl. repeated and degenerate combinations."""
+    from oracle import private_allelic as pa
+    from sieve_b200 import private_cov
+    rng = np.random.default_rng(3)
+    n = 11
+    for single in (True, False):
+        modeled = [1, 2] if single else [0, 1, 2]
+        for trial in range(40):
+            sf = rng.uniform(0.4, 2.5, n)
+            cov = rng.integers(0, 120, n)
+            n_comb = int(rng.integers(1, 5))
+            combos = []
+            for _ in range(n_comb):
+                ado = rng.integers(0, len(modeled), n)           # dropped alleles of each leaf's ML component
+                if trial % 7 == 0:
+                    ado[:] = 0                                   # one group only
+                combos.append(tuple(int(a) for a in ado) + (0,) * (2 * n))
+            if trial % 5 == 0:
+                combos.append(combos[0])                          # a duplicate: weight 2
+            pats = sorted(tuple(2 - c[j] for j in range(n)) for c in combos)
+            uniq, weights = [], []
+            for p in pats:
+                if uniq and uniq[-1] == p:
+                    weights[-1] += 1
+                else:
+                    uniq.append(p)
+                    weights.append(1)
+            want = pa.update_allelic_seq_cov_and_raw_var(cov, sf, modeled, [np.array(p) for p in uniq], weights, 7.5)
+            got = private_cov.update_pair(cov, sf, combos, single, 7.5)
+            assert abs(got[0] - want[0]) <= 1e-13 * abs(want[0]) + 1e-300
+            assert abs(got[1] - want[1]) <= 1e-13 * abs(want[1]) + 1e-300
