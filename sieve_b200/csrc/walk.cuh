@@ -15,6 +15,14 @@
 #pragma once
 #include "prune.cuh"
 
+// base + row * stride with ONE wide multiply-add (IMAD.WIDE.U32); written as a shift the compiler spends four
+// instructions per address (two funnel shifts, add, add-with-carry)
+__device__ __forceinline__ const char* sv_row_addr(const char* base, unsigned row, unsigned stride) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(row), "r"(stride), "l"((unsigned long long)base));
+    return reinterpret_cast<const char*>(r);
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? MINB : SV_PRUNE_MINB_Q)) k_walk(SvPruneArgs a) {
     constexpr int NS = SV_PRUNE_NS_Q;
@@ -32,9 +40,11 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         const int site = site0 + 8 * j;
         site_ok[j] = site < a.S;
         srow[j] = (unsigned)(site_ok[j] ? site : a.S - 1);
+        asm volatile("" : "+r"(srow[j]));  // keep it: re-deriving it costs three instructions per use
     }
     const char* const leaf_base = reinterpret_cast<const char*>(a.leafX);
     const char* const part_base = reinterpret_cast<const char*>(a.part) + k * 32;
+    const char* const scale_base = reinterpret_cast<const char*>(a.scale);
     // prefetch role of this lane: the lanes with category index j < NS ask for the line of their site of pass j
     unsigned pf_srow = srow[0];
 #pragma unroll
@@ -93,25 +103,25 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
             q2 = __ldg(a.qfac + (size_t)o1.x * SV_KMAX + k);
             const bool leaf2 = flags & SV_OP_LEAF2;
             const char* const base = leaf2 ? leaf_base : part_base;
-            const unsigned sh = leaf2 ? 5u : 7u;
+            const unsigned stride = leaf2 ? 32u : 128u;  // one wide multiply-add forms the address
 #pragma unroll
             for (int j = 0; j < NS; j++) {
                 const unsigned row = (unsigned)o0.z + srow[j];
-                sv_ld256(reinterpret_cast<const double*>(base + ((size_t)row << sh)), w[j]);
+                sv_ld256(reinterpret_cast<const double*>(sv_row_addr(base, row, stride)), w[j]);
                 we[j] = 0;
-                if (!leaf2) we[j] = a.scale[row];
+                if (!leaf2) we[j] = *reinterpret_cast<const int*>(sv_row_addr(scale_base, row, 4u));
             }
         }
         if (!(flags & SV_OP_FWD1)) {
             const bool leaf1 = flags & SV_OP_LEAF1;
             const char* const base = leaf1 ? leaf_base : part_base;
-            const unsigned sh = leaf1 ? 5u : 7u;
+            const unsigned stride = leaf1 ? 32u : 128u;
 #pragma unroll
             for (int j = 0; j < NS; j++) {
                 const unsigned row = (unsigned)o0.y + srow[j];
-                sv_ld256(reinterpret_cast<const double*>(base + ((size_t)row << sh)), x[j]);
+                sv_ld256(reinterpret_cast<const double*>(sv_row_addr(base, row, stride)), x[j]);
                 xe[j] = 0;
-                if (!leaf1) xe[j] = a.scale[row];
+                if (!leaf1) xe[j] = *reinterpret_cast<const int*>(sv_row_addr(scale_base, row, 4u));
             }
         }
         // ---- contraction(s) and product; both arms of the (rare) renormalisation write the registers that carry the
@@ -151,8 +161,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
             for (int j = 0; j < NS; j++) {
                 if (!site_ok[j]) continue;  // clamped duplicate lanes never store
                 const unsigned row = (unsigned)o0.x + srow[j];
-                sv_st256(a.part + (size_t)row * 16 + k * 4, x[j]);
-                a.scale[row] = xe[j];  // every category lane writes the (identical) exponent
+                sv_st256(reinterpret_cast<double*>(const_cast<char*>(sv_row_addr(part_base, row, 128u))), x[j]);
+                *reinterpret_cast<int*>(const_cast<char*>(sv_row_addr(scale_base, row, 4u))) = xe[j];  // every category lane writes the (identical) exponent
             }
         }
         if (flags & SV_OP_ROOT) {
