@@ -529,6 +529,14 @@ def main():
     # tree-only evaluation (stage-2 style proposal: matrices change, leaves do not)
     core.step_distances(W.nodes, W.D_host, W.ops, update_leaves=False)
     tree_only_ms = time_device_loop(core, lib_stream, args.steps, False, barrier) / args.steps
+    # the walk of a tree-only step on its own (events inside the library), for comparison with the walk after k_leaf
+    core.enable_timing(True)
+    tm2 = []
+    for i in range(5):
+        core.step_distances(W.nodes, W.D_host * (1.0 + 1e-12 * (i + 1)), W.ops, update_leaves=False)   # every matrix new
+        tm2.append(core.last_timing())
+    core.enable_timing(False)
+    prune_tree_only_ms = float(np.median([x["prune_ms"] for x in tm2]))
 
     r_last = W.exact_eval()
     results_last = global_results(core, r_last)
@@ -732,7 +740,7 @@ def main():
             "library_build_id": build_id,
             "kernels": {"leaf_ms": leaf_ms, "leaf_GBps": alg_leaf / (leaf_ms / 1000.0) / 1e9 if leaf_ms > 0 else None,
                         "leaf_frac": alg_leaf / (leaf_ms / 1000.0) / 1e9 / peak if leaf_ms > 0 else None,
-                        "prune_ms": prune_ms, "reduce_ms": reduce_ms, "tree_only_eval_ms": tree_only_ms,
+                        "prune_ms": prune_ms, "prune_ms_in_tree_only_step": prune_tree_only_ms, "reduce_ms": reduce_ms, "tree_only_eval_ms": tree_only_ms,
                         "tree_only_evals_per_s": 1000.0 / tree_only_ms},
             "mcmc": mcmc,
             "mcmc_states_per_s": mcmc.get("stage1", {}).get("states_per_s"),

@@ -17,15 +17,22 @@ from sieve_b200.core import ScsCudaLikelihoodCore  # noqa: E402
 def main():
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
+    # default: the bench workload; `ncu_target.py 10000 125000 sparse` = the per-GPU share of the north-star data set
     n, S = bench.N_CELLS, bench.N_SITES
+    mode = "dense"
+    if len(sys.argv) >= 3:
+        n, S = int(sys.argv[1]), int(sys.argv[2])
+        mode = sys.argv[3] if len(sys.argv) > 3 else "dense"
     tree, rates, props, br, mats = bench.make_tree_and_matrices(bench.SEED, n)
     counts_dev = bench.generate_counts_device(tree, rates, br, n, S, bench.SEED, dev)
     torch.cuda.synchronize()
-    core = ScsCudaLikelihoodCore(n, S, bench.K_CAT, 4, True, True, True, 0)
-    core.set_counts_device(counts_dev.data_ptr())
-    del counts_dev
-    torch.cuda.empty_cache()
-    core.compute_size_factors(0)
+    from sieve_b200.sizefactors import SizeFactorPart, solve_parts
+    part = SizeFactorPart(n, S, counts_dev.data_ptr(), None, 0, 0)   # pool-free size factors, before the core takes the HBM
+    sf, _ = solve_parts([part], None)
+    part.close()
+    core = ScsCudaLikelihoodCore(n, S, bench.K_CAT, 4, True, True, True, 0, sparse=(mode == "sparse"), external_counts=True)
+    core.set_counts_device(counts_dev.data_ptr())   # external counts: the tensor stays alive until the core is closed
+    core.set_size_factors(sf)
     core.set_leaf_params(*bench.PARAMS)
     core.update_leaves(for_update=False)
     core.set_root(tree.root, props, 0)
@@ -40,7 +47,8 @@ def main():
         core.set_leaf_params(*pr)
         r = core.step_distances(nodes, D, ops, update_leaves=True)
         t1 = time.perf_counter()
-        core.ml_trace()
+        if mode == "dense" and n <= 2000:
+            core.ml_trace()
         t2 = time.perf_counter()
         print("pass %d: evaluation %.2f ms, max-sum trace %.2f ms, sum logL %.6f" % (rep, 1e3 * (t1 - t0), 1e3 * (t2 - t1), r.sum_log_l))
     core.close()

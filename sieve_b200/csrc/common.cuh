@@ -3,6 +3,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Bounds-checked build (make variant NAME=checked DEFS=-DSV_CHECK_BOUNDS; never the product library): every pool and table
+// index of the hot kernels is asserted on the device.  compute-sanitizer is closed on the GPU pool this was developed on.
+#ifdef SV_CHECK_BOUNDS
+#include <cstdio>
+#define SV_BOUND(cond)                                                                      \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            printf("SV_BOUND failed: %s (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                       \
+        }                                                                                   \
+    } while (0)
+#else
+#define SV_BOUND(cond) ((void)0)
+#endif
+
 #define SV_MIN_VALUE 4.9406564584124654e-324  // java.lang.Double.MIN_VALUE
 #define SV_LN2 0.6931471805599453094
 #define SV_G 4                                 // genotype states (ScsFiniteMuExtendedModel.java:31-34)
@@ -52,6 +67,15 @@ __device__ __forceinline__ void sv_st256(double* p, const double (&v)[4]) {
 // one line into L2: no destination register, no scoreboard entry
 __device__ __forceinline__ void sv_prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// the walk's announcement of a leaf operand: L2 by default, L1 with -DSV_PF_L1 (experiment)
+__device__ __forceinline__ void sv_prefetch_leaf(const void* p) {
+#ifdef SV_PF_L1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
 }
 
 __device__ __forceinline__ double sv_max4(const double (&v)[4]) { return fmax(fmax(v[0], v[1]), fmax(v[2], v[3])); }

@@ -101,6 +101,7 @@ struct sieve_core {
     size_t last_stage_bytes = 0;
     bool last_qfast = false;
     bool force_generic = false;
+    unsigned long long pool_rows_part = 0, pool_rows_leaf = 0;  // rows (slot x site) of the partial / leaf pools (bounds-checked build)
     int pf_dist = 3;  // SIEVE_B200_PF_DIST: how many ops ahead the walk asks the TMA unit to bring operands into L2 (0: off)
     // streamed (SIEVE_FLAG_EPHEMERAL) evaluation: site chunks, a handful of scratch slots, leaves recomputed per chunk
     int chunk_cap = 0;   // sites per chunk == site capacity of the scratch pools
@@ -221,6 +222,11 @@ static int sv_alloc(sieve_core* h, T** p, size_t count) {
                        std::string("cudaMalloc of ") + std::to_string(b) + " bytes: " + cudaGetErrorString(e));
     }
     h->bytes += b;
+    // SIEVE_B200_POISON=1 (tests; compute-sanitizer's initcheck is not available on this pool): every pool starts as 0xFF
+    // bytes -- NaN as a double, -1 as an exponent or a count -- so a read of memory that no kernel or copy initialised
+    // shows up in the results instead of passing by luck on zeroed pages
+    static const bool poison = getenv("SIEVE_B200_POISON") && atoi(getenv("SIEVE_B200_POISON")) != 0;
+    if (poison && b) cudaMemset(*p, 0xFF, b);
     return SIEVE_OK;
 }
 #define SV_TRY(x)                    \

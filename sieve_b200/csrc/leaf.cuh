@@ -289,6 +289,7 @@ __device__ __forceinline__ void sv_leaf_nuc_terms(const int4 c, const double* __
                 // the shared-memory pipe for the entries that carry information
                 o[0] = o[1] = o[2] = o[3] = 0.0;
             } else if (COVERED || ci < C) {
+                SV_BOUND(ci < C);
                 const double2 u = *reinterpret_cast<const double2*>(dmA + 4 * ci);
                 const double2 w = *reinterpret_cast<const double2*>(dmA + 4 * ci + 2);
                 o[0] = u.x; o[1] = u.y; o[2] = w.x; o[3] = w.y;
@@ -310,6 +311,7 @@ __device__ __forceinline__ void sv_leaf_nuc_terms(const int4 c, const double* __
         s0 += T[1]; s1 += T[0]; s2 += T[3]; s3 += T[2];      // ref : (1-eps) | f | f | h
         double B0, B1;
         if (COVERED || (cov > 0 && cov < C)) {
+            SV_BOUND(cov > 0 && cov < C);
             const double2 u = *reinterpret_cast<const double2*>(dmB + 2 * cov);
             B0 = u.x; B1 = u.y;
         } else {
@@ -333,6 +335,7 @@ __device__ __forceinline__ void sv_leaf_site(const int4 c, const double* __restr
     sv_leaf_nuc_terms<COVERED>(c, dmA, dmB, C, a.al, N0, N1, N2, N3);
     double e[4];
     if (COVERED || (cov >= 0 && cov < C)) {
+        SV_BOUND(cov >= 0 && cov < C);
         if (CT_GLOBAL) {
             sv_leaf_row256(cT + 4 * cov, e);
         } else {

@@ -45,6 +45,8 @@ struct SvPruneArgs {
     double prop[4];        // category proportions at the root
     double* site_logl;     // [S]
     double* site_const;    // [S]
+    unsigned long long part_rows, leaf_rows;  // rows of the two pools (SV_BOUND only)
+    int n_matrix_slots;
 };
 
 __device__ __forceinline__ void sv_matvec(const double* __restrict__ M, const double (&x)[4], double (&y)[4]) {
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         const int m1 = o0.w, m2 = o1.x, flags = o1.y;
         const bool unary = flags & SV_OP_UNARY;
         const bool leaf1 = flags & SV_OP_LEAF1, leaf2 = flags & SV_OP_LEAF2;
+        SV_BOUND(m1 >= 0 && m1 < a.n_matrix_slots && (unary || (m2 >= 0 && m2 < a.n_matrix_slots)));
 #ifndef SV_PRUNE_NO_PF
         // leaf operands of the op pf_dist ahead: into L2 now
         announce((unsigned)o1.z, flags & SV_OP_PF1);
@@ -286,6 +289,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
 #pragma unroll
         for (int j = 0; j < NS; j++) {
             const size_t c1_row = c1_base + srow[j], c2_row = c2_base + srow[j];  // 32-bit sums, widened once
+            SV_BOUND((flags & SV_OP_FWD1) || c1_row < (leaf1 ? a.leaf_rows : a.part_rows));
+            SV_BOUND(unary || c2_row < (leaf2 ? a.leaf_rows : a.part_rows));
             if (!(flags & SV_OP_FWD1)) {
                 if (leaf1) {
                     sv_ld256_nc(LEAFK ? a.leafX + c1_row * 16 + k * 4 : a.leafX + c1_row * 4, x[j]);
@@ -431,6 +436,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
             // could otherwise overwrite a slot that the real lane of that site has not consumed yet
             if ((flags & SV_OP_NOSTORE) || !site_ok[j]) continue;
             const size_t dst_row = dst_base + srow[j];
+            SV_BOUND(dst_row < a.part_rows);
             sv_st256(a.part + dst_row * 16 + k * 4, x[j]);
             // every category lane writes the (identical) scale: a lane only ever re-reads what it wrote itself
             a.scale[dst_row] = xs[j];

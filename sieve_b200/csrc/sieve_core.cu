@@ -176,6 +176,8 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         CR(sv_alloc(h, &h->d_counts, n * S));
     CR(sv_alloc(h, &h->d_sf, n));
     CR(sv_alloc(h, &h->d_leafX, leaf_bufs * n * pool_sites * leaf_vals));
+    h->pool_rows_leaf = leaf_bufs * n * pool_sites;
+    h->pool_rows_part = part_slots * pool_sites;
     const size_t leaf_groups = (n + SV_LEAF_CELLS - 1) / SV_LEAF_CELLS;
     CR(sv_alloc(h, &h->d_sumS, leaf_groups * pool_sites));
     CR(sv_alloc(h, &h->d_lsum, 2 * S));
@@ -1184,6 +1186,9 @@ static int sv_launch_staged(sieve_core* h) {
         a.cpart = h->d_cpart;
         a.cscale = h->d_cscale;
         a.leafX = h->d_leafX;
+        a.part_rows = h->pool_rows_part;
+        a.leaf_rows = h->pool_rows_leaf;
+        a.n_matrix_slots = 2 * h->n_nodes;
         a.lsum = h->d_lsum + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S);
         a.mats = h->d_mats;
         a.qfac = h->d_qfac;

@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         for (int j = i0; j < jn; j++) {
             const int4 d0 = __ldg(reinterpret_cast<const int4*>(a.ops + j));
             const int fl = __ldg(reinterpret_cast<const int*>(a.ops + j) + 5);
-            if (fl & SV_OP_FAR1) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)d0.y + pf_srow) << 5));
-            if (fl & SV_OP_FAR2) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)d0.z + pf_srow) << 5));
+            if (fl & SV_OP_FAR1) sv_prefetch_leaf(leaf_base + ((size_t)((unsigned)d0.y + pf_srow) << 5));
+            if (fl & SV_OP_FAR2) sv_prefetch_leaf(leaf_base + ((size_t)((unsigned)d0.z + pf_srow) << 5));
         }
     }
 
@@ -89,11 +89,12 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         }
         const int flags = o1.y;
         // leaf operands of the op pf_dist ahead: into L2 now
-        if ((flags & SV_OP_PF1) && pf_lane) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)o1.z + pf_srow) << 5));
-        if ((flags & SV_OP_PF2) && pf_lane) sv_prefetch_l2(leaf_base + ((size_t)((unsigned)o1.w + pf_srow) << 5));
+        if ((flags & SV_OP_PF1) && pf_lane) sv_prefetch_leaf(leaf_base + ((size_t)((unsigned)o1.z + pf_srow) << 5));
+        if ((flags & SV_OP_PF2) && pf_lane) sv_prefetch_leaf(leaf_base + ((size_t)((unsigned)o1.w + pf_srow) << 5));
 
         const bool has2 = !(flags & SV_OP_UNARY);
         const bool cz0 = flags & SV_OP_ZEROD;
+        SV_BOUND(o0.w >= 0 && o0.w < a.n_matrix_slots);
         const double2 q1 = __ldg(a.qfac + (size_t)o0.w * SV_KMAX + k);
         double2 q2;
         double w[NS][4];
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
 #pragma unroll
             for (int j = 0; j < NS; j++) {
                 const unsigned row = (unsigned)o0.z + srow[j];
+                SV_BOUND(row < (leaf2 ? a.leaf_rows : a.part_rows) && o1.x >= 0 && o1.x < a.n_matrix_slots);
                 sv_ld256(reinterpret_cast<const double*>(sv_row_addr(base, row, stride)), w[j]);
                 we[j] = 0;
                 if (!leaf2) we[j] = *reinterpret_cast<const int*>(sv_row_addr(scale_base, row, 4u));
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
 #pragma unroll
             for (int j = 0; j < NS; j++) {
                 const unsigned row = (unsigned)o0.y + srow[j];
+                SV_BOUND(row < (leaf1 ? a.leaf_rows : a.part_rows));
                 sv_ld256(reinterpret_cast<const double*>(sv_row_addr(base, row, stride)), x[j]);
                 xe[j] = 0;
                 if (!leaf1) xe[j] = *reinterpret_cast<const int*>(sv_row_addr(scale_base, row, 4u));
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
             for (int j = 0; j < NS; j++) {
                 if (!site_ok[j]) continue;  // clamped duplicate lanes never store
                 const unsigned row = (unsigned)o0.x + srow[j];
+                SV_BOUND(row < a.part_rows);
                 sv_st256(reinterpret_cast<double*>(const_cast<char*>(sv_row_addr(part_base, row, 128u))), x[j]);
                 *reinterpret_cast<int*>(const_cast<char*>(sv_row_addr(scale_base, row, 4u))) = xe[j];  // every category lane writes the (identical) exponent
             }
