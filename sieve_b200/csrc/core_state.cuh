@@ -49,6 +49,9 @@ struct sieve_core {
     int* d_weights = nullptr;
     double* d_sf = nullptr;
     double *d_dmA = nullptr, *d_dmB = nullptr, *d_cellT = nullptr;
+    double *d_linA = nullptr, *d_linB = nullptr;  // linear-space twins of dmA / dmB (leaf.cuh, k_leaf_lin)
+    bool lin_range_ok = false;   // the current tables fit the 13-bit exponents of the linear tables
+    bool leaf_lin_allowed = true;  // SIEVE_B200_LEAF_LIN=0: always the log-space leaf kernels (A/B, tests)
     int C = 0;  // table entries per table
     int max_cov = -1;
     double* d_leafX = nullptr;                                                           // [2][n][S][4]

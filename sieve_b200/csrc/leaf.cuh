@@ -68,17 +68,53 @@ __host__ __device__ inline SvDmAlphas sv_dm_alphas(double eps, double w1, double
     return a;
 }
 
-__global__ void k_build_dm_tables(double* __restrict__ dmA, double* __restrict__ dmB, int C, SvDmAlphas al) {
+// exp(y) = m * 2^e with m in [1, 2): Cody-Waite reduction, so that |y| up to a few thousand keeps full precision
+__device__ __forceinline__ void sv_split_exp(double y, double* m_out, int* e_out) {
+    const double kf = rint(y * 1.4426950408889634074);
+    double r = fma(-kf, 6.93147180369123816490e-01, y);   // ln 2, high part (fdlibm)
+    r = fma(-kf, 1.90821492927058770002e-10, r);           // ln 2, low part
+    double m = exp(r);                                     // [0.70, 1.42]
+    int k = (int)kf;
+    if (m < 1.0) {
+        m *= 2.0;
+        k -= 1;
+    }
+    *m_out = m;
+    *e_out = k;
+}
+#define SV_LIN_BIAS 4096      // bias of the 16-bit binary exponents of the linear tables
+#define SV_LIN_MAX_LOG 2700.0 // largest |LP| the 13-bit exponents hold with room to spare (host check, sv_lin_tables_ok)
+#define SV_LINA_STRIDE 6      // doubles per row: 48 bytes, so that 8 consecutive rows start in 8 different groups of 4 banks
+#define SV_LINB_STRIDE 6
+
+// The same tables in LINEAR space for the default leaf kernel (k_leaf_lin): the reciprocals exp(-LP(c, alpha)) of the four
+// denominators' columns and exp(+LP(c, alpha)) of the two numerators, each as a mantissa in [1, 2) and a biased 16-bit
+// binary exponent, so that a Dirichlet-multinomial likelihood is five multiplications per genotype instead of four sums
+// and an exp: the leaf kernel is bound by the FP64 pipe, and the four exp were most of its FP64 work.
+//   linA[c] = { m0, m1, m2, m3, (e0 | e1 << 16 | e2 << 32 | e3 << 48) }      (48-byte rows)
+//   linB[c] = { m0, m1, (e0 | e1 << 16) }                                    (48-byte rows); linB[0] = e^1: the cov == 0 quirk
+__global__ void k_build_dm_tables(double* __restrict__ dmA, double* __restrict__ dmB, double* __restrict__ linA,
+                                  double* __restrict__ linB, int C, SvDmAlphas al) {
     // one thread per (count, column): six short logGamma chains per count instead of one long one
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = idx / 6, col = idx % 6;
     if (c >= C) return;
     const double alpha = col == 0 ? al.fw1 : col == 1 ? al.omw1 : col == 2 ? al.hw2 : col == 3 ? al.fw2 : col == 4 ? al.w1 : al.w2;
     const double v = sv_dm_log_partial(c, alpha);
-    if (col < 4)
+    double m;
+    int e;
+    if (col < 4) {
         dmA[4 * c + col] = v;
-    else
+        sv_split_exp(-v, &m, &e);
+        linA[SV_LINA_STRIDE * c + col] = m;
+        reinterpret_cast<unsigned short*>(linA + SV_LINA_STRIDE * c + 4)[col] = (unsigned short)(e + SV_LIN_BIAS);
+    } else {
         dmB[2 * c + (col - 4)] = v;
+        // DirichletMultinomial.logDensity returns 1.0 for an empty site (:29-30): row 0 is only ever read when cov == 0
+        sv_split_exp(c == 0 ? 1.0 : v, &m, &e);
+        linB[SV_LINB_STRIDE * c + (col - 4)] = m;
+        reinterpret_cast<unsigned short*>(linB + SV_LINB_STRIDE * c + 2)[col - 4] = (unsigned short)(e + SV_LIN_BIAS);
+    }
 }
 
 struct SvCovParams {
@@ -234,6 +270,7 @@ struct SvLeafArgs {
     const double* dmA;      // [C][4]
     const double* dmB;      // [C][2]
     const double* cellT;    // [cell][C][4]
+    const double *linA, *linB;  // linear-space tables of k_leaf_lin (k_build_dm_tables)
     const double* size_factors;
     const int* cell_list;   // NULL: entry e is cell e; else the cells to evaluate (read-back of a subtree's sums)
     double* leafX;          // [cell][site][4] (already offset to the write buffer), or NULL: sums only
@@ -474,5 +511,192 @@ __global__ void __launch_bounds__(SV_LEAF_THREADS, 2) k_leaf(SvLeafArgs a) {
         if (s >= a.S) continue;
         a.sumS[(size_t)blockIdx.y * a.sum_stride + s] = accS[it];
         if (want0) a.sum0[(size_t)blockIdx.y * a.sum_stride + s] = acc0[it];
+    }
+}
+
+
+// ---- the default leaf kernel: linear-space Dirichlet-multinomial terms --------------------------------------------------
+// Same model, same outputs and the same block / cell-group structure as k_leaf<1, true>; what differs is how the four
+// nucleotide likelihoods are formed: as products of tabulated (mantissa, exponent) pairs (k_build_dm_tables) instead of
+// exp(sum of tabulated logs - max).  No transcendental is evaluated per (cell, site) -- ncu had the FP64 pipe and the
+// issue slots of k_leaf<1, true> as its limiters, four exp being two thirds of its FP64 instructions -- and the scale of
+// a leaf is an exact power of two times the coverage table's maximum, summed as an integer.  The constant genotype's
+// log-likelihood (the column sum of the algebraic constant-site path) is accumulated as a running product over the
+// group's cells and logged once per (group, site).
+// Preconditions (host, sv_leaf_lin_ok): every count inside the tables, single dropout, constant genotype 0, tables within
+// the exponent range and small enough for shared memory; otherwise k_leaf<...> runs.
+// 512 threads x 2 sites per thread, two blocks per SM (64 registers): 32 resident warps.  Measured against 256 x 4 at two
+// and three blocks per SM, 512 x 1, 1024 x 1 / 2 (profiles/README.md): the kernel is bound by exposed latency (shared-memory
+// and L1 look-ups), so resident warps count, and two blocks of 512 stage the tables half as often as four of 256.
+#ifndef SV_LEAFL_THREADS
+#define SV_LEAFL_THREADS 512
+#endif
+#ifndef SV_LEAFL_IT
+#define SV_LEAFL_IT 2
+#endif
+#ifndef SV_LEAFL_MINB
+#define SV_LEAFL_MINB 2
+#endif
+#define SV_LEAFL_SITES (SV_LEAFL_THREADS * SV_LEAFL_IT)
+__global__ void __launch_bounds__(SV_LEAFL_THREADS, SV_LEAFL_MINB) k_leaf_lin(SvLeafArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int C = a.C;
+    const int e0c = blockIdx.y * SV_LEAF_CELLS;
+    const int e1c = min(a.n_cells, e0c + SV_LEAF_CELLS);
+    const int tid = threadIdx.x;
+    double* sA = sm;
+    double* sB = sm + SV_LINA_STRIDE * (size_t)C;
+    for (int i = tid; i < SV_LINA_STRIDE * C; i += SV_LEAFL_THREADS) sA[i] = a.linA[i];
+    for (int i = tid; i < SV_LINB_STRIDE * C; i += SV_LEAFL_THREADS) sB[i] = a.linB[i];
+    __syncthreads();
+    const int sbase = blockIdx.x * SV_LEAFL_SITES + tid;
+    const bool want0 = a.sum0 != nullptr;
+    constexpr unsigned BIAS2 = ((unsigned)SV_LIN_BIAS << 16) | (unsigned)SV_LIN_BIAS;
+    double accS[SV_LEAFL_IT], acc0m[SV_LEAFL_IT];
+    int accE[SV_LEAFL_IT], acc0e[SV_LEAFL_IT];
+#pragma unroll
+    for (int it = 0; it < SV_LEAFL_IT; it++) {
+        accS[it] = 0.0;
+        acc0m[it] = 1.0;
+        accE[it] = acc0e[it] = 0;
+    }
+    // the count tuples of the NEXT cell are requested while this cell's sites are evaluated: with no transcendental left,
+    // the DRAM latency of that load is what a warp would otherwise wait for once per cell
+    int4 cn[SV_LEAFL_IT];
+    {
+        const int j0 = a.cell_list ? a.cell_list[e0c] : e0c;
+        const int4* cnt = a.counts + (size_t)j0 * a.counts_stride + a.site_begin;
+#pragma unroll
+        for (int it = 0; it < SV_LEAFL_IT; it++) {
+            const int s = sbase + it * SV_LEAFL_THREADS;
+            cn[it] = s < a.S ? __ldg(cnt + s) : make_int4(0, 0, 0, 0);
+        }
+    }
+    for (int e = e0c; e < e1c; e++) {
+        const int j = a.cell_list ? a.cell_list[e] : e;
+        const double* cT = a.cellT + (size_t)j * C * 4;
+        double* outX = a.leafX ? a.leafX + (size_t)j * a.out_stride * 4 : nullptr;
+        int4 c[SV_LEAFL_IT];
+#pragma unroll
+        for (int it = 0; it < SV_LEAFL_IT; it++) c[it] = cn[it];
+        if (e + 1 < e1c) {
+            const int jn = a.cell_list ? a.cell_list[e + 1] : e + 1;
+            const int4* cnt = a.counts + (size_t)jn * a.counts_stride + a.site_begin;
+#pragma unroll
+            for (int it = 0; it < SV_LEAFL_IT; it++) {
+                const int s = sbase + it * SV_LEAFL_THREADS;
+                if (s < a.S) cn[it] = __ldg(cnt + s);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < SV_LEAFL_IT; it++) {
+            const int s = sbase + it * SV_LEAFL_THREADS;
+            if (s >= a.S) continue;
+            const int cov = c[it].w;
+            const int ref = max(cov - (c[it].x + c[it].y + c[it].z), 0);
+            SV_BOUND(cov >= 0 && cov < C && c[it].x >= 0 && c[it].x < C && c[it].y >= 0 && c[it].y < C && c[it].z >= 0 &&
+                     c[it].z < C && ref < C);
+            // the coverage mixture of this (cell, coverage): one 256-bit row through L1 (k_build_cell_tables)
+            double ce[4];
+            sv_leaf_row256(cT + 4 * cov, ce);
+            // numerators: genotypes 0/0 and 1/1 take alpha0 = w1, 1/1' and 0/1 take w2
+            const double2 bm = *reinterpret_cast<const double2*>(sB + SV_LINB_STRIDE * cov);
+            const unsigned be = *reinterpret_cast<const unsigned*>(sB + SV_LINB_STRIDE * cov + 2);
+            double v0 = bm.x, v1 = bm.x, v2 = bm.y, v3 = bm.y;
+            unsigned elo = __byte_perm(be, 0, 0x1010), ehi = __byte_perm(be, 0, 0x3232);  // exponents of (g0, g1), (g2, g3)
+            // denominators (reciprocals); table columns: [0] f*w1, [1] (1-eps)*w1, [2] (1/2-f)*w2, [3] f*w2
+            //   alt1: 0/0 f | 1/1 (1-eps) | 1/1' h | 0/1 h     alt2: f | f | h | f     alt3: f | f | f | f     ref: (1-eps) | f | f | h
+            // (a zero count contributes the factor 1: only the exponent bias is added)
+            if (c[it].x > 0) {
+                const double* r = sA + SV_LINA_STRIDE * c[it].x;
+                const double2 u = *reinterpret_cast<const double2*>(r);
+                const double2 w = *reinterpret_cast<const double2*>(r + 2);
+                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
+                v0 *= u.x; v1 *= u.y; v2 *= w.x; v3 *= w.x;
+                elo += pe.x;
+                ehi += __byte_perm(pe.y, 0, 0x1010);
+            } else {
+                elo += BIAS2;
+                ehi += BIAS2;
+            }
+            if (c[it].y > 0) {
+                const double* r = sA + SV_LINA_STRIDE * c[it].y;
+                const double2 u = *reinterpret_cast<const double2*>(r);
+                const double2 w = *reinterpret_cast<const double2*>(r + 2);
+                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
+                v0 *= u.x; v1 *= u.x; v2 *= w.x; v3 *= w.y;
+                elo += __byte_perm(pe.x, 0, 0x1010);
+                ehi += pe.y;
+            } else {
+                elo += BIAS2;
+                ehi += BIAS2;
+            }
+            if (c[it].z > 0) {
+                const double* r = sA + SV_LINA_STRIDE * c[it].z;
+                const double2 u = *reinterpret_cast<const double2*>(r);
+                const double2 w = *reinterpret_cast<const double2*>(r + 2);
+                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
+                v0 *= u.x; v1 *= u.x; v2 *= w.y; v3 *= w.y;
+                elo += __byte_perm(pe.x, 0, 0x1010);
+                ehi += __byte_perm(pe.y, 0, 0x3232);
+            } else {
+                elo += BIAS2;
+                ehi += BIAS2;
+            }
+            if (ref > 0) {
+                const double* r = sA + SV_LINA_STRIDE * ref;
+                const double2 u = *reinterpret_cast<const double2*>(r);
+                const double2 w = *reinterpret_cast<const double2*>(r + 2);
+                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
+                v0 *= u.y; v1 *= u.x; v2 *= w.y; v3 *= w.x;
+                elo += __byte_perm(pe.x, 0, 0x1032);  // (e1, e0)
+                ehi += __byte_perm(pe.y, 0, 0x1032);  // (e3, e2)
+            } else {
+                elo += BIAS2;
+                ehi += BIAS2;
+            }
+            // common binary scale of the four likelihoods: the largest exponent; a genotype more than 2^-1000 below it is
+            // flushed to that floor (the documented limit of the scaled representation)
+            const int E0 = (int)(elo & 0xffffu), E1 = (int)(elo >> 16), E2 = (int)(ehi & 0xffffu), E3 = (int)(ehi >> 16);
+            const int Emax = max(max(E0, E1), max(E2, E3));
+            const double n0 = v0 * __hiloint2double((1023 + max(E0 - Emax, -1000)) << 20, 0);
+            const double n1 = v1 * __hiloint2double((1023 + max(E1 - Emax, -1000)) << 20, 0);
+            const double n2 = v2 * __hiloint2double((1023 + max(E2 - Emax, -1000)) << 20, 0);
+            const double n3 = v3 * __hiloint2double((1023 + max(E3 - Emax, -1000)) << 20, 0);
+            // RawReadCountsModelFiniteMuDM.java:133-225, single-dropout arms, as in sv_leaf_site
+            const double both = ce[0] + ce[1];
+            double x[4];
+            x[0] = n0 * both;
+            x[1] = n3 * ce[0] + 0.5 * (n0 + n1) * ce[1];
+            x[2] = n1 * both;
+            x[3] = n2 * ce[0] + n1 * ce[1];
+            int e2;
+            const double f = sv_pow2_rescale_hi_int(sv_maxhi4(x), &e2);
+            x[0] *= f; x[1] *= f; x[2] *= f; x[3] *= f;
+            if (outX) sv_st256(outX + (size_t)s * 4, x);
+            // log scale of this leaf = ce[2] + (Emax - 5 bias + e2) ln 2: the table part as a double, the rest as an integer
+            accS[it] += ce[2];
+            accE[it] += Emax - 5 * SV_LIN_BIAS + e2;
+            if (want0) {
+                // constant genotype 0/0: log-likelihood = log(v0 * both) + (E0 - 5 bias) ln 2 + ce[2], kept as a running
+                // product (mantissa renormalised every cell) so that the log is taken once per (cell group, site)
+                double p = acc0m[it] * (v0 * both);
+                const int hi = __double2hiint(p);
+                const int ex = ((hi >> 20) & 0x7ff) - 1023;
+                if ((unsigned)ex < 256u) {  // finite, >= 1: always, unless a table entry is NaN (which then propagates)
+                    p = __hiloint2double(hi - (ex << 20), __double2loint(p));
+                    acc0e[it] += ex;
+                }
+                acc0m[it] = p;
+                acc0e[it] += E0 - 5 * SV_LIN_BIAS;
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < SV_LEAFL_IT; it++) {
+        const int s = sbase + it * SV_LEAFL_THREADS;
+        if (s >= a.S) continue;
+        a.sumS[(size_t)blockIdx.y * a.sum_stride + s] = fma((double)accE[it], SV_LN2, accS[it]);
+        if (want0) a.sum0[(size_t)blockIdx.y * a.sum_stride + s] = fma((double)acc0e[it], SV_LN2, accS[it]) + log(acc0m[it]);
     }
 }

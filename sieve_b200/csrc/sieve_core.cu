@@ -64,6 +64,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     if (const char* e = getenv("SIEVE_B200_PRUNE_MINB")) h->prune_minb = atoi(e);
     if (const char* e = getenv("SIEVE_B200_PF_DIST")) h->pf_dist = std::max(0, std::min(64, atoi(e)));
     if (const char* e = getenv("SIEVE_B200_LEAF_TAB")) h->leaf_tab = std::min(2, std::max(0, atoi(e)));
+    if (const char* e = getenv("SIEVE_B200_LEAF_LIN")) h->leaf_lin_allowed = atoi(e) != 0;
     if (const char* e = getenv("SIEVE_B200_LEAF_CHECKED")) h->leaf_force_checked = atoi(e) != 0;
     const bool twin = h->with_const && h->const_twin;
     const bool algebraic = h->with_const && !h->const_twin;
@@ -255,6 +256,8 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_dmA);
     cudaFree(h->d_dmB);
     cudaFree(h->d_cellT);
+    cudaFree(h->d_linA);
+    cudaFree(h->d_linB);
     cudaFree(h->d_leafX);
     cudaFree(h->d_sumS);
     cudaFree(h->d_sum0);
@@ -363,10 +366,16 @@ static int sv_alloc_tables(sieve_core* h) {
         cudaFree(h->d_dmA);
         cudaFree(h->d_dmB);
         cudaFree(h->d_cellT);
-        h->d_dmA = h->d_dmB = h->d_cellT = nullptr;
+        cudaFree(h->d_linA);
+        cudaFree(h->d_linB);
+        h->d_dmA = h->d_dmB = h->d_cellT = h->d_linA = h->d_linB = nullptr;
         h->C = std::max(C, 1);
         SV_TRY(sv_alloc(h, &h->d_dmA, (size_t)h->C * 4));
         SV_TRY(sv_alloc(h, &h->d_dmB, (size_t)h->C * 2));
+        SV_TRY(sv_alloc(h, &h->d_linA, (size_t)h->C * SV_LINA_STRIDE));
+        SV_TRY(sv_alloc(h, &h->d_linB, (size_t)h->C * SV_LINB_STRIDE));
+        SV_CUDA(cudaMemsetAsync(h->d_linA, 0, (size_t)h->C * SV_LINA_STRIDE * sizeof(double), h->stream));  // the rows' padding
+        SV_CUDA(cudaMemsetAsync(h->d_linB, 0, (size_t)h->C * SV_LINB_STRIDE * sizeof(double), h->stream));
         SV_TRY(sv_alloc(h, &h->d_cellT, (size_t)h->n * h->C * 4));
     }
     h->dm_dirty = h->cov_dirty = true;
@@ -651,6 +660,26 @@ extern "C" int sieve_set_leaf_params(sieve_core_t* h, const sieve_leaf_params_t*
 }
 
 // brings the look-up tables of the leaf kernel up to date with h->lp
+// Do the linear-space tables hold every entry?  |LP(c, alpha)| grows monotonically with c, so the last row decides (and the
+// first, for a tiny alpha); a non-positive alpha makes the entries NaN, which the tables carry like the log-space ones do.
+static bool sv_lin_tables_ok(const SvDmAlphas& al, int C) {
+    const double alphas[6] = {al.fw1, al.omw1, al.hw2, al.fw2, al.w1, al.w2};
+    for (double a : alphas) {
+        if (!(a > 0.0)) continue;
+        for (double c : {1.0, (double)std::max(C - 1, 1)}) {
+            const double lp = std::log(c) + std::lgamma(a) + std::lgamma(c) - std::lgamma(a + c);
+            if (!(std::fabs(lp) <= SV_LIN_MAX_LOG)) return false;
+        }
+    }
+    return true;
+}
+// Does the default leaf kernel (k_leaf_lin) apply?  Every count inside the tables, single dropout, constant genotype 0, the
+// tables in range and small enough for two blocks per SM to stage them in shared memory.
+static bool sv_leaf_lin_ok(const sieve_core* h) {
+    return h->leaf_lin_allowed && h->tables_cover_counts && h->single_ado && h->const_genotype == 0 && h->lin_range_ok &&
+           h->leaf_tab == 1 && (size_t)h->C * (SV_LINA_STRIDE + SV_LINB_STRIDE) * sizeof(double) <= 100 * 1024;
+}
+
 static int sv_refresh_leaf_tables(sieve_core* h, SvDmAlphas* al_out, SvCovParams* cp_out) {
     const SvDmAlphas al = sv_dm_alphas(h->lp.eff_seq_err_rate, h->lp.shape_ctrl1, h->lp.shape_ctrl2);
     SvCovParams cp;
@@ -669,9 +698,10 @@ static int sv_refresh_leaf_tables(sieve_core* h, SvDmAlphas* al_out, SvCovParams
         h->cov_dirty = true;
     h->tab_lp = h->lp;
     if (h->dm_dirty) {
-        k_build_dm_tables<<<(6 * C + 127) / 128, 128, 0, h->stream>>>(h->d_dmA, h->d_dmB, C, al);
+        k_build_dm_tables<<<(6 * C + 127) / 128, 128, 0, h->stream>>>(h->d_dmA, h->d_dmB, h->d_linA, h->d_linB, C, al);
         sv_count(h);
         h->dm_dirty = false;
+        h->lin_range_ok = sv_lin_tables_ok(al, C);
     }
     if (h->cov_dirty && h->private_cov) h->cov_dirty = false;  // the coverage terms are evaluated directly (leaf_private.cuh)
     if (h->cov_dirty) {
@@ -700,6 +730,8 @@ static int sv_launch_leaf_kernels(sieve_core* h, long long site_begin, int n_sit
     a.dmA = h->d_dmA;
     a.dmB = h->d_dmB;
     a.cellT = h->d_cellT;
+    a.linA = h->d_linA;
+    a.linB = h->d_linB;
     a.size_factors = h->d_sf;
     a.cell_list = d_cell_list;
     a.leafX = leafX;
@@ -725,9 +757,14 @@ static int sv_launch_leaf_kernels(sieve_core* h, long long site_begin, int n_sit
         SV_CUDA(cudaFuncSetAttribute(k_leaf<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         SV_CUDA(cudaFuncSetAttribute(k_leaf<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         SV_CUDA(cudaFuncSetAttribute(k_leaf<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        SV_CUDA(cudaFuncSetAttribute(k_leaf_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         h->leaf_attr_set = true;
     }
-    if (tab == 2)
+    if (sv_leaf_lin_ok(h)) {
+        dim3 gl((n_sites + SV_LEAFL_SITES - 1) / SV_LEAFL_SITES, groups);
+        k_leaf_lin<<<gl, SV_LEAFL_THREADS, (size_t)C * (SV_LINA_STRIDE + SV_LINB_STRIDE) * sizeof(double), h->stream>>>(a);
+    }
+    else if (tab == 2)
         k_leaf<2><<<grid, SV_LEAF_THREADS, smem, h->stream>>>(a);
     else if (tab == 1 && h->tables_cover_counts)
         k_leaf<1, true><<<grid, SV_LEAF_THREADS, smem, h->stream>>>(a);

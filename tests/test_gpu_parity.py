@@ -48,9 +48,9 @@ def _oracle_eval(oracle, counts, tree, sf, params, mats, props, asc, M=0.0, weig
 PARAMS = (0.3, 50.0, 50.0, 0.008, 150.0, 2.0)
 
 
-def _close(a, b, rtol):
+def _close(a, b, rtol, atol=0.0):
     a, b = np.asarray(a), np.asarray(b)
-    assert np.all(np.abs(a - b) <= rtol * np.abs(b)), (np.abs(a - b) / np.abs(b)).max()
+    assert np.all(np.abs(a - b) <= rtol * np.abs(b) + atol), (np.abs(a - b) / (np.abs(b) + atol)).max()
 
 
 @pytest.mark.parametrize("tag", ["cells10", "cells40"])
@@ -242,13 +242,16 @@ def test_leaf_scale_sums_over_cell_groups_and_site_blocks(core_mod, oracle, monk
 
 
 def test_leaf_kernel_without_bounds_checks_is_bit_identical(core_mod, monkeypatch):
-    """When the ingest scan finds every count inside the look-up tables the leaf kernel runs without its out-of-table
-    paths (k_leaf<1, true>); SIEVE_B200_LEAF_CHECKED=1 keeps them.  Same arithmetic, so the same bits -- also when the
-    tables are capped below the largest count, where the unchecked kernel must not be chosen at all."""
+    """When the ingest scan finds every count inside the look-up tables the log-space leaf kernel runs without its
+    out-of-table paths (k_leaf<1, true>); SIEVE_B200_LEAF_CHECKED=1 keeps them.  Same arithmetic, so the same bits -- also
+    when the tables are capped below the largest count, where the unchecked kernel must not be chosen at all.
+    (SIEVE_B200_LEAF_LIN=0: the log-space kernels on both sides.)  The default kernel, k_leaf_lin, forms the same
+    likelihoods as products of tabulated mantissa / exponent pairs: equal to rounding, leaf by leaf and site by site."""
     from sieve_b200.treelikelihood import ScsTreeLikelihood
     d = synthetic(37, 1300, seed=19)
     counts, tree = d["counts"], d["tree"]
     out = {}
+    monkeypatch.setenv("SIEVE_B200_LEAF_LIN", "0")
     for cap in (None, "24"):
         for checked in ("0", "1"):
             monkeypatch.setenv("SIEVE_B200_LEAF_CHECKED", checked)
@@ -271,6 +274,22 @@ def test_leaf_kernel_without_bounds_checks_is_bit_identical(core_mod, monkeypatc
             _close(got[1], ref[1], SITE_RTOL)
             _close(got[2], ref[2], SITE_RTOL)
     np.testing.assert_array_equal(out[("24", "0")][1], out[("24", "1")][1])
+    # the default kernel against the log-space one
+    monkeypatch.setenv("SIEVE_B200_LEAF_CHECKED", "0")
+    monkeypatch.delenv("SIEVE_B200_TABLE_CAP", raising=False)
+    tl0 = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=1000.0)
+    tl0.calculate_logp()
+    monkeypatch.delenv("SIEVE_B200_LEAF_LIN", raising=False)
+    tl = ScsTreeLikelihood(counts, tree.copy(), asc_mode="felsenstein_mean", n_background_sites=1000.0)
+    logp = tl.calculate_logp()
+    site, const = tl.pattern_log_likelihoods()
+    for leaf in range(0, tree.n, 4):
+        _close(tl.core.get_node_partials(leaf), tl0.core.get_node_partials(leaf), 1e-12, 1e-12)
+    tl.close()
+    tl0.close()
+    _close(site, ref[1], 1e-13)
+    _close(const, ref[2], 1e-13)
+    assert abs(logp - ref[0]) <= 1e-12 * abs(ref[0])
 
 
 def test_leaf_kernel_all_cells_and_edge_counts(core_mod, oracle, monkeypatch):
