@@ -95,13 +95,15 @@ static void sv_slot_bounds(sieve_core* h, const PendingMatrix& pm) {
     static const double P1[16] = {3, 6, -3, -6, 1, 2, -1, -2, -1, -2, 1, 2, -1, -2, 1, 2};     // 8 Pi1
     static const double P2[16] = {9, -18, 3, 6, -3, 6, -1, -2, 1, -2, 11, -10, 1, -2, -5, 6};  // 16 Pi2
     double mn = INFINITY, mnd = INFINITY;
-    for (int k = 0; k < K; k++)
+    for (int k = 0; k < K; k++) {
+        // (one pair of expm1 per category: this runs for every new matrix of a step, 2 000 of them in a whole-tree move)
+        const double d = pm.is_distance ? pv[k] : 0.0;
+        const double g1 = pm.is_distance ? expm1(-0.2 * d) : 0.0;  // expm1(-0.4 d) = g1 (g1 + 2)
+        const double q1 = g1 / 8.0, q2 = g1 * (g1 + 2.0) / 16.0;
         for (int e = 0; e < 16; e++) {
             double v;
             if (pm.is_distance) {
-                const double d = pv[k];
-                const double g1 = expm1(-0.2 * d), g2 = expm1(-0.4 * d);
-                v = ((e % 5 == 0) ? 1.0 : 0.0) + (g1 / 8.0) * P1[e] + (g2 / 16.0) * P2[e];
+                v = ((e % 5 == 0) ? 1.0 : 0.0) + q1 * P1[e] + q2 * P2[e];
                 if (d == 0.0) v = (e % 5 == 0) ? 1.0 : 0.0;
             } else
                 v = pv[k * 16 + e];
@@ -110,6 +112,7 @@ static void sv_slot_bounds(sieve_core* h, const PendingMatrix& pm) {
             mn = std::min(mn, v);
             if (e % 5 == 0) mnd = std::min(mnd, v);
         }
+    }
     // (the closed form above differs from the device's by rounding only; two binades of slack cover it)
     const int b = sv_floor_log2(mn), bd = sv_floor_log2(mnd);
     h->slot_b[pm.slot] = b == SV_BOUND_NONE ? b : b - 2;

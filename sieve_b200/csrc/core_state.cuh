@@ -77,9 +77,15 @@ struct sieve_core {
     unsigned int* d_counter = nullptr;
     double* d_result = nullptr;
     // staging
-    char* h_stage = nullptr;  // pinned
+    // staging of a step's ops and matrices: two halves used in turn, so that a flush can fill one while the kernels of the
+    // previous step still read the other (no stream synchronisation between the leaf kernels and the walk's launch)
+    char* h_stage = nullptr;  // pinned; the half the CURRENT step was staged in
     char* d_stage = nullptr;
-    size_t stage_cap = 0;
+    char *h_stage_base = nullptr, *d_stage_base = nullptr;
+    int stage_sel = 0;
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // recorded after the last launch that reads the half
+    bool ev_stage_set[2] = {false, false};
+    size_t stage_cap = 0;     // bytes per half
     double* h_result = nullptr;  // pinned, 8 doubles
 
     // host bookkeeping
@@ -238,20 +244,27 @@ static int sv_alloc(sieve_core* h, T** p, size_t count) {
         if (r__ != SIEVE_OK) return r__; \
     } while (0)
 
+// makes the OTHER half current, large enough for `bytes`, and waits until nothing in flight reads it any more
 static int sv_ensure_stage(sieve_core* h, size_t bytes) {
-    if (bytes <= h->stage_cap) return SIEVE_OK;
-    size_t cap = std::max<size_t>(bytes, std::max<size_t>(h->stage_cap * 2, (size_t)1 << 16));
-    SV_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->h_stage) cudaFreeHost(h->h_stage);
-    if (h->d_stage) {
-        cudaFree(h->d_stage);
-        h->bytes -= h->stage_cap;
+    if (bytes > h->stage_cap) {
+        size_t cap = std::max<size_t>(bytes, std::max<size_t>(h->stage_cap * 2, (size_t)1 << 16));
+        cap = (cap + 255) & ~(size_t)255;
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->h_stage_base) cudaFreeHost(h->h_stage_base);
+        if (h->d_stage_base) {
+            cudaFree(h->d_stage_base);
+            h->bytes -= 2 * h->stage_cap;
+        }
+        h->h_stage_base = h->d_stage_base = h->h_stage = h->d_stage = nullptr;
+        h->stage_cap = 0;
+        h->ev_stage_set[0] = h->ev_stage_set[1] = false;
+        SV_CUDA(cudaMallocHost((void**)&h->h_stage_base, 2 * cap));
+        SV_TRY(sv_alloc(h, &h->d_stage_base, 2 * cap));
+        h->stage_cap = cap;
     }
-    h->h_stage = nullptr;
-    h->d_stage = nullptr;
-    h->stage_cap = 0;
-    SV_CUDA(cudaMallocHost((void**)&h->h_stage, cap));
-    SV_TRY(sv_alloc(h, &h->d_stage, cap));
-    h->stage_cap = cap;
+    h->stage_sel ^= 1;
+    h->h_stage = h->h_stage_base + (size_t)h->stage_sel * h->stage_cap;
+    h->d_stage = h->d_stage_base + (size_t)h->stage_sel * h->stage_cap;
+    if (h->ev_stage_set[h->stage_sel]) SV_CUDA(cudaEventSynchronize(h->ev_stage[h->stage_sel]));  // two flushes ago: long done
     return SIEVE_OK;
 }

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+#include <cstdio>
 #include "../../include/sieve_b200.h"
 #include "common.cuh"
 #include "leaf.cuh"
@@ -241,6 +243,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
         return fail(SIEVE_ERR_CUDA);
     }
     for (int i = 0; i < 6; i++) cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&h->ev_stage[i], cudaEventDisableTiming);
     cudaStreamSynchronize(h->stream);
     *out = h;
     return SIEVE_OK;
@@ -291,8 +294,10 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     if (h->comm && sv_nccl().ok) sv_nccl().CommDestroy(h->comm);
     cudaFree(h->d_gather);
     if (h->h_gather) cudaFreeHost(h->h_gather);
-    cudaFree(h->d_stage);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
+    cudaFree(h->d_stage_base);
+    if (h->h_stage_base) cudaFreeHost(h->h_stage_base);
+    for (int i = 0; i < 2; i++)
+        if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
     if (h->h_result) cudaFreeHost(h->h_result);
     for (int i = 0; i < 6; i++)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1289,8 +1294,28 @@ static int sv_launch_staged(sieve_core* h) {
 }
 
 // uploads pending matrices / distances + ops with ONE host->device copy and launches scatter + pruning
+// SIEVE_B200_HOST_PROF=1: wall time of the host phases of a flush on stderr (diagnostic)
+struct SvHostProf {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    double us[6] = {0, 0, 0, 0, 0, 0};
+    SvHostProf() : on(getenv("SIEVE_B200_HOST_PROF") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(int i) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        us[i] += std::chrono::duration<double, std::micro>(t1 - t0).count();
+        t0 = t1;
+    }
+    void report(size_t no, size_t nm) {
+        if (on && no > 8)
+            fprintf(stderr, "sv_flush host us: matrices %.0f plan %.0f link %.0f stage+launch %.0f const-factors %.0f (ops %zu, matrices %zu)\n",
+                    us[0], us[1], us[2], us[3], us[4], no, nm);
+    }
+};
+
 static int sv_flush(sieve_core* h) {
     const int K = h->K;
+    SvHostProf prof;
     // slot attributes first: the op builders look at them.  Only the last entry of a slot counts.  With change tracking on,
     // an entry that repeats what its slot already holds is dropped, and one that repeats what the node's OTHER matrix
     // buffer holds (the usual case when a caller refreshes the matrices of unchanged branches after flipping them) is
@@ -1345,6 +1370,7 @@ static int sv_flush(sieve_core* h) {
                 sv_slot_bounds(h, pm);
         }
     }
+    prof.lap(0);
     if (h->ephemeral)
         SV_TRY(sv_build_streamed_ops(h));
     else if (h->pending_per_level) {
@@ -1360,6 +1386,7 @@ static int sv_flush(sieve_core* h) {
         h->pending_level_triples.clear();
     } else if (!h->dirty_list.empty() || !h->demand_list.empty())
         SV_TRY(sv_plan_resident_ops(h));
+    prof.lap(1);
     const size_t no = h->pending_ops.size();
     size_t nm = 0, nd = 0;
     for (const PendingMatrix& pm : h->pending_mats)
@@ -1377,14 +1404,14 @@ static int sv_flush(sieve_core* h) {
     const size_t off_ms = off_dv + nd * K * sizeof(double);
     const size_t off_ds = off_ms + nm * sizeof(int);
     const size_t total = off_ds + nd * sizeof(int);
-    SV_TRY(sv_ensure_stage(h, total));
-    SV_CUDA(cudaStreamSynchronize(h->stream));  // the previous step may still be reading the staging buffer
+    SV_TRY(sv_ensure_stage(h, total));  // the other half: the previous step's kernels may still be reading theirs
     sv_link_forwarding(h->pending_ops, h->pending_per_level);
     if (no) {
         std::vector<SvOp>& ops = h->pending_ops;
         sv_link_prefetch(ops, h->pending_per_level ? 0 : h->pf_dist);
         memcpy(h->h_stage, ops.data(), no * sizeof(SvOp));
     }
+    prof.lap(2);
     size_t im = 0, id = 0;
     for (const PendingMatrix& pm : h->pending_mats) {
         if (pm.skip) continue;
@@ -1416,6 +1443,9 @@ static int sv_flush(sieve_core* h) {
     h->last_levels = h->pending_levels;
     h->last_per_level = h->pending_per_level;
     SV_TRY(sv_launch_staged(h));
+    SV_CUDA(cudaEventRecord(h->ev_stage[h->stage_sel], h->stream));
+    h->ev_stage_set[h->stage_sel] = true;
+    prof.lap(3);
     // the site-independent constant-site factor is host arithmetic; done here it overlaps the kernels just launched
     // (only the reduce kernel, launched later, needs its result log C_tree)
     if (!h->hP.empty())
@@ -1430,6 +1460,8 @@ static int sv_flush(sieve_core* h) {
         }
     if (!h->G.empty() && !h->g_nodes.empty()) sv_update_G(h);
     h->g_nodes.clear();
+    prof.lap(4);
+    prof.report(no, nm + nd);
     if (!h->pending_ops.empty() || !h->pending_mats.empty()) h->ml_ready = false;
     h->pending_mats.clear();
     h->pending_vals.clear();
