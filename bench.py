@@ -655,6 +655,17 @@ def main():
         if args.mcmc_states > 0:
             ns_states = max(24, args.mcmc_states // (4 if mode != "streamed" else 16))
             ns_mcmc = run_mcmc(NSW, ns_states, (("stage1", True), ("stage2", True), ("relaxed2", True)))
+        # variant calling on the share: the max-sum pass in site chunks (sparse residency keeps only the calls)
+        ns_variants = None
+        if mode.startswith("sparse") and not args.no_variants:
+            t0 = time.perf_counter()
+            NSW.core.ml_trace()
+            g_ml, a_ml, cat_ml, amb_ml = NSW.core.ml_call()
+            t_vc = time.perf_counter() - t0
+            ns_variants = {"ml_trace_and_call_s_incl_d2h": rank_max(t_vc), "sites": int(share), "nodes": int(2 * NS_CELLS),
+                           "tied_sites": int((amb_ml != 0).sum()), "non_reference_leaf_calls": int((g_ml[:NS_CELLS] > 0).sum()),
+                           "d2h_bytes": int(g_ml.nbytes + a_ml.nbytes + cat_ml.nbytes + amb_ml.nbytes)}
+            del g_ml, a_ml, cat_ml, amb_ml
         peak, _ = measured_peak()
         ns_leaf_ms = rank_max(float(np.median([x["leaf_ms"] for x in tm])))
         ns_prune_ms = rank_max(float(np.median([x["prune_ms"] for x in tm])))
@@ -681,6 +692,7 @@ def main():
             "prune_ms": ns_prune_ms,
             "prune_frac_of_hbm_peak_algorithmic": (ns_alg / (ns_prune_ms / 1000.0) / 1e9 / peak) if ns_prune_ms > 0 else None,
             "mcmc": ns_mcmc,
+            "variant_calling": ns_variants,
             "parity": {"sites_checked_per_rank": npar["sites"], "ranks_checked": world,
                        "max_rel_site_logl": rank_max(npar["max_rel_site_logl"]),
                        "max_rel_site_const": rank_max(npar["max_rel_site_const"]),
@@ -734,7 +746,7 @@ def main():
             "e2e_dropin": dropin,
             "gpu_launches": int(launches),
             "clocks": clocks_headline,
-            "roofline": {"bound": "hbm", "kernel": "k_prune<%s, geno0, qfast>" % ("const twin" if with_const_twin else "variant only"),
+            "roofline": {"bound": "hbm", "kernel": ("k_prune<const twin, geno0, qfast>" if with_const_twin else "k_walk (single-launch walk, Q-specialised, variant partials)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_prune), "launch_ms": prune_ms,

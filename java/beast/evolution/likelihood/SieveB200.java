@@ -14,7 +14,7 @@ public final class SieveB200 {
     private SieveB200() {}
 
     public static final int FLAG_LOG_PARTIALS = 1, FLAG_CONST_PARTIALS = 2, FLAG_SINGLE_ADO = 4, FLAG_EPHEMERAL = 8, FLAG_SPARSE = 16,
-            FLAG_SINGLE_LEAF_BUFFER = 32, FLAG_EXTERNAL_COUNTS = 64;
+            FLAG_SINGLE_LEAF_BUFFER = 32, FLAG_EXTERNAL_COUNTS = 64, FLAG_PRIVATE_SEQ_COV = 128;
     public static final int UPDATE_FLIP = 1, UPDATE_PER_LEVEL = 2;
 
     /** sieve_create; returns the opaque handle; throws RuntimeException(sieve_last_error()) on failure */
@@ -27,6 +27,13 @@ public final class SieveB200 {
     public static native void setSizeFactors(long h, double[] sizeFactors);
     public static native void setLeafParams(long h, double adoRate, double allelicSeqCov, double allelicSeqCovRawVar,
                                             double effSeqErrRate, double shapeCtrl1, double shapeCtrl2);
+    /** PrivateAllelicSeqCovModel (FLAG_PRIVATE_SEQ_COV): allelicSeqCovPerPattern / allelicSeqCovRawVarPerPattern, [K * nSites] each,
+     *  index matrixIndex * nrOfPatterns + patternIndex (PrivateAllelicSeqCovModel.java:16-17) */
+    public static native void setPrivateSeqCov(long h, double[] allelicSeqCov, double[] allelicSeqCovRawVar);
+    public static native void getPrivateSeqCov(long h, double[] allelicSeqCov, double[] allelicSeqCovRawVar);
+    /** updateAllelicSeqCovAndRawVar from the max-sum trace of the current state (ScsTreeLikelihood.postProcess); returns the
+     *  number of (category, pattern) pairs whose values moved; outTied[K * nSites] flags the pairs left to the host */
+    public static native int privateUpdateFromMl(long h, int zeroCovMode, byte[] outTied);
     public static native void updateLeaves(long h, boolean forUpdate);
     public static native void setNodeMatrixForUpdate(long h, int node);
     public static native void setNodeMatrix(long h, int node, int category, double[] p16);

@@ -75,6 +75,28 @@ JNIEXPORT void JNICALL FN(setDistances)(JNIEnv *e, jclass c, jlong h, jintArray 
     (*e)->ReleasePrimitiveArrayCritical(e, nodes, pn, JNI_ABORT);
     chk(e, rc);
 }
+JNIEXPORT void JNICALL FN(setPrivateSeqCov)(JNIEnv *e, jclass c, jlong h, jdoubleArray t, jdoubleArray v) {
+    jdouble *pt = (*e)->GetPrimitiveArrayCritical(e, t, NULL), *pv = (*e)->GetPrimitiveArrayCritical(e, v, NULL);
+    int rc = sieve_set_private_seq_cov(H(h), pt, pv);
+    (*e)->ReleasePrimitiveArrayCritical(e, v, pv, JNI_ABORT);
+    (*e)->ReleasePrimitiveArrayCritical(e, t, pt, JNI_ABORT);
+    chk(e, rc);
+}
+JNIEXPORT void JNICALL FN(getPrivateSeqCov)(JNIEnv *e, jclass c, jlong h, jdoubleArray t, jdoubleArray v) {
+    jdouble *pt = (*e)->GetPrimitiveArrayCritical(e, t, NULL), *pv = (*e)->GetPrimitiveArrayCritical(e, v, NULL);
+    int rc = sieve_get_private_seq_cov(H(h), pt, pv);
+    (*e)->ReleasePrimitiveArrayCritical(e, v, pv, 0);
+    (*e)->ReleasePrimitiveArrayCritical(e, t, pt, 0);
+    chk(e, rc);
+}
+JNIEXPORT jint JNICALL FN(privateUpdateFromMl)(JNIEnv *e, jclass c, jlong h, jint zeroCovMode, jbyteArray tied) {
+    jbyte *pt = (*e)->GetPrimitiveArrayCritical(e, tied, NULL);
+    int32_t changed = 0;
+    int rc = sieve_private_update_from_ml(H(h), zeroCovMode, &changed, (uint8_t *)pt);
+    (*e)->ReleasePrimitiveArrayCritical(e, tied, pt, 0);
+    chk(e, rc);
+    return changed;
+}
 JNIEXPORT void JNICALL FN(mlTrace)(JNIEnv *e, jclass c, jlong h) { chk(e, sieve_ml_trace(H(h))); }
 JNIEXPORT void JNICALL FN(mlCall)(JNIEnv *e, jclass c, jlong h, jbyteArray g, jbyteArray a, jbyteArray k, jbyteArray m) {
     jbyte *pg = (*e)->GetPrimitiveArrayCritical(e, g, NULL), *pa = (*e)->GetPrimitiveArrayCritical(e, a, NULL);

@@ -45,50 +45,9 @@ static int sv_ml_require(sieve_core* h, const char* who) {
     return SIEVE_OK;
 }
 
-extern "C" int sieve_ml_trace(sieve_core_t* h) {
-    SV_REQUIRE(h, "null handle");
-    if (h->ephemeral || h->sparse)
-        return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: needs fully resident partials (not SIEVE_FLAG_EPHEMERAL / SIEVE_FLAG_SPARSE)");
-    if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: leaves not computed yet");
-    SV_CUDA(cudaSetDevice(h->device));
-    SV_TRY(sv_flush(h));
-    const size_t n = h->n, S = h->S, K = h->K, N = h->n_nodes, lanes = S * K;
-    std::vector<SvMlOp> ops;
-    SV_TRY(sv_ml_build_ops(h, ops));
-    SV_REQUIRE(!ops.empty() && ops.back().dst == h->root - (int)n, "sieve_ml_trace: the root is not the last node of the tree");
-    // the root's sum-product partial decides the ML category; make sure it is materialised
-    if (!h->valid[h->root]) {
-        h->demand_list.push_back(h->root);
-        SV_TRY(sv_flush(h));
-    }
-    if (!h->ml_alloc) {
-        SV_TRY(sv_alloc(h, &h->d_mlL, n * S * 4 * (h->private_cov ? K : 1)));
-        SV_TRY(sv_alloc(h, &h->d_mlado, n * S * (h->private_cov ? K : 1)));
-        SV_TRY(sv_alloc(h, &h->d_ml, n * lanes * 4));
-        SV_TRY(sv_alloc(h, &h->d_mlback, n * lanes));
-        SV_TRY(sv_alloc(h, &h->d_mlcoll, N * lanes));
-        SV_TRY(sv_alloc(h, &h->d_mladosel, n * lanes));
-        SV_TRY(sv_alloc(h, &h->d_mlamb, lanes));
-        SV_TRY(sv_alloc(h, &h->d_mlcats, S));
-        SV_TRY(sv_alloc(h, &h->d_mllogm, N * K * 16));
-        SV_TRY(sv_alloc(h, &h->d_mlops, n));
-        if (!h->private_cov) SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
-        h->ml_alloc = true;
-    }
-    // log P on the host, in double precision with the reference's clamp (ScsBeerLikelihoodCore.java:3100-3101)
-    std::vector<double> mats((size_t)2 * N * SV_KMAX * 16), logm(N * K * 16);
-    SV_CUDA(cudaMemcpyAsync(mats.data(), h->d_mats, mats.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    SV_CUDA(cudaStreamSynchronize(h->stream));
-    for (size_t v = 0; v < N; v++)
-        for (size_t k = 0; k < K; k++)
-            for (int e = 0; e < 16; e++) {
-                const double P = mats[((size_t)h->cur_mat[v] * N + v) * SV_KMAX * 16 + k * 16 + e];
-                logm[(v * K + k) * 16 + e] = std::log(P > 0.0 ? P : SV_MIN_VALUE);
-            }
-    SV_CUDA(cudaMemcpyAsync(h->d_mllogm, logm.data(), logm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    SV_CUDA(cudaMemcpyAsync(h->d_mlops, ops.data(), ops.size() * sizeof(SvMlOp), cudaMemcpyHostToDevice, h->stream));
-    h->ml_n_ops = (int)ops.size();
-
+// The max-sum pass over the sites [site_begin, site_begin + n_sites) of the shard into the (chunk-sized) pools.
+static int sv_ml_trace_range(sieve_core* h, long long site_begin, int n_sites) {
+    const size_t n = h->n, S = (size_t)n_sites, K = h->K, lanes = S * K;
     SvMlLeafArgs la;
     la.counts = h->d_counts;
     la.dmA = h->d_dmA;
@@ -99,6 +58,8 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
     la.ado = h->d_mlado;
     la.n_cells = (int)n;
     la.S = (int)S;
+    la.counts_stride = h->S;
+    la.site_begin = site_begin;
     la.C = h->C;
     // the trace belongs to the CURRENT leaf buffer: bring the tables to the parameters that buffer was computed with (after
     // a rejected proposal they still hold the rejected values; parameters set since, without a leaf update, do not count)
@@ -129,9 +90,12 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
         k_leaf_ml_private<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(pa);
         sv_count(h);
     } else {
-        k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
-                                                                                                      (int)n, h->C, la.cp);
-        sv_count(h);
+        if (!h->ml_cell_tables_ok) {
+            k_build_cell_log_tables<<<dim3((unsigned)((h->C + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(h->d_mlcellL, h->d_sf,
+                                                                                                          (int)n, h->C, la.cp);
+            sv_count(h);
+            h->ml_cell_tables_ok = true;  // per sieve_ml_trace / chunk loop: reset by the callers
+        }
         k_leaf_ml<<<dim3((unsigned)((S + 127) / 128), (unsigned)n), 128, 0, h->stream>>>(la);
         sv_count(h);
     }
@@ -157,13 +121,97 @@ extern "C" int sieve_ml_trace(sieve_core_t* h) {
     sv_count(h);
     k_ml_down<<<blocks, 128, 0, h->stream>>>(a);
     sv_count(h);
-    const size_t rslot = (size_t)h->cur_part[h->root] * h->n_internal + (h->root - n);
-    k_ml_categories<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(h->d_part + rslot * S * SV_KMAX * 4, (int)S,
-                                                                       (int)K, h->root_genotype, h->d_mlcats);
+    // the root's sum-product partial (always resident) decides the ML category
+    const size_t rslot = (size_t)h->slot_of[(size_t)h->cur_part[h->root] * h->n_nodes + h->root];
+    k_ml_categories<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(
+        h->d_part + (rslot * (size_t)h->S + (size_t)site_begin) * SV_KMAX * 4, (int)S, (int)K, h->root_genotype, h->d_mlcats);
     sv_count(h);
     SV_CUDA(cudaGetLastError());
+    h->ml_site_begin = site_begin;
+    h->ml_n_sites = (int)S;
+    return SIEVE_OK;
+}
+
+// Pools of the max-sum pass.  A dense core traces the whole shard at once (ml_cap == S: every getter works on the result);
+// a sparse core has the device memory for a chunk of sites only -- ~190 B per (cell, site) of max-sum partials, back-pointers
+// and genotype sets against the 32 B of a leaf -- so sieve_ml_call walks the shard chunk by chunk and keeps the calls.
+static int sv_ml_prepare(sieve_core* h) {
+    if (h->ephemeral)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: needs resident leaves and a resident root (not SIEVE_FLAG_EPHEMERAL)");
+    if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "sieve_ml_trace: leaves not computed yet");
+    SV_CUDA(cudaSetDevice(h->device));
+    SV_TRY(sv_flush(h));
+    const size_t n = h->n, S = h->S, K = h->K, N = h->n_nodes;
+    std::vector<SvMlOp> ops;
+    SV_TRY(sv_ml_build_ops(h, ops));
+    SV_REQUIRE(!ops.empty() && ops.back().dst == h->root - (int)n, "sieve_ml_trace: the root is not the last node of the tree");
+    // the root's sum-product partial decides the ML category; make sure it is materialised
+    if (!h->valid[h->root]) {
+        h->demand_list.push_back(h->root);
+        SV_TRY(sv_flush(h));
+    }
+    if (!h->ml_alloc) {
+        size_t cap = S;
+        if (h->sparse) {
+            const size_t pl = h->private_cov ? K : 1;
+            const size_t per_site = n * (pl * 34 + K * (32 + 4 + 1)) + N * K + K + 1;
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            cap = (size_t)(0.7 * (double)free_b / (double)per_site);
+            if (const char* e = getenv("SIEVE_B200_ML_CHUNK")) cap = (size_t)std::max(1, atoi(e));
+            cap = std::min(S, std::max<size_t>(cap / 128 * 128, 128));
+        }
+        const size_t lanes = cap * K;
+        SV_TRY(sv_alloc(h, &h->d_mlL, n * cap * 4 * (h->private_cov ? K : 1)));
+        SV_TRY(sv_alloc(h, &h->d_mlado, n * cap * (h->private_cov ? K : 1)));
+        SV_TRY(sv_alloc(h, &h->d_ml, n * lanes * 4));
+        SV_TRY(sv_alloc(h, &h->d_mlback, n * lanes));
+        SV_TRY(sv_alloc(h, &h->d_mlcoll, N * lanes));
+        SV_TRY(sv_alloc(h, &h->d_mladosel, n * lanes));
+        SV_TRY(sv_alloc(h, &h->d_mlamb, lanes));
+        SV_TRY(sv_alloc(h, &h->d_mlcats, cap));
+        SV_TRY(sv_alloc(h, &h->d_mllogm, N * K * 16));
+        SV_TRY(sv_alloc(h, &h->d_mlops, n));
+        if (!h->private_cov) SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
+        h->ml_cap = (int)cap;
+        h->ml_alloc = true;
+    }
+    // log P on the host, in double precision with the reference's clamp (ScsBeerLikelihoodCore.java:3100-3101)
+    std::vector<double> mats((size_t)2 * N * SV_KMAX * 16), logm(N * K * 16);
+    SV_CUDA(cudaMemcpyAsync(mats.data(), h->d_mats, mats.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     SV_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t v = 0; v < N; v++)
+        for (size_t k = 0; k < K; k++)
+            for (int e = 0; e < 16; e++) {
+                const double P = mats[((size_t)h->cur_mat[v] * N + v) * SV_KMAX * 16 + k * 16 + e];
+                logm[(v * K + k) * 16 + e] = std::log(P > 0.0 ? P : SV_MIN_VALUE);
+            }
+    SV_CUDA(cudaMemcpyAsync(h->d_mllogm, logm.data(), logm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SV_CUDA(cudaMemcpyAsync(h->d_mlops, ops.data(), ops.size() * sizeof(SvMlOp), cudaMemcpyHostToDevice, h->stream));
+    SV_CUDA(cudaStreamSynchronize(h->stream));  // logm / ops are locals
+    h->ml_n_ops = (int)ops.size();
+    h->ml_cell_tables_ok = false;
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_ml_trace(sieve_core_t* h) {
+    SV_REQUIRE(h, "null handle");
+    SV_TRY(sv_ml_prepare(h));
+    if (h->ml_cap >= h->S) {
+        SV_TRY(sv_ml_trace_range(h, 0, h->S));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+    } else
+        h->ml_n_sites = 0;  // a chunked core traces inside sieve_ml_call / sieve_ml_get_categories, chunk by chunk
     h->ml_ready = true;
+    return SIEVE_OK;
+}
+
+// getters that need the whole shard's trace in memory
+static int sv_ml_require_whole(sieve_core* h, const char* who) {
+    SV_TRY(sv_ml_require(h, who));
+    if (h->ml_cap < h->S)
+        return sv_fail(SIEVE_ERR_STATE, std::string(who) + ": this core traces in site chunks (sparse residency); per-node and per-site "
+                                            "read-backs need a dense core (e.g. one over the tied sites only)");
     return SIEVE_OK;
 }
 
@@ -171,28 +219,34 @@ extern "C" int sieve_ml_call(sieve_core_t* h, int8_t* genotypes, int8_t* ado, ui
     SV_TRY(sv_ml_require(h, "sieve_ml_call"));
     SV_REQUIRE(genotypes && ado && category && ambiguous, "sieve_ml_call: null output");
     SV_CUDA(cudaSetDevice(h->device));
-    const size_t n = h->n, S = h->S, N = h->n_nodes;
+    const size_t n = h->n, S = h->S, N = h->n_nodes, cap = (size_t)h->ml_cap;
     signed char *d_g = nullptr, *d_a = nullptr;
     unsigned char *d_c = nullptr, *d_m = nullptr;
-    cudaError_t e = cudaMalloc(&d_g, N * S);
-    if (e == cudaSuccess) e = cudaMalloc(&d_a, n * S);
-    if (e == cudaSuccess) e = cudaMalloc(&d_c, S);
-    if (e == cudaSuccess) e = cudaMalloc(&d_m, S);
-    if (e == cudaSuccess) {
-        k_ml_call<<<dim3((unsigned)((S + 255) / 256), (unsigned)N), 256, 0, h->stream>>>(
-            h->d_mlcoll, h->d_mladosel, h->d_mlcats, h->d_mlamb, (int)S, h->K, (int)N, (int)n, d_g, d_a, d_c, d_m);
+    cudaError_t e = cudaMalloc(&d_g, N * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&d_a, n * cap);
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, cap);
+    if (e == cudaSuccess) e = cudaMalloc(&d_m, cap);
+    int rc = SIEVE_OK;
+    for (size_t s0 = 0; s0 < S && e == cudaSuccess && rc == SIEVE_OK; s0 += cap) {
+        const size_t sc = std::min(cap, S - s0);
+        if (cap < S) rc = sv_ml_trace_range(h, (long long)s0, (int)sc);  // a dense core was traced by sieve_ml_trace
+        if (rc != SIEVE_OK) break;
+        k_ml_call<<<dim3((unsigned)((sc + 255) / 256), (unsigned)N), 256, 0, h->stream>>>(
+            h->d_mlcoll, h->d_mladosel, h->d_mlcats, h->d_mlamb, (int)sc, h->K, (int)N, (int)n, d_g, d_a, d_c, d_m);
         sv_count(h);
         e = cudaGetLastError();
+        // device [node][sc] -> host [node][S] at column s0
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(genotypes + s0, S, d_g, sc, sc, N, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(ado + s0, S, d_a, sc, sc, n, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(category + s0, d_c, sc, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ambiguous + s0, d_m, sc, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(genotypes, d_g, N * S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ado, d_a, n * S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(category, d_c, S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ambiguous, d_m, S, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_g);
     cudaFree(d_a);
     cudaFree(d_c);
     cudaFree(d_m);
+    SV_TRY(rc);
     SV_CUDA(e);
     return SIEVE_OK;
 }
@@ -201,8 +255,23 @@ extern "C" int sieve_ml_get_categories(sieve_core_t* h, uint8_t* out) {
     SV_TRY(sv_ml_require(h, "sieve_ml_get_categories"));
     SV_REQUIRE(out, "null output");
     SV_CUDA(cudaSetDevice(h->device));
-    SV_CUDA(cudaMemcpyAsync(out, h->d_mlcats, (size_t)h->S, cudaMemcpyDeviceToHost, h->stream));
-    SV_CUDA(cudaStreamSynchronize(h->stream));
+    const size_t S = h->S, cap = (size_t)h->ml_cap;
+    if (cap >= S) {
+        SV_CUDA(cudaMemcpyAsync(out, h->d_mlcats, S, cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+        return SIEVE_OK;
+    }
+    // chunked core: the categories come from the root's sum-product partial alone
+    const size_t rslot = (size_t)h->slot_of[(size_t)h->cur_part[h->root] * h->n_nodes + h->root];
+    for (size_t s0 = 0; s0 < S; s0 += cap) {
+        const size_t sc = std::min(cap, S - s0);
+        k_ml_categories<<<(unsigned)((sc + 255) / 256), 256, 0, h->stream>>>(h->d_part + (rslot * S + s0) * SV_KMAX * 4, (int)sc, h->K,
+                                                                           h->root_genotype, h->d_mlcats);
+        sv_count(h);
+        SV_CUDA(cudaGetLastError());
+        SV_CUDA(cudaMemcpyAsync(out + s0, h->d_mlcats, sc, cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return SIEVE_OK;
 }
 
@@ -210,7 +279,7 @@ extern "C" int sieve_ml_get_categories(sieve_core_t* h, uint8_t* out) {
 // MLGenotypesNodes[..][node][(k, s, parent genotype)]: low nibble = list of child 0, high nibble = list of child 1; for a
 // leaf the byte is the list of arg-max dropout components), collection [K][S] (MLGenotypesCollection).
 extern "C" int sieve_ml_get_node(sieve_core_t* h, int32_t node, double* ml_partials, uint8_t* back, uint8_t* collection) {
-    SV_TRY(sv_ml_require(h, "sieve_ml_get_node"));
+    SV_TRY(sv_ml_require_whole(h, "sieve_ml_get_node"));
     SV_REQUIRE(sv_node_ok(h, node), "sieve_ml_get_node: bad node");
     SV_CUDA(cudaSetDevice(h->device));
     const size_t n = h->n, S = h->S, K = h->K, lanes = S * K;
@@ -262,7 +331,7 @@ extern "C" int sieve_ml_get_node(sieve_core_t* h, int32_t node, double* ml_parti
 // One site, every node: back-pointer bytes [node][K][4] and sum-product log partials [node][K][4] -- what a host needs
 // to enumerate and rank the tied combinations of an ambiguous site (ScsTreeLikelihood.java:2083-2160).
 extern "C" int sieve_ml_get_site(sieve_core_t* h, int32_t site, uint8_t* back, double* log_partials) {
-    SV_TRY(sv_ml_require(h, "sieve_ml_get_site"));
+    SV_TRY(sv_ml_require_whole(h, "sieve_ml_get_site"));
     SV_REQUIRE(site >= 0 && site < h->S && back && log_partials, "sieve_ml_get_site: bad argument");
     SV_CUDA(cudaSetDevice(h->device));
     const int n = h->n, N = h->n_nodes, K = h->K;

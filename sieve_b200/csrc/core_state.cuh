@@ -195,7 +195,10 @@ struct sieve_core {
     double logw[SV_KMAX] = {0, 0, 0, 0}, logw_stored[SV_KMAX] = {0, 0, 0, 0};  // log(prop_k G_root[k][rg]) + scale of G_root
 
     // max-sum pass for variant calling (maxsum.cuh); its pools are allocated by the first sieve_ml_trace
-    bool ml_alloc = false, ml_ready = false;
+    bool ml_alloc = false, ml_ready = false, ml_cell_tables_ok = false;
+    int ml_cap = 0;               // site capacity of the max-sum pools: S on a dense core, a chunk on a sparse one
+    long long ml_site_begin = 0;  // the site range the pools currently hold
+    int ml_n_sites = 0;
     double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr, *d_mlcellL = nullptr;
     unsigned short* d_mlado = nullptr;
     unsigned* d_mlback = nullptr;

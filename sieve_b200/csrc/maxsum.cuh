@@ -53,7 +53,8 @@ struct SvMlLeafArgs {
     const double* size_factors;
     double* leafL;           // [cell][site][4] log genotype likelihoods (0/0, 0/1, 1/1, 1/1')
     unsigned short* ado;     // [cell][site] four nibbles: arg-max set of the dropout components of genotype g
-    int n_cells, S, C;
+    int n_cells, S, C;      // S = sites of this launch (a site chunk of a sparse core, else the shard)
+    long long counts_stride, site_begin;  // sites per cell in `counts`, first site of this launch
     SvDmAlphas al;
     SvCovParams cp;
 };
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(128) k_leaf_ml(SvMlLeafArgs a) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.S) return;
     const int C = a.C;
-    const int4 c = __ldg(a.counts + (size_t)j * a.S + s);
+    const int4 c = __ldg(a.counts + (size_t)j * a.counts_stride + a.site_begin + s);
     const int cov = c.w;
     double N0, N1, N2, N3;  // nucleotide log-densities of 0/0, 1/1, 1/1', 0/1 (NucReadCountsModelFiniteMuDM.java:33-96)
     sv_leaf_nuc_terms<false>(c, a.dmA, a.dmB, C, a.al, N0, N1, N2, N3);

@@ -51,7 +51,9 @@ class ScsTreeLikelihood:
         self.use_distances = use_distances
         # PrivateAllelicSeqCovModel instead of ExploredSharedAllelicSeqCovModel: (t, v) per (category, pattern)
         self.private_seq_cov, self.zero_cov_mode, self.single_ado = bool(private_seq_cov), int(zero_cov_mode), bool(single_ado)
-        self._counts = counts if private_seq_cov else None
+        self._counts = counts          # a reference (tied pairs / tied sites are re-examined on the host side)
+        self._ctor = dict(n_categories=n_categories, use_log_partials=use_log_partials, single_ado=single_ado, device=device,
+                          use_distances=use_distances)
         self.core = ScsCudaLikelihoodCore(self.n, self.S, n_categories, 4, use_log_partials, asc_mode != "none",
                                           single_ado, device, ephemeral, sparse, single_leaf_buffer,
                                           private_seq_cov=private_seq_cov)
@@ -103,6 +105,26 @@ class ScsTreeLikelihood:
             self.has_dirt = max(self.has_dirt, IS_DIRTY)
             self.calculate_logp()
         return changed
+
+    def call_variants(self):
+        """VariantCaller's core step on the current state (ScsTreeLikelihood.callVariants, :2444-2449): ML genotypes of every
+        node, dropout states of the leaves, ML rate category.  On a sparse core the tied sites (rare) are re-evaluated on a
+        small dense core over just those sites, which has the per-site read-backs the tie-break needs."""
+        from . import variants
+        made = []
+
+        def tied_core(sites):
+            sub = ScsTreeLikelihood(self._counts[sites], self.tree.copy(), size_factors=self.size_factors, leaf_params=self.params,
+                                    gamma_shape=self.gamma_shape, clock_rate=self.clock_rate, branch_rates=self.branch_rates,
+                                    asc_mode=self.asc_mode, n_background_sites=self.M, **self._ctor)
+            sub.calculate_logp()
+            made.append(sub)
+            return sub.core
+
+        out = variants.call_variants(self.core, self.tree, substmodel.ROOT_GENOTYPE, tied_core)
+        for sub in made:
+            sub.close()
+        return out
 
     def close(self):
         self.core.close()

@@ -59,19 +59,37 @@ class VariantCalls:
         self.genotypes, self.ado, self.category, self.tied = genotypes, ado, category, tied
 
 
-def call_variants(core, tree, root_genotype=0):
-    """Run the max-sum pass on `core`'s current state and resolve tied sites."""
+def call_variants(core, tree, root_genotype=0, tied_core=None):
+    """Run the max-sum pass on `core`'s current state and resolve tied sites.
+
+    A sparse core traces in site chunks and keeps only the calls; the per-site read-backs that the tie-break needs
+    (back-pointers and sum-product partials of EVERY node) exist on dense cores only.  `tied_core(sites)` must then return a
+    dense core over exactly those sites in the same state (ScsTreeLikelihood.call_variants builds one); without it the tied
+    sites of a sparse core stay unresolved (-1 entries, listed in `.tied` with an empty candidate list)."""
     core.ml_trace()
     g, a, cat, amb = core.ml_call()
     n = core.n
     children = {p: (int(tree.left[p]), int(tree.right[p])) for p in range(n, 2 * n)}
     tied = {}
     if amb.any():
-        cats = core.ml_categories()
-        for s in np.nonzero(amb)[0]:
-            back, logp = core.ml_site(int(s))
+        sites = [int(s) for s in np.nonzero(amb)[0]]
+        src, index = core, {s: s for s in sites}
+        try:
+            core.ml_site(sites[0])
+            chunked = False
+        except RuntimeError:      # a core that traces in site chunks has no per-site read-back
+            chunked = True
+        if chunked:
+            if tied_core is None:
+                return VariantCalls(g, a, cat, {s: [] for s in sites})
+            src = tied_core(sites)
+            src.ml_trace()
+            index = {s: i for i, s in enumerate(sites)}
+        cats = src.ml_categories()
+        for s in sites:
+            back, logp = src.ml_site(index[s])
             cand = []
-            for k in _bits(cats[s]):
+            for k in _bits(cats[index[s]]):
                 for comb in enumerate_combinations(children, tree.root, n, back[:, k, :], root_genotype):
                     cand.append((k, comb))
             if len(cand) > 1:

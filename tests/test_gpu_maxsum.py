@@ -184,3 +184,48 @@ def test_called_genotypes_recover_simulated_truth(core_mod, oracle):
     agree = (calls.genotypes[:n] == truth)[covered].mean()
     assert agree > 0.9, agree
     c.close()
+
+
+def test_sparse_core_calls_variants_in_site_chunks(core_mod, oracle, monkeypatch):
+    """A sparse core (the residency of the 10 000-cell shapes) has no room for the max-sum pools of a whole shard: it traces
+    chunk by chunk inside ml_call and keeps the calls.  Same calls, categories and tie flags as the dense core, with a ragged
+    last chunk; the tied sites are resolved on a small dense core over just those sites (ScsTreeLikelihood.call_variants)."""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    n, S = 48, 700
+    d = synthetic(n, S, seed=12)
+    counts, tree = d["counts"], d["tree"]
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    out = {}
+    for mode in ("dense", "sparse"):
+        if mode == "sparse":
+            monkeypatch.setenv("SIEVE_B200_POOL_SLOTS", "96")
+            monkeypatch.setenv("SIEVE_B200_ML_CHUNK", "256")
+        tl = ScsTreeLikelihood(counts, tree.copy(), size_factors=sf, asc_mode="felsenstein_mean", n_background_sites=2e3,
+                               sparse=(mode == "sparse"))
+        tl.calculate_logp()
+        calls = tl.call_variants()
+        cats = tl.core.ml_categories()
+        if mode == "sparse":
+            assert tl.core.sparse_info()["keep_leaves"] > 0
+            with pytest.raises(RuntimeError):
+                tl.core.ml_site(0)
+            with pytest.raises(RuntimeError):
+                tl.core.ml_node(n + 1)
+        # a local move, then again: the chunked trace follows the current state
+        moved = tree.copy()
+        v = n + n // 2
+        lo = max(moved.height[moved.left[v]], moved.height[moved.right[v]])
+        moved.height[v] = lo + 0.2 * (moved.height[moved.parent[v]] - lo)
+        tl.set_tree(moved, [v])
+        tl.calculate_logp()
+        calls2 = tl.call_variants()
+        out[mode] = (calls, cats, calls2)
+        tl.close()
+    for i in (0, 2):
+        a, b = out["dense"][i], out["sparse"][i]
+        np.testing.assert_array_equal(a.genotypes, b.genotypes)
+        np.testing.assert_array_equal(a.ado, b.ado)
+        np.testing.assert_array_equal(a.category, b.category)
+        assert a.tied == b.tied
+    np.testing.assert_array_equal(out["dense"][1], out["sparse"][1])
+    assert (out["dense"][0].genotypes[:n] > 0).any()
