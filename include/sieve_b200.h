@@ -278,8 +278,14 @@ int sieve_walk_blocks_per_sm(int64_t n_sites);
  * (rawreadcountsmodel/RawReadCountsModelFiniteMuDM.java:54-77), the ML rate category per pattern
  * (ScsBeerLikelihoodCore.java:278-296) and the top-down collection of the genotypes every node takes
  * (likelihood/ScsTreeLikelihood.java:947-1460, MLGenotypesCollection).  A tie list of the reference is a bit mask here
- * (bit g set <=> genotype / component g is listed).  Resident cores only.  The pass is recomputed by every call of
- * sieve_ml_trace; any later change of the state invalidates the results (the getters then fail with SIEVE_ERR_STATE). */
+ * (bit g set <=> genotype / component g is listed).  The pass is recomputed by every call of sieve_ml_trace; any later
+ * change of the state invalidates the results (the getters then fail with SIEVE_ERR_STATE).
+ * A core with linear partials (no SIEVE_FLAG_LOG_PARTIALS) runs the linear-space twin (ScsBeerLikelihoodCore.java:1759-2335):
+ * a LEAF child then contributes log(P[p][c] * leaf[c]) with the unclamped P, an internal child as in the log-space twin.
+ * Dense cores trace the whole shard and serve every getter.  SIEVE_FLAG_SPARSE cores (no room for ~190 B per cell and site of
+ * max-sum state) trace in site chunks inside sieve_ml_call / sieve_ml_get_categories and keep the calls only:
+ * sieve_ml_get_node / sieve_ml_get_site fail with SIEVE_ERR_STATE there -- resolve the (rare) tied sites on a small dense
+ * core over just those sites.  SIEVE_FLAG_EPHEMERAL cores hold no leaves or root to trace from: SIEVE_ERR_STATE. */
 int sieve_ml_trace(sieve_core_t *h);
 /* The common case of ScsTreeLikelihood.collectMLGenotypesAndLogLikelihoods (:2033-2081), for the lowest ML category of
  * every site: genotypes [node][S] and ado [leaf][S] hold the unique ML genotype / number of dropped alleles, or -1 where

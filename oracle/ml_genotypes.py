@@ -83,21 +83,55 @@ def pattern_categories(root_partials, root_genotype=0):
     return out
 
 
+def _argmax_masks(cand):
+    """cand [..., 4 parent genotypes, 4 child genotypes] -> (max [..., 4], masks uint8 [..., 4]): the reference's sequential
+    rule (first index seeds, '<' replaces, '==' appends) lists exactly the indices that attain the maximum."""
+    mx = cand.max(axis=-1)
+    eq = cand == mx[..., None]
+    masks = (eq * (1 << np.arange(4))).sum(axis=-1).astype(np.uint8)
+    return mx, masks
+
+
+def ml_lin_pruning(ch1, leaf1, m1, ch2, leaf2, m2):
+    """The max-sum part of the LINEAR-space twin (useLogPartials = false), ScsBeerLikelihoodCore.java:1759-2335:
+    calculateLeafLeafPruning :1895-2016, calculateLeafPartialPruning :2018-2166, calculatePartialPartialPruning :2168-2335.
+    A leaf child contributes log(P[p][c] * leaf[c]) with its LINEAR likelihood and the unclamped P (:1948-1949, 1964-1978);
+    an internal child log(P > 0 ? P : Double.MIN_VALUE) + ML[c] with its (log-valued) ML partial (:2260-2263).
+    ch* [K][S][4]: linear leaf partials (leaf* True) or log ML partials; m* [K][16]; ch2 None = unary root.
+    -> (ML partials [K][S][4], back-pointers uint8 [K][S][4])."""
+    def side(ch, is_leaf, m):
+        ch = np.asarray(ch, dtype=np.float64)
+        P = np.asarray(m, dtype=np.float64).reshape(-1, 1, 4, 4)           # [K][1][p][c]
+        with np.errstate(divide="ignore"):
+            if is_leaf:
+                cand = np.log(P * ch[:, :, None, :])
+            else:
+                cand = np.log(np.where(P > 0.0, P, 4.9406564584124654e-324)) + ch[:, :, None, :]
+        return _argmax_masks(cand)
+    mx1, b1 = side(ch1, leaf1, m1)
+    if ch2 is None:
+        return mx1, b1
+    mx2, b2 = side(ch2, leaf2, m2)
+    return mx1 + mx2, (b1 | (b2 << 4)).astype(np.uint8)
+
+
 def ml_trace(counts_s_n_5, size_factors, params, ops, matrices, root_genotype=0):
-    """The whole traceMLGenotypes evaluation on one tree (log partials, ScsTreeLikelihood.traverse :700-722).
+    """The whole traceMLGenotypes evaluation on one tree (ScsTreeLikelihood.traverse :700-722), log partials or -- with
+    params.use_log == 0 -- the linear-space twin (the leaf partials and sum-product partials are then linear likelihoods).
 
     ops: [(parent, c1, c2|-1)] post-order; matrices [2n][K][16].
     -> dict(leaf [n][S][4], ado [n][S][4] u8, ml {node: [K][S][4]}, back {node: [K][S][4] u8},
-            partials {node: [K][S][4]} sum-product log partials of every node, categories [S] u8 mask)."""
+            partials {node: [K][S][4]} sum-product partials of every node, categories [S] u8 mask)."""
     c = np.ascontiguousarray(counts_s_n_5, dtype=np.int32)
     S, n = c.shape[0], c.shape[1]
     matrices = np.asarray(matrices, dtype=np.float64)
     K = matrices.shape[1]
+    use_log = bool(params.use_log)
     leaf = np.empty((n, S, 4))
     ado = np.empty((n, S, 4), dtype=np.uint8)
     for j in range(n):
         leaf[j], ado[j] = leaf_likelihood_ml(c, j, size_factors[j], params)
-    core = so.Core(2 * n, n, S, K, 4, use_log=True)
+    core = so.Core(2 * n, n, S, K, 4, use_log=use_log)
     for j in range(n):
         core.set_node_partials(j, leaf[j])
     for node in range(2 * n):
@@ -111,7 +145,11 @@ def ml_trace(counts_s_n_5, size_factors, params, ops, matrices, root_genotype=0)
         a2 = None
         if c2 >= 0:
             a2 = np.broadcast_to(leaf[c2], (K, S, 4)) if c2 < n else ml[c2]
-        ml[parent], back[parent] = ml_log_pruning(a1, matrices[c1], a2, matrices[c2] if c2 >= 0 else None)
+        if use_log:
+            ml[parent], back[parent] = ml_log_pruning(a1, matrices[c1], a2, matrices[c2] if c2 >= 0 else None)
+        else:
+            ml[parent], back[parent] = ml_lin_pruning(a1, c1 < n, matrices[c1], a2, 0 <= c2 < n,
+                                                      matrices[c2] if c2 >= 0 else None)
         root = parent
     partials = {j: np.broadcast_to(leaf[j], (K, S, 4)) for j in range(n)}
     for parent, _, _ in ops:

@@ -116,6 +116,8 @@ static int sv_ml_trace_range(sieve_core* h, long long site_begin, int n_sites) {
     a.n_leaves = (int)n;
     a.root_genotype = h->root_genotype;
     a.leaf_k = h->private_cov ? 1 : 0;
+    a.rawm = h->d_mlrawm;
+    a.linear = h->log_mode ? 0 : 1;
     const unsigned blocks = (unsigned)((lanes + 127) / 128);
     k_ml_up<<<blocks, 128, 0, h->stream>>>(a);
     sv_count(h);
@@ -171,6 +173,7 @@ static int sv_ml_prepare(sieve_core* h) {
         SV_TRY(sv_alloc(h, &h->d_mlamb, lanes));
         SV_TRY(sv_alloc(h, &h->d_mlcats, cap));
         SV_TRY(sv_alloc(h, &h->d_mllogm, N * K * 16));
+        if (!h->log_mode) SV_TRY(sv_alloc(h, &h->d_mlrawm, N * K * 16));
         SV_TRY(sv_alloc(h, &h->d_mlops, n));
         if (!h->private_cov) SV_TRY(sv_alloc(h, &h->d_mlcellL, n * (size_t)h->C * 4));
         h->ml_cap = (int)cap;
@@ -187,6 +190,14 @@ static int sv_ml_prepare(sieve_core* h) {
                 logm[(v * K + k) * 16 + e] = std::log(P > 0.0 ? P : SV_MIN_VALUE);
             }
     SV_CUDA(cudaMemcpyAsync(h->d_mllogm, logm.data(), logm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> rawm;
+    if (!h->log_mode) {  // the linear-space twin multiplies a leaf child's likelihoods with P itself (maxsum.cuh)
+        rawm.resize(N * K * 16);
+        for (size_t v = 0; v < N; v++)
+            for (size_t k = 0; k < K; k++)
+                memcpy(&rawm[(v * K + k) * 16], &mats[((size_t)h->cur_mat[v] * N + v) * SV_KMAX * 16 + k * 16], 16 * sizeof(double));
+        SV_CUDA(cudaMemcpyAsync(h->d_mlrawm, rawm.data(), rawm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
     SV_CUDA(cudaMemcpyAsync(h->d_mlops, ops.data(), ops.size() * sizeof(SvMlOp), cudaMemcpyHostToDevice, h->stream));
     SV_CUDA(cudaStreamSynchronize(h->stream));  // logm / ops are locals
     h->ml_n_ops = (int)ops.size();

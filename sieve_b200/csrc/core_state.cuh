@@ -199,7 +199,7 @@ struct sieve_core {
     int ml_cap = 0;               // site capacity of the max-sum pools: S on a dense core, a chunk on a sparse one
     long long ml_site_begin = 0;  // the site range the pools currently hold
     int ml_n_sites = 0;
-    double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr, *d_mlcellL = nullptr;
+    double *d_mlL = nullptr, *d_ml = nullptr, *d_mllogm = nullptr, *d_mlcellL = nullptr, *d_mlrawm = nullptr;
     unsigned short* d_mlado = nullptr;
     unsigned* d_mlback = nullptr;
     unsigned char *d_mlcoll = nullptr, *d_mladosel = nullptr, *d_mlamb = nullptr, *d_mlcats = nullptr;

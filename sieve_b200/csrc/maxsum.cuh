@@ -200,6 +200,9 @@ struct SvMlArgs {
     unsigned char* ado_sel; // [cell][S][K] union of the arg-max dropout components over the leaf's genotype set
     unsigned char* ambiguous;  // [S][K] 1 <=> more than one ML combination
     int S, K, n_leaves, root_genotype;
+    const double* rawm;     // [node][K][16] P itself, for the leaf children of the linear-space twin (linear == 1)
+    int linear;             // 1: ScsBeerLikelihoodCore.java:1759-2335 (useLogPartials = false): a LEAF child contributes
+                            //    log(P[p][c] * leaf[c]) with the linear leaf likelihood and the unclamped P (:1948-1949, 1964-1978)
     int leaf_k;             // 1: the leaves are per category (k_leaf_ml_private): leafL [cell][S][K][4], ado [cell][S][K]
 };
 
@@ -217,6 +220,33 @@ __device__ __forceinline__ void sv_ml_side(const double* lm /* shared */, const 
 #pragma unroll
         for (int cgt = 1; cgt < 4; cgt++) {
             const double t = __dadd_rn(m[cgt], v[cgt]);
+            if (best < t) {
+                best = t;
+                bm = 1u << cgt;
+            } else if (best == t)
+                bm |= 1u << cgt;
+        }
+        mx[p] = best;
+        mask[p] = bm;
+    }
+}
+
+// a LEAF child in the linear-space twin (calculateLeafLeafPruning / calculateLeafPartialPruning, :1895-2166): the candidates
+// are log(P[p][c] * leaf[c]) -- product first, no Double.MIN_VALUE clamp, so a zero entry of P gives -inf and ties among
+// -inf candidates are ties (the comparison is on the logs, :1964-1978).  lm holds P, v the LOG leaf likelihoods.
+__device__ __forceinline__ void sv_ml_side_lin_leaf(const double* lm /* shared */, const double (&v)[4], double (&mx)[4],
+                                                    unsigned (&mask)[4]) {
+    const double L[4] = {exp(v[0]), exp(v[1]), exp(v[2]), exp(v[3])};
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const double2 ma = *reinterpret_cast<const double2*>(lm + 4 * p);
+        const double2 mb = *reinterpret_cast<const double2*>(lm + 4 * p + 2);
+        const double m[4] = {ma.x, ma.y, mb.x, mb.y};
+        double best = log(__dmul_rn(m[0], L[0]));
+        unsigned bm = 1u;
+#pragma unroll
+        for (int cgt = 1; cgt < 4; cgt++) {
+            const double t = log(__dmul_rn(m[cgt], L[cgt]));
             if (best < t) {
                 best = t;
                 bm = 1u << cgt;
@@ -253,8 +283,9 @@ __global__ void __launch_bounds__(128) k_ml_up(SvMlArgs a) {
         unsigned b1[4], b2[4] = {0u, 0u, 0u, 0u};
         {
             double m[4] = {0.0, 0.0, 0.0, 0.0};
+            const bool lin_leaf = a.linear && (op.flags & (st_which ? SV_OP_LEAF2 : SV_OP_LEAF1));
             if (st_kk < K && !(st_which == 1 && (op.flags & SV_OP_UNARY)))
-                sv_ld256_nc(a.logm + ((size_t)(st_which ? op.n2 : op.n1) * K + st_kk) * 16 + st_q * 4, m);
+                sv_ld256_nc((lin_leaf ? a.rawm : a.logm) + ((size_t)(st_which ? op.n2 : op.n1) * K + st_kk) * 16 + st_q * 4, m);
             __syncwarp();  // every lane is done with the previous op's matrices
             *reinterpret_cast<double2*>(st_dst) = make_double2(m[0], m[1]);
             *reinterpret_cast<double2*>(st_dst + 2) = make_double2(m[2], m[3]);
@@ -264,13 +295,19 @@ __global__ void __launch_bounds__(128) k_ml_up(SvMlArgs a) {
             sv_ld256_nc(a.leaf_k ? a.leafL + ((size_t)op.c1 * lanes + lane) * 4 : a.leafL + ((size_t)op.c1 * a.S + s) * 4, v1);
         else
             sv_ld256(a.ml + ((size_t)op.c1 * lanes + lane) * 4, v1);
-        sv_ml_side(M1, v1, m1, b1);
+        if (a.linear && (op.flags & SV_OP_LEAF1))
+            sv_ml_side_lin_leaf(M1, v1, m1, b1);
+        else
+            sv_ml_side(M1, v1, m1, b1);
         if (!(op.flags & SV_OP_UNARY)) {
             if (op.flags & SV_OP_LEAF2)
                 sv_ld256_nc(a.leaf_k ? a.leafL + ((size_t)op.c2 * lanes + lane) * 4 : a.leafL + ((size_t)op.c2 * a.S + s) * 4, v2);
             else
                 sv_ld256(a.ml + ((size_t)op.c2 * lanes + lane) * 4, v2);
-            sv_ml_side(M2, v2, m2, b2);
+            if (a.linear && (op.flags & SV_OP_LEAF2))
+                sv_ml_side_lin_leaf(M2, v2, m2, b2);
+            else
+                sv_ml_side(M2, v2, m2, b2);
 #pragma unroll
             for (int p = 0; p < 4; p++) m1[p] = __dadd_rn(m1[p], m2[p]);  // parentMLPartials = max1 + max2 (:3139)
         }

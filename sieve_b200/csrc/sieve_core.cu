@@ -283,6 +283,7 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_mlL);
     cudaFree(h->d_ml);
     cudaFree(h->d_mllogm);
+    cudaFree(h->d_mlrawm);
     cudaFree(h->d_mlcellL);
     cudaFree(h->d_mlado);
     cudaFree(h->d_mlback);

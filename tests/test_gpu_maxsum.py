@@ -22,7 +22,7 @@ def core_mod():
     return core
 
 
-def _case(core_mod, oracle, n, S, seed, single=True, K=4, asc=True):
+def _case(core_mod, oracle, n, S, seed, single=True, K=4, asc=True, use_log=True):
     from oracle import ml_genotypes as mlo
     d = synthetic(n, S, seed=seed)
     counts, tree = d["counts"], d["tree"]
@@ -30,7 +30,7 @@ def _case(core_mod, oracle, n, S, seed, single=True, K=4, asc=True):
     sf, _ = oracle.size_factors(c5)
     rates, props = substmodel.gamma_category_rates(0.8, K)
     mats = substmodel.node_matrices(tree, rates)
-    c = core_mod.ScsCudaLikelihoodCore(n, S, K, 4, True, asc, single)
+    c = core_mod.ScsCudaLikelihoodCore(n, S, K, 4, use_log, asc, single)
     c.set_counts(counts)
     c.set_size_factors(sf)
     c.set_leaf_params(*PARAMS)
@@ -40,7 +40,7 @@ def _case(core_mod, oracle, n, S, seed, single=True, K=4, asc=True):
     c.set_matrices(nodes, mats[nodes][:, :K], for_update=False)
     c.update_nodes(tree.ops(), flip=False)
     c.evaluate()
-    P = oracle.leaf_params(*PARAMS, single_ado=single)
+    P = oracle.leaf_params(*PARAMS, single_ado=single, use_log=use_log)
     tr = mlo.ml_trace(c5, sf, P, tree.ops(), mats[:, :K], 0)
     return c, tree, tr
 
@@ -229,3 +229,57 @@ def test_sparse_core_calls_variants_in_site_chunks(core_mod, oracle, monkeypatch
         assert a.tied == b.tied
     np.testing.assert_array_equal(out["dense"][1], out["sparse"][1])
     assert (out["dense"][0].genotypes[:n] > 0).any()
+
+
+@pytest.mark.parametrize("single", [True, False])
+def test_linear_space_twin_of_the_max_sum_pass(core_mod, oracle, single):
+    """A core with linear partials (useLogPartials = false) runs the linear-space twin of the max-sum pruning
+    (ScsBeerLikelihoodCore.java:1759-2335): leaf children enter as log(P * leaf) with the unclamped P.  Against
+    oracle.ml_genotypes.ml_lin_pruning, incl. a zero-length branch above a leaf, where the two twins differ."""
+    from oracle import ml_genotypes as mlo
+    n, S, K = 11, 260, 4
+    d = synthetic(n, S, seed=29)
+    counts, tree = d["counts"], d["tree"]
+    # a zero-length branch above leaf 3: P = I, log(0 * leaf) = -inf for the off-diagonal candidates
+    tree.height[tree.parent[3]] = tree.height[3]
+    c5 = oracle.counts5(counts)
+    sf, _ = oracle.size_factors(c5)
+    rates, props = substmodel.gamma_category_rates(0.8, K)
+    mats = substmodel.node_matrices(tree, rates)
+    assert np.allclose(mats[3, 0].reshape(4, 4), np.eye(4))
+    c = core_mod.ScsCudaLikelihoodCore(n, S, K, 4, False, True, single)
+    c.set_counts(counts)
+    c.set_size_factors(sf)
+    c.set_leaf_params(*PARAMS)
+    c.update_leaves(for_update=False)
+    c.set_root(tree.root, props, 0)
+    nodes = [i for i in range(tree.node_count) if i != tree.root]
+    c.set_matrices(nodes, mats[nodes], for_update=False)
+    c.update_nodes(tree.ops(), flip=False)
+    c.evaluate()
+    c.ml_trace()
+    tr = mlo.ml_trace(c5, sf, oracle.leaf_params(*PARAMS, single_ado=single, use_log=False), tree.ops(), mats, 0)
+    total = flips = 0
+    for node in range(n, 2 * n):
+        p, b, _ = c.ml_node(node)
+        ref, rb = tr["ml"][node], tr["back"][node]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(p), fin), node
+        assert np.all(np.abs(p[fin] - ref[fin]) <= 1e-12 * np.abs(ref[fin])), node
+        total += b.size
+        flips += int((b != rb).sum())
+    assert flips <= 2e-3 * total, (flips, total)
+    # the parent of leaf 3: for every parent genotype p the only candidate of that child is p itself
+    par = int(tree.parent[3])
+    _, b, _ = c.ml_node(par)
+    side = 0 if int(tree.left[par]) == 3 else 1
+    want = np.array([1, 2, 4, 8], dtype=np.uint8)
+    assert np.array_equal((b >> (4 * side)) & 15, np.broadcast_to(want, b.shape))
+    # calls agree with the oracle's enumeration on the linear twin's back-pointers
+    calls = variants.call_variants(c, tree)
+    for s in range(0, S, 7):
+        want_c = mlo.call_pattern(tree.ops(), n, tr, s, 0)
+        if s not in calls.tied and len(want_c) == 1:
+            k, comb = want_c[0]
+            assert calls.category[s] == k and list(calls.genotypes[:, s]) == list(comb[n:])
+    c.close()

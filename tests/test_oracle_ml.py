@@ -164,3 +164,36 @@ def test_host_enumerator_of_the_product_matches_the_oracle():
         want = mlo.enumerate_ml_genotypes(ops, n, back_at, back[:n], 0)
         got = variants.enumerate_combinations(children, tree.root, n, back, 0)
         assert got == want and len(got) >= 1
+
+
+def test_linear_space_twin_of_the_max_sum_pruning():
+    """ml_lin_pruning (ScsBeerLikelihoodCore.java:1759-2335) against the log-space twin where the two must agree (no
+    underflow, no zero entry of P), and on what is specific to it: a LEAF child under a zero-length branch contributes
+    log(0 * leaf) = -inf for the off-diagonal genotypes (no Double.MIN_VALUE clamp in :1948-1949), an INTERNAL child keeps
+    the clamp (:2260-2263)."""
+    import numpy as np
+    from oracle import ml_genotypes as mlo
+    rng = np.random.default_rng(5)
+    K, S = 2, 9
+    leafA = rng.uniform(1e-30, 1e-3, (K, S, 4))
+    leafB = rng.uniform(1e-30, 1e-3, (K, S, 4))
+    ml_int = rng.uniform(-300.0, -5.0, (K, S, 4))
+    P = rng.dirichlet(np.ones(4), size=(K, 4)).reshape(K, 16)
+    Q = rng.dirichlet(np.ones(4), size=(K, 4)).reshape(K, 16)
+    # leaf-leaf, leaf-partial, partial-partial against the log twin fed log leaves
+    for (a, la), (b, lb) in (((leafA, True), (leafB, True)), ((leafA, True), (ml_int, False)), ((ml_int, False), (ml_int[::-1], False))):
+        got, gb = mlo.ml_lin_pruning(a, la, P, b, lb, Q)
+        want, wb = mlo.ml_log_pruning(np.log(a) if la else a, P, np.log(b) if lb else b, Q)
+        np.testing.assert_allclose(got, want, rtol=1e-13)
+        assert (gb != wb).mean() < 0.02   # rounding-level near-ties only
+    # zero-length branch above a leaf: identity matrix, unclamped
+    I = np.tile(np.eye(4).reshape(16), (K, 1))
+    got, gb = mlo.ml_lin_pruning(leafA, True, I, None, False, None)
+    np.testing.assert_allclose(got, np.log(leafA), rtol=1e-15)
+    assert np.array_equal(gb, np.broadcast_to(np.array([1, 2, 4, 8], dtype=np.uint8), gb.shape))
+    # ... above an internal node: the clamp keeps every genotype a (hopeless) candidate, the diagonal wins
+    got, gb = mlo.ml_lin_pruning(ml_int, False, I, None, False, None)
+    np.testing.assert_allclose(got, ml_int, rtol=1e-15)
+    # a leaf whose likelihoods all underflowed: every candidate is -inf, every genotype is listed (:1964-1978 compare -inf == -inf)
+    got, gb = mlo.ml_lin_pruning(np.zeros((K, S, 4)), True, P, None, False, None)
+    assert np.all(np.isneginf(got)) and np.all(gb == 15)
