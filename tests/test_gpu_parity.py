@@ -973,19 +973,21 @@ def test_sparse_residency_is_bit_identical_to_dense(core_mod, oracle, monkeypatc
     c.close()
 
 
-def test_pipelined_walk_is_bit_identical(core_mod, oracle, monkeypatch):
-    """SIEVE_B200_PIPE=1 takes the cp.async-pipelined walk (prune_pipe.cuh), SIEVE_B200_RP=1 the register-pipelined walk
-    (prune_rp.cuh), SIEVE_B200_TMA=N the TMA-staged walk with N stages (prune_tma.cuh; needs an even site count): same op
-    list, same arithmetic, so every number must be identical -- resident with proposals / rejections, and streamed with
-    ragged chunks."""
+def test_walk_kernels_are_bit_identical(core_mod, oracle, monkeypatch):
+    """The lean default walk (k_walk, walk.cuh) and the general kernel (k_prune, SIEVE_B200_WALK=0) run the same op list with the
+    same arithmetic, and the L2 prefetch annotations (SIEVE_B200_PF_DIST) only move data: every number must be identical --
+    resident with proposals / rejections, and streamed with ragged chunks.  (The rejected cp.async / register / TMA pipelines
+    this test used to cover live under profiles/experiments/r01_rejected_walks, outside the product library.)"""
     from sieve_b200.treelikelihood import ScsTreeLikelihood
     d = synthetic(41, 334, seed=83)
     counts, tree = d["counts"], d["tree"]
     runs = {}
-    for P in ("0", "1", "rp", "tma2", "tma3", "tma4"):
-        monkeypatch.setenv("SIEVE_B200_PIPE", "1" if P == "1" else "0")
-        monkeypatch.setenv("SIEVE_B200_RP", "1" if P == "rp" else "0")
-        monkeypatch.setenv("SIEVE_B200_TMA", P[3] if P.startswith("tma") else "0")
+    for P in ("default", "k_prune", "pf0", "pf7"):
+        monkeypatch.setenv("SIEVE_B200_WALK", "0" if P == "k_prune" else "1")
+        if P.startswith("pf"):
+            monkeypatch.setenv("SIEVE_B200_PF_DIST", P[2:])
+        else:
+            monkeypatch.delenv("SIEVE_B200_PF_DIST", raising=False)
         out = []
         for eph in (False, True):
             if eph:
@@ -1009,8 +1011,8 @@ def test_pipelined_walk_is_bit_identical(core_mod, oracle, monkeypatch):
             tl.close()
             monkeypatch.delenv("SIEVE_B200_CHUNK_SITES", raising=False)
         runs[P] = out
-    for P in ("1", "rp", "tma2", "tma3", "tma4"):
-        for a, b in zip(runs["0"], runs[P]):
+    for P in ("k_prune", "pf0", "pf7"):
+        for a, b in zip(runs["default"], runs[P]):
             np.testing.assert_array_equal(a, b, err_msg=P)
 
 
