@@ -471,9 +471,13 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
 // scale: the node's own binary exponents, NULL for a leaf; lsum: the sum of the scales of the leaves below the node.
 // One thread per site: the site's K x 4 values are renormalised here, so that the exported bits do not depend on where
 // the walk happened to renormalise (which differs between the dense, sparse and streamed schedules).
+// underflow_log (leaves in log mode, or NULL): the leaf's log-space genotype likelihoods [S][4] ([S][K][4] when
+// underflow_per_cat), taken where the scaled linear value has underflowed to 0 (a genotype more than 2^-1000 below the best
+// one of its (cell, site)): the reference holds a finite log there (RawReadCountsModelFiniteMuDM.java:121-260)
 __global__ void k_export_partials(const double* __restrict__ x, const int* __restrict__ scale,
                                   const double* __restrict__ lsum, int S, int K, int is_leaf, int as_log,
-                                  int clamp_min, double* __restrict__ out) {
+                                  int clamp_min, double* __restrict__ out, const double* __restrict__ underflow_log = nullptr,
+                                  int underflow_per_cat = 0) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     double v[SV_KMAX][4];
@@ -491,6 +495,9 @@ __global__ void k_export_partials(const double* __restrict__ x, const int* __res
             const double vn = v[k][g] * f;
             const double lin = vn * exp(ls);
             // clamp_min: linear-mode constant-site partials, clamped like ScsBeerLikelihoodCore.java:1041-1047
-            out[((size_t)k * S + s) * 4 + g] = as_log ? log(vn) + ls : (clamp_min && !(lin > 0.0) ? SV_MIN_VALUE : lin);
+            double r = as_log ? log(vn) + ls : (clamp_min && !(lin > 0.0) ? SV_MIN_VALUE : lin);
+            if (underflow_log && as_log && vn == 0.0)
+                r = underflow_log[underflow_per_cat ? ((size_t)s * K + k) * 4 + g : (size_t)s * 4 + g];
+            out[((size_t)k * S + s) * 4 + g] = r;
         }
 }

@@ -1623,6 +1623,85 @@ extern "C" int sieve_get_result_device_ptr(sieve_core_t* h, void** d_result) {
     return SIEVE_OK;
 }
 
+// The log-space genotype likelihoods of ONE leaf straight from the log-space mixture (k_leaf_ml / k_leaf_ml_private: the
+// reference's own operation order, no common linear scale), into *d_L ([S][4], private model [S][K][4]; the caller frees
+// it).  sieve_get_node_partials takes them where the scaled linear leaf value has underflowed to 0.
+static int sv_leaf_log_exact(sieve_core* h, int node, double** d_L) {
+    const size_t S = h->S, K = h->K;
+    const int C = h->C;
+    const size_t per = h->private_cov ? K : 1;
+    double* d_cell = nullptr;
+    unsigned short* d_ado = nullptr;
+    *d_L = nullptr;
+    cudaError_t e = cudaMalloc(d_L, sizeof(double) * S * per * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ado, sizeof(unsigned short) * S * per);
+    if (e == cudaSuccess && !h->private_cov) e = cudaMalloc(&d_cell, sizeof(double) * (size_t)C * 4);
+    int rr = SIEVE_OK;
+    if (e == cudaSuccess) {
+        SvDmAlphas al;
+        SvCovParams cp;
+        // the tables of the parameters the CURRENT leaf buffer was computed with (as sv_subtree_leaf_sums)
+        const sieve_leaf_params_t pending = h->lp;
+        h->lp = h->leaf_lp[h->cur_leaf];
+        rr = sv_refresh_leaf_tables(h, &al, &cp);
+        h->lp = pending;
+        if (rr == SIEVE_OK && h->private_cov) {
+            if (!h->have_tv)
+                rr = sv_fail(SIEVE_ERR_STATE, "sieve_get_node_partials: sieve_set_private_seq_cov has not been called");
+            else {
+                SvMlLeafPrivArgs pa;
+                pa.counts = h->d_counts + (size_t)node * S;
+                pa.dmA = h->d_dmA;
+                pa.dmB = h->d_dmB;
+                pa.size_factors = h->d_sf + node;
+                pa.tv = h->d_tv;
+                pa.leafL = *d_L;
+                pa.ado = d_ado;
+                pa.n_cells = 1;
+                pa.S = (int)S;
+                pa.C = C;
+                pa.K = (int)K;
+                pa.al = al;
+                pa.theta = cp.theta;
+                pa.single_ado = cp.single_ado;
+                k_leaf_ml_private<<<dim3((unsigned)((S + 127) / 128), 1), 128, 0, h->stream>>>(pa);
+                sv_count(h);
+            }
+        } else if (rr == SIEVE_OK) {
+            k_build_cell_log_tables<<<dim3((unsigned)((C + 127) / 128), 1), 128, 0, h->stream>>>(d_cell, h->d_sf + node, 1, C, cp);
+            sv_count(h);
+            SvMlLeafArgs la;
+            la.counts = h->d_counts + (size_t)node * S;
+            la.dmA = h->d_dmA;
+            la.dmB = h->d_dmB;
+            la.cellL = d_cell;
+            la.size_factors = h->d_sf + node;
+            la.leafL = *d_L;
+            la.ado = d_ado;
+            la.n_cells = 1;
+            la.S = (int)S;
+            la.C = C;
+            la.counts_stride = (long long)S;
+            la.site_begin = 0;
+            la.al = al;
+            la.cp = cp;
+            k_leaf_ml<<<dim3((unsigned)((S + 127) / 128), 1), 128, 0, h->stream>>>(la);
+            sv_count(h);
+        }
+        if (rr == SIEVE_OK) e = cudaGetLastError();
+        if (rr == SIEVE_OK && e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(d_cell);
+    cudaFree(d_ado);
+    if (rr != SIEVE_OK || e != cudaSuccess) {
+        cudaFree(*d_L);
+        *d_L = nullptr;
+    }
+    if (rr != SIEVE_OK) return rr;
+    SV_CUDA(e);
+    return SIEVE_OK;
+}
+
 extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t which, double* out) {
     SV_REQUIRE(h && out && sv_node_ok(h, node), "sieve_get_node_partials: bad argument");
     SV_REQUIRE(which == 0 || which == 1, "sieve_get_node_partials: which must be 0 or 1");
@@ -1641,10 +1720,15 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     // the leaves' scales live only as sums (leaf.cuh): re-derive the sum over the leaves below this node
     double* d_sub = nullptr;  // [1 + (private model: K, else 1)][S]: scales, constant-genotype log-likelihoods (per category)
     SV_CUDA(cudaMalloc(&d_sub, sizeof(double) * (1 + (h->private_cov ? SV_KMAX : 1)) * S));
+    double* d_exact = nullptr;  // a leaf in log mode: its log-space likelihoods, for the entries the linear scale lost
     struct SubFree {
         double* p;
-        ~SubFree() { cudaFree(p); }
-    } sub_free{d_sub};
+        double** q;
+        ~SubFree() {
+            cudaFree(p);
+            cudaFree(*q);
+        }
+    } sub_free{d_sub, &d_exact};
     if (is_leaf) {
         SV_REQUIRE(which == 0, "leaves have no constant-site partials");
         if (!h->leaves_ready) return sv_fail(SIEVE_ERR_STATE, "leaves not computed yet");
@@ -1652,6 +1736,7 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
         x = h->d_leafX + ((size_t)h->cur_leaf * n + node) * S * (h->private_cov ? SV_KMAX * 4 : 4);
         sc = nullptr;
         if (h->private_cov) is_leaf = 0;  // K x 4 values per site, the layout of an internal partial (no exponent: sc == NULL)
+        if (h->log_mode) SV_TRY(sv_leaf_log_exact(h, node, &d_exact));
     } else {
         const int sl = h->slot_of[(size_t)h->cur_part[node] * h->n_nodes + node];
         if (sl < 0) return sv_fail(SIEVE_ERR_STATE, "sieve_get_node_partials: the node could not be materialised");
@@ -1688,7 +1773,8 @@ extern "C" int sieve_get_node_partials(sieve_core_t* h, int32_t node, int32_t wh
     const size_t N = K * S * 4;
     SV_CUDA(cudaMalloc(&d_out, N * sizeof(double)));
     k_export_partials<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(x, sc, d_sub, (int)S, (int)K, is_leaf,
-                                                                          h->log_mode ? 1 : 0, which == 1 ? 1 : 0, d_out);
+                                                                          h->log_mode ? 1 : 0, which == 1 ? 1 : 0, d_out, d_exact,
+                                                                          h->private_cov ? 1 : 0);
     sv_count(h);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, N * sizeof(double), cudaMemcpyDeviceToHost, h->stream);

@@ -319,13 +319,14 @@ def test_leaf_kernel_all_cells_and_edge_counts(core_mod, oracle, monkeypatch):
                 ref = oracle.leaf_likelihood(c5, j, sf[j], P)
                 got = c.get_node_partials(j)[0]
                 # the device keeps the 4 genotype likelihoods of a (cell, site) in linear space under one common scale:
-                # a genotype more than e^-700 below the best one underflows to 0 (log = -inf).  It cannot influence a
-                # site likelihood by more than 1e-300 relative; such entries (only at coverage in the thousands) are
-                # compared for "hugely negative" only.
+                # a genotype more than e^-700 below the best one underflows to 0 there (it cannot influence a site
+                # likelihood by more than 1e-300 relative; only at coverage in the thousands).  The read-back takes those
+                # entries from the log-space mixture instead, so the reference's finite logs come back everywhere.
                 lost = ref < ref.max(axis=1, keepdims=True) - 700.0
                 assert lost.sum() < 0.02 * ref.size
+                assert np.all(np.isfinite(got))
                 np.testing.assert_allclose(got[~lost], ref[~lost], rtol=2e-13, atol=2e-12)
-                assert np.all(got[lost] < ref.max(axis=1, keepdims=True).repeat(4, 1)[lost] - 700.0)
+                np.testing.assert_allclose(got[lost], ref[lost], rtol=2e-13, atol=2e-12)
             c.close()
 
 
