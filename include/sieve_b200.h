@@ -185,6 +185,15 @@ int sieve_get_private_seq_cov(sieve_core_t *h, double *allelic_seq_cov_ks, doubl
  * the pair back with sieve_set_private_seq_cov).  out_changed: number of pairs whose (t, v) moved.  The caller then
  * recomputes the state (sieve_update_leaves + a whole-tree update), as postProcess does for the changed patterns. */
 int sieve_private_update_from_ml(sieve_core_t *h, int32_t zero_cov_mode, int32_t *out_changed, uint8_t *out_tied);
+/* ScsTreeLikelihood.postProcess step 3 (likelihood/ScsTreeLikelihood.java:2493-2498: "traverse the entire tree for changed
+ * patterns"; the changedPatterns overloads of likelihood/ScsBeerLikelihoodCore.java:584-820, 1070-1266, 1516-1757): the sites
+ * at which any category's (t, v) differs from the pair the current leaves were computed with are re-evaluated IN PLACE --
+ * their leaves, every internal node (ops: the whole tree in post order, triples as for sieve_update_nodes), their site
+ * log-likelihoods and column sums; no buffer is flipped and every other site keeps its value, so the state equals what a
+ * whole-shard pass (sieve_update_leaves + sieve_update_nodes) produces, bit for bit.  The accepted state becomes the stored
+ * state (as by sieve_store).  out_sites: number of re-evaluated sites (0: nothing moved, nothing done).  Follow with
+ * sieve_evaluate for the totals.  Dense resident cores only (SIEVE_ERR_STATE otherwise: use the whole-shard pass). */
+int sieve_private_retraverse_changed(sieve_core_t *h, int32_t n_ops, const int32_t *ops, int32_t *out_sites);
 
 /* new values of the six leaf-model parameters; takes effect at the next sieve_update_leaves */
 int sieve_set_leaf_params(sieve_core_t *h, const sieve_leaf_params_t *p);

@@ -34,6 +34,10 @@ public final class SieveB200 {
     /** updateAllelicSeqCovAndRawVar from the max-sum trace of the current state (ScsTreeLikelihood.postProcess); returns the
      *  number of (category, pattern) pairs whose values moved; outTied[K * nSites] flags the pairs left to the host */
     public static native int privateUpdateFromMl(long h, int zeroCovMode, byte[] outTied);
+    /** ScsTreeLikelihood.postProcess step 3 (:2493-2498): the patterns whose (t, v) moved are re-evaluated in place (leaves, the
+     *  whole tree -- ops = (parent, child1, child2) triples in post order --, site log-likelihoods); the accepted state becomes
+     *  the stored state; returns the number of re-evaluated sites.  Dense resident cores. */
+    public static native int privateRetraverseChanged(long h, int[] ops);
     public static native void updateLeaves(long h, boolean forUpdate);
     public static native void setNodeMatrixForUpdate(long h, int node);
     public static native void setNodeMatrix(long h, int node, int category, double[] p16);

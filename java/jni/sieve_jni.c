@@ -97,6 +97,15 @@ JNIEXPORT jint JNICALL FN(privateUpdateFromMl)(JNIEnv *e, jclass c, jlong h, jin
     chk(e, rc);
     return changed;
 }
+JNIEXPORT jint JNICALL FN(privateRetraverseChanged)(JNIEnv *e, jclass c, jlong h, jintArray ops) {
+    const jsize n = (*e)->GetArrayLength(e, ops) / 3;
+    jint *po = (*e)->GetPrimitiveArrayCritical(e, ops, NULL);
+    int32_t sites = 0;
+    int rc = sieve_private_retraverse_changed(H(h), (int32_t)n, (const int32_t *)po, &sites);
+    (*e)->ReleasePrimitiveArrayCritical(e, ops, po, JNI_ABORT);
+    chk(e, rc);
+    return sites;
+}
 JNIEXPORT void JNICALL FN(mlTrace)(JNIEnv *e, jclass c, jlong h) { chk(e, sieve_ml_trace(H(h))); }
 JNIEXPORT void JNICALL FN(mlCall)(JNIEnv *e, jclass c, jlong h, jbyteArray g, jbyteArray a, jbyteArray k, jbyteArray m) {
     jbyte *pg = (*e)->GetPrimitiveArrayCritical(e, g, NULL), *pa = (*e)->GetPrimitiveArrayCritical(e, a, NULL);

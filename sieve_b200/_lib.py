@@ -79,6 +79,7 @@ SIGNATURES = {
     "sieve_set_private_seq_cov": (C.c_int, [_vp, _dp, _dp]),
     "sieve_get_private_seq_cov": (C.c_int, [_vp, _dp, _dp]),
     "sieve_private_update_from_ml": (C.c_int, [_vp, C.c_int32, _ip, _vp]),
+    "sieve_private_retraverse_changed": (C.c_int, [_vp, C.c_int32, _ip, _ip]),
     "sieve_set_leaf_params": (C.c_int, [_vp, C.POINTER(LeafParams)]),
     "sieve_update_leaves": (C.c_int, [_vp, C.c_int32]),
     "sieve_set_node_matrix_for_update": (C.c_int, [_vp, C.c_int32]),

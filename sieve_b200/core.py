@@ -117,6 +117,14 @@ class ScsCudaLikelihoodCore:
         check(self.L.sieve_private_update_from_ml(self.h, int(zero_cov_mode), C.byref(changed), tied.ctypes.data))
         return int(changed.value), tied
 
+    def private_retraverse_changed(self, ops):
+        """ScsTreeLikelihood.postProcess step 3 (:2493-2498): the patterns whose (t, v) moved are re-evaluated in place
+        (leaves, whole tree, site log-likelihoods); the accepted state becomes the stored state.  -> number of sites"""
+        o = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 3)
+        n = C.c_int32()
+        check(self.L.sieve_private_retraverse_changed(self.h, int(o.shape[0]), o.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)))
+        return int(n.value)
+
     def update_leaves(self, for_update=True):
         check(self.L.sieve_update_leaves(self.h, int(bool(for_update))))
 

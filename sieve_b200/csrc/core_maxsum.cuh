@@ -426,3 +426,85 @@ extern "C" int sieve_private_update_from_ml(sieve_core_t* h, int32_t zero_cov_mo
     if (changed) h->ml_ready = false;  // the trace belongs to the old (t, v)
     return SIEVE_OK;
 }
+
+// ScsTreeLikelihood.postProcess step 3 (likelihood/ScsTreeLikelihood.java:2493-2498): "traverse the entire tree for changed
+// patterns" -- the changedPatterns overloads of the core (ScsBeerLikelihoodCore.java:584-820, 1070-1266, 1516-1757) restated
+// as ONE site list for the device: the sites at which any category's (t, v) differs from the pair the current leaves were
+// computed with (after sieve_private_update_from_ml and / or sieve_set_private_seq_cov).  Their leaves, the whole tree
+// above them, their per-site log-likelihoods and column sums are re-evaluated IN PLACE in the current buffers -- as in
+// the reference no buffer is flipped: every other site keeps its value, which is what a whole-shard pass would
+// reproduce bit for bit.  The accepted state then becomes the stored state (sieve_store), since buffers the stored state
+// shares with the current one have changed.  ops: the whole tree in post order, as for sieve_update_nodes.
+extern "C" int sieve_private_retraverse_changed(sieve_core_t* h, int32_t n_ops, const int32_t* ops, int32_t* out_sites) {
+    SV_REQUIRE(h && out_sites && n_ops > 0 && ops, "sieve_private_retraverse_changed: bad argument");
+    if (!h->private_cov || !h->have_tv)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_private_retraverse_changed: needs a SIEVE_FLAG_PRIVATE_SEQ_COV core with its (t, v) set");
+    if (h->sparse || h->ephemeral)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_private_retraverse_changed: needs a dense resident core");
+    if (!h->leaves_ready || !h->tv_leaf_ok)
+        return sv_fail(SIEVE_ERR_STATE, "sieve_private_retraverse_changed: the leaves have not been computed yet");
+    for (int i = 0; i < n_ops; i++)
+        SV_REQUIRE(ops[3 * i] >= h->n && ops[3 * i] < h->n_nodes, "sieve_private_retraverse_changed: parent must be an internal node");
+    SV_CUDA(cudaSetDevice(h->device));
+    SV_TRY(sv_flush(h));  // nothing queued earlier may be mixed into the partial pass
+    const int S = h->S;
+    unsigned char* d_flag = nullptr;
+    int *d_list = nullptr, *d_n = nullptr;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int n_list = 0;
+    thrust::counting_iterator<int> sites(0);
+    cudaError_t e = cudaMalloc(&d_flag, S);
+    if (e == cudaSuccess) e = cudaMalloc(&d_list, sizeof(int) * S);
+    if (e == cudaSuccess) e = cudaMalloc(&d_n, sizeof(int));
+    if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, sites, d_flag, d_list, d_n, S, h->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) {
+        if (h->site_out_stale)
+            // the per-site outputs belong to a rejected proposal (sieve_restore since the last evaluation: not a sequence the
+            // reference produces, accept follows an accepted evaluation): every site is re-evaluated
+            e = cudaMemsetAsync(d_flag, 1, S, h->stream);
+        else {
+            k_tv_changed<<<(S + 255) / 256, 256, 0, h->stream>>>(h->d_tv, h->d_tv_leaf, S, h->K, d_flag);
+            sv_count(h);
+        }
+        if (e == cudaSuccess) {
+            e = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, sites, d_flag, d_list, d_n, S, h->stream);  // ascending site order
+            sv_count(h);
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_list, d_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    int r = SIEVE_OK;
+    if (e == cudaSuccess && n_list > 0) {
+        // leaves of the listed sites into the CURRENT leaf buffer (its other sites hold exactly what a full pass would write)
+        h->ml_ready = false;
+        h->leaf_ver[h->cur_leaf] = ++h->ver_counter;
+        if (h->single_leaf) h->leaf_changed_since_store = true;
+        const bool algebraic = h->with_const && !h->const_twin;
+        r = sv_launch_leaf_private(h, h->d_leafX + (size_t)h->cur_leaf * h->n * h->S * SV_KMAX * 4, nullptr, h->n, h->d_sumS,
+                                   h->d_sum0K, h->d_lsum + (size_t)h->cur_leaf * h->S,
+                                   algebraic ? h->d_lambdaK + (size_t)h->cur_leaf * SV_KMAX * h->S : nullptr, h->S, d_list, n_list);
+        // every internal node, in place (no flip), over the listed sites
+        for (int i = 0; r == SIEVE_OK && i < n_ops; i++) r = sv_record_children(h, ops[3 * i + 1], ops[3 * i + 2], ops[3 * i]);
+        if (r == SIEVE_OK) {
+            for (int i = 0; i < n_ops; i++) h->dirty_list.push_back(ops[3 * i]);
+            h->partial_list = d_list;
+            h->partial_n = n_list;
+            r = sv_flush(h);
+            h->partial_list = nullptr;
+            h->partial_n = 0;
+            if (r == SIEVE_OK && n_list == S) h->site_out_stale = false;
+        }
+        if (r == SIEVE_OK) e = cudaStreamSynchronize(h->stream);  // the list is freed below
+        if (r == SIEVE_OK) r = sieve_store(h);
+    }
+    cudaFree(d_flag);
+    cudaFree(d_list);
+    cudaFree(d_n);
+    cudaFree(d_tmp);
+    if (r != SIEVE_OK) return r;
+    SV_CUDA(e);
+    *out_sites = n_list;
+    return SIEVE_OK;
+}

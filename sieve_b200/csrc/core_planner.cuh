@@ -507,8 +507,12 @@ static int sv_plan_resident_ops(sieve_core* h) {
         sv_bound_op(h, v, h->eph_c1[v], h->eph_c2[v], &op);
         if (!store) op.flags |= SV_OP_NOSTORE;
         h->pending_ops.push_back(op);
-        h->valid[v] = store ? 1 : 0;
-        if (store) {
+        // a flush over a site list (sieve_private_retraverse_changed) writes the listed sites only: a node whose buffer was
+        // not in memory before may be written for its consumer, but it does not become a resident value
+        const bool partial_invalid = h->partial_list && !h->valid[v];
+        h->valid[v] = store && !partial_invalid ? 1 : 0;
+        if (partial_invalid) h->buf_has[bi] = 0;
+        if (store && !partial_invalid) {
             h->buf_has[bi] = 1;
             h->buf_ver[bi] = h->ver_cur[v];
             h->buf_fp[bi] = h->fp_cur[v];

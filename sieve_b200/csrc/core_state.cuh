@@ -190,6 +190,12 @@ struct sieve_core {
     // then holds K x 4 values per (cell, site) and the constant-site column sums are kept per category
     bool private_cov = false, have_tv = false;
     double2* d_tv = nullptr;       // [KMAX][S]
+    double2* d_tv_leaf = nullptr;  // [KMAX][S] the pairs the CURRENT leaf buffer was computed with (sieve_private_retraverse_changed)
+    bool tv_leaf_ok = false;
+    bool site_out_stale = true;   // d_site_logl does not belong to the current state (nothing evaluated yet, or sieve_restore
+                                  // since: like the reference's patternLogLikelihoods, the per-site outputs are not restored)
+    const int* partial_list = nullptr;  // while sieve_private_retraverse_changed runs: the flush covers these sites only, in place
+    int partial_n = 0;
     double* d_lambdaK = nullptr;   // [leaf buffers][KMAX][S]
     double* d_sum0K = nullptr;     // scratch [cell groups][KMAX][S]
     double logw[SV_KMAX] = {0, 0, 0, 0}, logw_stored[SV_KMAX] = {0, 0, 0, 0};  // log(prop_k G_root[k][rg]) + scale of G_root

@@ -23,6 +23,8 @@ struct SvLeafPrivArgs {
     const double* dmB;        // [C][2]
     const double* size_factors;
     const int* cell_list;     // NULL: entry e is cell e
+    const int* site_list;     // NULL: every site of the shard; else the n_list sites to evaluate (in place: the patterns whose
+    int n_list;               // (t, v) moved at an accepted state, sieve_private_retraverse_changed)
     const double2* tv;        // [K][tv_stride] (t, v) of every (category, site) of the shard
     double* leafXK;           // [cell][out_stride][KMAX][4] (already offset to the write buffer) or NULL: sums only
     double* sumS;             // [cell group][sum_stride]
@@ -52,8 +54,12 @@ __global__ void __launch_bounds__(SV_LEAFP_THREADS) k_leaf_private(SvLeafPrivArg
         dmA = sA;
         dmB = sB;
     }
-    const int s = blockIdx.x * SV_LEAFP_THREADS + tid;
-    if (s >= a.S) return;
+    int s = blockIdx.x * SV_LEAFP_THREADS + tid;
+    if (a.site_list) {
+        if (s >= a.n_list) return;
+        s = a.site_list[s];
+    } else if (s >= a.S)
+        return;
     const int e0 = blockIdx.y * SV_LEAF_CELLS;
     const int e1 = min(a.n_cells, e0 + SV_LEAF_CELLS);
     const int K = a.K;
@@ -160,9 +166,14 @@ __global__ void __launch_bounds__(SV_LEAFP_THREADS) k_leaf_private(SvLeafPrivArg
 __global__ void __launch_bounds__(256) k_colsum_private(const double* __restrict__ sumS, const double* __restrict__ sum0,
                                                         int n_groups, int S, int K, long long stride,
                                                         double* __restrict__ lsum, double* __restrict__ lambdaK,
-                                                        long long lambda_stride) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
+                                                        long long lambda_stride, const int* __restrict__ site_list = nullptr,
+                                                        int n_list = 0) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (site_list) {
+        if (s >= n_list) return;
+        s = site_list[s];
+    } else if (s >= S)
+        return;
     double a = 0.0;
     for (int g = 0; g < n_groups; g++) a += __ldg(sumS + (size_t)g * stride + s);
     lsum[s] = a;
@@ -193,6 +204,20 @@ __global__ void __launch_bounds__(256) k_const_private(const double* __restrict_
     double sum = 0.0;
     for (int k = 0; k < K; k++) sum += exp(v[k] - mx);
     site_const[s] = log(sum) + mx;
+}
+
+// flag[s] = 1 where the (t, v) pair of any category of site s differs (bitwise) from the pair the current leaves were
+// computed with: the patterns ScsTreeLikelihood.postProcess re-traverses (likelihood/ScsTreeLikelihood.java:2493-2498)
+__global__ void __launch_bounds__(256) k_tv_changed(const double2* __restrict__ tv, const double2* __restrict__ tv_leaf, int S,
+                                                    int K, unsigned char* __restrict__ flag) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    unsigned char f = 0;
+    for (int k = 0; k < K; k++) {
+        const double2 a = tv[(size_t)k * S + s], b = tv_leaf[(size_t)k * S + s];
+        f |= (__double_as_longlong(a.x) != __double_as_longlong(b.x)) || (__double_as_longlong(a.y) != __double_as_longlong(b.y));
+    }
+    flag[s] = f;
 }
 
 // ---- accept-time re-estimation of (t, v) --------------------------------------------------------------------------

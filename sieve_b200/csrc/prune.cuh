@@ -39,6 +39,8 @@ struct SvPruneArgs {
     int pf_dist;           // ops ahead that the L2 prefetch annotations look (0: none); the first pf_dist ops are announced by a prologue
     int S, K;              // S = sites of this launch; the ops' rows were formed with the pools' site capacity
     long long out_offset;  // first site of this launch in site_logl / site_const (streamed evaluation)
+    const int* site_list;  // LEAFK kernel only, or NULL: the S sites of this launch are site_list[0 .. S) of the shard (in-place
+                           // re-evaluation of the patterns whose (t, v) moved, sieve_private_retraverse_changed)
     int linear_const_clamp;  // !SIEVE_FLAG_LOG_PARTIALS: clamp of the constant-site product (:1041-1047)
     int const_genotype;
     int root_genotype;
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         const int site = site0 + 8 * j;
         site_ok[j] = site < a.S;
         srow[j] = (unsigned)(site_ok[j] ? site : a.S - 1);
+        if constexpr (LEAFK)
+            if (a.site_list) srow[j] = (unsigned)__ldg(a.site_list + srow[j]);
     }
     double* wm = sm + warp * (2 * SV_KMAX * SV_MAT_STRIDE);
     // staging role of this lane: matrix `which` (child 1 / 2), category kk, row q  ->  4 doubles = one 256-bit load
@@ -454,13 +458,14 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 // the scales of ALL leaves, which the walk never carried, come in here
-                const double lsum = site_ok[j] ? __ldg(a.lsum + a.out_offset + site0 + 8 * j) : 0.0;
-                if (site_ok[j] && klane == 0) a.site_logl[a.out_offset + site0 + 8 * j] = log(v) + fma((double)xs[j], SV_LN2, lsum);
+                const long long os = a.out_offset + (long long)srow[j];  // srow = the site itself wherever site_ok
+                const double lsum = site_ok[j] ? __ldg(a.lsum + os) : 0.0;
+                if (site_ok[j] && klane == 0) a.site_logl[os] = log(v) + fma((double)xs[j], SV_LN2, lsum);
                 if (WITH_CONST) {
                     double cv = (klane < a.K ? a.prop[klane] : 0.0) * (GENO0 ? cx[j][0] : sv_sel(cx[j], rg));
                     cv += __shfl_xor_sync(0xffffffffu, cv, 1);
                     cv += __shfl_xor_sync(0xffffffffu, cv, 2);
-                    if (site_ok[j] && klane == 0) a.site_const[a.out_offset + site0 + 8 * j] = log(cv) + fma((double)cxs[j], SV_LN2, lsum);
+                    if (site_ok[j] && klane == 0) a.site_const[os] = log(cv) + fma((double)cxs[j], SV_LN2, lsum);
                 }
             }
         }

@@ -192,6 +192,7 @@ extern "C" int sieve_create(const sieve_config_t* cfg, sieve_core_t** out) {
     }
     if (h->private_cov) {
         CR(sv_alloc(h, &h->d_tv, (size_t)SV_KMAX * S));
+        CR(sv_alloc(h, &h->d_tv_leaf, (size_t)SV_KMAX * S));
         if (algebraic) {
             CR(sv_alloc(h, &h->d_sum0K, leaf_groups * SV_KMAX * pool_sites));
             CR(sv_alloc(h, &h->d_lambdaK, (size_t)2 * SV_KMAX * S));
@@ -270,6 +271,7 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_cpart);
     cudaFree(h->d_lambda);
     cudaFree(h->d_tv);
+    cudaFree(h->d_tv_leaf);
     cudaFree(h->d_lambdaK);
     cudaFree(h->d_sum0K);
     cudaFree(h->d_cscale);
@@ -786,8 +788,10 @@ static int sv_launch_leaf_kernels(sieve_core* h, long long site_begin, int n_sit
 }
 
 // the same for a core with the per-pattern coverage model: k_leaf_private + k_colsum_private; lambdaK_out is [KMAX][lambda_stride]
+// d_site_list (or NULL: the whole shard): only these n_list sites are evaluated and written, everything else stays as it is
 static int sv_launch_leaf_private(sieve_core* h, double* leafXK, const int* d_cell_list, int n_entries, double* sumS,
-                                  double* sum0K, double* lsum_out, double* lambdaK_out, long long lambda_stride) {
+                                  double* sum0K, double* lsum_out, double* lambdaK_out, long long lambda_stride,
+                                  const int* d_site_list = nullptr, int n_list = 0) {
     if (!h->have_tv) return sv_fail(SIEVE_ERR_STATE, "sieve_set_private_seq_cov must be called before the leaves are computed");
     SvLeafPrivArgs a;
     SvCovParams cp_unused;
@@ -797,6 +801,8 @@ static int sv_launch_leaf_private(sieve_core* h, double* leafXK, const int* d_ce
     a.dmB = h->d_dmB;
     a.size_factors = h->d_sf;
     a.cell_list = d_cell_list;
+    a.site_list = d_site_list;
+    a.n_list = n_list;
     a.tv = h->d_tv;
     a.leafXK = leafXK;
     a.sumS = sumS;
@@ -820,13 +826,19 @@ static int sv_launch_leaf_private(sieve_core* h, double* leafXK, const int* d_ce
         SV_CUDA(cudaFuncSetAttribute(k_leaf_private, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    dim3 grid((h->S + SV_LEAFP_THREADS - 1) / SV_LEAFP_THREADS, groups);
+    const int n_eval = d_site_list ? n_list : h->S;
+    dim3 grid((n_eval + SV_LEAFP_THREADS - 1) / SV_LEAFP_THREADS, groups);
     k_leaf_private<<<grid, SV_LEAFP_THREADS, smem, h->stream>>>(a);
     sv_count(h);
-    k_colsum_private<<<(h->S + 255) / 256, 256, 0, h->stream>>>(sumS, a.sum0, groups, h->S, h->K, h->S, lsum_out, lambdaK_out,
-                                                               lambda_stride);
+    k_colsum_private<<<(n_eval + 255) / 256, 256, 0, h->stream>>>(sumS, a.sum0, groups, h->S, h->K, h->S, lsum_out, lambdaK_out,
+                                                                 lambda_stride, d_site_list, n_list);
     sv_count(h);
     SV_CUDA(cudaGetLastError());
+    if (leafXK && !d_cell_list) {
+        // the leaf buffer now holds the current pairs (for all sites: an unlisted site's pair did not move)
+        SV_CUDA(cudaMemcpyAsync(h->d_tv_leaf, h->d_tv, sizeof(double2) * SV_KMAX * h->S, cudaMemcpyDeviceToDevice, h->stream));
+        h->tv_leaf_ok = true;
+    }
     return SIEVE_OK;
 }
 
@@ -1247,12 +1259,14 @@ static int sv_launch_staged(sieve_core* h) {
         for (int k = 0; k < 4; k++) a.prop[k] = h->prop[k];
         a.site_logl = h->d_site_logl;
         a.site_const = h->d_site_const;
+        a.site_list = h->partial_list;
+        if (h->partial_list) a.S = h->partial_n;
         if (h->private_cov && (a.const_genotype != 0 || a.root_genotype != 0))
             return sv_fail(SIEVE_ERR_STATE, "SIEVE_FLAG_PRIVATE_SEQ_COV cores support root / constant genotype 0 only (ScsFiniteMuExtendedModel)");
         // the Q-specialised walk needs every matrix of the launch to have been given as a distance (and genotype 0)
         const bool qfast = h->last_qfast && a.const_genotype == 0 && a.root_genotype == 0 && !h->force_generic;
         const int spb = sv_prune_sites(h->with_const && h->const_twin, qfast);
-        const unsigned gx = (unsigned)((h->S + spb - 1) / spb);
+        const unsigned gx = (unsigned)(((h->partial_list ? (size_t)h->partial_n : h->S) + spb - 1) / spb);
         auto launch = [&](dim3 grid) {
             if (qfast)
                 sv_launch_prune_t<true>(h, grid, a);
@@ -1444,6 +1458,9 @@ static int sv_flush(sieve_core* h) {
     h->last_levels = h->pending_levels;
     h->last_per_level = h->pending_per_level;
     SV_TRY(sv_launch_staged(h));
+    if (!h->partial_list)
+        for (const SvOp& op : h->pending_ops)
+            if (op.flags & SV_OP_ROOT) h->site_out_stale = false;  // every site's log-likelihood was just written
     SV_CUDA(cudaEventRecord(h->ev_stage[h->stage_sel], h->stream));
     h->ev_stage_set[h->stage_sel] = true;
     prof.lap(3);
@@ -1858,6 +1875,7 @@ extern "C" int sieve_restore(sieve_core_t* h) {
     h->fp_cur.swap(h->fp_stored);
     if (h->eph_c1 != h->eph_c1_stored || h->eph_c2 != h->eph_c2_stored) h->topo_cache_ok = false;
     h->ml_ready = false;
+    h->site_out_stale = true;
     // after a rejected parameter proposal the tables hold the rejected values; they are compared with the values of
     // the next sieve_set_leaf_params at the next leaf update, so nothing has to be rebuilt here
     return SIEVE_OK;

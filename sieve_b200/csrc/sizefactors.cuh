@@ -7,6 +7,7 @@
 // The sort is CUB's segmented radix sort (one-off initialisation, not on the per-step path).
 #pragma once
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "common.cuh"
 

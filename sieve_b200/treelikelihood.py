@@ -51,6 +51,9 @@ class ScsTreeLikelihood:
         self.use_distances = use_distances
         # PrivateAllelicSeqCovModel instead of ExploredSharedAllelicSeqCovModel: (t, v) per (category, pattern)
         self.private_seq_cov, self.zero_cov_mode, self.single_ado = bool(private_seq_cov), int(zero_cov_mode), bool(single_ado)
+        # accept(): re-evaluate only the patterns whose (t, v) moved (as the reference does); False: a whole-shard pass
+        self.retraverse_changed_only = bool(private_seq_cov) and not (ephemeral or sparse)
+        self.last_retraversed_sites = None
         self._counts = counts          # a reference (tied pairs / tied sites are re-examined on the host side)
         self._ctor = dict(n_categories=n_categories, use_log_partials=use_log_partials, single_ado=single_ado, device=device,
                           use_distances=use_distances)
@@ -99,11 +102,19 @@ class ScsTreeLikelihood:
             changed += resolve_tied_pairs(self.core, self.tree, self._counts, self.size_factors, tied, self.zero_cov_mode,
                                           self.single_ado)
         if changed:
-            # the reference re-traverses the changed patterns only (:2493-2498); every pattern here -- unchanged pairs
-            # reproduce their values bit for bit
-            self.update_leaves = True
-            self.has_dirt = max(self.has_dirt, IS_DIRTY)
-            self.calculate_logp()
+            if self.retraverse_changed_only:
+                # step 3 (:2493-2498): the whole tree for the changed patterns only, in place; the accepted state is the
+                # stored state afterwards
+                self.last_retraversed_sites = self.core.private_retraverse_changed(self.tree.ops())
+                self.result = self.core.evaluate()
+                if not self.return_const_sum:
+                    self.logP = combine_shards([self.result], self.asc_mode, self.M)
+                self.store()
+            else:
+                # a whole-shard pass: unchanged pairs reproduce their values bit for bit
+                self.update_leaves = True
+                self.has_dirt = max(self.has_dirt, IS_DIRTY)
+                self.calculate_logp()
         return changed
 
     def call_variants(self):

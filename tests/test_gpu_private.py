@@ -194,6 +194,80 @@ def test_accept_mirror_and_idempotence(core_mod, oracle):
     tl.close()
 
 
+def test_retraverse_of_changed_patterns_equals_a_whole_shard_pass(core_mod, oracle):
+    """ScsTreeLikelihood.postProcess step 3 (:2493-2498): sieve_private_retraverse_changed re-evaluates, in place, only the
+    patterns whose (t, v) moved.  Chain A uses it, chain B the whole-shard pass (leaf flip + every node): logP, both per-site
+    vectors and node read-backs must agree bit for bit through accepted and rejected tree moves in between, and the later
+    accepts must touch fewer sites than the shard has.  (An accept right after a REJECTED move is not a sequence BEAST produces;
+    the per-site outputs then belong to the rejected proposal -- as the reference's patternLogLikelihoods would -- and the core
+    re-evaluates every site.)"""
+    from sieve_b200.treelikelihood import ScsTreeLikelihood
+    n, S = 19, 333          # ragged: not a multiple of the kernels' site blocks
+    d = synthetic(n, S, seed=11)
+    counts, tree = d["counts"], d["tree"]
+    sf, _ = oracle.size_factors(oracle.counts5(counts))
+    mk = lambda: ScsTreeLikelihood(counts, tree.copy(), size_factors=sf, asc_mode="felsenstein_mean", n_background_sites=5e3,
+                                   private_seq_cov=True)
+    A, B = mk(), mk()
+    assert A.retraverse_changed_only
+    B.retraverse_changed_only = False
+    assert A.calculate_logp() == B.calculate_logp()
+    rng = np.random.default_rng(3)
+    touched = []
+
+    def same_state():
+        assert A.logP == B.logP
+        for x, y in zip(A.pattern_log_likelihoods(), B.pattern_log_likelihoods()):
+            np.testing.assert_array_equal(x, y)
+        ta, tb = A.core.get_private_seq_cov(), B.core.get_private_seq_cov()
+        np.testing.assert_array_equal(ta[0], tb[0])
+        np.testing.assert_array_equal(ta[1], tb[1])
+
+    for it in range(6):
+        ma, mb = A.accept(), B.accept()
+        assert ma == mb
+        if ma:
+            touched.append(A.last_retraversed_sites)
+            assert 0 < touched[-1] <= S
+        same_state()
+        # node read-backs: a leaf, a small (transient) node, a large one, the root -- the variant and the constant-site partials
+        for node in (0, n - 1, tree.n, tree.n + 3, tree.root - 1, tree.root):
+            np.testing.assert_array_equal(A.core.get_node_partials(node), B.core.get_node_partials(node))
+            if node >= tree.n:
+                np.testing.assert_array_equal(A.core.get_node_partials(node, const=True), B.core.get_node_partials(node, const=True))
+        # a tree move in between: accepted on even rounds, rejected on odd ones
+        t2 = A.tree.copy()
+        node = int(rng.integers(tree.n, tree.node_count - 1))
+        lo = max(t2.height[t2.left[node]], t2.height[t2.right[node]])
+        t2.height[node] = lo + (t2.height[t2.parent[node]] - lo) * rng.random()
+        for tl in (A, B):
+            tl.store()
+            tl.set_tree(t2.copy(), [node])
+            tl.calculate_logp()
+        same_state()
+        if it % 2 == 1:
+            for tl in (A, B):
+                tl.restore()
+                tl.calculate_logp()
+            same_state()
+    assert len(touched) >= 3 and min(touched[1:]) < S      # later accepts move a part of the patterns only
+    assert touched[2] == S                                  # ... except right after a rejected move (stale per-site outputs)
+    # and the state after one more accept (the loop ended on a rejected move: per-site outputs are the proposal's until then)
+    # is the oracle's evaluation under the final pairs
+    assert A.accept() == B.accept()
+    same_state()
+    from oracle import private_allelic as pa
+    t_fin, v_fin = A.core.get_private_seq_cov()
+    P = oracle.leaf_params(*A.params.as_tuple(), single_ado=True)
+    mats = substmodel.node_matrices(A.tree, A.rates)
+    sl, lc, _ = pa.full_eval_private(oracle, oracle.counts5(counts), sf, P, t_fin, v_fin, A.tree.ops(), mats, A.proportions, A.tree.root)
+    got_l, got_c = A.pattern_log_likelihoods()
+    _close(got_l, sl, 1e-12)
+    _close(got_c, lc, 1e-12)
+    A.close()
+    B.close()
+
+
 def test_private_core_rejects_unsupported_modes(core_mod):
     for kw in (dict(sparse=True), dict(ephemeral=True), dict(single_leaf_buffer=True)):
         with pytest.raises(RuntimeError):
