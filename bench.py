@@ -10,7 +10,8 @@ complete evaluation of the hot path: leaf read-count likelihoods of every (cell,
 pruning of every internal node with fresh transition matrices (a relaxed-clock / scaler proposal dirties the whole tree),
 root integration, per-site log and reduction, acquisition-bias term.  At N > 1 the data set is N x 100,000 sites, one
 contiguous site range per rank (weak scaling, sites are independent) with GLOBAL size factors (exact distributed
-selection, sieve_sf_*); the only per-step exchange is a native NCCL all-gather of 5 doubles per rank.
+selection, sieve_sf_*); the only per-step exchange is the all-gather of 5 doubles per rank, fused into the reduction
+kernel over peer memory (ncclAllGather where the mailboxes cannot be mapped).
 
 value  : steps/s with matrices and ops already staged in HBM (kernels only, CUDA events on the handle's stream; the same
          native K-step loop at every N).
@@ -473,7 +474,10 @@ def main():
     W = Workload(n, S, SEED + 17 * rank, dev, local, world, mode=args.mode)
     core, tree = W.core, W.tree
     if world > 1:
-        bind_native_comm(core)      # every evaluation now ends with the native NCCL all-gather of the 5-double results
+        bind_native_comm(core)      # every evaluation now ends with the exchange of the 5-double results of all ranks
+    exchange_desc = {0: "no exchange (one rank)", 1: "ncclAllGather of 5 doubles per rank behind every reduction",
+                     2: "exchange of 5 doubles per rank fused into the reduction kernel over NVLink peer memory (CUDA IPC "
+                        "mailboxes; NCCL only at set-up)"}[core.comm_exchange_mode()]
     lib_stream = torch.cuda.ExternalStream(core.stream(), device=dev)
 
     r_first = W.exact_eval()
@@ -740,7 +744,7 @@ def main():
                                     "sparse_single_leaf": "sparse residency, one leaf buffer"}[args.mode],
                        "transition_matrices": "branch distances, P formed on the device (fixed Q)",
                        "l2": "inputs larger than L2 (%.1f GB of partials per evaluation)" % (alg_prune / 1e9),
-                       "parallelism": "site shards x%d, global size factors, native NCCL all-gather of 5 doubles per rank and step" % world},
+                       "parallelism": "site shards x%d, global size factors, %s" % (world, exchange_desc)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stage_bytes), "d2h_bytes_per_step": 40,
                     "ms_per_step": 1000.0 * e2e_s_max / args.steps},
             "e2e_dropin": dropin,

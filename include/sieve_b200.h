@@ -328,6 +328,10 @@ double sieve_combine_shards(const sieve_shard_result_t *shards, int32_t n_shards
 int sieve_comm_unique_id(uint8_t *id_out128);
 int sieve_comm_init(sieve_core_t *h, int32_t rank, int32_t world, const uint8_t *id128);
 int sieve_comm_size(sieve_core_t *h);
+/* how the per-evaluation exchange runs on this handle: 0 = not bound to a communicator, 1 = ncclAllGather behind the
+ * reduction, 2 = fused into the reduction kernel over peer memory (every rank maps its peers' mailboxes through CUDA IPC at
+ * sieve_comm_init; chosen when all ranks could, SIEVE_B200_P2P=0 forces 1) */
+int sieve_comm_exchange_mode(sieve_core_t *h);
 int sieve_last_global_results(sieve_core_t *h, sieve_shard_result_t *out_world);
 
 /* calcPatternPoints (likelihood/ThreadedScsTreeLikelihood.java:227-238): points[n_shards + 1] */

@@ -113,6 +113,7 @@ SIGNATURES = {
     "sieve_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "sieve_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
     "sieve_comm_size": (C.c_int, [_vp]),
+    "sieve_comm_exchange_mode": (C.c_int, [_vp]),
     "sieve_last_global_results": (C.c_int, [_vp, C.POINTER(ShardResult)]),
     "sieve_combine_shards": (C.c_double, [C.POINTER(ShardResult), C.c_int32, C.c_int32, C.c_double]),
     "sieve_pattern_points": (None, [C.c_int32, C.c_int32, _ip]),

@@ -303,6 +303,10 @@ class ScsCudaLikelihoodCore:
     def comm_size(self):
         return self.L.sieve_comm_size(self.h)
 
+    def comm_exchange_mode(self):
+        """0: no communicator; 1: ncclAllGather behind the reduction; 2: fused into the reduction kernel over peer memory"""
+        return self.L.sieve_comm_exchange_mode(self.h)
+
     def last_global_results(self):
         n = self.comm_size()
         arr = (ShardResult * n)()

@@ -132,6 +132,13 @@ struct sieve_core {
     int comm_rank = 0, comm_world = 1;
     double* d_gather = nullptr;   // [world][5]
     double* h_gather = nullptr;   // pinned
+    // peer-memory exchange fused into k_reduce (reduce.cuh, SvMail); p2p == false: ncclAllGather per evaluation instead
+    bool p2p = false;
+    double* d_mail = nullptr;             // own mailbox [2][world][8]
+    std::vector<void*> peer_mail;         // IPC mappings of the peers' mailboxes (own slot: d_mail)
+    double** d_peers = nullptr;           // the same pointers on the device
+    unsigned int* d_mail_err = nullptr;
+    unsigned long long mail_step = 0;
 
     // Change tracking (resident planner): every matrix slot, leaf buffer and node value carries a version number, and a
     // node remembers the versions of the inputs its value was computed from.  A node that the caller marks dirty but

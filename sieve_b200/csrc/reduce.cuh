@@ -54,6 +54,52 @@ __device__ __forceinline__ SvAcc sv_acc_zero() {
     return a;
 }
 
+// The one exchange step of the multi-GPU path, fused into the reduction (comm.cuh sets it up): every rank owns a mailbox
+// [2 parities][world][8 doubles] in its HBM that its peers have mapped through CUDA IPC.  The last block of k_reduce writes
+// this rank's five totals straight into every peer's mailbox over NVLink (slot = this rank), fences, raises the slot's flag
+// (the evaluation counter), then waits for the world's flags in its OWN mailbox and copies the rows into `gather` -- the
+// all-gather of likelihood/ThreadedScsTreeLikelihood.java:366-379 without a second kernel or a library call.  Two
+// parities: a rank can be at most one evaluation ahead of a peer (it needs the peer's flag of evaluation t to finish t),
+// so the rows of t + 1 never overwrite rows of t that are still being read.  peers == NULL: single process, no exchange.
+struct SvMail {
+    double* const* peers;        // [world] device pointers to the mailboxes (own one at [rank])
+    double* gather;              // [world][5] on this device
+    unsigned int* error;         // set to 1 when a peer did not answer within the time limit
+    unsigned long long step;     // evaluation counter, the same on every rank; starts at 1
+    int rank, world;
+};
+#define SV_MAIL_ROW 8
+#define SV_MAIL_TIMEOUT_NS 600000000000ull  // 10 minutes: a peer may legitimately be busy on its host for a while
+
+__device__ __forceinline__ unsigned long long sv_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void sv_mail_exchange(const SvMail& m, const double* res /*shared, [5]*/) {
+    const int r = threadIdx.x;
+    if (r >= m.world) return;
+    const size_t par = (size_t)(m.step & 1ull) * m.world;
+    volatile double* dst = m.peers[r] + (par + m.rank) * SV_MAIL_ROW;
+    for (int i = 0; i < 5; i++) dst[i] = res[i];
+    __threadfence_system();
+    reinterpret_cast<volatile unsigned long long*>(dst)[5] = m.step;
+    volatile double* src = m.peers[m.rank] + (par + r) * SV_MAIL_ROW;
+    const unsigned long long t0 = sv_globaltimer();
+    bool ok = true;
+    while (reinterpret_cast<volatile unsigned long long*>(src)[5] != m.step) {
+        if (sv_globaltimer() - t0 > SV_MAIL_TIMEOUT_NS) {
+            ok = false;
+            break;
+        }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    if (!ok) *m.error = 1u;
+    for (int i = 0; i < 5; i++) m.gather[r * 5 + i] = ok ? src[i] : __longlong_as_double(0x7ff8000000000000LL);
+}
+
 // out layout == sieve_shard_result_t {sum_log_l, const_lse, const_sum, lewis_sum, weight_sum}
 // The constant-site log-likelihood of site s is  cst[s] + cst_shift:  with the algebraic constant-site path cst is
 // Lambda (sum over cells of the leaves' constant-genotype log-likelihoods) and cst_shift = log C_tree (one number per
@@ -61,7 +107,7 @@ __device__ __forceinline__ SvAcc sv_acc_zero() {
 __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl, const double* __restrict__ cst,
                                                 double cst_shift, const int* __restrict__ w, int S, int with_const,
                                                 SvAcc* __restrict__ partials, unsigned int* __restrict__ counter,
-                                                double* __restrict__ out) {
+                                                double* __restrict__ out, SvMail mail = SvMail{nullptr, nullptr, nullptr, 0, 0, 1}) {
     __shared__ SvAcc sm[8];
     __shared__ bool last;
     SvAcc acc = sv_acc_zero();
@@ -105,14 +151,20 @@ __global__ void __launch_bounds__(256) k_reduce(const double* __restrict__ logl,
             if ((int)threadIdx.x < d) sv_acc_merge(fin[threadIdx.x], fin[threadIdx.x + d]);
             __syncthreads();
         }
+        __shared__ double res[5];
         if (threadIdx.x == 0) {
             t = fin[0];
-            out[0] = t.sum;
-            out[1] = with_const ? log(t.se) + t.m : 0.0;
-            out[2] = t.csum;
-            out[3] = -t.lewis;
-            out[4] = t.wsum;
+            res[0] = t.sum;
+            res[1] = with_const ? log(t.se) + t.m : 0.0;
+            res[2] = t.csum;
+            res[3] = -t.lewis;
+            res[4] = t.wsum;
+            for (int i = 0; i < 5; i++) out[i] = res[i];
             *counter = 0u;
+        }
+        if (mail.peers) {
+            __syncthreads();
+            sv_mail_exchange(mail, res);
         }
     }
 }

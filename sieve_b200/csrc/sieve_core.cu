@@ -294,6 +294,11 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_mlamb);
     cudaFree(h->d_mlcats);
     cudaFree(h->d_mlops);
+    for (size_t r = 0; r < h->peer_mail.size(); r++)
+        if (h->peer_mail[r] && h->peer_mail[r] != (void*)h->d_mail) cudaIpcCloseMemHandle(h->peer_mail[r]);
+    cudaFree(h->d_mail);
+    cudaFree(h->d_peers);
+    cudaFree(h->d_mail_err);
     if (h->comm && sv_nccl().ok) sv_nccl().CommDestroy(h->comm);
     cudaFree(h->d_gather);
     if (h->h_gather) cudaFreeHost(h->h_gather);
@@ -1498,18 +1503,35 @@ static void sv_launch_const_private(sieve_core* h) {
     sv_count(h);
 }
 
-static void sv_launch_reduce(sieve_core* h) {
+// the totals of the shard and -- bound to a communicator -- their exchange with the other ranks: fused into the reduction over
+// peer memory (reduce.cuh, SvMail) or, when the mailboxes could not be mapped, as an ncclAllGather behind it
+static int sv_launch_reduce(sieve_core* h) {
     const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
+    SvMail mail{nullptr, nullptr, nullptr, 0, 0, 1};
+    if (h->comm && h->p2p) {
+        mail.peers = h->d_peers;
+        mail.gather = h->d_gather;
+        mail.error = h->d_mail_err;
+        mail.step = ++h->mail_step;
+        mail.rank = h->comm_rank;
+        mail.world = h->comm_world;
+    }
     if (h->private_cov && h->with_const) {
         sv_launch_const_private(h);
         k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, h->d_site_const, 0.0, h->d_weights, h->S, 1, h->d_partials,
-                                                h->d_counter, h->d_result);
-        return;
+                                                h->d_counter, h->d_result, mail);
+    } else {
+        const bool algebraic = h->with_const && !h->const_twin;
+        const double* cst = algebraic ? h->d_lambda + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S) : h->d_site_const;
+        k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, cst, algebraic ? h->log_c : 0.0, h->d_weights, h->S,
+                                                h->with_const ? 1 : 0, h->d_partials, h->d_counter, h->d_result, mail);
     }
-    const bool algebraic = h->with_const && !h->const_twin;
-    const double* cst = algebraic ? h->d_lambda + (h->ephemeral ? 0 : (size_t)h->cur_leaf * h->S) : h->d_site_const;
-    k_reduce<<<blocks, 256, 0, h->stream>>>(h->d_site_logl, cst, algebraic ? h->log_c : 0.0, h->d_weights, h->S,
-                                            h->with_const ? 1 : 0, h->d_partials, h->d_counter, h->d_result);
+    sv_count(h);
+    if (h->comm && !h->p2p) {
+        ncclResult_t nr = sv_nccl().AllGather(h->d_result, h->d_gather, 5, ncclDouble, h->comm, h->stream);
+        if (nr != ncclSuccess) return sv_fail(SIEVE_ERR_CUDA, std::string("ncclAllGather: ") + sv_nccl().GetErrorString(nr));
+    }
+    return SIEVE_OK;
 }
 
 static int sv_evaluate(sieve_core* h, sieve_shard_result_t* out) {
@@ -1517,19 +1539,18 @@ static int sv_evaluate(sieve_core* h, sieve_shard_result_t* out) {
     SV_TRY(sv_flush(h));
     if (h->timing) SV_CUDA(cudaEventRecord(h->ev[3], h->stream));
     const int blocks = std::min(SV_REDUCE_BLOCKS, (h->S + 255) / 256);
-    sv_launch_reduce(h);
-    sv_count(h);
+    SV_TRY(sv_launch_reduce(h));  // + the one exchange of the multi-GPU path: every rank's 5 doubles to every rank
     SV_CUDA(cudaGetLastError());
     if (h->timing) SV_CUDA(cudaEventRecord(h->ev[4], h->stream));
     SV_CUDA(cudaMemcpyAsync(h->h_result, h->d_result, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    unsigned int mail_err = 0;
     if (h->comm) {
-        // the one exchange of the multi-GPU path: every rank's 5 doubles to every rank, ordered after the reduce kernel
-        ncclResult_t nr = sv_nccl().AllGather(h->d_result, h->d_gather, 5, ncclDouble, h->comm, h->stream);
-        if (nr != ncclSuccess) return sv_fail(SIEVE_ERR_CUDA, std::string("ncclAllGather: ") + sv_nccl().GetErrorString(nr));
         SV_CUDA(cudaMemcpyAsync(h->h_gather, h->d_gather, (size_t)h->comm_world * 5 * sizeof(double), cudaMemcpyDeviceToHost,
                                 h->stream));
+        if (h->p2p) SV_CUDA(cudaMemcpyAsync(&mail_err, h->d_mail_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     }
     SV_CUDA(cudaStreamSynchronize(h->stream));
+    if (mail_err) return sv_fail(SIEVE_ERR_CUDA, "the peer-memory exchange timed out: a rank did not reach this evaluation");
     if (out) {
         out->sum_log_l = h->h_result[0];
         out->const_lse = h->h_result[1];
@@ -1606,12 +1627,7 @@ extern "C" int sieve_replay(sieve_core_t* h, int32_t update_leaves, int32_t n_ti
             if (!h->ephemeral) SV_TRY(sv_launch_leaves(h, 0, h->S, h->S));
         }
         SV_TRY(sv_launch_staged(h));
-        sv_launch_reduce(h);
-        sv_count(h);
-        if (h->comm) {  // the per-evaluation exchange of a multi-process run, as in sv_evaluate
-            ncclResult_t nr = sv_nccl().AllGather(h->d_result, h->d_gather, 5, ncclDouble, h->comm, h->stream);
-            if (nr != ncclSuccess) return sv_fail(SIEVE_ERR_CUDA, std::string("ncclAllGather: ") + sv_nccl().GetErrorString(nr));
-        }
+        SV_TRY(sv_launch_reduce(h));  // with the per-evaluation exchange of a multi-process run, as in sv_evaluate
     }
     SV_CUDA(cudaGetLastError());
     return SIEVE_OK;
@@ -1930,6 +1946,88 @@ extern "C" int sieve_comm_unique_id(uint8_t* id_out128) {
     return SIEVE_OK;
 }
 
+// Mailboxes for the exchange fused into k_reduce (reduce.cuh, SvMail): every rank allocates one, the CUDA IPC handles go
+// round with one ncclAllGather, every rank maps its peers' mailboxes (NVLink peer access) and a second all-gather makes
+// sure that EVERY rank succeeded -- otherwise all of them keep the ncclAllGather per evaluation (ranks inside one process
+// cannot open each other's handles, a device pair without peer access cannot map).  SIEVE_B200_P2P=0 forces that path.
+static int sv_mail_setup(sieve_core* h) {
+    const int world = h->comm_world, rank = h->comm_rank;
+    h->p2p = false;
+    const char* env = getenv("SIEVE_B200_P2P");
+    int want = !(env && atoi(env) == 0);
+    const size_t mail_bytes = (size_t)2 * world * SV_MAIL_ROW * sizeof(double);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (want && (cudaMalloc(&h->d_mail, mail_bytes) != cudaSuccess || cudaMemset(h->d_mail, 0, mail_bytes) != cudaSuccess ||
+                 cudaMalloc(&h->d_peers, sizeof(double*) * world) != cudaSuccess ||
+                 cudaMalloc(&h->d_mail_err, sizeof(unsigned int)) != cudaSuccess ||
+                 cudaMemset(h->d_mail_err, 0, sizeof(unsigned int)) != cudaSuccess))
+        want = 0;
+    if (want && world > 1 && cudaIpcGetMemHandle(&mine, h->d_mail) != cudaSuccess) want = 0;
+    cudaGetLastError();
+    // round 1: (want, handle) of every rank
+    const size_t rec = 8 + sizeof(cudaIpcMemHandle_t);
+    std::vector<unsigned char> all(rec * world, 0);
+    unsigned char* d_all = nullptr;
+    SV_CUDA(cudaMalloc(&d_all, rec * world));
+    {
+        std::vector<unsigned char> me(rec, 0);
+        me[0] = (unsigned char)want;
+        memcpy(me.data() + 8, &mine, sizeof(mine));
+        SV_CUDA(cudaMemcpyAsync(d_all + rec * rank, me.data(), rec, cudaMemcpyHostToDevice, h->stream));
+        ncclResult_t nr = sv_nccl().AllGather(d_all + rec * rank, d_all, rec, ncclChar, h->comm, h->stream);
+        if (nr != ncclSuccess) {
+            cudaFree(d_all);
+            return sv_fail(SIEVE_ERR_CUDA, std::string("ncclAllGather: ") + sv_nccl().GetErrorString(nr));
+        }
+        SV_CUDA(cudaMemcpyAsync(all.data(), d_all, rec * world, cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    int ok = want;
+    for (int r = 0; r < world; r++) ok = ok && all[rec * r] != 0;
+    h->peer_mail.assign(world, nullptr);
+    if (ok) {
+        for (int r = 0; r < world && ok; r++) {
+            if (r == rank) {
+                h->peer_mail[r] = h->d_mail;
+                continue;
+            }
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, all.data() + rec * r + 8, sizeof(hd));
+            if (cudaIpcOpenMemHandle(&h->peer_mail[r], hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                h->peer_mail[r] = nullptr;
+                ok = 0;
+            }
+        }
+        cudaGetLastError();
+    }
+    // round 2: did everybody map everybody?
+    {
+        unsigned char flag = (unsigned char)ok;
+        SV_CUDA(cudaMemcpyAsync(d_all + rank, &flag, 1, cudaMemcpyHostToDevice, h->stream));
+        ncclResult_t nr = sv_nccl().AllGather(d_all + rank, d_all, 1, ncclChar, h->comm, h->stream);
+        if (nr != ncclSuccess) {
+            cudaFree(d_all);
+            return sv_fail(SIEVE_ERR_CUDA, std::string("ncclAllGather: ") + sv_nccl().GetErrorString(nr));
+        }
+        SV_CUDA(cudaMemcpyAsync(all.data(), d_all, world, cudaMemcpyDeviceToHost, h->stream));
+        SV_CUDA(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < world; r++) ok = ok && all[r] != 0;
+    }
+    cudaFree(d_all);
+    if (ok) {
+        SV_CUDA(cudaMemcpy(h->d_peers, h->peer_mail.data(), sizeof(double*) * world, cudaMemcpyHostToDevice));
+        h->p2p = true;
+        h->mail_step = 0;
+    }
+    if (getenv("SIEVE_B200_COMM_DEBUG"))
+        fprintf(stderr, "sieve_comm_init: rank %d of %d, exchange %s\n", rank, world,
+                h->p2p ? "fused into k_reduce over peer memory (CUDA IPC mailboxes)" : "ncclAllGather per evaluation");
+    return SIEVE_OK;
+}
+
+extern "C" int sieve_comm_exchange_mode(sieve_core_t* h) { return !h || !h->comm ? 0 : (h->p2p ? 2 : 1); }
+
 extern "C" int sieve_comm_init(sieve_core_t* h, int32_t rank, int32_t world, const uint8_t* id128) {
     SV_REQUIRE(h && id128 && world >= 1 && rank >= 0 && rank < world, "sieve_comm_init: bad argument");
     if (!sv_nccl().ok) return sv_fail(SIEVE_ERR_CUDA, "libnccl.so.2 could not be loaded");
@@ -1945,7 +2043,7 @@ extern "C" int sieve_comm_init(sieve_core_t* h, int32_t rank, int32_t world, con
     h->comm_world = world;
     SV_TRY(sv_alloc(h, &h->d_gather, (size_t)world * 5));
     SV_CUDA(cudaMallocHost((void**)&h->h_gather, (size_t)world * 5 * sizeof(double)));
-    return SIEVE_OK;
+    return sv_mail_setup(h);
 }
 
 extern "C" int sieve_comm_size(sieve_core_t* h) { return h && h->comm ? h->comm_world : 1; }
