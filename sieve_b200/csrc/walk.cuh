@@ -23,6 +23,39 @@ __device__ __forceinline__ const char* sv_row_addr(const char* base, unsigned ro
     return reinterpret_cast<const char*>(r);
 }
 
+// binary exponents through addresses formed by sv_row_addr: ptxas cannot see that they are global and emits generic LD / ST;
+// -DSV_WALK_GLOBAL_SCALE (experiment) states the address space
+__device__ __forceinline__ int sv_ld_scale(const char* p) {
+#ifdef SV_WALK_GLOBAL_SCALE
+    int v;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return *reinterpret_cast<const int*>(p);
+#endif
+}
+__device__ __forceinline__ void sv_st_scale(const char* p, int v) {
+#ifdef SV_WALK_GLOBAL_SCALE
+    asm volatile("st.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    *reinterpret_cast<int*>(const_cast<char*>(p)) = v;
+#endif
+}
+
+// the 32-byte op descriptor: one 256-bit load (-DSV_WALK_DESC256, experiment) or two 128-bit ones
+__device__ __forceinline__ void sv_ld_desc(const SvOp* p, int4& lo, int4& hi) {
+#ifdef SV_WALK_DESC256
+    unsigned long long r0, r1, r2, r3;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r0), "=l"(r1), "=l"(r2), "=l"(r3) : "l"(p));
+    lo = make_int4((int)(unsigned)r0, (int)(unsigned)(r0 >> 32), (int)(unsigned)r1, (int)(unsigned)(r1 >> 32));
+    hi = make_int4((int)(unsigned)r2, (int)(unsigned)(r2 >> 32), (int)(unsigned)r3, (int)(unsigned)(r3 >> 32));
+#else
+    const int4* q = reinterpret_cast<const int4*>(p);
+    lo = __ldg(q);
+    hi = __ldg(q + 1);
+#endif
+}
+
 template <int MINB>
 __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? MINB : SV_PRUNE_MINB_Q)) k_walk(SvPruneArgs a) {
     constexpr int NS = SV_PRUNE_NS_Q;
@@ -73,20 +106,12 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         for (int g = 0; g < 4; g++) x[j][g] = 0.0;
     }
     int4 n0 = make_int4(0, 0, 0, 0), n1 = make_int4(0, 0, 0, 0);
-    if (i0 < i1) {
-        const int4* opp = reinterpret_cast<const int4*>(a.ops + i0);
-        n0 = __ldg(opp);
-        n1 = __ldg(opp + 1);
-    }
+    if (i0 < i1) sv_ld_desc(a.ops + i0, n0, n1);
 #pragma unroll 1
     for (int i = i0; i < i1; i++) {
         __syncwarp();  // scratch slots are reused (streamed mode): keep the warp's reads of an op ahead of the next op's writes
         const int4 o0 = n0, o1 = n1;
-        if (i + 1 < i1) {  // the next op's descriptor, one op ahead: off the chain descriptor -> addresses -> loads
-            const int4* opp = reinterpret_cast<const int4*>(a.ops + i + 1);
-            n0 = __ldg(opp);
-            n1 = __ldg(opp + 1);
-        }
+        if (i + 1 < i1) sv_ld_desc(a.ops + i + 1, n0, n1);  // the next op's descriptor, one op ahead: off the chain descriptor -> addresses -> loads
         const int flags = o1.y;
         // leaf operands of the op pf_dist ahead: into L2 now
         if ((flags & SV_OP_PF1) && pf_lane) sv_prefetch_leaf(leaf_base + ((size_t)((unsigned)o1.z + pf_srow) << 5));
@@ -111,7 +136,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
                 SV_BOUND(row < (leaf2 ? a.leaf_rows : a.part_rows) && o1.x >= 0 && o1.x < a.n_matrix_slots);
                 sv_ld256(reinterpret_cast<const double*>(sv_row_addr(base, row, stride)), w[j]);
                 we[j] = 0;
-                if (!leaf2) we[j] = *reinterpret_cast<const int*>(sv_row_addr(scale_base, row, 4u));
+                if (!leaf2) we[j] = sv_ld_scale(sv_row_addr(scale_base, row, 4u));
             }
         }
         if (!(flags & SV_OP_FWD1)) {
@@ -124,7 +149,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
                 SV_BOUND(row < (leaf1 ? a.leaf_rows : a.part_rows));
                 sv_ld256(reinterpret_cast<const double*>(sv_row_addr(base, row, stride)), x[j]);
                 xe[j] = 0;
-                if (!leaf1) xe[j] = *reinterpret_cast<const int*>(sv_row_addr(scale_base, row, 4u));
+                if (!leaf1) xe[j] = sv_ld_scale(sv_row_addr(scale_base, row, 4u));
             }
         }
         // ---- contraction(s) and product; both arms of the (rare) renormalisation write the registers that carry the
@@ -166,7 +191,7 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
                 const unsigned row = (unsigned)o0.x + srow[j];
                 SV_BOUND(row < a.part_rows);
                 sv_st256(reinterpret_cast<double*>(const_cast<char*>(sv_row_addr(part_base, row, 128u))), x[j]);
-                *reinterpret_cast<int*>(const_cast<char*>(sv_row_addr(scale_base, row, 4u))) = xe[j];  // every category lane writes the (identical) exponent
+                sv_st_scale(sv_row_addr(scale_base, row, 4u), xe[j]);  // every category lane writes the (identical) exponent
             }
         }
         if (flags & SV_OP_ROOT) {
