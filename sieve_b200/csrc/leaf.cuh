@@ -193,8 +193,15 @@ __device__ __forceinline__ double sv_seq_cov_log_terms(int x, const SvCovCellTer
     return l;
 }
 
+// logGamma(x + 1) for every table row: depends on nothing but x, so it is tabulated once per count tensor (sv_alloc_tables)
+// instead of once per (cell, row) of every coverage-parameter proposal -- a third of k_build_cell_tables' logGamma chains
+__global__ void k_build_lgx1(double* __restrict__ lgx1, int C) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < C) lgx1[x] = sv_log_gamma(__dadd_rn((double)x, 1.0));
+}
+
 __global__ void k_build_cell_tables(double* __restrict__ cellT, const double* __restrict__ size_factors, int n_cells,
-                                    int C, SvCovParams cp) {
+                                    int C, SvCovParams cp, const double* __restrict__ lgx1) {
     __shared__ SvCovCellTerms terms[3];  // 2, 1 and (locus dropout) 0 sequenced alleles
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -202,7 +209,7 @@ __global__ void k_build_cell_tables(double* __restrict__ cellT, const double* __
     if (threadIdx.x < 3) terms[threadIdx.x] = sv_seq_cov_cell_terms(2 - (int)threadIdx.x, size_factors[j], cp.t, cp.v);
     __syncthreads();
     if (x >= C) return;
-    const double lg_x1 = sv_log_gamma(__dadd_rn((double)x, 1.0));
+    const double lg_x1 = __ldg(lgx1 + x);  // the same function of the same argument as before: same bits
     const double c2 = sv_seq_cov_log_terms(x, terms[0], lg_x1);
     const double c1 = sv_seq_cov_log_terms(x, terms[1], lg_x1);
     const double lt = log(cp.theta), l1t = log(1 - cp.theta);

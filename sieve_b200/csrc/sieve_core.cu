@@ -272,6 +272,7 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_lambda);
     cudaFree(h->d_tv);
     cudaFree(h->d_tv_leaf);
+    cudaFree(h->d_lgx1);
     cudaFree(h->d_lambdaK);
     cudaFree(h->d_sum0K);
     cudaFree(h->d_cscale);
@@ -390,6 +391,11 @@ static int sv_alloc_tables(sieve_core* h) {
         SV_CUDA(cudaMemsetAsync(h->d_linA, 0, (size_t)h->C * SV_LINA_STRIDE * sizeof(double), h->stream));  // the rows' padding
         SV_CUDA(cudaMemsetAsync(h->d_linB, 0, (size_t)h->C * SV_LINB_STRIDE * sizeof(double), h->stream));
         SV_TRY(sv_alloc(h, &h->d_cellT, (size_t)h->n * h->C * 4));
+        cudaFree(h->d_lgx1);
+        h->d_lgx1 = nullptr;
+        SV_TRY(sv_alloc(h, &h->d_lgx1, (size_t)h->C));
+        k_build_lgx1<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->d_lgx1, h->C);
+        sv_count(h);
     }
     h->dm_dirty = h->cov_dirty = true;
     // one pass over the counts (ingest time): are the tables complete for this shard?
@@ -719,7 +725,7 @@ static int sv_refresh_leaf_tables(sieve_core* h, SvDmAlphas* al_out, SvCovParams
     if (h->cov_dirty && h->private_cov) h->cov_dirty = false;  // the coverage terms are evaluated directly (leaf_private.cuh)
     if (h->cov_dirty) {
         dim3 g((C + 127) / 128, h->n);
-        k_build_cell_tables<<<g, 128, 0, h->stream>>>(h->d_cellT, h->d_sf, h->n, C, cp);
+        k_build_cell_tables<<<g, 128, 0, h->stream>>>(h->d_cellT, h->d_sf, h->n, C, cp, h->d_lgx1);
         sv_count(h);
         h->cov_dirty = false;
     }
