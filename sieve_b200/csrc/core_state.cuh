@@ -197,6 +197,7 @@ struct sieve_core {
     // then holds K x 4 values per (cell, site) and the constant-site column sums are kept per category
     bool private_cov = false, have_tv = false;
     double* d_lgx1 = nullptr;      // [C] logGamma(x + 1) of the table rows (k_build_lgx1)
+    double2* d_cellT2 = nullptr;   // [cell][C] compact rows of the cell table for k_leaf_lin (single dropout)
     double2* d_tv = nullptr;       // [KMAX][S]
     double2* d_tv_leaf = nullptr;  // [KMAX][S] the pairs the CURRENT leaf buffer was computed with (sieve_private_retraverse_changed)
     bool tv_leaf_ok = false;

@@ -200,8 +200,12 @@ __global__ void k_build_lgx1(double* __restrict__ lgx1, int C) {
     if (x < C) lgx1[x] = sv_log_gamma(__dadd_rn((double)x, 1.0));
 }
 
+// cellT2 (or NULL): the compact twin of the rows for k_leaf_lin, single dropout only: (+-rho, m) in 16 bytes.  Of the two
+// mixture weights exp(a - m), exp(b - m) with m = max(a, b) the larger one is exp(0) = 1 exactly, so the row only needs the
+// smaller one, rho, and which of the two it is (the sign bit: negative <=> the FIRST weight is rho) -- the same two
+// doubles come back bit for bit, from half the bytes of L1 / L2 traffic per look-up.
 __global__ void k_build_cell_tables(double* __restrict__ cellT, const double* __restrict__ size_factors, int n_cells,
-                                    int C, SvCovParams cp, const double* __restrict__ lgx1) {
+                                    int C, SvCovParams cp, const double* __restrict__ lgx1, double2* __restrict__ cellT2) {
     __shared__ SvCovCellTerms terms[3];  // 2, 1 and (locus dropout) 0 sequenced alleles
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -221,6 +225,11 @@ __global__ void k_build_cell_tables(double* __restrict__ cellT, const double* __
         e[1] = exp(b - m);
         e[2] = m;
         e[3] = log(e[0] + e[1]) + m;
+        if (cellT2) {
+            // (NaN parameters give NaN in both forms; a == b gives (1, 1) in both)
+            const bool first_is_one = a >= b;
+            cellT2[(size_t)j * C + x] = make_double2(first_is_one ? e[1] : -e[0], m);
+        }
     } else {
         const double c0 = sv_seq_cov_log_terms(x, terms[2], lg_x1);
         const double a = 2 * l1t + c2, b = lt + l1t + c1, z = 2 * lt + c0;
@@ -277,6 +286,7 @@ struct SvLeafArgs {
     const double* dmA;      // [C][4]
     const double* dmB;      // [C][2]
     const double* cellT;    // [cell][C][4]
+    const double2* cellT2;  // [cell][C] compact rows (+-rho, m) for k_leaf_lin, or NULL
     const double *linA, *linB;  // linear-space tables of k_leaf_lin (k_build_dm_tables)
     const double* size_factors;
     const int* cell_list;   // NULL: entry e is cell e; else the cells to evaluate (read-back of a subtree's sums)
@@ -581,7 +591,11 @@ __global__ void __launch_bounds__(SV_LEAFL_THREADS, SV_LEAFL_MINB) k_leaf_lin(Sv
     }
     for (int e = e0c; e < e1c; e++) {
         const int j = a.cell_list ? a.cell_list[e] : e;
+#ifdef SV_LEAF_CT32
         const double* cT = a.cellT + (size_t)j * C * 4;
+#else
+        const double2* cT2 = a.cellT2 + (size_t)j * C;
+#endif
         double* outX = a.leafX ? a.leafX + (size_t)j * a.out_stride * 4 : nullptr;
         int4 c[SV_LEAFL_IT];
 #pragma unroll
@@ -605,7 +619,19 @@ __global__ void __launch_bounds__(SV_LEAFL_THREADS, SV_LEAFL_MINB) k_leaf_lin(Sv
                      c[it].z < C && ref < C);
             // the coverage mixture of this (cell, coverage): one 256-bit row through L1 (k_build_cell_tables)
             double ce[4];
+#ifdef SV_LEAF_CT32
             sv_leaf_row256(cT + 4 * cov, ce);
+#else
+            {
+                // the compact row: 16 bytes through L1 (k_build_cell_tables); the larger weight is exactly 1
+                const double2 t = __ldg(cT2 + cov);
+                const bool first_is_rho = __double2hiint(t.x) < 0;
+                const double rho = fabs(t.x);
+                ce[0] = first_is_rho ? rho : 1.0;
+                ce[1] = first_is_rho ? 1.0 : rho;
+                ce[2] = t.y;
+            }
+#endif
             // numerators: genotypes 0/0 and 1/1 take alpha0 = w1, 1/1' and 0/1 take w2
             const double2 bm = *reinterpret_cast<const double2*>(sB + SV_LINB_STRIDE * cov);
             const unsigned be = *reinterpret_cast<const unsigned*>(sB + SV_LINB_STRIDE * cov + 2);

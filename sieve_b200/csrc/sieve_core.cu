@@ -273,6 +273,7 @@ extern "C" int sieve_destroy(sieve_core_t* h) {
     cudaFree(h->d_tv);
     cudaFree(h->d_tv_leaf);
     cudaFree(h->d_lgx1);
+    cudaFree(h->d_cellT2);
     cudaFree(h->d_lambdaK);
     cudaFree(h->d_sum0K);
     cudaFree(h->d_cscale);
@@ -392,7 +393,10 @@ static int sv_alloc_tables(sieve_core* h) {
         SV_CUDA(cudaMemsetAsync(h->d_linB, 0, (size_t)h->C * SV_LINB_STRIDE * sizeof(double), h->stream));
         SV_TRY(sv_alloc(h, &h->d_cellT, (size_t)h->n * h->C * 4));
         cudaFree(h->d_lgx1);
+        cudaFree(h->d_cellT2);
         h->d_lgx1 = nullptr;
+        h->d_cellT2 = nullptr;
+        if (h->single_ado && !h->private_cov) SV_TRY(sv_alloc(h, &h->d_cellT2, (size_t)h->n * h->C));
         SV_TRY(sv_alloc(h, &h->d_lgx1, (size_t)h->C));
         k_build_lgx1<<<(h->C + 127) / 128, 128, 0, h->stream>>>(h->d_lgx1, h->C);
         sv_count(h);
@@ -695,7 +699,7 @@ static bool sv_lin_tables_ok(const SvDmAlphas& al, int C) {
 // Does the default leaf kernel (k_leaf_lin) apply?  Every count inside the tables, single dropout, constant genotype 0, the
 // tables in range and small enough for two blocks per SM to stage them in shared memory.
 static bool sv_leaf_lin_ok(const sieve_core* h) {
-    return h->leaf_lin_allowed && h->tables_cover_counts && h->single_ado && h->const_genotype == 0 && h->lin_range_ok &&
+    return h->leaf_lin_allowed && h->tables_cover_counts && h->single_ado && h->d_cellT2 && h->const_genotype == 0 && h->lin_range_ok &&
            h->leaf_tab == 1 && (size_t)h->C * (SV_LINA_STRIDE + SV_LINB_STRIDE) * sizeof(double) <= 100 * 1024;
 }
 
@@ -725,7 +729,7 @@ static int sv_refresh_leaf_tables(sieve_core* h, SvDmAlphas* al_out, SvCovParams
     if (h->cov_dirty && h->private_cov) h->cov_dirty = false;  // the coverage terms are evaluated directly (leaf_private.cuh)
     if (h->cov_dirty) {
         dim3 g((C + 127) / 128, h->n);
-        k_build_cell_tables<<<g, 128, 0, h->stream>>>(h->d_cellT, h->d_sf, h->n, C, cp, h->d_lgx1);
+        k_build_cell_tables<<<g, 128, 0, h->stream>>>(h->d_cellT, h->d_sf, h->n, C, cp, h->d_lgx1, h->d_cellT2);
         sv_count(h);
         h->cov_dirty = false;
     }
@@ -749,6 +753,7 @@ static int sv_launch_leaf_kernels(sieve_core* h, long long site_begin, int n_sit
     a.dmA = h->d_dmA;
     a.dmB = h->d_dmB;
     a.cellT = h->d_cellT;
+    a.cellT2 = h->d_cellT2;
     a.linA = h->d_linA;
     a.linB = h->d_linB;
     a.size_factors = h->d_sf;
