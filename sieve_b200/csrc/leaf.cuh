@@ -82,17 +82,32 @@ __device__ __forceinline__ void sv_split_exp(double y, double* m_out, int* e_out
     *m_out = m;
     *e_out = k;
 }
-#define SV_LIN_BIAS 4096      // bias of the 16-bit binary exponents of the linear tables
-#define SV_LIN_MAX_LOG 2700.0 // largest |LP| the 13-bit exponents hold with room to spare (host check, sv_lin_tables_ok)
-#define SV_LINA_STRIDE 6      // doubles per row: 48 bytes, so that 8 consecutive rows start in 8 different groups of 4 banks
-#define SV_LINB_STRIDE 6
-
 // The same tables in LINEAR space for the default leaf kernel (k_leaf_lin): the reciprocals exp(-LP(c, alpha)) of the four
-// denominators' columns and exp(+LP(c, alpha)) of the two numerators, each as a mantissa in [1, 2) and a biased 16-bit
-// binary exponent, so that a Dirichlet-multinomial likelihood is five multiplications per genotype instead of four sums
-// and an exp: the leaf kernel is bound by the FP64 pipe, and the four exp were most of its FP64 work.
-//   linA[c] = { m0, m1, m2, m3, (e0 | e1 << 16 | e2 << 32 | e3 << 48) }      (48-byte rows)
-//   linB[c] = { m0, m1, (e0 | e1 << 16) }                                    (48-byte rows); linB[0] = e^1: the cov == 0 quirk
+// denominators' columns and exp(+LP(c, alpha)) of the two numerators, each as a mantissa in [1, 2) and a binary exponent,
+// so that a Dirichlet-multinomial likelihood is five multiplications per genotype instead of four sums and an exp.
+// The kernel is bound by L1TEX wavefronts (ncu: 97 % of the LSU data pipe, more than half of them these look-ups), so the
+// rows are as narrow as they can be: the exponent travels INSIDE the double -- a mantissa in [1, 2) has the constant sign /
+// exponent field 0x3FF, and those 12 bits hold the biased exponent instead (sv_lin_pack / sv_lin_unpack).  Three arrays of
+// 16-byte entries, so that a random row falls into a random one of the 8 groups of 4 banks:
+//   linA = [ (col 0, col 1) x C | (col 2, col 3) x C ],  linB = [ (w1, w2) x C ];  linB[0] = e^1: the cov == 0 quirk.
+// 12 bits: |exponent| < 2048, i.e. |LP| <= SV_LIN_MAX_LOG (host check sv_lin_tables_ok: otherwise, and for NaN entries,
+// the log-space kernel runs).
+#define SV_LIN_BIAS 2048
+#define SV_LIN_MAX_LOG 1400.0
+#define SV_LINA_STRIDE 4      // doubles per count in linA / linB (sizes only: see the layout above)
+#define SV_LINB_STRIDE 2
+
+__device__ __forceinline__ double sv_lin_pack(double m /* in [1, 2) */, int e) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(m) & 0x000FFFFFFFFFFFFFull;
+    return __longlong_as_double((long long)(b | ((unsigned long long)(unsigned)(e + SV_LIN_BIAS) << 52)));
+}
+// -> the mantissa as a double in [1, 2); E = the biased exponent
+__device__ __forceinline__ double sv_lin_unpack(double d, unsigned& E) {
+    const int hi = __double2hiint(d);
+    E = (unsigned)hi >> 20;
+    return __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(d));
+}
+
 __global__ void k_build_dm_tables(double* __restrict__ dmA, double* __restrict__ dmB, double* __restrict__ linA,
                                   double* __restrict__ linB, int C, SvDmAlphas al) {
     // one thread per (count, column): six short logGamma chains per count instead of one long one
@@ -106,14 +121,12 @@ __global__ void k_build_dm_tables(double* __restrict__ dmA, double* __restrict__
     if (col < 4) {
         dmA[4 * c + col] = v;
         sv_split_exp(-v, &m, &e);
-        linA[SV_LINA_STRIDE * c + col] = m;
-        reinterpret_cast<unsigned short*>(linA + SV_LINA_STRIDE * c + 4)[col] = (unsigned short)(e + SV_LIN_BIAS);
+        linA[(size_t)(col >> 1) * 2 * C + 2 * c + (col & 1)] = sv_lin_pack(m, e);
     } else {
         dmB[2 * c + (col - 4)] = v;
         // DirichletMultinomial.logDensity returns 1.0 for an empty site (:29-30): row 0 is only ever read when cov == 0
         sv_split_exp(c == 0 ? 1.0 : v, &m, &e);
-        linB[SV_LINB_STRIDE * c + (col - 4)] = m;
-        reinterpret_cast<unsigned short*>(linB + SV_LINB_STRIDE * c + 2)[col - 4] = (unsigned short)(e + SV_LIN_BIAS);
+        linB[2 * c + (col - 4)] = sv_lin_pack(m, e);
     }
 }
 
@@ -561,10 +574,15 @@ __global__ void __launch_bounds__(SV_LEAFL_THREADS, SV_LEAFL_MINB) k_leaf_lin(Sv
     const int e0c = blockIdx.y * SV_LEAF_CELLS;
     const int e1c = min(a.n_cells, e0c + SV_LEAF_CELLS);
     const int tid = threadIdx.x;
-    double* sA = sm;
-    double* sB = sm + SV_LINA_STRIDE * (size_t)C;
-    for (int i = tid; i < SV_LINA_STRIDE * C; i += SV_LEAFL_THREADS) sA[i] = a.linA[i];
-    for (int i = tid; i < SV_LINB_STRIDE * C; i += SV_LEAFL_THREADS) sB[i] = a.linB[i];
+    double2* sA01 = reinterpret_cast<double2*>(sm);  // (col 0, col 1) of count c at [c], (col 2, col 3) at [C + c], numerators at [2 C + c]
+    {
+        const double2* gA = reinterpret_cast<const double2*>(a.linA);
+        const double2* gB = reinterpret_cast<const double2*>(a.linB);
+        for (int i = tid; i < 2 * C; i += SV_LEAFL_THREADS) sA01[i] = gA[i];
+        for (int i = tid; i < C; i += SV_LEAFL_THREADS) sA01[2 * C + i] = gB[i];
+    }
+    const double2* sA23 = sA01 + C;
+    const double2* sB = sA01 + 2 * C;
     __syncthreads();
     const int sbase = blockIdx.x * SV_LEAFL_SITES + tid;
     const bool want0 = a.sum0 != nullptr;
@@ -633,69 +651,63 @@ __global__ void __launch_bounds__(SV_LEAFL_THREADS, SV_LEAFL_MINB) k_leaf_lin(Sv
             }
 #endif
             // numerators: genotypes 0/0 and 1/1 take alpha0 = w1, 1/1' and 0/1 take w2
-            const double2 bm = *reinterpret_cast<const double2*>(sB + SV_LINB_STRIDE * cov);
-            const unsigned be = *reinterpret_cast<const unsigned*>(sB + SV_LINB_STRIDE * cov + 2);
-            double v0 = bm.x, v1 = bm.x, v2 = bm.y, v3 = bm.y;
-            unsigned elo = __byte_perm(be, 0, 0x1010), ehi = __byte_perm(be, 0, 0x3232);  // exponents of (g0, g1), (g2, g3)
+            unsigned E0, E1, E2, E3;  // scratch: biased exponents of the row just read
+            const double2 bp = sB[cov];
+            const double bm0 = sv_lin_unpack(bp.x, E0), bm1 = sv_lin_unpack(bp.y, E1);
+            double v0 = bm0, v1 = bm0, v2 = bm1, v3 = bm1;
+            unsigned elo = E0 * 0x10001u, ehi = E1 * 0x10001u;  // packed exponents of (g0, g1), (g2, g3)
             // denominators (reciprocals); table columns: [0] f*w1, [1] (1-eps)*w1, [2] (1/2-f)*w2, [3] f*w2
             //   alt1: 0/0 f | 1/1 (1-eps) | 1/1' h | 0/1 h     alt2: f | f | h | f     alt3: f | f | f | f     ref: (1-eps) | f | f | h
             // (a zero count contributes the factor 1: only the exponent bias is added)
             if (c[it].x > 0) {
-                const double* r = sA + SV_LINA_STRIDE * c[it].x;
-                const double2 u = *reinterpret_cast<const double2*>(r);
-                const double2 w = *reinterpret_cast<const double2*>(r + 2);
-                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
-                v0 *= u.x; v1 *= u.y; v2 *= w.x; v3 *= w.x;
-                elo += pe.x;
-                ehi += __byte_perm(pe.y, 0, 0x1010);
+                const double2 u = sA01[c[it].x], w = sA23[c[it].x];
+                const double m0 = sv_lin_unpack(u.x, E0), m1 = sv_lin_unpack(u.y, E1), m2 = sv_lin_unpack(w.x, E2);
+                v0 *= m0; v1 *= m1; v2 *= m2; v3 *= m2;
+                elo += E0 | (E1 << 16);
+                ehi += E2 * 0x10001u;
             } else {
                 elo += BIAS2;
                 ehi += BIAS2;
             }
             if (c[it].y > 0) {
-                const double* r = sA + SV_LINA_STRIDE * c[it].y;
-                const double2 u = *reinterpret_cast<const double2*>(r);
-                const double2 w = *reinterpret_cast<const double2*>(r + 2);
-                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
-                v0 *= u.x; v1 *= u.x; v2 *= w.x; v3 *= w.y;
-                elo += __byte_perm(pe.x, 0, 0x1010);
-                ehi += pe.y;
+                const double2 u = sA01[c[it].y], w = sA23[c[it].y];
+                const double m0 = sv_lin_unpack(u.x, E0), m2 = sv_lin_unpack(w.x, E2), m3 = sv_lin_unpack(w.y, E3);
+                v0 *= m0; v1 *= m0; v2 *= m2; v3 *= m3;
+                elo += E0 * 0x10001u;
+                ehi += E2 | (E3 << 16);
             } else {
                 elo += BIAS2;
                 ehi += BIAS2;
             }
             if (c[it].z > 0) {
-                const double* r = sA + SV_LINA_STRIDE * c[it].z;
-                const double2 u = *reinterpret_cast<const double2*>(r);
-                const double2 w = *reinterpret_cast<const double2*>(r + 2);
-                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
-                v0 *= u.x; v1 *= u.x; v2 *= w.y; v3 *= w.y;
-                elo += __byte_perm(pe.x, 0, 0x1010);
-                ehi += __byte_perm(pe.y, 0, 0x3232);
+                const double2 u = sA01[c[it].z], w = sA23[c[it].z];
+                const double m0 = sv_lin_unpack(u.x, E0), m3 = sv_lin_unpack(w.y, E3);
+                v0 *= m0; v1 *= m0; v2 *= m3; v3 *= m3;
+                elo += E0 * 0x10001u;
+                ehi += E3 * 0x10001u;
             } else {
                 elo += BIAS2;
                 ehi += BIAS2;
             }
             if (ref > 0) {
-                const double* r = sA + SV_LINA_STRIDE * ref;
-                const double2 u = *reinterpret_cast<const double2*>(r);
-                const double2 w = *reinterpret_cast<const double2*>(r + 2);
-                const uint2 pe = *reinterpret_cast<const uint2*>(r + 4);
-                v0 *= u.y; v1 *= u.x; v2 *= w.y; v3 *= w.x;
-                elo += __byte_perm(pe.x, 0, 0x1032);  // (e1, e0)
-                ehi += __byte_perm(pe.y, 0, 0x1032);  // (e3, e2)
+                const double2 u = sA01[ref], w = sA23[ref];
+                const double m0 = sv_lin_unpack(u.x, E0), m1 = sv_lin_unpack(u.y, E1);
+                const double m2 = sv_lin_unpack(w.x, E2), m3 = sv_lin_unpack(w.y, E3);
+                v0 *= m1; v1 *= m0; v2 *= m3; v3 *= m2;
+                elo += E1 | (E0 << 16);
+                ehi += E3 | (E2 << 16);
             } else {
                 elo += BIAS2;
                 ehi += BIAS2;
             }
             // common binary scale of the four likelihoods: the largest exponent; a genotype more than 2^-1000 below it is
             // flushed to that floor (the documented limit of the scaled representation)
-            const int E0 = (int)(elo & 0xffffu), E1 = (int)(elo >> 16), E2 = (int)(ehi & 0xffffu), E3 = (int)(ehi >> 16);
-            const int Emax = max(max(E0, E1), max(E2, E3));
-            const double n0 = v0 * __hiloint2double((1023 + max(E0 - Emax, -1000)) << 20, 0);
-            const double n1 = v1 * __hiloint2double((1023 + max(E1 - Emax, -1000)) << 20, 0);
-            const double n2 = v2 * __hiloint2double((1023 + max(E2 - Emax, -1000)) << 20, 0);
-            const double n3 = v3 * __hiloint2double((1023 + max(E3 - Emax, -1000)) << 20, 0);
+            const int S0 = (int)(elo & 0xffffu), S1 = (int)(elo >> 16), S2 = (int)(ehi & 0xffffu), S3 = (int)(ehi >> 16);
+            const int Emax = max(max(S0, S1), max(S2, S3));
+            const double n0 = v0 * __hiloint2double((1023 + max(S0 - Emax, -1000)) << 20, 0);
+            const double n1 = v1 * __hiloint2double((1023 + max(S1 - Emax, -1000)) << 20, 0);
+            const double n2 = v2 * __hiloint2double((1023 + max(S2 - Emax, -1000)) << 20, 0);
+            const double n3 = v3 * __hiloint2double((1023 + max(S3 - Emax, -1000)) << 20, 0);
             // RawReadCountsModelFiniteMuDM.java:133-225, single-dropout arms, as in sv_leaf_site
             const double both = ce[0] + ce[1];
             double x[4];
@@ -721,7 +733,7 @@ __global__ void __launch_bounds__(SV_LEAFL_THREADS, SV_LEAFL_MINB) k_leaf_lin(Sv
                     acc0e[it] += ex;
                 }
                 acc0m[it] = p;
-                acc0e[it] += E0 - 5 * SV_LIN_BIAS;
+                acc0e[it] += S0 - 5 * SV_LIN_BIAS;
             }
         }
     }

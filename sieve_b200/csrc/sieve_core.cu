@@ -389,8 +389,6 @@ static int sv_alloc_tables(sieve_core* h) {
         SV_TRY(sv_alloc(h, &h->d_dmB, (size_t)h->C * 2));
         SV_TRY(sv_alloc(h, &h->d_linA, (size_t)h->C * SV_LINA_STRIDE));
         SV_TRY(sv_alloc(h, &h->d_linB, (size_t)h->C * SV_LINB_STRIDE));
-        SV_CUDA(cudaMemsetAsync(h->d_linA, 0, (size_t)h->C * SV_LINA_STRIDE * sizeof(double), h->stream));  // the rows' padding
-        SV_CUDA(cudaMemsetAsync(h->d_linB, 0, (size_t)h->C * SV_LINB_STRIDE * sizeof(double), h->stream));
         SV_TRY(sv_alloc(h, &h->d_cellT, (size_t)h->n * h->C * 4));
         cudaFree(h->d_lgx1);
         cudaFree(h->d_cellT2);
@@ -684,11 +682,12 @@ extern "C" int sieve_set_leaf_params(sieve_core_t* h, const sieve_leaf_params_t*
 
 // brings the look-up tables of the leaf kernel up to date with h->lp
 // Do the linear-space tables hold every entry?  |LP(c, alpha)| grows monotonically with c, so the last row decides (and the
-// first, for a tiny alpha); a non-positive alpha makes the entries NaN, which the tables carry like the log-space ones do.
+// first, for a tiny alpha); a non-positive alpha makes the entries NaN, which the packed rows cannot carry (the exponent
+// field holds the binary exponent): the log-space kernel runs then and propagates the NaN as the reference does.
 static bool sv_lin_tables_ok(const SvDmAlphas& al, int C) {
     const double alphas[6] = {al.fw1, al.omw1, al.hw2, al.fw2, al.w1, al.w2};
     for (double a : alphas) {
-        if (!(a > 0.0)) continue;
+        if (!(a > 0.0)) return false;
         for (double c : {1.0, (double)std::max(C - 1, 1)}) {
             const double lp = std::log(c) + std::lgamma(a) + std::lgamma(c) - std::lgamma(a + c);
             if (!(std::fabs(lp) <= SV_LIN_MAX_LOG)) return false;
