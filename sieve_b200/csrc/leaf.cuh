@@ -555,9 +555,11 @@ __global__ void __launch_bounds__(SV_LEAF_THREADS, 2) k_leaf(SvLeafArgs a) {
 // group's cells and logged once per (group, site).
 // Preconditions (host, sv_leaf_lin_ok): every count inside the tables, single dropout, constant genotype 0, tables within
 // the exponent range and small enough for shared memory; otherwise k_leaf<...> runs.
-// 512 threads x 2 sites per thread, two blocks per SM (64 registers): 32 resident warps.  Measured against 256 x 4 at two
-// and three blocks per SM, 512 x 1, 1024 x 1 / 2 (profiles/README.md): the kernel is bound by exposed latency (shared-memory
-// and L1 look-ups), so resident warps count, and two blocks of 512 stage the tables half as often as four of 256.
+// 512 threads x 2 sites per thread, two blocks per SM (60 registers): 32 resident warps.  Measured against 256 x 4 at two
+// and three blocks per SM, 512 x 1, 1024 x 1 / 2, and again after the row compactions 256 x 2 x 4, 384 x 2 x 3, 512 x 3
+// (profiles/README.md): the kernel is bound by the L1TEX wavefronts of its look-ups (ncu: 97 % of the LSU data pipe before
+// the rows were compacted), so what counts is bytes and look-ups per row -- the 16-byte coverage row (cellT2) and the
+// exponents packed into the mantissas (sv_lin_unpack).
 #ifndef SV_LEAFL_THREADS
 #define SV_LEAFL_THREADS 512
 #endif
