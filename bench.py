@@ -627,7 +627,26 @@ def main():
         # buffer (32 B) up to ~3e9, beyond that nothing but the counts is resident
         cs = float(NS_CELLS) * share
         mode = "sparse" if cs <= 1.6e9 else ("sparse_single_leaf" if cs <= 3.0e9 else "streamed")
-        NSW = Workload(NS_CELLS, share, SEED + 1000 + 17 * rank, dev, local, world, mode=mode, want_matrices=False, n_sample=256)
+        # the residency that fits is tried first; should a rank run out of memory (a pool that does not get its slots), ALL
+        # ranks step down together -- the main line must not be lost to the north-star block
+        order = ["sparse", "sparse_single_leaf", "streamed"]
+        NSW, ns_fallback = None, []
+        for mode in order[order.index(mode):]:
+            try:
+                NSW = Workload(NS_CELLS, share, SEED + 1000 + 17 * rank, dev, local, world, mode=mode, want_matrices=False,
+                               n_sample=256)
+                ok = 1.0
+            except RuntimeError as exc:      # SIEVE_ERR_OOM from sieve_create, or torch's allocator
+                ok, NSW = 0.0, None
+                ns_fallback.append("%s: %s" % (mode, str(exc)[:160]))
+                torch.cuda.empty_cache()
+            if -rank_max(-ok) > 0.5:
+                break
+            if NSW is not None:
+                NSW.close()
+                NSW = None
+        if NSW is None:
+            raise RuntimeError("north star: no residency fits: %s" % ns_fallback)
         if world > 1:
             bind_native_comm(NSW.core)
         ns_stream = torch.cuda.ExternalStream(NSW.core.stream(), device=dev)
@@ -680,7 +699,7 @@ def main():
             "gpus_for_the_whole_dataset": world if world > 1 else 8,
             "note": ("strong scaling: the data set is split over the %d ranks" % world) if world > 1 else
                     "one GPU holding the 1/8 share that an 8-GPU run gives each rank (no exchange)",
-            "residency": mode, "slots": NSW.core.sparse_info(),
+            "residency": mode, "residency_fallbacks": ns_fallback, "slots": NSW.core.sparse_info(),
             "ms_per_evaluation": ns_ms,
             "dataset_evals_per_s": (1000.0 / ns_ms) if world > 1 else None,
             "share_evals_per_s": 1000.0 / ns_ms,
