@@ -443,6 +443,10 @@ extern "C" int sieve_private_retraverse_changed(sieve_core_t* h, int32_t n_ops, 
         return sv_fail(SIEVE_ERR_STATE, "sieve_private_retraverse_changed: needs a dense resident core");
     if (!h->leaves_ready || !h->tv_leaf_ok)
         return sv_fail(SIEVE_ERR_STATE, "sieve_private_retraverse_changed: the leaves have not been computed yet");
+    if (memcmp(&h->lp, &h->leaf_lp[h->cur_leaf], sizeof(h->lp)) != 0)
+        return sv_fail(SIEVE_ERR_STATE,
+                       "sieve_private_retraverse_changed: leaf parameters were set since the leaves were computed (the listed sites "
+                       "would be evaluated under other parameters than the rest): call sieve_update_leaves first");
     for (int i = 0; i < n_ops; i++)
         SV_REQUIRE(ops[3 * i] >= h->n && ops[3 * i] < h->n_nodes, "sieve_private_retraverse_changed: parent must be an internal node");
     SV_CUDA(cudaSetDevice(h->device));

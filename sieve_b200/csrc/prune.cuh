@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(SV_PRUNE_THREADS, sv_prune_min_blocks(MINB ? M
         site_ok[j] = site < a.S;
         srow[j] = (unsigned)(site_ok[j] ? site : a.S - 1);
         if constexpr (LEAFK)
-            if (a.site_list) srow[j] = (unsigned)__ldg(a.site_list + srow[j]);
+            if (a.site_list) {
+                srow[j] = (unsigned)__ldg(a.site_list + srow[j]);
+                SV_BOUND(srow[j] < a.part_rows);  // (the row checks below bound it properly)
+            }
     }
     double* wm = sm + warp * (2 * SV_KMAX * SV_MAT_STRIDE);
     // staging role of this lane: matrix `which` (child 1 / 2), category kk, row q  ->  4 doubles = one 256-bit load

@@ -264,6 +264,12 @@ def test_retraverse_of_changed_patterns_equals_a_whole_shard_pass(core_mod, orac
     got_l, got_c = A.pattern_log_likelihoods()
     _close(got_l, sl, 1e-12)
     _close(got_c, lc, 1e-12)
+    # misuse: leaf parameters set without a leaf update -- the listed sites would be evaluated under other parameters
+    pr = list(A.params.as_tuple())
+    pr[3] *= 1.01
+    A.core.set_leaf_params(*pr)
+    with pytest.raises(RuntimeError):
+        A.core.private_retraverse_changed(A.tree.ops())
     A.close()
     B.close()
 
