@@ -213,14 +213,22 @@ def measured_peak():
 
 
 def library_build_id():
-    """sha256 of the built library (first 16 hex digits): stamps ncu-derived figures to the code they were taken from"""
+    """sha256 (first 16 hex digits) of everything the library is built from -- sieve_b200/csrc/* and include/*.h, in name
+    order -- so that a rebuild of the same sources on another box keeps the stamp: ncu-derived figures are tied to the code
+    they were taken from.  A kernel-variant library (SIEVE_B200_LIB, experiments) adds the hash of its binary."""
+    import glob
     import hashlib
-
-    from sieve_b200 import _lib
     h = hashlib.sha256()
-    with open(_lib.SO_PATH, "rb") as f:
-        for blk in iter(lambda: f.read(1 << 20), b""):
-            h.update(blk)
+    files = sorted(glob.glob(os.path.join(ROOT, "sieve_b200", "csrc", "*")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
+    for fn in files:
+        if not os.path.isfile(fn):
+            continue
+        h.update(os.path.basename(fn).encode())
+        with open(fn, "rb") as f:
+            h.update(f.read())
+    if os.environ.get("SIEVE_B200_LIB"):
+        with open(os.environ["SIEVE_B200_LIB"], "rb") as f:
+            h.update(hashlib.sha256(f.read()).digest())
     return h.hexdigest()[:16]
 
 
