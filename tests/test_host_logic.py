@@ -175,3 +175,21 @@ def test_private_cov_tied_pair_update_matches_the_oracle():
             got = private_cov.update_pair(cov, sf, combos, single, 7.5)
             assert abs(got[0] - want[0]) <= 1e-13 * abs(want[0]) + 1e-300
             assert abs(got[1] - want[1]) <= 1e-13 * abs(want[1]) + 1e-300
+
+
+def test_ncu_traffic_file_belongs_to_the_sources_in_the_tree():
+    """profiles/ncu_traffic.json (the per-launch DRAM bytes bench.py quotes as roofline.traffic) is stamped with the hash of
+    the library's sources at capture time; bench.py refuses the figure when the stamp differs.  The committed file must be
+    the capture of the committed sources (profiles/make_ncu_traffic.py regenerates it after any change under sieve_b200/csrc
+    or include/)."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    tr = json.load(open(os.path.join(root, "profiles", "ncu_traffic.json")))
+    assert tr["library_build_id"] == bench.library_build_id()
+    k = tr["kernels"]["k_prune"]
+    assert k["kernel"].startswith("k_walk") and 1.5 < k["duration_ms_under_ncu"] < 3.0
+    assert 8e9 < k["dram_bytes_read"] + k["dram_bytes_write"] < 11e9
